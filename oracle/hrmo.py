@@ -1,0 +1,265 @@
+"""ctypes loader for the CPU oracle (oracle/libhrm_oracle.so).
+
+ORACLE — TEST INFRASTRUCTURE ONLY.  Importable from tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py; never from hrm_b200/.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libhrm_oracle.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".hpp", ".cpp"))]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.hrmo_exponential_function.restype = C.c_double
+        _LIB.hrmo_exponential_function.argtypes = [C.c_double, C.c_double, C.c_int]
+        _LIB.hrmo_angular_distance.restype = C.c_double
+        _LIB.hrmo_time_layers3d.restype = C.c_double
+    return _LIB
+
+
+def _d(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def constants():
+    out = np.zeros(3)
+    lib().hrmo_constants(_p(out))
+    return {"PI": out[0], "HALF_PI": out[1], "EPSILON": out[2]}
+
+
+def quat_to_rot(q):
+    q = _d(q)
+    R = np.zeros(9)
+    lib().hrmo_quat_to_rot(_p(q), _p(R))
+    return R.reshape(3, 3)
+
+
+def rot_to_quat(R):
+    R = _d(R).reshape(9)
+    q = np.zeros(4)
+    lib().hrmo_rot_to_quat(_p(R), _p(q))
+    return q
+
+
+def angle_axis_to_quat(angle, axis):
+    axis = _d(axis)
+    q = np.zeros(4)
+    lib().hrmo_angle_axis_to_quat(C.c_double(angle), _p(axis), _p(q))
+    return q
+
+
+def slerp(a, t, b):
+    a, b = _d(a), _d(b)
+    out = np.zeros(4)
+    lib().hrmo_slerp(_p(a), C.c_double(t), _p(b), _p(out))
+    return out
+
+
+def angular_distance(a, b):
+    a, b = _d(a), _d(b)
+    return lib().hrmo_angular_distance(_p(a), _p(b))
+
+
+def linspaced(n, lo, hi):
+    out = np.zeros(n)
+    lib().hrmo_linspaced(C.c_int(n), C.c_double(lo), C.c_double(hi), _p(out))
+    return out
+
+
+def exponential_function(theta, power, is_sine):
+    return lib().hrmo_exponential_function(theta, power, int(bool(is_sine)))
+
+
+def sq_tables(sq, n):
+    sq = _d(sq)
+    out = np.zeros(8 * n)
+    lib().hrmo_sq_tables(_p(sq), C.c_int(n), _p(out))
+    return out.reshape(8, n)
+
+
+def origin_shape3d(sq, n):
+    sq = _d(sq)
+    out = np.zeros(3 * n * n)
+    lib().hrmo_origin_shape3d(_p(sq), C.c_int(n), _p(out))
+    return out.reshape(n * n, 3).T.copy()  # 3 x M like Eigen
+
+
+def minksum3d(sq, semiB, quatB, n, K):
+    sq, semiB, quatB = _d(sq), _d(semiB), _d(quatB)
+    out = np.zeros(3 * n * n)
+    lib().hrmo_minksum3d(_p(sq), _p(semiB), _p(quatB), C.c_int(n), C.c_int(K), _p(out))
+    return out.reshape(n * n, 3).T.copy()
+
+
+def origin_shape2d(se, num):
+    se = _d(se)
+    out = np.zeros(2 * num)
+    lib().hrmo_origin_shape2d(_p(se), C.c_int(num), _p(out))
+    return out.reshape(num, 2).T.copy()
+
+
+def minksum2d(se, semiB, angleB, num, K):
+    se, semiB = _d(se), _d(semiB)
+    out = np.zeros(2 * num)
+    lib().hrmo_minksum2d(_p(se), _p(semiB), C.c_double(angleB), C.c_int(num), C.c_int(K), _p(out))
+    return out.reshape(num, 2).T.copy()
+
+
+def mvce2d(a, b, thA, thB):
+    a, b = _d(a), _d(b)
+    out = np.zeros(3)
+    lib().hrmo_mvce2d(_p(a), _p(b), C.c_double(thA), C.c_double(thB), _p(out))
+    return out
+
+
+def mvce3d(a, b, qa, qb):
+    a, b, qa, qb = _d(a), _d(b), _d(qa), _d(qb)
+    out = np.zeros(7)
+    lib().hrmo_mvce3d(_p(a), _p(b), _p(qa), _p(qb), _p(out))
+    return out
+
+
+def tfe2d(a, thA, thB, num_step):
+    a = _d(a)
+    out = np.zeros(3)
+    lib().hrmo_tfe2d(_p(a), C.c_double(thA), C.c_double(thB), C.c_int(num_step), _p(out))
+    return out
+
+
+def tfe3d(a, qa, qb, num_step):
+    a, qa, qb = _d(a), _d(qa), _d(qb)
+    out = np.zeros(7)
+    lib().hrmo_tfe3d(_p(a), _p(qa), _p(qb), C.c_int(num_step), _p(out))
+    return out
+
+
+def vertical_line_mesh(bound3xM, n, x, y, z0=0.0):
+    b = _d(np.asarray(bound3xM).T)  # -> M x 3 == col-major 3 x M
+    z = np.zeros(2)
+    c = lib().hrmo_vertical_line_mesh(_p(b), C.c_int(n), C.c_double(x), C.c_double(y), C.c_double(z0), _p(z))
+    return c, z[:c].copy()
+
+
+def line_mesh(bound3xM, n, line6):
+    b = _d(np.asarray(bound3xM).T)
+    line6 = _d(line6)
+    h = np.zeros(6)
+    c = lib().hrmo_line_mesh(_p(b), C.c_int(n), _p(line6), _p(h))
+    return c, h.reshape(2, 3)[:c].copy()
+
+
+def horizontal_line_polygon(bound2xN, ty, cap=64):
+    b = _d(np.asarray(bound2xN).T)
+    out = np.zeros(cap)
+    c = lib().hrmo_horizontal_line_polygon(_p(b), C.c_int(b.shape[0]), C.c_double(ty), _p(out), C.c_int(cap))
+    return c, out[: min(c, cap)].copy()
+
+
+def seg_polygon(bound2xN, s1, s2):
+    b = _d(np.asarray(bound2xN).T)
+    s1, s2 = _d(s1), _d(s2)
+    return bool(lib().hrmo_seg_polygon(_p(b), C.c_int(b.shape[0]), _p(s1), _p(s2)))
+
+
+def free_segments(alo, aup, olo, oup, cap=1 << 16):
+    """Interval tables [Ly][Sa] / [Ly][So] -> (off[Ly+1], xL, xU, xM) incl. enhanceFreeSegment."""
+    alo, aup, olo, oup = _d(alo), _d(aup), _d(olo), _d(oup)
+    Ly, Sa = alo.shape
+    So = olo.shape[1]
+    off = np.zeros(Ly + 1, dtype=np.int32)
+    xL, xU, xM = np.zeros(cap), np.zeros(cap), np.zeros(cap)
+    tot = lib().hrmo_free_segments(C.c_int(Ly), C.c_int(Sa), C.c_int(So), _p(alo), _p(aup), _p(olo), _p(oup), _p(off),
+                                   _p(xL), _p(xU), _p(xM), C.c_int(cap))
+    assert tot <= cap
+    return off, xL[:tot].copy(), xU[:tot].copy(), xM[:tot].copy()
+
+
+def robot3d_body_poses(robot_rows, q):
+    robot_rows = _d(robot_rows)
+    B = robot_rows.shape[0]
+    q = _d(q)
+    bq, bo = np.zeros((B, 4)), np.zeros((B, 3))
+    lib().hrmo_robot3d_body_poses(C.c_int(B), _p(robot_rows), _p(q), _p(bq), _p(bo))
+    return bq, bo
+
+
+def robot2d_body_poses(robot_rows, theta):
+    robot_rows = _d(robot_rows)
+    B = robot_rows.shape[0]
+    ba, bo = np.zeros(B), np.zeros((B, 2))
+    lib().hrmo_robot2d_body_poses(C.c_int(B), _p(robot_rows), C.c_double(theta), _p(ba), _p(bo))
+    return ba, bo
+
+
+def layer3d(n_arena, n_obs, sq, n, body_semi, body_quat, body_off, lim, Lx, Ly, want_bound=True, seg_cap=1 << 18):
+    """One 3D C-layer. Returns dict(bound[S,3,M], lo[L,S], up[L,S], off[L+1], xL, xU, xM, single_hits)."""
+    sq, body_semi, body_quat, body_off, lim = _d(sq), _d(body_semi), _d(body_quat), _d(body_off), _d(lim)
+    B = body_semi.shape[0]
+    S = (n_arena + n_obs) * B
+    M = n * n
+    L = Lx * Ly
+    bound = np.zeros((S, M, 3)) if want_bound else None
+    lo, up = np.zeros((L, S)), np.zeros((L, S))
+    off = np.zeros(L + 1, dtype=np.int32)
+    xL, xU, xM = np.zeros(seg_cap), np.zeros(seg_cap), np.zeros(seg_cap)
+    sh = C.c_long(0)
+    tot = lib().hrmo_layer3d(C.c_int(n_arena), C.c_int(n_obs), _p(sq), C.c_int(n), C.c_int(B), _p(body_semi), _p(body_quat),
+                             _p(body_off), _p(lim), C.c_int(Lx), C.c_int(Ly), _p(bound), _p(lo), _p(up), _p(off), _p(xL), _p(xU),
+                             _p(xM), C.c_int(seg_cap), C.byref(sh))
+    assert 0 <= tot <= seg_cap, tot
+    return {
+        "bound": None if bound is None else np.ascontiguousarray(bound.transpose(0, 2, 1)),
+        "lo": lo, "up": up, "off": off, "xL": xL[:tot].copy(), "xU": xU[:tot].copy(), "xM": xM[:tot].copy(),
+        "single_hits": sh.value,
+    }
+
+
+def layer2d(n_arena, n_obs, se, num, body_semi, body_angle, body_off, lim, Ly, seg_cap=1 << 16):
+    se, body_semi, body_angle, body_off, lim = _d(se), _d(body_semi), _d(body_angle), _d(body_off), _d(lim)
+    B = body_semi.shape[0]
+    S = (n_arena + n_obs) * B
+    bound = np.zeros((S, num, 2))
+    lo, up = np.zeros((Ly, S)), np.zeros((Ly, S))
+    off = np.zeros(Ly + 1, dtype=np.int32)
+    xL, xU, xM = np.zeros(seg_cap), np.zeros(seg_cap), np.zeros(seg_cap)
+    sh = C.c_long(0)
+    tot = lib().hrmo_layer2d(C.c_int(n_arena), C.c_int(n_obs), _p(se), C.c_int(num), C.c_int(B), _p(body_semi), _p(body_angle),
+                             _p(body_off), _p(lim), C.c_int(Ly), _p(bound), _p(lo), _p(up), _p(off), _p(xL), _p(xU), _p(xM),
+                             C.c_int(seg_cap), C.byref(sh))
+    assert 0 <= tot <= seg_cap, tot
+    return {
+        "bound": np.ascontiguousarray(bound.transpose(0, 2, 1)), "lo": lo, "up": up, "off": off,
+        "xL": xL[:tot].copy(), "xU": xU[:tot].copy(), "xM": xM[:tot].copy(), "single_hits": sh.value,
+    }
+
+
+def time_layers3d(n_arena, n_obs, sq, n, body_semi, body_quat, body_off, lim, Lx, Ly, threads=1):
+    """CPU baseline: seconds to build K layers (body_quat [K,B,4], body_off [K,B,3])."""
+    sq, body_semi, body_quat, body_off, lim = _d(sq), _d(body_semi), _d(body_quat), _d(body_off), _d(lim)
+    K, B = body_quat.shape[0], body_quat.shape[1]
+    cs = C.c_long(0)
+    sec = lib().hrmo_time_layers3d(C.c_int(n_arena), C.c_int(n_obs), _p(sq), C.c_int(n), C.c_int(B), _p(body_semi), _p(body_quat),
+                                   _p(body_off), _p(lim), C.c_int(Lx), C.c_int(Ly), C.c_int(K), C.c_int(threads), C.byref(cs))
+    return sec, cs.value
