@@ -1,0 +1,233 @@
+"""ctypes binding of libhrmgpu.so (include/hrmgpu.h).  Loading fails loudly if the CUDA library has not
+been built; there is no CPU fallback anywhere in this package."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libhrmgpu.so")
+
+OK, E_ARG, E_CUDA, E_STATE, E_CAP, E_NOMEM, E_NODEVICE = 0, -1, -2, -3, -4, -5, -6
+F64_STRICT, F64, F32 = 0, 1, 2
+
+_STATUS = {E_ARG: "E_ARG", E_CUDA: "E_CUDA", E_STATE: "E_STATE", E_CAP: "E_CAP", E_NOMEM: "E_NOMEM", E_NODEVICE: "E_NODEVICE"}
+
+_lib = None
+
+
+class HrmGpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("hrmgpu %s (%d): %s" % (_STATUS.get(code, "?"), code, msg))
+        self.code = code
+
+
+def load():
+    """Loads libhrmgpu.so; raises if it is missing (build with `python -m hrm_b200.build`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libhrmgpu.so not built: run `python -m hrm_b200.build` (there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i, ll = C.c_void_p, C.c_int, C.c_longlong
+    sig = {
+        "hrmgpu_abi_version": (i, []),
+        "hrmgpu_device_count": (i, []),
+        "hrmgpu_create": (i, [C.POINTER(vp), i, C.c_uint]),
+        "hrmgpu_destroy": (None, [vp]),
+        "hrmgpu_last_error": (C.c_char_p, [vp]),
+        "hrmgpu_set_stream": (i, [vp, vp]),
+        "hrmgpu_synchronize": (i, [vp]),
+        "hrmgpu_set_scene3d": (i, [vp, i, i, vp, i]),
+        "hrmgpu_set_scene2d": (i, [vp, i, i, vp, i]),
+        "hrmgpu_set_sweep": (i, [vp, vp, i, i]),
+        "hrmgpu_build_layers": (i, [vp, i, i, vp, vp, vp, i]),
+        "hrmgpu_build_layers_dev": (i, [vp, i, i, vp, vp, vp, i]),
+        "hrmgpu_build_layers2d": (i, [vp, i, i, vp, vp, vp, i]),
+        "hrmgpu_get_dims": (i, [vp, vp]),
+        "hrmgpu_get_boundary": (i, [vp, i, i, vp]),
+        "hrmgpu_get_intervals": (i, [vp, i, vp, vp]),
+        "hrmgpu_get_segments": (i, [vp, i, vp, vp, vp, vp, i]),
+        "hrmgpu_get_segments_all": (i, [vp, vp, vp, vp, vp, ll]),
+        "hrmgpu_get_single_hit_count": (i, [vp, vp]),
+        "hrmgpu_test_edges": (i, [vp, i, i, vp, vp, vp]),
+        "hrmgpu_build_bridge": (i, [vp, i, i, vp, vp, i]),
+        "hrmgpu_build_bridge2d": (i, [vp, i, i, vp, vp, i]),
+        "hrmgpu_test_bridge": (i, [vp, i, i, vp, vp]),
+        "hrmgpu_pack_segments_dev": (ll, [vp, vp, ll]),
+        "hrmgpu_kernel_launches": (ll, [vp, i]),
+        "hrmgpu_last_minksweep_ms": (C.c_double, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def declared_symbols():
+    """Names of every function include/hrmgpu.h declares (parsed from the header)."""
+    import re
+
+    hdr = os.path.join(_HERE, "..", "include", "hrmgpu.h")
+    txt = open(hdr).read()
+    return sorted(set(re.findall(r"\b(hrmgpu_[a-z0-9_]+)\s*\(", txt)))
+
+
+def _d(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One hrmgpu context (one GPU).  Thin, argument-checked wrapper; arrays are numpy float64."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.hrmgpu_create(C.byref(h), device, 0)
+        if rc != OK:
+            raise HrmGpuError(rc, "hrmgpu_create failed (no CUDA device? there is no CPU fallback)")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.hrmgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc < 0:
+            raise HrmGpuError(rc, self.lib.hrmgpu_last_error(self.h).decode())
+        return rc
+
+    # ---- setup ----
+    def set_stream(self, cuda_stream_ptr):
+        self._chk(self.lib.hrmgpu_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def synchronize(self):
+        self._chk(self.lib.hrmgpu_synchronize(self.h))
+
+    def set_scene3d(self, n_arena, n_obs, sq17, n_grid):
+        sq17 = _d(sq17).reshape(-1, 17)
+        assert sq17.shape[0] == n_arena + n_obs
+        self.n_grid = n_grid
+        self._chk(self.lib.hrmgpu_set_scene3d(self.h, n_arena, n_obs, _p(sq17), n_grid))
+
+    def set_scene2d(self, n_arena, n_obs, se6, num):
+        se6 = _d(se6).reshape(-1, 6)
+        assert se6.shape[0] == n_arena + n_obs
+        self._chk(self.lib.hrmgpu_set_scene2d(self.h, n_arena, n_obs, _p(se6), num))
+
+    def set_sweep(self, lim, Lx, Ly):
+        lim = _d(lim)
+        self._chk(self.lib.hrmgpu_set_sweep(self.h, _p(lim), Lx, Ly))
+
+    # ---- builds ----
+    def build_layers(self, body_semi, body_R, body_off, precision=F64_STRICT):
+        body_semi = _d(body_semi).reshape(-1, 3)
+        B = body_semi.shape[0]
+        body_R = _d(body_R).reshape(-1, B, 9)
+        K = body_R.shape[0]
+        body_off = _d(body_off).reshape(K, B, 3)
+        self._chk(self.lib.hrmgpu_build_layers(self.h, K, B, _p(body_semi), _p(body_R), _p(body_off), precision))
+
+    def build_layers_dev(self, K, B, d_semi, d_R, d_off, precision=F64_STRICT):
+        self._chk(self.lib.hrmgpu_build_layers_dev(self.h, K, B, C.c_void_p(d_semi), C.c_void_p(d_R), C.c_void_p(d_off), precision))
+
+    def build_layers2d(self, body_semi, body_angle, body_off, precision=F64_STRICT):
+        body_semi = _d(body_semi).reshape(-1, 2)
+        B = body_semi.shape[0]
+        body_angle = _d(body_angle).reshape(-1, B)
+        K = body_angle.shape[0]
+        body_off = _d(body_off).reshape(K, B, 2)
+        self._chk(self.lib.hrmgpu_build_layers2d(self.h, K, B, _p(body_semi), _p(body_angle), _p(body_off), precision))
+
+    # ---- results ----
+    def dims(self):
+        out = np.zeros(8, dtype=np.int64)
+        self._chk(self.lib.hrmgpu_get_dims(self.h, _p(out)))
+        return dict(zip(["K", "B", "S", "Sa", "L", "M", "segments", "dim"], (int(v) for v in out)))
+
+    def boundary(self, k, surface):
+        d = self.dims()
+        out = np.zeros((d["M"], d["dim"]))
+        self._chk(self.lib.hrmgpu_get_boundary(self.h, k, surface, _p(out)))
+        return out.T.copy()  # dim x M like the reference's BoundaryPoints
+
+    def intervals(self, k):
+        d = self.dims()
+        lo = np.zeros((d["L"], d["S"]))
+        up = np.zeros((d["L"], d["S"]))
+        self._chk(self.lib.hrmgpu_get_intervals(self.h, k, _p(lo), _p(up)))
+        return lo, up
+
+    def segments(self, k):
+        d = self.dims()
+        off = np.zeros(d["L"] + 1, dtype=np.int32)
+        cnt = self._chk(self.lib.hrmgpu_get_segments(self.h, k, _p(off), None, None, None, 0))
+        xL, xU, xM = np.zeros(cnt), np.zeros(cnt), np.zeros(cnt)
+        if cnt:
+            self._chk(self.lib.hrmgpu_get_segments(self.h, k, _p(off), _p(xL), _p(xU), _p(xM), cnt))
+        return off, xL, xU, xM
+
+    def segments_all(self):
+        d = self.dims()
+        off = np.zeros(d["K"] * d["L"] + 1, dtype=np.int64)
+        tot = d["segments"]
+        xL, xU, xM = np.zeros(tot), np.zeros(tot), np.zeros(tot)
+        self._chk(self.lib.hrmgpu_get_segments_all(self.h, _p(off), _p(xL), _p(xU), _p(xM), tot))
+        return off, xL, xU, xM
+
+    def single_hit_count(self):
+        out = np.zeros(1, dtype=np.int64)
+        self._chk(self.lib.hrmgpu_get_single_hit_count(self.h, _p(out)))
+        return int(out[0])
+
+    def test_edges(self, k, v1, v2):
+        d = self.dims()
+        v1 = _d(v1).reshape(-1, d["dim"])
+        v2 = _d(v2).reshape(-1, d["dim"])
+        out = np.zeros(v1.shape[0], dtype=np.uint8)
+        if v1.shape[0]:
+            self._chk(self.lib.hrmgpu_test_edges(self.h, k, v1.shape[0], _p(v1), _p(v2), _p(out)))
+        return out.astype(bool)
+
+    def build_bridge(self, tfe_semi, tfe_R, precision=F64_STRICT):
+        tfe_semi = _d(tfe_semi)
+        P, B = tfe_semi.shape[0], tfe_semi.shape[1]
+        tfe_R = _d(tfe_R).reshape(P, B, 9)
+        self._chk(self.lib.hrmgpu_build_bridge(self.h, P, B, _p(tfe_semi), _p(tfe_R), precision))
+
+    def build_bridge2d(self, tfe_semi, tfe_angle, precision=F64_STRICT):
+        tfe_semi = _d(tfe_semi)
+        P, B = tfe_semi.shape[0], tfe_semi.shape[1]
+        tfe_angle = _d(tfe_angle).reshape(P, B)
+        self._chk(self.lib.hrmgpu_build_bridge2d(self.h, P, B, _p(tfe_semi), _p(tfe_angle), precision))
+
+    def test_bridge(self, p, centres):
+        centres = _d(centres)
+        Q = centres.shape[0]
+        out = np.zeros(Q, dtype=np.uint8)
+        if Q:
+            self._chk(self.lib.hrmgpu_test_bridge(self.h, p, Q, _p(centres), _p(out)))
+        return out.astype(bool)
+
+    def pack_segments_dev(self, d_ptr=None, cap_bytes=0):
+        return self._chk(self.lib.hrmgpu_pack_segments_dev(self.h, C.c_void_p(d_ptr) if d_ptr else None, cap_bytes))
+
+    def kernel_launches(self, reset=False):
+        return int(self.lib.hrmgpu_kernel_launches(self.h, int(reset)))
+
+    def last_minksweep_ms(self):
+        return float(self.lib.hrmgpu_last_minksweep_ms(self.h))

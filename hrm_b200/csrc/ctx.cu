@@ -1,0 +1,413 @@
+// C ABI of libhrmgpu.so (see include/hrmgpu.h): context, scene/sweep setup, build calls, getters.
+// There is deliberately no CPU fallback: without a CUDA device hrmgpu_create() fails with
+// HRMGPU_E_NODEVICE and nothing else can be called.
+#include "internal.cuh"
+
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <new>
+
+using namespace hrmgpu;
+
+struct hrmgpu_ctx : public Ctx {};
+
+namespace {
+
+// sgn(f(theta)) * |f(theta)|^p, sgn(0) = 0 — the superquadric power function
+// (reference src/util/ExponentialFunction.cpp:5-10), evaluated on the host in FP64 with libm because it
+// is needed only 8*n times per object per scene (separable in eta and omega).
+double power_fn(double theta, double p, bool sine) {
+    const double v = sine ? std::sin(theta) : std::cos(theta);
+    const double sg = (v < 0) ? -1.0 : ((v > 0) ? 1.0 : 0.0);
+    return sg * std::pow(std::fabs(v), p);
+}
+
+// Parameter grid of SuperQuadrics::SuperQuadrics (reference src/geometry/SuperQuadrics.cpp:18-24):
+// Eigen LinSpaced(n, lo, hi) = lo + i*step, last element exactly hi.
+void lin_grid(int n, double lo, double hi, std::vector<double>& v) {
+    v.resize(static_cast<size_t>(n));
+    const double step = (hi - lo) / static_cast<double>(n - 1);
+    const bool flip = std::fabs(hi) < std::fabs(lo);
+    for (int i = 0; i < n; ++i) {
+        if (flip)
+            v[i] = (i == 0) ? lo : (hi - static_cast<double>(n - 1 - i) * step);
+        else
+            v[i] = (i == n - 1) ? hi : (lo + static_cast<double>(i) * step);
+    }
+}
+
+// reference include/hrm/datastructure/DataType.h:30-32 (truncated on purpose)
+const double kPI = 3.1415926;
+const double kHALF_PI = kPI / 2.0;
+const double kEPS = 1e-6;
+
+template <class T>
+int upload(Ctx* c, DevBuf<T>& buf, const T* h, size_t n) {
+    int rc = ensure(c, buf, n);
+    if (rc) return rc;
+    if (n) HRMGPU_CUDA(c, cudaMemcpyAsync(buf.p, h, n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    return HRMGPU_OK;
+}
+
+template <class T>
+void release(DevBuf<T>& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.n = 0;
+}
+
+int check_built(Ctx* c, int k) {
+    if (!c->built) return fail(c, HRMGPU_E_STATE, "no layers built yet");
+    if (k < 0 || k >= c->K) return fail(c, HRMGPU_E_ARG, "layer index out of range");
+    return HRMGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hrmgpu_abi_version(void) { return HRMGPU_ABI_VERSION; }
+
+int hrmgpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int hrmgpu_create(hrmgpu_ctx** out, int device, unsigned flags) {
+    (void)flags;
+    if (!out) return HRMGPU_E_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return HRMGPU_E_NODEVICE;
+    }
+    if (device < 0 || device >= n) return HRMGPU_E_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return HRMGPU_E_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return HRMGPU_E_CUDA;
+    if (prop.major < 10) return HRMGPU_E_NODEVICE;  // kernels are built for sm_100a only
+    hrmgpu_ctx* c = new (std::nothrow) hrmgpu_ctx();
+    if (!c) return HRMGPU_E_NOMEM;
+    c->device = device;
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
+        delete c;
+        return HRMGPU_E_CUDA;
+    }
+    c->stream = c->own_stream;
+    if (ensure(c, c->counters, 4) != HRMGPU_OK) {
+        delete c;
+        return HRMGPU_E_NOMEM;
+    }
+    cudaMemsetAsync(c->counters.p, 0, 4 * sizeof(unsigned long long), c->stream);
+    *out = c;
+    return HRMGPU_OK;
+}
+
+void hrmgpu_destroy(hrmgpu_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    release(c->obj3);
+    release(c->obj2);
+    release(c->tab);
+    release(c->txs);
+    release(c->tys);
+    release(c->body_semi);
+    release(c->body_R);
+    release(c->body_off);
+    release(c->mesh);
+    release(c->ivl_lo);
+    release(c->ivl_up);
+    release(c->orig);
+    release(c->orig_cnt);
+    release(c->seg_cnt);
+    release(c->seg_off);
+    release(c->segL);
+    release(c->segU);
+    release(c->segM);
+    release(c->counters);
+    release(c->bridge_mesh);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+const char* hrmgpu_last_error(const hrmgpu_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int hrmgpu_set_stream(hrmgpu_ctx* c, void* s) {
+    if (!c) return HRMGPU_E_ARG;
+    HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->stream = s ? static_cast<cudaStream_t>(s) : c->own_stream;
+    return HRMGPU_OK;
+}
+
+int hrmgpu_synchronize(hrmgpu_ctx* c) {
+    if (!c) return HRMGPU_E_ARG;
+    HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));
+    return HRMGPU_OK;
+}
+
+int hrmgpu_set_scene3d(hrmgpu_ctx* c, int n_arena, int n_obs, const double* sq, int n) {
+    if (!c) return HRMGPU_E_ARG;
+    if (n_arena < 0 || n_obs < 0 || n_arena + n_obs <= 0 || !sq) return fail(c, HRMGPU_E_ARG, "set_scene3d: bad object counts");
+    if (n < 3 || n > kMaxGrid) return fail(c, HRMGPU_E_CAP, "set_scene3d: n_grid must be in [3, 200]");
+    HRMGPU_CUDA(c, cudaSetDevice(c->device));
+    const int S0 = n_arena + n_obs;
+    std::vector<Obj3> objs(static_cast<size_t>(S0));
+    std::vector<double> tab(static_cast<size_t>(S0) * 8 * n);
+    std::vector<double> eta, omega;
+    lin_grid(n, -kHALF_PI - kEPS, kHALF_PI + kEPS, eta);
+    lin_grid(n, -kPI - kEPS, kPI + kEPS, omega);
+    for (int i = 0; i < S0; ++i) {
+        const double* r = sq + static_cast<size_t>(i) * 17;
+        Obj3& o = objs[i];
+        o.a = r[0], o.b = r[1], o.c = r[2];
+        const double e1 = r[3], e2 = r[4];
+        o.px = r[5], o.py = r[6], o.pz = r[7];
+        for (int j = 0; j < 9; ++j) o.R[j] = r[8 + j];
+        o.sign = (i < n_arena) ? -1.0 : 1.0;
+        double* t = tab.data() + static_cast<size_t>(i) * 8 * n;
+        for (int j = 0; j < n; ++j) {
+            t[0 * n + j] = power_fn(eta[j], e1, false);
+            t[1 * n + j] = power_fn(eta[j], e1, true);
+            t[2 * n + j] = power_fn(eta[j], 2 - e1, false);
+            t[3 * n + j] = power_fn(eta[j], 2 - e1, true);
+            t[4 * n + j] = power_fn(omega[j], e2, false);
+            t[5 * n + j] = power_fn(omega[j], e2, true);
+            t[6 * n + j] = power_fn(omega[j], 2 - e2, false);
+            t[7 * n + j] = power_fn(omega[j], 2 - e2, true);
+        }
+    }
+    int rc;
+    if ((rc = upload(c, c->obj3, objs.data(), objs.size()))) return rc;
+    if ((rc = upload(c, c->tab, tab.data(), tab.size()))) return rc;
+    HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));  // host vectors go out of scope
+    c->dim = 3;
+    c->n_arena = n_arena;
+    c->n_obs = n_obs;
+    c->n = n;
+    c->built = false;
+    c->bridge_built = false;
+    return HRMGPU_OK;
+}
+
+int hrmgpu_set_sweep(hrmgpu_ctx* c, const double* lim, int Lx, int Ly) {
+    if (!c) return HRMGPU_E_ARG;
+    if (!lim) return fail(c, HRMGPU_E_ARG, "set_sweep: lim is NULL");
+    if (c->dim == 0) return fail(c, HRMGPU_E_STATE, "set_sweep: set a scene first");
+    HRMGPU_CUDA(c, cudaSetDevice(c->device));
+    if (c->dim == 3) {
+        if (Lx < 2 || Ly < 2) return fail(c, HRMGPU_E_ARG, "set_sweep: 3D needs Lx >= 2 and Ly >= 2");
+    } else {
+        Lx = 1;
+        if (Ly < 1) return fail(c, HRMGPU_E_ARG, "set_sweep: Ly must be >= 1");
+    }
+    if (Lx > kMaxLinesAxis || Ly > kMaxLinesAxis || static_cast<long long>(Lx) * Ly > kMaxLines)
+        return fail(c, HRMGPU_E_CAP, "set_sweep: at most 16383 lines per axis and 8192 lines per layer");
+    const int nl = (c->dim == 3) ? 6 : 4;
+    for (int i = 0; i < nl; ++i) c->lim[i] = lim[i];
+    if (c->dim == 2) c->lim[4] = c->lim[5] = 0.0;
+    c->Lx = Lx;
+    c->Ly = Ly;
+    const double inf = std::numeric_limits<double>::infinity();
+    std::vector<double> tx(static_cast<size_t>(Lx) + 2), ty(static_cast<size_t>(Ly) + 2);
+    // reference src/planners/HRM3D.cpp:66-81 (3D) / HRM2D.cpp:56-61 (2D): t_i = lo + double(i) * d
+    const double dx = (lim[1] - lim[0]) / static_cast<double>(Lx - 1);
+    const double dy = (lim[3] - lim[2]) / (static_cast<double>(Ly) - 1);
+    tx[0] = -inf;
+    tx[Lx + 1] = inf;
+    for (int i = 0; i < Lx; ++i) tx[i + 1] = (c->dim == 3) ? lim[0] + static_cast<double>(i) * dx : 0.0;
+    ty[0] = -inf;
+    ty[Ly + 1] = inf;
+    for (int i = 0; i < Ly; ++i) ty[i + 1] = lim[2] + static_cast<double>(i) * dy;
+    int rc;
+    if ((rc = upload(c, c->txs, tx.data(), tx.size()))) return rc;
+    if ((rc = upload(c, c->tys, ty.data(), ty.size()))) return rc;
+    HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->sweep_set = true;
+    c->built = false;
+    return HRMGPU_OK;
+}
+
+int hrmgpu_build_layers_dev(hrmgpu_ctx* c, int K, int B, const double* d_semi, const double* d_R, const double* d_off,
+                            int precision) {
+    if (!c) return HRMGPU_E_ARG;
+    if (c->dim != 3) return fail(c, HRMGPU_E_STATE, "build_layers: no 3D scene set");
+    if (!c->sweep_set) return fail(c, HRMGPU_E_STATE, "build_layers: set_sweep first");
+    if (K < 0 || B < 1 || !d_semi || (K > 0 && (!d_R || !d_off))) return fail(c, HRMGPU_E_ARG, "build_layers: bad arguments");
+    if (precision < HRMGPU_F64_STRICT || precision > HRMGPU_F32) return fail(c, HRMGPU_E_ARG, "build_layers: unknown precision");
+    HRMGPU_CUDA(c, cudaSetDevice(c->device));
+    const int S0 = c->n_arena + c->n_obs;
+    const int S = S0 * B, Sa = c->n_arena * B, L = c->Lx * c->Ly, M = c->n * c->n;
+    const size_t real = (precision == HRMGPU_F32) ? 4 : 8;
+    int rc;
+    if ((rc = ensure(c, c->mesh, static_cast<size_t>(K) * S * 3 * M * real))) return rc;
+    if ((rc = ensure(c, c->ivl_lo, static_cast<size_t>(K) * S * L))) return rc;
+    if ((rc = ensure(c, c->ivl_up, static_cast<size_t>(K) * S * L))) return rc;
+    HRMGPU_CUDA(c, cudaMemsetAsync(c->counters.p, 0, 4 * sizeof(unsigned long long), c->stream));
+    c->K = K, c->B = B, c->S = S, c->Sa = Sa, c->L = L, c->M = M, c->prec = precision;
+    c->built = false;
+    HRMGPU_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    if ((rc = launch_minksweep3d(c, K, B, 0, S0, d_semi, d_R, d_off, precision, c->mesh.p, c->ivl_lo.p, c->ivl_up.p, true))) return rc;
+    HRMGPU_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    if ((rc = launch_segments(c))) return rc;
+    c->built = true;
+    return HRMGPU_OK;
+}
+
+int hrmgpu_build_layers(hrmgpu_ctx* c, int K, int B, const double* semi, const double* R, const double* off, int precision) {
+    if (!c) return HRMGPU_E_ARG;
+    if (K < 0 || B < 1 || !semi || (K > 0 && (!R || !off))) return fail(c, HRMGPU_E_ARG, "build_layers: bad arguments");
+    HRMGPU_CUDA(c, cudaSetDevice(c->device));
+    int rc;
+    if ((rc = upload(c, c->body_semi, semi, static_cast<size_t>(B) * 3))) return rc;
+    if ((rc = upload(c, c->body_R, R, static_cast<size_t>(K) * B * 9))) return rc;
+    if ((rc = upload(c, c->body_off, off, static_cast<size_t>(K) * B * 3))) return rc;
+    return hrmgpu_build_layers_dev(c, K, B, c->body_semi.p, c->body_R.p, c->body_off.p, precision);
+}
+
+int hrmgpu_get_dims(hrmgpu_ctx* c, long long* out) {
+    if (!c || !out) return HRMGPU_E_ARG;
+    if (!c->built) return fail(c, HRMGPU_E_STATE, "no layers built yet");
+    out[0] = c->K, out[1] = c->B, out[2] = c->S, out[3] = c->Sa, out[4] = c->L, out[5] = c->M, out[6] = c->seg_total, out[7] = c->dim;
+    return HRMGPU_OK;
+}
+
+int hrmgpu_get_boundary(hrmgpu_ctx* c, int k, int surface, double* xyz) {
+    if (!c || !xyz) return HRMGPU_E_ARG;
+    int rc = check_built(c, k);
+    if (rc) return rc;
+    if (surface < 0 || surface >= c->S) return fail(c, HRMGPU_E_ARG, "surface index out of range");
+    HRMGPU_CUDA(c, cudaSetDevice(c->device));
+    const int D = c->dim, M = c->M;
+    const size_t cnt = static_cast<size_t>(D) * M;
+    const size_t base = (static_cast<size_t>(k) * c->S + surface) * cnt;
+    std::vector<double> planar(cnt);
+    if (c->prec == HRMGPU_F32) {
+        std::vector<float> pf(cnt);
+        HRMGPU_CUDA(c, cudaMemcpyAsync(pf.data(), reinterpret_cast<float*>(c->mesh.p) + base, cnt * 4, cudaMemcpyDeviceToHost, c->stream));
+        HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (size_t i = 0; i < cnt; ++i) planar[i] = pf[i];
+    } else {
+        HRMGPU_CUDA(c, cudaMemcpyAsync(planar.data(), reinterpret_cast<double*>(c->mesh.p) + base, cnt * 8, cudaMemcpyDeviceToHost, c->stream));
+        HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    for (int i = 0; i < M; ++i)
+        for (int d = 0; d < D; ++d) xyz[static_cast<size_t>(i) * D + d] = planar[static_cast<size_t>(d) * M + i];
+    return HRMGPU_OK;
+}
+
+int hrmgpu_get_intervals(hrmgpu_ctx* c, int k, double* lo, double* up) {
+    if (!c || !lo || !up) return HRMGPU_E_ARG;
+    int rc = check_built(c, k);
+    if (rc) return rc;
+    HRMGPU_CUDA(c, cudaSetDevice(c->device));
+    const size_t cnt = static_cast<size_t>(c->S) * c->L;
+    std::vector<double> a(cnt), b(cnt);
+    HRMGPU_CUDA(c, cudaMemcpyAsync(a.data(), c->ivl_lo.p + static_cast<size_t>(k) * cnt, cnt * 8, cudaMemcpyDeviceToHost, c->stream));
+    HRMGPU_CUDA(c, cudaMemcpyAsync(b.data(), c->ivl_up.p + static_cast<size_t>(k) * cnt, cnt * 8, cudaMemcpyDeviceToHost, c->stream));
+    HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int s = 0; s < c->S; ++s)
+        for (int l = 0; l < c->L; ++l) {
+            lo[static_cast<size_t>(l) * c->S + s] = a[static_cast<size_t>(s) * c->L + l];
+            up[static_cast<size_t>(l) * c->S + s] = b[static_cast<size_t>(s) * c->L + l];
+        }
+    return HRMGPU_OK;
+}
+
+int hrmgpu_get_segments(hrmgpu_ctx* c, int k, int* off, double* xL, double* xU, double* xM, int cap) {
+    if (!c) return HRMGPU_E_ARG;
+    int rc = check_built(c, k);
+    if (rc) return rc;
+    HRMGPU_CUDA(c, cudaSetDevice(c->device));
+    const size_t l0 = static_cast<size_t>(k) * c->L;
+    const long long b0 = c->h_seg_off[l0], b1 = c->h_seg_off[l0 + c->L];
+    const long long cnt = b1 - b0;
+    if (off)
+        for (int l = 0; l <= c->L; ++l) off[l] = static_cast<int>(c->h_seg_off[l0 + l] - b0);
+    if (xL) {
+        if (!xU || !xM) return fail(c, HRMGPU_E_ARG, "get_segments: xU/xM are NULL");
+        if (cap < cnt) return fail(c, HRMGPU_E_CAP, "get_segments: buffer too small");
+        if (cnt) {
+            HRMGPU_CUDA(c, cudaMemcpyAsync(xL, c->segL.p + b0, cnt * 8, cudaMemcpyDeviceToHost, c->stream));
+            HRMGPU_CUDA(c, cudaMemcpyAsync(xU, c->segU.p + b0, cnt * 8, cudaMemcpyDeviceToHost, c->stream));
+            HRMGPU_CUDA(c, cudaMemcpyAsync(xM, c->segM.p + b0, cnt * 8, cudaMemcpyDeviceToHost, c->stream));
+            HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));
+        }
+    }
+    return static_cast<int>(cnt);
+}
+
+int hrmgpu_get_segments_all(hrmgpu_ctx* c, long long* off, double* xL, double* xU, double* xM, long long cap) {
+    if (!c) return HRMGPU_E_ARG;
+    if (!c->built) return fail(c, HRMGPU_E_STATE, "no layers built yet");
+    HRMGPU_CUDA(c, cudaSetDevice(c->device));
+    const size_t nl = static_cast<size_t>(c->K) * c->L;
+    if (off) std::memcpy(off, c->h_seg_off.data(), sizeof(long long) * (nl + 1));
+    if (xL) {
+        if (!xU || !xM) return fail(c, HRMGPU_E_ARG, "get_segments_all: xU/xM are NULL");
+        if (cap < c->seg_total) return fail(c, HRMGPU_E_CAP, "get_segments_all: buffer too small");
+        if (c->seg_total) {
+            HRMGPU_CUDA(c, cudaMemcpyAsync(xL, c->segL.p, c->seg_total * 8, cudaMemcpyDeviceToHost, c->stream));
+            HRMGPU_CUDA(c, cudaMemcpyAsync(xU, c->segU.p, c->seg_total * 8, cudaMemcpyDeviceToHost, c->stream));
+            HRMGPU_CUDA(c, cudaMemcpyAsync(xM, c->segM.p, c->seg_total * 8, cudaMemcpyDeviceToHost, c->stream));
+        }
+        HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    return HRMGPU_OK;
+}
+
+int hrmgpu_get_single_hit_count(hrmgpu_ctx* c, long long* out) {
+    if (!c || !out) return HRMGPU_E_ARG;
+    HRMGPU_CUDA(c, cudaSetDevice(c->device));
+    unsigned long long v = 0;
+    HRMGPU_CUDA(c, cudaMemcpyAsync(&v, c->counters.p, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
+    HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));
+    *out = static_cast<long long>(v);
+    return HRMGPU_OK;
+}
+
+long long hrmgpu_pack_segments_dev(hrmgpu_ctx* c, void* d_buf, long long cap_bytes) {
+    if (!c) return HRMGPU_E_ARG;
+    if (!c->built) return fail(c, HRMGPU_E_STATE, "no layers built yet");
+    const long long nl = static_cast<long long>(c->K) * c->L;
+    const long long need = (nl + 1) * 8 + 3 * c->seg_total * 8;
+    if (!d_buf) return need;
+    if (cap_bytes < need) return fail(c, HRMGPU_E_CAP, "pack_segments_dev: buffer too small");
+    HRMGPU_CUDA(c, cudaSetDevice(c->device));
+    char* dst = static_cast<char*>(d_buf);
+    HRMGPU_CUDA(c, cudaMemcpyAsync(dst, c->seg_off.p, (nl + 1) * 8, cudaMemcpyDeviceToDevice, c->stream));
+    dst += (nl + 1) * 8;
+    if (c->seg_total) {
+        HRMGPU_CUDA(c, cudaMemcpyAsync(dst, c->segL.p, c->seg_total * 8, cudaMemcpyDeviceToDevice, c->stream));
+        HRMGPU_CUDA(c, cudaMemcpyAsync(dst + c->seg_total * 8, c->segU.p, c->seg_total * 8, cudaMemcpyDeviceToDevice, c->stream));
+        HRMGPU_CUDA(c, cudaMemcpyAsync(dst + 2 * c->seg_total * 8, c->segM.p, c->seg_total * 8, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    return need;
+}
+
+long long hrmgpu_kernel_launches(hrmgpu_ctx* c, int reset) {
+    if (!c) return HRMGPU_E_ARG;
+    const long long v = c->launches;
+    if (reset) c->launches = 0;
+    return v;
+}
+
+double hrmgpu_last_minksweep_ms(hrmgpu_ctx* c) {
+    if (!c || !c->built) return -1.0;
+    if (cudaSetDevice(c->device) != cudaSuccess) return -1.0;
+    if (cudaEventSynchronize(c->ev1) != cudaSuccess) return -1.0;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) != cudaSuccess) return -1.0;
+    return static_cast<double>(ms);
+}
+
+}  // extern "C"

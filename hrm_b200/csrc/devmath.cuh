@@ -1,0 +1,112 @@
+// Device arithmetic policies and the line/triangle test shared by the sweep, edge and bridge kernels.
+//
+// STRICT policy: every FP64 operation is issued through the *_rn intrinsics, which the compiler never
+// contracts into FMAs, and divisions / square roots are the IEEE-rounded ones.  Fed the same inputs in
+// the same order, this reproduces an x86-64 (SSE2, no FMA) evaluation of the reference bit for bit.
+// FAST policy: plain operators (FMA contraction allowed), used by the throughput variants.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace hrmgpu {
+
+struct Strict {
+    __device__ __forceinline__ static double add(double a, double b) { return __dadd_rn(a, b); }
+    __device__ __forceinline__ static double sub(double a, double b) { return __dsub_rn(a, b); }
+    __device__ __forceinline__ static double mul(double a, double b) { return __dmul_rn(a, b); }
+    __device__ __forceinline__ static double div(double a, double b) { return __ddiv_rn(a, b); }
+    __device__ __forceinline__ static double sqrt(double a) { return __dsqrt_rn(a); }
+    // a*b + c as two rounded operations
+    __device__ __forceinline__ static double mad(double a, double b, double c) { return __dadd_rn(__dmul_rn(a, b), c); }
+};
+
+struct Fast {
+    __device__ __forceinline__ static double add(double a, double b) { return a + b; }
+    __device__ __forceinline__ static double sub(double a, double b) { return a - b; }
+    __device__ __forceinline__ static double mul(double a, double b) { return a * b; }
+    __device__ __forceinline__ static double div(double a, double b) { return a / b; }
+    __device__ __forceinline__ static double sqrt(double a) { return ::sqrt(a); }
+    __device__ __forceinline__ static double mad(double a, double b, double c) { return fma(a, b, c); }
+};
+
+struct D3 {
+    double x, y, z;
+};
+
+template <class A>
+__device__ __forceinline__ double dot3(const D3& a, const D3& b) {
+    // (a.x*b.x + a.y*b.y) + a.z*b.z
+    return A::mad(a.z, b.z, A::mad(a.y, b.y, A::mul(a.x, b.x)));
+}
+template <class A>
+__device__ __forceinline__ D3 sub3(const D3& a, const D3& b) {
+    return {A::sub(a.x, b.x), A::sub(a.y, b.y), A::sub(a.z, b.z)};
+}
+
+// Strict::mad(a,b,c) computes mul then add, i.e. (a*b)+c; dot3 above therefore evaluates
+// ((ax*bx) + (ay*by)) + (az*bz) only if the additions are ordered that way:
+//   mad(ay,by, ax*bx) = (ay*by) + (ax*bx)  -- IEEE addition is commutative, so this equals (ax*bx)+(ay*by).
+//   mad(az,bz, t)     = (az*bz) + t        -- likewise equals t + (az*bz).
+
+// intersectLineTriangle3D (reference src/geometry/LineIntersection.cpp:126-171).
+// Line: origin o, direction d.  Triangle: t0, t0+u, t0+v.  Returns hit flag; pt = intersection point.
+template <class A>
+__device__ __forceinline__ bool line_triangle(const D3& o, const D3& d, const D3& t0, const D3& t1, const D3& t2, D3& pt) {
+    const double tol = 1e-12;
+    const D3 u = sub3<A>(t1, t0);
+    const D3 v = sub3<A>(t2, t0);
+    // n = u x v, normalised if non-zero (Eigen normalize())
+    D3 n = {A::sub(A::mul(u.y, v.z), A::mul(u.z, v.y)), A::sub(A::mul(u.z, v.x), A::mul(u.x, v.z)),
+            A::sub(A::mul(u.x, v.y), A::mul(u.y, v.x))};
+    const double z = dot3<A>(n, n);
+    if (z > 0.0) {
+        const double s = A::sqrt(z);
+        n.x = A::div(n.x, s);
+        n.y = A::div(n.y, s);
+        n.z = A::div(n.z, s);
+    }
+    const double a = -dot3<A>(n, sub3<A>(o, t0));
+    const double b = dot3<A>(n, d);
+    const double nn = A::sqrt(dot3<A>(n, n));
+    if (!((fabs(b) > tol) && (nn > tol))) return false;
+    const double pos = A::div(a, b);
+    pt.x = A::add(o.x, A::mul(pos, d.x));
+    pt.y = A::add(o.y, A::mul(pos, d.y));
+    pt.z = A::add(o.z, A::mul(pos, d.z));
+    const double uu = dot3<A>(u, u);
+    const double uv = dot3<A>(u, v);
+    const double vv = dot3<A>(v, v);
+    const D3 w = sub3<A>(pt, t0);
+    const double wu = dot3<A>(u, w);
+    const double wv = dot3<A>(v, w);
+    const double D = A::sub(A::mul(uv, uv), A::mul(uu, vv));
+    const double s = A::div(A::sub(A::mul(uv, wv), A::mul(vv, wu)), D);
+    if ((s < -tol) || (s > 1.0 + tol)) return false;
+    const double t = A::div(A::sub(A::mul(uv, wu), A::mul(uu, wv)), D);
+    return !((t < -tol) || (A::add(s, t) > 1.0 + tol));
+}
+
+// Implicit mesh connectivity of getMeshFromParamSurface (reference src/geometry/MeshGenerator.cpp:105-131):
+// face f < F/2 : (q, q+n, q+n+1);  face f >= F/2 : (q, q+1, q+n+1), q = i*n + j, cell = i*(n-1)+j.
+__device__ __forceinline__ void face_vertices(int f, int n, int& v0, int& v1, int& v2) {
+    const int nc = (n - 1) * (n - 1);
+    const int cell = (f < nc) ? f : f - nc;
+    const int i = cell / (n - 1);
+    const int j = cell - i * (n - 1);
+    const int q = i * n + j;
+    v0 = q;
+    v1 = (f < nc) ? q + n : q + 1;
+    v2 = q + n + 1;
+}
+
+// Ordered two-slot insertion: after all insertions for a line, (m0, m1) hold the two smallest face
+// indices that were inserted — the faces the reference's face-order loop with `break` at two hits
+// would have found (LineIntersection.cpp:46-50,116-120).  Deterministic for any arrival order.
+__device__ __forceinline__ void insert_two_smallest(uint32_t* m0, uint32_t* m1, uint32_t f) {
+    const uint32_t old = atomicMin(m0, f);
+    const uint32_t v = (old > f) ? old : f;
+    if (v != 0xFFFFFFFFu) atomicMin(m1, v);
+}
+
+}  // namespace hrmgpu

@@ -1,0 +1,122 @@
+// Internal declarations shared by the translation units of libhrmgpu.so (sm_100a only).
+#pragma once
+#include "../../include/hrmgpu.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+namespace hrmgpu {
+
+constexpr int kThreads = 256;          // CTA size of the fused Minkowski+sweep kernel
+constexpr int kQueueCap = 1024;        // candidate (face,line) queue entries in shared memory
+constexpr int kMaxGrid = 200;          // n_grid limit (vertex line codes: 4*n^2 bytes of shared memory)
+constexpr int kMaxLinesAxis = 16383;   // per-axis sweep-line limit (15-bit line codes)
+constexpr int kMaxLines = 8192;        // Lx*Ly limit (two-slot hit tables in shared memory)
+constexpr uint32_t kNoFace = 0xFFFFFFFFu;
+
+// Device-side description of one arena/obstacle superquadric (SoA would not help: 17 doubles read
+// once per CTA through the read-only path).
+struct Obj3 {
+    double a, b, c;
+    double px, py, pz;
+    double R[9];
+    double sign;  // -1 arena (Minkowski difference), +1 obstacle (sum): SuperQuadrics.cpp:84-85
+};
+
+struct Obj2 {
+    double a, b, eps;
+    double px, py, angle;
+    double sign;
+};
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;  // capacity in elements
+};
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    long long launches = 0;
+
+    // scene
+    int dim = 0;  // 2 or 3 once a scene is set
+    int n_arena = 0, n_obs = 0, n = 0;
+    DevBuf<Obj3> obj3;
+    DevBuf<Obj2> obj2;
+    DevBuf<double> tab;    // 3D: [S0][8][n] power tables; 2D: [S0][4][num] (x0 factors ce,se; gradient factors)
+    // sweep
+    bool sweep_set = false;
+    double lim[6] = {0, 0, 0, 0, 0, 0};
+    int Lx = 0, Ly = 0;
+    DevBuf<double> txs, tys;  // sentinel-padded line coordinates: [-inf, t_0..t_{L-1}, +inf]
+
+    // last build
+    int K = 0, B = 0, S = 0, Sa = 0, L = 0, M = 0, prec = 0;
+    bool built = false;
+    DevBuf<double> body_semi, body_R, body_off;  // staged copies of host inputs
+    DevBuf<char> mesh;                           // [K][S][dim][M] planar, double (or float in F32 mode)
+    DevBuf<double> ivl_lo, ivl_up;               // [K][S][L]
+    DevBuf<double> orig;                         // [K][L][So+1][2] original (pre-enhancement) segments
+    DevBuf<int> orig_cnt;                        // [K][L]
+    DevBuf<int> seg_cnt;                         // [K][L]
+    DevBuf<long long> seg_off;                   // [K*L+1]
+    DevBuf<double> segL, segU, segM;             // [total]
+    DevBuf<unsigned long long> counters;         // [0] single-hit count, [1] capacity overflow flag
+    long long seg_total = 0;
+    std::vector<long long> h_seg_off;            // host mirror of seg_off (filled on build)
+
+    // bridge layers
+    int P = 0, bridge_B = 0, bridge_prec = 0;
+    bool bridge_built = false;
+    DevBuf<char> bridge_mesh;  // [P][B][n_obs][dim][M]
+};
+
+#define HRMGPU_CUDA(ctx, expr)                                                                        \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess) {                                                                      \
+            (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                          \
+            return (_e == cudaErrorMemoryAllocation) ? HRMGPU_E_NOMEM : HRMGPU_E_CUDA;                \
+        }                                                                                             \
+    } while (0)
+
+template <class T>
+inline int ensure(Ctx* c, DevBuf<T>& b, size_t n) {
+    if (b.n >= n && b.p) return HRMGPU_OK;
+    if (b.p) {
+        cudaFree(b.p);
+        b.p = nullptr;
+        b.n = 0;
+    }
+    if (n == 0) n = 1;
+    HRMGPU_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&b.p), n * sizeof(T)));
+    b.n = n;
+    return HRMGPU_OK;
+}
+
+inline int fail(Ctx* c, int code, const std::string& msg) {
+    c->err = msg;
+    return code;
+}
+
+// kernels / launchers implemented in the other translation units
+int launch_minksweep3d(Ctx* c, int K, int B, int n_first_obj, int n_objs, const double* d_semi, const double* d_R,
+                       const double* d_off, int precision, char* d_mesh, double* d_lo, double* d_up, bool do_sweep);
+int launch_minksweep2d(Ctx* c, int K, int B, int n_first_obj, int n_objs, const double* d_semi, const double* d_angle,
+                       const double* d_off, int precision, char* d_mesh, double* d_lo, double* d_up, bool do_sweep);
+int launch_segments(Ctx* c);
+int launch_edges3d(Ctx* c, int k, int E, const double* d_v1, const double* d_v2, unsigned char* d_out);
+int launch_edges2d(Ctx* c, int k, int E, const double* d_v1, const double* d_v2, unsigned char* d_out);
+int launch_bridge_test3d(Ctx* c, int p, int Q, const double* d_centres, unsigned char* d_out);
+int launch_bridge_test2d(Ctx* c, int p, int Q, const double* d_centres, unsigned char* d_out);
+
+}  // namespace hrmgpu

@@ -1,0 +1,157 @@
+/* hrmgpu.h — C ABI of the B200-native free-space construction for the Highway RoadMap planner.
+ *
+ * This is the drop-in boundary behind the reference's FreeSpaceComputator seam
+ * (ChirikjianLab/hrm include/hrm/datastructure/FreeSpace.h:45-128, FreeSpace3D.h:29-55) and the
+ * planner-side edge / bridge tests (src/planners/HRM3D.cpp:301-425, HRM2D.cpp:199-282).  Plain C:
+ * pointers and sizes only, no C++/torch types.  Every entry point names the reference interface
+ * it replaces.  INTEGRATION.md shows the reference-side C++ binding.
+ *
+ * Conventions
+ *  - All functions return HRMGPU_OK (0) or a negative hrmgpu_status; they never throw or abort.
+ *    hrmgpu_last_error() returns a human-readable message for the last failure on that context.
+ *  - A context is bound to one CUDA device and is NOT thread-safe (like the reference objects).
+ *  - Caller owns host buffers; the context owns all device buffers.  Results of a build call stay
+ *    resident in HBM until the next build call of the same kind or hrmgpu_destroy().
+ *  - Surfaces are ordered j = object * B + body, arena objects first, then obstacles
+ *    (FreeSpace-inl.h:42-60).  Sa = n_arena*B, So = n_obs*B, S = Sa+So.
+ *  - 3D sweep lines are ordered l = ix * Ly + iy (HRM3D.cpp:63-91);  2D: l = iy.
+ *  - Rotations are 3x3 row-major, exactly the matrix Eigen's Quaterniond::toRotationMatrix() gives
+ *    for the (un-normalised) quaternion the reference holds (SuperQuadrics.cpp:78,109-110).
+ *  - Boundary points come back in the reference's BoundaryPoints layout: 3 x M (2 x N) column-major,
+ *    point index k = r + c*n with the omega index r fastest (SuperQuadrics.cpp:63-72).
+ */
+#ifndef HRMGPU_H
+#define HRMGPU_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HRMGPU_ABI_VERSION 1
+
+typedef struct hrmgpu_ctx hrmgpu_ctx;
+
+typedef enum {
+    HRMGPU_OK = 0,
+    HRMGPU_E_ARG = -1,     /* invalid argument */
+    HRMGPU_E_CUDA = -2,    /* CUDA runtime error (message in hrmgpu_last_error) */
+    HRMGPU_E_STATE = -3,   /* call order violated (e.g. build before set_scene) */
+    HRMGPU_E_CAP = -4,     /* a documented capacity limit was exceeded */
+    HRMGPU_E_NOMEM = -5,   /* device or host allocation failed */
+    HRMGPU_E_NODEVICE = -6 /* no usable CUDA device: there is NO CPU fallback */
+} hrmgpu_status;
+
+/* Arithmetic mode of the Minkowski + sweep kernels. */
+typedef enum {
+    HRMGPU_F64_STRICT = 0, /* IEEE op-for-op replica of the reference's FP64 arithmetic (no FMA contraction,
+                              true divisions): bit-identical boundary points, identical hit decisions */
+    HRMGPU_F64 = 1,        /* FP64 with FMA and hoisted column constants: <=1e-12 relative on points */
+    HRMGPU_F32 = 2         /* FP32 throughput variant: <=1e-5 relative (to surface scale) on points */
+} hrmgpu_precision;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int hrmgpu_abi_version(void);
+int hrmgpu_device_count(void);
+/* One context per GPU.  device = CUDA ordinal.  flags: reserved, pass 0. */
+int hrmgpu_create(hrmgpu_ctx** out, int device, unsigned flags);
+void hrmgpu_destroy(hrmgpu_ctx* ctx);
+const char* hrmgpu_last_error(const hrmgpu_ctx* ctx);
+/* Run all subsequent work of this context on an existing CUDA stream (cudaStream_t as void*);
+ * NULL = the context's own stream.  Lets a host framework time / order the work with its own events. */
+int hrmgpu_set_stream(hrmgpu_ctx* ctx, void* cuda_stream);
+int hrmgpu_synchronize(hrmgpu_ctx* ctx);
+
+/* ---- scene --------------------------------------------------------------------------------- */
+/* Replaces: the arena_/obstacle_ vectors a FreeSpace3D is constructed with (FreeSpace3D.cpp:6-10) and
+ * the per-object parameter grids of SuperQuadrics::SuperQuadrics (SuperQuadrics.cpp:8-26).
+ * sq: [n_arena + n_obs][17] = a,b,c, eps1,eps2, px,py,pz, R1[9] row-major.  n_grid = num_ (points per
+ * parameter, M = n_grid^2).  Limits: 3 <= n_grid <= 200. */
+int hrmgpu_set_scene3d(hrmgpu_ctx* ctx, int n_arena, int n_obs, const double* sq, int n_grid);
+/* 2D twin (FreeSpace2D.cpp:6-10, SuperEllipse.cpp:10-18). se: [n_arena+n_obs][6] = a,b,eps,px,py,angle. */
+int hrmgpu_set_scene2d(hrmgpu_ctx* ctx, int n_arena, int n_obs, const double* se, int num);
+/* Replaces: FreeSpaceComputator::setup(numLine, lowBound, upBound) (FreeSpace-inl.h:20-39) plus the
+ * sweep-line grids of HRM3D::sweepLineProcess (HRM3D.cpp:63-91) / HRM2D::sweepLineProcess (HRM2D.cpp:53-70).
+ * lim = boundaryLimits {xlo,xhi,ylo,yhi,zlo,zhi} (2D: first four; Lx ignored, pass 1).
+ * 3D requires Lx >= 2 and Ly >= 2 (with one line the reference's spacing is a division by zero). */
+int hrmgpu_set_sweep(hrmgpu_ctx* ctx, const double* lim, int Lx, int Ly);
+
+/* ---- C-layer construction (K1 + K2 + K3) ---------------------------------------------------- */
+/* Replaces, for K layers in one call: computeCSpaceBoundary() (FreeSpace-inl.h:42-60 ->
+ * MultiBodyTree3D::minkSum, MultiBodyTree3D.cpp:91-105 -> SuperQuadrics::getMinkSum3D,
+ * SuperQuadrics.cpp:84-143), computeCSpaceBoundaryMesh() (FreeSpace3D.cpp:14-27),
+ * computeIntersectionInterval() for every x-plane (FreeSpace3D.cpp:29-68 ->
+ * intersectVerticalLineMesh3D, LineIntersection.cpp:56-171) and computeFreeSegment()
+ * (FreeSpace-inl.h:63-174, Interval.cpp).
+ *   body_semi [B][3]   semi-axes of the ellipsoidal robot bodies (base first)
+ *   body_R    [K][B][9] per-layer world rotation of every body (row-major)
+ *   body_off  [K][B][3] per-layer offset subtracted from the body's boundary (link centre; zeros for
+ *                       the base) (MultiBodyTree3D.cpp:98-101)
+ * Feeding the as-loaded pose for every k reproduces the reference snapshot (SURVEY.md finding 1);
+ * feeding R(q_k)*R_link gives the per-orientation C-layers.  Host pointers; copied H2D inside. */
+int hrmgpu_build_layers(hrmgpu_ctx* ctx, int K, int B, const double* body_semi, const double* body_R,
+                        const double* body_off, int precision);
+/* Same, with the three arrays already resident in device memory (device pointers). */
+int hrmgpu_build_layers_dev(hrmgpu_ctx* ctx, int K, int B, const double* d_body_semi, const double* d_body_R,
+                            const double* d_body_off, int precision);
+/* 2D twin: computeCSpaceBoundary() -> MultiBodyTree2D::minkSum (MultiBodyTree2D.cpp:43-65) ->
+ * SuperEllipse::getMinkSum2D (SuperEllipse.cpp:58-101); FreeSpace2D::computeIntersectionInterval
+ * (FreeSpace2D.cpp:14-50); computeFreeSegment.  body_semi [B][2], body_angle [K][B], body_off [K][B][2]. */
+int hrmgpu_build_layers2d(hrmgpu_ctx* ctx, int K, int B, const double* body_semi, const double* body_angle,
+                          const double* body_off, int precision);
+
+/* ---- results of the last build -------------------------------------------------------------- */
+/* Sizes of the last build: out[0]=K, [1]=B, [2]=S, [3]=Sa, [4]=L, [5]=M (points per surface),
+ * [6]=total segment count over all layers, [7]=dimension (2|3). */
+int hrmgpu_get_dims(hrmgpu_ctx* ctx, long long* out8);
+/* Replaces getCSpaceBoundary() (FreeSpace.h:70): boundary of one surface of layer k, dim x M column-major. */
+int hrmgpu_get_boundary(hrmgpu_ctx* ctx, int k, int surface, double* xyz);
+/* Replaces getIntersectionInterval() (FreeSpace.h:74): lo/up [L][S] of layer k; NaN = no hit. */
+int hrmgpu_get_intervals(hrmgpu_ctx* ctx, int k, double* lo, double* up);
+/* Replaces getFreeSegment() (FreeSpace.h:80) for all lines of layer k: CSR offsets off[L+1] and
+ * xL/xU/xM[cap].  Two-call convention: with xL==NULL only off[] (if non-NULL) is written.
+ * Returns the layer's segment count (>= 0) or a negative status. */
+int hrmgpu_get_segments(hrmgpu_ctx* ctx, int k, int* off, double* xL, double* xU, double* xM, int cap);
+/* All layers at once: off [K*L+1] (global CSR, 64-bit), payload arrays sized out8[6]. */
+int hrmgpu_get_segments_all(hrmgpu_ctx* ctx, long long* off, double* xL, double* xU, double* xM, long long cap);
+/* Count of (line, surface) pairs that saw exactly ONE mesh hit in the last build.  The reference reads
+ * hit[1] out of bounds there (FreeSpace3D.cpp:44-49,61-64); this library defines it as "no interval". */
+int hrmgpu_get_single_hit_count(hrmgpu_ctx* ctx, long long* out);
+
+/* ---- intra-layer edge tests (K4) ------------------------------------------------------------- */
+/* Replaces HRM3D::isSameSliceTransitionFree (HRM3D.cpp:319-365 -> intersectLineMesh3D,
+ * LineIntersection.cpp:7-54) against the C-obstacle meshes of layer k of the last 3D build, and
+ * HRM2D::isSameSliceTransitionFree (HRM2D.cpp:215-232 -> isIntersectSegPolygon2D,
+ * LineIntersection.cpp:173-213) for a 2D build.  v1,v2: [E][3] ([E][2] in 2D) segment end points.
+ * free_out[e] = 1 if the transition is collision-free. */
+int hrmgpu_test_edges(hrmgpu_ctx* ctx, int k, int E, const double* v1, const double* v2, unsigned char* free_out);
+
+/* ---- bridge layers (K5) ----------------------------------------------------------------------- */
+/* Replaces HRM3D::bridgeSlice (HRM3D.cpp:301-317): for P layer pairs, the Minkowski sums of every
+ * OBSTACLE with each body's tightly-fitted ellipsoid (centred at the origin).
+ * tfe_semi [P][B][3], tfe_R [P][B][9].  Meshes stay resident until the next call. */
+int hrmgpu_build_bridge(hrmgpu_ctx* ctx, int P, int B, const double* tfe_semi, const double* tfe_R, int precision);
+/* 2D twin (HRM2D.cpp:199-213): tfe_semi [P][B][2], tfe_angle [P][B]. */
+int hrmgpu_build_bridge2d(hrmgpu_ctx* ctx, int P, int B, const double* tfe_semi, const double* tfe_angle, int precision);
+/* Replaces isPtInCFree for all bodies of Q interpolated robot poses of pair p (HRM3D.cpp:367-425,
+ * HRM2D.cpp:235-282): centres [Q][B][3] ([Q][B][2] in 2D) are the body centres at each pose;
+ * free_out[q] = 1 iff every body centre is outside every bridge C-obstacle of its body. */
+int hrmgpu_test_bridge(hrmgpu_ctx* ctx, int p, int Q, const double* centres, unsigned char* free_out);
+
+/* ---- multi-GPU exchange ------------------------------------------------------------------------ */
+/* Packs the last build's free segments into one contiguous DEVICE buffer owned by the caller's
+ * framework (e.g. a torch tensor) so that an NCCL all-gather can exchange them between ranks:
+ * header [K*L+1] int64 CSR offsets followed by xL, xU, xM (doubles).  With d_buf == NULL returns the
+ * required size in bytes.  See INTEGRATION.md §multi-GPU. */
+long long hrmgpu_pack_segments_dev(hrmgpu_ctx* ctx, void* d_buf, long long cap_bytes);
+
+/* ---- instrumentation ---------------------------------------------------------------------------- */
+/* Number of kernels this context has launched since creation / since the last reset. */
+long long hrmgpu_kernel_launches(hrmgpu_ctx* ctx, int reset);
+/* Device time of the dominant kernel (fused Minkowski + sweep) of the last build call, measured with
+ * CUDA events on the launching stream.  Synchronises.  Returns < 0 on error. */
+double hrmgpu_last_minksweep_ms(hrmgpu_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HRMGPU_H */
