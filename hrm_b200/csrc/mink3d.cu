@@ -87,10 +87,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_minksweep3d(const MinkParams p)
     double* tys = txs + (SWEEP ? p.Lx + 2 : 0);                           // [Ly+2]
     ofs += SWEEP ? sizeof(double) * (p.Lx + p.Ly + 4) : 0;
     uint32_t* vcode = reinterpret_cast<uint32_t*>(smem_raw + ofs);       // [M]
-    ofs += SWEEP ? sizeof(uint32_t) * M : 0;
+    ofs += SWEEP ? ((sizeof(uint32_t) * M + 15) & ~size_t(15)) : 0;
     uint32_t* m0 = reinterpret_cast<uint32_t*>(smem_raw + ofs);          // [L]
     uint32_t* m1 = m0 + (SWEEP ? p.L : 0);                                // [L]
-    ofs += SWEEP ? sizeof(uint32_t) * 2 * p.L : 0;
+    ofs += SWEEP ? ((sizeof(uint32_t) * 2 * p.L + 15) & ~size_t(15)) : 0;
     uint2* queue = reinterpret_cast<uint2*>(smem_raw + ofs);             // [kQueueCap]
     ofs += SWEEP ? sizeof(uint2) * kQueueCap : 0;
     int* qcount = reinterpret_cast<int*>(smem_raw + ofs);
@@ -333,8 +333,8 @@ static size_t smem_bytes(int MODE, bool sweep, int n, int Lx, int Ly) {
     size_t b = (real * 8 * n + 15) & ~size_t(15);
     if (sweep) {
         b += sizeof(double) * (Lx + Ly + 4);
-        b += sizeof(uint32_t) * static_cast<size_t>(n) * n;
-        b += sizeof(uint32_t) * 2 * static_cast<size_t>(Lx) * Ly;
+        b += (sizeof(uint32_t) * static_cast<size_t>(n) * n + 15) & ~size_t(15);
+        b += (sizeof(uint32_t) * 2 * static_cast<size_t>(Lx) * Ly + 15) & ~size_t(15);
         b += sizeof(uint2) * kQueueCap;
     }
     return b + 16;
