@@ -134,6 +134,7 @@ void hrmgpu_destroy(hrmgpu_ctx* c) {
     release(c->segM);
     release(c->counters);
     release(c->bridge_mesh);
+    release(c->dbg);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -392,6 +393,24 @@ long long hrmgpu_pack_segments_dev(hrmgpu_ctx* c, void* d_buf, long long cap_byt
         HRMGPU_CUDA(c, cudaMemcpyAsync(dst + 2 * c->seg_total * 8, c->segM.p, c->seg_total * 8, cudaMemcpyDeviceToDevice, c->stream));
     }
     return need;
+}
+
+// Profiling aid (not part of the drop-in surface): with enable != 0 the next 3D build records, per CTA of the
+// fused kernel, clock64() durations of its phases; out (if non-NULL) receives [n_cta][8] values of the last build.
+long long hrmgpu_debug_phase_times(hrmgpu_ctx* c, int enable, long long n_cta, long long* out) {
+    if (!c) return HRMGPU_E_ARG;
+    if (cudaSetDevice(c->device) != cudaSuccess) return HRMGPU_E_CUDA;
+    if (!enable) {
+        release(c->dbg);
+        return 0;
+    }
+    if (out && c->dbg.p && c->dbg.n >= static_cast<size_t>(n_cta) * 8) {
+        cudaStreamSynchronize(c->stream);
+        cudaMemcpy(out, c->dbg.p, sizeof(long long) * n_cta * 8, cudaMemcpyDeviceToHost);
+        return n_cta;
+    }
+    int rc = ensure(c, c->dbg, static_cast<size_t>(n_cta) * 8);
+    return rc ? rc : 0;
 }
 
 long long hrmgpu_kernel_launches(hrmgpu_ctx* c, int reset) {

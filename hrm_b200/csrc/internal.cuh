@@ -12,7 +12,7 @@
 namespace hrmgpu {
 
 constexpr int kThreads = 256;          // CTA size of the fused Minkowski+sweep kernel
-constexpr int kQueueCap = 1024;        // candidate (face,line) queue entries in shared memory
+constexpr int kQueueCap = 512;         // candidate (face,line) queue entries in shared memory
 constexpr int kMaxGrid = 200;          // n_grid limit (vertex line codes: 4*n^2 bytes of shared memory)
 constexpr int kMaxLinesAxis = 16383;   // per-axis sweep-line limit (15-bit line codes)
 constexpr int kMaxLines = 8192;        // Lx*Ly limit (two-slot hit tables in shared memory)
@@ -71,6 +71,7 @@ struct Ctx {
     DevBuf<long long> seg_off;                   // [K*L+1]
     DevBuf<double> segL, segU, segM;             // [total]
     DevBuf<unsigned long long> counters;         // [0] single-hit count, [1] capacity overflow flag
+    DevBuf<long long> dbg;                       // optional per-CTA phase timings (hrmgpu_debug_phase_times)
     long long seg_total = 0;
     std::vector<long long> h_seg_off;            // host mirror of seg_off (filled on build)
 

@@ -8,17 +8,24 @@
 //   FreeSpace3D::computeIntersectionInterval           src/datastructure/FreeSpace3D.cpp:29-68
 //   intersectVerticalLineMesh3D / intersectLineTriangle3D  src/geometry/LineIntersection.cpp:56-171
 //
-// Phases inside one CTA (256 threads):
-//   A  every thread evaluates boundary points k = r + c*n (omega index r fastest), stores them
-//      planar (x[M] y[M] z[M]) with coalesced writes, and classifies each vertex against the sweep
-//      grid into a packed 2x16-bit "line code" kept in shared memory.
-//   B  every thread takes mesh cells, derives from the 4 corner codes (integer SIMD min/max) the
-//      exact set of sweep lines inside each of the two faces' inclusive xy bounding boxes and
-//      pushes the rare (face, line) candidates into a shared-memory queue.
+// Thread mapping: the CTA's 256 threads form G groups of LPC lanes (LPC chosen on the host so that
+// n / (LPC*ceil(n/LPC)) and n / (G*ceil(n/G)) are close to 1).  A group owns whole eta-columns c of
+// the parameter grid; its lanes stride over the omega index r.  Point index k = r + c*n (omega fastest,
+// SuperQuadrics.cpp:63-72), so a group's stores are LPC consecutive values.
+//
+// Phases inside one CTA:
+//   A  boundary points.  All transcendental factors are separable (8 host-built tables per object), and
+//      in the fast modes everything that depends on the column only (R1*X-part, M1*g-part, M2*g-part: 27
+//      values) is hoisted into registers, leaving 24 FMAs + one rsqrt per point.  Points are stored planar
+//      (x[M] y[M] z[M]); each vertex is classified against the sweep grid into a packed 2x16-bit
+//      "line code" (2*lo+eq per axis, lo = first grid line >= coordinate) kept in shared memory.
+//   B  per mesh cell, integer SIMD min/max over the 4 corner codes give the exact set of sweep lines
+//      inside each of the two faces' inclusive xy bounding boxes (LineIntersection.cpp:77-101); the rare
+//      (face, line) candidates go to a shared-memory queue.
 //   C  the queue is drained densely: triangle test per candidate, hits recorded with an ordered
 //      two-slot atomicMin so that the two LOWEST face indices per line survive (the reference's
-//      "first two hits in face order" rule, SURVEY.md finding 2).
-//   D  per line the two surviving faces are re-evaluated for z and the [lo, up] interval is written.
+//      "first two hits in face order" rule, SURVEY.md finding 2); z of each hit is parked in shared memory.
+//   D  per line the [lo, up] interval is formed from the two surviving hits and written.
 #include "devmath.cuh"
 #include "internal.cuh"
 
@@ -39,21 +46,39 @@ struct MinkParams {
     double* lo;            // [K][So][L]
     double* up;
     unsigned long long* counters;
+    long long* dbg;        // optional [grid][8] phase timestamps (profiling builds of tools/phase_times.py)
     int n, M, B, first_obj, n_objs;
     int Lx, Ly, L;
-    double x0, inv_dx, y0, inv_dy;  // line-index guess
+    int lpc, groups;                        // thread mapping
+    double inv_dx, bias_x, inv_dy, bias_y;  // line-index guess g = x*inv_d + bias
     double zlow, zup;
 };
 
-// Smallest line index i in [0, Lc] with t_i >= x (Lc if none), and whether t_i == x; packed 2*i + eq.
-// ts is sentinel padded: ts[0] = -inf, ts[1+i] = t_i, ts[Lc+1] = +inf.  Exact for any rounding of the guess.
-__device__ __forceinline__ uint32_t line_code(double x, const double* ts, int Lc, double t0, double inv_d) {
-    const double g = (x - t0) * inv_d;
-    int i = (g > 0.0) ? ((g < static_cast<double>(Lc)) ? __double2int_ru(g) : Lc) : 0;
+constexpr uint32_t kPosBits = 9;
+constexpr uint32_t kPosMask = (1u << kPosBits) - 1u;  // == "not queued"
+static_assert((1u << kPosBits) == kQueueCap, "queue slots must fit the packed hit entries");
+
+// Exact classification of a coordinate against the sweep grid: smallest line index i in [0, Lc] with
+// t_i >= x (Lc if none) and whether t_i == x, packed as 2*i + eq.  ts is sentinel padded:
+// ts[0] = -inf, ts[1+i] = t_i, ts[Lc+1] = +inf.  Fast path: ceil of the affine guess when it is provably
+// not within rounding distance of a grid line; otherwise an exact search on the t_i the host computed with
+// the reference's formula (HRM3D.cpp:66-81).
+__device__ __noinline__ uint32_t line_code_slow(double x, const double* ts, int Lc, int i) {
+    i = min(max(i, 0), Lc);
     while (i > 0 && ts[i] >= x) --i;
     while (ts[i + 1] < x) ++i;
     const uint32_t eq = (ts[i + 1] == x) ? 1u : 0u;
     return 2u * static_cast<uint32_t>(i) + eq;
+}
+__device__ __forceinline__ uint32_t line_code(double x, const double* ts, int Lc, double inv_d, double bias) {
+    const double g = fma(x, inv_d, bias);
+    const double kMagic = 6755399441055744.0;  // 1.5 * 2^52: low word of (g + magic) = rint(g)
+    const double t = g + kMagic;
+    const int rn = __double2loint(t);
+    const double diff = g - (t - kMagic);  // in [-0.5, 0.5]
+    const int i = rn + ((diff > 0.0) ? 1 : 0);
+    if (!(fabs(diff) > 1e-6) || !(fabs(g) < 1e9)) return line_code_slow(x, ts, Lc, (g > 0.0) ? ((g < 1e9) ? i : Lc) : 0);
+    return 2u * static_cast<uint32_t>(min(max(i, 0), Lc));
 }
 
 template <int MODE>
@@ -79,20 +104,33 @@ __global__ void __launch_bounds__(kThreads, 2) k_minksweep3d(const MinkParams p)
     const int b = s - oi * p.B;
     const int obj_id = p.first_obj + oi;
     const int tid = threadIdx.x;
+    const int grp = tid / p.lpc;
+    const int ln = tid - grp * p.lpc;
+    const bool worker = grp < p.groups;
 
-    // ---- shared memory carve-up -----------------------------------------------------------
+    long long t_start = 0, t_pro = 0, t_a = 0, t_scan = 0, t_drain = 0;
+    int rounds = 0;
+    if (p.dbg) t_start = clock64();
+    // ---- shared memory carve-up (every region 16-byte aligned) ------------------------------
     Real* tab = reinterpret_cast<Real*>(smem_raw);                       // [8][n]
     size_t ofs = (sizeof(Real) * 8 * n + 15) & ~size_t(15);
+    double* mats = reinterpret_cast<double*>(smem_raw + ofs);            // M1[9] M2[9]
+    ofs += sizeof(double) * 18;
     double* txs = reinterpret_cast<double*>(smem_raw + ofs);             // [Lx+2]
     double* tys = txs + (SWEEP ? p.Lx + 2 : 0);                           // [Ly+2]
-    ofs += SWEEP ? sizeof(double) * (p.Lx + p.Ly + 4) : 0;
+    ofs += SWEEP ? ((sizeof(double) * (p.Lx + p.Ly + 4) + 15) & ~size_t(15)) : 0;
+    double* zq = reinterpret_cast<double*>(smem_raw + ofs);              // [kQueueCap] z of queued hits
+    ofs += SWEEP ? sizeof(double) * kQueueCap : 0;
+    uint2* queue = reinterpret_cast<uint2*>(smem_raw + ofs);             // [kQueueCap] (face, ix | iy << 16)
+    ofs += SWEEP ? sizeof(uint2) * kQueueCap : 0;
     uint32_t* vcode = reinterpret_cast<uint32_t*>(smem_raw + ofs);       // [M]
     ofs += SWEEP ? ((sizeof(uint32_t) * M + 15) & ~size_t(15)) : 0;
+    double* zc0 = reinterpret_cast<double*>(smem_raw + ofs);             // [L] committed z of the two lowest hit faces
+    double* zc1 = zc0 + (SWEEP ? p.L : 0);                                // [L]
+    ofs += SWEEP ? sizeof(double) * 2 * p.L : 0;
     uint32_t* m0 = reinterpret_cast<uint32_t*>(smem_raw + ofs);          // [L]
     uint32_t* m1 = m0 + (SWEEP ? p.L : 0);                                // [L]
     ofs += SWEEP ? ((sizeof(uint32_t) * 2 * p.L + 15) & ~size_t(15)) : 0;
-    uint2* queue = reinterpret_cast<uint2*>(smem_raw + ofs);             // [kQueueCap]
-    ofs += SWEEP ? sizeof(uint2) * kQueueCap : 0;
     int* qcount = reinterpret_cast<int*>(smem_raw + ofs);
 
     // ---- prologue: tables, line coordinates, per-surface matrices -------------------------
@@ -104,37 +142,39 @@ __global__ void __launch_bounds__(kThreads, 2) k_minksweep3d(const MinkParams p)
         for (int i = tid; i < p.L; i += kThreads) m0[i] = kNoFace, m1[i] = kNoFace;
         if (tid == 0) *qcount = 0;
     }
-
-    const Obj3 ob = p.obj[obj_id];
-    double R2[9], T[9], M1[9], M2[9];
-    {
+    const Obj3& ob = p.obj[obj_id];
+    if (tid == 0) {
+        // Tinv = (R2 * diag) * R2^T ;  M1 = Tinv * R1 ;  M2 = ((K * Tinv) * Tinv) * R1
+        // (SuperQuadrics.cpp:115,137-140), evaluated in the reference's association order.
+        double R2[9], T[9], R1[9];
         const double* r2 = p.R + (static_cast<size_t>(k) * p.B + b) * 9;
 #pragma unroll
-        for (int i = 0; i < 9; ++i) R2[i] = __ldg(r2 + i);
+        for (int i = 0; i < 9; ++i) R2[i] = __ldg(r2 + i), R1[i] = __ldg(&ob.R[i]);
         const double d0 = __ldg(p.semi + 3 * b), d1 = __ldg(p.semi + 3 * b + 1), d2 = __ldg(p.semi + 3 * b + 2);
-        // Tinv = (R2 * diag) * R2^T                                  SuperQuadrics.cpp:115
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
             for (int j = 0; j < 3; ++j)
                 T[3 * i + j] = A::mad(A::mul(R2[3 * i + 2], d2), R2[3 * j + 2],
                                       A::mad(A::mul(R2[3 * i + 1], d1), R2[3 * j + 1], A::mul(A::mul(R2[3 * i], d0), R2[3 * j])));
-        // M1 = Tinv * R1 ;  M2 = ((K * Tinv) * Tinv) * R1            SuperQuadrics.cpp:137-140
+        const double sign = __ldg(&ob.sign);
         double KT[9], KTT[9];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) KT[i] = A::mul(ob.sign, T[i]);
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                M1[3 * i + j] = A::mad(T[3 * i + 2], ob.R[6 + j], A::mad(T[3 * i + 1], ob.R[3 + j], A::mul(T[3 * i], ob.R[j])));
-                KTT[3 * i + j] = A::mad(KT[3 * i + 2], T[6 + j], A::mad(KT[3 * i + 1], T[3 + j], A::mul(KT[3 * i], T[j])));
-            }
+        for (int i = 0; i < 9; ++i) KT[i] = A::mul(sign, T[i]);
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
             for (int j = 0; j < 3; ++j)
-                M2[3 * i + j] = A::mad(KTT[3 * i + 2], ob.R[6 + j], A::mad(KTT[3 * i + 1], ob.R[3 + j], A::mul(KTT[3 * i], ob.R[j])));
+                KTT[3 * i + j] = A::mad(KT[3 * i + 2], T[6 + j], A::mad(KT[3 * i + 1], T[3 + j], A::mul(KT[3 * i], T[j])));
+        if (tid == 0) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    mats[3 * i + j] = A::mad(T[3 * i + 2], R1[6 + j], A::mad(T[3 * i + 1], R1[3 + j], A::mul(T[3 * i], R1[j])));
+                    mats[9 + 3 * i + j] = A::mad(KTT[3 * i + 2], R1[6 + j], A::mad(KTT[3 * i + 1], R1[3 + j], A::mul(KTT[3 * i], R1[j])));
+                }
+        }
     }
     const double offx = __ldg(p.off + (static_cast<size_t>(k) * p.B + b) * 3);
     const double offy = __ldg(p.off + (static_cast<size_t>(k) * p.B + b) * 3 + 1);
@@ -145,115 +185,128 @@ __global__ void __launch_bounds__(kThreads, 2) k_minksweep3d(const MinkParams p)
     Real* my = mesh + M;
     Real* mz = mesh + 2 * static_cast<size_t>(M);
     __syncthreads();
+    if (p.dbg) t_pro = clock64();
 
     // ---- phase A: boundary points ---------------------------------------------------------
-    if constexpr (MODE == HRMGPU_F32) {
-        // FP32 throughput variant: same closed form, float arithmetic, fast reciprocal square root.
-        float m1f[9], m2f[9], r1f[9];
+    if (worker) {
+        const double oa = __ldg(&ob.a), obb = __ldg(&ob.b), oc = __ldg(&ob.c);
+        const double px = __ldg(&ob.px), py = __ldg(&ob.py), pz = __ldg(&ob.pz);
+        if constexpr (MODE == HRMGPU_F64_STRICT) {
+            // IEEE replica of the reference's evaluation order; only exact products are hoisted per column.
+            double R1[9], M1[9], M2[9];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) m1f[i] = static_cast<float>(M1[i]), m2f[i] = static_cast<float>(M2[i]), r1f[i] = static_cast<float>(ob.R[i]);
-        const float fa = static_cast<float>(ob.a), fb = static_cast<float>(ob.b), fc = static_cast<float>(ob.c);
-        const float ia = 1.0f / fa, ib = 1.0f / fb, ic = 1.0f / fc;
-        const float fpx = static_cast<float>(ob.px - offx), fpy = static_cast<float>(ob.py - offy), fpz = static_cast<float>(ob.pz - offz);
-        int c = tid / n, r = tid - c * n;
-        const int dc = kThreads / n, dr = kThreads - dc * n;
-        for (int kk = tid; kk < M; kk += kThreads) {
-            const float ce1 = tab[c], se1 = tab[n + c], ce2 = tab[2 * n + c], se2 = tab[3 * n + c];
-            const float cw1 = tab[4 * n + r], sw1 = tab[5 * n + r], cw2 = tab[6 * n + r], sw2 = tab[7 * n + r];
-            const float X = fa * (ce1 * cw1), Y = fb * (ce1 * sw1), Z = fc * se1;
-            const float gx = ce2 * cw2 * ia, gy = ce2 * sw2 * ib, gz = se2 * ic;
-            const float ux = m1f[0] * gx + m1f[1] * gy + m1f[2] * gz;
-            const float uy = m1f[3] * gx + m1f[4] * gy + m1f[5] * gz;
-            const float uz = m1f[6] * gx + m1f[7] * gy + m1f[8] * gz;
-            const float inv = rsqrtf(ux * ux + uy * uy + uz * uz);
-            const float wx = m2f[0] * gx + m2f[1] * gy + m2f[2] * gz;
-            const float wy = m2f[3] * gx + m2f[4] * gy + m2f[5] * gz;
-            const float wz = m2f[6] * gx + m2f[7] * gy + m2f[8] * gz;
-            const float ox = r1f[0] * X + r1f[1] * Y + r1f[2] * Z + fpx + wx * inv;
-            const float oy = r1f[3] * X + r1f[4] * Y + r1f[5] * Z + fpy + wy * inv;
-            const float oz = r1f[6] * X + r1f[7] * Y + r1f[8] * Z + fpz + wz * inv;
-            reinterpret_cast<float*>(mx)[kk] = ox;
-            reinterpret_cast<float*>(my)[kk] = oy;
-            reinterpret_cast<float*>(mz)[kk] = oz;
-            if (SWEEP) {
-                const uint32_t cx = line_code(static_cast<double>(ox), txs, p.Lx, p.x0, p.inv_dx);
-                const uint32_t cy = line_code(static_cast<double>(oy), tys, p.Ly, p.y0, p.inv_dy);
-                vcode[kk] = cx | (cy << 16);
+            for (int i = 0; i < 9; ++i) R1[i] = __ldg(&ob.R[i]), M1[i] = mats[i], M2[i] = mats[9 + i];
+            for (int c = grp; c < n; c += p.groups) {
+                const double ce1 = tab[c], se1 = tab[n + c], ce2 = tab[2 * n + c], se2 = tab[3 * n + c];
+                const double Z = A::mul(oc, se1);   // c * (se1 * 1.0)
+                const double gz = A::div(se2, oc);  // (se2 * 1.0) / c
+                const double rz0 = A::mul(R1[2], Z), rz1 = A::mul(R1[5], Z), rz2 = A::mul(R1[8], Z);
+                const double uz0 = A::mul(M1[2], gz), uz1 = A::mul(M1[5], gz), uz2 = A::mul(M1[8], gz);
+                const double wz0 = A::mul(M2[2], gz), wz1 = A::mul(M2[5], gz), wz2 = A::mul(M2[8], gz);
+                for (int r = ln; r < n; r += p.lpc) {
+                    const double cw1 = tab[4 * n + r], sw1 = tab[5 * n + r], cw2 = tab[6 * n + r], sw2 = tab[7 * n + r];
+                    const int kk = c * n + r;
+                    // getOriginShape: canonical point, rotate, translate              SuperQuadrics.cpp:58-78
+                    const double X = A::mul(oa, A::mul(ce1, cw1));
+                    const double Y = A::mul(obb, A::mul(ce1, sw1));
+                    const double x0 = A::add(A::add(A::mad(R1[1], Y, A::mul(R1[0], X)), rz0), px);
+                    const double y0 = A::add(A::add(A::mad(R1[4], Y, A::mul(R1[3], X)), rz1), py);
+                    const double z0 = A::add(A::add(A::mad(R1[7], Y, A::mul(R1[6], X)), rz2), pz);
+                    // gradient                                                       SuperQuadrics.cpp:118-135
+                    const double gx = A::div(A::mul(ce2, cw2), oa);
+                    const double gy = A::div(A::mul(ce2, sw2), obb);
+                    const double ux = A::add(A::mad(M1[1], gy, A::mul(M1[0], gx)), uz0);
+                    const double uy = A::add(A::mad(M1[4], gy, A::mul(M1[3], gx)), uz1);
+                    const double uz = A::add(A::mad(M1[7], gy, A::mul(M1[6], gx)), uz2);
+                    const double wx = A::add(A::mad(M2[1], gy, A::mul(M2[0], gx)), wz0);
+                    const double wy = A::add(A::mad(M2[4], gy, A::mul(M2[3], gx)), wz1);
+                    const double wz = A::add(A::mad(M2[7], gy, A::mul(M2[6], gx)), wz2);
+                    const double nrm = A::sqrt(A::mad(uz, uz, A::mad(uy, uy, A::mul(ux, ux))));  // :137-140
+                    const double ox = A::sub(A::add(x0, A::div(wx, nrm)), offx);                   // MultiBodyTree3D.cpp:98-101
+                    const double oy = A::sub(A::add(y0, A::div(wy, nrm)), offy);
+                    const double oz = A::sub(A::add(z0, A::div(wz, nrm)), offz);
+                    mx[kk] = ox;
+                    my[kk] = oy;
+                    mz[kk] = oz;
+                    if (SWEEP) {
+                        const uint32_t cx = line_code(ox, txs, p.Lx, p.inv_dx, p.bias_x);
+                        const uint32_t cy = line_code(oy, tys, p.Ly, p.inv_dy, p.bias_y);
+                        vcode[kk] = cx | (cy << 16);
+                    }
+                }
             }
-            r += dr;
-            c += dc;
-            if (r >= n) r -= n, ++c;
-        }
-    } else {
-        const double* dtab = reinterpret_cast<const double*>(tab);
-        double ia = 0, ib = 0, ic = 0;
-        if constexpr (MODE == HRMGPU_F64) ia = 1.0 / ob.a, ib = 1.0 / ob.b, ic = 1.0 / ob.c;
-        int c = tid / n, r = tid - c * n;
-        const int dc = kThreads / n, dr = kThreads - dc * n;
-        for (int kk = tid; kk < M; kk += kThreads) {
-            const double ce1 = dtab[c], se1 = dtab[n + c], ce2 = dtab[2 * n + c], se2 = dtab[3 * n + c];
-            const double cw1 = dtab[4 * n + r], sw1 = dtab[5 * n + r], cw2 = dtab[6 * n + r], sw2 = dtab[7 * n + r];
-            // getOriginShape: canonical point, rotate, translate                 SuperQuadrics.cpp:58-78
-            const double X = A::mul(ob.a, A::mul(ce1, cw1));
-            const double Y = A::mul(ob.b, A::mul(ce1, sw1));
-            const double Z = A::mul(ob.c, se1);
-            const double x0 = A::add(A::mad(ob.R[2], Z, A::mad(ob.R[1], Y, A::mul(ob.R[0], X))), ob.px);
-            const double y0 = A::add(A::mad(ob.R[5], Z, A::mad(ob.R[4], Y, A::mul(ob.R[3], X))), ob.py);
-            const double z0 = A::add(A::mad(ob.R[8], Z, A::mad(ob.R[7], Y, A::mul(ob.R[6], X))), ob.pz);
-            // gradient                                                          SuperQuadrics.cpp:118-135
-            double gx, gy, gz;
-            if constexpr (MODE == HRMGPU_F64_STRICT) {
-                gx = A::div(A::mul(ce2, cw2), ob.a);
-                gy = A::div(A::mul(ce2, sw2), ob.b);
-                gz = A::div(se2, ob.c);
-            } else {
-                gx = ce2 * cw2 * ia;
-                gy = ce2 * sw2 * ib;
-                gz = se2 * ic;
+        } else {
+            // Fast variants: x = P*cw1 + Q*sw1 + C,  u = U1*cw2 + U2*sw2 + U3,  w = W1*cw2 + W2*sw2 + W3 with the
+            // nine 3-vectors depending on the column only; out = x + w * rsqrt(u.u).
+            const Real ia = Real(1) / Real(oa), ib = Real(1) / Real(obb), ic = Real(1) / Real(oc);
+            for (int c = grp; c < n; c += p.groups) {
+                Real P[3], Q[3], C[3], U1[3], U2[3], U3[3], W1[3], W2[3], W3[3];
+                {
+                    const Real ce1 = tab[c], se1 = tab[n + c], ce2 = tab[2 * n + c], se2 = tab[3 * n + c];
+                    const Real Ac = Real(oa) * ce1, Bc = Real(obb) * ce1, Zc = Real(oc) * se1;
+                    const Real ga = ce2 * ia, gb = ce2 * ib, gc = se2 * ic;
+                    const Real tr[3] = {Real(px - offx), Real(py - offy), Real(pz - offz)};
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        P[i] = Real(__ldg(&ob.R[3 * i])) * Ac;
+                        Q[i] = Real(__ldg(&ob.R[3 * i + 1])) * Bc;
+                        C[i] = Real(__ldg(&ob.R[3 * i + 2])) * Zc + tr[i];
+                        U1[i] = Real(mats[3 * i]) * ga;
+                        U2[i] = Real(mats[3 * i + 1]) * gb;
+                        U3[i] = Real(mats[3 * i + 2]) * gc;
+                        W1[i] = Real(mats[9 + 3 * i]) * ga;
+                        W2[i] = Real(mats[9 + 3 * i + 1]) * gb;
+                        W3[i] = Real(mats[9 + 3 * i + 2]) * gc;
+                    }
+                }
+                // two rows per iteration: independent dependency chains for the FP64 pipe
+                for (int r = ln; r < n; r += 2 * p.lpc) {
+                    Real o[2][3];
+                    int rr[2] = {r, (r + p.lpc < n) ? r + p.lpc : r};
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const Real cw1 = tab[4 * n + rr[h]], sw1 = tab[5 * n + rr[h]], cw2 = tab[6 * n + rr[h]], sw2 = tab[7 * n + rr[h]];
+                        const Real ux = U1[0] * cw2 + (U2[0] * sw2 + U3[0]);
+                        const Real uy = U1[1] * cw2 + (U2[1] * sw2 + U3[1]);
+                        const Real uz = U1[2] * cw2 + (U2[2] * sw2 + U3[2]);
+                        Real inv;
+                        if constexpr (MODE == HRMGPU_F32)
+                            inv = rsqrtf(ux * ux + uy * uy + uz * uz);
+                        else
+                            inv = rsqrt(ux * ux + uy * uy + uz * uz);
+                        o[h][0] = (W1[0] * cw2 + (W2[0] * sw2 + W3[0])) * inv + (P[0] * cw1 + (Q[0] * sw1 + C[0]));
+                        o[h][1] = (W1[1] * cw2 + (W2[1] * sw2 + W3[1])) * inv + (P[1] * cw1 + (Q[1] * sw1 + C[1]));
+                        o[h][2] = (W1[2] * cw2 + (W2[2] * sw2 + W3[2])) * inv + (P[2] * cw1 + (Q[2] * sw1 + C[2]));
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (h == 1 && rr[1] == r) break;
+                        const int kk = c * n + rr[h];
+                        mx[kk] = o[h][0];
+                        my[kk] = o[h][1];
+                        mz[kk] = o[h][2];
+                        if (SWEEP) {
+                            const uint32_t cx = line_code(static_cast<double>(o[h][0]), txs, p.Lx, p.inv_dx, p.bias_x);
+                            const uint32_t cy = line_code(static_cast<double>(o[h][1]), tys, p.Ly, p.inv_dy, p.bias_y);
+                            vcode[kk] = cx | (cy << 16);
+                        }
+                    }
+                }
             }
-            const double ux = A::mad(M1[2], gz, A::mad(M1[1], gy, A::mul(M1[0], gx)));
-            const double uy = A::mad(M1[5], gz, A::mad(M1[4], gy, A::mul(M1[3], gx)));
-            const double uz = A::mad(M1[8], gz, A::mad(M1[7], gy, A::mul(M1[6], gx)));
-            const double wx = A::mad(M2[2], gz, A::mad(M2[1], gy, A::mul(M2[0], gx)));
-            const double wy = A::mad(M2[5], gz, A::mad(M2[4], gy, A::mul(M2[3], gx)));
-            const double wz = A::mad(M2[8], gz, A::mad(M2[7], gy, A::mul(M2[6], gx)));
-            const double nn = A::mad(uz, uz, A::mad(uy, uy, A::mul(ux, ux)));
-            double ox, oy, oz;
-            if constexpr (MODE == HRMGPU_F64_STRICT) {
-                const double nrm = A::sqrt(nn);                                  // SuperQuadrics.cpp:137-140
-                ox = A::sub(A::add(x0, A::div(wx, nrm)), offx);                  // MultiBodyTree3D.cpp:98-101
-                oy = A::sub(A::add(y0, A::div(wy, nrm)), offy);
-                oz = A::sub(A::add(z0, A::div(wz, nrm)), offz);
-            } else {
-                const double inv = rsqrt(nn);
-                ox = fma(wx, inv, x0) - offx;
-                oy = fma(wy, inv, y0) - offy;
-                oz = fma(wz, inv, z0) - offz;
-            }
-            reinterpret_cast<double*>(mx)[kk] = ox;
-            reinterpret_cast<double*>(my)[kk] = oy;
-            reinterpret_cast<double*>(mz)[kk] = oz;
-            if (SWEEP) {
-                const uint32_t cx = line_code(ox, txs, p.Lx, p.x0, p.inv_dx);
-                const uint32_t cy = line_code(oy, tys, p.Ly, p.y0, p.inv_dy);
-                vcode[kk] = cx | (cy << 16);
-            }
-            r += dr;
-            c += dc;
-            if (r >= n) r -= n, ++c;
         }
     }
     if (!SWEEP) return;
+    __syncwarp();  // lanes leave the column/row loops at different trips: reconverge before the block barrier
     __syncthreads();
+    if (p.dbg) t_a = clock64();
 
-    // One candidate: triangle test of face f against sweep line l, ordered insertion on a hit.
-    auto test_face = [&](uint32_t f, uint32_t l, double& z) -> bool {
+    // Triangle test of face f against the sweep line (ix, iy).
+    auto test_face = [&](uint32_t f, uint32_t ix, uint32_t iy, double& z) -> bool {
         int v0, v1, v2;
         face_vertices(static_cast<int>(f), n, v0, v1, v2);
         const D3 t0 = {static_cast<double>(mx[v0]), static_cast<double>(my[v0]), static_cast<double>(mz[v0])};
         const D3 t1 = {static_cast<double>(mx[v1]), static_cast<double>(my[v1]), static_cast<double>(mz[v1])};
         const D3 t2 = {static_cast<double>(mx[v2]), static_cast<double>(my[v2]), static_cast<double>(mz[v2])};
-        const uint32_t ix = l / p.Ly, iy = l - ix * p.Ly;
         const D3 o = {txs[ix + 1], tys[iy + 1], 0.0};
         const D3 d = {0.0, 0.0, 1.0};
         D3 pt;
@@ -261,83 +314,167 @@ __global__ void __launch_bounds__(kThreads, 2) k_minksweep3d(const MinkParams p)
         z = pt.z;
         return hit;
     };
-    auto candidate = [&](uint32_t f, uint32_t l) {
-        double z;
-        if (test_face(f, l, z)) insert_two_smallest(&m0[l], &m1[l], f);
-    };
 
-    // ---- phase B: face bounding boxes vs the sweep grid, via the vertex line codes -----------
+    // ---- phases B + C, interleaved: scan cells -> queue candidates -> cooperative drain ----------
+    // A thread scans its cells and pushes (face, line) candidates until the shared queue is full, then
+    // parks its scan position.  The whole CTA drains the queue (one candidate per thread at a time, so
+    // even faces that cover hundreds of lines -- the eps=0.1 arena -- are spread over all threads),
+    // commits the per-line two lowest hit faces with their z, and resumes scanning.
     const int nc1 = n - 1;
     const int ncell = nc1 * nc1;
-    for (int cell = tid; cell < ncell; cell += kThreads) {
-        const int i = cell / nc1, j = cell - i * nc1;
-        const int q = i * n + j;
-        const uint32_t c00 = vcode[q], c01 = vcode[q + 1], c10 = vcode[q + n], c11 = vcode[q + n + 1];
-        const uint32_t dmin = __vminu2(c00, c11), dmax = __vmaxu2(c00, c11);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const uint32_t cm = half ? c01 : c10;
-            const uint32_t mn = __vminu2(dmin, cm), mxx = __vmaxu2(dmax, cm);
-            // lo = min(2*lo+eq) >> 1 ; hi+1 = (max(2*lo+eq) + 1) >> 1  (per 16-bit half)
-            const uint32_t lo2 = (mn >> 1) & 0x7FFF7FFFu;
-            const uint32_t hi2 = ((mxx + 0x00010001u) >> 1) & 0x7FFF7FFFu;
-            const uint32_t lox = lo2 & 0xFFFFu, loy = lo2 >> 16, hix = hi2 & 0xFFFFu, hiy = hi2 >> 16;  // [lo, hi)
-            if (lox < hix && loy < hiy) {
-                const uint32_t f = half ? static_cast<uint32_t>(cell + ncell) : static_cast<uint32_t>(cell);
-                for (uint32_t ix = lox; ix < hix; ++ix)
-                    for (uint32_t iy = loy; iy < hiy; ++iy) {
-                        const uint32_t l = ix * p.Ly + iy;
-                        const int pos = atomicAdd(qcount, 1);
-                        if (pos < kQueueCap)
-                            queue[pos] = make_uint2(f, l);
-                        else
-                            candidate(f, l);  // queue full (huge faces / the arena): test in place
+    int si = grp, sj = ln, shalf = 0;          // scan position: cell (si, sj), face half
+    uint32_t six = 0, siy = 0;                  // next line of the current face to push (absolute indices)
+    bool face_open = false;                    // (six, siy) valid for the current face
+    uint32_t f_lox = 0, f_loy = 0, f_hix = 0, f_hiy = 0;
+    bool scanning = worker && si < nc1 && sj < nc1;
+    for (;;) {
+        while (scanning) {
+            if (!face_open) {
+                const int q = si * n + sj;
+                const uint32_t c00 = vcode[q], c11 = vcode[q + n + 1];
+                const uint32_t cm = shalf ? vcode[q + 1] : vcode[q + n];
+                // quick reject (the common case): all three vertices in the same grid cell and none on a line
+                if (!((c00 == c11) && (c00 == cm) && ((c00 & 0x00010001u) == 0u))) {
+                    const uint32_t mn = __vminu2(__vminu2(c00, c11), cm), mxx = __vmaxu2(__vmaxu2(c00, c11), cm);
+                    // lo = min(2*lo+eq) >> 1 ; hi+1 = (max(2*lo+eq) + 1) >> 1  (per 16-bit half): lines [lo, hi)
+                    const uint32_t lo2 = (mn >> 1) & 0x7FFF7FFFu;
+                    const uint32_t hi2 = ((mxx + 0x00010001u) >> 1) & 0x7FFF7FFFu;
+                    f_lox = lo2 & 0xFFFFu, f_loy = lo2 >> 16, f_hix = hi2 & 0xFFFFu, f_hiy = hi2 >> 16;
+                    if (f_lox < f_hix && f_loy < f_hiy) {
+                        six = f_lox, siy = f_loy;
+                        face_open = true;
                     }
+                }
+            }
+            if (face_open) {
+                const uint32_t f = static_cast<uint32_t>(si * nc1 + sj + (shalf ? ncell : 0));
+                bool full = false;
+                while (six < f_hix) {
+                    const int pos = atomicAdd(qcount, 1);
+                    if (pos >= static_cast<int>(kPosMask)) {  // slots 0..1022; 1023 is the 'committed' marker
+                        full = true;
+                        break;
+                    }
+                    queue[pos] = make_uint2(f, six | (siy << 16));
+                    if (++siy == f_hiy) siy = f_loy, ++six;
+                }
+                if (full) break;  // park here; resume after the drain
+                face_open = false;
+            }
+            // next face / cell of this thread
+            if (shalf == 0) {
+                shalf = 1;
+            } else {
+                shalf = 0;
+                sj += p.lpc;
+                if (sj >= nc1) sj = ln, si += p.groups;
+                if (si >= nc1) scanning = false;
             }
         }
+        __syncwarp();  // the scan loop exits lane by lane: the drain below must run with full warps
+        __syncthreads();
+        long long tq0 = 0;
+        if (p.dbg) tq0 = clock64();
+        // drain
+        const int nq = min(*qcount, static_cast<int>(kPosMask));
+        for (int i = tid; i < nq; i += kThreads) {
+            const uint2 e = queue[i];
+            const uint32_t ix = e.y & 0xFFFFu, iy = e.y >> 16;
+            double z;
+            if (test_face(e.x, ix, iy, z)) {
+                zq[i] = z;
+                const uint32_t l = ix * p.Ly + iy;
+                insert_two_smallest(&m0[l], &m1[l], (e.x << kPosBits) | static_cast<uint32_t>(i));
+            }
+        }
+        __syncwarp();
+        __syncthreads();
+        // commit: bind z to the surviving entries of every line (entries from earlier rounds carry the
+        // marker kPosMask and already own zc0/zc1; an older entry can only have moved from slot 0 to slot 1)
+        for (int l = tid; l < p.L; l += kThreads) {
+            const uint32_t e0 = m0[l], e1 = m1[l];
+            if (e0 == kNoFace) continue;
+            const double old0 = zc0[l];
+            double z0, z1 = 0.0;
+            const bool fresh0 = (e0 & kPosMask) != kPosMask;
+            z0 = fresh0 ? zq[e0 & kPosMask] : old0;
+            if (e1 != kNoFace) {
+                const bool fresh1 = (e1 & kPosMask) != kPosMask;
+                // a committed entry in slot 1 is either the old slot-1 entry (slot 0 unchanged) or the old slot-0 entry
+                z1 = fresh1 ? zq[e1 & kPosMask] : (fresh0 ? old0 : zc1[l]);
+                zc1[l] = z1;
+                m1[l] = e1 | kPosMask;
+            }
+            zc0[l] = z0;
+            m0[l] = e0 | kPosMask;
+        }
+        if (tid == 0) *qcount = 0;
+        ++rounds;
+        const int more = __syncthreads_or(scanning ? 1 : 0);
+        if (p.dbg) t_drain += clock64() - tq0;
+        if (!more) break;
     }
-    __syncthreads();
 
-    // ---- phase C: dense drain of the candidate queue ------------------------------------------
-    const int nq = min(*qcount, kQueueCap);
-    for (int i = tid; i < nq; i += kThreads) candidate(queue[i].x, queue[i].y);
-    __syncthreads();
-
+    if (p.dbg) t_scan = clock64();
     // ---- phase D: intervals ----------------------------------------------------------------
-    const bool is_arena = ob.sign < 0.0;
+    const bool is_arena = __ldg(&ob.sign) < 0.0;
     double* lo = p.lo + static_cast<size_t>(blockIdx.x) * p.L;
     double* up = p.up + static_cast<size_t>(blockIdx.x) * p.L;
     unsigned single = 0;
     for (int l = tid; l < p.L; l += kThreads) {
-        const uint32_t f0 = m0[l], f1 = m1[l];
+        const uint32_t e0 = m0[l], e1 = m1[l];
         double a = is_arena ? p.zlow : __longlong_as_double(0x7FF8000000000000LL);
         double bb = is_arena ? p.zup : __longlong_as_double(0x7FF8000000000000LL);
-        if (f1 != kNoFace) {
-            double z0, z1;
-            test_face(f0, l, z0);
-            test_face(f1, l, z1);
+        if (e1 != kNoFace) {
+            const double z0 = zc0[l], z1 = zc1[l];
             const double zl = fmin(z0, z1), zu = fmax(z0, z1);
-            a = is_arena ? fmin(p.zlow, zl) : zl;      // FreeSpace3D.cpp:44-49 / 61-64
+            a = is_arena ? fmin(p.zlow, zl) : zl;  // FreeSpace3D.cpp:44-49 / 61-64
             bb = is_arena ? fmax(p.zup, zu) : zu;
-        } else if (f0 != kNoFace) {
+        } else if (e0 != kNoFace) {
             ++single;  // exactly one hit: reference reads out of bounds; defined here as "no interval"
         }
         lo[l] = a;
         up[l] = bb;
     }
     if (single) atomicAdd(p.counters, static_cast<unsigned long long>(single));
+    if (p.dbg && tid == 0) {
+        long long* d = p.dbg + static_cast<size_t>(blockIdx.x) * 8;
+        d[0] = t_pro - t_start;      // prologue
+        d[1] = t_a - t_pro;          // phase A
+        d[2] = t_scan - t_a;         // scan + drain + commit
+        d[3] = t_drain;              // of which drain + commit
+        d[4] = clock64() - t_scan;   // phase D
+        d[5] = rounds;
+        d[6] = s;
+        d[7] = clock64() - t_start;
+    }
 }
 
 static size_t smem_bytes(int MODE, bool sweep, int n, int Lx, int Ly) {
     const size_t real = (MODE == HRMGPU_F32) ? 4 : 8;
     size_t b = (real * 8 * n + 15) & ~size_t(15);
+    b += sizeof(double) * 18;
     if (sweep) {
-        b += sizeof(double) * (Lx + Ly + 4);
+        b += (sizeof(double) * (Lx + Ly + 4) + 15) & ~size_t(15);
+        b += sizeof(double) * kQueueCap + sizeof(uint2) * kQueueCap;
         b += (sizeof(uint32_t) * static_cast<size_t>(n) * n + 15) & ~size_t(15);
+        b += sizeof(double) * 2 * static_cast<size_t>(Lx) * Ly;
         b += (sizeof(uint32_t) * 2 * static_cast<size_t>(Lx) * Ly + 15) & ~size_t(15);
-        b += sizeof(uint2) * kQueueCap;
     }
     return b + 16;
+}
+
+// Lanes per column group: maximise n^2 / (threads * ceil(n/lpc) * ceil(n/groups)).
+static void pick_mapping(int n, int& lpc, int& groups) {
+    double best = -1;
+    lpc = 32;
+    groups = kThreads / 32;
+    for (int l = 32; l >= 4; --l) {  // prefer wide groups (longer contiguous stores) unless a narrower one is >3% better
+        const int g = kThreads / l;
+        const double steps = static_cast<double>((n + l - 1) / l) * ((n + g - 1) / g);
+        const double eff = static_cast<double>(n) * n / (steps * kThreads);
+        if (eff > best * 1.03) best = eff, lpc = l, groups = g;
+    }
 }
 
 template <int MODE, bool SWEEP>
@@ -364,6 +501,7 @@ int launch_minksweep3d(Ctx* c, int K, int B, int n_first_obj, int n_objs, const 
     p.lo = d_lo;
     p.up = d_up;
     p.counters = c->counters.p;
+    p.dbg = c->dbg.p && c->dbg.n >= static_cast<size_t>(K) * n_objs * B * 8 ? c->dbg.p : nullptr;
     p.n = c->n;
     p.M = c->n * c->n;
     p.B = B;
@@ -372,12 +510,13 @@ int launch_minksweep3d(Ctx* c, int K, int B, int n_first_obj, int n_objs, const 
     p.Lx = c->Lx;
     p.Ly = c->Ly;
     p.L = c->Lx * c->Ly;
-    p.x0 = c->lim[0];
-    p.y0 = c->lim[2];
+    pick_mapping(c->n, p.lpc, p.groups);
     const double dx = (c->lim[1] - c->lim[0]) / static_cast<double>(c->Lx - 1);
     const double dy = (c->lim[3] - c->lim[2]) / static_cast<double>(c->Ly - 1);
     p.inv_dx = 1.0 / dx;
     p.inv_dy = 1.0 / dy;
+    p.bias_x = -c->lim[0] * p.inv_dx;
+    p.bias_y = -c->lim[2] * p.inv_dy;
     p.zlow = c->lim[4];
     p.zup = c->lim[5];
     const long long grid = static_cast<long long>(K) * n_objs * B;

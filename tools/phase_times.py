@@ -1,0 +1,38 @@
+"""Per-phase clock64() timing of the fused Minkowski+sweep kernel (profiling aid, not a bench):
+    python tools/phase_times.py <f64|f64_strict|f32> <layers>"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from hrm_b200 import capi, workload as wl  # noqa: E402
+
+prec = {"f64": capi.F64, "f64_strict": capi.F64_STRICT, "f32": capi.F32}[sys.argv[1]]
+layers = int(sys.argv[2])
+ctx = capi.Context(0)
+lib = ctx.lib
+lib.hrmgpu_debug_phase_times.restype = C.c_longlong
+lib.hrmgpu_debug_phase_times.argtypes = [C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]
+rows = wl.scene_rows12()
+ctx.set_scene3d(1, wl.N_OBS, wl.scene_rows17(rows), wl.N_GRID)
+ctx.set_sweep(wl.LIM, wl.LX, wl.LY)
+R = wl.body_rotations(wl.orientations(layers))
+off = np.zeros((layers, 1, 3))
+n_cta = layers * (wl.N_OBS + 1)
+for rep in range(3):
+    if rep == 2:
+        lib.hrmgpu_debug_phase_times(ctx.h, 1, n_cta, None)
+    ctx.build_layers(np.array(wl.BODY_SEMI), R, off, prec)
+    print("rep", rep, "kernel ms", ctx.last_minksweep_ms())
+out = np.zeros((n_cta, 8), dtype=np.int64)
+lib.hrmgpu_debug_phase_times(ctx.h, 1, n_cta, out.ctypes.data_as(C.c_void_p))
+names = ["prologue", "phaseA(t0)", "scan+drain", "drain+commit", "phaseD", "rounds", "surface", "total"]
+arena = (np.arange(n_cta) % (wl.N_OBS + 1)) == 0
+for label, sel in (("obstacle CTAs", ~arena), ("arena CTAs", arena)):
+    print(label, sel.sum())
+    for i, nm in enumerate(names):
+        v = out[sel, i]
+        print("   %-13s mean %10.1f  p50 %10.1f  p99 %10.1f  max %10d" % (nm, v.mean(), np.percentile(v, 50), np.percentile(v, 99), v.max()))
+ctx.close()
