@@ -30,6 +30,21 @@ struct Fast {
     __device__ __forceinline__ static double mad(double a, double b, double c) { return fma(a, b, c); }
 };
 
+// Branch-free 1/sqrt(x) for normal positive x (fast modes only): hardware seed (MUFU.RSQ64H, ~2^-20) refined by two
+// Newton-Raphson steps y += 0.5*y*(1 - x*y^2) to ~1 ulp.  Unlike ::rsqrt() it contains no special-case branch, so the
+// compiler can interleave several independent evaluations.  x = 0 / inf / NaN propagate to inf / 0 / NaN like 1/sqrt.
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const double t = x * y;
+        const double e = fma(-t, y, 1.0);
+        y = fma(0.5 * y, e, y);
+    }
+    return y;
+}
+
 struct D3 {
     double x, y, z;
 };

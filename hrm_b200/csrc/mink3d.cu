@@ -70,15 +70,25 @@ __device__ __noinline__ uint32_t line_code_slow(double x, const double* ts, int 
     const uint32_t eq = (ts[i + 1] == x) ? 1u : 0u;
     return 2u * static_cast<uint32_t>(i) + eq;
 }
-__device__ __forceinline__ uint32_t line_code(double x, const double* ts, int Lc, double inv_d, double bias) {
+// Fast part only: returns the code and sets ok = false when the exact search is required.
+__device__ __forceinline__ uint32_t line_code_fast(double x, int Lc, double inv_d, double bias, bool& ok) {
     const double g = fma(x, inv_d, bias);
     const double kMagic = 6755399441055744.0;  // 1.5 * 2^52: low word of (g + magic) = rint(g)
     const double t = g + kMagic;
     const int rn = __double2loint(t);
     const double diff = g - (t - kMagic);  // in [-0.5, 0.5]
     const int i = rn + ((diff > 0.0) ? 1 : 0);
-    if (!(fabs(diff) > 1e-6) || !(fabs(g) < 1e9)) return line_code_slow(x, ts, Lc, (g > 0.0) ? ((g < 1e9) ? i : Lc) : 0);
+    ok = (fabs(diff) > 1e-6) && (fabs(g) < 1e9);
     return 2u * static_cast<uint32_t>(min(max(i, 0), Lc));
+}
+__device__ __forceinline__ uint32_t line_code(double x, const double* ts, int Lc, double inv_d, double bias) {
+    bool ok;
+    const uint32_t c = line_code_fast(x, Lc, inv_d, bias, ok);
+    if (!ok) {
+        const double g = fma(x, inv_d, bias);
+        return line_code_slow(x, ts, Lc, (g > 0.0) ? ((g < 1e9) ? static_cast<int>(c >> 1) : Lc) : 0);
+    }
+    return c;
 }
 
 template <int MODE>
@@ -114,8 +124,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_minksweep3d(const MinkParams p)
     // ---- shared memory carve-up (every region 16-byte aligned) ------------------------------
     Real* tab = reinterpret_cast<Real*>(smem_raw);                       // [8][n]
     size_t ofs = (sizeof(Real) * 8 * n + 15) & ~size_t(15);
-    double* mats = reinterpret_cast<double*>(smem_raw + ofs);            // M1[9] M2[9]
-    ofs += sizeof(double) * 18;
+    double* mats = reinterpret_cast<double*>(smem_raw + ofs);            // M1[9] M2[9] + scratch T[9] KTT[9]
+    ofs += sizeof(double) * 36;
     double* txs = reinterpret_cast<double*>(smem_raw + ofs);             // [Lx+2]
     double* tys = txs + (SWEEP ? p.Lx + 2 : 0);                           // [Ly+2]
     ofs += SWEEP ? ((sizeof(double) * (p.Lx + p.Ly + 4) + 15) & ~size_t(15)) : 0;
@@ -143,37 +153,29 @@ __global__ void __launch_bounds__(kThreads, 2) k_minksweep3d(const MinkParams p)
         if (tid == 0) *qcount = 0;
     }
     const Obj3& ob = p.obj[obj_id];
-    if (tid == 0) {
+    if (tid < 32) {
         // Tinv = (R2 * diag) * R2^T ;  M1 = Tinv * R1 ;  M2 = ((K * Tinv) * Tinv) * R1
-        // (SuperQuadrics.cpp:115,137-140), evaluated in the reference's association order.
-        double R2[9], T[9], R1[9];
+        // (SuperQuadrics.cpp:115,137-140), each entry evaluated in the reference's association order by its own
+        // lane (9 lanes, three dependent steps through shared memory instead of ~90 serial FP64 operations).
+        double* Ts = mats + 18;   // scratch: T[9], KTT[9]
+        const int e = tid < 9 ? tid : 0;
+        const int i = e / 3, j = e - 3 * i;
         const double* r2 = p.R + (static_cast<size_t>(k) * p.B + b) * 9;
-#pragma unroll
-        for (int i = 0; i < 9; ++i) R2[i] = __ldg(r2 + i), R1[i] = __ldg(&ob.R[i]);
         const double d0 = __ldg(p.semi + 3 * b), d1 = __ldg(p.semi + 3 * b + 1), d2 = __ldg(p.semi + 3 * b + 2);
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j)
-                T[3 * i + j] = A::mad(A::mul(R2[3 * i + 2], d2), R2[3 * j + 2],
-                                      A::mad(A::mul(R2[3 * i + 1], d1), R2[3 * j + 1], A::mul(A::mul(R2[3 * i], d0), R2[3 * j])));
         const double sign = __ldg(&ob.sign);
-        double KT[9], KTT[9];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) KT[i] = A::mul(sign, T[i]);
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j)
-                KTT[3 * i + j] = A::mad(KT[3 * i + 2], T[6 + j], A::mad(KT[3 * i + 1], T[3 + j], A::mul(KT[3 * i], T[j])));
-        if (tid == 0) {
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    mats[3 * i + j] = A::mad(T[3 * i + 2], R1[6 + j], A::mad(T[3 * i + 1], R1[3 + j], A::mul(T[3 * i], R1[j])));
-                    mats[9 + 3 * i + j] = A::mad(KTT[3 * i + 2], R1[6 + j], A::mad(KTT[3 * i + 1], R1[3 + j], A::mul(KTT[3 * i], R1[j])));
-                }
+        const double t = A::mad(A::mul(__ldg(r2 + 3 * i + 2), d2), __ldg(r2 + 3 * j + 2),
+                                A::mad(A::mul(__ldg(r2 + 3 * i + 1), d1), __ldg(r2 + 3 * j + 1),
+                                       A::mul(A::mul(__ldg(r2 + 3 * i), d0), __ldg(r2 + 3 * j))));
+        if (tid < 9) Ts[e] = t;
+        __syncwarp();
+        const double ktt = A::mad(A::mul(sign, Ts[3 * i + 2]), Ts[6 + j],
+                                  A::mad(A::mul(sign, Ts[3 * i + 1]), Ts[3 + j], A::mul(A::mul(sign, Ts[3 * i]), Ts[j])));
+        if (tid < 9) Ts[9 + e] = ktt;
+        __syncwarp();
+        const double r1a = __ldg(&ob.R[j]), r1b = __ldg(&ob.R[3 + j]), r1c = __ldg(&ob.R[6 + j]);
+        if (tid < 9) {
+            mats[e] = A::mad(Ts[3 * i + 2], r1c, A::mad(Ts[3 * i + 1], r1b, A::mul(Ts[3 * i], r1a)));
+            mats[9 + e] = A::mad(Ts[9 + 3 * i + 2], r1c, A::mad(Ts[9 + 3 * i + 1], r1b, A::mul(Ts[9 + 3 * i], r1a)));
         }
     }
     const double offx = __ldg(p.off + (static_cast<size_t>(k) * p.B + b) * 3);
@@ -259,12 +261,15 @@ __global__ void __launch_bounds__(kThreads, 2) k_minksweep3d(const MinkParams p)
                         W3[i] = Real(mats[9 + 3 * i + 2]) * gc;
                     }
                 }
-                // two rows per iteration: independent dependency chains for the FP64 pipe
-                for (int r = ln; r < n; r += 2 * p.lpc) {
-                    Real o[2][3];
-                    int rr[2] = {r, (r + p.lpc < n) ? r + p.lpc : r};
+                // kRows rows per iteration: independent dependency chains for the FP64 pipe
+                constexpr int kRows = 4;
+                for (int r = ln; r < n; r += kRows * p.lpc) {
+                    Real o[kRows][3];
+                    int rr[kRows];
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
+                    for (int h = 0; h < kRows; ++h) rr[h] = (r + h * p.lpc < n) ? r + h * p.lpc : r;
+#pragma unroll
+                    for (int h = 0; h < kRows; ++h) {
                         const Real cw1 = tab[4 * n + rr[h]], sw1 = tab[5 * n + rr[h]], cw2 = tab[6 * n + rr[h]], sw2 = tab[7 * n + rr[h]];
                         const Real ux = U1[0] * cw2 + (U2[0] * sw2 + U3[0]);
                         const Real uy = U1[1] * cw2 + (U2[1] * sw2 + U3[1]);
@@ -273,23 +278,38 @@ __global__ void __launch_bounds__(kThreads, 2) k_minksweep3d(const MinkParams p)
                         if constexpr (MODE == HRMGPU_F32)
                             inv = rsqrtf(ux * ux + uy * uy + uz * uz);
                         else
-                            inv = rsqrt(ux * ux + uy * uy + uz * uz);
+                            inv = fast_rsqrt(ux * ux + uy * uy + uz * uz);
                         o[h][0] = (W1[0] * cw2 + (W2[0] * sw2 + W3[0])) * inv + (P[0] * cw1 + (Q[0] * sw1 + C[0]));
                         o[h][1] = (W1[1] * cw2 + (W2[1] * sw2 + W3[1])) * inv + (P[1] * cw1 + (Q[1] * sw1 + C[1]));
                         o[h][2] = (W1[2] * cw2 + (W2[2] * sw2 + W3[2])) * inv + (P[2] * cw1 + (Q[2] * sw1 + C[2]));
                     }
+                    uint32_t code[kRows];
+                    bool all_ok = true;
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        if (h == 1 && rr[1] == r) break;
-                        const int kk = c * n + rr[h];
+                    for (int h = 0; h < kRows; ++h) {
+                        const int kk = c * n + rr[h];  // rows past the end alias row r and rewrite the same values
                         mx[kk] = o[h][0];
                         my[kk] = o[h][1];
                         mz[kk] = o[h][2];
                         if (SWEEP) {
-                            const uint32_t cx = line_code(static_cast<double>(o[h][0]), txs, p.Lx, p.inv_dx, p.bias_x);
-                            const uint32_t cy = line_code(static_cast<double>(o[h][1]), tys, p.Ly, p.inv_dy, p.bias_y);
-                            vcode[kk] = cx | (cy << 16);
+                            bool okx, oky;
+                            const uint32_t cx = line_code_fast(static_cast<double>(o[h][0]), p.Lx, p.inv_dx, p.bias_x, okx);
+                            const uint32_t cy = line_code_fast(static_cast<double>(o[h][1]), p.Ly, p.inv_dy, p.bias_y, oky);
+                            code[h] = cx | (cy << 16);
+                            all_ok = all_ok && okx && oky;
                         }
+                    }
+                    if (SWEEP) {
+                        if (!all_ok) {  // rare: some coordinate within rounding distance of a sweep line -> exact search
+#pragma unroll
+                            for (int h = 0; h < kRows; ++h) {
+                                const uint32_t cx = line_code(static_cast<double>(o[h][0]), txs, p.Lx, p.inv_dx, p.bias_x);
+                                const uint32_t cy = line_code(static_cast<double>(o[h][1]), tys, p.Ly, p.inv_dy, p.bias_y);
+                                code[h] = cx | (cy << 16);
+                            }
+                        }
+#pragma unroll
+                        for (int h = 0; h < kRows; ++h) vcode[c * n + rr[h]] = code[h];
                     }
                 }
             }
@@ -322,54 +342,89 @@ __global__ void __launch_bounds__(kThreads, 2) k_minksweep3d(const MinkParams p)
     // commits the per-line two lowest hit faces with their z, and resumes scanning.
     const int nc1 = n - 1;
     const int ncell = nc1 * nc1;
-    int si = grp, sj = ln, shalf = 0;          // scan position: cell (si, sj), face half
-    uint32_t six = 0, siy = 0;                  // next line of the current face to push (absolute indices)
-    bool face_open = false;                    // (six, siy) valid for the current face
-    uint32_t f_lox = 0, f_loy = 0, f_hix = 0, f_hiy = 0;
-    bool scanning = worker && si < nc1 && sj < nc1;
+    // Every thread owns the cells (i, j) = (grp + groups*s, ln + lpc*t), enumerated ci = s*Tn + t, in chunks of 16
+    // cells (32 faces).  B1 builds a register bitmask of the faces that survive the quick reject with independent
+    // loads; B2 expands the few set bits into queue entries.
+    const int Tn = (nc1 + p.lpc - 1) / p.lpc;
+    const int Sn = (nc1 + p.groups - 1) / p.groups;
+    const int ncell_t = worker ? Sn * Tn : 0;
+    int chunk = 0;
+    uint32_t mask = 0;
+    bool have_mask = false;
+    uint32_t six = 0, siy = 0;                  // next line of the open face to push
+    bool face_open = false;
+    uint32_t f_lox = 0, f_loy = 0, f_hix = 0, f_hiy = 0, f_id = 0;
+    bool scanning = ncell_t > 0;
     for (;;) {
         while (scanning) {
-            if (!face_open) {
-                const int q = si * n + sj;
-                const uint32_t c00 = vcode[q], c11 = vcode[q + n + 1];
-                const uint32_t cm = shalf ? vcode[q + 1] : vcode[q + n];
-                // quick reject (the common case): all three vertices in the same grid cell and none on a line
-                if (!((c00 == c11) && (c00 == cm) && ((c00 & 0x00010001u) == 0u))) {
+            if (!have_mask) {
+                if (chunk * 16 >= ncell_t) {
+                    scanning = false;
+                    break;
+                }
+                mask = 0;
+                int ci = chunk * 16;
+                int s_ = ci / Tn, t_ = ci - s_ * Tn;
+#pragma unroll 4
+                for (int u = 0; u < 16; ++u) {
+                    const int i = grp + p.groups * s_, j = ln + p.lpc * t_;
+                    const bool valid = (ci + u < ncell_t) && (i < nc1) && (j < nc1);
+                    const int q = valid ? i * n + j : 0;
+                    const uint32_t c00 = vcode[q], c01 = vcode[q + 1], c10 = vcode[q + n], c11 = vcode[q + n + 1];
+                    // exact emptiness test of both faces' line sets, branch free.  Per axis with mn = min code,
+                    // mx = max code (code = 2*lo + eq): lines [mn>>1, (mx+1)>>1) is non-empty  <=>  (mx & 1) || (mn|1) < mx.
+                    const uint32_t dmin = __vminu2(c00, c11), dmax = __vmaxu2(c00, c11);
+                    const uint32_t mnA = __vminu2(dmin, c10), mxA = __vmaxu2(dmax, c10);
+                    const uint32_t mnB = __vminu2(dmin, c01), mxB = __vmaxu2(dmax, c01);
+                    // per 16-bit half: bit 15 of ((mx | 0x8000) - (mn | 1) - 1) is set  <=>  (mn | 1) < mx  (codes < 2^15)
+                    const uint32_t dA = (mxA | 0x80008000u) - (mnA | 0x00010001u) - 0x00010001u;
+                    const uint32_t dB = (mxB | 0x80008000u) - (mnB | 0x00010001u) - 0x00010001u;
+                    const uint32_t keepA = (valid && ((((dA >> 15) | mxA) & 0x00010001u) == 0x00010001u)) ? 1u : 0u;
+                    const uint32_t keepB = (valid && ((((dB >> 15) | mxB) & 0x00010001u) == 0x00010001u)) ? 1u : 0u;
+                    mask |= (keepA | (keepB << 1)) << (2 * u);
+                    if (++t_ == Tn) t_ = 0, ++s_;
+                }
+                have_mask = true;
+            }
+            bool full = false;
+            while (mask) {
+                if (!face_open) {
+                    const int bpos = __ffs(mask) - 1;
+                    const int ci = chunk * 16 + (bpos >> 1), half = bpos & 1;
+                    const int s_ = ci / Tn, t_ = ci - s_ * Tn;
+                    const int i = grp + p.groups * s_, j = ln + p.lpc * t_;
+                    const int q = i * n + j;
+                    const uint32_t c00 = vcode[q], c11 = vcode[q + n + 1];
+                    const uint32_t cm = half ? vcode[q + 1] : vcode[q + n];
                     const uint32_t mn = __vminu2(__vminu2(c00, c11), cm), mxx = __vmaxu2(__vmaxu2(c00, c11), cm);
                     // lo = min(2*lo+eq) >> 1 ; hi+1 = (max(2*lo+eq) + 1) >> 1  (per 16-bit half): lines [lo, hi)
                     const uint32_t lo2 = (mn >> 1) & 0x7FFF7FFFu;
                     const uint32_t hi2 = ((mxx + 0x00010001u) >> 1) & 0x7FFF7FFFu;
                     f_lox = lo2 & 0xFFFFu, f_loy = lo2 >> 16, f_hix = hi2 & 0xFFFFu, f_hiy = hi2 >> 16;
-                    if (f_lox < f_hix && f_loy < f_hiy) {
-                        six = f_lox, siy = f_loy;
-                        face_open = true;
+                    if (!(f_lox < f_hix && f_loy < f_hiy)) {
+                        mask &= mask - 1;
+                        continue;
                     }
+                    f_id = static_cast<uint32_t>(i * nc1 + j + (half ? ncell : 0));
+                    six = f_lox, siy = f_loy;
+                    face_open = true;
                 }
-            }
-            if (face_open) {
-                const uint32_t f = static_cast<uint32_t>(si * nc1 + sj + (shalf ? ncell : 0));
-                bool full = false;
                 while (six < f_hix) {
                     const int pos = atomicAdd(qcount, 1);
-                    if (pos >= static_cast<int>(kPosMask)) {  // slots 0..1022; 1023 is the 'committed' marker
+                    if (pos >= static_cast<int>(kPosMask)) {  // slots 0..kPosMask-1; kPosMask is the 'committed' marker
                         full = true;
                         break;
                     }
-                    queue[pos] = make_uint2(f, six | (siy << 16));
+                    queue[pos] = make_uint2(f_id, six | (siy << 16));
                     if (++siy == f_hiy) siy = f_loy, ++six;
                 }
                 if (full) break;  // park here; resume after the drain
                 face_open = false;
+                mask &= mask - 1;
             }
-            // next face / cell of this thread
-            if (shalf == 0) {
-                shalf = 1;
-            } else {
-                shalf = 0;
-                sj += p.lpc;
-                if (sj >= nc1) sj = ln, si += p.groups;
-                if (si >= nc1) scanning = false;
-            }
+            if (full) break;
+            have_mask = false;
+            ++chunk;
         }
         __syncwarp();  // the scan loop exits lane by lane: the drain below must run with full warps
         __syncthreads();
@@ -453,7 +508,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_minksweep3d(const MinkParams p)
 static size_t smem_bytes(int MODE, bool sweep, int n, int Lx, int Ly) {
     const size_t real = (MODE == HRMGPU_F32) ? 4 : 8;
     size_t b = (real * 8 * n + 15) & ~size_t(15);
-    b += sizeof(double) * 18;
+    b += sizeof(double) * 36;
     if (sweep) {
         b += (sizeof(double) * (Lx + Ly + 4) + 15) & ~size_t(15);
         b += sizeof(double) * kQueueCap + sizeof(uint2) * kQueueCap;
