@@ -263,3 +263,80 @@ def time_layers3d(n_arena, n_obs, sq, n, body_semi, body_quat, body_off, lim, Lx
     sec = lib().hrmo_time_layers3d(C.c_int(n_arena), C.c_int(n_obs), _p(sq), C.c_int(n), C.c_int(B), _p(body_semi), _p(body_quat),
                                    _p(body_off), _p(lim), C.c_int(Lx), C.c_int(Ly), C.c_int(K), C.c_int(threads), C.byref(cs))
     return sec, cs.value
+
+
+def _bounds_flat(bounds):
+    """list/array of dim x M boundaries -> contiguous [count][M][dim] (Eigen column-major per boundary)."""
+    arr = np.stack([np.asarray(b).T for b in bounds])
+    return np.ascontiguousarray(arr, dtype=np.float64)
+
+
+def edges3d(bounds, n, v1, v2):
+    """isSameSliceTransitionFree (HRM3D.cpp:319-365) of E segments against C-obstacle boundaries (each 3 x n^2)."""
+    b = _bounds_flat(bounds)
+    v1, v2 = _d(v1).reshape(-1, 3), _d(v2).reshape(-1, 3)
+    out = np.zeros(v1.shape[0], dtype=np.uint8)
+    lib().hrmo_edges3d.restype = C.c_long
+    single = lib().hrmo_edges3d(_p(b), C.c_int(n), C.c_int(b.shape[0]), C.c_int(v1.shape[0]), _p(v1), _p(v2), _p(out))
+    return out.astype(bool), single
+
+
+def edges2d(bounds, v1, v2):
+    b = _bounds_flat(bounds)
+    v1, v2 = _d(v1).reshape(-1, 2), _d(v2).reshape(-1, 2)
+    out = np.zeros(v1.shape[0], dtype=np.uint8)
+    lib().hrmo_edges2d(_p(b), C.c_int(b.shape[1]), C.c_int(b.shape[0]), C.c_int(v1.shape[0]), _p(v1), _p(v2), _p(out))
+    return out.astype(bool)
+
+
+def pt_in_cfree3d(bounds, n, pts):
+    b = _bounds_flat(bounds)
+    pts = _d(pts).reshape(-1, 3)
+    out = np.zeros(pts.shape[0], dtype=np.uint8)
+    lib().hrmo_pt_in_cfree3d.restype = C.c_long
+    single = lib().hrmo_pt_in_cfree3d(_p(b), C.c_int(n), C.c_int(b.shape[0]), C.c_int(pts.shape[0]), _p(pts), _p(out))
+    return out.astype(bool), single
+
+
+def pt_in_cfree2d(bounds, pts):
+    b = _bounds_flat(bounds)
+    pts = _d(pts).reshape(-1, 2)
+    out = np.zeros(pts.shape[0], dtype=np.uint8)
+    lib().hrmo_pt_in_cfree2d.restype = C.c_long
+    single = lib().hrmo_pt_in_cfree2d(_p(b), C.c_int(b.shape[1]), C.c_int(b.shape[0]), C.c_int(pts.shape[0]), _p(pts), _p(out))
+    return out.astype(bool), single
+
+
+def _plan_out(info, vertex, edge, path):
+    nv, ne, npth = int(info[1]), int(info[2]), int(info[3])
+    return {"solved": bool(info[0]), "vertex": vertex[:nv].copy(), "edge": edge[:ne].copy(), "path": path[:npth].copy(),
+            "single_hits": int(info[4]), "edge_tests": int(info[5])}
+
+
+def plan3d(n_arena, n_obs, sq, n, robot_rows, quats, lim, Lx, Ly, num_point, start, goal, per_orientation=False,
+           cap_v=1 << 18, cap_e=1 << 21):
+    sq, robot_rows, quats, lim, start, goal = _d(sq), _d(robot_rows), _d(quats), _d(lim), _d(start)[:7].copy(), _d(goal)[:7].copy()
+    info = np.zeros(8, dtype=np.int64)
+    vertex = np.zeros((cap_v, 7))
+    edge = np.zeros((cap_e, 2), dtype=np.int64)
+    path = np.zeros(cap_v, dtype=np.int64)
+    lib().hrmo_plan3d(C.c_int(n_arena), C.c_int(n_obs), _p(sq), C.c_int(n), C.c_int(robot_rows.shape[0]), _p(robot_rows),
+                      C.c_int(quats.shape[0]), _p(quats), _p(lim), C.c_int(Lx), C.c_int(Ly), C.c_int(num_point), _p(start), _p(goal),
+                      C.c_int(int(per_orientation)), _p(info), _p(vertex), C.c_long(cap_v), _p(edge), C.c_long(cap_e), _p(path),
+                      C.c_long(cap_v))
+    assert info[1] <= cap_v and info[2] <= cap_e
+    return _plan_out(info, vertex, edge, path)
+
+
+def plan2d(n_arena, n_obs, se, num, robot_rows, num_slice, lim, Ly, num_point, start, goal, per_orientation=False,
+           cap_v=1 << 16, cap_e=1 << 20):
+    se, robot_rows, lim, start, goal = _d(se), _d(robot_rows), _d(lim), _d(start)[:3].copy(), _d(goal)[:3].copy()
+    info = np.zeros(8, dtype=np.int64)
+    vertex = np.zeros((cap_v, 3))
+    edge = np.zeros((cap_e, 2), dtype=np.int64)
+    path = np.zeros(cap_v, dtype=np.int64)
+    lib().hrmo_plan2d(C.c_int(n_arena), C.c_int(n_obs), _p(se), C.c_int(num), C.c_int(robot_rows.shape[0]), _p(robot_rows),
+                      C.c_int(num_slice), _p(lim), C.c_int(Ly), C.c_int(num_point), _p(start), _p(goal), C.c_int(int(per_orientation)),
+                      _p(info), _p(vertex), C.c_long(cap_v), _p(edge), C.c_long(cap_e), _p(path), C.c_long(cap_v))
+    assert info[1] <= cap_v and info[2] <= cap_e
+    return _plan_out(info, vertex, edge, path)

@@ -6,6 +6,7 @@
 // [a,b,eps,px,py,angle]; surfaces are ordered j = object*B + body, arena objects first; sweep lines
 // are ordered l = ix*Ly + iy; boundaries are Eigen-layout 3 x M (2 x N) column-major.
 #include "hrmo_freespace.hpp"
+#include "hrmo_planner.hpp"
 
 #include <chrono>
 #include <cstring>
@@ -349,6 +350,127 @@ double hrmo_time_layers3d(int n_arena, int n_obs, const double* sq, int n, int B
     for (long v : sums) s += v;
     if (checksum) *checksum = s;
     return sec;
+}
+
+// ---- edge / bridge predicates ----------------------------------------------------------------------------------
+static std::vector<MeshMatrix> meshes_from(const double* bound, int n, int count) {
+    std::vector<MeshMatrix> out;
+    const int M = n * n;
+    for (int i = 0; i < count; ++i) {
+        Points p;
+        p.dim = 3, p.num = M;
+        p.p.assign(bound + static_cast<size_t>(i) * 3 * M, bound + static_cast<size_t>(i + 1) * 3 * M);
+        out.push_back(getMeshFromParamSurface(p, n));
+    }
+    return out;
+}
+static std::vector<Points> curves_from(const double* bound, int num, int count) {
+    std::vector<Points> out;
+    for (int i = 0; i < count; ++i) {
+        Points p;
+        p.dim = 2, p.num = num;
+        p.p.assign(bound + static_cast<size_t>(i) * 2 * num, bound + static_cast<size_t>(i + 1) * 2 * num);
+        out.push_back(std::move(p));
+    }
+    return out;
+}
+
+// isSameSliceTransitionFree for E segments against `count` C-obstacle boundaries ([count][M][3] Eigen layout).
+long hrmo_edges3d(const double* bound, int n, int count, int E, const double* v1, const double* v2, unsigned char* out) {
+    const auto meshes = meshes_from(bound, n, count);
+    long single = 0;
+    for (int e = 0; e < E; ++e) out[e] = isSameSliceTransitionFree3D(meshes, v1 + 3 * e, v2 + 3 * e, &single) ? 1 : 0;
+    return single;
+}
+void hrmo_edges2d(const double* bound, int num, int count, int E, const double* v1, const double* v2, unsigned char* out) {
+    const auto curves = curves_from(bound, num, count);
+    for (int e = 0; e < E; ++e) out[e] = isSameSliceTransitionFree2D(curves, v1 + 2 * e, v2 + 2 * e) ? 1 : 0;
+}
+// isPtInCFree of Q points against `count` bridge C-obstacle boundaries of one body.
+long hrmo_pt_in_cfree3d(const double* bound, int n, int count, int Q, const double* pts, unsigned char* out) {
+    const auto meshes = meshes_from(bound, n, count);
+    long single = 0;
+    for (int q = 0; q < Q; ++q) out[q] = isPtInCFree3D(meshes, pts + 3 * q, &single) ? 1 : 0;
+    return single;
+}
+long hrmo_pt_in_cfree2d(const double* bound, int num, int count, int Q, const double* pts, unsigned char* out) {
+    const auto curves = curves_from(bound, num, count);
+    long single = 0;
+    for (int q = 0; q < Q; ++q) out[q] = isPtInCFree2D(curves, pts + 2 * q, &single) ? 1 : 0;
+    return single;
+}
+
+// ---- planners ------------------------------------------------------------------------------------------------------
+// HRM3D::plan on a scene given as rows (arena first).  robot rows: base first, links relative to base.
+// quats [numSlice][4] (w,x,y,z).  lim[6], Lx, Ly, numPoint.  start/goal: 7 doubles (x,y,z,qw,qx,qy,qz).
+// per_orientation = 0 reproduces the reference snapshot (frozen FreeSpace robot copy).
+// out_info[8]: solved, n_vertex, n_edge, n_path, single_hits, n_edge_tests, -, -.   vertex [cap_v][7], edge [cap_e][2].
+int hrmo_plan3d(int n_arena, int n_obs, const double* sq, int n, int B, const double* robot, int numSlice, const double* quats,
+                const double lim[6], int Lx, int Ly, int numPoint, const double* start, const double* goal, int per_orientation,
+                long* out_info, double* vertex, long cap_v, long* edge, long cap_e, long* path, long cap_p) {
+    std::vector<SuperQuadrics> arena, obs;
+    for (int i = 0; i < n_arena; ++i) arena.push_back(make_sq(sq + 12 * i, n));
+    for (int i = 0; i < n_obs; ++i) obs.push_back(make_sq(sq + 12 * (n_arena + i), n));
+    MultiBodyTree3D rb;
+    rb.base = make_sq(robot, n);
+    for (int b = 1; b < B; ++b) rb.addBody(make_sq(robot + 12 * b, n));
+    std::vector<Quat> qs;
+    for (int i = 0; i < numSlice; ++i) qs.push_back(Quat{quats[4 * i], quats[4 * i + 1], quats[4 * i + 2], quats[4 * i + 3]});
+    PlanningRequest req;
+    req.parameters.boundaryLimits.assign(lim, lim + 6);
+    req.parameters.numSlice = static_cast<size_t>(numSlice);
+    req.parameters.numLineX = static_cast<size_t>(Lx);
+    req.parameters.numLineY = static_cast<size_t>(Ly);
+    req.parameters.numPoint = static_cast<size_t>(numPoint);
+    req.start.assign(start, start + 7);
+    req.goal.assign(goal, goal + 7);
+    HRM3D hrm(rb, arena, obs, req, qs, per_orientation != 0);
+    hrm.plan();
+    const auto& g = hrm.res_.graphStructure;
+    out_info[0] = hrm.res_.solved ? 1 : 0;
+    out_info[1] = static_cast<long>(g.vertex.size());
+    out_info[2] = static_cast<long>(g.edge.size());
+    out_info[3] = static_cast<long>(hrm.res_.PathId.size());
+    out_info[4] = hrm.singleHitCount;
+    out_info[5] = hrm.numEdgeTests;
+    for (size_t i = 0; i < g.vertex.size() && static_cast<long>(i) < cap_v; ++i)
+        for (int d = 0; d < 7; ++d) vertex[7 * i + d] = g.vertex[i][d];
+    for (size_t i = 0; i < g.edge.size() && static_cast<long>(i) < cap_e; ++i) edge[2 * i] = static_cast<long>(g.edge[i].first), edge[2 * i + 1] = static_cast<long>(g.edge[i].second);
+    for (size_t i = 0; i < hrm.res_.PathId.size() && static_cast<long>(i) < cap_p; ++i) path[i] = hrm.res_.PathId[i];
+    return 0;
+}
+
+// HRM2D::plan.  se rows [a,b,eps,px,py,angle]; lim[4]; start/goal: (x, y, theta).  vertex [cap_v][3].
+int hrmo_plan2d(int n_arena, int n_obs, const double* se, int num, int B, const double* robot, int numSlice, const double lim[4], int Ly,
+                int numPoint, const double* start, const double* goal, int per_orientation, long* out_info, double* vertex, long cap_v,
+                long* edge, long cap_e, long* path, long cap_p) {
+    std::vector<SuperEllipse> arena, obs;
+    for (int i = 0; i < n_arena; ++i) arena.push_back(make_se(se + 6 * i, num));
+    for (int i = 0; i < n_obs; ++i) obs.push_back(make_se(se + 6 * (n_arena + i), num));
+    MultiBodyTree2D rb;
+    rb.base = make_se(robot, num);
+    for (int b = 1; b < B; ++b) rb.addBody(make_se(robot + 6 * b, num));
+    PlanningRequest req;
+    req.parameters.boundaryLimits.assign(lim, lim + 4);
+    req.parameters.numSlice = static_cast<size_t>(numSlice);
+    req.parameters.numLineY = static_cast<size_t>(Ly);
+    req.parameters.numPoint = static_cast<size_t>(numPoint);
+    req.start.assign(start, start + 3);
+    req.goal.assign(goal, goal + 3);
+    HRM2D hrm(rb, arena, obs, req, per_orientation != 0);
+    hrm.plan();
+    const auto& g = hrm.res_.graphStructure;
+    out_info[0] = hrm.res_.solved ? 1 : 0;
+    out_info[1] = static_cast<long>(g.vertex.size());
+    out_info[2] = static_cast<long>(g.edge.size());
+    out_info[3] = static_cast<long>(hrm.res_.PathId.size());
+    out_info[4] = hrm.singleHitCount;
+    out_info[5] = hrm.numEdgeTests;
+    for (size_t i = 0; i < g.vertex.size() && static_cast<long>(i) < cap_v; ++i)
+        for (int d = 0; d < 3; ++d) vertex[3 * i + d] = g.vertex[i][d];
+    for (size_t i = 0; i < g.edge.size() && static_cast<long>(i) < cap_e; ++i) edge[2 * i] = static_cast<long>(g.edge[i].first), edge[2 * i + 1] = static_cast<long>(g.edge[i].second);
+    for (size_t i = 0; i < hrm.res_.PathId.size() && static_cast<long>(i) < cap_p; ++i) path[i] = hrm.res_.PathId[i];
+    return 0;
 }
 
 }  // extern "C"
