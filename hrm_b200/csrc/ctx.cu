@@ -135,6 +135,14 @@ void hrmgpu_destroy(hrmgpu_ctx* c) {
     release(c->counters);
     release(c->bridge_mesh);
     release(c->dbg);
+    release(c->q_a);
+    release(c->q_b);
+    release(c->q_out);
+    release(c->bbox);
+    release(c->q_flag);
+    release(c->bridge_semi);
+    release(c->bridge_R);
+    release(c->bridge_off);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -275,6 +283,158 @@ int hrmgpu_build_layers(hrmgpu_ctx* c, int K, int B, const double* semi, const d
     return hrmgpu_build_layers_dev(c, K, B, c->body_semi.p, c->body_R.p, c->body_off.p, precision);
 }
 
+int hrmgpu_set_scene2d(hrmgpu_ctx* c, int n_arena, int n_obs, const double* se, int num) {
+    if (!c) return HRMGPU_E_ARG;
+    if (n_arena < 0 || n_obs < 0 || n_arena + n_obs <= 0 || !se) return fail(c, HRMGPU_E_ARG, "set_scene2d: bad object counts");
+    if (num < 3 || num > 8192) return fail(c, HRMGPU_E_CAP, "set_scene2d: num must be in [3, 8192]");
+    HRMGPU_CUDA(c, cudaSetDevice(c->device));
+    const int S0 = n_arena + n_obs;
+    std::vector<Obj2> objs(static_cast<size_t>(S0));
+    std::vector<double> tab(static_cast<size_t>(S0) * 4 * num);
+    for (int i = 0; i < S0; ++i) {
+        const double* r = se + static_cast<size_t>(i) * 6;
+        Obj2& o = objs[i];
+        o.a = r[0], o.b = r[1], o.eps = r[2], o.px = r[3], o.py = r[4];
+        o.c1 = std::cos(r[5]);  // Eigen::Rotation2Dd(angle).matrix()
+        o.s1 = std::sin(r[5]);
+        o.sign = (i < n_arena) ? -1.0 : 1.0;
+        double* t = tab.data() + static_cast<size_t>(i) * 4 * num;
+        for (int j = 0; j < num; ++j) {
+            const double th = 2 * j * kPI / (static_cast<double>(num) - 1);  // reference src/geometry/SuperEllipse.cpp:40,89
+            t[0 * num + j] = power_fn(th, o.eps, false);
+            t[1 * num + j] = power_fn(th, o.eps, true);
+            t[2 * num + j] = power_fn(th, 2 - o.eps, false);
+            t[3 * num + j] = power_fn(th, 2 - o.eps, true);
+        }
+    }
+    int rc;
+    if ((rc = upload(c, c->obj2, objs.data(), objs.size()))) return rc;
+    if ((rc = upload(c, c->tab, tab.data(), tab.size()))) return rc;
+    HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->dim = 2;
+    c->n_arena = n_arena;
+    c->n_obs = n_obs;
+    c->n = num;
+    c->built = false;
+    c->bridge_built = false;
+    c->sweep_set = false;
+    return HRMGPU_OK;
+}
+
+int hrmgpu_build_layers2d(hrmgpu_ctx* c, int K, int B, const double* semi, const double* angle, const double* off, int precision) {
+    if (!c) return HRMGPU_E_ARG;
+    if (c->dim != 2) return fail(c, HRMGPU_E_STATE, "build_layers2d: no 2D scene set");
+    if (!c->sweep_set) return fail(c, HRMGPU_E_STATE, "build_layers2d: set_sweep first");
+    if (K < 0 || B < 1 || !semi || (K > 0 && (!angle || !off))) return fail(c, HRMGPU_E_ARG, "build_layers2d: bad arguments");
+    if (precision < HRMGPU_F64_STRICT || precision > HRMGPU_F32) return fail(c, HRMGPU_E_ARG, "build_layers2d: unknown precision");
+    if (precision == HRMGPU_F32) precision = HRMGPU_F64;  // the 2D path has no FP32 variant (it is tiny); FP64 fast math instead
+    HRMGPU_CUDA(c, cudaSetDevice(c->device));
+    std::vector<double> cs(static_cast<size_t>(K) * B * 2);
+    for (size_t i = 0; i < static_cast<size_t>(K) * B; ++i) cs[2 * i] = std::cos(angle[i]), cs[2 * i + 1] = std::sin(angle[i]);
+    int rc;
+    if ((rc = upload(c, c->body_semi, semi, static_cast<size_t>(B) * 2))) return rc;
+    if ((rc = upload(c, c->body_R, cs.data(), cs.size()))) return rc;
+    if ((rc = upload(c, c->body_off, off, static_cast<size_t>(K) * B * 2))) return rc;
+    const int S0 = c->n_arena + c->n_obs;
+    const int S = S0 * B, Sa = c->n_arena * B, L = c->Ly, M = c->n;
+    if ((rc = ensure(c, c->mesh, static_cast<size_t>(K) * S * 2 * M * 8))) return rc;
+    if ((rc = ensure(c, c->ivl_lo, static_cast<size_t>(K) * S * L))) return rc;
+    if ((rc = ensure(c, c->ivl_up, static_cast<size_t>(K) * S * L))) return rc;
+    HRMGPU_CUDA(c, cudaMemsetAsync(c->counters.p, 0, 4 * sizeof(unsigned long long), c->stream));
+    c->K = K, c->B = B, c->S = S, c->Sa = Sa, c->L = L, c->M = M, c->prec = precision;
+    c->built = false;
+    HRMGPU_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    if ((rc = launch_minksweep2d(c, K, B, 0, S0, c->body_semi.p, c->body_R.p, c->body_off.p, precision, c->mesh.p, c->ivl_lo.p,
+                                 c->ivl_up.p, true)))
+        return rc;
+    HRMGPU_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));  // cs goes out of scope
+    if ((rc = launch_segments(c))) return rc;
+    c->built = true;
+    return HRMGPU_OK;
+}
+
+int hrmgpu_test_edges(hrmgpu_ctx* c, int k, int E, const double* v1, const double* v2, unsigned char* free_out) {
+    if (!c) return HRMGPU_E_ARG;
+    int rc = check_built(c, k);
+    if (rc) return rc;
+    if (E < 0 || (E > 0 && (!v1 || !v2 || !free_out))) return fail(c, HRMGPU_E_ARG, "test_edges: bad arguments");
+    if (E == 0) return HRMGPU_OK;
+    HRMGPU_CUDA(c, cudaSetDevice(c->device));
+    const size_t cnt = static_cast<size_t>(E) * c->dim;
+    if ((rc = upload(c, c->q_a, v1, cnt))) return rc;
+    if ((rc = upload(c, c->q_b, v2, cnt))) return rc;
+    if ((rc = ensure(c, c->q_out, static_cast<size_t>(E)))) return rc;
+    if ((rc = launch_edges(c, k, E, c->q_a.p, c->q_b.p, c->q_out.p))) return rc;
+    HRMGPU_CUDA(c, cudaMemcpyAsync(free_out, c->q_out.p, static_cast<size_t>(E), cudaMemcpyDeviceToHost, c->stream));
+    HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));
+    return HRMGPU_OK;
+}
+
+static int build_bridge_common(hrmgpu_ctx* c, int P, int B, const double* semi, const double* rot, int precision, int dim) {
+    if (!c) return HRMGPU_E_ARG;
+    if (c->dim != dim) return fail(c, HRMGPU_E_STATE, "build_bridge: scene dimension mismatch");
+    if (P < 0 || B < 1 || (P > 0 && (!semi || !rot))) return fail(c, HRMGPU_E_ARG, "build_bridge: bad arguments");
+    if (precision < HRMGPU_F64_STRICT || precision > HRMGPU_F32) return fail(c, HRMGPU_E_ARG, "build_bridge: unknown precision");
+    if (dim == 2 && precision == HRMGPU_F32) precision = HRMGPU_F64;
+    HRMGPU_CUDA(c, cudaSetDevice(c->device));
+    const int M = (dim == 3) ? c->n * c->n : c->n;
+    const size_t real = (precision == HRMGPU_F32) ? 4 : 8;
+    int rc;
+    if ((rc = ensure(c, c->bridge_mesh, static_cast<size_t>(P) * c->n_obs * B * dim * M * real))) return rc;
+    // every pair has its own body shapes: launch one layer-batch per pair with that pair's semi-axes
+    std::vector<double> zeros(static_cast<size_t>(B) * dim, 0.0);
+    if ((rc = upload(c, c->bridge_off, zeros.data(), zeros.size()))) return rc;
+    if ((rc = upload(c, c->bridge_semi, semi, static_cast<size_t>(P) * B * dim))) return rc;
+    std::vector<double> cs;
+    if (dim == 3) {
+        if ((rc = upload(c, c->bridge_R, rot, static_cast<size_t>(P) * B * 9))) return rc;
+    } else {
+        cs.resize(static_cast<size_t>(P) * B * 2);
+        for (size_t i = 0; i < static_cast<size_t>(P) * B; ++i) cs[2 * i] = std::cos(rot[i]), cs[2 * i + 1] = std::sin(rot[i]);
+        if ((rc = upload(c, c->bridge_R, cs.data(), cs.size()))) return rc;
+    }
+    for (int pi = 0; pi < P; ++pi) {
+        char* mesh = c->bridge_mesh.p + static_cast<size_t>(pi) * c->n_obs * B * dim * M * real;
+        if (dim == 3)
+            rc = launch_minksweep3d(c, 1, B, c->n_arena, c->n_obs, c->bridge_semi.p + static_cast<size_t>(pi) * B * 3,
+                                    c->bridge_R.p + static_cast<size_t>(pi) * B * 9, c->bridge_off.p, precision, mesh, nullptr, nullptr, false);
+        else
+            rc = launch_minksweep2d(c, 1, B, c->n_arena, c->n_obs, c->bridge_semi.p + static_cast<size_t>(pi) * B * 2,
+                                    c->bridge_R.p + static_cast<size_t>(pi) * B * 2, c->bridge_off.p, precision, mesh, nullptr, nullptr, false);
+        if (rc) return rc;
+    }
+    HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->P = P;
+    c->bridge_B = B;
+    c->bridge_prec = precision;
+    c->bridge_built = true;
+    return HRMGPU_OK;
+}
+
+int hrmgpu_build_bridge(hrmgpu_ctx* c, int P, int B, const double* tfe_semi, const double* tfe_R, int precision) {
+    return build_bridge_common(c, P, B, tfe_semi, tfe_R, precision, 3);
+}
+int hrmgpu_build_bridge2d(hrmgpu_ctx* c, int P, int B, const double* tfe_semi, const double* tfe_angle, int precision) {
+    return build_bridge_common(c, P, B, tfe_semi, tfe_angle, precision, 2);
+}
+
+int hrmgpu_test_bridge(hrmgpu_ctx* c, int p, int Q, const double* centres, unsigned char* free_out) {
+    if (!c) return HRMGPU_E_ARG;
+    if (!c->bridge_built) return fail(c, HRMGPU_E_STATE, "test_bridge: no bridge layers built");
+    if (p < 0 || p >= c->P) return fail(c, HRMGPU_E_ARG, "test_bridge: pair index out of range");
+    if (Q < 0 || (Q > 0 && (!centres || !free_out))) return fail(c, HRMGPU_E_ARG, "test_bridge: bad arguments");
+    if (Q == 0) return HRMGPU_OK;
+    HRMGPU_CUDA(c, cudaSetDevice(c->device));
+    int rc;
+    if ((rc = upload(c, c->q_a, centres, static_cast<size_t>(Q) * c->bridge_B * c->dim))) return rc;
+    if ((rc = ensure(c, c->q_out, static_cast<size_t>(Q)))) return rc;
+    if ((rc = launch_bridge_test(c, p, Q, c->q_a.p, c->q_out.p))) return rc;
+    HRMGPU_CUDA(c, cudaMemcpyAsync(free_out, c->q_out.p, static_cast<size_t>(Q), cudaMemcpyDeviceToHost, c->stream));
+    HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));
+    return HRMGPU_OK;
+}
+
 int hrmgpu_get_dims(hrmgpu_ctx* c, long long* out) {
     if (!c || !out) return HRMGPU_E_ARG;
     if (!c->built) return fail(c, HRMGPU_E_STATE, "no layers built yet");
@@ -402,6 +562,14 @@ long long hrmgpu_debug_phase_times(hrmgpu_ctx* c, int enable, long long n_cta, l
     if (cudaSetDevice(c->device) != cudaSuccess) return HRMGPU_E_CUDA;
     if (!enable) {
         release(c->dbg);
+    release(c->q_a);
+    release(c->q_b);
+    release(c->q_out);
+    release(c->bbox);
+    release(c->q_flag);
+    release(c->bridge_semi);
+    release(c->bridge_R);
+    release(c->bridge_off);
         return 0;
     }
     if (out && c->dbg.p && c->dbg.n >= static_cast<size_t>(n_cta) * 8) {

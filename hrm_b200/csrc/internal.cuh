@@ -29,7 +29,8 @@ struct Obj3 {
 
 struct Obj2 {
     double a, b, eps;
-    double px, py, angle;
+    double px, py;
+    double c1, s1;  // cos / sin of the object's angle, evaluated on the host with libm like the reference
     double sign;
 };
 
@@ -63,6 +64,10 @@ struct Ctx {
     int K = 0, B = 0, S = 0, Sa = 0, L = 0, M = 0, prec = 0;
     bool built = false;
     DevBuf<double> body_semi, body_R, body_off;  // staged copies of host inputs
+    DevBuf<double> q_a, q_b;                     // staged query inputs (edge end points, body centres)
+    DevBuf<unsigned char> q_out;                 // staged query results
+    DevBuf<double> bbox;                         // [meshes][6] min/max per axis of the queried meshes
+    DevBuf<unsigned int> q_flag;                 // per-query blocked flags
     DevBuf<char> mesh;                           // [K][S][dim][M] planar, double (or float in F32 mode)
     DevBuf<double> ivl_lo, ivl_up;               // [K][S][L]
     DevBuf<double> orig;                         // [K][L][So+1][2] original (pre-enhancement) segments
@@ -78,7 +83,8 @@ struct Ctx {
     // bridge layers
     int P = 0, bridge_B = 0, bridge_prec = 0;
     bool bridge_built = false;
-    DevBuf<char> bridge_mesh;  // [P][B][n_obs][dim][M]
+    DevBuf<char> bridge_mesh;  // [P][n_obs][B][dim][M]
+    DevBuf<double> bridge_semi, bridge_R, bridge_off;
 };
 
 #define HRMGPU_CUDA(ctx, expr)                                                                        \
@@ -115,9 +121,7 @@ int launch_minksweep3d(Ctx* c, int K, int B, int n_first_obj, int n_objs, const 
 int launch_minksweep2d(Ctx* c, int K, int B, int n_first_obj, int n_objs, const double* d_semi, const double* d_angle,
                        const double* d_off, int precision, char* d_mesh, double* d_lo, double* d_up, bool do_sweep);
 int launch_segments(Ctx* c);
-int launch_edges3d(Ctx* c, int k, int E, const double* d_v1, const double* d_v2, unsigned char* d_out);
-int launch_edges2d(Ctx* c, int k, int E, const double* d_v1, const double* d_v2, unsigned char* d_out);
-int launch_bridge_test3d(Ctx* c, int p, int Q, const double* d_centres, unsigned char* d_out);
-int launch_bridge_test2d(Ctx* c, int p, int Q, const double* d_centres, unsigned char* d_out);
+int launch_edges(Ctx* c, int k, int E, const double* d_v1, const double* d_v2, unsigned char* d_out);
+int launch_bridge_test(Ctx* c, int p, int Q, const double* d_centres, unsigned char* d_out);
 
 }  // namespace hrmgpu

@@ -1,0 +1,350 @@
+// K4 (intra-layer edge tests) and K5 (bridge-layer point tests) against the meshes / curves a build left
+// resident in HBM.
+//
+// Replaces (reference):
+//   HRM3D::isSameSliceTransitionFree + intersectLineMesh3D       src/planners/HRM3D.cpp:319-365, LineIntersection.cpp:7-54
+//   HRM2D::isSameSliceTransitionFree + isIntersectSegPolygon2D   src/planners/HRM2D.cpp:215-232, LineIntersection.cpp:173-213
+//   HRM3D::isPtInCFree + intersectVerticalLineMesh3D             src/planners/HRM3D.cpp:394-425, LineIntersection.cpp:56-124
+//   HRM2D::isPtInCFree + intersectHorizontalLinePolygon2D        src/planners/HRM2D.cpp:267-282, LineIntersection.cpp:215-248
+//
+// 3D: one WARP per (query, mesh).  Lanes test 32 consecutive faces, a ballot orders the hits, and the walk stops as
+// soon as two hits exist in the scanned prefix -- exactly the reference's face-order loop with `break`.
+// 2D: one thread per (query, curve) walks the polygon edges in order.
+#include "devmath.cuh"
+#include "internal.cuh"
+
+namespace hrmgpu {
+
+// min / max of every coordinate row of `count` meshes (planar [dim][M]): the reference's maxCoeff()/minCoeff().
+template <class Real>
+__global__ void k_mesh_bbox(const Real* mesh, int dim, int M, double* bbox) {
+    const Real* m = mesh + static_cast<size_t>(blockIdx.x) * dim * M;
+    __shared__ double smin[3][32], smax[3][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int d = 0; d < dim; ++d) {
+        double mn = static_cast<double>(m[static_cast<size_t>(d) * M]), mx = mn;
+        for (int i = threadIdx.x; i < M; i += blockDim.x) {
+            const double v = static_cast<double>(m[static_cast<size_t>(d) * M + i]);
+            mn = (v < mn) ? v : mn;
+            mx = (v > mx) ? v : mx;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double a = __shfl_xor_sync(0xFFFFFFFFu, mn, o), b = __shfl_xor_sync(0xFFFFFFFFu, mx, o);
+            mn = (a < mn) ? a : mn;
+            mx = (b > mx) ? b : mx;
+        }
+        if (lane == 0) smin[d][warp] = mn, smax[d][warp] = mx;
+    }
+    __syncthreads();
+    if (threadIdx.x < dim) {
+        const int d = threadIdx.x;
+        double mn = smin[d][0], mx = smax[d][0];
+        for (int w = 1; w < static_cast<int>(blockDim.x >> 5); ++w) {
+            mn = (smin[d][w] < mn) ? smin[d][w] : mn;
+            mx = (smax[d][w] > mx) ? smax[d][w] : mx;
+        }
+        bbox[static_cast<size_t>(blockIdx.x) * 6 + 2 * d] = mn;
+        bbox[static_cast<size_t>(blockIdx.x) * 6 + 2 * d + 1] = mx;
+    }
+}
+
+// First two hits of line (o, d) on the implicit mesh in face order.  VERTICAL adds the inclusive per-face xy
+// bounding-box test of intersectVerticalLineMesh3D.  Returns the hit count (0..2); all lanes get h0, h1.
+template <class A, class Real, bool VERTICAL>
+__device__ __forceinline__ int warp_first_two_hits(const Real* mesh, int n, int M, const D3& o, const D3& d, D3& h0, D3& h1) {
+    const int lane = threadIdx.x & 31;
+    const int F = 2 * (n - 1) * (n - 1);
+    const Real* mx = mesh;
+    const Real* my = mesh + M;
+    const Real* mz = mesh + 2 * static_cast<size_t>(M);
+    int cnt = 0;
+    for (int base = 0; base < F && cnt < 2; base += 32) {
+        const int f = base + lane;
+        bool hit = false;
+        D3 pt = {0, 0, 0};
+        if (f < F) {
+            int v0, v1, v2;
+            face_vertices(f, n, v0, v1, v2);
+            const D3 t0 = {static_cast<double>(mx[v0]), static_cast<double>(my[v0]), static_cast<double>(mz[v0])};
+            const D3 t1 = {static_cast<double>(mx[v1]), static_cast<double>(my[v1]), static_cast<double>(mz[v1])};
+            const D3 t2 = {static_cast<double>(mx[v2]), static_cast<double>(my[v2]), static_cast<double>(mz[v2])};
+            bool skip = false;
+            if (VERTICAL) {  // LineIntersection.cpp:77-101
+                skip = (o.x < fmin(t0.x, fmin(t1.x, t2.x))) || (o.x > fmax(t0.x, fmax(t1.x, t2.x))) ||
+                       (o.y < fmin(t0.y, fmin(t1.y, t2.y))) || (o.y > fmax(t0.y, fmax(t1.y, t2.y)));
+            }
+            if (!skip) hit = line_triangle<A>(o, d, t0, t1, t2, pt);
+        }
+        unsigned bal = __ballot_sync(0xFFFFFFFFu, hit);
+        while (bal && cnt < 2) {
+            const int src = __ffs(bal) - 1;
+            const double x = __shfl_sync(0xFFFFFFFFu, pt.x, src), y = __shfl_sync(0xFFFFFFFFu, pt.y, src),
+                         z = __shfl_sync(0xFFFFFFFFu, pt.z, src);
+            if (cnt == 0) h0 = {x, y, z}; else h1 = {x, y, z};
+            ++cnt;
+            bal &= bal - 1;
+        }
+    }
+    return cnt;
+}
+
+struct QueryParams {
+    const void* mesh;      // first mesh of the queried set, planar [dim][M] each
+    const double* bbox;    // [n_mesh][6]
+    const double* a;       // edges: v1 [E][dim]; bridge: centres [Q][B][dim]
+    const double* b;       // edges: v2 [E][dim]
+    unsigned int* flag;    // [n_query] set to 1 when blocked
+    unsigned long long* counters;
+    int n, M, n_mesh, n_query, B, n_obs;
+};
+
+// ---- K4 3D ----
+template <class A, class Real>
+__global__ void __launch_bounds__(128) k_edges3d(const QueryParams p) {
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp_global >= p.n_query * p.n_mesh) return;
+    const int e = warp_global / p.n_mesh, m = warp_global - e * p.n_mesh;
+    const D3 t1 = {p.a[3 * e], p.a[3 * e + 1], p.a[3 * e + 2]};
+    const D3 t2 = {p.b[3 * e], p.b[3 * e + 1], p.b[3 * e + 2]};
+    D3 d = sub3<A>(t2, t1);                           // HRM3D.cpp:322-325
+    const double z = dot3<A>(d, d);
+    if (z > 0.0) {
+        const double s = A::sqrt(z);
+        d.x = A::div(d.x, s), d.y = A::div(d.y, s), d.z = A::div(d.z, s);
+    }
+    // LineIntersection.cpp:12-30: reject on the mesh bounding box only along (nearly) axis-parallel directions
+    const double* bb = p.bbox + static_cast<size_t>(m) * 6;
+    const double oc[3] = {t1.x, t1.y, t1.z}, dc[3] = {d.x, d.y, d.z};
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        if (fabs(dc[i]) < 1e-6 && (oc[i] > bb[2 * i + 1] || oc[i] < bb[2 * i])) return;
+    const Real* mesh = reinterpret_cast<const Real*>(p.mesh) + static_cast<size_t>(m) * 3 * p.M;
+    D3 h0, h1;
+    const int cnt = warp_first_two_hits<A, Real, false>(mesh, p.n, p.M, t1, d, h0, h1);
+    if (lane == 0) {
+        if (cnt == 2) {
+            const double s0 = dot3<A>(sub3<A>(h0, t1), sub3<A>(h0, t2));  // HRM3D.cpp:344-351
+            const double s1 = dot3<A>(sub3<A>(h1, t1), sub3<A>(h1, t2));
+            if ((s0 < 0) || (s1 < 0)) p.flag[e] = 1u;
+        } else if (cnt == 1) {
+            atomicAdd(p.counters + 2, 1ULL);  // single hit: reference reads out of bounds; defined as not blocking
+        }
+    }
+}
+
+// Explicit 2x2 column-pivoted QR solve standing in for Eigen's colPivHouseholderQr().solve() (LineIntersection.cpp:203).
+template <class A>
+__device__ __forceinline__ void solve2x2(const double Am[2][2], const double b[2], double sol[2]) {
+    const double n0 = A::mad(Am[1][0], Am[1][0], A::mul(Am[0][0], Am[0][0]));
+    const double n1 = A::mad(Am[1][1], Am[1][1], A::mul(Am[0][1], Am[0][1]));
+    const int p0 = (n1 > n0) ? 1 : 0, p1 = 1 - p0;
+    const double a0 = Am[0][p0], a1 = Am[1][p0], c0 = Am[0][p1], c1 = Am[1][p1];
+    const double nrm = A::sqrt(A::mad(a1, a1, A::mul(a0, a0)));
+    sol[0] = sol[1] = 0.0;
+    if (nrm == 0.0) return;
+    const double q0x = A::div(a0, nrm), q0y = A::div(a1, nrm);
+    const double r01 = A::mad(q0y, c1, A::mul(q0x, c0));
+    const double ex = A::sub(c0, A::mul(r01, q0x)), ey = A::sub(c1, A::mul(r01, q0y));
+    const double r11 = A::sqrt(A::mad(ey, ey, A::mul(ex, ex)));
+    const double y0 = A::mad(q0y, b[1], A::mul(q0x, b[0]));
+    const double thresh = A::mul(A::mul(2.220446049250313e-16, 2.0), nrm);
+    if (r11 <= thresh) {
+        sol[p0] = A::div(y0, nrm);
+        sol[p1] = 0.0;
+        return;
+    }
+    const double q1x = A::div(ex, r11), q1y = A::div(ey, r11);
+    const double y1 = A::mad(q1y, b[1], A::mul(q1x, b[0]));
+    const double x1 = A::div(y1, r11);
+    const double x0 = A::div(A::sub(y0, A::mul(r01, x1)), nrm);
+    sol[p0] = x0;
+    sol[p1] = x1;
+}
+
+// ---- K4 2D ----
+template <class A>
+__global__ void __launch_bounds__(128) k_edges2d(const QueryParams p) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.n_query * p.n_mesh) return;
+    const int e = t / p.n_mesh, m = t - e * p.n_mesh;
+    const double* sx = reinterpret_cast<const double*>(p.mesh) + static_cast<size_t>(m) * 2 * p.M;
+    const double* sy = sx + p.M;
+    const double px1 = p.a[2 * e], py1 = p.a[2 * e + 1], px2 = p.b[2 * e], py2 = p.b[2 * e + 1];
+    double Am[2][2], b[2], sol[2];
+    Am[0][0] = A::sub(px2, px1);
+    Am[1][0] = A::sub(py2, py1);
+    for (int i = 0; i < p.M; ++i) {
+        const int i2 = (i != p.M - 1) ? i + 1 : 0;
+        const double x1 = sx[i], y1 = sy[i], x2 = sx[i2], y2 = sy[i2];
+        Am[0][1] = A::sub(x1, x2);
+        Am[1][1] = A::sub(y1, y2);
+        b[0] = A::sub(x1, px1);
+        b[1] = A::sub(y1, py1);
+        solve2x2<A>(Am, b, sol);
+        if ((sol[0] > 0 && sol[0] < 1) && (sol[1] > 0 && sol[1] < 1)) {
+            p.flag[e] = 1u;
+            return;
+        }
+    }
+}
+
+// ---- K5 3D: warp per (pose q, body b, obstacle o); mesh of (o, b) = index o*B + b of the pair's bridge set ----
+template <class A, class Real>
+__global__ void __launch_bounds__(128) k_bridge3d(const QueryParams p) {
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int per_q = p.B * p.n_obs;
+    if (warp_global >= p.n_query * per_q) return;
+    const int q = warp_global / per_q, rem = warp_global - q * per_q;
+    const int b = rem / p.n_obs, o = rem - b * p.n_obs;
+    const double* v = p.a + (static_cast<size_t>(q) * p.B + b) * 3;
+    const D3 org = {v[0], v[1], v[2]};
+    const D3 dir = {0.0, 0.0, 1.0};
+    const Real* mesh = reinterpret_cast<const Real*>(p.mesh) + (static_cast<size_t>(o) * p.B + b) * 3 * p.M;
+    D3 h0, h1;
+    const int cnt = warp_first_two_hits<A, Real, true>(mesh, p.n, p.M, org, dir, h0, h1);
+    if (lane == 0) {
+        if (cnt == 2) {
+            if (org.z > fmin(h0.z, h1.z) && org.z < fmax(h0.z, h1.z)) p.flag[q] = 1u;  // HRM3D.cpp:409-413
+        } else if (cnt == 1) {
+            atomicAdd(p.counters + 3, 1ULL);
+        }
+    }
+}
+
+// ---- K5 2D: thread per (pose q, body b, obstacle o) ----
+template <class A>
+__global__ void __launch_bounds__(128) k_bridge2d(const QueryParams p) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int per_q = p.B * p.n_obs;
+    if (t >= p.n_query * per_q) return;
+    const int q = t / per_q, rem = t - q * per_q;
+    const int b = rem / p.n_obs, o = rem - b * p.n_obs;
+    const double* v = p.a + (static_cast<size_t>(q) * p.B + b) * 2;
+    const double* sx = reinterpret_cast<const double*>(p.mesh) + (static_cast<size_t>(o) * p.B + b) * 2 * p.M;
+    const double* sy = sx + p.M;
+    const double ty = v[1];
+    double h[2];
+    int cnt = 0;
+    for (int i = 0; i < p.M && cnt < 2; ++i) {
+        const int i2 = (i == p.M - 1) ? 0 : i + 1;
+        const double x1 = sx[i], y1 = sy[i], x2 = sx[i2], y2 = sy[i2];
+        if (ty >= fmin(y1, y2) && ty <= fmax(y1, y2)) {
+            const double tt = A::div(A::sub(ty, y2), A::sub(y1, y2));
+            if (tt >= 0.0 && tt <= 1.0) h[cnt++] = A::add(A::mul(tt, x1), A::mul(A::sub(1.0, tt), x2));
+        }
+    }
+    if (cnt == 2) {
+        if (v[0] > fmin(h[0], h[1]) && v[0] < fmax(h[0], h[1])) p.flag[q] = 1u;  // HRM2D.cpp:273-277
+    } else if (cnt == 1) {
+        atomicAdd(p.counters + 3, 1ULL);
+    }
+}
+
+__global__ void k_flags_to_free(const unsigned int* flag, unsigned char* out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = flag[i] ? 0 : 1;
+}
+
+static int finish_flags(Ctx* c, int n, unsigned char* d_out) {
+    k_flags_to_free<<<(n + 255) / 256, 256, 0, c->stream>>>(c->q_flag.p, d_out, n);
+    HRMGPU_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    return HRMGPU_OK;
+}
+
+int launch_edges(Ctx* c, int k, int E, const double* d_v1, const double* d_v2, unsigned char* d_out) {
+    const int So = c->S - c->Sa;
+    int rc;
+    if ((rc = ensure(c, c->q_flag, static_cast<size_t>(E)))) return rc;
+    HRMGPU_CUDA(c, cudaMemsetAsync(c->q_flag.p, 0, sizeof(unsigned int) * E, c->stream));
+    if (So > 0) {
+        QueryParams p;
+        p.a = d_v1;
+        p.b = d_v2;
+        p.flag = c->q_flag.p;
+        p.counters = c->counters.p;
+        p.n = c->n;
+        p.M = c->M;
+        p.n_mesh = So;
+        p.n_query = E;
+        p.B = c->B;
+        p.n_obs = c->n_obs;
+        const size_t real = (c->prec == HRMGPU_F32) ? 4 : 8;
+        const char* mesh = c->mesh.p + (static_cast<size_t>(k) * c->S + c->Sa) * c->dim * c->M * real;
+        p.mesh = mesh;
+        const long long work = static_cast<long long>(E) * So;
+        if (c->dim == 3) {
+            if ((rc = ensure(c, c->bbox, static_cast<size_t>(So) * 6))) return rc;
+            p.bbox = c->bbox.p;
+            if (c->prec == HRMGPU_F32)
+                k_mesh_bbox<float><<<So, 128, 0, c->stream>>>(reinterpret_cast<const float*>(mesh), 3, c->M, c->bbox.p);
+            else
+                k_mesh_bbox<double><<<So, 128, 0, c->stream>>>(reinterpret_cast<const double*>(mesh), 3, c->M, c->bbox.p);
+            HRMGPU_CUDA(c, cudaGetLastError());
+            const unsigned grid = static_cast<unsigned>((work * 32 + 127) / 128);
+            if (c->prec == HRMGPU_F64_STRICT)
+                k_edges3d<Strict, double><<<grid, 128, 0, c->stream>>>(p);
+            else if (c->prec == HRMGPU_F64)
+                k_edges3d<Fast, double><<<grid, 128, 0, c->stream>>>(p);
+            else
+                k_edges3d<Fast, float><<<grid, 128, 0, c->stream>>>(p);
+            c->launches += 2;
+        } else {
+            p.bbox = nullptr;
+            const unsigned grid = static_cast<unsigned>((work + 127) / 128);
+            if (c->prec == HRMGPU_F64_STRICT)
+                k_edges2d<Strict><<<grid, 128, 0, c->stream>>>(p);
+            else
+                k_edges2d<Fast><<<grid, 128, 0, c->stream>>>(p);
+            c->launches += 1;
+        }
+        HRMGPU_CUDA(c, cudaGetLastError());
+    }
+    return finish_flags(c, E, d_out);
+}
+
+int launch_bridge_test(Ctx* c, int pidx, int Q, const double* d_centres, unsigned char* d_out) {
+    int rc;
+    if ((rc = ensure(c, c->q_flag, static_cast<size_t>(Q)))) return rc;
+    HRMGPU_CUDA(c, cudaMemsetAsync(c->q_flag.p, 0, sizeof(unsigned int) * Q, c->stream));
+    if (c->n_obs > 0) {
+        QueryParams p;
+        p.a = d_centres;
+        p.b = nullptr;
+        p.bbox = nullptr;
+        p.flag = c->q_flag.p;
+        p.counters = c->counters.p;
+        p.n = c->n;
+        p.M = (c->dim == 3) ? c->n * c->n : c->n;
+        p.n_mesh = c->n_obs * c->bridge_B;
+        p.n_query = Q;
+        p.B = c->bridge_B;
+        p.n_obs = c->n_obs;
+        const size_t real = (c->bridge_prec == HRMGPU_F32) ? 4 : 8;
+        p.mesh = c->bridge_mesh.p + static_cast<size_t>(pidx) * c->n_obs * c->bridge_B * c->dim * p.M * real;
+        const long long work = static_cast<long long>(Q) * c->bridge_B * c->n_obs;
+        if (c->dim == 3) {
+            const unsigned grid = static_cast<unsigned>((work * 32 + 127) / 128);
+            if (c->bridge_prec == HRMGPU_F64_STRICT)
+                k_bridge3d<Strict, double><<<grid, 128, 0, c->stream>>>(p);
+            else if (c->bridge_prec == HRMGPU_F64)
+                k_bridge3d<Fast, double><<<grid, 128, 0, c->stream>>>(p);
+            else
+                k_bridge3d<Fast, float><<<grid, 128, 0, c->stream>>>(p);
+        } else {
+            const unsigned grid = static_cast<unsigned>((work + 127) / 128);
+            if (c->bridge_prec == HRMGPU_F64_STRICT)
+                k_bridge2d<Strict><<<grid, 128, 0, c->stream>>>(p);
+            else
+                k_bridge2d<Fast><<<grid, 128, 0, c->stream>>>(p);
+        }
+        HRMGPU_CUDA(c, cudaGetLastError());
+        c->launches += 1;
+    }
+    return finish_flags(c, Q, d_out);
+}
+
+}  // namespace hrmgpu

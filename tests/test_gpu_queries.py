@@ -1,0 +1,146 @@
+"""GPU parity of the intra-layer edge tests (K4) and the bridge-layer tests (K5) against the CPU oracle."""
+import numpy as np
+import pytest
+
+from hrm_b200 import capi
+from hrm_b200 import hostmath as hm
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def layer_vertices3d(sc, off, xM):
+    """(tx, ty, xM) of every free segment in (plane, line, segment) order (reference HRM3D.cpp:93-113)."""
+    lim, Lx, Ly = sc["lim"], sc["Lx"], sc["Ly"]
+    dx = (lim[1] - lim[0]) / float(Lx - 1)
+    dy = (lim[3] - lim[2]) / float(Ly - 1)
+    v = []
+    for ix in range(Lx):
+        for iy in range(Ly):
+            l = ix * Ly + iy
+            for j in range(off[l], off[l + 1]):
+                v.append([lim[0] + float(ix) * dx, lim[2] + float(iy) * dy, xM[j]])
+    return np.array(v)
+
+
+@pytest.mark.parametrize("name,n", [("3D_superquadrics_cluttered_rabbit", 10), ("3D_superquadrics_sparse_rabbit", 14)])
+def test_edges3d_match_oracle(oracle, gpu_ctx, name, n):
+    sc = util.scenes()[name]
+    rows = sc["arena"] + sc["obstacle"]
+    n_arena, n_obs = len(sc["arena"]), len(sc["obstacle"])
+    semi, R, off, quat = util.body_poses3d(sc["robot"], sc["quats"][:3])
+    gpu_ctx.set_scene3d(n_arena, n_obs, util.sq17(rows, n), n)
+    gpu_ctx.set_sweep(sc["lim"], sc["Lx"], sc["Ly"])
+    gpu_ctx.build_layers(semi, R, off, capi.F64_STRICT)
+    rng = np.random.default_rng(5)
+    B = semi.shape[0]
+    for k in range(3):
+        ref = oracle.layer3d(n_arena, n_obs, np.array(rows), n, semi, quat[k], off[k], sc["lim"], sc["Lx"], sc["Ly"])
+        o, xL, xU, xM = gpu_ctx.segments(k)
+        V = layer_vertices3d(sc, o, xM)
+        assert len(V) > 10
+        # all vertex pairs at distance <= 3 in the list + vertical detours (bridgeVertex) + random segments through the scene
+        i1 = rng.integers(0, len(V), 600)
+        i2 = np.clip(i1 + rng.integers(-12, 13, 600), 0, len(V) - 1)
+        v1, v2 = V[i1], V[i2]
+        det = v1.copy()
+        det[:, 2] = v2[:, 2]
+        lim = np.array(sc["lim"])
+        r1 = rng.uniform(lim[0::2], lim[1::2], size=(300, 3))
+        r2 = rng.uniform(lim[0::2], lim[1::2], size=(300, 3))
+        a = np.concatenate([v1, v1, det, r1, v1[:5]])
+        b = np.concatenate([v2, det, v2, r2, v1[:5]])
+        got = gpu_ctx.test_edges(k, a, b)
+        want, _ = oracle.edges3d(ref["bound"][n_arena * B:], n, a, b)
+        assert np.array_equal(got, want)
+        assert 0 < want.sum() < len(want)
+
+
+def test_edges2d_match_oracle(oracle, gpu_ctx):
+    sc = util.scenes()["2D_superellipse_cluttered_rabbit"]
+    rows = sc["arena"] + sc["obstacle"]
+    n_arena, n_obs = len(sc["arena"]), len(sc["obstacle"])
+    thetas = [-2.0, 0.3, 1.7]
+    semi, ang, off = util.body_poses2d(sc["robot"], thetas)
+    gpu_ctx.set_scene2d(n_arena, n_obs, np.array(rows), 50)
+    gpu_ctx.set_sweep(sc["lim"], 1, 12)
+    gpu_ctx.build_layers2d(semi, ang, off, capi.F64_STRICT)
+    rng = np.random.default_rng(11)
+    lim = np.array(sc["lim"])
+    B = semi.shape[0]
+    for k in range(3):
+        ref = oracle.layer2d(n_arena, n_obs, np.array(rows), 50, semi, ang[k], off[k], sc["lim"], 12)
+        a = rng.uniform(lim[0::2], lim[1::2], size=(500, 2))
+        b = a + rng.normal(scale=8.0, size=(500, 2))
+        got = gpu_ctx.test_edges(k, a, b)
+        want = oracle.edges2d(ref["bound"][n_arena * B:], a, b)
+        assert np.array_equal(got, want)
+        assert 0 < want.sum() < len(want)
+
+
+def test_bridge3d_match_oracle(oracle, gpu_ctx):
+    sc = util.scenes()["3D_superquadrics_cluttered_rabbit"]
+    rows = sc["arena"] + sc["obstacle"]
+    n_arena, n_obs = len(sc["arena"]), len(sc["obstacle"])
+    n = 10
+    rb = util.robot3d(sc["robot"])
+    semis = [rb.base.semiAxis] + [l.semiAxis for l in rb.link]
+    B = len(semis)
+    quats = sc["quats"]
+    pairs = [(1, 0), (2, 1), (7, 3)]
+    tfe_semi, tfe_R, tfe_q = [], [], []
+    for (i, j) in pairs:
+        ps, pr, pq = [], [], []
+        for b in range(B):
+            if b == 0:
+                qa, qb = quats[i], quats[j]
+            else:  # HRM3D.cpp:531-537: Quaterniond(q.toRotationMatrix() * rotLink)
+                Rl = rb.tf[b - 1][0]
+                qa = hm.rot_to_quat(hm.mat_mul(hm.quat_to_rot(quats[i]), Rl))
+                qb = hm.rot_to_quat(hm.mat_mul(hm.quat_to_rot(quats[j]), Rl))
+            t = oracle.tfe3d(semis[b], qa, qb, 5)  # TFE itself is host-side work (tiny SVDs)
+            ps.append(t[:3])
+            pq.append(t[3:])
+            pr.append(hm.flat9(hm.quat_to_rot(t[3:])))
+        tfe_semi.append(ps), tfe_R.append(pr), tfe_q.append(pq)
+    gpu_ctx.set_scene3d(n_arena, n_obs, util.sq17(rows, n), n)
+    gpu_ctx.build_bridge(np.array(tfe_semi), np.array(tfe_R), capi.F64_STRICT)
+    rng = np.random.default_rng(3)
+    lim = np.array(sc["lim"])
+    for p in range(len(pairs)):
+        Q = 400
+        centres = rng.uniform(lim[0::2] - 5, lim[1::2] + 5, size=(Q, B, 3))
+        got = gpu_ctx.test_bridge(p, centres)
+        want = np.ones(Q, dtype=bool)
+        for b in range(B):
+            bounds = [oracle.minksum3d(rows[n_arena + o], tfe_semi[p][b], tfe_q[p][b], n, +1) for o in range(n_obs)]
+            w, _ = oracle.pt_in_cfree3d(bounds, n, centres[:, b, :])
+            want &= w
+        assert np.array_equal(got, want)
+        assert 0 < want.sum() < Q
+
+
+def test_bridge2d_match_oracle(oracle, gpu_ctx):
+    sc = util.scenes()["2D_superellipse_cluttered_rabbit"]
+    rows = sc["arena"] + sc["obstacle"]
+    n_arena, n_obs = len(sc["arena"]), len(sc["obstacle"])
+    rb = util.robot2d(sc["robot"])
+    semis = [rb.base.semiAxis] + [l.semiAxis for l in rb.link]
+    B = len(semis)
+    tfe = [[oracle.tfe2d(semis[b], -1.0 + 0.2 * b, -0.4 + 0.2 * b, 5) for b in range(B)], [oracle.tfe2d(semis[b], 2.0, 2.6, 5) for b in range(B)]]
+    tfe = np.array(tfe)  # [P][B][3] = a, b, angle
+    gpu_ctx.set_scene2d(n_arena, n_obs, np.array(rows), 50)
+    gpu_ctx.build_bridge2d(tfe[:, :, :2], tfe[:, :, 2], capi.F64_STRICT)
+    rng = np.random.default_rng(9)
+    lim = np.array(sc["lim"])
+    for p in range(2):
+        Q = 500
+        centres = rng.uniform(lim[0::2], lim[1::2], size=(Q, B, 2))
+        got = gpu_ctx.test_bridge(p, centres)
+        want = np.ones(Q, dtype=bool)
+        for b in range(B):
+            bounds = [oracle.minksum2d(rows[n_arena + o], tfe[p, b, :2], tfe[p, b, 2], 50, +1) for o in range(n_obs)]
+            w, _ = oracle.pt_in_cfree2d(bounds, centres[:, b, :])
+            want &= w
+        assert np.array_equal(got, want)
+        assert 0 < want.sum() < Q
