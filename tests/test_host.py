@@ -1,0 +1,86 @@
+"""CPU-side tests: the C-ABI library loads and exports every declared symbol, fails loudly without a GPU, the host-side
+mirror classes produce the arrays the reference would hold, scene fixtures are what defineParameters gives."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from hrm_b200 import capi
+from hrm_b200 import hostmath as hm
+from hrm_b200 import workload as wl
+from tests import util
+
+
+def test_library_exports_every_declared_symbol():
+    lib = capi.load()
+    names = capi.declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), n
+    assert lib.hrmgpu_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    assert capi.load().hrmgpu_device_count() == 0
+    with pytest.raises(capi.HrmGpuError) as e:
+        capi.Context(0)
+    assert e.value.code == capi.E_NODEVICE
+
+
+def test_product_never_imports_the_oracle():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for dirpath, _, files in os.walk(os.path.join(root, "hrm_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                for pat in (r"^\s*(from|import)\s+oracle", r"#include\s*[\"<][^\n]*(oracle|hrmo_)", r"hrm_oracle", r"\bhrmo\b", r"libhrm_oracle"):
+                    assert not re.search(pat, txt, flags=re.M), (pat, os.path.join(dirpath, f))
+
+
+def test_hostmath_matches_oracle_bitwise(oracle):
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        q = util.f32round(rng.normal(size=4))
+        assert np.array_equal(np.array(hm.quat_to_rot(q)), oracle.quat_to_rot(q))
+        R = oracle.quat_to_rot(q / np.linalg.norm(q))
+        assert np.array_equal(np.array(hm.rot_to_quat(R.tolist())), oracle.rot_to_quat(R))
+    assert np.array_equal(np.array(hm.angle_axis_to_quat(0.7, [0.2, 0.4, -1.3])), oracle.angle_axis_to_quat(0.7, [0.2, 0.4, -1.3]))
+
+
+def test_multibody_poses_match_oracle(oracle):
+    sc = util.scenes()["3D_superquadrics_cluttered_rabbit"]
+    for q in sc["quats"][:10]:
+        semi, R, off, quat = util.body_poses3d(sc["robot"], [q])
+        bq, bo = oracle.robot3d_body_poses(np.array(sc["robot"]), q)
+        assert np.array_equal(quat[0], bq) and np.array_equal(off[0], bo)
+    sc = util.scenes()["2D_superellipse_sparse_rabbit"]
+    for th in (-3.1415926, -1.0, 0.0, 2.2):
+        semi, ang, off = util.body_poses2d(sc["robot"], [th])
+        ba, bo = oracle.robot2d_body_poses(np.array(sc["robot"]), th)
+        assert np.array_equal(ang[0], ba) and np.array_equal(off[0], bo)
+
+
+def test_scene_fixtures_follow_define_parameters():
+    S = util.scenes()
+    c = S["3D_superquadrics_cluttered_rabbit"]
+    assert c["lim"] == [-58.0, 58.0, -28.0, 28.0, -18.0, 18.0] and (c["Lx"], c["Ly"]) == (11, 5) and len(c["quats"]) == 60
+    assert len(c["arena"]) == 1 and len(c["obstacle"]) == 7 and len(c["robot"]) == 3
+    s = S["2D_superellipse_sparse_rabbit"]
+    assert s["lim"] == [-62.5, 62.5, -32.5, 32.5] and s["Ly"] == 3
+    # values went through stof: they are exactly representable as float32
+    a = np.array(c["obstacle"])
+    assert np.array_equal(a, a.astype(np.float32).astype(np.float64))
+
+
+def test_workload_is_seeded_and_float_rounded():
+    r1, r2 = wl.scene_rows12(50), wl.scene_rows12(50)
+    assert np.array_equal(r1, r2) and r1.shape == (51, 12)
+    assert np.array_equal(r1, r1.astype(np.float32).astype(np.float64))
+    assert wl.algorithmic_bytes_per_layer(1001, 10000, 512, 8) == 3 * 1001 * 10000 * 8 + 2 * 512 * 1001 * 8
+    r17 = wl.scene_rows17(r1)
+    assert r17.shape == (51, 17) and np.array_equal(r17[0, 8:], np.eye(3).ravel())
