@@ -1,0 +1,101 @@
+"""Planner-level parity on the reference's bundled maps: the GPU-backed HRM3D / HRM2D (hrm_b200/planner.py: K1-K5 on the
+GPU, host replay) must produce the SAME roadmap as the CPU oracle's restatement of the reference planners — identical
+vertex list (bit for bit in STRICT mode), identical edge list, identical planning success."""
+import numpy as np
+import pytest
+
+from hrm_b200 import capi
+from hrm_b200.planner import HRM2D, HRM3D, PlanningRequest
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def request3d(sc, num_point=5):
+    req = PlanningRequest()
+    req.start, req.goal = list(sc["end_points"][0][:7]), list(sc["end_points"][1][:7])
+    req.parameters.boundaryLimits = list(sc["lim"])
+    req.parameters.numLineX, req.parameters.numLineY = sc["Lx"], sc["Ly"]
+    req.parameters.numPoint = num_point
+    return req
+
+
+@pytest.mark.parametrize("name", ["3D_superquadrics_sparse_rabbit", "3D_superquadrics_cluttered_rabbit", "3D_superquadrics_maze_rabbit",
+                                  "3D_superquadrics_narrow_rabbit"])
+@pytest.mark.parametrize("per_orientation", [False, True])
+def test_hrm3d_roadmap_identical(oracle, gpu_ctx, name, per_orientation):
+    sc = util.scenes()[name]
+    n = 10
+    rows = np.array(sc["arena"] + sc["obstacle"])
+    ref = oracle.plan3d(len(sc["arena"]), len(sc["obstacle"]), rows, n, np.array(sc["robot"]), np.array(sc["quats"]), sc["lim"], sc["Lx"],
+                        sc["Ly"], 5, sc["end_points"][0], sc["end_points"][1], per_orientation=per_orientation)
+    hrm = HRM3D(util.robot3d(sc["robot"], n), util.sq_objects(sc["arena"], n), util.sq_objects(sc["obstacle"], n), request3d(sc),
+                sc["quats"], ctx=gpu_ctx, precision=capi.F64_STRICT, per_orientation=per_orientation)
+    hrm.plan()
+    res = hrm.getPlanningResult()
+    assert len(res.vertex) == len(ref["vertex"])
+    assert np.array_equal(np.array(res.vertex), ref["vertex"])
+    assert np.array_equal(np.array(res.edge, dtype=np.int64).reshape(-1, 2), ref["edge"])
+    assert res.solved == ref["solved"]
+    if ref["solved"]:
+        assert res.PathId[0] == ref["path"][0] and res.PathId[-1] == ref["path"][-1]
+    assert hrm.ctx.kernel_launches() > 0
+
+
+def test_hrm3d_home_map_first_layers(oracle, gpu_ctx):
+    """The 21-object home map (config 4 scene) restricted to 8 orientations to keep the oracle fast."""
+    sc = util.scenes()["3D_superquadrics_home_rabbit"]
+    n = 10
+    quats = sc["quats"][:8]
+    rows = np.array(sc["arena"] + sc["obstacle"])
+    ref = oracle.plan3d(1, len(sc["obstacle"]), rows, n, np.array(sc["robot"]), np.array(quats), sc["lim"], sc["Lx"], sc["Ly"], 5,
+                        sc["end_points"][0], sc["end_points"][1], per_orientation=True)
+    hrm = HRM3D(util.robot3d(sc["robot"], n), util.sq_objects(sc["arena"], n), util.sq_objects(sc["obstacle"], n), request3d(sc), quats,
+                ctx=gpu_ctx, precision=capi.F64_STRICT, per_orientation=True)
+    hrm.plan()
+    res = hrm.getPlanningResult()
+    assert np.array_equal(np.array(res.vertex), ref["vertex"])
+    assert np.array_equal(np.array(res.edge, dtype=np.int64).reshape(-1, 2), ref["edge"])
+    assert res.solved == ref["solved"]
+
+
+@pytest.mark.parametrize("name,Ly", [("2D_superellipse_sparse_rabbit", None), ("2D_superellipse_sparse_rabbit", 30),
+                                     ("2D_superellipse_cluttered_rabbit", 30), ("2D_superellipse_maze2_rabbit", 30),
+                                     ("2D_ellipse_sparse_rabbit", 20)])
+@pytest.mark.parametrize("per_orientation", [False, True])
+def test_hrm2d_roadmap_identical(oracle, gpu_ctx, name, Ly, per_orientation):
+    sc = util.scenes()[name]
+    Ly = Ly or sc["Ly"]
+    num, num_slice = 50, 10 if Ly < 10 else 20  # TestHRM2D.cpp: 50 / 10; README bench example: 20 slices, 30 lines
+    rows = np.array(sc["arena"] + sc["obstacle"])
+    ref = oracle.plan2d(len(sc["arena"]), len(sc["obstacle"]), rows, num, np.array(sc["robot"]), num_slice, sc["lim"], Ly, 5,
+                        sc["end_points"][0], sc["end_points"][1], per_orientation=per_orientation)
+    req = PlanningRequest()
+    req.start, req.goal = list(sc["end_points"][0]), list(sc["end_points"][1])
+    req.parameters.boundaryLimits = list(sc["lim"])
+    req.parameters.numLineY, req.parameters.numSlice, req.parameters.numPoint = Ly, num_slice, 5
+    hrm = HRM2D(util.robot2d(sc["robot"], num), util.se_objects(sc["arena"], num), util.se_objects(sc["obstacle"], num), req, ctx=gpu_ctx,
+                precision=capi.F64_STRICT, per_orientation=per_orientation)
+    hrm.plan()
+    res = hrm.getPlanningResult()
+    assert np.array_equal(np.array(res.vertex), ref["vertex"])
+    assert np.array_equal(np.array(res.edge, dtype=np.int64).reshape(-1, 2), ref["edge"])
+    assert res.solved == ref["solved"]
+
+
+def test_hrm3d_fast_mode_same_connectivity(oracle, gpu_ctx):
+    """The bench's arithmetic mode (FP64 with FMA) on the reference's TestHRM3D scene: same vertex count, same edges,
+    same success; vertices within 1e-6."""
+    sc = util.scenes()["3D_superquadrics_sparse_rabbit"]
+    n = 10
+    rows = np.array(sc["arena"] + sc["obstacle"])
+    ref = oracle.plan3d(1, len(sc["obstacle"]), rows, n, np.array(sc["robot"]), np.array(sc["quats"]), sc["lim"], sc["Lx"], sc["Ly"], 5,
+                        sc["end_points"][0], sc["end_points"][1], per_orientation=True)
+    hrm = HRM3D(util.robot3d(sc["robot"], n), util.sq_objects(sc["arena"], n), util.sq_objects(sc["obstacle"], n), request3d(sc),
+                sc["quats"], ctx=gpu_ctx, precision=capi.F64, per_orientation=True)
+    hrm.plan()
+    res = hrm.getPlanningResult()
+    assert len(res.vertex) == len(ref["vertex"])
+    assert np.max(np.abs(np.array(res.vertex) - ref["vertex"])) <= 1e-6
+    assert np.array_equal(np.array(res.edge, dtype=np.int64).reshape(-1, 2), ref["edge"])
+    assert res.solved == ref["solved"] is True
