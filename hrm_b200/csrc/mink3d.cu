@@ -71,14 +71,17 @@ __device__ __noinline__ uint32_t line_code_slow(double x, const double* ts, int 
     return 2u * static_cast<uint32_t>(i) + eq;
 }
 // Fast part only: returns the code and sets ok = false when the exact search is required.
+// g = (x - t_0) / d in line units is converted to Q11.20 fixed point by the magic-number addition (1.5 * 2^32: the low
+// word of the sum is rint(g * 2^20)); ceil, the "within 2^-17 of a grid line" test and the range test are then integer
+// operations, which keeps the FP64 pipe free for the boundary arithmetic.
 __device__ __forceinline__ uint32_t line_code_fast(double x, int Lc, double inv_d, double bias, bool& ok) {
     const double g = fma(x, inv_d, bias);
-    const double kMagic = 6755399441055744.0;  // 1.5 * 2^52: low word of (g + magic) = rint(g)
-    const double t = g + kMagic;
-    const int rn = __double2loint(t);
-    const double diff = g - (t - kMagic);  // in [-0.5, 0.5]
-    const int i = rn + ((diff > 0.0) ? 1 : 0);
-    ok = (fabs(diff) > 1e-6) && (fabs(g) < 1e9);
+    const double t = g + 6442450944.0;  // 1.5 * 2^32
+    const int fx = __double2loint(t);
+    const int i = (fx + 0xFFFFF) >> 20;                                   // ceil(g)
+    const unsigned fr = static_cast<unsigned>(fx + 8) & 0xFFFFFu;         // < 16  <=>  |g - rint(g)| <= 8 * 2^-20
+    const bool in_range = (__double2hiint(g) & 0x7FFFFFFF) < 0x40900000;  // |g| < 1024 (also rejects NaN / inf)
+    ok = (fr >= 16u) && in_range;
     return 2u * static_cast<uint32_t>(min(max(i, 0), Lc));
 }
 __device__ __forceinline__ uint32_t line_code(double x, const double* ts, int Lc, double inv_d, double bias) {
@@ -86,7 +89,7 @@ __device__ __forceinline__ uint32_t line_code(double x, const double* ts, int Lc
     const uint32_t c = line_code_fast(x, Lc, inv_d, bias, ok);
     if (!ok) {
         const double g = fma(x, inv_d, bias);
-        return line_code_slow(x, ts, Lc, (g > 0.0) ? ((g < 1e9) ? static_cast<int>(c >> 1) : Lc) : 0);
+        return line_code_slow(x, ts, Lc, (g > 0.0) ? ((g < 1000.0) ? static_cast<int>(c >> 1) : Lc) : 0);
     }
     return c;
 }
@@ -101,7 +104,7 @@ struct RealOf<HRMGPU_F32> {
 };
 
 template <int MODE, bool SWEEP>
-__global__ void __launch_bounds__(kThreads, 2) k_minksweep3d(const MinkParams p) {
+__global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F32 ? 3 : 2) k_minksweep3d(const MinkParams p) {
     using A = typename std::conditional<MODE == HRMGPU_F64_STRICT, Strict, Fast>::type;
     using Real = typename RealOf<MODE>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -118,7 +121,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_minksweep3d(const MinkParams p)
     const int ln = tid - grp * p.lpc;
     const bool worker = grp < p.groups;
 
-    long long t_start = 0, t_pro = 0, t_a = 0, t_scan = 0, t_drain = 0;
+    long long t_start = 0, t_pro = 0, t_a = 0, t_scan = 0, t_drain = 0, acc_b1 = 0, acc_b2 = 0;
+    __shared__ unsigned long long dbg_max[4];
+    if (threadIdx.x < 4) dbg_max[threadIdx.x] = 0;
     int rounds = 0;
     if (p.dbg) t_start = clock64();
     // ---- shared memory carve-up (every region 16-byte aligned) ------------------------------
@@ -134,7 +139,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_minksweep3d(const MinkParams p)
     uint2* queue = reinterpret_cast<uint2*>(smem_raw + ofs);             // [kQueueCap] (face, ix | iy << 16)
     ofs += SWEEP ? sizeof(uint2) * kQueueCap : 0;
     uint32_t* vcode = reinterpret_cast<uint32_t*>(smem_raw + ofs);       // [M]
-    ofs += SWEEP ? ((sizeof(uint32_t) * M + 15) & ~size_t(15)) : 0;
+    ofs += SWEEP ? ((sizeof(uint32_t) * (M + 4) + 15) & ~size_t(15)) : 0;  // +4: the 5th code of the last unit
     double* zc0 = reinterpret_cast<double*>(smem_raw + ofs);             // [L] committed z of the two lowest hit faces
     double* zc1 = zc0 + (SWEEP ? p.L : 0);                                // [L]
     ofs += SWEEP ? sizeof(double) * 2 * p.L : 0;
@@ -342,89 +347,128 @@ __global__ void __launch_bounds__(kThreads, 2) k_minksweep3d(const MinkParams p)
     // commits the per-line two lowest hit faces with their z, and resumes scanning.
     const int nc1 = n - 1;
     const int ncell = nc1 * nc1;
-    // Every thread owns the cells (i, j) = (grp + groups*s, ln + lpc*t), enumerated ci = s*Tn + t, in chunks of 16
-    // cells (32 faces).  B1 builds a register bitmask of the faces that survive the quick reject with independent
-    // loads; B2 expands the few set bits into queue entries.
-    const int Tn = (nc1 + p.lpc - 1) / p.lpc;
+    // Every thread owns units of 4 consecutive cells (i, j0..j0+3), i = grp + groups*s, j0 = 4*(ln + lpc*t), enumerated
+    // ui = s*Tn + t, in chunks of 4 units (16 cells, 32 faces).  B1 builds a register bitmask of the faces whose line set
+    // is non-empty (exact integer test on 128-bit loads of the vertex codes); B2 expands the few set bits into queue entries.
+    const int Tn = (nc1 + 4 * p.lpc - 1) / (4 * p.lpc);
     const int Sn = (nc1 + p.groups - 1) / p.groups;
-    const int ncell_t = worker ? Sn * Tn : 0;
+    const int nunit = Sn * Tn;  // the same for every thread, so the chunk loop below is warp-uniform
+    const bool vec_ok = (n & 3) == 0;
+    const int lane = tid & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
     int chunk = 0;
     uint32_t mask = 0;
     bool have_mask = false;
     uint32_t six = 0, siy = 0;                  // next line of the open face to push
     bool face_open = false;
     uint32_t f_lox = 0, f_loy = 0, f_hix = 0, f_hiy = 0, f_id = 0;
-    bool scanning = ncell_t > 0;
+    bool scanning = true;  // warp-uniform
     for (;;) {
         while (scanning) {
             if (!have_mask) {
-                if (chunk * 16 >= ncell_t) {
+                if (chunk * 4 >= nunit) {
                     scanning = false;
                     break;
                 }
+                long long tb = 0;
+                if (p.dbg) tb = clock64();
                 mask = 0;
-                int ci = chunk * 16;
-                int s_ = ci / Tn, t_ = ci - s_ * Tn;
-#pragma unroll 4
-                for (int u = 0; u < 16; ++u) {
-                    const int i = grp + p.groups * s_, j = ln + p.lpc * t_;
-                    const bool valid = (ci + u < ncell_t) && (i < nc1) && (j < nc1);
-                    const int q = valid ? i * n + j : 0;
-                    const uint32_t c00 = vcode[q], c01 = vcode[q + 1], c10 = vcode[q + n], c11 = vcode[q + n + 1];
-                    // exact emptiness test of both faces' line sets, branch free.  Per axis with mn = min code,
-                    // mx = max code (code = 2*lo + eq): lines [mn>>1, (mx+1)>>1) is non-empty  <=>  (mx & 1) || (mn|1) < mx.
-                    const uint32_t dmin = __vminu2(c00, c11), dmax = __vmaxu2(c00, c11);
-                    const uint32_t mnA = __vminu2(dmin, c10), mxA = __vmaxu2(dmax, c10);
-                    const uint32_t mnB = __vminu2(dmin, c01), mxB = __vmaxu2(dmax, c01);
-                    // per 16-bit half: bit 15 of ((mx | 0x8000) - (mn | 1) - 1) is set  <=>  (mn | 1) < mx  (codes < 2^15)
-                    const uint32_t dA = (mxA | 0x80008000u) - (mnA | 0x00010001u) - 0x00010001u;
-                    const uint32_t dB = (mxB | 0x80008000u) - (mnB | 0x00010001u) - 0x00010001u;
-                    const uint32_t keepA = (valid && ((((dA >> 15) | mxA) & 0x00010001u) == 0x00010001u)) ? 1u : 0u;
-                    const uint32_t keepB = (valid && ((((dB >> 15) | mxB) & 0x00010001u) == 0x00010001u)) ? 1u : 0u;
-                    mask |= (keepA | (keepB << 1)) << (2 * u);
+                const int ui0 = chunk * 4;
+                int s_ = ui0 / Tn, t_ = ui0 - s_ * Tn;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = grp + p.groups * s_, j0 = 4 * (ln + p.lpc * t_);
+                    const bool uvalid = worker && (ui0 + u < nunit) && (i < nc1) && (j0 < nc1);
+                    const int q = uvalid ? i * n + j0 : 0;
+                    uint32_t r0[5], r1[5];
+                    if (vec_ok) {
+                        const uint4 a = *reinterpret_cast<const uint4*>(vcode + q);
+                        const uint4 b = *reinterpret_cast<const uint4*>(vcode + q + n);
+                        r0[0] = a.x, r0[1] = a.y, r0[2] = a.z, r0[3] = a.w;
+                        r1[0] = b.x, r1[1] = b.y, r1[2] = b.z, r1[3] = b.w;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) r0[e] = vcode[q + e], r1[e] = vcode[q + n + e];
+                    }
+                    r0[4] = vcode[q + 4];
+                    r1[4] = vcode[q + n + 4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const bool valid = uvalid && (j0 + e < nc1);
+                        const uint32_t c00 = r0[e], c01 = r0[e + 1], c10 = r1[e], c11 = r1[e + 1];
+                        // exact emptiness test of both faces' line sets, branch free.  Per axis with mn = min code,
+                        // mx = max code (code = 2*lo + eq): lines [mn>>1, (mx+1)>>1) is non-empty  <=>  (mx & 1) || (mn|1) < mx.
+                        const uint32_t dmin = __vminu2(c00, c11), dmax = __vmaxu2(c00, c11);
+                        const uint32_t mnA = __vminu2(dmin, c10), mxA = __vmaxu2(dmax, c10);
+                        const uint32_t mnB = __vminu2(dmin, c01), mxB = __vmaxu2(dmax, c01);
+                        // per 16-bit half: bit 15 of ((mx | 0x8000) - (mn | 1) - 1) is set  <=>  (mn | 1) < mx  (codes < 2^15)
+                        const uint32_t dA = (mxA | 0x80008000u) - (mnA | 0x00010001u) - 0x00010001u;
+                        const uint32_t dB = (mxB | 0x80008000u) - (mnB | 0x00010001u) - 0x00010001u;
+                        const uint32_t keepA = (valid && ((((dA >> 15) | mxA) & 0x00010001u) == 0x00010001u)) ? 1u : 0u;
+                        const uint32_t keepB = (valid && ((((dB >> 15) | mxB) & 0x00010001u) == 0x00010001u)) ? 1u : 0u;
+                        mask |= (keepA | (keepB << 1)) << (8 * u + 2 * e);
+                    }
                     if (++t_ == Tn) t_ = 0, ++s_;
                 }
                 have_mask = true;
+                if (p.dbg) acc_b1 += clock64() - tb;
             }
-            bool full = false;
-            while (mask) {
-                if (!face_open) {
-                    const int bpos = __ffs(mask) - 1;
-                    const int ci = chunk * 16 + (bpos >> 1), half = bpos & 1;
-                    const int s_ = ci / Tn, t_ = ci - s_ * Tn;
-                    const int i = grp + p.groups * s_, j = ln + p.lpc * t_;
-                    const int q = i * n + j;
-                    const uint32_t c00 = vcode[q], c11 = vcode[q + n + 1];
-                    const uint32_t cm = half ? vcode[q + 1] : vcode[q + n];
-                    const uint32_t mn = __vminu2(__vminu2(c00, c11), cm), mxx = __vmaxu2(__vmaxu2(c00, c11), cm);
-                    // lo = min(2*lo+eq) >> 1 ; hi+1 = (max(2*lo+eq) + 1) >> 1  (per 16-bit half): lines [lo, hi)
-                    const uint32_t lo2 = (mn >> 1) & 0x7FFF7FFFu;
-                    const uint32_t hi2 = ((mxx + 0x00010001u) >> 1) & 0x7FFF7FFFu;
-                    f_lox = lo2 & 0xFFFFu, f_loy = lo2 >> 16, f_hix = hi2 & 0xFFFFu, f_hiy = hi2 >> 16;
-                    if (!(f_lox < f_hix && f_loy < f_hiy)) {
-                        mask &= mask - 1;
-                        continue;
-                    }
-                    f_id = static_cast<uint32_t>(i * nc1 + j + (half ? ncell : 0));
-                    six = f_lox, siy = f_loy;
-                    face_open = true;
-                }
-                while (six < f_hix) {
-                    const int pos = atomicAdd(qcount, 1);
-                    if (pos >= static_cast<int>(kPosMask)) {  // slots 0..kPosMask-1; kPosMask is the 'committed' marker
-                        full = true;
+            // B2, warp-aggregated: every iteration each lane offers at most one (face, line) candidate; one shared-memory
+            // atomic per warp reserves the queue slots (per-lane atomics on the single counter serialise badly).
+            long long tb2 = 0;
+            if (p.dbg) tb2 = clock64();
+            bool parked = false;
+            for (;;) {
+                if (!parked && !face_open) {
+                    while (mask) {
+                        const int bpos = __ffs(mask) - 1;
+                        const int ui = chunk * 4 + (bpos >> 3), half = bpos & 1;
+                        const int s_ = ui / Tn, t_ = ui - s_ * Tn;
+                        const int i = grp + p.groups * s_, j = 4 * (ln + p.lpc * t_) + ((bpos >> 1) & 3);
+                        const int q = i * n + j;
+                        const uint32_t c00 = vcode[q], c11 = vcode[q + n + 1];
+                        const uint32_t cm = half ? vcode[q + 1] : vcode[q + n];
+                        const uint32_t mn = __vminu2(__vminu2(c00, c11), cm), mxx = __vmaxu2(__vmaxu2(c00, c11), cm);
+                        // lo = min(2*lo+eq) >> 1 ; hi+1 = (max(2*lo+eq) + 1) >> 1  (per 16-bit half): lines [lo, hi)
+                        const uint32_t lo2 = (mn >> 1) & 0x7FFF7FFFu;
+                        const uint32_t hi2 = ((mxx + 0x00010001u) >> 1) & 0x7FFF7FFFu;
+                        f_lox = lo2 & 0xFFFFu, f_loy = lo2 >> 16, f_hix = hi2 & 0xFFFFu, f_hiy = hi2 >> 16;
+                        f_id = static_cast<uint32_t>(i * nc1 + j + (half ? ncell : 0));
+                        six = f_lox, siy = f_loy;
+                        face_open = true;  // B1's test is exact: the line set of a set bit is never empty
                         break;
                     }
-                    queue[pos] = make_uint2(f_id, six | (siy << 16));
-                    if (++siy == f_hiy) siy = f_loy, ++six;
                 }
-                if (full) break;  // park here; resume after the drain
-                face_open = false;
-                mask &= mask - 1;
+                const bool has = face_open && !parked;
+                const unsigned bal = __ballot_sync(0xFFFFFFFFu, has);
+                if (bal == 0u) break;
+                int base = 0;
+                const int leader = __ffs(bal) - 1;
+                if (lane == leader) base = atomicAdd(qcount, __popc(bal));
+                base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                if (has) {
+                    const int pos = base + __popc(bal & lt_mask);
+                    if (pos < static_cast<int>(kPosMask)) {  // slots 0..kPosMask-1; kPosMask is the 'committed' marker
+                        queue[pos] = make_uint2(f_id, six | (siy << 16));
+                        if (++siy == f_hiy) siy = f_loy, ++six;
+                        if (six >= f_hix) {
+                            face_open = false;
+                            mask &= mask - 1;
+                        }
+                    } else {
+                        parked = true;  // queue full: keep the position, resume after the drain
+                    }
+                }
             }
-            if (full) break;
+            if (p.dbg) acc_b2 += clock64() - tb2;
+            if (__any_sync(0xFFFFFFFFu, parked)) break;
             have_mask = false;
             ++chunk;
+        }
+        if (p.dbg && rounds == 0) {
+            atomicMax(&dbg_max[0], (unsigned long long)acc_b1);
+            atomicMax(&dbg_max[1], (unsigned long long)acc_b2);
+            atomicMax(&dbg_max[2], (unsigned long long)(clock64() - t_a));
         }
         __syncwarp();  // the scan loop exits lane by lane: the drain below must run with full warps
         __syncthreads();
@@ -498,9 +542,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_minksweep3d(const MinkParams p)
         d[1] = t_a - t_pro;          // phase A
         d[2] = t_scan - t_a;         // scan + drain + commit
         d[3] = t_drain;              // of which drain + commit
-        d[4] = clock64() - t_scan;   // phase D
+        d[4] = (long long)dbg_max[0];   // max over threads: B1 time in the first round
         d[5] = rounds;
-        d[6] = s;
+        d[6] = (long long)dbg_max[1];   // max over threads: B2 time in the first round
         d[7] = clock64() - t_start;
     }
 }
@@ -512,7 +556,7 @@ static size_t smem_bytes(int MODE, bool sweep, int n, int Lx, int Ly) {
     if (sweep) {
         b += (sizeof(double) * (Lx + Ly + 4) + 15) & ~size_t(15);
         b += sizeof(double) * kQueueCap + sizeof(uint2) * kQueueCap;
-        b += (sizeof(uint32_t) * static_cast<size_t>(n) * n + 15) & ~size_t(15);
+        b += (sizeof(uint32_t) * (static_cast<size_t>(n) * n + 4) + 15) & ~size_t(15);
         b += sizeof(double) * 2 * static_cast<size_t>(Lx) * Ly;
         b += (sizeof(uint32_t) * 2 * static_cast<size_t>(Lx) * Ly + 15) & ~size_t(15);
     }
