@@ -103,8 +103,17 @@ struct RealOf<HRMGPU_F32> {
     using type = float;
 };
 
-template <int MODE, bool SWEEP>
-__global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F32 ? 3 : 2) k_minksweep3d(const MinkParams p) {
+// Pair of Reals for 2-wide shared-memory loads of the per-column constants.
+template <class Real>
+struct alignas(2 * sizeof(Real)) Real2 {
+    Real a, b;
+};
+
+constexpr int kColStride = 30;  // Reals per column in the constant table: 3 groups (U, W, P) of 9 values + 1 pad
+
+template <int MODE, bool SWEEP, bool CODE8>
+__global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k_minksweep3d(const MinkParams p) {
+    using Code = typename std::conditional<CODE8, uint16_t, uint32_t>::type;  // packed line codes: 2 x 8 or 2 x 16 bits
     using A = typename std::conditional<MODE == HRMGPU_F64_STRICT, Strict, Fast>::type;
     using Real = typename RealOf<MODE>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -131,6 +140,8 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F32 ? 3 : 2) k_minksw
     size_t ofs = (sizeof(Real) * 8 * n + 15) & ~size_t(15);
     double* mats = reinterpret_cast<double*>(smem_raw + ofs);            // M1[9] M2[9] + scratch T[9] KTT[9]
     ofs += sizeof(double) * 36;
+    Real* cc = reinterpret_cast<Real*>(smem_raw + ofs);                  // [n][kColStride] per-column constants (fast modes)
+    ofs += (MODE != HRMGPU_F64_STRICT) ? ((sizeof(Real) * kColStride * n + 15) & ~size_t(15)) : 0;
     double* txs = reinterpret_cast<double*>(smem_raw + ofs);             // [Lx+2]
     double* tys = txs + (SWEEP ? p.Lx + 2 : 0);                           // [Ly+2]
     ofs += SWEEP ? ((sizeof(double) * (p.Lx + p.Ly + 4) + 15) & ~size_t(15)) : 0;
@@ -138,8 +149,11 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F32 ? 3 : 2) k_minksw
     ofs += SWEEP ? sizeof(double) * kQueueCap : 0;
     uint2* queue = reinterpret_cast<uint2*>(smem_raw + ofs);             // [kQueueCap] (face, ix | iy << 16)
     ofs += SWEEP ? sizeof(uint2) * kQueueCap : 0;
-    uint32_t* vcode = reinterpret_cast<uint32_t*>(smem_raw + ofs);       // [M]
-    ofs += SWEEP ? ((sizeof(uint32_t) * (M + 4) + 15) & ~size_t(15)) : 0;  // +4: the 5th code of the last unit
+    Code* vcode = reinterpret_cast<Code*>(smem_raw + ofs);               // [M]
+    ofs += SWEEP ? ((sizeof(Code) * (M + 8) + 15) & ~size_t(15)) : 0;    // +8: the 5th code of the last unit
+    auto pack_code = [](uint32_t cx, uint32_t cy) -> Code { return static_cast<Code>(CODE8 ? (cx | (cy << 8)) : (cx | (cy << 16))); };
+    // expanded form used by the SIMD min/max tests: x code in bits 0..15, y code in bits 16..31
+    auto code_at = [&](int q) -> uint32_t { return CODE8 ? __byte_perm(static_cast<uint32_t>(vcode[q]), 0u, 0x4140) : static_cast<uint32_t>(vcode[q]); };
     double* zc0 = reinterpret_cast<double*>(smem_raw + ofs);             // [L] committed z of the two lowest hit faces
     double* zc1 = zc0 + (SWEEP ? p.L : 0);                                // [L]
     ofs += SWEEP ? sizeof(double) * 2 * p.L : 0;
@@ -192,6 +206,31 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F32 ? 3 : 2) k_minksw
     Real* my = mesh + M;
     Real* mz = mesh + 2 * static_cast<size_t>(M);
     __syncthreads();
+    if constexpr (MODE != HRMGPU_F64_STRICT) {
+        // per-column constants: group U = M1 * diag(ga, gb, gc), group W = M2 * diag(..), group P = R1 * diag(A, B, Z) + shift
+        const Real oa = Real(__ldg(&ob.a)), obb = Real(__ldg(&ob.b)), oc = Real(__ldg(&ob.c));
+        const Real ia = Real(1) / oa, ib = Real(1) / obb, ic = Real(1) / oc;
+        const Real tr[3] = {Real(__ldg(&ob.px) - offx), Real(__ldg(&ob.py) - offy), Real(__ldg(&ob.pz) - offz)};
+        for (int c = tid; c < n; c += kThreads) {
+            const Real ce1 = tab[c], se1 = tab[n + c], ce2 = tab[2 * n + c], se2 = tab[3 * n + c];
+            const Real Ac = oa * ce1, Bc = obb * ce1, Zc = oc * se1;
+            const Real ga = ce2 * ia, gb = ce2 * ib, gc = se2 * ic;
+            Real* k = cc + c * kColStride;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                k[i] = Real(mats[3 * i]) * ga;
+                k[3 + i] = Real(mats[3 * i + 1]) * gb;
+                k[6 + i] = Real(mats[3 * i + 2]) * gc;
+                k[10 + i] = Real(mats[9 + 3 * i]) * ga;
+                k[13 + i] = Real(mats[9 + 3 * i + 1]) * gb;
+                k[16 + i] = Real(mats[9 + 3 * i + 2]) * gc;
+                k[20 + i] = Real(__ldg(&ob.R[3 * i])) * Ac;
+                k[23 + i] = Real(__ldg(&ob.R[3 * i + 1])) * Bc;
+                k[26 + i] = Real(__ldg(&ob.R[3 * i + 2])) * Zc + tr[i];
+            }
+        }
+        __syncthreads();
+    }
     if (p.dbg) t_pro = clock64();
 
     // ---- phase A: boundary points ---------------------------------------------------------
@@ -238,69 +277,93 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F32 ? 3 : 2) k_minksw
                     if (SWEEP) {
                         const uint32_t cx = line_code(ox, txs, p.Lx, p.inv_dx, p.bias_x);
                         const uint32_t cy = line_code(oy, tys, p.Ly, p.inv_dy, p.bias_y);
-                        vcode[kk] = cx | (cy << 16);
+                        vcode[kk] = pack_code(cx, cy);
                     }
                 }
             }
         } else {
-            // Fast variants: x = P*cw1 + Q*sw1 + C,  u = U1*cw2 + U2*sw2 + U3,  w = W1*cw2 + W2*sw2 + W3 with the
-            // nine 3-vectors depending on the column only; out = x + w * rsqrt(u.u).
-            const Real ia = Real(1) / Real(oa), ib = Real(1) / Real(obb), ic = Real(1) / Real(oc);
-            for (int c = grp; c < n; c += p.groups) {
-                Real P[3], Q[3], C[3], U1[3], U2[3], U3[3], W1[3], W2[3], W3[3];
-                {
-                    const Real ce1 = tab[c], se1 = tab[n + c], ce2 = tab[2 * n + c], se2 = tab[3 * n + c];
-                    const Real Ac = Real(oa) * ce1, Bc = Real(obb) * ce1, Zc = Real(oc) * se1;
-                    const Real ga = ce2 * ia, gb = ce2 * ib, gc = se2 * ic;
-                    const Real tr[3] = {Real(px - offx), Real(py - offy), Real(pz - offz)};
+            // Fast variants: x = P*cw1 + Q*sw1 + C,  u = U1*cw2 + U2*sw2 + U3,  w = W1*cw2 + W2*sw2 + W3 with the nine
+            // 3-vectors depending on the column only (table `cc`, built below); out = x + w * rsqrt(u.u).
+            // A thread keeps the omega-dependent factors of its rows in registers and streams the columns' constants from
+            // shared memory (all lanes of a group read the same address: broadcast), which keeps the register count low
+            // enough for 3 CTAs per SM.
+            using R2 = Real2<Real>;
+            constexpr int kRows = 2;
+            const int nh = (n + p.lpc - 1) / p.lpc;
+            for (int h0 = 0; h0 < nh; h0 += kRows) {
+                int rr[kRows];
+                bool rvalid[kRows];
+                Real cw1[kRows], sw1[kRows], cw2[kRows], sw2[kRows];
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        P[i] = Real(__ldg(&ob.R[3 * i])) * Ac;
-                        Q[i] = Real(__ldg(&ob.R[3 * i + 1])) * Bc;
-                        C[i] = Real(__ldg(&ob.R[3 * i + 2])) * Zc + tr[i];
-                        U1[i] = Real(mats[3 * i]) * ga;
-                        U2[i] = Real(mats[3 * i + 1]) * gb;
-                        U3[i] = Real(mats[3 * i + 2]) * gc;
-                        W1[i] = Real(mats[9 + 3 * i]) * ga;
-                        W2[i] = Real(mats[9 + 3 * i + 1]) * gb;
-                        W3[i] = Real(mats[9 + 3 * i + 2]) * gc;
-                    }
+                for (int h = 0; h < kRows; ++h) {
+                    const int r = ln + (h0 + h) * p.lpc;
+                    rvalid[h] = r < n;
+                    rr[h] = rvalid[h] ? r : ln;  // rows past the end compute the thread's first row again and store nothing
+                    cw1[h] = tab[4 * n + rr[h]], sw1[h] = tab[5 * n + rr[h]], cw2[h] = tab[6 * n + rr[h]], sw2[h] = tab[7 * n + rr[h]];
                 }
-                // kRows rows per iteration: independent dependency chains for the FP64 pipe
-                constexpr int kRows = 4;
-                for (int r = ln; r < n; r += kRows * p.lpc) {
-                    Real o[kRows][3];
-                    int rr[kRows];
+                for (int c = grp; c < n; c += p.groups) {
+                    const R2* k2 = reinterpret_cast<const R2*>(cc + c * kColStride);
+                    Real o[kRows][3], inv[kRows];
+                    {
+                        Real U[10];
 #pragma unroll
-                    for (int h = 0; h < kRows; ++h) rr[h] = (r + h * p.lpc < n) ? r + h * p.lpc : r;
+                        for (int i = 0; i < 5; ++i) {
+                            const R2 v = k2[i];
+                            U[2 * i] = v.a, U[2 * i + 1] = v.b;
+                        }
 #pragma unroll
-                    for (int h = 0; h < kRows; ++h) {
-                        const Real cw1 = tab[4 * n + rr[h]], sw1 = tab[5 * n + rr[h]], cw2 = tab[6 * n + rr[h]], sw2 = tab[7 * n + rr[h]];
-                        const Real ux = U1[0] * cw2 + (U2[0] * sw2 + U3[0]);
-                        const Real uy = U1[1] * cw2 + (U2[1] * sw2 + U3[1]);
-                        const Real uz = U1[2] * cw2 + (U2[2] * sw2 + U3[2]);
-                        Real inv;
-                        if constexpr (MODE == HRMGPU_F32)
-                            inv = rsqrtf(ux * ux + uy * uy + uz * uz);
-                        else
-                            inv = fast_rsqrt(ux * ux + uy * uy + uz * uz);
-                        o[h][0] = (W1[0] * cw2 + (W2[0] * sw2 + W3[0])) * inv + (P[0] * cw1 + (Q[0] * sw1 + C[0]));
-                        o[h][1] = (W1[1] * cw2 + (W2[1] * sw2 + W3[1])) * inv + (P[1] * cw1 + (Q[1] * sw1 + C[1]));
-                        o[h][2] = (W1[2] * cw2 + (W2[2] * sw2 + W3[2])) * inv + (P[2] * cw1 + (Q[2] * sw1 + C[2]));
+                        for (int h = 0; h < kRows; ++h) {
+                            const Real ux = U[0] * cw2[h] + (U[3] * sw2[h] + U[6]);
+                            const Real uy = U[1] * cw2[h] + (U[4] * sw2[h] + U[7]);
+                            const Real uz = U[2] * cw2[h] + (U[5] * sw2[h] + U[8]);
+                            if constexpr (MODE == HRMGPU_F32)
+                                inv[h] = rsqrtf(ux * ux + uy * uy + uz * uz);
+                            else
+                                inv[h] = fast_rsqrt(ux * ux + uy * uy + uz * uz);
+                        }
                     }
-                    uint32_t code[kRows];
+                    {
+                        Real W[10];
+#pragma unroll
+                        for (int i = 0; i < 5; ++i) {
+                            const R2 v = k2[5 + i];
+                            W[2 * i] = v.a, W[2 * i + 1] = v.b;
+                        }
+#pragma unroll
+                        for (int h = 0; h < kRows; ++h) {
+                            o[h][0] = (W[0] * cw2[h] + (W[3] * sw2[h] + W[6])) * inv[h];
+                            o[h][1] = (W[1] * cw2[h] + (W[4] * sw2[h] + W[7])) * inv[h];
+                            o[h][2] = (W[2] * cw2[h] + (W[5] * sw2[h] + W[8])) * inv[h];
+                        }
+                    }
+                    {
+                        Real P[10];
+#pragma unroll
+                        for (int i = 0; i < 5; ++i) {
+                            const R2 v = k2[10 + i];
+                            P[2 * i] = v.a, P[2 * i + 1] = v.b;
+                        }
+#pragma unroll
+                        for (int h = 0; h < kRows; ++h) {
+                            o[h][0] += P[0] * cw1[h] + (P[3] * sw1[h] + P[6]);
+                            o[h][1] += P[1] * cw1[h] + (P[4] * sw1[h] + P[7]);
+                            o[h][2] += P[2] * cw1[h] + (P[5] * sw1[h] + P[8]);
+                        }
+                    }
+                    uint32_t cx[kRows], cy[kRows];
                     bool all_ok = true;
 #pragma unroll
                     for (int h = 0; h < kRows; ++h) {
-                        const int kk = c * n + rr[h];  // rows past the end alias row r and rewrite the same values
-                        mx[kk] = o[h][0];
-                        my[kk] = o[h][1];
-                        mz[kk] = o[h][2];
+                        const int kk = c * n + rr[h];
+                        if (rvalid[h]) {
+                            mx[kk] = o[h][0];
+                            my[kk] = o[h][1];
+                            mz[kk] = o[h][2];
+                        }
                         if (SWEEP) {
                             bool okx, oky;
-                            const uint32_t cx = line_code_fast(static_cast<double>(o[h][0]), p.Lx, p.inv_dx, p.bias_x, okx);
-                            const uint32_t cy = line_code_fast(static_cast<double>(o[h][1]), p.Ly, p.inv_dy, p.bias_y, oky);
-                            code[h] = cx | (cy << 16);
+                            cx[h] = line_code_fast(static_cast<double>(o[h][0]), p.Lx, p.inv_dx, p.bias_x, okx);
+                            cy[h] = line_code_fast(static_cast<double>(o[h][1]), p.Ly, p.inv_dy, p.bias_y, oky);
                             all_ok = all_ok && okx && oky;
                         }
                     }
@@ -308,13 +371,13 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F32 ? 3 : 2) k_minksw
                         if (!all_ok) {  // rare: some coordinate within rounding distance of a sweep line -> exact search
 #pragma unroll
                             for (int h = 0; h < kRows; ++h) {
-                                const uint32_t cx = line_code(static_cast<double>(o[h][0]), txs, p.Lx, p.inv_dx, p.bias_x);
-                                const uint32_t cy = line_code(static_cast<double>(o[h][1]), tys, p.Ly, p.inv_dy, p.bias_y);
-                                code[h] = cx | (cy << 16);
+                                cx[h] = line_code(static_cast<double>(o[h][0]), txs, p.Lx, p.inv_dx, p.bias_x);
+                                cy[h] = line_code(static_cast<double>(o[h][1]), tys, p.Ly, p.inv_dy, p.bias_y);
                             }
                         }
 #pragma unroll
-                        for (int h = 0; h < kRows; ++h) vcode[c * n + rr[h]] = code[h];
+                        for (int h = 0; h < kRows; ++h)
+                            if (rvalid[h]) vcode[c * n + rr[h]] = pack_code(cx[h], cy[h]);
                     }
                 }
             }
@@ -381,17 +444,24 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F32 ? 3 : 2) k_minksw
                     const bool uvalid = worker && (ui0 + u < nunit) && (i < nc1) && (j0 < nc1);
                     const int q = uvalid ? i * n + j0 : 0;
                     uint32_t r0[5], r1[5];
-                    if (vec_ok) {
+                    if (vec_ok && !CODE8) {
                         const uint4 a = *reinterpret_cast<const uint4*>(vcode + q);
                         const uint4 b = *reinterpret_cast<const uint4*>(vcode + q + n);
                         r0[0] = a.x, r0[1] = a.y, r0[2] = a.z, r0[3] = a.w;
                         r1[0] = b.x, r1[1] = b.y, r1[2] = b.z, r1[3] = b.w;
+                    } else if (vec_ok) {  // four 2x8-bit codes per 64-bit load, expanded to the 2x16-bit SIMD form
+                        const uint2 a = *reinterpret_cast<const uint2*>(vcode + q);
+                        const uint2 b = *reinterpret_cast<const uint2*>(vcode + q + n);
+                        r0[0] = __byte_perm(a.x, 0u, 0x4140), r0[1] = __byte_perm(a.x, 0u, 0x4342);
+                        r0[2] = __byte_perm(a.y, 0u, 0x4140), r0[3] = __byte_perm(a.y, 0u, 0x4342);
+                        r1[0] = __byte_perm(b.x, 0u, 0x4140), r1[1] = __byte_perm(b.x, 0u, 0x4342);
+                        r1[2] = __byte_perm(b.y, 0u, 0x4140), r1[3] = __byte_perm(b.y, 0u, 0x4342);
                     } else {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) r0[e] = vcode[q + e], r1[e] = vcode[q + n + e];
+                        for (int e = 0; e < 4; ++e) r0[e] = code_at(q + e), r1[e] = code_at(q + n + e);
                     }
-                    r0[4] = vcode[q + 4];
-                    r1[4] = vcode[q + n + 4];
+                    r0[4] = code_at(q + 4);
+                    r1[4] = code_at(q + n + 4);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const bool valid = uvalid && (j0 + e < nc1);
@@ -426,8 +496,8 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F32 ? 3 : 2) k_minksw
                         const int s_ = ui / Tn, t_ = ui - s_ * Tn;
                         const int i = grp + p.groups * s_, j = 4 * (ln + p.lpc * t_) + ((bpos >> 1) & 3);
                         const int q = i * n + j;
-                        const uint32_t c00 = vcode[q], c11 = vcode[q + n + 1];
-                        const uint32_t cm = half ? vcode[q + 1] : vcode[q + n];
+                        const uint32_t c00 = code_at(q), c11 = code_at(q + n + 1);
+                        const uint32_t cm = half ? code_at(q + 1) : code_at(q + n);
                         const uint32_t mn = __vminu2(__vminu2(c00, c11), cm), mxx = __vmaxu2(__vmaxu2(c00, c11), cm);
                         // lo = min(2*lo+eq) >> 1 ; hi+1 = (max(2*lo+eq) + 1) >> 1  (per 16-bit half): lines [lo, hi)
                         const uint32_t lo2 = (mn >> 1) & 0x7FFF7FFFu;
@@ -549,14 +619,15 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F32 ? 3 : 2) k_minksw
     }
 }
 
-static size_t smem_bytes(int MODE, bool sweep, int n, int Lx, int Ly) {
+static size_t smem_bytes(int MODE, bool sweep, bool code8, int n, int Lx, int Ly) {
     const size_t real = (MODE == HRMGPU_F32) ? 4 : 8;
     size_t b = (real * 8 * n + 15) & ~size_t(15);
     b += sizeof(double) * 36;
+    if (MODE != HRMGPU_F64_STRICT) b += (real * kColStride * n + 15) & ~size_t(15);
     if (sweep) {
         b += (sizeof(double) * (Lx + Ly + 4) + 15) & ~size_t(15);
         b += sizeof(double) * kQueueCap + sizeof(uint2) * kQueueCap;
-        b += (sizeof(uint32_t) * (static_cast<size_t>(n) * n + 4) + 15) & ~size_t(15);
+        b += ((code8 ? 2 : 4) * (static_cast<size_t>(n) * n + 8) + 15) & ~size_t(15);
         b += sizeof(double) * 2 * static_cast<size_t>(Lx) * Ly;
         b += (sizeof(uint32_t) * 2 * static_cast<size_t>(Lx) * Ly + 15) & ~size_t(15);
     }
@@ -576,9 +647,9 @@ static void pick_mapping(int n, int& lpc, int& groups) {
     }
 }
 
-template <int MODE, bool SWEEP>
+template <int MODE, bool SWEEP, bool CODE8>
 static int launch_t(Ctx* c, const MinkParams& p, int grid, size_t smem) {
-    auto kern = k_minksweep3d<MODE, SWEEP>;
+    auto kern = k_minksweep3d<MODE, SWEEP, CODE8>;
     HRMGPU_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     kern<<<grid, kThreads, smem, c->stream>>>(p);
     HRMGPU_CUDA(c, cudaGetLastError());
@@ -621,19 +692,27 @@ int launch_minksweep3d(Ctx* c, int K, int B, int n_first_obj, int n_objs, const 
     const long long grid = static_cast<long long>(K) * n_objs * B;
     if (grid <= 0) return HRMGPU_OK;
     if (grid > 0x7FFFFFFFLL) return fail(c, HRMGPU_E_CAP, "K*S exceeds the CUDA grid limit");
-    const size_t smem = smem_bytes(precision, do_sweep, c->n, c->Lx, c->Ly);
+    // 2 x 8-bit vertex line codes when both axes have at most 127 lines (code = 2*lo + eq <= 255), else 2 x 16-bit
+    const bool code8 = do_sweep && c->Lx <= 127 && c->Ly <= 127;
+    const size_t smem = smem_bytes(precision, do_sweep, code8, c->n, c->Lx, c->Ly);
     if (smem > 227 * 1024) return fail(c, HRMGPU_E_CAP, "n_grid / sweep-line count need more than 227 KB of shared memory");
     const int g = static_cast<int>(grid);
+#define HRMGPU_LAUNCH3D(M_)                                                                      \
+    do {                                                                                         \
+        if (!do_sweep) return launch_t<M_, false, false>(c, p, g, smem);                         \
+        return code8 ? launch_t<M_, true, true>(c, p, g, smem) : launch_t<M_, true, false>(c, p, g, smem); \
+    } while (0)
     switch (precision) {
         case HRMGPU_F64_STRICT:
-            return do_sweep ? launch_t<HRMGPU_F64_STRICT, true>(c, p, g, smem) : launch_t<HRMGPU_F64_STRICT, false>(c, p, g, smem);
+            HRMGPU_LAUNCH3D(HRMGPU_F64_STRICT);
         case HRMGPU_F64:
-            return do_sweep ? launch_t<HRMGPU_F64, true>(c, p, g, smem) : launch_t<HRMGPU_F64, false>(c, p, g, smem);
+            HRMGPU_LAUNCH3D(HRMGPU_F64);
         case HRMGPU_F32:
-            return do_sweep ? launch_t<HRMGPU_F32, true>(c, p, g, smem) : launch_t<HRMGPU_F32, false>(c, p, g, smem);
+            HRMGPU_LAUNCH3D(HRMGPU_F32);
         default:
             return fail(c, HRMGPU_E_ARG, "unknown precision");
     }
+#undef HRMGPU_LAUNCH3D
 }
 
 }  // namespace hrmgpu
