@@ -82,7 +82,7 @@ __device__ __forceinline__ uint32_t line_code_fast(double x, int Lc, double inv_
     const unsigned fr = static_cast<unsigned>(fx + 8) & 0xFFFFFu;         // < 16  <=>  |g - rint(g)| <= 8 * 2^-20
     const bool in_range = (__double2hiint(g) & 0x7FFFFFFF) < 0x40900000;  // |g| < 1024 (also rejects NaN / inf)
     ok = (fr >= 16u) && in_range;
-    return 2u * static_cast<uint32_t>(min(max(i, 0), Lc));
+    return 2u * static_cast<uint32_t>(__vimin_s32_relu(i, Lc));  // clamp to [0, Lc]
 }
 __device__ __forceinline__ uint32_t line_code(double x, const double* ts, int Lc, double inv_d, double bias) {
     bool ok;
@@ -301,7 +301,9 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
                     rr[h] = rvalid[h] ? r : ln;  // rows past the end compute the thread's first row again and store nothing
                     cw1[h] = tab[4 * n + rr[h]], sw1[h] = tab[5 * n + rr[h]], cw2[h] = tab[6 * n + rr[h]], sw2[h] = tab[7 * n + rr[h]];
                 }
-                for (int c = grp; c < n; c += p.groups) {
+                int koff = grp * n;  // c * n
+                const int kstep = p.groups * n;
+                for (int c = grp; c < n; c += p.groups, koff += kstep) {
                     const R2* k2 = reinterpret_cast<const R2*>(cc + c * kColStride);
                     Real o[kRows][3], inv[kRows];
                     {
@@ -323,20 +325,6 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
                         }
                     }
                     {
-                        Real W[10];
-#pragma unroll
-                        for (int i = 0; i < 5; ++i) {
-                            const R2 v = k2[5 + i];
-                            W[2 * i] = v.a, W[2 * i + 1] = v.b;
-                        }
-#pragma unroll
-                        for (int h = 0; h < kRows; ++h) {
-                            o[h][0] = (W[0] * cw2[h] + (W[3] * sw2[h] + W[6])) * inv[h];
-                            o[h][1] = (W[1] * cw2[h] + (W[4] * sw2[h] + W[7])) * inv[h];
-                            o[h][2] = (W[2] * cw2[h] + (W[5] * sw2[h] + W[8])) * inv[h];
-                        }
-                    }
-                    {
                         Real P[10];
 #pragma unroll
                         for (int i = 0; i < 5; ++i) {
@@ -345,16 +333,30 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
                         }
 #pragma unroll
                         for (int h = 0; h < kRows; ++h) {
-                            o[h][0] += P[0] * cw1[h] + (P[3] * sw1[h] + P[6]);
-                            o[h][1] += P[1] * cw1[h] + (P[4] * sw1[h] + P[7]);
-                            o[h][2] += P[2] * cw1[h] + (P[5] * sw1[h] + P[8]);
+                            o[h][0] = P[0] * cw1[h] + (P[3] * sw1[h] + P[6]);
+                            o[h][1] = P[1] * cw1[h] + (P[4] * sw1[h] + P[7]);
+                            o[h][2] = P[2] * cw1[h] + (P[5] * sw1[h] + P[8]);
+                        }
+                    }
+                    {
+                        Real W[10];
+#pragma unroll
+                        for (int i = 0; i < 5; ++i) {
+                            const R2 v = k2[5 + i];
+                            W[2 * i] = v.a, W[2 * i + 1] = v.b;
+                        }
+#pragma unroll
+                        for (int h = 0; h < kRows; ++h) {
+                            o[h][0] = (W[0] * cw2[h] + (W[3] * sw2[h] + W[6])) * inv[h] + o[h][0];
+                            o[h][1] = (W[1] * cw2[h] + (W[4] * sw2[h] + W[7])) * inv[h] + o[h][1];
+                            o[h][2] = (W[2] * cw2[h] + (W[5] * sw2[h] + W[8])) * inv[h] + o[h][2];
                         }
                     }
                     uint32_t cx[kRows], cy[kRows];
                     bool all_ok = true;
 #pragma unroll
                     for (int h = 0; h < kRows; ++h) {
-                        const int kk = c * n + rr[h];
+                        const int kk = koff + rr[h];
                         if (rvalid[h]) {
                             mx[kk] = o[h][0];
                             my[kk] = o[h][1];
@@ -377,7 +379,7 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
                         }
 #pragma unroll
                         for (int h = 0; h < kRows; ++h)
-                            if (rvalid[h]) vcode[c * n + rr[h]] = pack_code(cx[h], cy[h]);
+                            if (rvalid[h]) vcode[koff + rr[h]] = pack_code(cx[h], cy[h]);
                     }
                 }
             }
@@ -417,6 +419,8 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
     const int Sn = (nc1 + p.groups - 1) / p.groups;
     const int nunit = Sn * Tn;  // the same for every thread, so the chunk loop below is warp-uniform
     const bool vec_ok = (n & 3) == 0;
+    // ui / Tn == umulhi(ui, magic) for ui < 2^16 and Tn >= 2 (Tn == 1, the common case, needs no division)
+    const uint32_t tn_magic = (Tn > 1) ? 0xFFFFFFFFu / static_cast<uint32_t>(Tn) + 1u : 0u;
     const int lane = tid & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     int chunk = 0;
@@ -493,7 +497,7 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
                     while (mask) {
                         const int bpos = __ffs(mask) - 1;
                         const int ui = chunk * 4 + (bpos >> 3), half = bpos & 1;
-                        const int s_ = ui / Tn, t_ = ui - s_ * Tn;
+                        const int s_ = (Tn > 1) ? static_cast<int>(__umulhi(static_cast<uint32_t>(ui), tn_magic)) : ui, t_ = ui - s_ * Tn;
                         const int i = grp + p.groups * s_, j = 4 * (ln + p.lpc * t_) + ((bpos >> 1) & 3);
                         const int q = i * n + j;
                         const uint32_t c00 = code_at(q), c11 = code_at(q + n + 1);
