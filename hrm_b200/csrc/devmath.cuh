@@ -102,6 +102,29 @@ __device__ __forceinline__ bool line_triangle(const D3& o, const D3& d, const D3
     return !((t < -tol) || (A::add(s, t) > 1.0 + tol));
 }
 
+// Fast-mode variant of the test above for a VERTICAL line through (x, y): for a non-degenerate triangle the 3D
+// barycentric coordinates of the plane intersection equal those of (x, y) in the projected triangle, so one division
+// (by the projected area n_z) replaces the normalisation, the plane solve and the two barycentric divisions.  Same
+// acceptance rule (tolerance 1e-12 on s, t, s+t; |n.d| / |n| > 1e-12); results differ from the reference only at
+// rounding level, i.e. decisions can differ only for lines within ~1e-12 of a triangle edge.  z = hit height.
+__device__ __forceinline__ bool vertical_hit_fast(double x, double y, const D3& t0, const D3& t1, const D3& t2, double& z) {
+    const double tol = 1e-12;
+    const double ux = t1.x - t0.x, uy = t1.y - t0.y, uz = t1.z - t0.z;
+    const double vx = t2.x - t0.x, vy = t2.y - t0.y, vz = t2.z - t0.z;
+    const double nz = ux * vy - uy * vx;
+    const double nx = uy * vz - uz * vy, ny = uz * vx - ux * vz;
+    const double nn = fma(nz, nz, fma(ny, ny, nx * nx));
+    if (!(nz * nz > (tol * tol) * nn)) return false;  // |b| = |n_z| / |n| > tol and |n| > 0
+    const double inv = 1.0 / nz;
+    const double px = x - t0.x, py = y - t0.y;
+    const double s = (px * vy - py * vx) * inv;
+    if ((s < -tol) || (s > 1.0 + tol)) return false;
+    const double t = (py * ux - px * uy) * inv;
+    if ((t < -tol) || (s + t > 1.0 + tol)) return false;
+    z = fma(t, vz, fma(s, uz, t0.z));
+    return true;
+}
+
 // Implicit mesh connectivity of getMeshFromParamSurface (reference src/geometry/MeshGenerator.cpp:105-131):
 // face f < F/2 : (q, q+n, q+n+1);  face f >= F/2 : (q, q+1, q+n+1), q = i*n + j, cell = i*(n-1)+j.
 __device__ __forceinline__ void face_vertices(int f, int n, int& v0, int& v1, int& v2) {

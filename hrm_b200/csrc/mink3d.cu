@@ -47,7 +47,7 @@ struct MinkParams {
     double* up;
     unsigned long long* counters;
     long long* dbg;        // optional [grid][8] phase timestamps (profiling builds of tools/phase_times.py)
-    int n, M, B, first_obj, n_objs;
+    int n, M, B, first_obj, n_objs, n_heavy;
     int Lx, Ly, L;
     int lpc, groups;                        // thread mapping
     double inv_dx, bias_x, inv_dy, bias_y;  // line-index guess g = x*inv_d + bias
@@ -120,8 +120,23 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
 
     const int n = p.n, M = p.M;
     const int per_layer = p.n_objs * p.B;
-    const int k = blockIdx.x / per_layer;
-    const int s = blockIdx.x - k * per_layer;  // surface index inside the layer's output
+    // Heavy surfaces first: the arena objects (eps ~ 0.1, a few huge faces, tens of thousands of sweep candidates) take ~20x
+    // longer than an obstacle surface, so their CTAs are issued at the start of the grid instead of trailing it.
+    int k, s;
+    {
+        const int heavy = p.n_heavy * p.B;  // surfaces [0, heavy) of every layer
+        const int nk = gridDim.x / per_layer;
+        const int bid = blockIdx.x;
+        if (bid < nk * heavy) {
+            k = bid / heavy;
+            s = bid - k * heavy;
+        } else {
+            const int rem = bid - nk * heavy, light = per_layer - heavy;
+            k = rem / light;
+            s = heavy + (rem - k * light);
+        }
+    }
+    const int slot = k * per_layer + s;  // position of this surface in the output arrays
     const int oi = s / p.B;
     const int b = s - oi * p.B;
     const int obj_id = p.first_obj + oi;
@@ -201,7 +216,7 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
     const double offy = __ldg(p.off + (static_cast<size_t>(k) * p.B + b) * 3 + 1);
     const double offz = __ldg(p.off + (static_cast<size_t>(k) * p.B + b) * 3 + 2);
 
-    Real* mesh = reinterpret_cast<Real*>(p.mesh) + static_cast<size_t>(blockIdx.x) * 3 * M;
+    Real* mesh = reinterpret_cast<Real*>(p.mesh) + static_cast<size_t>(slot) * 3 * M;
     Real* mx = mesh;
     Real* my = mesh + M;
     Real* mz = mesh + 2 * static_cast<size_t>(M);
@@ -397,12 +412,16 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
         const D3 t0 = {static_cast<double>(mx[v0]), static_cast<double>(my[v0]), static_cast<double>(mz[v0])};
         const D3 t1 = {static_cast<double>(mx[v1]), static_cast<double>(my[v1]), static_cast<double>(mz[v1])};
         const D3 t2 = {static_cast<double>(mx[v2]), static_cast<double>(my[v2]), static_cast<double>(mz[v2])};
-        const D3 o = {txs[ix + 1], tys[iy + 1], 0.0};
-        const D3 d = {0.0, 0.0, 1.0};
-        D3 pt;
-        const bool hit = line_triangle<A>(o, d, t0, t1, t2, pt);
-        z = pt.z;
-        return hit;
+        if constexpr (MODE == HRMGPU_F64_STRICT) {
+            const D3 o = {txs[ix + 1], tys[iy + 1], 0.0};
+            const D3 d = {0.0, 0.0, 1.0};
+            D3 pt;
+            const bool hit = line_triangle<A>(o, d, t0, t1, t2, pt);
+            z = pt.z;
+            return hit;
+        } else {
+            return vertical_hit_fast(txs[ix + 1], tys[iy + 1], t0, t1, t2, z);
+        }
     };
 
     // ---- phases B + C, interleaved: scan cells -> queue candidates -> cooperative drain ----------
@@ -591,8 +610,8 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
     if (p.dbg) t_scan = clock64();
     // ---- phase D: intervals ----------------------------------------------------------------
     const bool is_arena = __ldg(&ob.sign) < 0.0;
-    double* lo = p.lo + static_cast<size_t>(blockIdx.x) * p.L;
-    double* up = p.up + static_cast<size_t>(blockIdx.x) * p.L;
+    double* lo = p.lo + static_cast<size_t>(slot) * p.L;
+    double* up = p.up + static_cast<size_t>(slot) * p.L;
     unsigned single = 0;
     for (int l = tid; l < p.L; l += kThreads) {
         const uint32_t e0 = m0[l], e1 = m1[l];
@@ -611,7 +630,7 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
     }
     if (single) atomicAdd(p.counters, static_cast<unsigned long long>(single));
     if (p.dbg && tid == 0) {
-        long long* d = p.dbg + static_cast<size_t>(blockIdx.x) * 8;
+        long long* d = p.dbg + static_cast<size_t>(slot) * 8;
         d[0] = t_pro - t_start;      // prologue
         d[1] = t_a - t_pro;          // phase A
         d[2] = t_scan - t_a;         // scan + drain + commit
@@ -681,6 +700,7 @@ int launch_minksweep3d(Ctx* c, int K, int B, int n_first_obj, int n_objs, const 
     p.B = B;
     p.first_obj = n_first_obj;
     p.n_objs = n_objs;
+    p.n_heavy = (n_first_obj < c->n_arena) ? ((c->n_arena - n_first_obj < n_objs) ? c->n_arena - n_first_obj : n_objs) : 0;  // arena objects in this launch
     p.Lx = c->Lx;
     p.Ly = c->Ly;
     p.L = c->Lx * c->Ly;
