@@ -12,6 +12,8 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libhrmgpu.so")
+HOST_DIR = os.path.join(HERE, "host")
+HOST_LIB = os.path.join(LIBDIR, "libhrmhost.so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -55,6 +57,12 @@ def build(force=False, verbose=False):
         list(ex.map(run, jobs))
     if force or jobs or _stale(LIB, objs):
         run([NVCC] + ARCH + ["-shared", "-o", LIB] + objs)
+    # C++ host layer (planner API mirror) on top of the C ABI; no CUDA in it, linked against libhrmgpu.so
+    host_src = [os.path.join(HOST_DIR, f) for f in sorted(os.listdir(HOST_DIR)) if f.endswith(".cpp")]
+    host_dep = host_src + [os.path.join(HOST_DIR, f) for f in os.listdir(HOST_DIR) if f.endswith(".hpp")] + [LIB, headers[-1]]
+    if force or _stale(HOST_LIB, host_dep):
+        run([os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-Wall", "-shared", "-o", HOST_LIB] + host_src +
+            ["-L" + LIBDIR, "-lhrmgpu", "-Wl,-rpath,$ORIGIN"])
     return LIB
 
 

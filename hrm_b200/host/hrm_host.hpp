@@ -1,0 +1,1022 @@
+// Host-side C++ mirror of the reference's planner API for the accelerated path (same class and method names as
+// ChirikjianLab/hrm where Eigen-free signatures allow it):
+//
+//   hrm::SuperQuadrics / SuperEllipse          include/hrm/geometry/SuperQuadrics.h:23-74, SuperEllipse.h:23-65  (parameters only)
+//   hrm::MultiBodyTree3D / MultiBodyTree2D     include/hrm/datastructure/MultiBodyTree.h:12-63
+//   hrm::FreeSpaceGPU3D / FreeSpaceGPU2D       drop-in for FreeSpace3D / FreeSpace2D (FreeSpace.h:45-128, FreeSpace3D.h:29-55),
+//                                              every compute* call forwarded to the C ABI of include/hrmgpu.h (batched over layers)
+//   hrm::getMVCE3D/2D, getTFE3D/2D, interpolate*   src/geometry/TightFitEllipsoid.cpp, src/util/InterpolateSE3.cpp  (host, tiny)
+//   hrm::planners::HighwayRoadMap / HRM3D / HRM2D, PlanningRequest, PlanningResult   include/hrm/planners/*.h
+//
+// The GPU does K1-K5; the host enumerates candidates, replays the reference's loops with the returned booleans (so vertex
+// ids and edge order are the reference's) and runs A*.  There is no CPU implementation of the kernels here: without a
+// device every FreeSpaceGPU constructor throws.
+#pragma once
+#include "../../include/hrmgpu.h"
+#include "hrm_math.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <functional>
+#include <map>
+#include <queue>
+#include <stdexcept>
+#include <string>
+#include <utility>
+
+namespace hrm {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// geometric models (parameter holders; the boundary arithmetic lives in the CUDA kernels)
+// ---------------------------------------------------------------------------------------------------------------------
+class SuperQuadrics {
+  public:
+    SuperQuadrics() = default;
+    SuperQuadrics(std::vector<double> semiAxis, std::vector<double> epsilon, std::vector<double> position, const Quaternion& quat,
+                  Index num)
+        : semiAxis_(std::move(semiAxis)), epsilon_(std::move(epsilon)), position_(std::move(position)), quat_(quat), num_(num) {}
+    const std::vector<double>& getSemiAxis() const { return semiAxis_; }
+    const std::vector<double>& getEpsilon() const { return epsilon_; }
+    const std::vector<double>& getPosition() const { return position_; }
+    const Quaternion& getQuaternion() const { return quat_; }
+    Index getNumParam() const { return num_; }
+    Index getNum() const { return num_ * num_; }
+    void setPosition(const std::vector<double>& p) { position_ = p; }
+    void setQuaternion(const Quaternion& q) { quat_ = q; }
+    void setQuatSamples(const std::vector<Quaternion>& q) { qSample_ = q; }
+    const std::vector<Quaternion>& getQuatSamples() const { return qSample_; }
+
+  private:
+    std::vector<double> semiAxis_{1, 1, 1}, epsilon_{1, 1}, position_{0, 0, 0};
+    Quaternion quat_{1, 0, 0, 0};
+    Index num_ = 0;
+    std::vector<Quaternion> qSample_;
+};
+
+class SuperEllipse {
+  public:
+    SuperEllipse() = default;
+    SuperEllipse(std::vector<double> semiAxis, double epsilon, std::vector<double> position, double angle, Index num)
+        : semiAxis_(std::move(semiAxis)), epsilon_(epsilon), position_(std::move(position)), angle_(angle), num_(num) {}
+    const std::vector<double>& getSemiAxis() const { return semiAxis_; }
+    double getEpsilon() const { return epsilon_; }
+    const std::vector<double>& getPosition() const { return position_; }
+    double getAngle() const { return angle_; }
+    Index getNum() const { return num_; }
+    void setPosition(const std::vector<double>& p) { position_ = p; }
+    void setAngle(double a) { angle_ = a; }
+
+  private:
+    std::vector<double> semiAxis_{1, 1}, position_{0, 0};
+    double epsilon_ = 1, angle_ = 0;
+    Index num_ = 0;
+};
+
+struct SE3Transform {
+    Mat3 R{{{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}};
+    Vec3 t{0, 0, 0};
+};
+
+// reference src/datastructure/MultiBodyTree3D.cpp
+class MultiBodyTree3D {
+  public:
+    explicit MultiBodyTree3D(const SuperQuadrics& base) : base_(base) {}
+    void addBody(const SuperQuadrics& link) {  // :21-32
+        link_.push_back(link);
+        SE3Transform g;
+        g.R = toRotationMatrix(link.getQuaternion());
+        g.t = {link.getPosition()[0], link.getPosition()[1], link.getPosition()[2]};
+        tf_.push_back(g);
+    }
+    void robotTF(const SE3Transform& g) {  // :34-53
+        base_.setPosition({g.t[0], g.t[1], g.t[2]});
+        base_.setQuaternion(toQuaternion(g.R));
+        for (size_t i = 0; i < link_.size(); ++i) {
+            const Mat3 R = matMul(g.R, tf_[i].R);
+            const Vec3 v = matVec(g.R, tf_[i].t);
+            link_[i].setPosition({v[0] + g.t[0], v[1] + g.t[1], v[2] + g.t[2]});
+            link_[i].setQuaternion(toQuaternion(R));
+        }
+    }
+    const SuperQuadrics& getBase() const { return base_; }
+    const std::vector<SuperQuadrics>& getLinks() const { return link_; }
+    const std::vector<SE3Transform>& getTF() const { return tf_; }
+    Index getNumLinks() const { return link_.size(); }
+    std::vector<SuperQuadrics> getBodyShapes() const {
+        std::vector<SuperQuadrics> b{base_};
+        b.insert(b.end(), link_.begin(), link_.end());
+        return b;
+    }
+    // flat arrays of the current pose as MultiBodyTree3D::minkSum consumes it (:91-105): rotation of every body, link
+    // centres subtracted from the link boundaries
+    void bodyArrays(std::vector<double>& semi, std::vector<double>& R, std::vector<double>& off) const {
+        const auto bodies = getBodyShapes();
+        for (size_t b = 0; b < bodies.size(); ++b) {
+            for (double v : bodies[b].getSemiAxis()) semi.push_back(v);
+            const Mat3 Rb = toRotationMatrix(bodies[b].getQuaternion());
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) R.push_back(Rb[i][j]);
+            for (int d = 0; d < 3; ++d) off.push_back(b == 0 ? 0.0 : bodies[b].getPosition()[d]);
+        }
+    }
+
+  private:
+    SuperQuadrics base_;
+    std::vector<SuperQuadrics> link_;
+    std::vector<SE3Transform> tf_;
+};
+
+struct SE2Transform {
+    double R[2][2] = {{1, 0}, {0, 1}};
+    double t[2] = {0, 0};
+};
+
+// reference src/datastructure/MultiBodyTree2D.cpp
+class MultiBodyTree2D {
+  public:
+    explicit MultiBodyTree2D(const SuperEllipse& base) : base_(base) {}
+    void addBody(const SuperEllipse& link) {  // :10-22
+        link_.push_back(link);
+        SE2Transform g;
+        const double c = std::cos(link.getAngle()), s = std::sin(link.getAngle());
+        g.R[0][0] = c, g.R[0][1] = -s, g.R[1][0] = s, g.R[1][1] = c;
+        g.t[0] = link.getPosition()[0], g.t[1] = link.getPosition()[1];
+        tf_.push_back(g);
+    }
+    void robotTF(double theta, double x, double y) {  // :24-41 with g = [Rot(theta) (x,y); 0 1]
+        const double c = std::cos(theta), s = std::sin(theta);
+        const double R[2][2] = {{c, -s}, {s, c}};
+        base_.setPosition({x, y});
+        base_.setAngle(std::atan2(R[1][0], R[0][0]));
+        for (size_t i = 0; i < link_.size(); ++i) {
+            const SE2Transform& l = tf_[i];
+            const double m00 = R[0][0] * l.R[0][0] + R[0][1] * l.R[1][0];
+            const double m10 = R[1][0] * l.R[0][0] + R[1][1] * l.R[1][0];
+            link_[i].setPosition({(R[0][0] * l.t[0] + R[0][1] * l.t[1]) + x, (R[1][0] * l.t[0] + R[1][1] * l.t[1]) + y});
+            link_[i].setAngle(std::atan2(m10, m00));
+        }
+    }
+    const SuperEllipse& getBase() const { return base_; }
+    const std::vector<SuperEllipse>& getLinks() const { return link_; }
+    const std::vector<SE2Transform>& getTF() const { return tf_; }
+    Index getNumLinks() const { return link_.size(); }
+    // (semi, angle, offset) of every body as MultiBodyTree2D::minkSum derives them from the base angle (:43-65)
+    void bodyArrays(std::vector<double>& semi, std::vector<double>& angle, std::vector<double>& off) const {
+        for (double v : base_.getSemiAxis()) semi.push_back(v);
+        angle.push_back(base_.getAngle());
+        off.push_back(0.0), off.push_back(0.0);
+        const double c = std::cos(base_.getAngle()), s = std::sin(base_.getAngle());
+        for (size_t i = 0; i < link_.size(); ++i) {
+            for (double v : link_[i].getSemiAxis()) semi.push_back(v);
+            const SE2Transform& l = tf_[i];
+            const double m00 = c * l.R[0][0] + (-s) * l.R[1][0];
+            const double m10 = s * l.R[0][0] + c * l.R[1][0];
+            angle.push_back(std::atan2(m10, m00));
+            off.push_back(c * l.t[0] + (-s) * l.t[1]);
+            off.push_back(s * l.t[0] + c * l.t[1]);
+        }
+    }
+
+  private:
+    SuperEllipse base_;
+    std::vector<SuperEllipse> link_;
+    std::vector<SE2Transform> tf_;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// interpolation + tightly-fitted ellipsoids (host)
+// ---------------------------------------------------------------------------------------------------------------------
+inline std::vector<Quaternion> interpolateSlerp(const Quaternion& a, const Quaternion& b, Index numStep) {  // InterpolateSE3.cpp:89-103
+    std::vector<Quaternion> out;
+    const double dt = 1.0 / static_cast<double>(numStep);
+    for (size_t i = 0; i <= numStep; ++i) out.push_back(slerp(a, static_cast<double>(i) * dt, b));
+    return out;
+}
+inline std::vector<std::vector<Coordinate>> interpolateSE3(const std::vector<Coordinate>& v0, const std::vector<Coordinate>& v1,
+                                                           Index numStep) {  // :5-29
+    const auto q = interpolateSlerp({v0[3], v0[4], v0[5], v0[6]}, {v1[3], v1[4], v1[5], v1[6]}, numStep);
+    const double dt = 1.0 / static_cast<double>(numStep);
+    std::vector<std::vector<Coordinate>> out;
+    for (size_t i = 0; i <= numStep; ++i) {
+        std::vector<Coordinate> s;
+        for (int j = 0; j < 3; ++j) s.push_back((1.0 - static_cast<double>(i) * dt) * v0[j] + static_cast<double>(i) * dt * v1[j]);
+        s.insert(s.end(), q[i].begin(), q[i].end());
+        out.push_back(s);
+    }
+    return out;
+}
+
+struct Ellipsoid {
+    Vec3 semi;
+    Quaternion quat;
+};
+inline Ellipsoid getMVCE3D(const Vec3& a, const Vec3& b, const Quaternion& quatA, const Quaternion& quatB) {  // TightFitEllipsoid.cpp:43-81
+    const Mat3 Ra = toRotationMatrix(quatA), Rb = toRotationMatrix(quatB);
+    const double r = std::fmin(b[0], std::fmin(b[1], b[2]));
+    const Vec3 dg = {r / b[0], r / b[1], r / b[2]};
+    const Vec3 dA = {std::pow(a[0], -2.0), std::pow(a[1], -2.0), std::pow(a[2], -2.0)};
+    const Mat3 T = matMul(mulDiag(Rb, dg), transpose(Rb));
+    const Mat3 Ti = inverse(T);
+    const Mat3 aP = matMul(matMul(Ti, matMul(mulDiag(Ra, dA), transpose(Ra))), Ti);
+    Vec3 ev;
+    Mat3 U;
+    symEig3(aP, ev, U);
+    Vec3 dC;
+    for (int i = 0; i < 3; ++i) dC[i] = std::pow(std::fmax(std::pow(ev[i], -0.5), r), -2.0);
+    const Mat3 C = matMul(matMul(mulDiag(matMul(T, U), dC), transpose(U)), T);
+    symEig3(C, ev, U);
+    Ellipsoid e;
+    e.quat = toQuaternion(U);
+    for (int i = 0; i < 3; ++i) e.semi[i] = std::pow(ev[i], -0.5);
+    return e;
+}
+inline Ellipsoid getTFE3D(const Vec3& a, const Quaternion& quatA, const Quaternion& quatB, Index numStep) {  // :98-114
+    const auto qi = interpolateSlerp(quatA, quatB, numStep);
+    Ellipsoid e = getMVCE3D(a, a, quatA, quatB);
+    for (size_t i = 1; i < numStep; ++i) e = getMVCE3D(a, e.semi, qi.at(i), e.quat);
+    return e;
+}
+
+struct Ellipse {
+    double semi[2];
+    double angle;
+};
+inline void symEig2(const double A[2][2], double ev[2], double U[2][2]) {
+    const double a = A[0][0], b = 0.5 * (A[0][1] + A[1][0]), d = A[1][1];
+    const double tr = a + d, df = a - d, rt = std::sqrt(df * df + 4.0 * b * b);
+    ev[0] = 0.5 * (tr + rt), ev[1] = 0.5 * (tr - rt);
+    double vx, vy;
+    if (std::fabs(b) > 0.0) {
+        vx = ev[0] - d, vy = b;
+        if (std::fabs(vx) + std::fabs(vy) == 0.0) vx = b, vy = ev[0] - a;
+    } else if (a >= d) {
+        vx = 1.0, vy = 0.0;
+    } else {
+        vx = 0.0, vy = 1.0;
+    }
+    const double n = std::sqrt(vx * vx + vy * vy);
+    vx /= n, vy /= n;
+    U[0][0] = vx, U[1][0] = vy, U[0][1] = -vy, U[1][1] = vx;
+}
+inline Ellipse getMVCE2D(const double a[2], const double b[2], double thetaA, double thetaB) {  // TightFitEllipsoid.cpp:6-41
+    const double Ra[2][2] = {{std::cos(thetaA), -std::sin(thetaA)}, {std::sin(thetaA), std::cos(thetaA)}};
+    const double Rb[2][2] = {{std::cos(thetaB), -std::sin(thetaB)}, {std::sin(thetaB), std::cos(thetaB)}};
+    const double r = std::fmin(b[0], b[1]);
+    const double dg[2] = {r / b[0], r / b[1]};
+    const double dA[2] = {std::pow(a[0], -2), std::pow(a[1], -2)};
+    auto rdrt = [](const double R[2][2], const double d[2], double out[2][2]) {
+        for (int i = 0; i < 2; ++i)
+            for (int j = 0; j < 2; ++j) out[i][j] = (R[i][0] * d[0]) * R[j][0] + (R[i][1] * d[1]) * R[j][1];
+    };
+    auto mul = [](const double X[2][2], const double Y[2][2], double out[2][2]) {
+        for (int i = 0; i < 2; ++i)
+            for (int j = 0; j < 2; ++j) out[i][j] = X[i][0] * Y[0][j] + X[i][1] * Y[1][j];
+    };
+    double T[2][2], Am[2][2], tmp[2][2], aP[2][2];
+    rdrt(Rb, dg, T);
+    rdrt(Ra, dA, Am);
+    const double idt = 1.0 / (T[0][0] * T[1][1] - T[0][1] * T[1][0]);
+    const double Ti[2][2] = {{T[1][1] * idt, -T[0][1] * idt}, {-T[1][0] * idt, T[0][0] * idt}};
+    mul(Ti, Am, tmp);
+    mul(tmp, Ti, aP);
+    double ev[2], U[2][2];
+    symEig2(aP, ev, U);
+    const double cP[2] = {std::max(std::pow(ev[0], -0.5), r), std::max(std::pow(ev[1], -0.5), r)};
+    const double dC[2] = {std::pow(cP[0], -2), std::pow(cP[1], -2)};
+    const double Ut[2][2] = {{U[0][0], U[1][0]}, {U[0][1], U[1][1]}};
+    double TU[2][2], TUD[2][2], C[2][2];
+    mul(T, U, TU);
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j) TUD[i][j] = TU[i][j] * dC[j];
+    mul(TUD, Ut, tmp);
+    mul(tmp, T, C);
+    symEig2(C, ev, U);
+    Ellipse e;
+    e.angle = std::acos(std::fmax(-1.0, std::fmin(1.0, U[0][0])));
+    e.semi[0] = std::pow(ev[0], -0.5), e.semi[1] = std::pow(ev[1], -0.5);
+    return e;
+}
+inline Ellipse getTFE2D(const double a[2], double thetaA, double thetaB, Index numStep) {  // :83-96
+    Ellipse e = getMVCE2D(a, a, thetaA, thetaB);
+    const double dt = 1.0 / (static_cast<double>(numStep) - 1);
+    for (size_t i = 0; i < numStep; ++i) {
+        const double ci = static_cast<double>(i);
+        e = getMVCE2D(a, e.semi, (1 - ci * dt) * thetaA + ci * dt * thetaB, e.angle);
+    }
+    return e;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// free-space computators backed by the GPU
+// ---------------------------------------------------------------------------------------------------------------------
+struct FreeSegment2D {  // include/hrm/datastructure/FreeSpace.h:29-41
+    std::vector<Coordinate> ty;
+    std::vector<std::vector<Coordinate>> xL, xU, xM;
+};
+struct FreeSegment3D {  // include/hrm/datastructure/FreeSpace3D.h:10-16
+    std::vector<Coordinate> tx;
+    std::vector<FreeSegment2D> freeSegmentYZ;
+};
+using BoundaryPoints = std::vector<double>;  // dim x M column-major, like Eigen::MatrixXd
+struct BoundaryInfo {
+    std::vector<BoundaryPoints> arena, obstacle;
+};
+
+class FreeSpaceGPU {
+  public:
+    explicit FreeSpaceGPU(int device) {
+        const int rc = hrmgpu_create(&ctx_, device, 0);
+        if (rc != HRMGPU_OK) throw std::runtime_error("hrmgpu_create failed (no sm_100 device? there is no CPU fallback), status " + std::to_string(rc));
+    }
+    virtual ~FreeSpaceGPU() { hrmgpu_destroy(ctx_); }
+    FreeSpaceGPU(const FreeSpaceGPU&) = delete;
+    FreeSpaceGPU& operator=(const FreeSpaceGPU&) = delete;
+
+    /** setup(numLine, low, up) of the reference + the sweep grids of sweepLineProcess */
+    void setup(const std::vector<Coordinate>& boundaryLimits, Index numLineX, Index numLineY) {
+        check(hrmgpu_set_sweep(ctx_, boundaryLimits.data(), static_cast<int>(numLineX), static_cast<int>(numLineY)));
+    }
+    /** getCSpaceBoundary() of layer k */
+    BoundaryInfo getCSpaceBoundary(int k) {
+        long long d[8];
+        check(hrmgpu_get_dims(ctx_, d));
+        BoundaryInfo out;
+        for (int s = 0; s < d[2]; ++s) {
+            BoundaryPoints p(static_cast<size_t>(d[7] * d[5]));
+            check(hrmgpu_get_boundary(ctx_, k, s, p.data()));
+            (s < d[3] ? out.arena : out.obstacle).push_back(std::move(p));
+        }
+        return out;
+    }
+    /** all free segments of the last build: global CSR over (layer, line) */
+    void getFreeSegmentsAll(std::vector<long long>& off, std::vector<double>& xL, std::vector<double>& xU, std::vector<double>& xM) {
+        long long d[8];
+        check(hrmgpu_get_dims(ctx_, d));
+        off.resize(static_cast<size_t>(d[0] * d[4]) + 1);
+        xL.resize(static_cast<size_t>(d[6])), xU.resize(static_cast<size_t>(d[6])), xM.resize(static_cast<size_t>(d[6]));
+        check(hrmgpu_get_segments_all(ctx_, off.data(), xL.data(), xU.data(), xM.data(), d[6]));
+    }
+    /** isSameSliceTransitionFree for a batch of segments against the C-obstacles of layer k */
+    std::vector<unsigned char> testEdges(int k, const std::vector<double>& v1, const std::vector<double>& v2, int dim) {
+        std::vector<unsigned char> out(v1.size() / dim);
+        if (!out.empty()) check(hrmgpu_test_edges(ctx_, k, static_cast<int>(out.size()), v1.data(), v2.data(), out.data()));
+        return out;
+    }
+    /** isPtInCFree of Q robot poses (body centres [Q][B][dim]) against the bridge layer of pair p */
+    std::vector<unsigned char> testBridge(int p, const std::vector<double>& centres, int Q) {
+        std::vector<unsigned char> out(static_cast<size_t>(Q));
+        if (Q > 0) check(hrmgpu_test_bridge(ctx_, p, Q, centres.data(), out.data()));
+        return out;
+    }
+    long long kernelLaunches() { return hrmgpu_kernel_launches(ctx_, 0); }
+    hrmgpu_ctx* handle() { return ctx_; }
+
+  protected:
+    void check(int rc) {
+        if (rc < 0) throw std::runtime_error(std::string("hrmgpu: ") + hrmgpu_last_error(ctx_));
+    }
+    hrmgpu_ctx* ctx_ = nullptr;
+};
+
+class FreeSpaceGPU3D : public FreeSpaceGPU {
+  public:
+    FreeSpaceGPU3D(const std::vector<SuperQuadrics>& arena, const std::vector<SuperQuadrics>& obstacle, int device = 0)
+        : FreeSpaceGPU(device) {
+        std::vector<double> sq;
+        auto push = [&](const SuperQuadrics& s) {
+            for (double v : s.getSemiAxis()) sq.push_back(v);
+            for (double v : s.getEpsilon()) sq.push_back(v);
+            for (double v : s.getPosition()) sq.push_back(v);
+            const Mat3 R = toRotationMatrix(s.getQuaternion());
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) sq.push_back(R[i][j]);
+        };
+        for (const auto& a : arena) push(a);
+        for (const auto& o : obstacle) push(o);
+        check(hrmgpu_set_scene3d(ctx_, static_cast<int>(arena.size()), static_cast<int>(obstacle.size()), sq.data(),
+                                 static_cast<int>(arena.at(0).getNumParam())));
+    }
+    /** computeCSpaceBoundary + computeCSpaceBoundaryMesh + sweepLineProcess (intervals, free segments) for K robot poses */
+    void buildLayers(const std::vector<MultiBodyTree3D>& poses, int precision) {
+        std::vector<double> semi, R, off, semiK;
+        for (size_t k = 0; k < poses.size(); ++k) {
+            semiK.clear();
+            poses[k].bodyArrays(semiK, R, off);
+            if (k == 0) semi = semiK;
+        }
+        check(hrmgpu_build_layers(ctx_, static_cast<int>(poses.size()), static_cast<int>(semi.size() / 3), semi.data(), R.data(), off.data(),
+                                  precision));
+    }
+    /** bridgeSlice for P layer pairs: tfe[p][b] */
+    void buildBridge(const std::vector<std::vector<Ellipsoid>>& tfe, int precision) {
+        std::vector<double> semi, R;
+        for (const auto& pr : tfe)
+            for (const auto& e : pr) {
+                for (double v : e.semi) semi.push_back(v);
+                const Mat3 Rb = toRotationMatrix(e.quat);
+                for (int i = 0; i < 3; ++i)
+                    for (int j = 0; j < 3; ++j) R.push_back(Rb[i][j]);
+            }
+        check(hrmgpu_build_bridge(ctx_, static_cast<int>(tfe.size()), static_cast<int>(tfe.at(0).size()), semi.data(), R.data(), precision));
+    }
+};
+
+class FreeSpaceGPU2D : public FreeSpaceGPU {
+  public:
+    FreeSpaceGPU2D(const std::vector<SuperEllipse>& arena, const std::vector<SuperEllipse>& obstacle, int device = 0) : FreeSpaceGPU(device) {
+        std::vector<double> se;
+        auto push = [&](const SuperEllipse& s) {
+            se.push_back(s.getSemiAxis()[0]), se.push_back(s.getSemiAxis()[1]), se.push_back(s.getEpsilon());
+            se.push_back(s.getPosition()[0]), se.push_back(s.getPosition()[1]), se.push_back(s.getAngle());
+        };
+        for (const auto& a : arena) push(a);
+        for (const auto& o : obstacle) push(o);
+        check(hrmgpu_set_scene2d(ctx_, static_cast<int>(arena.size()), static_cast<int>(obstacle.size()), se.data(),
+                                 static_cast<int>(arena.at(0).getNum())));
+    }
+    void buildLayers(const std::vector<MultiBodyTree2D>& poses, int precision) {
+        std::vector<double> semi, ang, off, semiK;
+        for (size_t k = 0; k < poses.size(); ++k) {
+            semiK.clear();
+            poses[k].bodyArrays(semiK, ang, off);
+            if (k == 0) semi = semiK;
+        }
+        check(hrmgpu_build_layers2d(ctx_, static_cast<int>(poses.size()), static_cast<int>(semi.size() / 2), semi.data(), ang.data(), off.data(),
+                                    precision));
+    }
+    void buildBridge(const std::vector<std::vector<Ellipse>>& tfe, int precision) {
+        std::vector<double> semi, ang;
+        for (const auto& pr : tfe)
+            for (const auto& e : pr) semi.push_back(e.semi[0]), semi.push_back(e.semi[1]), ang.push_back(e.angle);
+        check(hrmgpu_build_bridge2d(ctx_, static_cast<int>(tfe.size()), static_cast<int>(tfe.at(0).size()), semi.data(), ang.data(), precision));
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// planners
+// ---------------------------------------------------------------------------------------------------------------------
+struct PlannerParameter {  // include/hrm/planners/PlanningRequest.h:10-32
+    std::vector<Coordinate> boundaryLimits;
+    Index numSlice = 0, numLineX = 0, numLineY = 0, numPoint = 5, numSearchNeighbor = 10;
+    double searchRadius = HALF_PI;
+};
+struct PlanningRequest {  // :35-47
+    bool isRobotRigid = true;
+    PlannerParameter parameters;
+    std::vector<Coordinate> start, goal;
+};
+using Edge = std::vector<std::pair<Index, Index>>;
+struct Graph {  // include/hrm/planners/PlanningResult.h:14-23
+    std::vector<std::vector<Coordinate>> vertex;
+    Edge edge;
+    std::vector<double> weight;
+};
+struct SolutionPathInfo {  // :26-38
+    std::vector<Index> PathId;
+    std::vector<std::vector<Coordinate>> solvedPath, interpolatedPath;
+    double cost = 0;
+};
+struct Time {  // :41-50
+    double buildTime = 0, searchTime = 0, totalTime = 0;
+};
+struct PlanningResult {  // :53-65
+    bool solved = false;
+    Time planningTime;
+    Graph graphStructure;
+    SolutionPathInfo solutionPath;
+};
+
+namespace planners {
+
+/** A* with the Euclidean heuristic of HighwayRoadMap-inl.h:135-147 (Boost.Graph replaced by a binary heap). */
+inline bool astar(const Graph& g, Index s, Index t, std::vector<Index>& pred) {
+    const Index n = g.vertex.size();
+    std::vector<std::vector<std::pair<Index, double>>> adj(n);
+    for (size_t i = 0; i < g.edge.size(); ++i) {
+        adj[g.edge[i].first].push_back({g.edge[i].second, g.weight[i]});
+        adj[g.edge[i].second].push_back({g.edge[i].first, g.weight[i]});
+    }
+    std::vector<double> d(n, INFINITY);
+    pred.assign(n, n);
+    using QE = std::pair<double, Index>;
+    std::priority_queue<QE, std::vector<QE>, std::greater<QE>> pq;
+    d[s] = 0;
+    pred[s] = s;
+    pq.push({vectorEuclidean(g.vertex[s], g.vertex[t]), s});
+    std::vector<char> closed(n, 0);
+    while (!pq.empty()) {
+        const Index u = pq.top().second;
+        pq.pop();
+        if (closed[u]) continue;
+        closed[u] = 1;
+        if (u == t) return true;
+        for (const auto& e : adj[u]) {
+            const double nd = d[u] + e.second;
+            if (nd < d[e.first]) {
+                d[e.first] = nd;
+                pred[e.first] = u;
+                pq.push({nd + vectorEuclidean(g.vertex[e.first], g.vertex[t]), e.first});
+            }
+        }
+    }
+    return false;
+}
+
+class HighwayRoadMapBase {
+  public:
+    HighwayRoadMapBase(const PlanningRequest& req, int precision, bool perOrientation)
+        : start_(req.start), goal_(req.goal), param_(req.parameters), precision_(precision), perOrientation_(perOrientation) {}
+    virtual ~HighwayRoadMapBase() = default;
+
+    /** HighwayRoadMap-inl.h:65-89 (no refinement loop: the reference's refinement throws, SURVEY.md finding 6) */
+    virtual void plan(double /*timeLim*/ = 0.0) {
+        auto t0 = std::chrono::high_resolution_clock::now();
+        buildRoadmap();
+        res_.planningTime.buildTime = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+        t0 = std::chrono::high_resolution_clock::now();
+        search();
+        res_.planningTime.searchTime = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+        res_.planningTime.totalTime = res_.planningTime.buildTime + res_.planningTime.searchTime;
+        if (res_.solved) {
+            const size_t pose = res_.graphStructure.vertex.at(0).size();
+            start_.resize(pose), goal_.resize(pose);
+            res_.solutionPath.solvedPath.push_back(start_);
+            for (Index id : res_.solutionPath.PathId) res_.solutionPath.solvedPath.push_back(res_.graphStructure.vertex.at(id));
+            res_.solutionPath.solvedPath.push_back(goal_);
+            res_.solutionPath.interpolatedPath = res_.solutionPath.solvedPath;
+        }
+    }
+    const PlanningResult& getPlanningResult() const { return res_; }
+    const PlannerParameter& getPlannerParameters() const { return param_; }
+    long numEdgeTests() const { return numEdgeTests_; }
+
+  protected:
+    virtual void buildRoadmap() = 0;
+    virtual std::vector<Index> getNearestNeighborsOnGraph(const std::vector<Coordinate>& vertex, Index k, double radius) = 0;
+
+    /** HighwayRoadMap-inl.h:110-175 */
+    void search() {
+        Graph& g = res_.graphStructure;
+        if (g.vertex.empty()) return;
+        const auto idxS = getNearestNeighborsOnGraph(start_, param_.numSearchNeighbor, param_.searchRadius);
+        const auto idxG = getNearestNeighborsOnGraph(goal_, param_.numSearchNeighbor, param_.searchRadius);
+        for (Index s : idxS)
+            for (Index t : idxG) {
+                std::vector<Index> p;
+                if (astar(g, s, t, p)) {
+                    auto& sp = res_.solutionPath;
+                    sp.PathId.clear();
+                    sp.cost = 0;
+                    Index cur = t;
+                    sp.PathId.push_back(cur);
+                    while (cur != s) {
+                        sp.cost += vectorEuclidean(g.vertex[cur], g.vertex[p[cur]]);
+                        cur = p[cur];
+                        sp.PathId.push_back(cur);
+                    }
+                    std::reverse(sp.PathId.begin(), sp.PathId.end());
+                    res_.solved = true;
+                    return;
+                }
+            }
+    }
+    void addEdge(Index i, Index j) {
+        res_.graphStructure.edge.push_back({i, j});
+        res_.graphStructure.weight.push_back(vectorEuclidean(res_.graphStructure.vertex[i], res_.graphStructure.vertex[j]));
+    }
+    /** one (idx1, idx2) candidate of connectOneSlice: code 0 direct edge, 1 / 2 via bridgeVertex's vNew1 / vNew2 (:295-326), 3 none */
+    void connectPair(Index idx1, Index idx2, int code, int zi) {
+        auto& g = res_.graphStructure;
+        if (code == 0) {
+            addEdge(idx1, idx2);
+        } else if (code == 1 || code == 2) {
+            const auto v1 = g.vertex[idx1], v2 = g.vertex[idx2];
+            auto vn = (code == 1) ? v1 : v2;
+            vn[zi] = (code == 1) ? v2[zi] : v1[zi];
+            const Index idn = g.vertex.size();
+            g.vertex.push_back(vn);
+            g.edge.push_back({idx1, idn});
+            g.weight.push_back(vectorEuclidean(v1, vn));
+            g.edge.push_back({idn, idx2});
+            g.weight.push_back(vectorEuclidean(vn, v2));
+        }
+    }
+    static int pairCode(bool f0, bool f1, bool f2, bool f3, bool f4) { return f0 ? 0 : ((f1 && f2) ? 1 : ((f3 && f4) ? 2 : 3)); }
+
+    std::vector<Coordinate> start_, goal_;
+    PlannerParameter param_;
+    PlanningResult res_;
+    std::vector<std::pair<Index, Index>> vertexIdx_;  // (startId, slice) per C-layer
+    int precision_;
+    bool perOrientation_;
+    long numEdgeTests_ = 0;
+};
+
+/** src/planners/HRM3D.cpp */
+class HRM3D : public HighwayRoadMapBase {
+  public:
+    HRM3D(const MultiBodyTree3D& robot, const std::vector<SuperQuadrics>& arena, const std::vector<SuperQuadrics>& obs, const PlanningRequest& req,
+          int device = 0, int precision = HRMGPU_F64_STRICT, bool perOrientation = false)
+        : HighwayRoadMapBase(req, precision, perOrientation), robot_(robot), freeSpace_(arena, obs, device) {
+        q_ = robot_.getBase().getQuatSamples();  // pre-defined samples (HRM3D.cpp:436-440); random sampling must be injected (App. C12)
+        param_.numSlice = q_.size();
+    }
+    FreeSpaceGPU3D& freeSpace() { return freeSpace_; }
+
+  protected:
+    void buildRoadmap() override {
+        const auto& lim = param_.boundaryLimits;
+        const int Lx = static_cast<int>(param_.numLineX), Ly = static_cast<int>(param_.numLineY);
+        freeSpace_.setup(lim, param_.numLineX, param_.numLineY);
+        // K1+K2+K3 for every orientation in ONE call
+        std::vector<MultiBodyTree3D> poses;
+        std::vector<Quaternion> baseQ;
+        MultiBodyTree3D rb = robot_;
+        for (const auto& q : q_) {
+            SE3Transform g;
+            g.R = toRotationMatrix(q);
+            rb.robotTF(g);  // HRM3D.cpp:27-31,510-518 (planner's robot)
+            baseQ.push_back(rb.getBase().getQuaternion());
+            poses.push_back(perOrientation_ ? rb : robot_);  // the reference's FreeSpace copy keeps the as-loaded pose (finding 1)
+        }
+        freeSpace_.buildLayers(poses, precision_);
+        std::vector<long long> off;
+        std::vector<double> xL, xU, xM;
+        freeSpace_.getFreeSegmentsAll(off, xL, xU, xM);
+        const double dx = (lim[1] - lim[0]) / static_cast<double>(Lx - 1), dy = (lim[3] - lim[2]) / static_cast<double>(Ly - 1);
+        std::vector<double> tx(Lx), ty(Ly);
+        for (int i = 0; i < Lx; ++i) tx[i] = lim[0] + static_cast<double>(i) * dx;
+        for (int i = 0; i < Ly; ++i) ty[i] = lim[2] + static_cast<double>(i) * dy;
+        for (size_t k = 0; k < q_.size(); ++k) connectOneSlice3D(static_cast<int>(k), baseQ[k], tx, ty, off.data() + k * Lx * Ly, xL, xU, xM);
+        connectMultiSlice();
+    }
+
+    /** generateVertices + connectOneSlice2D per plane + cross-plane connections (HRM3D.cpp:93-156), edge tests batched on the GPU */
+    void connectOneSlice3D(int k, const Quaternion& q, const std::vector<double>& tx, const std::vector<double>& ty, const long long* o,
+                           const std::vector<double>& xL, const std::vector<double>& xU, const std::vector<double>& xM) {
+        const int Lx = static_cast<int>(tx.size()), Ly = static_cast<int>(ty.size());
+        auto seg0 = [&](int ix, int iy) { return o[ix * Ly + iy]; };
+        auto segN = [&](int ix, int iy) { return static_cast<int>(o[ix * Ly + iy + 1] - o[ix * Ly + iy]); };
+        struct Pair {
+            double a[3], b[3];
+        };
+        std::vector<Pair> pairs;
+        for (int ix = 0; ix < Lx; ++ix)
+            for (int iy = 0; iy + 1 < Ly; ++iy)
+                for (int j1 = 0; j1 < segN(ix, iy); ++j1)
+                    for (int j2 = 0; j2 < segN(ix, iy + 1); ++j2)
+                        pairs.push_back({{tx[ix], ty[iy], xM[seg0(ix, iy) + j1]}, {tx[ix], ty[iy + 1], xM[seg0(ix, iy + 1) + j2]}});
+        const size_t nInPlane = pairs.size();
+        for (int ix = 0; ix + 1 < Lx; ++ix)
+            for (int iy = 0; iy < Ly; ++iy)
+                for (int k1 = 0; k1 < segN(ix, iy); ++k1)
+                    for (int k2 = 0; k2 < segN(ix + 1, iy); ++k2)
+                        pairs.push_back({{tx[ix], ty[iy], xM[seg0(ix, iy) + k1]}, {tx[ix + 1], ty[iy], xM[seg0(ix + 1, iy) + k2]}});
+        std::vector<int> codes(pairs.size(), 3);
+        if (!pairs.empty()) {
+            const size_t P = pairs.size();
+            std::vector<double> A(15 * P), Bq(15 * P);
+            for (size_t i = 0; i < P; ++i) {
+                const double* v1 = pairs[i].a;
+                const double* v2 = pairs[i].b;
+                const double n1[3] = {v1[0], v1[1], v2[2]}, n2[3] = {v2[0], v2[1], v1[2]};  // vNew1, vNew2 (HighwayRoadMap-inl.h:301-304)
+                const double* as[5] = {v1, v1, n1, v1, n2};
+                const double* bs[5] = {v2, n1, v2, n2, v2};
+                for (int t = 0; t < 5; ++t)
+                    for (int d = 0; d < 3; ++d) A[(t * P + i) * 3 + d] = as[t][d], Bq[(t * P + i) * 3 + d] = bs[t][d];
+            }
+            const auto f = freeSpace_.testEdges(k, A, Bq, 3);
+            numEdgeTests_ += static_cast<long>(5 * P);
+            for (size_t i = 0; i < P; ++i) codes[i] = pairCode(f[i], f[P + i], f[2 * P + i], f[3 * P + i], f[4 * P + i]);
+        }
+        // replay in the reference's order
+        auto& V = res_.graphStructure.vertex;
+        const Index startId = V.size();
+        std::vector<std::vector<Index>> lineIds;
+        size_t pc = 0;
+        for (int ix = 0; ix < Lx; ++ix) {
+            std::vector<Index> plane;
+            for (int iy = 0; iy < Ly; ++iy) {  // generateVertices
+                plane.push_back(V.size());
+                for (int j = 0; j < segN(ix, iy); ++j) V.push_back({tx[ix], ty[iy], xM[seg0(ix, iy) + j], q[0], q[1], q[2], q[3]});
+            }
+            lineIds.push_back(plane);
+            // connectOneSlice2D (HighwayRoadMap-inl.h:218-261); its pair order is the enumeration order above restricted to plane ix
+            std::vector<size_t> base(Ly, 0);  // index of the first pair of (ix, iy) in `pairs`
+            {
+                size_t acc = pc;
+                for (int iy = 0; iy + 1 < Ly; ++iy) base[iy] = acc, acc += static_cast<size_t>(segN(ix, iy)) * segN(ix, iy + 1);
+                pc = acc;
+            }
+            for (int iy = 0; iy < Ly; ++iy) {
+                const Index n1 = plane[iy];
+                const int cnt = segN(ix, iy);
+                for (int j1 = 0; j1 < cnt; ++j1) {
+                    if (j1 != cnt - 1 && std::fabs(xU[seg0(ix, iy) + j1] - xL[seg0(ix, iy) + j1 + 1]) < 1e-6) addEdge(n1 + j1, n1 + j1 + 1);
+                    if (iy != Ly - 1) {
+                        const Index n2 = plane[iy + 1];
+                        const int c2 = segN(ix, iy + 1);
+                        for (int j2 = 0; j2 < c2; ++j2) connectPair(n1 + j1, n2 + j2, codes[base[iy] + static_cast<size_t>(j1) * c2 + j2], 2);
+                    }
+                }
+            }
+        }
+        size_t pi = nInPlane;
+        for (int ix = 0; ix + 1 < Lx; ++ix)  // HRM3D.cpp:131-155
+            for (int iy = 0; iy < Ly; ++iy) {
+                const Index n1 = lineIds[ix][iy], n2 = lineIds[ix + 1][iy];
+                for (int k1 = 0; k1 < segN(ix, iy); ++k1)
+                    for (int k2 = 0; k2 < segN(ix + 1, iy); ++k2) connectPair(n1 + k1, n2 + k2, codes[pi++], 2);
+            }
+        vertexIdx_.push_back({startId, V.size()});  // numVertex_.slice is re-read after constructOneSlice (HighwayRoadMap-inl.h:100-102)
+    }
+
+    /** HRM3D.cpp:158-224 with computeTFE (:521-539), bridgeSlice (:301-317), isMultiSliceTransitionFree (:367-392) */
+    void connectMultiSlice() {
+        if (vertexIdx_.size() == 1) return;
+        auto& V = res_.graphStructure.vertex;
+        const auto& lim = param_.boundaryLimits;
+        const size_t B = 1 + robot_.getNumLinks();
+        const auto bodies = robot_.getBodyShapes();
+        std::vector<int> nearest;
+        std::vector<std::vector<Ellipsoid>> tfe;
+        for (size_t i = 0; i < vertexIdx_.size(); ++i) {
+            double minDist = INFINITY;
+            int minIdx = 0;
+            for (size_t j = 0; j != i && j < param_.numSlice; ++j) {  // only earlier layers (App. C9)
+                const double d = angularDistance(q_[i], q_[j]);
+                if (d < minDist) minDist = d, minIdx = static_cast<int>(j);
+            }
+            nearest.push_back(minIdx);
+            std::vector<Ellipsoid> pr;
+            for (size_t b = 0; b < B; ++b) {
+                const Vec3 semi = {bodies[b].getSemiAxis()[0], bodies[b].getSemiAxis()[1], bodies[b].getSemiAxis()[2]};
+                if (b == 0) {
+                    pr.push_back(getTFE3D(semi, q_[i], q_[minIdx], param_.numPoint));
+                } else {
+                    const Mat3& Rl = robot_.getTF()[b - 1].R;
+                    pr.push_back(getTFE3D(semi, toQuaternion(matMul(toRotationMatrix(q_[i]), Rl)),
+                                          toQuaternion(matMul(toRotationMatrix(q_[minIdx]), Rl)), param_.numPoint));
+                }
+            }
+            tfe.push_back(pr);
+        }
+        freeSpace_.buildBridge(tfe, precision_);
+        const double thx = 2.0 * (lim[1] - lim[0]) / static_cast<double>(param_.numLineX);
+        const double thy = 2.0 * (lim[3] - lim[2]) / static_cast<double>(param_.numLineY);
+        const size_t steps = param_.numPoint;
+        MultiBodyTree3D rb = robot_;
+        for (size_t i = 0; i < vertexIdx_.size(); ++i) {
+            const Index cur0 = vertexIdx_[i].first, cur1 = vertexIdx_[i].second;
+            const Index start = vertexIdx_[nearest[i]].first, n2 = vertexIdx_[nearest[i]].second;
+            if (n2 <= start || cur1 <= cur0) continue;
+            std::vector<std::pair<Index, Index>> cand;
+            std::vector<double> centres;
+            for (Index m0 = start; m0 < n2; ++m0)
+                for (Index m1 = cur0; m1 < cur1; ++m1) {
+                    if (std::fabs(V[m0][0] - V[m1][0]) > thx || std::fabs(V[m0][1] - V[m1][1]) > thy) continue;
+                    cand.push_back({m0, m1});
+                    for (const auto& vs : interpolateSE3(V[m0], V[m1], steps)) {  // numPoint+1 poses incl. both ends
+                        SE3Transform g;
+                        g.R = toRotationMatrix({vs[3], vs[4], vs[5], vs[6]});
+                        g.t = {vs[0], vs[1], vs[2]};
+                        rb.robotTF(g);  // setTransform
+                        for (double v : rb.getBase().getPosition()) centres.push_back(v);
+                        for (const auto& l : rb.getLinks())
+                            for (double v : l.getPosition()) centres.push_back(v);
+                    }
+                }
+            std::map<std::pair<Index, Index>, bool> freePair;
+            if (!cand.empty()) {
+                const auto ok = freeSpace_.testBridge(static_cast<int>(i), centres, static_cast<int>(cand.size() * (steps + 1)));
+                for (size_t c = 0; c < cand.size(); ++c) {
+                    bool all = true;
+                    for (size_t s = 0; s <= steps; ++s) all = all && ok[c * (steps + 1) + s];
+                    freePair[cand[c]] = all;
+                }
+            }
+            Index n22 = cur0;  // replay with the reference's moving lower bound
+            for (Index m0 = start; m0 < n2; ++m0)
+                for (Index m1 = n22; m1 < cur1; ++m1) {
+                    auto it = freePair.find({m0, m1});
+                    if (it == freePair.end()) continue;
+                    if (it->second) {
+                        addEdge(m0, m1);
+                        n22 = m1;
+                        break;
+                    }
+                }
+        }
+    }
+
+    /** HRM3D.cpp:443-508 with minQuat initialised to q_[0] (App. C18) */
+    std::vector<Index> getNearestNeighborsOnGraph(const std::vector<Coordinate>& vertex, Index k, double radius) override {
+        const auto& V = res_.graphStructure.vertex;
+        const auto& lim = param_.boundaryLimits;
+        const Quaternion qq = {vertex[3], vertex[4], vertex[5], vertex[6]};
+        Quaternion minQuat = q_[0];
+        double minD = angularDistance(qq, q_[0]);
+        for (const auto& q : q_) {
+            const double d = angularDistance(qq, q);
+            if (d < minD) minD = d, minQuat = q;
+        }
+        std::vector<Quaternion> list;
+        for (const auto& q : q_) {
+            if (angularDistance(minQuat, q) < radius) list.push_back(q);
+            if (list.size() >= k) break;
+        }
+        std::vector<Index> idx;
+        for (const auto& qc : list) {
+            Index idxSlice = 0;
+            double best = INFINITY;
+            for (size_t i = 0; i < V.size(); ++i) {
+                const double d = vectorEuclidean(vertex, V[i]);
+                if (d < best && angularDistance(qc, {V[i][3], V[i][4], V[i][5], V[i][6]}) < 1e-6) best = d, idxSlice = i;
+            }
+            if (std::abs(vertex[0] - V[idxSlice][0]) < radius * (lim[1] - lim[0]) / static_cast<double>(param_.numLineX) &&
+                std::abs(vertex[1] - V[idxSlice][1]) < radius * (lim[3] - lim[2]) / static_cast<double>(param_.numLineY))
+                idx.push_back(idxSlice);
+        }
+        return idx;
+    }
+
+    MultiBodyTree3D robot_;
+    FreeSpaceGPU3D freeSpace_;
+    std::vector<Quaternion> q_;
+};
+
+/** src/planners/HRM2D.cpp */
+class HRM2D : public HighwayRoadMapBase {
+  public:
+    HRM2D(const MultiBodyTree2D& robot, const std::vector<SuperEllipse>& arena, const std::vector<SuperEllipse>& obs, const PlanningRequest& req,
+          int device = 0, int precision = HRMGPU_F64_STRICT, bool perOrientation = false)
+        : HighwayRoadMapBase(req, precision, perOrientation), robot_(robot), freeSpace_(arena, obs, device) {}
+    FreeSpaceGPU2D& freeSpace() { return freeSpace_; }
+
+  protected:
+    void buildRoadmap() override {
+        const auto& lim = param_.boundaryLimits;
+        const int Ly = static_cast<int>(param_.numLineY);
+        const double dr = 2 * PI / (static_cast<double>(param_.numSlice) - 1);  // HRM2D.cpp:46-51
+        for (size_t i = 0; i < param_.numSlice; ++i) headings_.push_back(-PI + dr * static_cast<double>(i));
+        freeSpace_.setup(lim, 1, param_.numLineY);
+        std::vector<MultiBodyTree2D> poses;
+        std::vector<double> baseAngle;
+        MultiBodyTree2D rb = robot_;
+        for (double th : headings_) {
+            rb.robotTF(th, 0.0, 0.0);
+            baseAngle.push_back(rb.getBase().getAngle());
+            poses.push_back(perOrientation_ ? rb : robot_);
+        }
+        freeSpace_.buildLayers(poses, precision_);
+        std::vector<long long> off;
+        std::vector<double> xL, xU, xM;
+        freeSpace_.getFreeSegmentsAll(off, xL, xU, xM);
+        const double dy = (lim[3] - lim[2]) / (static_cast<double>(Ly) - 1);  // :56-61
+        std::vector<double> ty(Ly);
+        for (int i = 0; i < Ly; ++i) ty[i] = lim[2] + static_cast<double>(i) * dy;
+        auto& V = res_.graphStructure.vertex;
+        for (size_t k = 0; k < headings_.size(); ++k) {
+            const long long* o = off.data() + k * Ly;
+            auto cnt = [&](int iy) { return static_cast<int>(o[iy + 1] - o[iy]); };
+            std::vector<double> A, Bq;
+            for (int iy = 0; iy + 1 < Ly; ++iy)
+                for (int j1 = 0; j1 < cnt(iy); ++j1)
+                    for (int j2 = 0; j2 < cnt(iy + 1); ++j2) {
+                        A.push_back(xM[o[iy] + j1]), A.push_back(ty[iy]);
+                        Bq.push_back(xM[o[iy + 1] + j2]), Bq.push_back(ty[iy + 1]);
+                    }
+            // bridgeVertex swaps index 2 = theta in 2D: vNew1 == v1, vNew2 == v2 as points, so it can never add a vertex (App. C8)
+            const auto f = freeSpace_.testEdges(static_cast<int>(k), A, Bq, 2);
+            numEdgeTests_ += static_cast<long>(f.size());
+            const Index startId = V.size();
+            std::vector<Index> plane;
+            for (int iy = 0; iy < Ly; ++iy) {  // generateVertices (:72-89)
+                plane.push_back(V.size());
+                for (int j = 0; j < cnt(iy); ++j) V.push_back({xM[o[iy] + j], ty[iy], baseAngle[k]});
+            }
+            size_t pi = 0;
+            for (int iy = 0; iy < Ly; ++iy) {  // connectOneSlice2D
+                const Index n1 = plane[iy];
+                for (int j1 = 0; j1 < cnt(iy); ++j1) {
+                    if (j1 != cnt(iy) - 1 && std::fabs(xU[o[iy] + j1] - xL[o[iy] + j1 + 1]) < 1e-6) addEdge(n1 + j1, n1 + j1 + 1);
+                    if (iy != Ly - 1)
+                        for (int j2 = 0; j2 < cnt(iy + 1); ++j2)
+                            if (f[pi++]) addEdge(n1 + j1, plane[iy + 1] + j2);
+                }
+            }
+            vertexIdx_.push_back({startId, V.size()});
+        }
+        connectMultiSlice();
+    }
+
+    void connectMultiSlice() {  // HRM2D.cpp:91-156
+        if (vertexIdx_.size() == 1) return;
+        auto& V = res_.graphStructure.vertex;
+        const auto& lim = param_.boundaryLimits;
+        const size_t B = 1 + robot_.getNumLinks(), ns = param_.numSlice;
+        std::vector<size_t> adj;
+        std::vector<std::vector<Ellipse>> tfe;
+        for (size_t i = 0; i < vertexIdx_.size(); ++i) {
+            const size_t j = (i == ns - 1 && ns != 2) ? 0 : i + 1;
+            adj.push_back(j);
+            const double tha = headings_[i], thb = headings_[j];
+            std::vector<Ellipse> pr;
+            for (size_t b = 0; b < B; ++b) {  // computeTFE (:352-373)
+                if (b == 0) {
+                    const double a[2] = {robot_.getBase().getSemiAxis()[0], robot_.getBase().getSemiAxis()[1]};
+                    pr.push_back(getTFE2D(a, tha, thb, param_.numPoint));
+                } else {
+                    const SE2Transform& g = robot_.getTF()[b - 1];
+                    const double rl = std::atan2(g.R[1][0], g.R[0][0]), cl = std::cos(rl), sl = std::sin(rl);
+                    auto ang = [&](double th) {
+                        const double c = std::cos(th), s = std::sin(th);
+                        const double m00 = c * cl + (-s) * sl, m10 = s * cl + c * sl;
+                        return std::atan2(m10, m00);
+                    };
+                    const double a[2] = {robot_.getLinks()[b - 1].getSemiAxis()[0], robot_.getLinks()[b - 1].getSemiAxis()[1]};
+                    pr.push_back(getTFE2D(a, ang(tha), ang(thb), param_.numPoint));
+                }
+            }
+            tfe.push_back(pr);
+        }
+        freeSpace_.buildBridge(tfe, precision_);
+        const double th = 2.0 * std::fabs(lim[3] - lim[2]) / static_cast<double>(param_.numLineY);
+        const size_t steps = param_.numPoint;
+        const double dt = 1.0 / (static_cast<double>(steps) - 1);
+        MultiBodyTree2D rb = robot_;
+        for (size_t i = 0; i < vertexIdx_.size(); ++i) {
+            const Index sCur = vertexIdx_[i].first, eCur = vertexIdx_[i].second;
+            const Index sAdj0 = vertexIdx_[adj[i]].first, eAdj = vertexIdx_[adj[i]].second;
+            if (eCur <= sCur || eAdj <= sAdj0) continue;
+            std::vector<std::pair<Index, Index>> cand;
+            std::vector<double> centres;
+            for (Index m0 = sCur; m0 < eCur; ++m0)
+                for (Index m1 = sAdj0; m1 < eAdj; ++m1) {
+                    if (std::fabs(V[m0][1] - V[m1][1]) > th) continue;
+                    cand.push_back({m0, m1});
+                    for (size_t s = 0; s < steps; ++s) {  // :237-247
+                        double vs[3];
+                        for (int j = 0; j < 3; ++j) vs[j] = (1.0 - static_cast<double>(s) * dt) * V[m0][j] + static_cast<double>(s) * dt * V[m1][j];
+                        rb.robotTF(vs[2], vs[0], vs[1]);
+                        for (double v : rb.getBase().getPosition()) centres.push_back(v);
+                        for (const auto& l : rb.getLinks())
+                            for (double v : l.getPosition()) centres.push_back(v);
+                    }
+                }
+            std::map<std::pair<Index, Index>, bool> freePair;
+            if (!cand.empty()) {
+                const auto ok = freeSpace_.testBridge(static_cast<int>(i), centres, static_cast<int>(cand.size() * steps));
+                for (size_t c = 0; c < cand.size(); ++c) {
+                    bool all = true;
+                    for (size_t s = 0; s < steps; ++s) all = all && ok[c * steps + s];
+                    freePair[cand[c]] = all;
+                }
+            }
+            Index sAdj = sAdj0;
+            for (Index m0 = sCur; m0 < eCur; ++m0)
+                for (Index m1 = sAdj; m1 < eAdj; ++m1) {
+                    auto it = freePair.find({m0, m1});
+                    if (it == freePair.end()) continue;
+                    if (it->second) {
+                        addEdge(m0, m1);
+                        sAdj = m1;
+                        break;
+                    }
+                }
+        }
+    }
+
+    std::vector<Index> getNearestNeighborsOnGraph(const std::vector<Coordinate>& vertex, Index k, double radius) override {  // :284-342
+        const auto& V = res_.graphStructure.vertex;
+        const auto& lim = param_.boundaryLimits;
+        double minAngle = V[0][2], minD = std::fabs(vertex[2] - minAngle);
+        for (const auto& v : V) {
+            const double d = std::fabs(vertex[2] - v[2]);
+            if (d < minD) minD = d, minAngle = v[2];
+        }
+        std::vector<double> angList;
+        for (double h : headings_) {
+            if (std::fabs(minAngle - h) < radius) angList.push_back(h);
+            if (angList.size() >= k) break;
+        }
+        std::vector<Index> idx;
+        for (double ac : angList) {
+            Index idxSlice = 0;
+            double best = vectorEuclidean(vertex, V[0]);
+            for (size_t i = 0; i < V.size(); ++i) {
+                const double d = vectorEuclidean(vertex, V[i]);
+                if (d < best && std::fabs(V[i][2] - ac) < EPSILON) best = d, idxSlice = i;
+            }
+            if (std::abs(vertex[1] - V[idxSlice][1]) < radius * (lim[1] - lim[0]) / static_cast<double>(param_.numLineY)) idx.push_back(idxSlice);
+        }
+        return idx;
+    }
+
+    MultiBodyTree2D robot_;
+    FreeSpaceGPU2D freeSpace_;
+    std::vector<double> headings_;
+};
+
+}  // namespace planners
+}  // namespace hrm

@@ -99,3 +99,43 @@ def test_hrm3d_fast_mode_same_connectivity(oracle, gpu_ctx):
     assert np.max(np.abs(np.array(res.vertex) - ref["vertex"])) <= 1e-6
     assert np.array_equal(np.array(res.edge, dtype=np.int64).reshape(-1, 2), ref["edge"])
     assert res.solved == ref["solved"] is True
+
+
+# ---- the same parity through the C++ host layer (libhrmhost.so: hrm::planners::HRM3D / HRM2D over the C ABI) ----------
+@pytest.mark.parametrize("name", ["3D_superquadrics_sparse_rabbit", "3D_superquadrics_cluttered_rabbit", "3D_superquadrics_maze_rabbit",
+                                  "3D_superquadrics_narrow_rabbit"])
+@pytest.mark.parametrize("per_orientation", [False, True])
+def test_cpp_host_hrm3d_roadmap_identical(oracle, name, per_orientation):
+    from hrm_b200 import hostlib
+
+    sc = util.scenes()[name]
+    n = 10
+    rows = np.array(sc["arena"] + sc["obstacle"])
+    args = (len(sc["arena"]), len(sc["obstacle"]), rows, n, np.array(sc["robot"]), np.array(sc["quats"]), sc["lim"], sc["Lx"], sc["Ly"], 5,
+            sc["end_points"][0], sc["end_points"][1])
+    ref = oracle.plan3d(*args, per_orientation=per_orientation)
+    got = hostlib.plan3d(*args, per_orientation=per_orientation, precision=capi.F64_STRICT)
+    assert np.array_equal(got["vertex"], ref["vertex"])
+    assert np.array_equal(got["edge"], ref["edge"])
+    assert got["solved"] == ref["solved"]
+    assert got["edge_tests"] > 0 and got["gpu_launches"] > 0
+    if ref["solved"]:
+        assert got["path"][0] == ref["path"][0] and got["path"][-1] == ref["path"][-1]
+
+
+@pytest.mark.parametrize("name,Ly", [("2D_superellipse_sparse_rabbit", 3), ("2D_superellipse_cluttered_rabbit", 30),
+                                     ("2D_superellipse_maze2_rabbit", 30)])
+@pytest.mark.parametrize("per_orientation", [False, True])
+def test_cpp_host_hrm2d_roadmap_identical(oracle, name, Ly, per_orientation):
+    from hrm_b200 import hostlib
+
+    sc = util.scenes()[name]
+    num, num_slice = 50, 10 if Ly < 10 else 20
+    rows = np.array(sc["arena"] + sc["obstacle"])
+    args = (len(sc["arena"]), len(sc["obstacle"]), rows, num, np.array(sc["robot"]), num_slice, sc["lim"], Ly, 5, sc["end_points"][0],
+            sc["end_points"][1])
+    ref = oracle.plan2d(*args, per_orientation=per_orientation)
+    got = hostlib.plan2d(*args, per_orientation=per_orientation, precision=capi.F64_STRICT)
+    assert np.array_equal(got["vertex"], ref["vertex"])
+    assert np.array_equal(got["edge"], ref["edge"])
+    assert got["solved"] == ref["solved"]

@@ -21,6 +21,29 @@ def test_library_exports_every_declared_symbol():
     assert lib.hrmgpu_abi_version() == 1
 
 
+def test_cpp_host_library_loads_and_exports_planners():
+    from hrm_b200 import hostlib
+
+    lib = hostlib.load()
+    for n in ("hrmhost_plan3d", "hrmhost_plan2d", "hrmhost_last_error"):
+        assert hasattr(lib, n), n
+
+
+def test_cpp_host_fails_loudly_without_device():
+    import torch
+
+    from hrm_b200 import hostlib
+    from tests import util as u
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    sc = u.scenes()["3D_superquadrics_sparse_rabbit"]
+    rows = np.array(sc["arena"] + sc["obstacle"])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        hostlib.plan3d(1, len(sc["obstacle"]), rows, 10, np.array(sc["robot"]), np.array(sc["quats"][:2]), sc["lim"], sc["Lx"], sc["Ly"], 5,
+                       sc["end_points"][0], sc["end_points"][1])
+
+
 def test_no_cpu_fallback_without_device():
     import torch
 
