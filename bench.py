@@ -59,6 +59,33 @@ def cpu_layers_per_s(n_obs_sample, layers, threads):
     return layers * frac / sec, sec
 
 
+def plan_ms_block():
+    """Secondary metric of BASELINE.json ('end-to-end plan ms'): HRM3D::plan() on the bundled cluttered map (configs[1]:
+    1+7 superquadrics, rabbit robot, q_icosahedron_60, n=10, 11x5 lines) through the C++ host layer + GPU kernels, next to the
+    CPU oracle planner on one core.  Roadmaps are identical (tests/test_gpu_planner.py)."""
+    import json as _json
+
+    from hrm_b200 import hostlib
+    from oracle import hrmo
+
+    sc = _json.load(open(os.path.join(ROOT, "tests", "golden", "scenes.json")))["3D_superquadrics_cluttered_rabbit"]
+    rows = np.array(sc["arena"] + sc["obstacle"])
+    a = (1, len(sc["obstacle"]), rows, 10, np.array(sc["robot"]), np.array(sc["quats"]), sc["lim"], sc["Lx"], sc["Ly"], 5, sc["end_points"][0],
+         sc["end_points"][1])
+    t = []
+    for _ in range(4):
+        t0 = time.perf_counter()
+        got = hostlib.plan3d(*a, per_orientation=True, precision=0)
+        t.append((time.perf_counter() - t0) * 1e3)
+    t0 = time.perf_counter()
+    ref = hrmo.plan3d(*a, per_orientation=True)
+    cpu_ms = (time.perf_counter() - t0) * 1e3
+    return {"scene": "HRM3D cluttered/rabbit (BASELINE.json configs[1]), 60 C-layers, n=10, 11x5 lines, per-orientation, F64_STRICT",
+            "gpu_plan_ms": sorted(t[1:])[len(t[1:]) // 2], "cpu_oracle_plan_ms": cpu_ms, "cpu_cores": 1, "solved": bool(got["solved"]),
+            "vertices": int(len(got["vertex"])), "edges": int(len(got["edge"])), "identical_roadmap": bool(
+                np.array_equal(got["vertex"], ref["vertex"]) and np.array_equal(got["edge"], ref["edge"]))}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -279,6 +306,12 @@ def run_gpu(args):
             cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": "%d full layers (1 per host thread, %d threads) of the same workload, %.1f s; oracle = CPU restatement "
                              "of the reference (reference not buildable here: Eigen absent)" % (threads, threads, sec)}
+        plan = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                plan = plan_ms_block()
+            except Exception as e:  # the headline metric must not depend on the secondary one
+                plan = {"error": str(e)}
         cfg = workload_config(layers, n_obs)
         cfg["precision_mode"] = args.precision
         cfg["exchange"] = "all-gather of free segments per step (NCCL)" if world > 1 else "none (1 GPU)"
@@ -292,7 +325,7 @@ def run_gpu(args):
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
-            "gpu_launches": launches, "clocks": clocks.summary(),
+            "gpu_launches": launches, "clocks": clocks.summary(), "plan": plan,
         }
     if world > 1:
         dist.barrier()

@@ -169,6 +169,9 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
     auto pack_code = [](uint32_t cx, uint32_t cy) -> Code { return static_cast<Code>(CODE8 ? (cx | (cy << 8)) : (cx | (cy << 16))); };
     // expanded form used by the SIMD min/max tests: x code in bits 0..15, y code in bits 16..31
     auto code_at = [&](int q) -> uint32_t { return CODE8 ? __byte_perm(static_cast<uint32_t>(vcode[q]), 0u, 0x4140) : static_cast<uint32_t>(vcode[q]); };
+    unsigned char* fbits = smem_raw + ofs;                                // [(n-1) * ceil((n-1)/4)] face keep bits, one byte per unit
+    const size_t fbytes = ((static_cast<size_t>(n - 1) * ((n + 2) >> 2) + 3) & ~size_t(3)) + 16;
+    ofs += SWEEP ? ((fbytes + 15) & ~size_t(15)) : 0;
     double* zc0 = reinterpret_cast<double*>(smem_raw + ofs);             // [L] committed z of the two lowest hit faces
     double* zc1 = zc0 + (SWEEP ? p.L : 0);                                // [L]
     ofs += SWEEP ? sizeof(double) * 2 * p.L : 0;
@@ -184,6 +187,7 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
         for (int i = tid; i < p.Lx + 2; i += kThreads) txs[i] = __ldg(p.txs + i);
         for (int i = tid; i < p.Ly + 2; i += kThreads) tys[i] = __ldg(p.tys + i);
         for (int i = tid; i < p.L; i += kThreads) m0[i] = kNoFace, m1[i] = kNoFace;
+        for (int i = tid; i < static_cast<int>(fbytes >> 2); i += kThreads) reinterpret_cast<uint32_t*>(fbits)[i] = 0u;
         if (tid == 0) *qcount = 0;
     }
     const Obj3& ob = p.obj[obj_id];
@@ -431,41 +435,29 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
     // commits the per-line two lowest hit faces with their z, and resumes scanning.
     const int nc1 = n - 1;
     const int ncell = nc1 * nc1;
-    // Every thread owns units of 4 consecutive cells (i, j0..j0+3), i = grp + groups*s, j0 = 4*(ln + lpc*t), enumerated
-    // ui = s*Tn + t, in chunks of 4 units (16 cells, 32 faces).  B1 builds a register bitmask of the faces whose line set
-    // is non-empty (exact integer test on 128-bit loads of the vertex codes); B2 expands the few set bits into queue entries.
-    const int Tn = (nc1 + 4 * p.lpc - 1) / (4 * p.lpc);
-    const int Sn = (nc1 + p.groups - 1) / p.groups;
-    const int nunit = Sn * Tn;  // the same for every thread, so the chunk loop below is warp-uniform
+    // B1: every thread owns units of 4 consecutive cells (i, j0..j0+3), i = grp + groups*s, j0 = 4*(ln + lpc*t), and
+    // writes one byte of "line set non-empty" bits per unit (8 faces) into `fbits` (exact integer test on 128/64-bit loads of
+    // the vertex codes).  B2: the warps then walk the bit array 32 words at a time and balance the few set bits over their
+    // lanes (prefix sum of popcounts + rank search), so no lane works through a long private list and every queue
+    // reservation is one shared-memory atomic per warp.
+    const int UPR = (nc1 + 3) >> 2;            // units per mesh row
+    const int nunits = nc1 * UPR;
+    const int nwords = (nunits + 3) >> 2;      // 4 unit bytes per 32-bit word
+    const uint32_t upr_magic = (UPR > 1) ? 0xFFFFFFFFu / static_cast<uint32_t>(UPR) + 1u : 0u;  // u / UPR == umulhi(u, magic), u < 2^16
     const bool vec_ok = (n & 3) == 0;
-    // ui / Tn == umulhi(ui, magic) for ui < 2^16 and Tn >= 2 (Tn == 1, the common case, needs no division)
-    const uint32_t tn_magic = (Tn > 1) ? 0xFFFFFFFFu / static_cast<uint32_t>(Tn) + 1u : 0u;
-    const int lane = tid & 31;
+    const int lane = tid & 31, warp = tid >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
-    int chunk = 0;
-    uint32_t mask = 0;
-    bool have_mask = false;
-    uint32_t six = 0, siy = 0;                  // next line of the open face to push
-    bool face_open = false;
-    uint32_t f_lox = 0, f_loy = 0, f_hix = 0, f_hiy = 0, f_id = 0;
-    bool scanning = true;  // warp-uniform
-    for (;;) {
-        while (scanning) {
-            if (!have_mask) {
-                if (chunk * 4 >= nunit) {
-                    scanning = false;
-                    break;
-                }
-                long long tb = 0;
-                if (p.dbg) tb = clock64();
-                mask = 0;
-                const int ui0 = chunk * 4;
-                int s_ = ui0 / Tn, t_ = ui0 - s_ * Tn;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int i = grp + p.groups * s_, j0 = 4 * (ln + p.lpc * t_);
-                    const bool uvalid = worker && (ui0 + u < nunit) && (i < nc1) && (j0 < nc1);
-                    const int q = uvalid ? i * n + j0 : 0;
+    {
+        long long tb = 0;
+        if (p.dbg) tb = clock64();
+        const int Tn = (UPR + p.lpc - 1) / p.lpc;
+        if (worker) {
+            for (int i = grp; i < nc1; i += p.groups) {
+                for (int t = 0; t < Tn; ++t) {
+                    const int jq = ln + p.lpc * t;
+                    if (jq >= UPR) break;
+                    const int j0 = 4 * jq;
+                    const int q = i * n + j0;
                     uint32_t r0[5], r1[5];
                     if (vec_ok && !CODE8) {
                         const uint4 a = *reinterpret_cast<const uint4*>(vcode + q);
@@ -485,9 +477,10 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
                     }
                     r0[4] = code_at(q + 4);
                     r1[4] = code_at(q + n + 4);
+                    uint32_t bits = 0;
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const bool valid = uvalid && (j0 + e < nc1);
+                        const bool valid = j0 + e < nc1;
                         const uint32_t c00 = r0[e], c01 = r0[e + 1], c10 = r1[e], c11 = r1[e + 1];
                         // exact emptiness test of both faces' line sets, branch free.  Per axis with mn = min code,
                         // mx = max code (code = 2*lo + eq): lines [mn>>1, (mx+1)>>1) is non-empty  <=>  (mx & 1) || (mn|1) < mx.
@@ -499,25 +492,79 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
                         const uint32_t dB = (mxB | 0x80008000u) - (mnB | 0x00010001u) - 0x00010001u;
                         const uint32_t keepA = (valid && ((((dA >> 15) | mxA) & 0x00010001u) == 0x00010001u)) ? 1u : 0u;
                         const uint32_t keepB = (valid && ((((dB >> 15) | mxB) & 0x00010001u) == 0x00010001u)) ? 1u : 0u;
-                        mask |= (keepA | (keepB << 1)) << (8 * u + 2 * e);
+                        bits |= (keepA | (keepB << 1)) << (2 * e);
                     }
-                    if (++t_ == Tn) t_ = 0, ++s_;
+                    fbits[i * UPR + jq] = static_cast<unsigned char>(bits);
                 }
-                have_mask = true;
-                if (p.dbg) acc_b1 += clock64() - tb;
             }
-            // B2, warp-aggregated: every iteration each lane offers at most one (face, line) candidate; one shared-memory
-            // atomic per warp reserves the queue slots (per-lane atomics on the single counter serialise badly).
-            long long tb2 = 0;
-            if (p.dbg) tb2 = clock64();
+        }
+        if (p.dbg) acc_b1 += clock64() - tb;
+    }
+    __syncwarp();
+    __syncthreads();
+
+    // B2 state of a warp: batch of 32 words [bw*32, bw*32+32), its words / popcount prefix, the rank chunk r0, and per lane
+    // the open face with the next line to push.
+    const uint32_t* fwords = reinterpret_cast<const uint32_t*>(fbits);
+    int bw = warp;                 // current batch (warp-uniform)
+    bool batch_loaded = false;
+    uint32_t w_bits = 0, w_cnt = 0, w_incl = 0, w_total = 0;
+    uint32_t r0c = 0;              // first rank of the current chunk of 32 set bits
+    bool chunk_started = false;    // warp-uniform: the lanes have taken their set bit of the current chunk
+    bool face_open = false;
+    uint32_t six = 0, siy = 0, f_lox = 0, f_loy = 0, f_hix = 0, f_hiy = 0, f_id = 0;
+    bool scanning = true;          // warp-uniform
+    for (;;) {
+        long long tb2 = 0;
+        if (p.dbg) tb2 = clock64();
+        while (scanning) {
+            if (!batch_loaded) {
+                if (bw * 32 >= nwords) {
+                    scanning = false;
+                    break;
+                }
+                const int widx = bw * 32 + lane;
+                w_bits = (widx < nwords) ? fwords[widx] : 0u;
+                w_cnt = __popc(w_bits);
+                w_incl = w_cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, w_incl, o);
+                    if (lane >= o) w_incl += t;
+                }
+                w_total = __shfl_sync(0xFFFFFFFFu, w_incl, 31);
+                batch_loaded = true;
+                r0c = 0;
+                chunk_started = false;
+                face_open = false;
+                if (w_total == 0u) {  // nothing in these 32 words
+                    batch_loaded = false;
+                    bw += kThreads / 32;
+                    continue;
+                }
+            }
             bool parked = false;
-            for (;;) {
-                if (!parked && !face_open) {
-                    while (mask) {
-                        const int bpos = __ffs(mask) - 1;
-                        const int ui = chunk * 4 + (bpos >> 3), half = bpos & 1;
-                        const int s_ = (Tn > 1) ? static_cast<int>(__umulhi(static_cast<uint32_t>(ui), tn_magic)) : ui, t_ = ui - s_ * Tn;
-                        const int i = grp + p.groups * s_, j = 4 * (ln + p.lpc * t_) + ((bpos >> 1) & 3);
+            while (r0c < w_total) {
+                if (!chunk_started) {  // warp-uniform branch: every lane takes set bit number r0c + lane of the batch
+                    chunk_started = true;
+                    const uint32_t rank = r0c + lane;
+                    // smallest source lane whose inclusive prefix exceeds rank (binary search with shuffles)
+                    int src = 0;
+#pragma unroll
+                    for (int step = 16; step > 0; step >>= 1) {
+                        const uint32_t v = __shfl_sync(0xFFFFFFFFu, w_incl, (src + step - 1) & 31);
+                        if (v <= rank) src += step;
+                    }
+                    src &= 31;
+                    const uint32_t wsrc = __shfl_sync(0xFFFFFFFFu, w_bits, src);
+                    const uint32_t excl = __shfl_sync(0xFFFFFFFFu, w_incl - w_cnt, src);
+                    if (rank < w_total) {
+                        uint32_t x = wsrc;
+                        for (uint32_t k = rank - excl; k > 0; --k) x &= x - 1;  // drop the lower set bits of that word
+                        const int bit = __ffs(x) - 1;
+                        const int unit = (bw * 32 + src) * 4 + (bit >> 3), half = bit & 1;
+                        const int i = (UPR > 1) ? static_cast<int>(__umulhi(static_cast<uint32_t>(unit), upr_magic)) : unit;
+                        const int j = 4 * (unit - i * UPR) + ((bit >> 1) & 3);
                         const int q = i * n + j;
                         const uint32_t c00 = code_at(q), c11 = code_at(q + n + 1);
                         const uint32_t cm = half ? code_at(q + 1) : code_at(q + n);
@@ -529,35 +576,42 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
                         f_id = static_cast<uint32_t>(i * nc1 + j + (half ? ncell : 0));
                         six = f_lox, siy = f_loy;
                         face_open = true;  // B1's test is exact: the line set of a set bit is never empty
+                    }
+                }
+                // push the lines of the open faces, one per lane per iteration, one atomic per warp
+                for (;;) {
+                    const bool has = face_open;
+                    const unsigned bal = __ballot_sync(0xFFFFFFFFu, has);
+                    if (bal == 0u) break;
+                    int base = 0;
+                    const int leader = __ffs(bal) - 1;
+                    if (lane == leader) base = atomicAdd(qcount, __popc(bal));
+                    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                    bool over = false;
+                    if (has) {
+                        const int pos = base + __popc(bal & lt_mask);
+                        if (pos < static_cast<int>(kPosMask)) {  // slots 0..kPosMask-1; kPosMask is the 'committed' marker
+                            queue[pos] = make_uint2(f_id, six | (siy << 16));
+                            if (++siy == f_hiy) siy = f_loy, ++six;
+                            if (six >= f_hix) face_open = false;
+                        } else {
+                            over = true;  // queue full: keep the position, resume after the drain
+                        }
+                    }
+                    if (__any_sync(0xFFFFFFFFu, over)) {
+                        parked = true;
                         break;
                     }
                 }
-                const bool has = face_open && !parked;
-                const unsigned bal = __ballot_sync(0xFFFFFFFFu, has);
-                if (bal == 0u) break;
-                int base = 0;
-                const int leader = __ffs(bal) - 1;
-                if (lane == leader) base = atomicAdd(qcount, __popc(bal));
-                base = __shfl_sync(0xFFFFFFFFu, base, leader);
-                if (has) {
-                    const int pos = base + __popc(bal & lt_mask);
-                    if (pos < static_cast<int>(kPosMask)) {  // slots 0..kPosMask-1; kPosMask is the 'committed' marker
-                        queue[pos] = make_uint2(f_id, six | (siy << 16));
-                        if (++siy == f_hiy) siy = f_loy, ++six;
-                        if (six >= f_hix) {
-                            face_open = false;
-                            mask &= mask - 1;
-                        }
-                    } else {
-                        parked = true;  // queue full: keep the position, resume after the drain
-                    }
-                }
+                if (parked) break;
+                r0c += 32;  // all lanes finished their face of this chunk
+                chunk_started = false;
             }
-            if (p.dbg) acc_b2 += clock64() - tb2;
-            if (__any_sync(0xFFFFFFFFu, parked)) break;
-            have_mask = false;
-            ++chunk;
+            if (parked) break;
+            batch_loaded = false;
+            bw += kThreads / 32;
         }
+        if (p.dbg) acc_b2 += clock64() - tb2;
         if (p.dbg && rounds == 0) {
             atomicMax(&dbg_max[0], (unsigned long long)acc_b1);
             atomicMax(&dbg_max[1], (unsigned long long)acc_b2);
@@ -651,6 +705,7 @@ static size_t smem_bytes(int MODE, bool sweep, bool code8, int n, int Lx, int Ly
         b += (sizeof(double) * (Lx + Ly + 4) + 15) & ~size_t(15);
         b += sizeof(double) * kQueueCap + sizeof(uint2) * kQueueCap;
         b += ((code8 ? 2 : 4) * (static_cast<size_t>(n) * n + 8) + 15) & ~size_t(15);
+        b += ((((static_cast<size_t>(n - 1) * ((n + 2) >> 2) + 3) & ~size_t(3)) + 16) + 15) & ~size_t(15);
         b += sizeof(double) * 2 * static_cast<size_t>(Lx) * Ly;
         b += (sizeof(uint32_t) * 2 * static_cast<size_t>(Lx) * Ly + 15) & ~size_t(15);
     }
