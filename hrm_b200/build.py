@@ -61,8 +61,16 @@ def build(force=False, verbose=False):
     host_src = [os.path.join(HOST_DIR, f) for f in sorted(os.listdir(HOST_DIR)) if f.endswith(".cpp")]
     host_dep = host_src + [os.path.join(HOST_DIR, f) for f in os.listdir(HOST_DIR) if f.endswith(".hpp")] + [LIB, headers[-1]]
     if force or _stale(HOST_LIB, host_dep):
-        run([os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-Wall", "-shared", "-o", HOST_LIB] + host_src +
+        run([os.environ.get("HRM_CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-Wall", "-shared", "-o", HOST_LIB] + host_src +
             ["-L" + LIBDIR, "-lhrmgpu", "-Wl,-rpath,$ORIGIN"])
+    # command-line twins of the reference's benchmark drivers
+    apps = os.path.join(HOST_DIR, "apps")
+    for f in sorted(os.listdir(apps)):
+        if f.endswith(".cpp"):
+            exe = os.path.join(LIBDIR, f[:-4])
+            if force or _stale(exe, [os.path.join(apps, f)] + host_dep):
+                run([os.environ.get("HRM_CXX", "g++"), "-O2", "-std=c++17", "-ffp-contract=off", "-Wall", "-o", exe, os.path.join(apps, f),
+                     "-I" + os.path.join(HERE, "..", "include"), "-L" + LIBDIR, "-lhrmgpu", "-Wl,-rpath,$ORIGIN"])
     return LIB
 
 

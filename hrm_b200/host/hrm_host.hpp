@@ -369,6 +369,8 @@ class FreeSpaceGPU {
         return out;
     }
     long long kernelLaunches() { return hrmgpu_kernel_launches(ctx_, 0); }
+    /** {K, B, S, n_arena, L, M, total segments, dim} of the last build (hrmgpu_get_dims) */
+    void dims(long long d[8]) { check(hrmgpu_get_dims(ctx_, d)); }
     hrmgpu_ctx* handle() { return ctx_; }
 
   protected:

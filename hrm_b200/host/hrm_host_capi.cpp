@@ -2,7 +2,7 @@
 // caller — can run the GPU-backed planners.  Argument layout mirrors the reference's scene files after
 // parsePlanningConfig: superquadric rows [a,b,c,e1,e2,px,py,pz,qw,qx,qy,qz], superellipse rows [a,b,eps,px,py,angle],
 // robot rows = base first, links relative to the base (resources/readme.md).
-#include "hrm_host.hpp"
+#include "hrm_io.hpp"
 
 #include <cstring>
 
@@ -92,6 +92,124 @@ int hrmhost_plan2d(int n_arena, int n_obs, const double* se, int num, int B, con
         planners::HRM2D hrm(rb, arena, obs, req, device, precision, per_orientation != 0);
         hrm.plan();
         exportResult(hrm, info, vertex, cap_v, 3, edge, cap_e, path, cap_p);
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+
+// ---- scene / config I/O (hrm_io.hpp) ---------------------------------------------------------------------------------
+// parse2DCsvFile: rows flattened with a fixed stride; row_len[i] = number of cells of record i.  Returns the record
+// count (which may exceed cap_rows: call again with a larger buffer) or -1.
+long hrmhost_parse_csv(const char* filename, double* out, int stride, int* row_len, long cap_rows) {
+    try {
+        const auto data = parse2DCsvFile(filename);
+        for (size_t i = 0; i < data.size() && static_cast<long>(i) < cap_rows; ++i) {
+            row_len[i] = static_cast<int>(data[i].size());
+            for (size_t j = 0; j < data[i].size() && static_cast<int>(j) < stride; ++j) out[static_cast<size_t>(stride) * i + j] = data[i][j];
+        }
+        return static_cast<long>(data.size());
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+// parsePlanningConfig(objectType, envType, robotType, dim) with explicit resources / config directories
+int hrmhost_parse_planning_config(const char* objectType, const char* envType, const char* robotType, const char* dim, const char* resources,
+                                  const char* config) {
+    try {
+        Paths p = Paths::fromEnv();
+        p.resources = resources;
+        p.config = config;
+        parsePlanningConfig(objectType, envType, robotType, dim, p);
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+// PlannerSetting::loadEnvironment + loadRobotMultiBody* + defineParameters on a config directory (prefix ends in '/').
+// counts[8] = n_arena, n_obs, n_robot_bodies, n_end_points, n_quats, numLineX, numLineY, numSlice.  Object rows have
+// stride 12 (3D: a,b,c,e1,e2,px,py,pz,qw,qx,qy,qz) or 6 (2D), end points stride 16, quats w,x,y,z, lim[6|4].
+// Robot link rows are the links as stored in the tree (relative to the base, like the file).
+int hrmhost_load_scene(const char* dim, const char* config_prefix, const char* quat_file, int num_param, int numLineX, int numLineY, long* counts,
+                       double* arena, double* obstacle, double* robot, double* ends, double* quats, double* lim, long cap_rows) {
+    try {
+        PlannerParameter param;
+        param.numLineX = static_cast<Index>(numLineX), param.numLineY = static_cast<Index>(numLineY);
+        std::vector<std::vector<double>> endPts;
+        auto put = [&](double* dst, long i, const std::vector<double>& row, int stride) {
+            if (i < cap_rows)
+                for (size_t j = 0; j < row.size() && static_cast<int>(j) < stride; ++j) dst[stride * i + static_cast<long>(j)] = row[j];
+        };
+        if (std::string(dim) == "3D") {
+            PlannerSetting3D env(num_param);
+            env.loadEnvironment(config_prefix);
+            const MultiBodyTree3D rb = loadRobotMultiBody3D(config_prefix, quat_file, num_param);
+            defineParameters(rb, env, param);
+            auto row = [](const SuperQuadrics& s) {
+                std::vector<double> r = s.getSemiAxis();
+                r.insert(r.end(), s.getEpsilon().begin(), s.getEpsilon().end());
+                r.insert(r.end(), s.getPosition().begin(), s.getPosition().end());
+                r.insert(r.end(), s.getQuaternion().begin(), s.getQuaternion().end());
+                return r;
+            };
+            for (size_t i = 0; i < env.getArena().size(); ++i) put(arena, static_cast<long>(i), row(env.getArena()[i]), 12);
+            for (size_t i = 0; i < env.getObstacle().size(); ++i) put(obstacle, static_cast<long>(i), row(env.getObstacle()[i]), 12);
+            put(robot, 0, row(rb.getBase()), 12);
+            for (size_t i = 0; i < rb.getLinks().size(); ++i) put(robot, static_cast<long>(i) + 1, row(rb.getLinks()[i]), 12);
+            const auto& qs = rb.getBase().getQuatSamples();
+            for (size_t i = 0; i < qs.size(); ++i) put(quats, static_cast<long>(i), {qs[i][0], qs[i][1], qs[i][2], qs[i][3]}, 4);
+            counts[0] = static_cast<long>(env.getArena().size()), counts[1] = static_cast<long>(env.getObstacle().size());
+            counts[2] = static_cast<long>(rb.getNumLinks()) + 1, counts[4] = static_cast<long>(qs.size());
+            endPts = env.getEndPoints();
+        } else {
+            PlannerSetting2D env(num_param);
+            env.loadEnvironment(config_prefix);
+            const MultiBodyTree2D rb = loadRobotMultiBody2D(config_prefix, num_param);
+            defineParameters(rb, env, param);
+            auto row = [](const SuperEllipse& s) {
+                return std::vector<double>{s.getSemiAxis()[0], s.getSemiAxis()[1], s.getEpsilon(), s.getPosition()[0], s.getPosition()[1], s.getAngle()};
+            };
+            for (size_t i = 0; i < env.getArena().size(); ++i) put(arena, static_cast<long>(i), row(env.getArena()[i]), 6);
+            for (size_t i = 0; i < env.getObstacle().size(); ++i) put(obstacle, static_cast<long>(i), row(env.getObstacle()[i]), 6);
+            put(robot, 0, row(rb.getBase()), 6);
+            for (size_t i = 0; i < rb.getLinks().size(); ++i) put(robot, static_cast<long>(i) + 1, row(rb.getLinks()[i]), 6);
+            counts[0] = static_cast<long>(env.getArena().size()), counts[1] = static_cast<long>(env.getObstacle().size());
+            counts[2] = static_cast<long>(rb.getNumLinks()) + 1, counts[4] = 0;
+            endPts = env.getEndPoints();
+        }
+        for (size_t i = 0; i < endPts.size(); ++i) put(ends, static_cast<long>(i), endPts[i], 16);
+        counts[3] = static_cast<long>(endPts.size());
+        counts[5] = static_cast<long>(param.numLineX), counts[6] = static_cast<long>(param.numLineY), counts[7] = static_cast<long>(param.numSlice);
+        for (size_t i = 0; i < param.boundaryLimits.size(); ++i) lim[i] = param.boundaryLimits[i];
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+// storeGraphInfo + storePathInfo on a caller-supplied roadmap (the writers' formats can be checked without a GPU)
+int hrmhost_store_result(const char* details_dir, const char* suffix, int vdim, long n_vertex, const double* vertex, long n_edge, const long* edge,
+                         long n_path, const long* path) {
+    try {
+        Paths p = Paths::fromEnv();
+        p.details = details_dir;
+        Graph g;
+        for (long i = 0; i < n_vertex; ++i) g.vertex.emplace_back(vertex + vdim * i, vertex + vdim * (i + 1));
+        for (long i = 0; i < n_edge; ++i) g.edge.emplace_back(static_cast<Index>(edge[2 * i]), static_cast<Index>(edge[2 * i + 1]));
+        SolutionPathInfo sp;
+        for (long i = 0; i < n_path; ++i) {
+            sp.PathId.push_back(static_cast<Index>(path[i]));
+            sp.solvedPath.push_back(g.vertex.at(static_cast<size_t>(path[i])));
+        }
+        storeGraphInfo(g, suffix, p);
+        storePathInfo(sp, suffix, p);
         return 0;
     } catch (const std::exception& e) {
         g_err = e.what();

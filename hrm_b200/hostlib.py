@@ -64,3 +64,55 @@ def plan2d(n_arena, n_obs, se6, num, robot_rows, num_slice, lim, Ly, num_point, 
     if rc != 0:
         raise RuntimeError(load().hrmhost_last_error().decode())
     return _out(info, vertex, edge, path)
+
+
+# ---- scene / config I/O (hrm_b200/host/hrm_io.hpp) --------------------------------------------------------------------
+def _err():
+    return RuntimeError(load().hrmhost_last_error().decode())
+
+
+def parse_csv(filename, stride=32, cap_rows=1 << 16):
+    """hrm::parse2DCsvFile: list of rows (std::stof cells, '#' comments skipped)."""
+    lib = load()
+    lib.hrmhost_parse_csv.restype = C.c_long
+    out = np.zeros((cap_rows, stride))
+    row_len = np.zeros(cap_rows, dtype=np.int32)
+    n = lib.hrmhost_parse_csv(filename.encode(), _p(out), C.c_int(stride), _p(row_len), C.c_long(cap_rows))
+    if n < 0:
+        raise _err()
+    return [out[i, :row_len[i]].tolist() for i in range(min(n, cap_rows))]
+
+
+def parse_planning_config(object_type, env_type, robot_type, dim, resources, config):
+    """hrm::parsePlanningConfig: resources/<dim>/*.csv (angle-axis) -> config/*_config_<dim>.csv (quaternion)."""
+    rc = load().hrmhost_parse_planning_config(object_type.encode(), env_type.encode(), robot_type.encode(), dim.encode(), resources.encode(),
+                                              config.encode())
+    if rc != 0:
+        raise _err()
+
+
+def load_scene(dim, config_prefix, quat_file="0", num_param=10, num_line_x=0, num_line_y=0, cap_rows=4096):
+    """PlannerSetting::loadEnvironment + loadRobotMultiBody{2,3}D + defineParameters on a config directory."""
+    w = 12 if dim == "3D" else 6
+    counts = np.zeros(8, dtype=np.int64)
+    arena, obstacle, robot = np.zeros((cap_rows, w)), np.zeros((cap_rows, w)), np.zeros((cap_rows, w))
+    ends, quats, lim = np.zeros((cap_rows, 16)), np.zeros((cap_rows, 4)), np.zeros(6)
+    rc = load().hrmhost_load_scene(dim.encode(), config_prefix.encode(), quat_file.encode(), C.c_int(num_param), C.c_int(num_line_x),
+                                   C.c_int(num_line_y), _p(counts), _p(arena), _p(obstacle), _p(robot), _p(ends), _p(quats), _p(lim),
+                                   C.c_long(cap_rows))
+    if rc != 0:
+        raise _err()
+    na, no, nr, ne, nq, lx, ly, ns = (int(v) for v in counts)
+    return {"arena": arena[:na].copy(), "obstacle": obstacle[:no].copy(), "robot": robot[:nr].copy(), "end_points": ends[:ne].copy(),
+            "quats": quats[:nq].copy(), "lim": lim[: 6 if dim == "3D" else 4].copy(), "Lx": lx, "Ly": ly, "numSlice": ns}
+
+
+def store_result(details_dir, suffix, vertex, edge, path):
+    """hrm::storeGraphInfo + hrm::storePathInfo (vertex_/edge_/path_id_/solution_path_/interpolated_path_<suffix>.csv)."""
+    vertex = _d(vertex)
+    edge = np.ascontiguousarray(edge, dtype=np.int64).reshape(-1, 2)
+    path = np.ascontiguousarray(path, dtype=np.int64)
+    rc = load().hrmhost_store_result(details_dir.encode(), suffix.encode(), C.c_int(vertex.shape[1]), C.c_long(vertex.shape[0]), _p(vertex),
+                                     C.c_long(edge.shape[0]), _p(edge), C.c_long(path.shape[0]), _p(path))
+    if rc != 0:
+        raise _err()

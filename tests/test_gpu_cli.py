@@ -1,0 +1,86 @@
+"""End-to-end run of hrm_b200/lib/BenchHRM3D (command-line twin of the reference's test/benchmark/BenchHRM3D.cpp): resources
+tree -> parsePlanningConfig -> loadEnvironment -> GPU-backed HRM3D -> time_high_3D.csv + vertex/edge/path/segment dumps.
+The resources tree is rebuilt from tests/golden/scenes.json (the reference's own files are not on the GPU box); the oracle
+plans on exactly the numbers the CLI parsed (hostlib.load_scene on the same config directory)."""
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from hrm_b200 import hostlib
+from tests import util
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "hrm_b200", "lib", "BenchHRM3D")
+
+
+def _angle_axis_row(row):
+    """[a,b,c,e1,e2,x,y,z,qw,qx,qy,qz] -> the resource format [..., ax,ay,az,angle]."""
+    w, x, y, z = row[8:12]
+    nv = math.sqrt(x * x + y * y + z * z)
+    axis = [x / nv, y / nv, z / nv] if nv > 0 else [0.0, 0.0, 1.0]
+    return list(row[:8]) + axis + [2.0 * math.atan2(nv, w)]
+
+
+def _write(path, rows):
+    with open(path, "w") as f:
+        f.write("# generated from tests/golden/scenes.json\n")
+        for r in rows:
+            f.write(",".join("%.9g" % v for v in r) + "\n")
+
+
+def make_resources(sc, root, env="t", robot="r"):
+    os.makedirs(root / "3D"), os.makedirs(root / "SO3_sequence")
+    _write(root / "3D" / f"env_superquadrics_{env}_3D_arena.csv", [_angle_axis_row(r) for r in sc["arena"]])
+    _write(root / "3D" / f"env_superquadrics_{env}_3D_obstacle.csv", [_angle_axis_row(r) for r in sc["obstacle"]])
+    _write(root / "3D" / f"robot_{robot}_3D.csv", [_angle_axis_row(r) for r in sc["robot"]])
+    ends = []
+    for e in sc["end_points"]:
+        aa = _angle_axis_row([0] * 8 + list(e[3:7]))
+        ends.append(list(e[:3]) + aa[8:12])
+    _write(root / "3D" / f"setting_superquadrics_{env}_3D.csv", ends)
+    _write(root / "SO3_sequence" / f"q_icosahedron_{len(sc['quats'])}.csv", [[q[1], q[2], q[3], q[0]] for q in sc["quats"]])
+
+
+@pytest.mark.parametrize("name", ["3D_superquadrics_sparse_rabbit", "3D_superquadrics_cluttered_rabbit"])
+def test_bench_hrm3d_cli(oracle, name, tmp_path):
+    sc = util.scenes()[name]
+    res, cfg, out = tmp_path / "resources", tmp_path / "config", tmp_path / "result"
+    make_resources(sc, res)
+    os.makedirs(cfg), os.makedirs(out / "details"), os.makedirs(out / "benchmark")
+    env = dict(os.environ, HRM_RESOURCES_PATH=str(res), HRM_CONFIG_PATH=str(cfg), HRM_RESULT_PATH=str(out), HRM_STORE_DETAILS="1")
+    ns = len(sc["quats"])
+    p = subprocess.run([EXE, "t", "r", "2", "60", str(ns), "icosahedron"], env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert f"Initial number of C-slices: {ns}" in p.stdout and "Number of valid configurations:" in p.stdout
+
+    # what the CLI planned on, and the oracle's roadmap for exactly those numbers
+    got = hostlib.load_scene("3D", str(cfg) + "/", str(res / "SO3_sequence" / f"q_icosahedron_{ns}.csv"))
+    assert got["numSlice"] == ns and np.array_equal(got["quats"], np.array(sc["quats"]))
+    assert np.allclose(got["obstacle"], np.array(sc["obstacle"]), rtol=2e-5, atol=2e-6)  # %g round trip of the angle-axis detour
+    rows = np.vstack([got["arena"], got["obstacle"]])
+    ref = oracle.plan3d(len(got["arena"]), len(got["obstacle"]), rows, 10, got["robot"], got["quats"], got["lim"], got["Lx"], got["Ly"], 5,
+                        got["end_points"][0][:7], got["end_points"][1][:7], per_orientation=False)
+
+    stats = (out / "benchmark" / "time_high_3D.csv").read_text().strip().split("\n")
+    assert stats[0] == "SUCCESS,BUILD_TIME,SEARCH_TIME,PLAN_TIME,N_LAYERS,N_X,N_Y,GRAPH_NODE,GRAPH_EDGE,PATH_NODE"
+    assert len(stats) == 3
+    for line in stats[1:]:
+        c = line.split(",")
+        assert int(c[0]) == int(ref["solved"]) and int(c[4]) == ns and (int(c[5]), int(c[6])) == (got["Lx"], got["Ly"])
+        assert int(c[7]) == len(ref["vertex"]) and int(c[8]) == len(ref["edge"]) and int(c[9]) == len(ref["path"])
+
+    V = np.array([[float(v) for v in l.rstrip(",").split(",")] for l in (out / "details" / "vertex_hrm_3D.csv").read_text().strip().split("\n")])
+    assert V.shape == ref["vertex"].shape and np.allclose(V, ref["vertex"], rtol=1e-5, atol=1e-5)  # file holds 6 significant digits
+    E = np.array([[int(v) for v in l.split(",")] for l in (out / "details" / "edge_hrm_3D.csv").read_text().strip().split("\n")])
+    assert np.array_equal(E, ref["edge"])
+    ids = [int(v) for v in (out / "details" / "path_id_hrm_3D.csv").read_text().rstrip(",").split(",") if v]
+    assert ids == [int(v) for v in ref["path"]]
+    seg = (out / "details" / "segment_hrm_3D.csv").read_text().strip().split("\n")
+    assert len(seg) > 0 and all(len(l.split(",")) == 5 for l in seg)
+    bound = (out / "details" / "mink_bound_hrm_3D.csv").read_text().rstrip("\n").split("\n")
+    assert len(bound) == 3 * (len(got["arena"]) + len(got["obstacle"])) * len(got["robot"])
+    assert all(len(l.split()) == 100 for l in bound)
