@@ -183,6 +183,7 @@ int hrmgpu_set_scene3d(hrmgpu_ctx* c, int n_arena, int n_obs, const double* sq, 
         o.px = r[5], o.py = r[6], o.pz = r[7];
         for (int j = 0; j < 9; ++j) o.R[j] = r[8 + j];
         o.sign = (i < n_arena) ? -1.0 : 1.0;
+        o.ia = 1.0 / o.a, o.ib = 1.0 / o.b, o.ic = 1.0 / o.c;
         double* t = tab.data() + static_cast<size_t>(i) * 8 * n;
         for (int j = 0; j < n; ++j) {
             t[0 * n + j] = power_fn(eta[j], e1, false);

@@ -25,6 +25,7 @@ struct Obj3 {
     double px, py, pz;
     double R[9];
     double sign;  // -1 arena (Minkowski difference), +1 obstacle (sum): SuperQuadrics.cpp:84-85
+    double ia, ib, ic;  // 1/a, 1/b, 1/c for the non-strict modes (the strict mode divides like the reference)
 };
 
 struct Obj2 {

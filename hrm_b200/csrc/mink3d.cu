@@ -50,7 +50,9 @@ struct MinkParams {
     int n, M, B, first_obj, n_objs, n_heavy;
     int Lx, Ly, L;
     int lpc, groups;                        // thread mapping
+    int paired;                             // phase A handles rows in adjacent pairs (n even, lpc divides n/2)
     double inv_dx, bias_x, inv_dy, bias_y;  // line-index guess g = x*inv_d + bias
+    double bias_xm, bias_ym;                // bias + 1.5 * 2^32 (fixed-point conversion folded into the FMA)
     double zlow, zup;
 };
 
@@ -92,6 +94,32 @@ __device__ __forceinline__ uint32_t line_code(double x, const double* ts, int Lc
         return line_code_slow(x, ts, Lc, (g > 0.0) ? ((g < 1000.0) ? static_cast<int>(c >> 1) : Lc) : 0);
     }
     return c;
+}
+
+
+// 32-bit shared-window addresses and explicit paired loads/stores: phase A keeps running addresses in registers and
+// bumps them per column instead of letting the compiler re-derive the shared-memory carve-up inside the loop.
+__device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return static_cast<uint32_t>(__cvta_generic_to_shared(ptr)); }
+__device__ __forceinline__ void lds_pair(uint32_t addr, double& a, double& b) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
+}
+__device__ __forceinline__ void lds_pair(uint32_t addr, float& a, float& b) {
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(addr));
+}
+__device__ __forceinline__ void sts_codes(uint32_t addr, uint16_t c0, uint16_t c1) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(static_cast<uint32_t>(c0) | (static_cast<uint32_t>(c1) << 16)) : "memory");
+}
+__device__ __forceinline__ void sts_codes(uint32_t addr, uint32_t c0, uint32_t c1) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(c0), "r"(c1) : "memory");
+}
+// Fixed-point line index of the paired fast path: one FMA with the magic constant folded into the bias (the sum's low
+// word is rint(g * 2^20), its high word is 0x41F80000 exactly while |g| < 2^11), then integer ceil / near-line test.
+__device__ __forceinline__ uint32_t line_code_magic(double x, int Lc, double inv_d, double bias_magic, bool& ok) {
+    const double t = fma(x, inv_d, bias_magic);
+    const int fx = __double2loint(t);
+    const int i = (fx + 0xFFFFF) >> 20;
+    ok = ((static_cast<unsigned>(fx + 8) & 0xFFFF0u) != 0u) && (__double2hiint(t) == 0x41F80000);
+    return static_cast<uint32_t>(__vimin_s32_relu(i, Lc));  // the line index; the code is twice that (eq = 0 off the lines)
 }
 
 template <int MODE>
@@ -181,44 +209,78 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
     int* qcount = reinterpret_cast<int*>(smem_raw + ofs);
 
     // ---- prologue: tables, line coordinates, per-surface matrices -------------------------
-    const double* gtab = p.tab + static_cast<size_t>(obj_id) * 8 * n;
-    for (int i = tid; i < 8 * n; i += kThreads) tab[i] = static_cast<Real>(__ldg(gtab + i));
-    if (SWEEP) {
-        for (int i = tid; i < p.Lx + 2; i += kThreads) txs[i] = __ldg(p.txs + i);
-        for (int i = tid; i < p.Ly + 2; i += kThreads) tys[i] = __ldg(p.tys + i);
-        for (int i = tid; i < p.L; i += kThreads) m0[i] = kNoFace, m1[i] = kNoFace;
-        for (int i = tid; i < static_cast<int>(fbytes >> 2); i += kThreads) reinterpret_cast<uint32_t*>(fbits)[i] = 0u;
-        if (tid == 0) *qcount = 0;
-    }
     const Obj3& ob = p.obj[obj_id];
+    // warp 0 requests the operands of the per-surface matrices first: their (HBM) latency overlaps the table loads below
+    const int me = tid < 9 ? tid : 0;
+    double mi0 = 0, mi1 = 0, mi2 = 0, mj0 = 0, mj1 = 0, mj2 = 0, md0 = 0, md1 = 0, md2 = 0, msign = 0, r1a = 0, r1b = 0, r1c = 0;
+    if (tid < 32) {
+        const int i = me / 3, j = me - 3 * i;
+        const double* r2 = p.R + (static_cast<size_t>(k) * p.B + b) * 9;
+        mi0 = __ldg(r2 + 3 * i), mi1 = __ldg(r2 + 3 * i + 1), mi2 = __ldg(r2 + 3 * i + 2);
+        mj0 = __ldg(r2 + 3 * j), mj1 = __ldg(r2 + 3 * j + 1), mj2 = __ldg(r2 + 3 * j + 2);
+        md0 = __ldg(p.semi + 3 * b), md1 = __ldg(p.semi + 3 * b + 1), md2 = __ldg(p.semi + 3 * b + 2);
+        msign = __ldg(&ob.sign);
+        r1a = __ldg(&ob.R[j]), r1b = __ldg(&ob.R[3 + j]), r1c = __ldg(&ob.R[6 + j]);
+    }
+    const double* gtab = p.tab + static_cast<size_t>(obj_id) * 8 * n;
+    {
+        // All global requests of the prologue are issued back to back (one L2/HBM round trip), the shared-memory
+        // initialisation that needs no data runs while they are in flight, and only then are the values consumed.
+        double v[4], vx = 0.0, vy = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = (tid + j * kThreads < 8 * n) ? __ldg(gtab + tid + j * kThreads) : 0.0;
+        if (SWEEP) {
+            if (tid < p.Lx + 2) vx = __ldg(p.txs + tid);
+            if (tid < p.Ly + 2) vy = __ldg(p.tys + tid);
+            for (int i = tid; i < p.L; i += kThreads) m0[i] = kNoFace, m1[i] = kNoFace;
+            for (int i = tid; i < static_cast<int>(fbytes >> 2); i += kThreads) reinterpret_cast<uint32_t*>(fbits)[i] = 0u;
+            if (tid == 0) *qcount = 0;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (tid + j * kThreads < 8 * n) tab[tid + j * kThreads] = static_cast<Real>(v[j]);
+        for (int i = tid + 4 * kThreads; i < 8 * n; i += kThreads) tab[i] = static_cast<Real>(__ldg(gtab + i));
+        if (SWEEP) {
+            if (tid < p.Lx + 2) txs[tid] = vx;
+            if (tid < p.Ly + 2) tys[tid] = vy;
+            for (int i = tid + kThreads; i < p.Lx + 2; i += kThreads) txs[i] = __ldg(p.txs + i);
+            for (int i = tid + kThreads; i < p.Ly + 2; i += kThreads) tys[i] = __ldg(p.tys + i);
+        }
+    }
     if (tid < 32) {
         // Tinv = (R2 * diag) * R2^T ;  M1 = Tinv * R1 ;  M2 = ((K * Tinv) * Tinv) * R1
         // (SuperQuadrics.cpp:115,137-140), each entry evaluated in the reference's association order by its own
         // lane (9 lanes, three dependent steps through shared memory instead of ~90 serial FP64 operations).
         double* Ts = mats + 18;   // scratch: T[9], KTT[9]
-        const int e = tid < 9 ? tid : 0;
-        const int i = e / 3, j = e - 3 * i;
-        const double* r2 = p.R + (static_cast<size_t>(k) * p.B + b) * 9;
-        const double d0 = __ldg(p.semi + 3 * b), d1 = __ldg(p.semi + 3 * b + 1), d2 = __ldg(p.semi + 3 * b + 2);
-        const double sign = __ldg(&ob.sign);
-        const double t = A::mad(A::mul(__ldg(r2 + 3 * i + 2), d2), __ldg(r2 + 3 * j + 2),
-                                A::mad(A::mul(__ldg(r2 + 3 * i + 1), d1), __ldg(r2 + 3 * j + 1),
-                                       A::mul(A::mul(__ldg(r2 + 3 * i), d0), __ldg(r2 + 3 * j))));
-        if (tid < 9) Ts[e] = t;
+        const double t = A::mad(A::mul(mi2, md2), mj2, A::mad(A::mul(mi1, md1), mj1, A::mul(A::mul(mi0, md0), mj0)));
+        if (tid < 9) Ts[me] = t;
         __syncwarp();
-        const double ktt = A::mad(A::mul(sign, Ts[3 * i + 2]), Ts[6 + j],
-                                  A::mad(A::mul(sign, Ts[3 * i + 1]), Ts[3 + j], A::mul(A::mul(sign, Ts[3 * i]), Ts[j])));
-        if (tid < 9) Ts[9 + e] = ktt;
+        const int i = me / 3, j = me - 3 * i;
+        const double ktt = A::mad(A::mul(msign, Ts[3 * i + 2]), Ts[6 + j],
+                                  A::mad(A::mul(msign, Ts[3 * i + 1]), Ts[3 + j], A::mul(A::mul(msign, Ts[3 * i]), Ts[j])));
+        if (tid < 9) Ts[9 + me] = ktt;
         __syncwarp();
-        const double r1a = __ldg(&ob.R[j]), r1b = __ldg(&ob.R[3 + j]), r1c = __ldg(&ob.R[6 + j]);
         if (tid < 9) {
-            mats[e] = A::mad(Ts[3 * i + 2], r1c, A::mad(Ts[3 * i + 1], r1b, A::mul(Ts[3 * i], r1a)));
-            mats[9 + e] = A::mad(Ts[9 + 3 * i + 2], r1c, A::mad(Ts[9 + 3 * i + 1], r1b, A::mul(Ts[9 + 3 * i], r1a)));
+            mats[me] = A::mad(Ts[3 * i + 2], r1c, A::mad(Ts[3 * i + 1], r1b, A::mul(Ts[3 * i], r1a)));
+            mats[9 + me] = A::mad(Ts[9 + 3 * i + 2], r1c, A::mad(Ts[9 + 3 * i + 1], r1b, A::mul(Ts[9 + 3 * i], r1a)));
         }
     }
     const double offx = __ldg(p.off + (static_cast<size_t>(k) * p.B + b) * 3);
     const double offy = __ldg(p.off + (static_cast<size_t>(k) * p.B + b) * 3 + 1);
     const double offz = __ldg(p.off + (static_cast<size_t>(k) * p.B + b) * 3 + 2);
+
+    // object constants for the column table, requested before the barrier so their latency overlaps the table loads
+    double pre_a = 0, pre_b = 0, pre_c = 0, pre_ia = 0, pre_ib = 0, pre_ic = 0, pre_px = 0, pre_py = 0, pre_pz = 0, pre_R[9] = {};
+    if constexpr (MODE != HRMGPU_F64_STRICT) {
+        if (tid & 1) {
+            pre_a = __ldg(&ob.a), pre_b = __ldg(&ob.b), pre_c = __ldg(&ob.c);
+            pre_px = __ldg(&ob.px), pre_py = __ldg(&ob.py), pre_pz = __ldg(&ob.pz);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) pre_R[i] = __ldg(&ob.R[3 * i]), pre_R[3 + i] = __ldg(&ob.R[3 * i + 1]), pre_R[6 + i] = __ldg(&ob.R[3 * i + 2]);
+        } else {
+            pre_ia = __ldg(&ob.ia), pre_ib = __ldg(&ob.ib), pre_ic = __ldg(&ob.ic);
+        }
+    }
 
     Real* mesh = reinterpret_cast<Real*>(p.mesh) + static_cast<size_t>(slot) * 3 * M;
     Real* mx = mesh;
@@ -226,26 +288,32 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
     Real* mz = mesh + 2 * static_cast<size_t>(M);
     __syncthreads();
     if constexpr (MODE != HRMGPU_F64_STRICT) {
-        // per-column constants: group U = M1 * diag(ga, gb, gc), group W = M2 * diag(..), group P = R1 * diag(A, B, Z) + shift
-        const Real oa = Real(__ldg(&ob.a)), obb = Real(__ldg(&ob.b)), oc = Real(__ldg(&ob.c));
-        const Real ia = Real(1) / oa, ib = Real(1) / obb, ic = Real(1) / oc;
-        const Real tr[3] = {Real(__ldg(&ob.px) - offx), Real(__ldg(&ob.py) - offy), Real(__ldg(&ob.pz) - offz)};
-        for (int c = tid; c < n; c += kThreads) {
+        // per-column constants: group U = M1 * diag(ga, gb, gc), group W = M2 * diag(..), group P = R1 * diag(A, B, Z) + shift.
+        // Two threads per column: the first writes U and W (18 values), the second P (9 values).
+        const int part = tid & 1;
+        for (int c = tid >> 1; c < n; c += kThreads >> 1) {
             const Real ce1 = tab[c], se1 = tab[n + c], ce2 = tab[2 * n + c], se2 = tab[3 * n + c];
-            const Real Ac = oa * ce1, Bc = obb * ce1, Zc = oc * se1;
-            const Real ga = ce2 * ia, gb = ce2 * ib, gc = se2 * ic;
             Real* k = cc + c * kColStride;
+            if (part == 0) {
+                const Real ga = ce2 * Real(pre_ia), gb = ce2 * Real(pre_ib), gc = se2 * Real(pre_ic);
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                k[i] = Real(mats[3 * i]) * ga;
-                k[3 + i] = Real(mats[3 * i + 1]) * gb;
-                k[6 + i] = Real(mats[3 * i + 2]) * gc;
-                k[10 + i] = Real(mats[9 + 3 * i]) * ga;
-                k[13 + i] = Real(mats[9 + 3 * i + 1]) * gb;
-                k[16 + i] = Real(mats[9 + 3 * i + 2]) * gc;
-                k[20 + i] = Real(__ldg(&ob.R[3 * i])) * Ac;
-                k[23 + i] = Real(__ldg(&ob.R[3 * i + 1])) * Bc;
-                k[26 + i] = Real(__ldg(&ob.R[3 * i + 2])) * Zc + tr[i];
+                for (int i = 0; i < 3; ++i) {
+                    k[i] = Real(mats[3 * i]) * ga;
+                    k[3 + i] = Real(mats[3 * i + 1]) * gb;
+                    k[6 + i] = Real(mats[3 * i + 2]) * gc;
+                    k[10 + i] = Real(mats[9 + 3 * i]) * ga;
+                    k[13 + i] = Real(mats[9 + 3 * i + 1]) * gb;
+                    k[16 + i] = Real(mats[9 + 3 * i + 2]) * gc;
+                }
+            } else {
+                const Real Ac = Real(pre_a) * ce1, Bc = Real(pre_b) * ce1, Zc = Real(pre_c) * se1;
+                const Real tr[3] = {Real(pre_px - offx), Real(pre_py - offy), Real(pre_pz - offz)};
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    k[20 + i] = Real(pre_R[i]) * Ac;
+                    k[23 + i] = Real(pre_R[3 + i]) * Bc;
+                    k[26 + i] = Real(pre_R[6 + i]) * Zc + tr[i];
+                }
             }
         }
         __syncthreads();
@@ -309,6 +377,87 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
             using R2 = Real2<Real>;
             constexpr int kRows = 2;
             const int nh = (n + p.lpc - 1) / p.lpc;
+            if (p.paired) {
+                // A thread owns the adjacent rows (r0, r0 + 1): the two points of a column are one 16-byte store per
+                // coordinate plane and one packed store of their line codes; no tail handling (lpc divides n / 2).
+                const int npass = n / (2 * p.lpc);
+                const uint32_t cc_step = static_cast<uint32_t>(p.groups * kColStride * sizeof(Real));
+                const uint32_t v_step = static_cast<uint32_t>(p.groups * n * sizeof(Code));
+                const size_t g_step = static_cast<size_t>(p.groups) * n;
+                for (int h = 0; h < npass; ++h) {
+                    const int r0 = 2 * (ln + h * p.lpc);
+                    Real cw1[2], sw1[2], cw2[2], sw2[2];
+                    lds_pair(smem_u32(tab + 4 * n + r0), cw1[0], cw1[1]);
+                    lds_pair(smem_u32(tab + 5 * n + r0), sw1[0], sw1[1]);
+                    lds_pair(smem_u32(tab + 6 * n + r0), cw2[0], cw2[1]);
+                    lds_pair(smem_u32(tab + 7 * n + r0), sw2[0], sw2[1]);
+                    uint32_t ca = smem_u32(cc) + static_cast<uint32_t>(grp * kColStride * sizeof(Real));
+                    uint32_t va = smem_u32(vcode) + static_cast<uint32_t>((grp * n + r0) * sizeof(Code));
+                    Real* gx = mx + grp * n + r0;
+                    for (int c = grp; c < n; c += p.groups, ca += cc_step, va += v_step, gx += g_step) {
+                        Real o[2][3], inv[2];
+                        {
+                            Real U[10];
+#pragma unroll
+                            for (int i = 0; i < 5; ++i) lds_pair(ca + i * 2 * sizeof(Real), U[2 * i], U[2 * i + 1]);
+#pragma unroll
+                            for (int h2 = 0; h2 < 2; ++h2) {
+                                const Real ux = U[0] * cw2[h2] + (U[3] * sw2[h2] + U[6]);
+                                const Real uy = U[1] * cw2[h2] + (U[4] * sw2[h2] + U[7]);
+                                const Real uz = U[2] * cw2[h2] + (U[5] * sw2[h2] + U[8]);
+                                if constexpr (MODE == HRMGPU_F32)
+                                    inv[h2] = rsqrtf(ux * ux + uy * uy + uz * uz);
+                                else
+                                    inv[h2] = fast_rsqrt(ux * ux + uy * uy + uz * uz);
+                            }
+                        }
+                        {
+                            Real P[10];
+#pragma unroll
+                            for (int i = 0; i < 5; ++i) lds_pair(ca + (20 + 2 * i) * sizeof(Real), P[2 * i], P[2 * i + 1]);
+#pragma unroll
+                            for (int h2 = 0; h2 < 2; ++h2) {
+                                o[h2][0] = P[0] * cw1[h2] + (P[3] * sw1[h2] + P[6]);
+                                o[h2][1] = P[1] * cw1[h2] + (P[4] * sw1[h2] + P[7]);
+                                o[h2][2] = P[2] * cw1[h2] + (P[5] * sw1[h2] + P[8]);
+                            }
+                        }
+                        {
+                            Real W[10];
+#pragma unroll
+                            for (int i = 0; i < 5; ++i) lds_pair(ca + (10 + 2 * i) * sizeof(Real), W[2 * i], W[2 * i + 1]);
+#pragma unroll
+                            for (int h2 = 0; h2 < 2; ++h2) {
+                                o[h2][0] = (W[0] * cw2[h2] + (W[3] * sw2[h2] + W[6])) * inv[h2] + o[h2][0];
+                                o[h2][1] = (W[1] * cw2[h2] + (W[4] * sw2[h2] + W[7])) * inv[h2] + o[h2][1];
+                                o[h2][2] = (W[2] * cw2[h2] + (W[5] * sw2[h2] + W[8])) * inv[h2] + o[h2][2];
+                            }
+                        }
+                        *reinterpret_cast<R2*>(gx) = R2{o[0][0], o[1][0]};
+                        *reinterpret_cast<R2*>(gx + M) = R2{o[0][1], o[1][1]};
+                        *reinterpret_cast<R2*>(gx + 2 * static_cast<size_t>(M)) = R2{o[0][2], o[1][2]};
+                        if (SWEEP) {
+                            bool k0, k1, k2, k3;
+                            const uint32_t ix0 = line_code_magic(static_cast<double>(o[0][0]), p.Lx, p.inv_dx, p.bias_xm, k0);
+                            const uint32_t iy0 = line_code_magic(static_cast<double>(o[0][1]), p.Ly, p.inv_dy, p.bias_ym, k1);
+                            const uint32_t ix1 = line_code_magic(static_cast<double>(o[1][0]), p.Lx, p.inv_dx, p.bias_xm, k2);
+                            const uint32_t iy1 = line_code_magic(static_cast<double>(o[1][1]), p.Ly, p.inv_dy, p.bias_ym, k3);
+                            if (k0 && k1 && k2 && k3) {
+                                if constexpr (CODE8)  // codes = 2 * index, doubled after packing (index <= 127: no carry between fields)
+                                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(va), "r"((ix0 | (iy0 << 8) | (ix1 << 16) | (iy1 << 24)) << 1) : "memory");
+                                else
+                                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(va), "r"((ix0 | (iy0 << 16)) << 1), "r"((ix1 | (iy1 << 16)) << 1) : "memory");
+                            } else {  // rare: a coordinate within rounding distance of a sweep line -> exact search
+                                const uint32_t cx0 = line_code(static_cast<double>(o[0][0]), txs, p.Lx, p.inv_dx, p.bias_x);
+                                const uint32_t cy0 = line_code(static_cast<double>(o[0][1]), tys, p.Ly, p.inv_dy, p.bias_y);
+                                const uint32_t cx1 = line_code(static_cast<double>(o[1][0]), txs, p.Lx, p.inv_dx, p.bias_x);
+                                const uint32_t cy1 = line_code(static_cast<double>(o[1][1]), tys, p.Ly, p.inv_dy, p.bias_y);
+                                sts_codes(va, pack_code(cx0, cy0), pack_code(cx1, cy1));
+                            }
+                        }
+                    }
+                }
+            } else
             for (int h0 = 0; h0 < nh; h0 += kRows) {
                 int rr[kRows];
                 bool rvalid[kRows];
@@ -685,13 +834,13 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
     if (single) atomicAdd(p.counters, static_cast<unsigned long long>(single));
     if (p.dbg && tid == 0) {
         long long* d = p.dbg + static_cast<size_t>(slot) * 8;
+        d[3] = t_drain;              // of which drain + commit
         d[0] = t_pro - t_start;      // prologue
         d[1] = t_a - t_pro;          // phase A
         d[2] = t_scan - t_a;         // scan + drain + commit
-        d[3] = t_drain;              // of which drain + commit
         d[4] = (long long)dbg_max[0];   // max over threads: B1 time in the first round
-        d[5] = rounds;
         d[6] = (long long)dbg_max[1];   // max over threads: B2 time in the first round
+        d[5] = rounds;
         d[7] = clock64() - t_start;
     }
 }
@@ -713,10 +862,22 @@ static size_t smem_bytes(int MODE, bool sweep, bool code8, int n, int Lx, int Ly
 }
 
 // Lanes per column group: maximise n^2 / (threads * ceil(n/lpc) * ceil(n/groups)).
-static void pick_mapping(int n, int& lpc, int& groups) {
+static void pick_mapping(int n, int& lpc, int& groups, int& paired) {
     double best = -1;
     lpc = 32;
     groups = kThreads / 32;
+    paired = 0;
+    if ((n & 1) == 0) {  // paired rows: lanes-per-column must divide n / 2
+        for (int l = 32; l >= 2; --l) {
+            if ((n / 2) % l) continue;
+            const int g = kThreads / l;
+            const double steps = static_cast<double>(n / (2 * l)) * ((n + g - 1) / g);
+            const double eff = static_cast<double>(n) * n / (2.0 * steps * kThreads);
+            if (eff > best * 1.03) best = eff, lpc = l, groups = g, paired = 1;
+        }
+        if (paired) return;
+        best = -1;
+    }
     for (int l = 32; l >= 4; --l) {  // prefer wide groups (longer contiguous stores) unless a narrower one is >3% better
         const int g = kThreads / l;
         const double steps = static_cast<double>((n + l - 1) / l) * ((n + g - 1) / g);
@@ -759,13 +920,15 @@ int launch_minksweep3d(Ctx* c, int K, int B, int n_first_obj, int n_objs, const 
     p.Lx = c->Lx;
     p.Ly = c->Ly;
     p.L = c->Lx * c->Ly;
-    pick_mapping(c->n, p.lpc, p.groups);
+    pick_mapping(c->n, p.lpc, p.groups, p.paired);
     const double dx = (c->lim[1] - c->lim[0]) / static_cast<double>(c->Lx - 1);
     const double dy = (c->lim[3] - c->lim[2]) / static_cast<double>(c->Ly - 1);
     p.inv_dx = 1.0 / dx;
     p.inv_dy = 1.0 / dy;
     p.bias_x = -c->lim[0] * p.inv_dx;
     p.bias_y = -c->lim[2] * p.inv_dy;
+    p.bias_xm = p.bias_x + 6442450944.0;
+    p.bias_ym = p.bias_y + 6442450944.0;
     p.zlow = c->lim[4];
     p.zup = c->lim[5];
     const long long grid = static_cast<long long>(K) * n_objs * B;
