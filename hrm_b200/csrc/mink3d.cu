@@ -629,20 +629,19 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
                     uint32_t bits = 0;
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const bool valid = j0 + e < nc1;
                         const uint32_t c00 = r0[e], c01 = r0[e + 1], c10 = r1[e], c11 = r1[e + 1];
-                        // exact emptiness test of both faces' line sets, branch free.  Per axis with mn = min code,
-                        // mx = max code (code = 2*lo + eq): lines [mn>>1, (mx+1)>>1) is non-empty  <=>  (mx & 1) || (mn|1) < mx.
-                        const uint32_t dmin = __vminu2(c00, c11), dmax = __vmaxu2(c00, c11);
-                        const uint32_t mnA = __vminu2(dmin, c10), mxA = __vmaxu2(dmax, c10);
-                        const uint32_t mnB = __vminu2(dmin, c01), mxB = __vmaxu2(dmax, c01);
-                        // per 16-bit half: bit 15 of ((mx | 0x8000) - (mn | 1) - 1) is set  <=>  (mn | 1) < mx  (codes < 2^15)
-                        const uint32_t dA = (mxA | 0x80008000u) - (mnA | 0x00010001u) - 0x00010001u;
-                        const uint32_t dB = (mxB | 0x80008000u) - (mnB | 0x00010001u) - 0x00010001u;
-                        const uint32_t keepA = (valid && ((((dA >> 15) | mxA) & 0x00010001u) == 0x00010001u)) ? 1u : 0u;
-                        const uint32_t keepB = (valid && ((((dB >> 15) | mxB) & 0x00010001u) == 0x00010001u)) ? 1u : 0u;
-                        bits |= (keepA | (keepB << 1)) << (2 * e);
+                        // exact emptiness test of both faces' line sets, branch free, on (x, y) code pairs in 16-bit halves.
+                        // Per axis with mn = min code, mx = max code (code = 2*lo + eq): the face covers lines
+                        // [mn >> 1, (mx + 1) >> 1), non-empty  <=>  (mn | 1) < mx + (mx & 1)  <=>  no borrow out of bit 14 in
+                        // (mx + (mx & 1)) - (mn | 1) - 1, evaluated as a packed add of the complement (codes < 2^15).
+                        const uint32_t mnA = __vimin3_u16x2(c00, c11, c10), mxA = __vimax3_u16x2(c00, c11, c10);
+                        const uint32_t mnB = __vimin3_u16x2(c00, c11, c01), mxB = __vimax3_u16x2(c00, c11, c01);
+                        const uint32_t dA = __vadd2(__vadd2(mxA, mxA & 0x00010001u), ~(mnA | 0x00010001u));
+                        const uint32_t dB = __vadd2(__vadd2(mxB, mxB & 0x00010001u), ~(mnB | 0x00010001u));
+                        if ((dA & 0x80008000u) == 0u) bits |= 1u << (2 * e);
+                        if ((dB & 0x80008000u) == 0u) bits |= 2u << (2 * e);
                     }
+                    if (j0 + 4 > nc1) bits &= (1u << (2 * (nc1 - j0))) - 1u;  // cells past the end of the mesh row
                     fbits[i * UPR + jq] = static_cast<unsigned char>(bits);
                 }
             }

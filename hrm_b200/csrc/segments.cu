@@ -111,23 +111,32 @@ __global__ void __launch_bounds__(kSegWarps * 32) k_line_segments(const SegParam
     const bool arena_ok = (na > 0) && !(as > ae);
 
     // obstacles: ordered compaction of the non-NaN intervals
+    // (four chunks of 32 surfaces are requested before the first one is consumed: the loads are strided by L doubles,
+    // so the loop is bound by memory latency, not bandwidth)
     int m = 0;
-    for (int base = p.Sa; base < p.S; base += 32) {
-        const int j = base + lane;
-        double a = 0, b = 0;
-        bool ok = false;
-        if (j < p.S) {
-            a = lo[static_cast<size_t>(j) * p.L];
-            b = up[static_cast<size_t>(j) * p.L];
-            ok = !isnan(a) && !isnan(b);
+    constexpr int kUnroll = 4;
+    for (int base = p.Sa; base < p.S; base += 32 * kUnroll) {
+        double a[kUnroll], b[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int j = base + 32 * u + lane;
+            a[u] = b[u] = __longlong_as_double(0x7FF8000000000000LL);
+            if (j < p.S) {
+                a[u] = __ldg(lo + static_cast<size_t>(j) * p.L);
+                b[u] = __ldg(up + static_cast<size_t>(j) * p.L);
+            }
         }
-        const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
-        if (ok) {
-            const int pos = m + __popc(bal & ((1u << lane) - 1u));
-            ks[pos] = a;
-            ke[pos] = b;
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const bool ok = !isnan(a[u]) && !isnan(b[u]);
+            const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
+            if (ok) {
+                const int pos = m + __popc(bal & ((1u << lane) - 1u));
+                ks[pos] = a[u];
+                ke[pos] = b[u];
+            }
+            m += __popc(bal);
         }
-        m += __popc(bal);
     }
     __syncwarp();
 
