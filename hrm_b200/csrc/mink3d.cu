@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
     const int ln = tid - grp * p.lpc;
     const bool worker = grp < p.groups;
 
-    long long t_start = 0, t_pro = 0, t_a = 0, t_scan = 0, t_drain = 0, acc_b1 = 0, acc_b2 = 0;
+    long long t_start = 0, t_pro = 0, t_a = 0, t_scan = 0, t_drain = 0, acc_b2 = 0;
     __shared__ unsigned long long dbg_max[4];
     if (threadIdx.x < 4) dbg_max[threadIdx.x] = 0;
     int rounds = 0;
@@ -197,19 +197,18 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
     auto pack_code = [](uint32_t cx, uint32_t cy) -> Code { return static_cast<Code>(CODE8 ? (cx | (cy << 8)) : (cx | (cy << 16))); };
     // expanded form used by the SIMD min/max tests: x code in bits 0..15, y code in bits 16..31
     auto code_at = [&](int q) -> uint32_t { return CODE8 ? __byte_perm(static_cast<uint32_t>(vcode[q]), 0u, 0x4140) : static_cast<uint32_t>(vcode[q]); };
-    unsigned char* fbits = smem_raw + ofs;                                // [(n-1) * ceil((n-1)/4)] face keep bits, one byte per unit
-    const size_t fbytes = ((static_cast<size_t>(n - 1) * ((n + 2) >> 2) + 3) & ~size_t(3)) + 16;
-    ofs += SWEEP ? ((fbytes + 15) & ~size_t(15)) : 0;
     double* zc0 = reinterpret_cast<double*>(smem_raw + ofs);             // [L] committed z of the two lowest hit faces
     double* zc1 = zc0 + (SWEEP ? p.L : 0);                                // [L]
     ofs += SWEEP ? sizeof(double) * 2 * p.L : 0;
     uint32_t* m0 = reinterpret_cast<uint32_t*>(smem_raw + ofs);          // [L]
     uint32_t* m1 = m0 + (SWEEP ? p.L : 0);                                // [L]
     ofs += SWEEP ? ((sizeof(uint32_t) * 2 * p.L + 15) & ~size_t(15)) : 0;
-    int* qcount = reinterpret_cast<int*>(smem_raw + ofs);
+    int* qcount = reinterpret_cast<int*>(smem_raw + ofs);  // [0] queue fill, [1] next scan batch
+    int* batch_ctr = qcount + 1;
 
     // ---- prologue: tables, line coordinates, per-surface matrices -------------------------
     const Obj3& ob = p.obj[obj_id];
+    const bool sign_neg = __ldg(&ob.sign) < 0.0;  // arena surface (requested here, consumed in phase D)
     // warp 0 requests the operands of the per-surface matrices first: their (HBM) latency overlaps the table loads below
     const int me = tid < 9 ? tid : 0;
     double mi0 = 0, mi1 = 0, mi2 = 0, mj0 = 0, mj1 = 0, mj2 = 0, md0 = 0, md1 = 0, md2 = 0, msign = 0, r1a = 0, r1b = 0, r1c = 0;
@@ -233,8 +232,7 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
             if (tid < p.Lx + 2) vx = __ldg(p.txs + tid);
             if (tid < p.Ly + 2) vy = __ldg(p.tys + tid);
             for (int i = tid; i < p.L; i += kThreads) m0[i] = kNoFace, m1[i] = kNoFace;
-            for (int i = tid; i < static_cast<int>(fbytes >> 2); i += kThreads) reinterpret_cast<uint32_t*>(fbits)[i] = 0u;
-            if (tid == 0) *qcount = 0;
+            if (tid == 0) *qcount = 0, *batch_ctr = 0;
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -558,13 +556,15 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
     __syncthreads();
     if (p.dbg) t_a = clock64();
 
-    // Triangle test of face f against the sweep line (ix, iy).
-    auto test_face = [&](uint32_t f, uint32_t ix, uint32_t iy, double& z) -> bool {
+    // Vertices of face f, and the triangle test of a loaded face against the sweep line (ix, iy).
+    auto load_face = [&](uint32_t f, D3& t0, D3& t1, D3& t2) {
         int v0, v1, v2;
         face_vertices(static_cast<int>(f), n, v0, v1, v2);
-        const D3 t0 = {static_cast<double>(mx[v0]), static_cast<double>(my[v0]), static_cast<double>(mz[v0])};
-        const D3 t1 = {static_cast<double>(mx[v1]), static_cast<double>(my[v1]), static_cast<double>(mz[v1])};
-        const D3 t2 = {static_cast<double>(mx[v2]), static_cast<double>(my[v2]), static_cast<double>(mz[v2])};
+        t0 = {static_cast<double>(mx[v0]), static_cast<double>(my[v0]), static_cast<double>(mz[v0])};
+        t1 = {static_cast<double>(mx[v1]), static_cast<double>(my[v1]), static_cast<double>(mz[v1])};
+        t2 = {static_cast<double>(mx[v2]), static_cast<double>(my[v2]), static_cast<double>(mz[v2])};
+    };
+    auto test_loaded = [&](uint32_t ix, uint32_t iy, const D3& t0, const D3& t1, const D3& t2, double& z) -> bool {
         if constexpr (MODE == HRMGPU_F64_STRICT) {
             const D3 o = {txs[ix + 1], tys[iy + 1], 0.0};
             const D3 d = {0.0, 0.0, 1.0};
@@ -584,77 +584,62 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
     // commits the per-line two lowest hit faces with their z, and resumes scanning.
     const int nc1 = n - 1;
     const int ncell = nc1 * nc1;
-    // B1: every thread owns units of 4 consecutive cells (i, j0..j0+3), i = grp + groups*s, j0 = 4*(ln + lpc*t), and
-    // writes one byte of "line set non-empty" bits per unit (8 faces) into `fbits` (exact integer test on 128/64-bit loads of
-    // the vertex codes).  B2: the warps then walk the bit array 32 words at a time and balance the few set bits over their
-    // lanes (prefix sum of popcounts + rank search), so no lane works through a long private list and every queue
-    // reservation is one shared-memory atomic per warp.
+    // Scan: the cells of the mesh are grouped in units of 4 consecutive cells of a mesh row (8 faces), 4 units per lane,
+    // 128 units per warp batch; warps claim batches from a shared counter.  B1 (per lane): exact, branch-free test of
+    // every face's line set for emptiness on packed (x, y) vertex codes -> one keep bit per face, a 32-bit word per lane.
+    // B2 (per warp): the few set bits of the 32 words are balanced over the lanes (prefix sum of popcounts + rank search),
+    // so no lane works through a long private list, and every queue reservation is one shared-memory atomic per warp.
     const int UPR = (nc1 + 3) >> 2;            // units per mesh row
     const int nunits = nc1 * UPR;
-    const int nwords = (nunits + 3) >> 2;      // 4 unit bytes per 32-bit word
     const uint32_t upr_magic = (UPR > 1) ? 0xFFFFFFFFu / static_cast<uint32_t>(UPR) + 1u : 0u;  // u / UPR == umulhi(u, magic), u < 2^16
     const bool vec_ok = (n & 3) == 0;
-    const int lane = tid & 31, warp = tid >> 5;
+    const int lane = tid & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
-    {
-        long long tb = 0;
-        if (p.dbg) tb = clock64();
-        const int Tn = (UPR + p.lpc - 1) / p.lpc;
-        if (worker) {
-            for (int i = grp; i < nc1; i += p.groups) {
-                for (int t = 0; t < Tn; ++t) {
-                    const int jq = ln + p.lpc * t;
-                    if (jq >= UPR) break;
-                    const int j0 = 4 * jq;
-                    const int q = i * n + j0;
-                    uint32_t r0[5], r1[5];
-                    if (vec_ok && !CODE8) {
-                        const uint4 a = *reinterpret_cast<const uint4*>(vcode + q);
-                        const uint4 b = *reinterpret_cast<const uint4*>(vcode + q + n);
-                        r0[0] = a.x, r0[1] = a.y, r0[2] = a.z, r0[3] = a.w;
-                        r1[0] = b.x, r1[1] = b.y, r1[2] = b.z, r1[3] = b.w;
-                    } else if (vec_ok) {  // four 2x8-bit codes per 64-bit load, expanded to the 2x16-bit SIMD form
-                        const uint2 a = *reinterpret_cast<const uint2*>(vcode + q);
-                        const uint2 b = *reinterpret_cast<const uint2*>(vcode + q + n);
-                        r0[0] = __byte_perm(a.x, 0u, 0x4140), r0[1] = __byte_perm(a.x, 0u, 0x4342);
-                        r0[2] = __byte_perm(a.y, 0u, 0x4140), r0[3] = __byte_perm(a.y, 0u, 0x4342);
-                        r1[0] = __byte_perm(b.x, 0u, 0x4140), r1[1] = __byte_perm(b.x, 0u, 0x4342);
-                        r1[2] = __byte_perm(b.y, 0u, 0x4140), r1[3] = __byte_perm(b.y, 0u, 0x4342);
-                    } else {
+    // keep bits of the 8 faces of unit u
+    auto unit_bits = [&](int unit) -> uint32_t {
+        const int i = (UPR > 1) ? static_cast<int>(__umulhi(static_cast<uint32_t>(unit), upr_magic)) : unit;
+        const int j0 = 4 * (unit - i * UPR);
+        const int q = i * n + j0;
+        uint32_t r0[5], r1[5];
+        if (vec_ok && !CODE8) {
+            const uint4 a = *reinterpret_cast<const uint4*>(vcode + q);
+            const uint4 b = *reinterpret_cast<const uint4*>(vcode + q + n);
+            r0[0] = a.x, r0[1] = a.y, r0[2] = a.z, r0[3] = a.w;
+            r1[0] = b.x, r1[1] = b.y, r1[2] = b.z, r1[3] = b.w;
+        } else if (vec_ok) {  // four 2x8-bit codes per 64-bit load, expanded to the 2x16-bit SIMD form
+            const uint2 a = *reinterpret_cast<const uint2*>(vcode + q);
+            const uint2 b = *reinterpret_cast<const uint2*>(vcode + q + n);
+            r0[0] = __byte_perm(a.x, 0u, 0x4140), r0[1] = __byte_perm(a.x, 0u, 0x4342);
+            r0[2] = __byte_perm(a.y, 0u, 0x4140), r0[3] = __byte_perm(a.y, 0u, 0x4342);
+            r1[0] = __byte_perm(b.x, 0u, 0x4140), r1[1] = __byte_perm(b.x, 0u, 0x4342);
+            r1[2] = __byte_perm(b.y, 0u, 0x4140), r1[3] = __byte_perm(b.y, 0u, 0x4342);
+        } else {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) r0[e] = code_at(q + e), r1[e] = code_at(q + n + e);
-                    }
-                    r0[4] = code_at(q + 4);
-                    r1[4] = code_at(q + n + 4);
-                    uint32_t bits = 0;
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const uint32_t c00 = r0[e], c01 = r0[e + 1], c10 = r1[e], c11 = r1[e + 1];
-                        // exact emptiness test of both faces' line sets, branch free, on (x, y) code pairs in 16-bit halves.
-                        // Per axis with mn = min code, mx = max code (code = 2*lo + eq): the face covers lines
-                        // [mn >> 1, (mx + 1) >> 1), non-empty  <=>  (mn | 1) < mx + (mx & 1)  <=>  no borrow out of bit 14 in
-                        // (mx + (mx & 1)) - (mn | 1) - 1, evaluated as a packed add of the complement (codes < 2^15).
-                        const uint32_t mnA = __vimin3_u16x2(c00, c11, c10), mxA = __vimax3_u16x2(c00, c11, c10);
-                        const uint32_t mnB = __vimin3_u16x2(c00, c11, c01), mxB = __vimax3_u16x2(c00, c11, c01);
-                        const uint32_t dA = __vadd2(__vadd2(mxA, mxA & 0x00010001u), ~(mnA | 0x00010001u));
-                        const uint32_t dB = __vadd2(__vadd2(mxB, mxB & 0x00010001u), ~(mnB | 0x00010001u));
-                        if ((dA & 0x80008000u) == 0u) bits |= 1u << (2 * e);
-                        if ((dB & 0x80008000u) == 0u) bits |= 2u << (2 * e);
-                    }
-                    if (j0 + 4 > nc1) bits &= (1u << (2 * (nc1 - j0))) - 1u;  // cells past the end of the mesh row
-                    fbits[i * UPR + jq] = static_cast<unsigned char>(bits);
-                }
-            }
+            for (int e = 0; e < 4; ++e) r0[e] = code_at(q + e), r1[e] = code_at(q + n + e);
         }
-        if (p.dbg) acc_b1 += clock64() - tb;
-    }
-    __syncwarp();
-    __syncthreads();
+        r0[4] = code_at(q + 4);
+        r1[4] = code_at(q + n + 4);
+        uint32_t bits = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const uint32_t c00 = r0[e], c01 = r0[e + 1], c10 = r1[e], c11 = r1[e + 1];
+            // Per axis with mn = min code, mx = max code (code = 2*lo + eq): the face covers lines [mn >> 1, (mx + 1) >> 1),
+            // non-empty  <=>  (mn | 1) < mx + (mx & 1)  <=>  no borrow out of bit 14 in (mx + (mx & 1)) - (mn | 1) - 1,
+            // evaluated as a packed add of the complement (codes < 2^15).
+            const uint32_t mnA = __vimin3_u16x2(c00, c11, c10), mxA = __vimax3_u16x2(c00, c11, c10);
+            const uint32_t mnB = __vimin3_u16x2(c00, c11, c01), mxB = __vimax3_u16x2(c00, c11, c01);
+            const uint32_t dA = __vadd2(__vadd2(mxA, mxA & 0x00010001u), ~(mnA | 0x00010001u));
+            const uint32_t dB = __vadd2(__vadd2(mxB, mxB & 0x00010001u), ~(mnB | 0x00010001u));
+            if ((dA & 0x80008000u) == 0u) bits |= 1u << (2 * e);
+            if ((dB & 0x80008000u) == 0u) bits |= 2u << (2 * e);
+        }
+        if (j0 + 4 > nc1) bits &= (1u << (2 * (nc1 - j0))) - 1u;  // cells past the end of the mesh row
+        return bits;
+    };
 
     // B2 state of a warp: batch of 32 words [bw*32, bw*32+32), its words / popcount prefix, the rank chunk r0, and per lane
     // the open face with the next line to push.
-    const uint32_t* fwords = reinterpret_cast<const uint32_t*>(fbits);
-    int bw = warp;                 // current batch (warp-uniform)
+    int bw = 0;                    // current batch (warp-uniform)
     bool batch_loaded = false;
     uint32_t w_bits = 0, w_cnt = 0, w_incl = 0, w_total = 0;
     uint32_t r0c = 0;              // first rank of the current chunk of 32 set bits
@@ -667,12 +652,18 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
         if (p.dbg) tb2 = clock64();
         while (scanning) {
             if (!batch_loaded) {
-                if (bw * 32 >= nwords) {
+                if (lane == 0) bw = atomicAdd(batch_ctr, 1);
+                bw = __shfl_sync(0xFFFFFFFFu, bw, 0);
+                if (bw * 128 >= nunits) {
                     scanning = false;
                     break;
                 }
-                const int widx = bw * 32 + lane;
-                w_bits = (widx < nwords) ? fwords[widx] : 0u;
+                w_bits = 0u;
+#pragma unroll
+                for (int uu = 0; uu < 4; ++uu) {
+                    const int unit = (bw * 32 + lane) * 4 + uu;
+                    if (unit < nunits) w_bits |= unit_bits(unit) << (8 * uu);
+                }
                 w_cnt = __popc(w_bits);
                 w_incl = w_cnt;
 #pragma unroll
@@ -687,7 +678,6 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
                 face_open = false;
                 if (w_total == 0u) {  // nothing in these 32 words
                     batch_loaded = false;
-                    bw += kThreads / 32;
                     continue;
                 }
             }
@@ -757,16 +747,14 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
             }
             if (parked) break;
             batch_loaded = false;
-            bw += kThreads / 32;
         }
         if (p.dbg) acc_b2 += clock64() - tb2;
         if (p.dbg && rounds == 0) {
-            atomicMax(&dbg_max[0], (unsigned long long)acc_b1);
             atomicMax(&dbg_max[1], (unsigned long long)acc_b2);
             atomicMax(&dbg_max[2], (unsigned long long)(clock64() - t_a));
         }
         __syncwarp();  // the scan loop exits lane by lane: the drain below must run with full warps
-        __syncthreads();
+        const int more = __syncthreads_or(scanning ? 1 : 0);  // no warp has cells left: this drain is the last one
         long long tq0 = 0;
         if (p.dbg) tq0 = clock64();
         // drain
@@ -774,8 +762,10 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
         for (int i = tid; i < nq; i += kThreads) {
             const uint2 e = queue[i];
             const uint32_t ix = e.y & 0xFFFFu, iy = e.y >> 16;
+            D3 t0, t1, t2;
+            load_face(e.x, t0, t1, t2);
             double z;
-            if (test_face(e.x, ix, iy, z)) {
+            if (test_loaded(ix, iy, t0, t1, t2, z)) {
                 zq[i] = z;
                 const uint32_t l = ix * p.Ly + iy;
                 insert_two_smallest(&m0[l], &m1[l], (e.x << kPosBits) | static_cast<uint32_t>(i));
@@ -783,6 +773,10 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
         }
         __syncwarp();
         __syncthreads();
+        if (!more) {  // last round: phase D resolves the z of the fresh entries from the queue itself
+            if (p.dbg) t_drain += clock64() - tq0;
+            break;
+        }
         // commit: bind z to the surviving entries of every line (entries from earlier rounds carry the
         // marker kPosMask and already own zc0/zc1; an older entry can only have moved from slot 0 to slot 1)
         for (int l = tid; l < p.L; l += kThreads) {
@@ -804,14 +798,13 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
         }
         if (tid == 0) *qcount = 0;
         ++rounds;
-        const int more = __syncthreads_or(scanning ? 1 : 0);
+        __syncthreads();
         if (p.dbg) t_drain += clock64() - tq0;
-        if (!more) break;
     }
 
     if (p.dbg) t_scan = clock64();
     // ---- phase D: intervals ----------------------------------------------------------------
-    const bool is_arena = __ldg(&ob.sign) < 0.0;
+    const bool is_arena = sign_neg;
     double* lo = p.lo + static_cast<size_t>(slot) * p.L;
     double* up = p.up + static_cast<size_t>(slot) * p.L;
     unsigned single = 0;
@@ -820,7 +813,10 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
         double a = is_arena ? p.zlow : __longlong_as_double(0x7FF8000000000000LL);
         double bb = is_arena ? p.zup : __longlong_as_double(0x7FF8000000000000LL);
         if (e1 != kNoFace) {
-            const double z0 = zc0[l], z1 = zc1[l];
+            // same resolution as the commit step: fresh entries (slot != kPosMask) take their z from the queue
+            const bool fresh0 = (e0 & kPosMask) != kPosMask, fresh1 = (e1 & kPosMask) != kPosMask;
+            const double z0 = fresh0 ? zq[e0 & kPosMask] : zc0[l];
+            const double z1 = fresh1 ? zq[e1 & kPosMask] : (fresh0 ? zc0[l] : zc1[l]);
             const double zl = fmin(z0, z1), zu = fmax(z0, z1);
             a = is_arena ? fmin(p.zlow, zl) : zl;  // FreeSpace3D.cpp:44-49 / 61-64
             bb = is_arena ? fmax(p.zup, zu) : zu;
@@ -853,7 +849,6 @@ static size_t smem_bytes(int MODE, bool sweep, bool code8, int n, int Lx, int Ly
         b += (sizeof(double) * (Lx + Ly + 4) + 15) & ~size_t(15);
         b += sizeof(double) * kQueueCap + sizeof(uint2) * kQueueCap;
         b += ((code8 ? 2 : 4) * (static_cast<size_t>(n) * n + 8) + 15) & ~size_t(15);
-        b += ((((static_cast<size_t>(n - 1) * ((n + 2) >> 2) + 3) & ~size_t(3)) + 16) + 15) & ~size_t(15);
         b += sizeof(double) * 2 * static_cast<size_t>(Lx) * Ly;
         b += (sizeof(uint32_t) * 2 * static_cast<size_t>(Lx) * Ly + 15) & ~size_t(15);
     }
