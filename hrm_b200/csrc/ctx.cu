@@ -4,6 +4,7 @@
 #include "internal.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <new>
@@ -101,6 +102,9 @@ int hrmgpu_create(hrmgpu_ctx** out, int device, unsigned flags) {
         return HRMGPU_E_CUDA;
     }
     c->stream = c->own_stream;
+    // test hooks of the segment pass (tests/test_gpu_layers3d.py): list capacity of the 4-line kernel / one-line kernel only
+    if (const char* e = std::getenv("HRMGPU_SEG_FAST_CAP")) c->seg_fast_cap = std::atoi(e);
+    if (const char* e = std::getenv("HRMGPU_SEG_ONE_LINE")) c->force_seg_fallback = std::atoi(e) != 0;
     if (ensure(c, c->counters, 4) != HRMGPU_OK) {
         delete c;
         return HRMGPU_E_NOMEM;

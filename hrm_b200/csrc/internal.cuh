@@ -71,6 +71,8 @@ struct Ctx {
     DevBuf<unsigned int> q_flag;                 // per-query blocked flags
     DevBuf<char> mesh;                           // [K][S][dim][M] planar, double (or float in F32 mode)
     DevBuf<double> ivl_lo, ivl_up;               // [K][S][L]
+    int seg_fast_cap = 0;                        // test hook: list capacity of the 4-line segment pass (0 = default 256)
+    bool force_seg_fallback = false;             // test hook: always use the one-line-per-warp pass
     DevBuf<double> orig;                         // [K][L][So+1][2] original (pre-enhancement) segments
     DevBuf<int> orig_cnt;                        // [K][L]
     DevBuf<int> seg_cnt;                         // [K][L]

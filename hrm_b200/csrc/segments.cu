@@ -15,11 +15,13 @@
 // but the last one of a plane independently, exactly like the reference.
 #include "internal.cuh"
 
+#include <algorithm>
 #include <cfloat>
 
 namespace hrmgpu {
 
 constexpr int kSegWarps = 8;
+constexpr int kSeg4Warps = 7;  // 4-line pass: 7 warps x 16 KB of lists = 112 KB per CTA, two CTAs per SM
 
 struct SegParams {
     const double* lo;   // [K][S][L]
@@ -34,6 +36,7 @@ struct SegParams {
     int K, S, Sa, L, Lx, Ly, cap;  // cap = So + 1 original segments per line at most
     int warps;                     // warps per CTA in pass 1
     int sort_cap;                  // intervals per warp in shared memory
+    int only_flagged;              // pass 1 fallback: process only the lines k_line_segments4 marked with orig_cnt = -1
 };
 
 // Ascending sort of n keys (with optional payload) by a warp; works for any n (virtual +inf padding).
@@ -77,69 +80,10 @@ __device__ __forceinline__ void warp_bitonic(double* key, double* val, int n, in
     }
 }
 
-// Pass 1: original free segments of every line.  grid = ceil(K*L / warps) CTAs of `warps` warps.
-__global__ void __launch_bounds__(kSegWarps * 32) k_line_segments(const SegParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long gl = static_cast<long long>(blockIdx.x) * p.warps + warp;  // global line id = k*L + l
-    if (warp >= p.warps || gl >= static_cast<long long>(p.K) * p.L) return;
-    const int k = static_cast<int>(gl / p.L);
-    const int l = static_cast<int>(gl - static_cast<long long>(k) * p.L);
-    double* ks = reinterpret_cast<double*>(smem_raw) + static_cast<size_t>(warp) * 2 * p.sort_cap;  // starts
-    double* ke = ks + p.sort_cap;                                                                      // ends
-
-    const double* lo = p.lo + static_cast<size_t>(k) * p.S * p.L + l;
-    const double* up = p.up + static_cast<size_t>(k) * p.S * p.L + l;
-
-    // arena: A = [max lo, min up] over non-NaN arena entries (Interval::intersects)
-    double as = -DBL_MAX, ae = DBL_MAX;
-    int na = 0;
-    for (int j = lane; j < p.Sa; j += 32) {
-        const double a = lo[static_cast<size_t>(j) * p.L], b = up[static_cast<size_t>(j) * p.L];
-        if (!isnan(a) && !isnan(b)) {
-            as = fmax(as, a);
-            ae = fmin(ae, b);
-            ++na;
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        as = fmax(as, __shfl_xor_sync(0xFFFFFFFFu, as, o));
-        ae = fmin(ae, __shfl_xor_sync(0xFFFFFFFFu, ae, o));
-        na += __shfl_xor_sync(0xFFFFFFFFu, na, o);
-    }
-    const bool arena_ok = (na > 0) && !(as > ae);
-
-    // obstacles: ordered compaction of the non-NaN intervals
-    // (four chunks of 32 surfaces are requested before the first one is consumed: the loads are strided by L doubles,
-    // so the loop is bound by memory latency, not bandwidth)
-    int m = 0;
-    constexpr int kUnroll = 4;
-    for (int base = p.Sa; base < p.S; base += 32 * kUnroll) {
-        double a[kUnroll], b[kUnroll];
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-            const int j = base + 32 * u + lane;
-            a[u] = b[u] = __longlong_as_double(0x7FF8000000000000LL);
-            if (j < p.S) {
-                a[u] = __ldg(lo + static_cast<size_t>(j) * p.L);
-                b[u] = __ldg(up + static_cast<size_t>(j) * p.L);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-            const bool ok = !isnan(a[u]) && !isnan(b[u]);
-            const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
-            if (ok) {
-                const int pos = m + __popc(bal & ((1u << lane) - 1u));
-                ks[pos] = a[u];
-                ke[pos] = b[u];
-            }
-            m += __popc(bal);
-        }
-    }
-    __syncwarp();
-
+// Original free segments of one line from its m compacted C-obstacle intervals (ks = starts, ke = ends, in shared
+// memory) and its arena interval [as, ae]: sort by start, gaps of the union clipped to the arena, count to orig_cnt.
+__device__ __forceinline__ void emit_line(const SegParams& p, long long gl, double* ks, double* ke, int m, double as, double ae,
+                                          bool arena_ok, int lane) {
     double* out = p.orig + (static_cast<size_t>(gl) * p.cap) * 2;
     int cnt = 0;
     if (!arena_ok) {
@@ -185,6 +129,161 @@ __global__ void __launch_bounds__(kSegWarps * 32) k_line_segments(const SegParam
         }
     }
     if (lane == 0) p.orig_cnt[gl] = cnt;
+}
+
+// Pass 1: original free segments of every line.  grid = ceil(K*L / warps) CTAs of `warps` warps.
+__global__ void __launch_bounds__(kSegWarps * 32) k_line_segments(const SegParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp >= p.warps) return;
+    const long long nl = static_cast<long long>(p.K) * p.L;
+    // p.only_flagged: fallback pass behind k_line_segments4, a small grid walks all lines and redoes the overflowed ones
+    for (long long gl = static_cast<long long>(blockIdx.x) * p.warps + warp; gl < nl; gl += static_cast<long long>(gridDim.x) * p.warps) {
+        if (p.only_flagged && p.orig_cnt[gl] != -1) continue;
+        const int k = static_cast<int>(gl / p.L);
+        const int l = static_cast<int>(gl - static_cast<long long>(k) * p.L);
+        double* ks = reinterpret_cast<double*>(smem_raw) + static_cast<size_t>(warp) * 2 * p.sort_cap;  // starts
+        double* ke = ks + p.sort_cap;                                                                      // ends
+
+        const double* lo = p.lo + static_cast<size_t>(k) * p.S * p.L + l;
+        const double* up = p.up + static_cast<size_t>(k) * p.S * p.L + l;
+
+        // arena: A = [max lo, min up] over non-NaN arena entries (Interval::intersects)
+        double as = -DBL_MAX, ae = DBL_MAX;
+        int na = 0;
+        for (int j = lane; j < p.Sa; j += 32) {
+            const double a = lo[static_cast<size_t>(j) * p.L], b = up[static_cast<size_t>(j) * p.L];
+            if (!isnan(a) && !isnan(b)) {
+                as = fmax(as, a);
+                ae = fmin(ae, b);
+                ++na;
+            }
+        }
+    #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            as = fmax(as, __shfl_xor_sync(0xFFFFFFFFu, as, o));
+            ae = fmin(ae, __shfl_xor_sync(0xFFFFFFFFu, ae, o));
+            na += __shfl_xor_sync(0xFFFFFFFFu, na, o);
+        }
+        const bool arena_ok = (na > 0) && !(as > ae);
+
+        // obstacles: ordered compaction of the non-NaN intervals
+        // (eight chunks of 32 surfaces are requested before the first one is consumed: the loads are strided by L doubles,
+        // so the loop is bound by memory latency, not bandwidth)
+        int m = 0;
+        constexpr int kUnroll = 8;
+        for (int base = p.Sa; base < p.S; base += 32 * kUnroll) {
+            double a[kUnroll], b[kUnroll];
+    #pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const int j = base + 32 * u + lane;
+                a[u] = b[u] = __longlong_as_double(0x7FF8000000000000LL);
+                if (j < p.S) {
+                    a[u] = __ldg(lo + static_cast<size_t>(j) * p.L);
+                    b[u] = __ldg(up + static_cast<size_t>(j) * p.L);
+                }
+            }
+    #pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const bool ok = !isnan(a[u]) && !isnan(b[u]);
+                const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
+                if (ok) {
+                    const int pos = m + __popc(bal & ((1u << lane) - 1u));
+                    ks[pos] = a[u];
+                    ke[pos] = b[u];
+                }
+                m += __popc(bal);
+            }
+        }
+        __syncwarp();
+
+        emit_line(p, gl, ks, ke, m, as, ae, arena_ok, lane);
+        __syncwarp();
+    }
+}
+
+// Pass 1, fast path (L % 4 == 0): one warp per group of 4 consecutive lines.  A lane reads the 32-byte sector that holds
+// the four lines' entries of one surface (the tables are surface-major, so one line alone would use 8 of every 32 bytes
+// fetched), and the warp compacts four interval lists at once, `cap4` entries each.  A line with more intervals than
+// that is flagged (orig_cnt = -1) and redone by k_line_segments with full-size lists.
+__global__ void __launch_bounds__(kSeg4Warps * 32, 2) k_line_segments4(const SegParams p, int cap4) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long grp = static_cast<long long>(blockIdx.x) * kSeg4Warps + warp;
+    const long long gl0 = grp * 4;  // first global line id (k*L + l) of the group; L % 4 == 0 keeps a group inside one layer
+    if (gl0 >= static_cast<long long>(p.K) * p.L) return;
+    const int k = static_cast<int>(gl0 / p.L);
+    const int l = static_cast<int>(gl0 - static_cast<long long>(k) * p.L);
+    double* base_s = reinterpret_cast<double*>(smem_raw) + static_cast<size_t>(warp) * 8 * cap4;  // [4][2][cap4]
+    const double* lo = p.lo + static_cast<size_t>(k) * p.S * p.L + l;
+    const double* up = p.up + static_cast<size_t>(k) * p.S * p.L + l;
+    const unsigned lt = (1u << lane) - 1u;
+
+    double as[4], ae[4];
+    int na[4], m[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) as[t] = -DBL_MAX, ae[t] = DBL_MAX, na[t] = 0, m[t] = 0;
+    for (int j = lane; j < p.Sa; j += 32) {
+        const double2 a01 = __ldg(reinterpret_cast<const double2*>(lo + static_cast<size_t>(j) * p.L));
+        const double2 a23 = __ldg(reinterpret_cast<const double2*>(lo + static_cast<size_t>(j) * p.L) + 1);
+        const double2 b01 = __ldg(reinterpret_cast<const double2*>(up + static_cast<size_t>(j) * p.L));
+        const double2 b23 = __ldg(reinterpret_cast<const double2*>(up + static_cast<size_t>(j) * p.L) + 1);
+        const double a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            if (!isnan(a[t]) && !isnan(b[t])) as[t] = fmax(as[t], a[t]), ae[t] = fmin(ae[t], b[t]), ++na[t];
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            as[t] = fmax(as[t], __shfl_xor_sync(0xFFFFFFFFu, as[t], o));
+            ae[t] = fmin(ae[t], __shfl_xor_sync(0xFFFFFFFFu, ae[t], o));
+            na[t] += __shfl_xor_sync(0xFFFFFFFFu, na[t], o);
+        }
+
+    constexpr int kUnroll = 4;  // 16 sector loads in flight per lane
+    const double qnan = __longlong_as_double(0x7FF8000000000000LL);
+    for (int base = p.Sa; base < p.S; base += 32 * kUnroll) {
+        double2 a01[kUnroll], a23[kUnroll], b01[kUnroll], b23[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int j = base + 32 * u + lane;
+            a01[u] = a23[u] = b01[u] = b23[u] = make_double2(qnan, qnan);
+            if (j < p.S) {
+                const double2* pa = reinterpret_cast<const double2*>(lo + static_cast<size_t>(j) * p.L);
+                const double2* pb = reinterpret_cast<const double2*>(up + static_cast<size_t>(j) * p.L);
+                a01[u] = __ldg(pa), a23[u] = __ldg(pa + 1), b01[u] = __ldg(pb), b23[u] = __ldg(pb + 1);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const double a[4] = {a01[u].x, a01[u].y, a23[u].x, a23[u].y}, b[4] = {b01[u].x, b01[u].y, b23[u].x, b23[u].y};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const bool ok = !isnan(a[t]) && !isnan(b[t]);
+                const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
+                if (ok) {
+                    const int pos = m[t] + __popc(bal & lt);
+                    if (pos < cap4) {
+                        base_s[(2 * t) * cap4 + pos] = a[t];
+                        base_s[(2 * t + 1) * cap4 + pos] = b[t];
+                    }
+                }
+                m[t] += __popc(bal);
+            }
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        if (m[t] > cap4) {
+            if (lane == 0) p.orig_cnt[gl0 + t] = -1;  // overflow: redone by the fallback pass
+            continue;
+        }
+        emit_line(p, gl0 + t, base_s + (2 * t) * cap4, base_s + (2 * t + 1) * cap4, m[t], as[t], ae[t], (na[t] > 0) && !(as[t] > ae[t]), lane);
+        __syncwarp();
+    }
 }
 
 // The four append rules of enhanceFreeSegment for the ordered pair (line i, line i+1), segment j1 of
@@ -376,8 +475,27 @@ int launch_segments(Ctx* c) {
     const size_t smem = per_warp * warps;
     HRMGPU_CUDA(c, cudaFuncSetAttribute(k_line_segments, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     const long long g1 = (nl + warps - 1) / warps;
-    k_line_segments<<<static_cast<unsigned>(g1), warps * 32, smem, c->stream>>>(p);
-    HRMGPU_CUDA(c, cudaGetLastError());
+    p.only_flagged = 0;
+    if (c->L % 4 == 0 && !c->force_seg_fallback) {
+        // fast path: a warp per 4 lines with short lists, then the full-size kernel on a small grid for flagged lines
+        const int cap4 = std::min(p.sort_cap, c->seg_fast_cap > 0 ? c->seg_fast_cap : 256);
+        const size_t smem4 = static_cast<size_t>(kSeg4Warps) * 8 * cap4 * sizeof(double);
+        HRMGPU_CUDA(c, cudaFuncSetAttribute(k_line_segments4, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem4)));
+        const long long groups = nl / 4;
+        k_line_segments4<<<static_cast<unsigned>((groups + kSeg4Warps - 1) / kSeg4Warps), kSeg4Warps * 32, smem4, c->stream>>>(p, cap4);
+        HRMGPU_CUDA(c, cudaGetLastError());
+        c->launches += 1;
+        if (cap4 < p.sort_cap) {
+            p.only_flagged = 1;
+            k_line_segments<<<static_cast<unsigned>(std::min<long long>(g1, 148)), warps * 32, smem, c->stream>>>(p);
+            HRMGPU_CUDA(c, cudaGetLastError());
+            c->launches += 1;
+        }
+        c->launches -= 1;  // (the common tail below counts one pass-1 launch)
+    } else {
+        k_line_segments<<<static_cast<unsigned>(g1), warps * 32, smem, c->stream>>>(p);
+        HRMGPU_CUDA(c, cudaGetLastError());
+    }
     const long long g2 = (nl + kSegWarps - 1) / kSegWarps;
     k_enhance<false><<<static_cast<unsigned>(g2), kSegWarps * 32, 0, c->stream>>>(p);
     HRMGPU_CUDA(c, cudaGetLastError());

@@ -139,3 +139,20 @@ def test_roundtrip_properties_full_size(gpu_ctx):
                 assert not inside.any()
         b = gpu_ctx.boundary(k, 5)
         assert b.shape == (3, 10000) and np.isfinite(b).all()
+
+
+@pytest.mark.parametrize("env", [{"HRMGPU_SEG_FAST_CAP": "2"}, {"HRMGPU_SEG_ONE_LINE": "1"}])
+def test_segment_pass_variants_bit_exact(oracle, env, monkeypatch):
+    """K3 pass 1 has a 4-lines-per-warp fast path with short interval lists and a one-line-per-warp pass with full-size
+    lists for lines that overflow them.  A list capacity of 2 sends every busy line through the fallback; the second
+    variant disables the fast path.  Both must still match the oracle bit for bit (L = 8 x 12 is divisible by 4)."""
+    for k_, v in env.items():
+        monkeypatch.setenv(k_, v)
+    ctx = capi.Context(0)  # the hooks are read when the context is created
+    sc = util.scenes()["3D_superquadrics_cluttered_rabbit"]
+    rows = sc["arena"] + sc["obstacle"]
+    semi, R, off, quat = util.body_poses3d(sc["robot"], sc["quats"][:3])
+    res = run_both(oracle, ctx, rows, 1, 10, semi, R, off, quat, sc["lim"], 8, 12, capi.F64_STRICT)
+    assert any((np.diff(ref["off"]) > 2).any() for ref, _ in res)
+    for ref, got in res:
+        assert_bit_exact(ref, got)
