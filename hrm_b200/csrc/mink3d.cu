@@ -52,7 +52,7 @@ struct MinkParams {
     int lpc, groups;                        // thread mapping
     int paired;                             // phase A handles rows in adjacent pairs (n even, lpc divides n/2)
     double inv_dx, bias_x, inv_dy, bias_y;  // line-index guess g = x*inv_d + bias
-    double bias_xm, bias_ym;                // bias + 1.5 * 2^32 (fixed-point conversion folded into the FMA)
+    double bias_xq, bias_yq;                // bias + 1.5 * 2^36 + (1 - 2^-16): Q15.16 conversion and ceil folded into the FMA
     double zlow, zup;
 };
 
@@ -112,14 +112,15 @@ __device__ __forceinline__ void sts_codes(uint32_t addr, uint16_t c0, uint16_t c
 __device__ __forceinline__ void sts_codes(uint32_t addr, uint32_t c0, uint32_t c1) {
     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(c0), "r"(c1) : "memory");
 }
-// Fixed-point line index of the paired fast path: one FMA with the magic constant folded into the bias (the sum's low
-// word is rint(g * 2^20), its high word is 0x41F80000 exactly while |g| < 2^11), then integer ceil / near-line test.
-__device__ __forceinline__ uint32_t line_code_magic(double x, int Lc, double inv_d, double bias_magic, bool& ok) {
-    const double t = fma(x, inv_d, bias_magic);
-    const int fx = __double2loint(t);
-    const int i = (fx + 0xFFFFF) >> 20;
-    ok = ((static_cast<unsigned>(fx + 8) & 0xFFFF0u) != 0u) && (__double2hiint(t) == 0x41F80000);
-    return static_cast<uint32_t>(__vimin_s32_relu(i, Lc));  // the line index; the code is twice that (eq = 0 off the lines)
+// Fixed-point line index of the paired fast path.  t = fma(x, inv_d, bias_q) with bias_q = bias + 1.5 * 2^36 + (1 - 2^-16):
+// the low word of t is w = rint(g * 2^16) + 0xFFFF (two's complement, g in line units), so its upper half is ceil(g);
+// that holds while the high word of t is 0x42380000 (g >= 0) or 0x4237FFFF (g < 0), i.e. |g| < 2^15.  ok = false when g
+// is within 4 * 2^-16 of a grid line (the computed w is off by at most one unit) or out of range: exact search instead.
+__device__ __forceinline__ uint32_t line_q(double x, double inv_d, double bias_q, bool& ok) {
+    const double t = fma(x, inv_d, bias_q);
+    const uint32_t w = static_cast<uint32_t>(__double2loint(t));
+    ok = (((w + 5u) & 0xFFF8u) != 0u) && (static_cast<uint32_t>(__double2hiint(t)) - 0x4237FFFFu < 2u);
+    return w;
 }
 
 template <int MODE>
@@ -382,6 +383,7 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
                 const uint32_t cc_step = static_cast<uint32_t>(p.groups * kColStride * sizeof(Real));
                 const uint32_t v_step = static_cast<uint32_t>(p.groups * n * sizeof(Code));
                 const size_t g_step = static_cast<size_t>(p.groups) * n;
+                const uint32_t lx2 = static_cast<uint32_t>(p.Lx) * 0x00010001u, ly2 = static_cast<uint32_t>(p.Ly) * 0x00010001u;
                 for (int h = 0; h < npass; ++h) {
                     const int r0 = 2 * (ln + h * p.lpc);
                     Real cw1[2], sw1[2], cw2[2], sw2[2];
@@ -436,15 +438,20 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
                         *reinterpret_cast<R2*>(gx + 2 * static_cast<size_t>(M)) = R2{o[0][2], o[1][2]};
                         if (SWEEP) {
                             bool k0, k1, k2, k3;
-                            const uint32_t ix0 = line_code_magic(static_cast<double>(o[0][0]), p.Lx, p.inv_dx, p.bias_xm, k0);
-                            const uint32_t iy0 = line_code_magic(static_cast<double>(o[0][1]), p.Ly, p.inv_dy, p.bias_ym, k1);
-                            const uint32_t ix1 = line_code_magic(static_cast<double>(o[1][0]), p.Lx, p.inv_dx, p.bias_xm, k2);
-                            const uint32_t iy1 = line_code_magic(static_cast<double>(o[1][1]), p.Ly, p.inv_dy, p.bias_ym, k3);
+                            const uint32_t wx0 = line_q(static_cast<double>(o[0][0]), p.inv_dx, p.bias_xq, k0);
+                            const uint32_t wy0 = line_q(static_cast<double>(o[0][1]), p.inv_dy, p.bias_yq, k1);
+                            const uint32_t wx1 = line_q(static_cast<double>(o[1][0]), p.inv_dx, p.bias_xq, k2);
+                            const uint32_t wy1 = line_q(static_cast<double>(o[1][1]), p.inv_dy, p.bias_yq, k3);
                             if (k0 && k1 && k2 && k3) {
-                                if constexpr (CODE8)  // codes = 2 * index, doubled after packing (index <= 127: no carry between fields)
-                                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(va), "r"((ix0 | (iy0 << 8) | (ix1 << 16) | (iy1 << 24)) << 1) : "memory");
+                                // both points at once: [ceil(g1) : ceil(g0)] in 16-bit halves, clamped to [0, Lc]; code = 2 * index
+                                const uint32_t X = __vimin_s16x2_relu(__byte_perm(wx0, wx1, 0x7632), lx2);
+                                const uint32_t Y = __vimin_s16x2_relu(__byte_perm(wy0, wy1, 0x7632), ly2);
+                                if constexpr (CODE8)  // index <= 127: no carry between the byte fields
+                                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(va), "r"((X | (Y << 8)) << 1) : "memory");
                                 else
-                                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(va), "r"((ix0 | (iy0 << 16)) << 1), "r"((ix1 | (iy1 << 16)) << 1) : "memory");
+                                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(va), "r"(__byte_perm(X, Y, 0x5410) << 1),
+                                                 "r"(__byte_perm(X, Y, 0x7632) << 1)
+                                                 : "memory");
                             } else {  // rare: a coordinate within rounding distance of a sweep line -> exact search
                                 const uint32_t cx0 = line_code(static_cast<double>(o[0][0]), txs, p.Lx, p.inv_dx, p.bias_x);
                                 const uint32_t cy0 = line_code(static_cast<double>(o[0][1]), tys, p.Ly, p.inv_dy, p.bias_y);
@@ -921,8 +928,8 @@ int launch_minksweep3d(Ctx* c, int K, int B, int n_first_obj, int n_objs, const 
     p.inv_dy = 1.0 / dy;
     p.bias_x = -c->lim[0] * p.inv_dx;
     p.bias_y = -c->lim[2] * p.inv_dy;
-    p.bias_xm = p.bias_x + 6442450944.0;
-    p.bias_ym = p.bias_y + 6442450944.0;
+    p.bias_xq = p.bias_x + (103079215104.0 + 0.9999847412109375);
+    p.bias_yq = p.bias_y + (103079215104.0 + 0.9999847412109375);
     p.zlow = c->lim[4];
     p.zup = c->lim[5];
     const long long grid = static_cast<long long>(K) * n_objs * B;
