@@ -600,6 +600,7 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
     const int nunits = nc1 * UPR;
     const uint32_t upr_magic = (UPR > 1) ? 0xFFFFFFFFu / static_cast<uint32_t>(UPR) + 1u : 0u;  // u / UPR == umulhi(u, magic), u < 2^16
     const bool vec_ok = (n & 3) == 0;
+    constexpr int kUPL = 4;  // units per lane and batch: smaller batches balance the warps better, larger ones amortise the prefix scan
     const int lane = tid & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     // keep bits of the 8 faces of unit u
@@ -661,14 +662,14 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
             if (!batch_loaded) {
                 if (lane == 0) bw = atomicAdd(batch_ctr, 1);
                 bw = __shfl_sync(0xFFFFFFFFu, bw, 0);
-                if (bw * 128 >= nunits) {
+                if (bw * (32 * kUPL) >= nunits) {
                     scanning = false;
                     break;
                 }
                 w_bits = 0u;
 #pragma unroll
-                for (int uu = 0; uu < 4; ++uu) {
-                    const int unit = (bw * 32 + lane) * 4 + uu;
+                for (int uu = 0; uu < kUPL; ++uu) {
+                    const int unit = (bw * 32 + lane) * kUPL + uu;
                     if (unit < nunits) w_bits |= unit_bits(unit) << (8 * uu);
                 }
                 w_cnt = __popc(w_bits);
@@ -707,7 +708,7 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
                         uint32_t x = wsrc;
                         for (uint32_t k = rank - excl; k > 0; --k) x &= x - 1;  // drop the lower set bits of that word
                         const int bit = __ffs(x) - 1;
-                        const int unit = (bw * 32 + src) * 4 + (bit >> 3), half = bit & 1;
+                        const int unit = (bw * 32 + src) * kUPL + (bit >> 3), half = bit & 1;
                         const int i = (UPR > 1) ? static_cast<int>(__umulhi(static_cast<uint32_t>(unit), upr_magic)) : unit;
                         const int j = 4 * (unit - i * UPR) + ((bit >> 1) & 3);
                         const int q = i * n + j;
