@@ -340,3 +340,47 @@ def plan2d(n_arena, n_obs, se, num, robot_rows, num_slice, lim, Ly, num_point, s
                       _p(info), _p(vertex), C.c_long(cap_v), _p(edge), C.c_long(cap_e), _p(path), C.c_long(cap_v))
     assert info[1] <= cap_v and info[2] <= cap_e
     return _plan_out(info, vertex, edge, path)
+
+
+# ---- articulated path (hrmo_articulated.hpp) ----------------------------------------------------------------------------
+def fk(urdf, joints, body):
+    """ParseURDF::getTransform(jointConfig, "body<k>") (body 0 = root link) -> (4x4 matrix, number of joints)."""
+    joints = _d(joints)
+    out = np.zeros(16)
+    nj = lib().hrmo_fk(str(urdf).encode(), _p(joints), C.c_int(joints.shape[0]), C.c_int(body), _p(out))
+    if nj < 0:
+        raise RuntimeError("hrmo_fk failed for %s body %d" % (urdf, body))
+    return out.reshape(4, 4), nj
+
+
+def robot_tf_urdf(n, robot_rows, urdf, base7, joints):
+    """MultiBodyTree3D::robotTF(urdf, gBase, jointConfig) -> body poses [B][7] (x,y,z,qw,qx,qy,qz), base first."""
+    robot_rows, base7, joints = _d(robot_rows), _d(base7), _d(joints)
+    out = np.zeros((robot_rows.shape[0], 7))
+    rc = lib().hrmo_robot_tf_urdf(C.c_int(n), C.c_int(robot_rows.shape[0]), _p(robot_rows), str(urdf).encode(), _p(base7), _p(joints),
+                                  C.c_int(joints.shape[0]), _p(out))
+    if rc != 0:
+        raise RuntimeError("hrmo_robot_tf_urdf failed")
+    return out
+
+
+def plan_prob3d(n_arena, n_obs, sq, n, robot_rows, urdf, samples, lim, Lx, Ly, num_point, start, goal, per_orientation=False,
+                cap_v=1 << 18, cap_e=1 << 21):
+    """ProbHRM3D::plan with the random draws injected: samples [N][4 + nj] for the slices after start and goal."""
+    sq, robot_rows, samples, lim = _d(sq), _d(robot_rows), _d(samples), _d(lim)
+    nj = samples.shape[1] - 4
+    start, goal = _d(start)[: 7 + nj].copy(), _d(goal)[: 7 + nj].copy()
+    info = np.zeros(8, dtype=np.int64)
+    vertex = np.zeros((cap_v, 7 + nj))
+    edge = np.zeros((cap_e, 2), dtype=np.int64)
+    path = np.zeros(cap_v, dtype=np.int64)
+    rc = lib().hrmo_plan_prob3d(C.c_int(n_arena), C.c_int(n_obs), _p(sq), C.c_int(n), C.c_int(robot_rows.shape[0]), _p(robot_rows),
+                                str(urdf).encode(), C.c_int(nj), C.c_int(samples.shape[0]), _p(samples), _p(lim), C.c_int(Lx), C.c_int(Ly),
+                                C.c_int(num_point), _p(start), _p(goal), C.c_int(int(per_orientation)), _p(info), _p(vertex),
+                                C.c_long(cap_v), _p(edge), C.c_long(cap_e), _p(path), C.c_long(cap_v))
+    if rc != 0:
+        raise RuntimeError("hrmo_plan_prob3d failed (%d)" % rc)
+    assert info[1] <= cap_v and info[2] <= cap_e
+    out = _plan_out(info, vertex, edge, path)
+    out["slices"] = int(info[6])
+    return out

@@ -6,7 +6,7 @@
 // [a,b,eps,px,py,angle]; surfaces are ordered j = object*B + body, arena objects first; sweep lines
 // are ordered l = ix*Ly + iy; boundaries are Eigen-layout 3 x M (2 x N) column-major.
 #include "hrmo_freespace.hpp"
-#include "hrmo_planner.hpp"
+#include "hrmo_articulated.hpp"
 
 #include <chrono>
 #include <cstring>
@@ -473,4 +473,90 @@ int hrmo_plan2d(int n_arena, int n_obs, const double* se, int num, int B, const 
     return 0;
 }
 
+
+// ---- articulated path (hrmo_articulated.hpp) ---------------------------------------------------------------------------
+// ParseURDF::getTransform(jointConfig, "body<k>") of the URDF's revolute tree: out16 = row-major 4x4.  Returns the number
+// of joints, or -1 (file / link not found).
+int hrmo_fk(const char* urdf, const double* joints, int nj, int body, double* out16) {
+    try {
+        KinematicTree kdl(urdf);
+        const std::vector<double> q(joints, joints + nj);
+        const Tf3 f = kdl.getTransform(q, body == 0 ? kdl.root : "body" + std::to_string(body));
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j) out16[4 * i + j] = f.R.m[i][j];
+            out16[4 * i + 3] = f.t[i];
+        }
+        out16[12] = out16[13] = out16[14] = 0.0, out16[15] = 1.0;
+        return static_cast<int>(kdl.getNrOfJoints());
+    } catch (const std::exception&) {
+        return -1;
+    }
+}
+
+// MultiBodyTree3D::robotTF(urdf, gBase, jointConfig): body poses [B][7] = (x,y,z,qw,qx,qy,qz), base first.
+int hrmo_robot_tf_urdf(int n, int B, const double* robot, const char* urdf, const double* base7, const double* joints, int nj, double* out) {
+    try {
+        MultiBodyTree3D rb;
+        rb.base = make_sq(robot, n);
+        for (int b = 1; b < B; ++b) rb.addBody(make_sq(robot + 12 * b, n));
+        KinematicTree kdl(urdf);
+        Tf3 g;
+        g.R = quat_to_rot(Quat{base7[3], base7[4], base7[5], base7[6]});
+        for (int d = 0; d < 3; ++d) g.t[d] = base7[d];
+        robotTF(rb, kdl, g, std::vector<double>(joints, joints + nj));
+        for (int b = 0; b < B; ++b) {
+            const SuperQuadrics& s = b == 0 ? rb.base : rb.link[static_cast<size_t>(b) - 1];
+            for (int d = 0; d < 3; ++d) out[7 * b + d] = s.position[d];
+            out[7 * b + 3] = s.quat.w, out[7 * b + 4] = s.quat.x, out[7 * b + 5] = s.quat.y, out[7 * b + 6] = s.quat.z;
+        }
+        return 0;
+    } catch (const std::exception&) {
+        return -1;
+    }
+}
+
+// ProbHRM3D::plan with injected draws.  samples [n_samples][4 + nj] = (qw,qx,qy,qz, joints) for slices 2, 3, ...;
+// start/goal: 7 + nj doubles.  vertex [cap_v][7 + nj].  out_info as hrmo_plan3d, [6] = number of C-slices built.
+int hrmo_plan_prob3d(int n_arena, int n_obs, const double* sq, int n, int B, const double* robot, const char* urdf, int nj, int n_samples,
+                     const double* samples, const double lim[6], int Lx, int Ly, int numPoint, const double* start, const double* goal,
+                     int per_orientation, long* out_info, double* vertex, long cap_v, long* edge, long cap_e, long* path, long cap_p) {
+    try {
+        std::vector<SuperQuadrics> arena, obs;
+        for (int i = 0; i < n_arena; ++i) arena.push_back(make_sq(sq + 12 * i, n));
+        for (int i = 0; i < n_obs; ++i) obs.push_back(make_sq(sq + 12 * (n_arena + i), n));
+        MultiBodyTree3D rb;
+        rb.base = make_sq(robot, n);
+        for (int b = 1; b < B; ++b) rb.addBody(make_sq(robot + 12 * b, n));
+        PlanningRequest req;
+        req.isRobotRigid = false;
+        req.parameters.boundaryLimits.assign(lim, lim + 6);
+        req.parameters.numLineX = static_cast<size_t>(Lx);
+        req.parameters.numLineY = static_cast<size_t>(Ly);
+        req.parameters.numPoint = static_cast<size_t>(numPoint);
+        req.start.assign(start, start + 7 + nj);
+        req.goal.assign(goal, goal + 7 + nj);
+        std::vector<std::vector<double>> draws;
+        for (int i = 0; i < n_samples; ++i) draws.emplace_back(samples + static_cast<size_t>(i) * (4 + nj), samples + static_cast<size_t>(i + 1) * (4 + nj));
+        ProbHRM3D hrm(rb, urdf, arena, obs, req, draws, per_orientation != 0);
+        if (static_cast<int>(hrm.kdl_.getNrOfJoints()) != nj) return -2;
+        hrm.planProb();
+        const auto& g = hrm.res_.graphStructure;
+        const int W = 7 + nj;
+        out_info[0] = hrm.res_.solved ? 1 : 0;
+        out_info[1] = static_cast<long>(g.vertex.size());
+        out_info[2] = static_cast<long>(g.edge.size());
+        out_info[3] = static_cast<long>(hrm.res_.PathId.size());
+        out_info[4] = hrm.singleHitCount;
+        out_info[5] = hrm.numEdgeTests;
+        out_info[6] = static_cast<long>(hrm.param_.numSlice);
+        for (size_t i = 0; i < g.vertex.size() && static_cast<long>(i) < cap_v; ++i)
+            for (int d = 0; d < W; ++d) vertex[static_cast<size_t>(W) * i + d] = g.vertex[i][d];
+        for (size_t i = 0; i < g.edge.size() && static_cast<long>(i) < cap_e; ++i)
+            edge[2 * i] = static_cast<long>(g.edge[i].first), edge[2 * i + 1] = static_cast<long>(g.edge[i].second);
+        for (size_t i = 0; i < hrm.res_.PathId.size() && static_cast<long>(i) < cap_p; ++i) path[i] = hrm.res_.PathId[i];
+        return 0;
+    } catch (const std::exception&) {
+        return -1;
+    }
+}
 }  // extern "C"

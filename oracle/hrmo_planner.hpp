@@ -284,6 +284,7 @@ struct HRM3D : HighwayRoadMap<MultiBodyTree3D, SuperQuadrics> {
     FreeSpace3D freeSpace_;
     std::vector<Quat> q_;
     std::vector<Quat> quatSamples_;  // robot_.getBase().getQuatSamples()
+    std::vector<std::vector<double>> v_;  // articulated robot shapes, one per C-slice (HRM3D.h: v_)
     BoundaryInfo sliceBound_;
     BoundaryMesh sliceBoundMesh_;
     std::vector<BoundaryInfo> sliceBoundAll_;
@@ -300,7 +301,7 @@ struct HRM3D : HighwayRoadMap<MultiBodyTree3D, SuperQuadrics> {
     }
 
     // :510-518
-    void setTransform(const std::vector<double>& v) {
+    virtual void setTransform(const std::vector<double>& v) {
         Tf3 g;
         g.R = quat_to_rot(Quat{v[3], v[4], v[5], v[6]});
         g.t[0] = v[0], g.t[1] = v[1], g.t[2] = v[2];
@@ -315,7 +316,10 @@ struct HRM3D : HighwayRoadMap<MultiBodyTree3D, SuperQuadrics> {
 
     // :24-54
     void constructOneSlice(size_t sliceIdx) override {
-        setTransform({0.0, 0.0, 0.0, q_.at(sliceIdx).w, q_.at(sliceIdx).x, q_.at(sliceIdx).y, q_.at(sliceIdx).z});
+        if (isRobotRigid_)
+            setTransform({0.0, 0.0, 0.0, q_.at(sliceIdx).w, q_.at(sliceIdx).x, q_.at(sliceIdx).y, q_.at(sliceIdx).z});
+        else
+            setTransform(v_.at(sliceIdx));  // articulated: base pose + joint angles (ProbHRM3D)
         if (perOrientationFreeSpace_) freeSpace_.setRobot(robot_);
         freeSpace_.computeCSpaceBoundary();
         sliceBound_ = freeSpace_.cSpaceBoundary_;
@@ -333,7 +337,7 @@ struct HRM3D : HighwayRoadMap<MultiBodyTree3D, SuperQuadrics> {
     }
 
     // :93-113
-    void generateVertices(double tx, const FreeSegment2D& freeSeg) {
+    virtual void generateVertices(double tx, const FreeSegment2D& freeSeg) {
         numVertex_.plane.clear();
         for (size_t i = 0; i < freeSeg.ty.size(); ++i) {
             numVertex_.plane.push_back(res_.graphStructure.vertex.size());

@@ -114,12 +114,46 @@ def scene2d(obj_type, env, robot):
             "Ly": int(bound[1] / min_obs), "source": f"{obj_type}/{env}/{robot}"}
 
 
+def emit_urdf(name):
+    """Re-emits the kinematic skeleton (joints only: parent, child, origin, axis, type) of resources/3D/urdf/<name>.urdf."""
+    import xml.etree.ElementTree as ET
+    root = ET.parse(f"{REF}/3D/urdf/{name}.urdf").getroot()
+    lines = ['<?xml version="1.0" ?>', f'<!-- kinematic skeleton of the reference robot "{name}" (joints only), written by tests/golden/make_scenes.py -->',
+             f'<robot name="{name}">']
+    links = []
+    for j in root.findall("joint"):
+        for tag in ("parent", "child"):
+            if j.find(tag).get("link") not in links:
+                links.append(j.find(tag).get("link"))
+    for link in links:
+        lines.append(f'  <link name="{link}"/>')
+    for j in root.findall("joint"):
+        o, a = j.find("origin"), j.find("axis")
+        lines.append(f'  <joint name="{j.get("name")}" type="{j.get("type")}">')
+        lines.append(f'    <parent link="{j.find("parent").get("link")}"/>')
+        lines.append(f'    <child link="{j.find("child").get("link")}"/>')
+        lines.append(f'    <origin rpy="{o.get("rpy", "0 0 0")}" xyz="{o.get("xyz", "0 0 0")}"/>')
+        if a is not None:
+            lines.append(f'    <axis xyz="{a.get("xyz")}"/>')
+        lines.append("  </joint>")
+    lines.append("</robot>")
+    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), f"{name}.urdf")
+    with open(out, "w") as f:
+        f.write("\n".join(lines) + "\n")
+    print("wrote", out)
+
+
 def main():
+    for name in ("snake", "tree"):
+        emit_urdf(name)
+
     scenes = {}
     for env in ["sparse", "cluttered", "maze", "narrow", "home"]:
         scenes[f"3D_superquadrics_{env}_rabbit"] = scene3d("superquadrics", env, "rabbit")
     scenes["3D_superquadrics_home_snake"] = scene3d("superquadrics", "home", "snake")
     scenes["3D_superquadrics_sparse_snake"] = scene3d("superquadrics", "sparse", "snake")
+    scenes["3D_superquadrics_sparse_tree"] = scene3d("superquadrics", "sparse", "tree")
+    scenes["3D_superquadrics_cluttered_snake"] = scene3d("superquadrics", "cluttered", "snake")
     scenes["3D_ellipsoid_sparse_rabbit"] = scene3d("ellipsoid", "sparse", "rabbit")
     for env in ["sparse", "cluttered", "maze1", "maze2", "maze3", "NAO_lab"]:
         scenes[f"2D_superellipse_{env}_rabbit"] = scene2d("superellipse", env, "rabbit")

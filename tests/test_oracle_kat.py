@@ -1,6 +1,9 @@
 """Pins the CPU oracle against every known-answer value the reference's own tests hold for the hot path
 (/root/reference/test/TestGeometry.cpp) and against analytic identities for the parts the reference leaves unpinned."""
+import os
+
 import numpy as np
+import pytest
 
 from tests import util
 
@@ -156,3 +159,127 @@ def test_planner_solves_reference_test_scenes(oracle):
     r = oracle.plan2d(1, len(sc["obstacle"]), np.array(sc["arena"] + sc["obstacle"]), 50, np.array(sc["robot"]), 10, sc["lim"], sc["Ly"],
                       5, sc["end_points"][0], sc["end_points"][1])
     assert sc["Ly"] == 3 and r["solved"]
+
+
+# ---- articulated path: URDF revolute tree, forward kinematics, ProbHRM3D (oracle/hrmo_articulated.hpp) -------------------
+# KDL / urdfdom are third-party dependencies absent from the reference tree: the FK restatement is pinned by analytic
+# identities, the planner by the assertion of the reference's own test (test/TestProbHRM3D.cpp:8-62: `solved`).
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_fk_zero_configuration_is_a_translation_chain(oracle):
+    urdf = os.path.join(GOLDEN, "snake.urdf")
+    for body, x in ((0, 0.0), (1, 7.0), (2, 15.2), (3, 23.4)):  # joint origins 7.0, +8.2, +8.2 along x
+        T, nj = oracle.fk(urdf, [0.0, 0.0, 0.0], body)
+        assert nj == 3
+        assert np.allclose(T[:3, :3], np.eye(3), atol=1e-15) and np.allclose(T[:3, 3], [x, 0, 0], atol=1e-14)
+
+
+def test_fk_known_rotations(oracle):
+    urdf = os.path.join(GOLDEN, "snake.urdf")
+    h = np.pi / 2
+    # joint 1 about +y by 90 deg: the chain's x axis turns to -z; body2's origin sits 8.2 along the rotated x
+    T2, _ = oracle.fk(urdf, [h, 0.0, 0.0], 2)
+    assert np.allclose(T2[:3, 3], [7.0, 0.0, -8.2], atol=1e-14)
+    assert np.allclose(T2[:3, :3], [[0, 0, 1], [0, 1, 0], [-1, 0, 0]], atol=1e-15)
+    # joint 2 about +z by 90 deg (joint 1 at rest): body3's origin moves from x to y
+    T3, _ = oracle.fk(urdf, [0.0, h, 0.0], 3)
+    assert np.allclose(T3[:3, 3], [15.2, 8.2, 0.0], atol=1e-14)
+    # composition: FK(q) of body3 == T01(q0) T12(q1) T23(q2) built by hand
+    q = [0.3, -0.7, 1.1]
+
+    def rot(axis, a):
+        c, s = np.cos(a), np.sin(a)
+        return {"y": np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]]), "z": np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]])}[axis]
+
+    def hom(R, t):
+        M = np.eye(4)
+        M[:3, :3], M[:3, 3] = R, t
+        return M
+
+    want = hom(rot("y", q[0]), [7.0, 0, 0]) @ hom(rot("z", q[1]), [8.2, 0, 0]) @ hom(rot("y", q[2]), [8.2, 0, 0])
+    got, _ = oracle.fk(urdf, q, 3)
+    assert np.allclose(got, want, atol=1e-14)
+
+
+def test_fk_tree_joint_numbering(oracle):
+    """tree.urdf: three chains off the base; KDL numbers joints depth first in name order, so joint k drives body k+1."""
+    urdf = os.path.join(GOLDEN, "tree.urdf")
+    T0, nj = oracle.fk(urdf, np.zeros(9), 9)
+    assert nj == 9 and np.allclose(T0[:3, 3], [0, 0, 2.1 + 8.2 + 8.2], atol=1e-14)
+    for k in range(9):
+        q = np.zeros(9)
+        q[k] = 0.5
+        for body in range(1, 10):
+            T, _ = oracle.fk(urdf, q, body)
+            base, _ = oracle.fk(urdf, np.zeros(9), body)
+            chain = (body - 1) // 3
+            moved = not np.allclose(T, base, atol=1e-15)
+            assert moved == (chain == k // 3 and body - 1 >= k), (k, body)
+
+
+def test_robot_tf_urdf_matches_rigid_tf_at_zero_joints(oracle):
+    """With all joints at rest the articulated transform must place the links where the rigid-body tree does, given that the
+    robot file's link poses are expressed relative to the URDF frames of body<k> (resources/3D/robot_snake_3D.csv)."""
+    sc = util.scenes()["3D_superquadrics_sparse_snake"]
+    urdf = os.path.join(GOLDEN, "snake.urdf")
+    base = [1.0, -2.0, 0.5, 0.5, 0.5, 0.5, 0.5]
+    poses = oracle.robot_tf_urdf(10, np.array(sc["robot"]), urdf, base, [0.0, 0.0, 0.0])
+    R = np.array([[0, 0, 1], [1, 0, 0], [0, 1, 0]], dtype=float)  # rotation of the quaternion (.5,.5,.5,.5)
+    assert np.allclose(poses[0, :3], base[:3]) and np.allclose(poses[0, 3:], base[3:], atol=1e-15)
+    for k, x in enumerate((7.0 + 4.1, 15.2 + 4.1, 23.4 + 4.1)):
+        assert np.allclose(poses[k + 1, :3], np.array(base[:3]) + R @ np.array([x, 0, 0]), atol=1e-13)
+        assert np.allclose(np.abs(poses[k + 1, 3:]), 0.5, atol=1e-15)
+
+
+def _halton(i, base):
+    f, r = 1.0, 0.0
+    while i > 0:
+        f /= base
+        r += f * (i % base)
+        i //= base
+    return r
+
+
+def prob_samples(count, nj, max_joint=np.pi / 2):
+    """Deterministic stand-in for Quaterniond::UnitRandom() + ompl::RNG::uniformReal: Halton points mapped to unit quaternions
+    (Shoemake) and joint angles in [-max_joint, max_joint]."""
+    out = []
+    primes = [2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37]
+    for i in range(1, count + 1):
+        u1, u2, u3 = _halton(i, 2), _halton(i, 3), _halton(i, 5)
+        q = [np.sqrt(u1) * np.cos(2 * np.pi * u3), np.sqrt(1 - u1) * np.sin(2 * np.pi * u2), np.sqrt(1 - u1) * np.cos(2 * np.pi * u2),
+             np.sqrt(u1) * np.sin(2 * np.pi * u3)]
+        joints = [(2 * _halton(i, primes[3 + j]) - 1) * max_joint for j in range(nj)]
+        out.append(q + joints)
+    return np.array(out)
+
+
+@pytest.mark.parametrize("per_orientation", [False, True])
+def test_prob_hrm3d_sparse_snake_solves(oracle, per_orientation):
+    """test/TestProbHRM3D.cpp: superquadrics/sparse/snake, n = 10, default sweep lines -> solved.  (With the reference's
+    search rule -- start and goal are matched to their nearest vertices of the slices built so far -- the sparse map is
+    already solved inside the first slice.)"""
+    sc = util.scenes()["3D_superquadrics_sparse_snake"]
+    rows = np.array(sc["arena"] + sc["obstacle"])
+    res = oracle.plan_prob3d(len(sc["arena"]), len(sc["obstacle"]), rows, 10, np.array(sc["robot"]), os.path.join(GOLDEN, "snake.urdf"),
+                             prob_samples(40, 3), sc["lim"], sc["Lx"], sc["Ly"], 5, sc["end_points"][0], sc["end_points"][1],
+                             per_orientation=per_orientation)
+    assert res["solved"] and res["slices"] >= 1
+    assert res["vertex"].shape[1] == 10  # x, y, z, quaternion, 3 joint angles
+    assert np.array_equal(res["vertex"][0, 7:], np.array(sc["end_points"][0][7:10]))  # slice 0 carries the start joint angles
+    assert len(res["path"]) >= 2
+
+
+def test_prob_hrm3d_home_snake_needs_several_slices(oracle):
+    """BASELINE.json configs[3] scene (home map, snake): with per-orientation layers the start slice alone does not connect
+    start and goal, so the random slices, the nearest-slice bridge (TFE over the interpolated articulated motion) and the
+    joint-carrying vertices are all exercised."""
+    sc = util.scenes()["3D_superquadrics_home_snake"]
+    rows = np.array(sc["arena"] + sc["obstacle"])
+    res = oracle.plan_prob3d(1, len(sc["obstacle"]), rows, 10, np.array(sc["robot"]), os.path.join(GOLDEN, "snake.urdf"), prob_samples(30, 3),
+                             sc["lim"], sc["Lx"], sc["Ly"], 5, sc["end_points"][0], sc["end_points"][1], per_orientation=True)
+    assert res["solved"] and res["slices"] > 2
+    joints = np.unique(res["vertex"][:, 7:], axis=0)
+    assert len(joints) == res["slices"]  # one joint configuration per slice
+    assert np.all(np.abs(joints) <= np.pi / 2 + 1e-6)
