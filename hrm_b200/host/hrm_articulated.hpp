@@ -1,0 +1,357 @@
+// Articulated robots on the GPU-backed free space: URDF revolute tree + forward kinematics and the
+// probabilistic planner, with the reference's names --
+//   hrm::ParseURDF                      include/hrm/util/ParseURDF.h, src/util/ParseURDF.cpp:10-33 (urdfdom + kdl_parser + KDL FK)
+//   MultiBodyTree3D::robotTF(kdl, ...)  src/datastructure/MultiBodyTree3D.cpp:55-89 (template member in hrm_host.hpp)
+//   hrm::planners::ProbHRM3D            include/hrm/planners/ProbHRM3D.h, src/planners/ProbHRM3D.cpp:7-246
+// orocos-KDL / urdfdom are not vendored by the reference: a URDF joint is the frame Frame(Rot(axis, q), xyz) * Frame(RPY, 0)
+// (kdl_parser's toKdl), joints are numbered depth first with children in joint-name order, poses multiply from the root.
+//
+// B200 design: the reference builds ONE C-slice per iteration.  The draws (base rotation + joint angles) do not depend on
+// the roadmap, so this planner draws `batch` slices ahead, builds their layers (K1+K2+K3) in one `hrmgpu_build_layers`
+// call, and then replays the reference's sequential loop -- vertices, intra-layer edges (K4 batches), nearest-slice
+// bridge (host TFE over the interpolated articulated motion, K5) and graph search -- slice by slice, so the roadmap is the
+// reference's for the same draws.
+#pragma once
+#include "hrm_host.hpp"
+
+#include <fstream>
+#include <random>
+#include <sstream>
+
+namespace hrm {
+
+class ParseURDF {
+  public:
+    explicit ParseURDF(const std::string& urdfFile) {
+        std::ifstream in(urdfFile);
+        if (!in) throw std::invalid_argument("Failed to parse and construct KDL tree: cannot open " + urdfFile);
+        std::stringstream buf;
+        buf << in.rdbuf();
+        std::string xml = buf.str();
+        for (size_t a; (a = xml.find("<!--")) != std::string::npos;) {
+            const size_t b = xml.find("-->", a);
+            xml.erase(a, (b == std::string::npos ? xml.size() : b + 3) - a);
+        }
+        std::vector<JointDesc> joints;
+        for (size_t p = 0; (p = xml.find("<joint ", p)) != std::string::npos;) {
+            const size_t headEnd = xml.find('>', p), end = xml.find("</joint>", p);
+            if (end == std::string::npos) break;
+            const std::string head = xml.substr(p, headEnd - p + 1), body = xml.substr(headEnd + 1, end - headEnd - 1);
+            JointDesc j;
+            j.name = attr(head, "name"), j.type = attr(head, "type");
+            j.parent = attr(element(body, "parent"), "link"), j.child = attr(element(body, "child"), "link");
+            triple(attr(element(body, "origin"), "xyz"), j.xyz);
+            triple(attr(element(body, "origin"), "rpy"), j.rpy);
+            triple(attr(element(body, "axis"), "xyz"), j.axis);
+            joints.push_back(j);
+            p = end;
+        }
+        std::map<std::string, std::vector<const JointDesc*>> children;
+        std::map<std::string, bool> isChild;
+        for (const auto& j : joints) children[j.parent].push_back(&j), isChild[j.child] = true;
+        for (auto& c : children)
+            std::sort(c.second.begin(), c.second.end(), [](const JointDesc* a, const JointDesc* b) { return a->name < b->name; });
+        for (const auto& j : joints)
+            if (!isChild.count(j.parent)) root_ = j.parent;
+        addChildren(root_, children);
+    }
+
+    size_t getNrOfJoints() const { return numJoints_; }
+    const std::string& getRootName() const { return root_; }
+
+    /** pose of link `bodyName` in the root frame for the joint angles `jointConfig` (rotation passed through a quaternion) */
+    SE3Transform getTransform(const std::vector<double>& jointConfig, const std::string& bodyName) const {
+        SE3Transform f = pose(jointConfig, bodyName);
+        f.R = toRotationMatrix(toQuaternion(f.R));
+        return f;
+    }
+
+  private:
+    struct JointDesc {
+        std::string name, type, parent, child;
+        double xyz[3] = {0, 0, 0}, rpy[3] = {0, 0, 0}, axis[3] = {1, 0, 0};
+    };
+    struct Segment {
+        std::string parent;
+        Mat3 originR;
+        Vec3 origin, axis;
+        int q = -1;
+    };
+    static std::string attr(const std::string& tag, const std::string& key) {
+        const std::string k = " " + key + "=\"";
+        size_t p = tag.find(k);
+        if (p == std::string::npos) return "";
+        p += k.size();
+        return tag.substr(p, tag.find('"', p) - p);
+    }
+    static std::string element(const std::string& body, const std::string& name) {
+        const size_t a = body.find("<" + name);
+        return a == std::string::npos ? std::string() : body.substr(a, body.find('>', a) - a + 1);
+    }
+    static void triple(const std::string& s, double out[3]) {
+        if (s.empty()) return;
+        std::istringstream in(s);
+        in >> out[0] >> out[1] >> out[2];
+    }
+    static Mat3 rotAxis(const Vec3& v, double angle) {  // KDL::Rotation::Rot2
+        const double ct = std::cos(angle), st = std::sin(angle), vt = 1.0 - ct;
+        const double mvt0 = vt * v[0], mvt1 = vt * v[1], mvt2 = vt * v[2];
+        const double mst0 = v[0] * st, mst1 = v[1] * st, mst2 = v[2] * st;
+        const double mvt01 = mvt0 * v[1], mvt02 = mvt0 * v[2], mvt12 = mvt1 * v[2];
+        Mat3 r;
+        r[0] = {ct + mvt0 * v[0], -mst2 + mvt01, mst1 + mvt02};
+        r[1] = {mst2 + mvt01, ct + mvt1 * v[1], -mst0 + mvt12};
+        r[2] = {-mst1 + mvt02, mst0 + mvt12, ct + mvt2 * v[2]};
+        return r;
+    }
+    static Mat3 rotRPY(double roll, double pitch, double yaw) {  // KDL::Rotation::RPY = Rz(yaw) Ry(pitch) Rx(roll)
+        const double ca1 = std::cos(yaw), sa1 = std::sin(yaw), cb1 = std::cos(pitch), sb1 = std::sin(pitch), cc1 = std::cos(roll),
+                     sc1 = std::sin(roll);
+        Mat3 r;
+        r[0] = {ca1 * cb1, ca1 * sb1 * sc1 - sa1 * cc1, ca1 * sb1 * cc1 + sa1 * sc1};
+        r[1] = {sa1 * cb1, sa1 * sb1 * sc1 + ca1 * cc1, sa1 * sb1 * cc1 - ca1 * sc1};
+        r[2] = {-sb1, cb1 * sc1, cb1 * cc1};
+        return r;
+    }
+    void addChildren(const std::string& link, const std::map<std::string, std::vector<const JointDesc*>>& children) {
+        const auto it = children.find(link);
+        if (it == children.end()) return;
+        for (const JointDesc* j : it->second) {
+            Segment s;
+            s.parent = j->parent;
+            s.originR = rotRPY(j->rpy[0], j->rpy[1], j->rpy[2]);
+            s.origin = {j->xyz[0], j->xyz[1], j->xyz[2]};
+            const Vec3 a = matVec(s.originR, {j->axis[0], j->axis[1], j->axis[2]});
+            const double nrm = std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+            s.axis = {a[0] / nrm, a[1] / nrm, a[2] / nrm};
+            if (j->type == "revolute" || j->type == "continuous") s.q = static_cast<int>(numJoints_++);
+            segments_[j->child] = s;
+            addChildren(j->child, children);
+        }
+    }
+    SE3Transform pose(const std::vector<double>& q, const std::string& link) const {
+        SE3Transform id;
+        if (link == root_) return id;
+        const auto it = segments_.find(link);
+        if (it == segments_.end()) throw std::invalid_argument("Error in solving forward kinematics: no link " + link);
+        const Segment& s = it->second;
+        SE3Transform cur;  // Segment::pose(q) = Frame(Rot2(axis, q), origin) * Frame(originR, 0)
+        const Mat3 eye = id.R;
+        cur.R = matMul(s.q >= 0 ? rotAxis(s.axis, q.at(static_cast<size_t>(s.q))) : eye, s.originR);
+        cur.t = s.origin;
+        if (s.parent == root_) return cur;
+        const SE3Transform par = pose(q, s.parent);
+        SE3Transform out;
+        out.R = matMul(par.R, cur.R);
+        const Vec3 v = matVec(par.R, cur.t);
+        out.t = {v[0] + par.t[0], v[1] + par.t[1], v[2] + par.t[2]};
+        return out;
+    }
+
+    std::map<std::string, Segment> segments_;  // keyed by child link
+    std::string root_;
+    size_t numJoints_ = 0;
+};
+
+namespace planners {
+
+class ProbHRM3D : public HRM3D {
+  public:
+    ProbHRM3D(const MultiBodyTree3D& robot, const std::string& urdfFile, const std::vector<SuperQuadrics>& arena,
+              const std::vector<SuperQuadrics>& obs, const PlanningRequest& req, int device = 0, int precision = HRMGPU_F64_STRICT,
+              bool perOrientation = false)
+        : HRM3D(robot, arena, obs, req, device, precision, perOrientation), urdfFile_(urdfFile), kdl_(urdfFile) {
+        q_.clear();
+        param_.numSlice = 0;
+    }
+
+    /** The reference draws Quaterniond::UnitRandom() and ompl::RNG::uniformReal(-pi/2, pi/2) per slice (ProbHRM3D.cpp:67-96,
+     * srand(time)): rows [qw,qx,qy,qz, joints...] given here replace those draws (slices 2, 3, ...); planning stops when the
+     * list is exhausted.  Without a list the draws come from a seeded std::mt19937_64. */
+    void setSampleList(const std::vector<std::vector<double>>& samples) { samples_ = samples, injected_ = true; }
+    void setSeed(unsigned long long seed) { rng_.seed(seed); }
+    void setBatch(size_t batch) { batch_ = batch > 0 ? batch : 1; }
+    void setMaxSlices(size_t n) { maxSlices_ = n; }
+    Index numSlices() const { return param_.numSlice; }
+
+    /** ProbHRM3D.cpp:18-65 */
+    void plan(double timeLim = 0.0) override {
+        auto t0 = std::chrono::high_resolution_clock::now();
+        const auto& lim = param_.boundaryLimits;
+        const int Lx = static_cast<int>(param_.numLineX), Ly = static_cast<int>(param_.numLineY);
+        freeSpace_.setup(lim, param_.numLineX, param_.numLineY);
+        const double dx = (lim[1] - lim[0]) / static_cast<double>(Lx - 1), dy = (lim[3] - lim[2]) / static_cast<double>(Ly - 1);
+        std::vector<double> tx(Lx), ty(Ly);
+        for (int i = 0; i < Lx; ++i) tx[i] = lim[0] + static_cast<double>(i) * dx;
+        for (int i = 0; i < Ly; ++i) ty[i] = lim[2] + static_cast<double>(i) * dy;
+
+        param_.numSlice = 0;
+        size_t batchStart = 0, batchEnd = 0;  // slices [batchStart, batchEnd) have their layers on the device
+        std::vector<long long> off;
+        std::vector<double> xL, xU, xM;
+        std::vector<Quaternion> baseQ;
+        do {
+            const size_t s = param_.numSlice;
+            if (s >= batchEnd) {  // draw the next batch of robot shapes and build their C-layers in one call
+                const size_t want = s < 2 ? 2 : batch_;
+                size_t have = 0;
+                std::vector<MultiBodyTree3D> poses;
+                baseQ.clear();
+                while (have < want && drawShape(s + have)) {
+                    setTransform(v_.at(s + have));
+                    baseQ.push_back(robot_.getBase().getQuaternion());
+                    poses.push_back(perOrientation_ ? robot_ : robot0_);  // the reference's FreeSpace copy keeps the as-loaded pose (finding 1)
+                    ++have;
+                }
+                if (have == 0) break;  // injected draws exhausted
+                freeSpace_.buildLayers(poses, precision_);
+                freeSpace_.getFreeSegmentsAll(off, xL, xU, xM);
+                batchStart = s, batchEnd = s + have;
+            }
+            // constructOneSlice: vertices + intra-layer edges of slice s
+            const size_t k = s - batchStart;
+            vertexTail_.assign(v_.at(s).begin() + 7, v_.at(s).end());
+            q_.push_back({v_.at(s)[3], v_.at(s)[4], v_.at(s)[5], v_.at(s)[6]});
+            connectOneSlice3D(static_cast<int>(k), baseQ.at(k), tx, ty, off.data() + k * static_cast<size_t>(Lx) * Ly, xL, xU, xM);
+            param_.numSlice++;
+            if (param_.numSlice >= 2) connectNearestSlice();
+            res_.planningTime.buildTime += seconds(t0);
+            t0 = std::chrono::high_resolution_clock::now();
+            search();
+            res_.planningTime.searchTime += seconds(t0);
+            t0 = std::chrono::high_resolution_clock::now();
+            res_.planningTime.totalTime = res_.planningTime.buildTime + res_.planningTime.searchTime;
+        } while (!res_.solved && param_.numSlice < maxSlices_ && (timeLim <= 0.0 || res_.planningTime.totalTime < timeLim));
+        if (res_.solved) {
+            const size_t pose = res_.graphStructure.vertex.at(0).size();
+            start_.resize(pose), goal_.resize(pose);
+            res_.solutionPath.solvedPath.push_back(start_);
+            for (Index id : res_.solutionPath.PathId) res_.solutionPath.solvedPath.push_back(res_.graphStructure.vertex.at(id));
+            res_.solutionPath.solvedPath.push_back(goal_);
+            res_.solutionPath.interpolatedPath = res_.solutionPath.solvedPath;
+        }
+    }
+
+  protected:
+    static double seconds(std::chrono::high_resolution_clock::time_point t0) {
+        return std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+    }
+
+    /** sampleOrientations (:67-102) for slice s; false when the injected list has no more rows */
+    bool drawShape(size_t s) {
+        if (s < v_.size()) return true;
+        const size_t nj = kdl_.getNrOfJoints();
+        std::vector<Coordinate> config{0.0, 0.0, 0.0};
+        if (s == 0) {
+            config.insert(config.end(), start_.begin() + 3, start_.begin() + 7 + static_cast<long>(nj));
+        } else if (s == 1) {
+            config.insert(config.end(), goal_.begin() + 3, goal_.begin() + 7 + static_cast<long>(nj));
+        } else if (injected_) {
+            if (s - 2 >= samples_.size()) return false;
+            config.insert(config.end(), samples_[s - 2].begin(), samples_[s - 2].begin() + 4 + static_cast<long>(nj));
+        } else {
+            std::uniform_real_distribution<double> u(0.0, 1.0);  // Shoemake's uniform unit quaternion
+            const double u1 = u(rng_), u2 = u(rng_), u3 = u(rng_), twoPi = 6.283185307179586;
+            config.push_back(std::sqrt(u1) * std::cos(twoPi * u3));
+            config.push_back(std::sqrt(1.0 - u1) * std::sin(twoPi * u2));
+            config.push_back(std::sqrt(1.0 - u1) * std::cos(twoPi * u2));
+            config.push_back(std::sqrt(u1) * std::sin(twoPi * u3));
+            for (size_t i = 0; i < nj; ++i) config.push_back((2.0 * u(rng_) - 1.0) * maxJointAngle_);
+        }
+        v_.push_back(config);
+        return true;
+    }
+
+    /** setTransform (:198-213) */
+    void setTransform(const std::vector<Coordinate>& V) {
+        SE3Transform g;
+        g.R = toRotationMatrix({V[3], V[4], V[5], V[6]});
+        g.t = {V[0], V[1], V[2]};
+        robot_.robotTF(kdl_, g, std::vector<double>(V.begin() + 7, V.begin() + 7 + static_cast<long>(kdl_.getNrOfJoints())));
+    }
+
+    /** computeTFE (:216-246) */
+    std::vector<Ellipsoid> computeTFE(const std::vector<Coordinate>& v1, const std::vector<Coordinate>& v2) {
+        const auto vInterp = interpolateCompoundSE3Rn(v1, v2, param_.numPoint);
+        setTransform(v1);
+        auto bodies = robot_.getBodyShapes();
+        std::vector<Ellipsoid> mvce;
+        for (const auto& b : bodies) mvce.push_back({{b.getSemiAxis()[0], b.getSemiAxis()[1], b.getSemiAxis()[2]}, b.getQuaternion()});
+        for (const auto& vStep : vInterp) {
+            setTransform(vStep);
+            bodies = robot_.getBodyShapes();
+            for (size_t i = 0; i < bodies.size(); ++i)
+                mvce[i] = getMVCE3D(mvce[i].semi, {bodies[i].getSemiAxis()[0], bodies[i].getSemiAxis()[1], bodies[i].getSemiAxis()[2]}, mvce[i].quat,
+                                    bodies[i].getQuaternion());
+        }
+        return mvce;
+    }
+
+    /** connectMultiSlice (:105-162): the newest slice against its nearest earlier one; K5 batch + host replay */
+    void connectNearestSlice() {
+        if (param_.numSlice == 1) return;
+        auto& V = res_.graphStructure.vertex;
+        const auto& lim = param_.boundaryLimits;
+        double minDist = INFINITY;
+        size_t minIdx = 0;
+        for (size_t i = 0; i + 1 < param_.numSlice; ++i) {
+            const double dist = vectorEuclidean(v_.at(param_.numSlice - 1), v_.at(i));
+            if (dist < minDist) minDist = dist, minIdx = i;
+        }
+        const Index new0 = vertexIdx_.at(param_.numSlice - 1).first, new1 = vertexIdx_.at(param_.numSlice - 1).second;
+        const Index start = vertexIdx_.at(minIdx).first, n1 = vertexIdx_.at(minIdx).second;
+        const auto tfe = computeTFE(v_.at(param_.numSlice - 1), v_.at(minIdx));
+        if (n1 <= start || new1 <= new0) return;
+        freeSpace_.buildBridge({tfe}, precision_);
+        const double thx = 2.0 * (lim[1] - lim[0]) / static_cast<double>(param_.numLineX);
+        const double thy = 2.0 * (lim[3] - lim[2]) / static_cast<double>(param_.numLineY);
+        const size_t steps = param_.numPoint;
+        std::vector<std::pair<Index, Index>> cand;
+        std::vector<double> centres;
+        for (Index m0 = start; m0 < n1; ++m0)
+            for (Index m1 = new0; m1 < new1; ++m1) {
+                if (std::fabs(V[m0][0] - V[m1][0]) > thx || std::fabs(V[m0][1] - V[m1][1]) > thy) continue;
+                cand.push_back({m0, m1});
+                for (const auto& vs : interpolateCompoundSE3Rn(V[m0], V[m1], steps)) {  // isMultiSliceTransitionFree (HRM3D.cpp:367-392)
+                    setTransform(vs);
+                    for (double v : robot_.getBase().getPosition()) centres.push_back(v);
+                    for (const auto& l : robot_.getLinks())
+                        for (double v : l.getPosition()) centres.push_back(v);
+                }
+            }
+        std::map<std::pair<Index, Index>, bool> freePair;
+        if (!cand.empty()) {
+            const auto ok = freeSpace_.testBridge(0, centres, static_cast<int>(cand.size() * (steps + 1)));
+            for (size_t c = 0; c < cand.size(); ++c) {
+                bool all = true;
+                for (size_t s = 0; s <= steps; ++s) all = all && ok[c * (steps + 1) + s];
+                freePair[cand[c]] = all;
+            }
+        }
+        Index n12 = new0;  // replay with the reference's moving lower bound
+        for (Index m0 = start; m0 < n1; ++m0)
+            for (Index m1 = n12; m1 < new1; ++m1) {
+                const auto it = freePair.find({m0, m1});
+                if (it == freePair.end()) continue;
+                if (it->second) {
+                    addEdge(m0, m1);
+                    n12 = m1;
+                    break;
+                }
+            }
+    }
+
+    std::string urdfFile_;
+    ParseURDF kdl_;
+    MultiBodyTree3D robot0_ = robot_;  // the as-loaded robot
+    std::vector<std::vector<Coordinate>> v_;  // robot shapes, one per slice
+    std::vector<std::vector<double>> samples_;
+    bool injected_ = false;
+    std::mt19937_64 rng_{20220726ULL};
+    size_t batch_ = 8;
+    size_t maxSlices_ = 4096;  // hard stop for the seeded-RNG mode without a time limit
+    double maxJointAngle_ = PI / 2;
+};
+
+}  // namespace planners
+}  // namespace hrm

@@ -98,6 +98,23 @@ class MultiBodyTree3D {
             link_[i].setQuaternion(toQuaternion(R));
         }
     }
+    /** articulated body (:55-89): link i sits at gBase * FK("body<i+1>") * tf_i; Kdl = hrm::ParseURDF (hrm_articulated.hpp) */
+    template <class Kdl>
+    void robotTF(const Kdl& kdl, const SE3Transform& gBase, const std::vector<double>& jointConfig) {
+        base_.setPosition({gBase.t[0], gBase.t[1], gBase.t[2]});
+        base_.setQuaternion(toQuaternion(gBase.R));
+        for (size_t i = 0; i < link_.size(); ++i) {
+            const SE3Transform fk = kdl.getTransform(jointConfig, "body" + std::to_string(i + 1));
+            SE3Transform a;  // gBase * fk
+            a.R = matMul(gBase.R, fk.R);
+            Vec3 v = matVec(gBase.R, fk.t);
+            a.t = {v[0] + gBase.t[0], v[1] + gBase.t[1], v[2] + gBase.t[2]};
+            const Mat3 R = matMul(a.R, tf_[i].R);
+            v = matVec(a.R, tf_[i].t);
+            link_[i].setPosition({v[0] + a.t[0], v[1] + a.t[1], v[2] + a.t[2]});
+            link_[i].setQuaternion(toQuaternion(R));
+        }
+    }
     const SuperQuadrics& getBase() const { return base_; }
     const std::vector<SuperQuadrics>& getLinks() const { return link_; }
     const std::vector<SE3Transform>& getTF() const { return tf_; }
@@ -203,6 +220,25 @@ inline std::vector<std::vector<Coordinate>> interpolateSE3(const std::vector<Coo
         s.insert(s.end(), q[i].begin(), q[i].end());
         out.push_back(s);
     }
+    return out;
+}
+
+inline std::vector<std::vector<Coordinate>> interpolateRn(const std::vector<Coordinate>& v0, const std::vector<Coordinate>& v1, Index numStep) {  // :105-122
+    const double dt = 1.0 / static_cast<double>(numStep);
+    std::vector<std::vector<Coordinate>> out;
+    for (size_t i = 0; i <= numStep; ++i) {
+        std::vector<Coordinate> s;
+        for (size_t j = 0; j < v0.size(); ++j) s.push_back((1.0 - static_cast<double>(i) * dt) * v0[j] + static_cast<double>(i) * dt * v1[j]);
+        out.push_back(s);
+    }
+    return out;
+}
+inline std::vector<std::vector<Coordinate>> interpolateCompoundSE3Rn(const std::vector<Coordinate>& v0, const std::vector<Coordinate>& v1,
+                                                                     Index numStep) {  // :31-65
+    if (v0.size() == 7) return interpolateSE3(v0, v1, numStep);
+    auto out = interpolateSE3(v0, v1, numStep);  // reads the first 7 entries
+    const auto rn = interpolateRn({v0.begin() + 7, v0.end()}, {v1.begin() + 7, v1.end()}, numStep);
+    for (size_t i = 0; i <= numStep; ++i) out[i].insert(out[i].end(), rn[i].begin(), rn[i].end());
     return out;
 }
 
@@ -700,7 +736,10 @@ class HRM3D : public HighwayRoadMapBase {
             std::vector<Index> plane;
             for (int iy = 0; iy < Ly; ++iy) {  // generateVertices
                 plane.push_back(V.size());
-                for (int j = 0; j < segN(ix, iy); ++j) V.push_back({tx[ix], ty[iy], xM[seg0(ix, iy) + j], q[0], q[1], q[2], q[3]});
+                for (int j = 0; j < segN(ix, iy); ++j) {
+                    V.push_back({tx[ix], ty[iy], xM[seg0(ix, iy) + j], q[0], q[1], q[2], q[3]});
+                    V.back().insert(V.back().end(), vertexTail_.begin(), vertexTail_.end());  // joint angles (ProbHRM3D.cpp:185-188)
+                }
             }
             lineIds.push_back(plane);
             // connectOneSlice2D (HighwayRoadMap-inl.h:218-261); its pair order is the enumeration order above restricted to plane ix
@@ -845,6 +884,7 @@ class HRM3D : public HighwayRoadMapBase {
     MultiBodyTree3D robot_;
     FreeSpaceGPU3D freeSpace_;
     std::vector<Quaternion> q_;
+    std::vector<Coordinate> vertexTail_;  // appended to every vertex of the slice under construction (empty for rigid bodies)
 };
 
 /** src/planners/HRM2D.cpp */

@@ -2,6 +2,7 @@
 // caller — can run the GPU-backed planners.  Argument layout mirrors the reference's scene files after
 // parsePlanningConfig: superquadric rows [a,b,c,e1,e2,px,py,pz,qw,qx,qy,qz], superellipse rows [a,b,eps,px,py,angle],
 // robot rows = base first, links relative to the base (resources/readme.md).
+#include "hrm_articulated.hpp"
 #include "hrm_io.hpp"
 
 #include <cstring>
@@ -210,6 +211,63 @@ int hrmhost_store_result(const char* details_dir, const char* suffix, int vdim, 
         }
         storeGraphInfo(g, suffix, p);
         storePathInfo(sp, suffix, p);
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+// ---- articulated robots (hrm_articulated.hpp) ---------------------------------------------------------------------------
+// hrm::ParseURDF::getTransform(jointConfig, "body<k>") (body 0 = root link): out16 row-major 4x4; returns the joint count.
+int hrmhost_fk(const char* urdf, const double* joints, int nj, int body, double* out16) {
+    try {
+        ParseURDF kdl(urdf);
+        const SE3Transform f = kdl.getTransform(std::vector<double>(joints, joints + nj), body == 0 ? kdl.getRootName() : "body" + std::to_string(body));
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j) out16[4 * i + j] = f.R[i][j];
+            out16[4 * i + 3] = f.t[i];
+        }
+        out16[12] = out16[13] = out16[14] = 0.0, out16[15] = 1.0;
+        return static_cast<int>(kdl.getNrOfJoints());
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+// hrm::planners::ProbHRM3D(robot, urdf, arena, obs, req).plan().  samples [n_samples][4 + nj] replace the random draws
+// (n_samples < 0: seeded RNG, `seed`); start/goal 7 + nj doubles; vertex stride 7 + nj; info[4] = C-slices built.
+int hrmhost_plan_prob3d(int n_arena, int n_obs, const double* sq, int n, int B, const double* robot, const char* urdf, int nj, int n_samples,
+                        const double* samples, unsigned long long seed, int batch, const double* lim, int Lx, int Ly, int numPoint,
+                        const double* start, const double* goal, int per_orientation, int precision, int device, double time_limit, long* info,
+                        double* vertex, long cap_v, long* edge, long cap_e, long* path, long cap_p) {
+    try {
+        std::vector<SuperQuadrics> arena, obs;
+        for (int i = 0; i < n_arena; ++i) arena.push_back(sqFromRow(sq + 12 * i, n));
+        for (int i = 0; i < n_obs; ++i) obs.push_back(sqFromRow(sq + 12 * (n_arena + i), n));
+        MultiBodyTree3D rb(sqFromRow(robot, n));
+        for (int b = 1; b < B; ++b) rb.addBody(sqFromRow(robot + 12 * b, n));
+        PlanningRequest req;
+        req.isRobotRigid = false;
+        req.parameters.boundaryLimits.assign(lim, lim + 6);
+        req.parameters.numLineX = static_cast<Index>(Lx);
+        req.parameters.numLineY = static_cast<Index>(Ly);
+        req.parameters.numPoint = static_cast<Index>(numPoint);
+        req.start.assign(start, start + 7 + nj);
+        req.goal.assign(goal, goal + 7 + nj);
+        planners::ProbHRM3D hrm(rb, urdf, arena, obs, req, device, precision, per_orientation != 0);
+        if (n_samples >= 0) {
+            std::vector<std::vector<double>> draws;
+            for (int i = 0; i < n_samples; ++i) draws.emplace_back(samples + static_cast<size_t>(i) * (4 + nj), samples + static_cast<size_t>(i + 1) * (4 + nj));
+            hrm.setSampleList(draws);
+        } else {
+            hrm.setSeed(seed);
+        }
+        hrm.setBatch(static_cast<size_t>(batch));
+        hrm.plan(time_limit);
+        exportResult(hrm, info, vertex, cap_v, 7 + nj, edge, cap_e, path, cap_p);
+        info[4] = static_cast<long>(hrm.numSlices());
         return 0;
     } catch (const std::exception& e) {
         g_err = e.what();

@@ -116,3 +116,40 @@ def store_result(details_dir, suffix, vertex, edge, path):
                                      C.c_long(edge.shape[0]), _p(edge), C.c_long(path.shape[0]), _p(path))
     if rc != 0:
         raise _err()
+
+
+# ---- articulated robots (hrm_b200/host/hrm_articulated.hpp) -------------------------------------------------------------
+def fk(urdf, joints, body):
+    """hrm::ParseURDF::getTransform(jointConfig, "body<k>") -> (4x4, number of joints)."""
+    joints = _d(joints)
+    out = np.zeros(16)
+    nj = load().hrmhost_fk(str(urdf).encode(), _p(joints), C.c_int(joints.shape[0]), C.c_int(body), _p(out))
+    if nj < 0:
+        raise _err()
+    return out.reshape(4, 4), nj
+
+
+def plan_prob3d(n_arena, n_obs, sq12, n, robot_rows, urdf, samples, lim, Lx, Ly, num_point, start, goal, per_orientation=False, precision=0,
+                device=0, batch=8, seed=20220726, time_limit=0.0, nj=None, cap_v=1 << 18, cap_e=1 << 21):
+    """hrm::planners::ProbHRM3D(robot, urdf, arena, obstacle, request).plan(); `samples` [N][4 + nj] replace the random draws
+    (None: seeded RNG, then `nj` is required)."""
+    sq12, robot_rows, lim = _d(sq12), _d(robot_rows), _d(lim)
+    if samples is not None:
+        samples = _d(samples)
+        nj = samples.shape[1] - 4
+        ns = samples.shape[0]
+    else:
+        samples, ns = np.zeros((1, 4 + nj)), -1
+    start, goal = _d(start)[: 7 + nj].copy(), _d(goal)[: 7 + nj].copy()
+    info = np.zeros(8, dtype=np.int64)
+    vertex, edge, path = np.zeros((cap_v, 7 + nj)), np.zeros((cap_e, 2), dtype=np.int64), np.zeros(cap_v, dtype=np.int64)
+    rc = load().hrmhost_plan_prob3d(C.c_int(n_arena), C.c_int(n_obs), _p(sq12), C.c_int(n), C.c_int(robot_rows.shape[0]), _p(robot_rows),
+                                    str(urdf).encode(), C.c_int(nj), C.c_int(ns), _p(samples), C.c_ulonglong(seed), C.c_int(batch), _p(lim),
+                                    C.c_int(Lx), C.c_int(Ly), C.c_int(num_point), _p(start), _p(goal), C.c_int(int(per_orientation)),
+                                    C.c_int(precision), C.c_int(device), C.c_double(time_limit), _p(info), _p(vertex), C.c_long(cap_v),
+                                    _p(edge), C.c_long(cap_e), _p(path), C.c_long(cap_v))
+    if rc != 0:
+        raise _err()
+    out = _out(info, vertex, edge, path)
+    out["slices"] = int(info[4])
+    return out

@@ -139,3 +139,46 @@ def test_cpp_host_hrm2d_roadmap_identical(oracle, name, Ly, per_orientation):
     assert np.array_equal(got["vertex"], ref["vertex"])
     assert np.array_equal(got["edge"], ref["edge"])
     assert got["solved"] == ref["solved"]
+
+
+# ---- ProbHRM3D: articulated robot, batched C-layers, injected draws (hrm_b200/host/hrm_articulated.hpp) ---------------------
+def _prob_case(oracle, name, per_orientation, n_samples, batch):
+    import os
+
+    from hrm_b200 import hostlib
+    from tests.test_oracle_kat import GOLDEN, prob_samples
+
+    sc = util.scenes()[name]
+    rows = np.array(sc["arena"] + sc["obstacle"])
+    urdf = os.path.join(GOLDEN, "snake.urdf")
+    draws = prob_samples(n_samples, 3)
+    args = (len(sc["arena"]), len(sc["obstacle"]), rows, 10, np.array(sc["robot"]), urdf, draws, sc["lim"], sc["Lx"], sc["Ly"], 5,
+            sc["end_points"][0], sc["end_points"][1])
+    ref = oracle.plan_prob3d(*args, per_orientation=per_orientation)
+    got = hostlib.plan_prob3d(*args, per_orientation=per_orientation, precision=capi.F64_STRICT, batch=batch)
+    return ref, got
+
+
+@pytest.mark.parametrize("name,per_orientation,batch", [("3D_superquadrics_sparse_snake", False, 8), ("3D_superquadrics_cluttered_snake", True, 4),
+                                                        ("3D_superquadrics_home_snake", True, 8), ("3D_superquadrics_home_snake", True, 3)])
+def test_prob_hrm3d_roadmap_identical(oracle, name, per_orientation, batch):
+    """Same draws -> the GPU-backed ProbHRM3D (layers built `batch` slices ahead) must reproduce the oracle's sequential
+    planner: slice count, vertex list (with joint angles), edge list, solved, path."""
+    ref, got = _prob_case(oracle, name, per_orientation, 30, batch)
+    assert got["slices"] == ref["slices"]
+    assert got["vertex"].shape == ref["vertex"].shape
+    assert np.array_equal(got["vertex"], ref["vertex"])
+    assert np.array_equal(got["edge"], ref["edge"])
+    assert got["solved"] == ref["solved"]
+    assert np.array_equal(got["path"], ref["path"])
+    assert got["gpu_launches"] > 0
+    if name.endswith("home_snake"):
+        assert ref["slices"] > 2  # several random slices and nearest-slice bridges were needed
+
+
+def test_prob_hrm3d_stops_when_draws_run_out(oracle):
+    """Too few draws to solve the per-orientation home map: both planners stop unsolved after the same number of slices."""
+    ref, got = _prob_case(oracle, "3D_superquadrics_home_snake", True, 3, 8)
+    assert not ref["solved"] and not got["solved"]
+    assert got["slices"] == ref["slices"] == 5
+    assert np.array_equal(got["vertex"], ref["vertex"]) and np.array_equal(got["edge"], ref["edge"])
