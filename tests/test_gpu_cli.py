@@ -33,14 +33,14 @@ def _write(path, rows):
 
 
 def make_resources(sc, root, env="t", robot="r"):
-    os.makedirs(root / "3D"), os.makedirs(root / "SO3_sequence")
+    os.makedirs(root / "3D" / "urdf"), os.makedirs(root / "SO3_sequence")
     _write(root / "3D" / f"env_superquadrics_{env}_3D_arena.csv", [_angle_axis_row(r) for r in sc["arena"]])
     _write(root / "3D" / f"env_superquadrics_{env}_3D_obstacle.csv", [_angle_axis_row(r) for r in sc["obstacle"]])
     _write(root / "3D" / f"robot_{robot}_3D.csv", [_angle_axis_row(r) for r in sc["robot"]])
     ends = []
     for e in sc["end_points"]:
         aa = _angle_axis_row([0] * 8 + list(e[3:7]))
-        ends.append(list(e[:3]) + aa[8:12])
+        ends.append(list(e[:3]) + aa[8:12] + list(e[7:]))  # joint angles of articulated robots follow the base pose
     _write(root / "3D" / f"setting_superquadrics_{env}_3D.csv", ends)
     _write(root / "SO3_sequence" / f"q_icosahedron_{len(sc['quats'])}.csv", [[q[1], q[2], q[3], q[0]] for q in sc["quats"]])
 
@@ -84,3 +84,29 @@ def test_bench_hrm3d_cli(oracle, name, tmp_path):
     bound = (out / "details" / "mink_bound_hrm_3D.csv").read_text().rstrip("\n").split("\n")
     assert len(bound) == 3 * (len(got["arena"]) + len(got["obstacle"])) * len(got["robot"])
     assert all(len(l.split()) == 100 for l in bound)
+
+
+def test_bench_prob_hrm3d_cli(tmp_path):
+    """BenchProbHRM3D on the home map with the snake robot: resources -> config (robot type "snake" keeps 3 joint angles in
+    the end points) -> URDF FK -> batched C-layers -> solved, with the reference's CSV columns."""
+    import shutil
+
+    sc = util.scenes()["3D_superquadrics_home_snake"]
+    res, cfg, out = tmp_path / "resources", tmp_path / "config", tmp_path / "result"
+    make_resources(sc, res, env="home", robot="snake")
+    shutil.copy(os.path.join(ROOT, "tests", "golden", "snake.urdf"), res / "3D" / "urdf" / "snake.urdf")
+    os.makedirs(cfg), os.makedirs(out / "details"), os.makedirs(out / "benchmark")
+    env = dict(os.environ, HRM_RESOURCES_PATH=str(res), HRM_CONFIG_PATH=str(cfg), HRM_RESULT_PATH=str(out), HRM_PER_ORIENTATION="1",
+               HRM_SEED="5")
+    exe = os.path.join(ROOT, "hrm_b200", "lib", "BenchProbHRM3D")
+    p = subprocess.run([exe, "home", "snake", "2", "120"], env=env, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "Final number of C-slices:" in p.stdout
+    ends = (cfg / "end_points_3D.csv").read_text().strip().split("\n")
+    assert all(len(l.split(",")) == 10 for l in ends)  # x,y,z, quaternion, 3 joints (parseStartGoalConfig, robotType == "snake")
+    stats = (out / "benchmark" / "time_prob_high_3D.csv").read_text().strip().split("\n")
+    assert stats[0] == "SUCCESS,PLAN_TIME,N_LAYERS,N_X,N_Y,GRAPH_NODE,GRAPH_EDGE,PATH_NODE"
+    assert len(stats) == 3
+    for line in stats[1:]:
+        c = line.split(",")
+        assert int(c[0]) == 1 and int(c[2]) >= 1 and int(c[5]) > 0 and int(c[6]) > 0 and int(c[7]) >= 2
