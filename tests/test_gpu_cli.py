@@ -110,3 +110,31 @@ def test_bench_prob_hrm3d_cli(tmp_path):
     for line in stats[1:]:
         c = line.split(",")
         assert int(c[0]) == 1 and int(c[2]) >= 1 and int(c[5]) > 0 and int(c[6]) > 0 and int(c[7]) >= 2
+
+
+def test_bench_hrm2d_cli(oracle, tmp_path):
+    """BenchHRM2D (README example: sparse rabbit, 20 slices, 30 sweep lines): same roadmap size as the oracle planning on the
+    numbers the CLI parsed; 2D resource rows are already in their final form (a,b,eps,x,y,angle)."""
+    from hrm_b200 import hostlib
+
+    sc = util.scenes()["2D_superellipse_sparse_rabbit"]
+    res, cfg, out = tmp_path / "resources", tmp_path / "config", tmp_path / "result"
+    os.makedirs(res / "2D"), os.makedirs(cfg), os.makedirs(out / "details"), os.makedirs(out / "benchmark")
+    _write(res / "2D" / "env_superellipse_t_2D_arena.csv", sc["arena"])
+    _write(res / "2D" / "env_superellipse_t_2D_obstacle.csv", sc["obstacle"])
+    _write(res / "2D" / "robot_r_2D.csv", sc["robot"])
+    _write(res / "2D" / "setting_superellipse_t_2D.csv", sc["end_points"])
+    env = dict(os.environ, HRM_RESOURCES_PATH=str(res), HRM_CONFIG_PATH=str(cfg), HRM_RESULT_PATH=str(out))
+    exe = os.path.join(ROOT, "hrm_b200", "lib", "BenchHRM2D")
+    p = subprocess.run([exe, "t", "r", "2", "20", "30"], env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
+    got = hostlib.load_scene("2D", str(cfg) + "/", num_param=50, num_line_y=30)
+    rows = np.vstack([got["arena"], got["obstacle"]])
+    ref = oracle.plan2d(len(got["arena"]), len(got["obstacle"]), rows, 50, got["robot"], 20, got["lim"], 30, 5, got["end_points"][0][:3],
+                        got["end_points"][1][:3], per_orientation=False)
+    stats = (out / "benchmark" / "time_hrm_2D.csv").read_text().strip().split("\n")
+    assert stats[0] == "BUILD_TIME,SEARCH_TIME,PLAN_TIME,GRAPH_NODE,GRAPH_EDGE,PATH_NODE" and len(stats) == 3
+    for line in stats[1:]:
+        c = line.split(",")
+        assert int(c[3]) == len(ref["vertex"]) and int(c[4]) == len(ref["edge"]) and int(c[5]) == len(ref["path"])
+    assert ref["solved"] and "Number of configurations in Path:" in p.stdout
