@@ -51,6 +51,9 @@ struct MinkParams {
     int Lx, Ly, L;
     int lpc, groups;                        // thread mapping
     int paired;                             // phase A handles rows in adjacent pairs (n even, lpc divides n/2)
+    // byte offsets of the shared-memory regions (host-computed, see smem_layout): read from the constant bank instead of
+    // being re-derived from n, Lx, Ly wherever the compiler rematerialises a pointer
+    int o_mats, o_cc, o_txs, o_tys, o_zq, o_queue, o_vcode, o_zc0, o_zc1, o_m0, o_m1, o_qcount;
     double inv_dx, bias_x, inv_dy, bias_y;  // line-index guess g = x*inv_d + bias
     double bias_xq, bias_yq;                // bias + 1.5 * 2^36 + (1 - 2^-16): Q15.16 conversion and ceil folded into the FMA
     double zlow, zup;
@@ -180,31 +183,22 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
     int rounds = 0;
     if (p.dbg) t_start = clock64();
     // ---- shared memory carve-up (every region 16-byte aligned) ------------------------------
-    Real* tab = reinterpret_cast<Real*>(smem_raw);                       // [8][n]
-    size_t ofs = (sizeof(Real) * 8 * n + 15) & ~size_t(15);
-    double* mats = reinterpret_cast<double*>(smem_raw + ofs);            // M1[9] M2[9] + scratch T[9] KTT[9]
-    ofs += sizeof(double) * 36;
-    Real* cc = reinterpret_cast<Real*>(smem_raw + ofs);                  // [n][kColStride] per-column constants (fast modes)
-    ofs += (MODE != HRMGPU_F64_STRICT) ? ((sizeof(Real) * kColStride * n + 15) & ~size_t(15)) : 0;
-    double* txs = reinterpret_cast<double*>(smem_raw + ofs);             // [Lx+2]
-    double* tys = txs + (SWEEP ? p.Lx + 2 : 0);                           // [Ly+2]
-    ofs += SWEEP ? ((sizeof(double) * (p.Lx + p.Ly + 4) + 15) & ~size_t(15)) : 0;
-    double* zq = reinterpret_cast<double*>(smem_raw + ofs);              // [kQueueCap] z of queued hits
-    ofs += SWEEP ? sizeof(double) * kQueueCap : 0;
-    uint2* queue = reinterpret_cast<uint2*>(smem_raw + ofs);             // [kQueueCap] (face, ix | iy << 16)
-    ofs += SWEEP ? sizeof(uint2) * kQueueCap : 0;
-    Code* vcode = reinterpret_cast<Code*>(smem_raw + ofs);               // [M]
-    ofs += SWEEP ? ((sizeof(Code) * (M + 8) + 15) & ~size_t(15)) : 0;    // +8: the 5th code of the last unit
+    Real* tab = reinterpret_cast<Real*>(smem_raw);                             // [8][n]
+    double* mats = reinterpret_cast<double*>(smem_raw + p.o_mats);             // M1[9] M2[9] + scratch T[9] KTT[9]
+    Real* cc = reinterpret_cast<Real*>(smem_raw + p.o_cc);                     // [n][kColStride] per-column constants (fast modes)
+    double* txs = reinterpret_cast<double*>(smem_raw + p.o_txs);               // [Lx+2]
+    double* tys = reinterpret_cast<double*>(smem_raw + p.o_tys);               // [Ly+2]
+    double* zq = reinterpret_cast<double*>(smem_raw + p.o_zq);                 // [kQueueCap] z of queued hits
+    uint2* queue = reinterpret_cast<uint2*>(smem_raw + p.o_queue);             // [kQueueCap] (face, ix | iy << 16)
+    Code* vcode = reinterpret_cast<Code*>(smem_raw + p.o_vcode);               // [M + 8]: the 5th code of the last unit
     auto pack_code = [](uint32_t cx, uint32_t cy) -> Code { return static_cast<Code>(CODE8 ? (cx | (cy << 8)) : (cx | (cy << 16))); };
     // expanded form used by the SIMD min/max tests: x code in bits 0..15, y code in bits 16..31
     auto code_at = [&](int q) -> uint32_t { return CODE8 ? __byte_perm(static_cast<uint32_t>(vcode[q]), 0u, 0x4140) : static_cast<uint32_t>(vcode[q]); };
-    double* zc0 = reinterpret_cast<double*>(smem_raw + ofs);             // [L] committed z of the two lowest hit faces
-    double* zc1 = zc0 + (SWEEP ? p.L : 0);                                // [L]
-    ofs += SWEEP ? sizeof(double) * 2 * p.L : 0;
-    uint32_t* m0 = reinterpret_cast<uint32_t*>(smem_raw + ofs);          // [L]
-    uint32_t* m1 = m0 + (SWEEP ? p.L : 0);                                // [L]
-    ofs += SWEEP ? ((sizeof(uint32_t) * 2 * p.L + 15) & ~size_t(15)) : 0;
-    int* qcount = reinterpret_cast<int*>(smem_raw + ofs);  // [0] queue fill, [1] next scan batch
+    double* zc0 = reinterpret_cast<double*>(smem_raw + p.o_zc0);               // [L] committed z of the two lowest hit faces
+    double* zc1 = reinterpret_cast<double*>(smem_raw + p.o_zc1);               // [L]
+    uint32_t* m0 = reinterpret_cast<uint32_t*>(smem_raw + p.o_m0);             // [L]
+    uint32_t* m1 = reinterpret_cast<uint32_t*>(smem_raw + p.o_m1);             // [L]
+    int* qcount = reinterpret_cast<int*>(smem_raw + p.o_qcount);               // [0] queue fill, [1] next scan batch
     int* batch_ctr = qcount + 1;
 
     // ---- prologue: tables, line coordinates, per-surface matrices -------------------------
@@ -848,18 +842,23 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
     }
 }
 
-static size_t smem_bytes(int MODE, bool sweep, bool code8, int n, int Lx, int Ly) {
+// Shared-memory layout of k_minksweep3d (every region 16-byte aligned); fills the offsets of `p` and returns the total.
+static size_t smem_layout(MinkParams& p, int MODE, bool sweep, bool code8, int n, int Lx, int Ly) {
     const size_t real = (MODE == HRMGPU_F32) ? 4 : 8;
-    size_t b = (real * 8 * n + 15) & ~size_t(15);
-    b += sizeof(double) * 36;
-    if (MODE != HRMGPU_F64_STRICT) b += (real * kColStride * n + 15) & ~size_t(15);
-    if (sweep) {
-        b += (sizeof(double) * (Lx + Ly + 4) + 15) & ~size_t(15);
-        b += sizeof(double) * kQueueCap + sizeof(uint2) * kQueueCap;
-        b += ((code8 ? 2 : 4) * (static_cast<size_t>(n) * n + 8) + 15) & ~size_t(15);
-        b += sizeof(double) * 2 * static_cast<size_t>(Lx) * Ly;
-        b += (sizeof(uint32_t) * 2 * static_cast<size_t>(Lx) * Ly + 15) & ~size_t(15);
-    }
+    auto al = [](size_t v) { return (v + 15) & ~size_t(15); };
+    size_t b = al(real * 8 * n);  // tab
+    p.o_mats = static_cast<int>(b), b += sizeof(double) * 36;
+    p.o_cc = static_cast<int>(b);
+    if (MODE != HRMGPU_F64_STRICT) b += al(real * kColStride * n);
+    p.o_txs = static_cast<int>(b), p.o_tys = static_cast<int>(b + (sweep ? sizeof(double) * (Lx + 2) : 0));
+    if (sweep) b += al(sizeof(double) * (Lx + Ly + 4));
+    p.o_zq = static_cast<int>(b), b += sweep ? sizeof(double) * kQueueCap : 0;
+    p.o_queue = static_cast<int>(b), b += sweep ? sizeof(uint2) * kQueueCap : 0;
+    p.o_vcode = static_cast<int>(b), b += sweep ? al((code8 ? 2 : 4) * (static_cast<size_t>(n) * n + 8)) : 0;
+    const size_t L = static_cast<size_t>(Lx) * Ly;
+    p.o_zc0 = static_cast<int>(b), p.o_zc1 = static_cast<int>(b + (sweep ? sizeof(double) * L : 0)), b += sweep ? sizeof(double) * 2 * L : 0;
+    p.o_m0 = static_cast<int>(b), p.o_m1 = static_cast<int>(b + (sweep ? sizeof(uint32_t) * L : 0)), b += sweep ? al(sizeof(uint32_t) * 2 * L) : 0;
+    p.o_qcount = static_cast<int>(b);
     return b + 16;
 }
 
@@ -938,7 +937,7 @@ int launch_minksweep3d(Ctx* c, int K, int B, int n_first_obj, int n_objs, const 
     if (grid > 0x7FFFFFFFLL) return fail(c, HRMGPU_E_CAP, "K*S exceeds the CUDA grid limit");
     // 2 x 8-bit vertex line codes when both axes have at most 127 lines (code = 2*lo + eq <= 255), else 2 x 16-bit
     const bool code8 = do_sweep && c->Lx <= 127 && c->Ly <= 127;
-    const size_t smem = smem_bytes(precision, do_sweep, code8, c->n, c->Lx, c->Ly);
+    const size_t smem = smem_layout(p, precision, do_sweep, code8, c->n, c->Lx, c->Ly);
     if (smem > 227 * 1024) return fail(c, HRMGPU_E_CAP, "n_grid / sweep-line count need more than 227 KB of shared memory");
     const int g = static_cast<int>(grid);
 #define HRMGPU_LAUNCH3D(M_)                                                                      \
