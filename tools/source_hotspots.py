@@ -48,10 +48,10 @@ for k in keys:
 
 # phase roll-up for hrm_b200/csrc/mink3d.cu (+ device helpers): edit the ranges when the kernel moves
 if len(sys.argv) > 3 and sys.argv[3] == "phases":
-    ranges = [("line-code helpers (phase A)", "mink3d.cu", 1, 142), ("entry + smem carve-up", "mink3d.cu", 143, 208),
-              ("prologue", "mink3d.cu", 209, 320), ("phase A", "mink3d.cu", 321, 559), ("face load/test lambdas (drain)", "mink3d.cu", 560, 586),
-              ("scan B1 (face tests)", "mink3d.cu", 587, 639), ("scan B2 (expansion + queue)", "mink3d.cu", 640, 759),
-              ("drain", "mink3d.cu", 760, 779), ("commit", "mink3d.cu", 780, 805), ("phase D", "mink3d.cu", 806, 900),
+    ranges = [("line-code helpers (phase A)", "mink3d.cu", 1, 146), ("entry + smem carve-up", "mink3d.cu", 147, 203),
+              ("prologue", "mink3d.cu", 204, 315), ("phase A", "mink3d.cu", 316, 560), ("face load/test lambdas (drain)", "mink3d.cu", 561, 587),
+              ("scan B1 (face tests)", "mink3d.cu", 588, 641), ("scan B2 (expansion + queue)", "mink3d.cu", 642, 761),
+              ("drain", "mink3d.cu", 762, 781), ("commit", "mink3d.cu", 782, 807), ("phase D", "mink3d.cu", 808, 900),
               ("rsqrt (phase A)", "devmath.cuh", 30, 50), ("triangle test (drain)", "devmath.cuh", 51, 129),
               ("face_vertices / insert (drain)", "devmath.cuh", 130, 200)]
     print("\nphase roll-up: share of warp instructions / of stall samples, top stall reasons")
