@@ -80,6 +80,42 @@ __device__ __forceinline__ void warp_bitonic(double* key, double* val, int n, in
     }
 }
 
+// Ascending sort of m <= 32 * SLOTS (start, end) pairs by start: every lane keeps its pairs in registers, counts for each
+// of them the pairs that precede it (smaller start, or equal start and smaller position: a permutation) while the starts
+// are broadcast from shared memory, then scatters its pairs to their ranks in place.  No dependent shared-memory passes
+// and no barriers inside the counting loop, unlike the bitonic network (28 passes for 128 pairs); used for the short lists
+// of k_line_segments4.  The order among equal starts does not affect the gaps (an interval's end is never below its
+// start, so the second of two equal starts never opens a gap).
+template <int SLOTS>
+__device__ __forceinline__ void warp_rank_sort(double* ks, double* ke, int m, int lane) {
+    double k[SLOTS], v[SLOTS];
+    int r[SLOTS];
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+        const int i = lane + 32 * s;
+        k[s] = i < m ? ks[i] : DBL_MAX;
+        v[s] = i < m ? ke[i] : 0.0;
+        r[s] = 0;
+    }
+    for (int j = 0; j < m; ++j) {
+        const double kj = ks[j];  // same address in all lanes: one broadcast
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) r[s] += (kj < k[s] || (kj == k[s] && j < lane + 32 * s)) ? 1 : 0;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s)
+        if (lane + 32 * s < m) ks[r[s]] = k[s], ke[r[s]] = v[s];
+    __syncwarp();
+}
+__device__ __forceinline__ void warp_sort_pairs(double* ks, double* ke, int m, int lane) {
+    if (m <= 32) warp_rank_sort<1>(ks, ke, m, lane);
+    else if (m <= 64) warp_rank_sort<2>(ks, ke, m, lane);
+    else if (m <= 128) warp_rank_sort<4>(ks, ke, m, lane);
+    else if (m <= 256) warp_rank_sort<8>(ks, ke, m, lane);
+    else warp_bitonic<true>(ks, ke, m, lane);
+}
+
 // Original free segments of one line from its m compacted C-obstacle intervals (ks = starts, ke = ends, in shared
 // memory) and its arena interval [as, ae]: sort by start, gaps of the union clipped to the arena, count to orig_cnt.
 __device__ __forceinline__ void emit_line(const SegParams& p, long long gl, double* ks, double* ke, int m, double as, double ae,
@@ -92,7 +128,7 @@ __device__ __forceinline__ void emit_line(const SegParams& p, long long gl, doub
         if (lane == 0) out[0] = as, out[1] = ae;  // complements(): empty inner -> outer
         cnt = 1;
     } else {
-        warp_bitonic<true>(ks, ke, m, lane);
+        warp_sort_pairs(ks, ke, m, lane);
         // gaps of the union: before interval i iff (running max of earlier ends) < start_i   (Interval.cpp:21-29)
         double carry = -DBL_MAX;  // running max of ends of intervals [0, base)
         for (int base = 0; base < m + 1; base += 32) {
