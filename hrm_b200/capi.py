@@ -42,6 +42,7 @@ def load():
         "hrmgpu_set_scene3d": (i, [vp, i, i, vp, i]),
         "hrmgpu_set_scene2d": (i, [vp, i, i, vp, i]),
         "hrmgpu_set_sweep": (i, [vp, vp, i, i]),
+        "hrmgpu_resweep": (i, [vp, vp, i, i]),
         "hrmgpu_build_layers": (i, [vp, i, i, vp, vp, vp, i]),
         "hrmgpu_build_layers_dev": (i, [vp, i, i, vp, vp, vp, i]),
         "hrmgpu_build_layers2d": (i, [vp, i, i, vp, vp, vp, i]),
@@ -132,6 +133,11 @@ class Context:
     def set_sweep(self, lim, Lx, Ly):
         lim = _d(lim)
         self._chk(self.lib.hrmgpu_set_sweep(self.h, _p(lim), Lx, Ly))
+
+    def resweep(self, lim, Lx, Ly):
+        """hrmgpu_resweep: redo sweep + free segments of all built layers on their cached boundaries for a new grid."""
+        lim = _d(lim)
+        self._chk(self.lib.hrmgpu_resweep(self.h, _p(lim), Lx, Ly))
 
     # ---- builds ----
     def build_layers(self, body_semi, body_R, body_off, precision=F64_STRICT):

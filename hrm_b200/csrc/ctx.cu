@@ -213,19 +213,20 @@ int hrmgpu_set_scene3d(hrmgpu_ctx* c, int n_arena, int n_obs, const double* sq, 
     return HRMGPU_OK;
 }
 
-int hrmgpu_set_sweep(hrmgpu_ctx* c, const double* lim, int Lx, int Ly) {
-    if (!c) return HRMGPU_E_ARG;
-    if (!lim) return fail(c, HRMGPU_E_ARG, "set_sweep: lim is NULL");
-    if (c->dim == 0) return fail(c, HRMGPU_E_STATE, "set_sweep: set a scene first");
+// Sweep-line grids of HRM3D::sweepLineProcess / HRM2D::sweepLineProcess for the current scene (shared by set_sweep and resweep)
+static int set_grid(hrmgpu_ctx* c, const double* lim, int Lx, int Ly, const char* who) {
+    if (!lim) return fail(c, HRMGPU_E_ARG, "sweep grid: lim is NULL");
+    if (c->dim == 0) return fail(c, HRMGPU_E_STATE, "sweep grid: set a scene first");
     HRMGPU_CUDA(c, cudaSetDevice(c->device));
     if (c->dim == 3) {
-        if (Lx < 2 || Ly < 2) return fail(c, HRMGPU_E_ARG, "set_sweep: 3D needs Lx >= 2 and Ly >= 2");
+        if (Lx < 2 || Ly < 2) return fail(c, HRMGPU_E_ARG, "sweep grid: 3D needs Lx >= 2 and Ly >= 2");
     } else {
         Lx = 1;
-        if (Ly < 1) return fail(c, HRMGPU_E_ARG, "set_sweep: Ly must be >= 1");
+        if (Ly < 1) return fail(c, HRMGPU_E_ARG, "sweep grid: Ly must be >= 1");
     }
     if (Lx > kMaxLinesAxis || Ly > kMaxLinesAxis || static_cast<long long>(Lx) * Ly > kMaxLines)
-        return fail(c, HRMGPU_E_CAP, "set_sweep: at most 16383 lines per axis and 8192 lines per layer");
+        return fail(c, HRMGPU_E_CAP, "sweep grid: at most 16383 lines per axis and 8192 lines per layer");
+    (void)who;
     const int nl = (c->dim == 3) ? 6 : 4;
     for (int i = 0; i < nl; ++i) c->lim[i] = lim[i];
     if (c->dim == 2) c->lim[4] = c->lim[5] = 0.0;
@@ -247,7 +248,42 @@ int hrmgpu_set_sweep(hrmgpu_ctx* c, const double* lim, int Lx, int Ly) {
     if ((rc = upload(c, c->tys, ty.data(), ty.size()))) return rc;
     HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));
     c->sweep_set = true;
+    return HRMGPU_OK;
+}
+
+int hrmgpu_set_sweep(hrmgpu_ctx* c, const double* lim, int Lx, int Ly) {
+    if (!c) return HRMGPU_E_ARG;
+    const int rc = set_grid(c, lim, Lx, Ly, "set_sweep");
+    if (rc == HRMGPU_OK) c->built = false;
+    return rc;
+}
+
+// Refinement path (HighwayRoadMap-inl.h:178-215, HRM3D.cpp:24-54 with isRefine_): the C-boundaries of the last build stay in
+// HBM (the reference caches them in sliceBoundAll_ / sliceBoundMeshAll_) and only the sweep (K2) and the free segments (K3)
+// are redone for a new grid.  Interval tables are sized by the new line count (the reference's are not: SURVEY finding 6).
+int hrmgpu_resweep(hrmgpu_ctx* c, const double* lim, int Lx, int Ly) {
+    if (!c) return HRMGPU_E_ARG;
+    if (!c->built) return fail(c, HRMGPU_E_STATE, "resweep: no layers built");
+    int rc = set_grid(c, lim, Lx, Ly, "resweep");
+    if (rc) {
+        return rc;
+    }
     c->built = false;
+    const int S0 = c->n_arena + c->n_obs;
+    c->L = c->Lx * c->Ly;
+    if ((rc = ensure(c, c->ivl_lo, static_cast<size_t>(c->K) * c->S * c->L))) return rc;
+    if ((rc = ensure(c, c->ivl_up, static_cast<size_t>(c->K) * c->S * c->L))) return rc;
+    HRMGPU_CUDA(c, cudaMemsetAsync(c->counters.p, 0, 4 * sizeof(unsigned long long), c->stream));
+    HRMGPU_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    if (c->dim == 3)
+        rc = launch_minksweep3d(c, c->K, c->B, 0, S0, nullptr, nullptr, nullptr, c->prec, c->mesh.p, c->ivl_lo.p, c->ivl_up.p, true, true);
+    else
+        rc = launch_minksweep2d(c, c->K, c->B, 0, S0, c->body_semi.p, c->body_R.p, c->body_off.p, c->prec, c->mesh.p, c->ivl_lo.p, c->ivl_up.p,
+                                true, true);
+    if (rc) return rc;
+    HRMGPU_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    if ((rc = launch_segments(c))) return rc;
+    c->built = true;
     return HRMGPU_OK;
 }
 

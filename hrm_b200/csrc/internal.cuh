@@ -120,9 +120,9 @@ inline int fail(Ctx* c, int code, const std::string& msg) {
 
 // kernels / launchers implemented in the other translation units
 int launch_minksweep3d(Ctx* c, int K, int B, int n_first_obj, int n_objs, const double* d_semi, const double* d_R,
-                       const double* d_off, int precision, char* d_mesh, double* d_lo, double* d_up, bool do_sweep);
+                       const double* d_off, int precision, char* d_mesh, double* d_lo, double* d_up, bool do_sweep, bool reload = false);
 int launch_minksweep2d(Ctx* c, int K, int B, int n_first_obj, int n_objs, const double* d_semi, const double* d_angle,
-                       const double* d_off, int precision, char* d_mesh, double* d_lo, double* d_up, bool do_sweep);
+                       const double* d_off, int precision, char* d_mesh, double* d_lo, double* d_up, bool do_sweep, bool reload = false);
 int launch_segments(Ctx* c);
 int launch_edges(Ctx* c, int k, int E, const double* d_v1, const double* d_v2, unsigned char* d_out);
 int launch_bridge_test(Ctx* c, int p, int Q, const double* d_centres, unsigned char* d_out);

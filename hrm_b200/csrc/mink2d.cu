@@ -27,6 +27,7 @@ struct Mink2Params {
     double* up;
     unsigned long long* counters;
     int num, B, first_obj, n_objs, Ly;
+    int reload;  // re-sweep: the curve is read back from `mesh` instead of being computed
     double xlow, xup;
 };
 
@@ -85,6 +86,10 @@ __global__ void __launch_bounds__(128) k_minksweep2d(const Mink2Params p) {
 
     // ---- phase A ----
     for (int i = tid; i < num; i += blockDim.x) {
+        if (p.reload) {  // refinement path: classify the cached curve against the new sweep lines
+            if (SWEEP) sx[i] = gx[i], sy[i] = gy[i];
+            continue;
+        }
         const double ce = __ldg(tab + i), se = __ldg(tab + num + i), ce2 = __ldg(tab + 2 * num + i), se2 = __ldg(tab + 3 * num + i);
         const double X = A::mul(a1, ce), Y = A::mul(b1, se);                      // SuperEllipse.cpp:42-43
         const double x0 = A::add(A::mad(-s1, Y, A::mul(c1, X)), ob.px);            // :52
@@ -137,7 +142,7 @@ __global__ void __launch_bounds__(128) k_minksweep2d(const Mink2Params p) {
 }
 
 int launch_minksweep2d(Ctx* c, int K, int B, int n_first_obj, int n_objs, const double* d_semi, const double* d_cs,
-                       const double* d_off, int precision, char* d_mesh, double* d_lo, double* d_up, bool do_sweep) {
+                       const double* d_off, int precision, char* d_mesh, double* d_lo, double* d_up, bool do_sweep, bool reload) {
     Mink2Params p;
     p.obj = c->obj2.p;
     p.tab = c->tab.p;
@@ -154,6 +159,7 @@ int launch_minksweep2d(Ctx* c, int K, int B, int n_first_obj, int n_objs, const 
     p.first_obj = n_first_obj;
     p.n_objs = n_objs;
     p.Ly = c->Ly;
+    p.reload = reload ? 1 : 0;
     p.xlow = c->lim[0];
     p.xup = c->lim[1];
     const long long grid = static_cast<long long>(K) * n_objs * B;

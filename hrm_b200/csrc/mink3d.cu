@@ -51,6 +51,7 @@ struct MinkParams {
     int Lx, Ly, L;
     int lpc, groups;                        // thread mapping
     int paired;                             // phase A handles rows in adjacent pairs (n even, lpc divides n/2)
+    int reload;                             // re-sweep: the boundary points are read back from `mesh` instead of being computed
     // byte offsets of the shared-memory regions (host-computed, see smem_layout): read from the constant bank instead of
     // being re-derived from n, Lx, Ly wherever the compiler rematerialises a pointer
     int o_mats, o_cc, o_txs, o_tys, o_zq, o_queue, o_vcode, o_zc0, o_zc1, o_m0, o_m1, o_qcount;
@@ -201,9 +202,30 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
     int* qcount = reinterpret_cast<int*>(smem_raw + p.o_qcount);               // [0] queue fill, [1] next scan batch
     int* batch_ctr = qcount + 1;
 
-    // ---- prologue: tables, line coordinates, per-surface matrices -------------------------
     const Obj3& ob = p.obj[obj_id];
     const bool sign_neg = __ldg(&ob.sign) < 0.0;  // arena surface (requested here, consumed in phase D)
+    Real* mesh = reinterpret_cast<Real*>(p.mesh) + static_cast<size_t>(slot) * 3 * M;
+    Real* mx = mesh;
+    Real* my = mesh + M;
+    Real* mz = mesh + 2 * static_cast<size_t>(M);
+
+    if (p.reload) {
+        // ---- re-sweep (refinement path, HighwayRoadMap-inl.h:178-215): the cached boundary of this surface is classified
+        // against the new sweep grid; nothing of K1 is recomputed ----
+        if (SWEEP) {
+            for (int i = tid; i < p.Lx + 2; i += kThreads) txs[i] = __ldg(p.txs + i);
+            for (int i = tid; i < p.Ly + 2; i += kThreads) tys[i] = __ldg(p.tys + i);
+            for (int i = tid; i < p.L; i += kThreads) m0[i] = kNoFace, m1[i] = kNoFace;
+            if (tid == 0) *qcount = 0, *batch_ctr = 0;
+            __syncthreads();
+            for (int i = tid; i < M; i += kThreads) {
+                const uint32_t cx = line_code(static_cast<double>(mx[i]), txs, p.Lx, p.inv_dx, p.bias_x);
+                const uint32_t cy = line_code(static_cast<double>(my[i]), tys, p.Ly, p.inv_dy, p.bias_y);
+                vcode[i] = pack_code(cx, cy);
+            }
+        }
+    } else {
+    // ---- prologue: tables, line coordinates, per-surface matrices -------------------------
     // warp 0 requests the operands of the per-surface matrices first: their (HBM) latency overlaps the table loads below
     const int me = tid < 9 ? tid : 0;
     double mi0 = 0, mi1 = 0, mi2 = 0, mj0 = 0, mj1 = 0, mj2 = 0, md0 = 0, md1 = 0, md2 = 0, msign = 0, r1a = 0, r1b = 0, r1c = 0;
@@ -275,10 +297,6 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
         }
     }
 
-    Real* mesh = reinterpret_cast<Real*>(p.mesh) + static_cast<size_t>(slot) * 3 * M;
-    Real* mx = mesh;
-    Real* my = mesh + M;
-    Real* mz = mesh + 2 * static_cast<size_t>(M);
     __syncthreads();
     if constexpr (MODE != HRMGPU_F64_STRICT) {
         // per-column constants: group U = M1 * diag(ga, gb, gc), group W = M2 * diag(..), group P = R1 * diag(A, B, Z) + shift.
@@ -552,6 +570,7 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
             }
         }
     }
+    }  // !p.reload
     if (!SWEEP) return;
     __syncwarp();  // lanes leave the column/row loops at different trips: reconverge before the block barrier
     __syncthreads();
@@ -898,7 +917,7 @@ static int launch_t(Ctx* c, const MinkParams& p, int grid, size_t smem) {
 }
 
 int launch_minksweep3d(Ctx* c, int K, int B, int n_first_obj, int n_objs, const double* d_semi, const double* d_R,
-                       const double* d_off, int precision, char* d_mesh, double* d_lo, double* d_up, bool do_sweep) {
+                       const double* d_off, int precision, char* d_mesh, double* d_lo, double* d_up, bool do_sweep, bool reload) {
     MinkParams p;
     p.obj = c->obj3.p;
     p.tab = c->tab.p;
@@ -922,6 +941,7 @@ int launch_minksweep3d(Ctx* c, int K, int B, int n_first_obj, int n_objs, const 
     p.Ly = c->Ly;
     p.L = c->Lx * c->Ly;
     pick_mapping(c->n, p.lpc, p.groups, p.paired);
+    p.reload = reload ? 1 : 0;
     const double dx = (c->lim[1] - c->lim[0]) / static_cast<double>(c->Lx - 1);
     const double dy = (c->lim[3] - c->lim[2]) / static_cast<double>(c->Ly - 1);
     p.inv_dx = 1.0 / dx;

@@ -98,6 +98,12 @@ int hrmgpu_build_layers_dev(hrmgpu_ctx* ctx, int K, int B, const double* d_body_
  * (FreeSpace2D.cpp:14-50); computeFreeSegment.  body_semi [B][2], body_angle [K][B], body_off [K][B][2]. */
 int hrmgpu_build_layers2d(hrmgpu_ctx* ctx, int K, int B, const double* body_semi, const double* body_angle,
                           const double* body_off, int precision);
+/* Refinement: HighwayRoadMap::refineExistRoadmap (include/hrm/planners/HighwayRoadMap-inl.h:178-215) doubles the sweep
+ * lines and HRM3D/HRM2D::constructOneSlice (src/planners/HRM3D.cpp:24-54) reuses the cached C-boundaries
+ * (sliceBoundAll_, sliceBoundMeshAll_).  Re-runs the sweep and the free-segment passes of ALL layers of the last build
+ * on their meshes resident in device memory for a new grid; boundaries, edge and bridge tests are unaffected.
+ * Interval tables are sized by the new line count (the reference overruns its tables here, SURVEY.md finding 6). */
+int hrmgpu_resweep(hrmgpu_ctx* ctx, const double* boundaryLimits, int numLineX, int numLineY);
 
 /* ---- results of the last build -------------------------------------------------------------- */
 /* Sizes of the last build: out[0]=K, [1]=B, [2]=S, [3]=Sa, [4]=L, [5]=M (points per surface),

@@ -67,3 +67,28 @@ def test_fast_f64_within_tolerance_2d(oracle, gpu_ctx):
         assert np.array_equal(ref["off"], got["off"])
         for key in ("xL", "xU", "xM"):
             assert np.max(np.abs(ref[key] - got[key]), initial=0.0) <= 1e-6
+
+
+def test_resweep2d_equals_fresh_build(gpu_ctx):
+    """2D refinement path: hrmgpu_resweep on the cached curves == a fresh build with the doubled line count."""
+    sc = util.scenes()["2D_superellipse_cluttered_rabbit"]
+    rows = sc["arena"] + sc["obstacle"]
+    num = 50
+    semi, ang, off = util.body_poses2d(sc["robot"], np.linspace(-3.0, 3.0, 5))
+    gpu_ctx.set_scene2d(len(sc["arena"]), len(sc["obstacle"]), np.array(rows), num)
+    gpu_ctx.set_sweep(sc["lim"], 1, 20)
+    gpu_ctx.build_layers2d(semi, ang, off, capi.F64_STRICT)
+    gpu_ctx.resweep(sc["lim"], 1, 40)
+    re = [(gpu_ctx.intervals(k), gpu_ctx.segments(k)) for k in range(5)]
+    fresh = capi.Context(0)
+    fresh.set_scene2d(len(sc["arena"]), len(sc["obstacle"]), np.array(rows), num)
+    fresh.set_sweep(sc["lim"], 1, 40)
+    fresh.build_layers2d(semi, ang, off, capi.F64_STRICT)
+    for k in range(5):
+        (lo, up), seg = re[k]
+        flo, fup = fresh.intervals(k)
+        assert lo.shape[0] == 40
+        assert np.array_equal(lo, flo, equal_nan=True) and np.array_equal(up, fup, equal_nan=True)
+        for a, b in zip(seg, fresh.segments(k)):
+            assert np.array_equal(a, b)
+    fresh.close()

@@ -156,3 +156,37 @@ def test_segment_pass_variants_bit_exact(oracle, env, monkeypatch):
     assert any((np.diff(ref["off"]) > 2).any() for ref, _ in res)
     for ref, got in res:
         assert_bit_exact(ref, got)
+
+
+@pytest.mark.parametrize("precision", [capi.F64_STRICT, capi.F64, capi.F32])
+def test_resweep_equals_fresh_build(oracle, gpu_ctx, precision):
+    """Refinement path (hrmgpu_resweep): doubling the sweep lines on the cached boundaries must give exactly the intervals
+    and free segments of a fresh build at the doubled grid -- and, in strict mode, the oracle's."""
+    sc = util.scenes()["3D_superquadrics_cluttered_rabbit"]
+    rows = sc["arena"] + sc["obstacle"]
+    n = 12
+    semi, R, off, quat = util.body_poses3d(sc["robot"], sc["quats"][:3])
+    Lx, Ly = sc["Lx"], sc["Ly"]
+    gpu_ctx.set_scene3d(1, len(sc["obstacle"]), util.sq17(rows, n), n)
+    gpu_ctx.set_sweep(sc["lim"], Lx, Ly)
+    gpu_ctx.build_layers(semi, R, off, precision)
+    bound0 = gpu_ctx.boundary(1, 2).copy()
+    gpu_ctx.resweep(sc["lim"], 2 * Lx, 2 * Ly)
+    re = [(gpu_ctx.intervals(k), gpu_ctx.segments(k)) for k in range(3)]
+    assert np.array_equal(gpu_ctx.boundary(1, 2), bound0)  # boundaries untouched
+    fresh = capi.Context(0)
+    fresh.set_scene3d(1, len(sc["obstacle"]), util.sq17(rows, n), n)
+    fresh.set_sweep(sc["lim"], 2 * Lx, 2 * Ly)
+    fresh.build_layers(semi, R, off, precision)
+    for k in range(3):
+        (lo, up), seg = re[k]
+        flo, fup = fresh.intervals(k)
+        assert np.array_equal(lo, flo, equal_nan=True) and np.array_equal(up, fup, equal_nan=True)
+        for a, b in zip(seg, fresh.segments(k)):
+            assert np.array_equal(a, b)
+        if precision == capi.F64_STRICT:
+            ref = oracle.layer3d(1, len(sc["obstacle"]), np.array(rows), n, semi, quat[k], off[k], sc["lim"], 2 * Lx, 2 * Ly)
+            assert np.array_equal(lo, ref["lo"], equal_nan=True) and np.array_equal(seg[3], ref["xM"])
+    fresh.close()
+    # edge tests still run on the cached meshes
+    assert gpu_ctx.test_edges(0, np.zeros((1, 3)), np.ones((1, 3))).shape == (1,)
