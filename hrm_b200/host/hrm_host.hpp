@@ -372,6 +372,10 @@ class FreeSpaceGPU {
     void setup(const std::vector<Coordinate>& boundaryLimits, Index numLineX, Index numLineY) {
         check(hrmgpu_set_sweep(ctx_, boundaryLimits.data(), static_cast<int>(numLineX), static_cast<int>(numLineY)));
     }
+    /** refinement (HighwayRoadMap-inl.h:178-215): sweep + free segments of all built layers redone on their cached boundaries */
+    void resweep(const std::vector<Coordinate>& boundaryLimits, Index numLineX, Index numLineY) {
+        check(hrmgpu_resweep(ctx_, boundaryLimits.data(), static_cast<int>(numLineX), static_cast<int>(numLineY)));
+    }
     /** getCSpaceBoundary() of layer k */
     BoundaryInfo getCSpaceBoundary(int k) {
         long long d[8];
@@ -574,6 +578,14 @@ class HighwayRoadMapBase {
         t0 = std::chrono::high_resolution_clock::now();
         search();
         res_.planningTime.searchTime = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+        // HighwayRoadMap-inl.h:78-81: refine while unsolved (the reference is bounded by the time limit only; here also by a
+        // round count so that runs are reproducible -- 0 rounds by default, like a reference run that solves at once)
+        while (!res_.solved && numRefineDone_ < maxRefine_) {
+            t0 = std::chrono::high_resolution_clock::now();
+            refineExistRoadmap();
+            ++numRefineDone_;
+            res_.planningTime.buildTime += std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+        }
         res_.planningTime.totalTime = res_.planningTime.buildTime + res_.planningTime.searchTime;
         if (res_.solved) {
             const size_t pose = res_.graphStructure.vertex.at(0).size();
@@ -587,9 +599,13 @@ class HighwayRoadMapBase {
     const PlanningResult& getPlanningResult() const { return res_; }
     const PlannerParameter& getPlannerParameters() const { return param_; }
     long numEdgeTests() const { return numEdgeTests_; }
+    void setMaxRefine(size_t rounds) { maxRefine_ = rounds; }
+    size_t numRefineDone() const { return numRefineDone_; }
 
   protected:
     virtual void buildRoadmap() = 0;
+    /** refineExistRoadmap (:178-215): doubled sweep lines on the cached C-boundaries, new vertices tied to the existing ones */
+    virtual void refineExistRoadmap() {}
     virtual std::vector<Index> getNearestNeighborsOnGraph(const std::vector<Coordinate>& vertex, Index k, double radius) = 0;
 
     /** HighwayRoadMap-inl.h:110-175 */
@@ -648,6 +664,36 @@ class HighwayRoadMapBase {
     int precision_;
     bool perOrientation_;
     long numEdgeTests_ = 0;
+    size_t maxRefine_ = 0, numRefineDone_ = 0;
+    std::vector<std::vector<std::pair<Index, Index>>> vertexIdxAll_;  // vertexIdx_ of the previous refinement rounds
+
+    /** connectExistSlice (HRM3D.cpp:226-270, HRM2D.cpp:158-197): vertices of the refined layer against the same layer's
+     * vertices of the previous round; `near(v1, v2)` is the sweep-line adjacency filter, edge tests in one K4 batch, replay with
+     * the reference's moving lower bound. */
+    template <class Near, class TestBatch>
+    void connectExistSliceReplay(size_t sliceId, Near near, TestBatch testBatch) {
+        const auto& V = res_.graphStructure.vertex;
+        const Index cur0 = vertexIdx_.at(sliceId).first, cur1 = vertexIdx_.at(sliceId).second;
+        const Index ex0 = vertexIdxAll_.back().at(sliceId).first, ex1 = vertexIdxAll_.back().at(sliceId).second;
+        std::vector<std::pair<Index, Index>> cand;
+        for (Index m0 = cur0; m0 < cur1; ++m0)
+            for (Index m1 = ex0; m1 < ex1; ++m1)
+                if (near(V[m0], V[m1])) cand.push_back({m0, m1});
+        if (cand.empty()) return;
+        const std::vector<unsigned char> ok = testBatch(cand);
+        numEdgeTests_ += static_cast<long>(cand.size());
+        std::map<std::pair<Index, Index>, bool> freePair;
+        for (size_t c = 0; c < cand.size(); ++c) freePair[cand[c]] = ok[c] != 0;
+        Index startIdExist = ex0;
+        for (Index m0 = cur0; m0 < cur1; ++m0)
+            for (Index m1 = startIdExist; m1 < ex1; ++m1) {
+                const auto it = freePair.find({m0, m1});
+                if (it == freePair.end() || !it->second) continue;
+                addEdge(m0, m1);
+                startIdExist = m1;
+                break;
+            }
+    }
 };
 
 /** src/planners/HRM3D.cpp */
@@ -668,7 +714,8 @@ class HRM3D : public HighwayRoadMapBase {
         freeSpace_.setup(lim, param_.numLineX, param_.numLineY);
         // K1+K2+K3 for every orientation in ONE call
         std::vector<MultiBodyTree3D> poses;
-        std::vector<Quaternion> baseQ;
+        std::vector<Quaternion>& baseQ = baseQ_;
+        baseQ.clear();
         MultiBodyTree3D rb = robot_;
         for (const auto& q : q_) {
             SE3Transform g;
@@ -687,6 +734,39 @@ class HRM3D : public HighwayRoadMapBase {
         for (int i = 0; i < Ly; ++i) ty[i] = lim[2] + static_cast<double>(i) * dy;
         for (size_t k = 0; k < q_.size(); ++k) connectOneSlice3D(static_cast<int>(k), baseQ[k], tx, ty, off.data() + k * Lx * Ly, xL, xU, xM);
         connectMultiSlice();
+    }
+
+    void refineExistRoadmap() override {
+        vertexIdxAll_.push_back(vertexIdx_);
+        vertexIdx_.clear();
+        param_.numLineX *= 2;
+        param_.numLineY *= 2;
+        const auto& lim = param_.boundaryLimits;
+        const int Lx = static_cast<int>(param_.numLineX), Ly = static_cast<int>(param_.numLineY);
+        freeSpace_.resweep(lim, param_.numLineX, param_.numLineY);  // K2 + K3 of every layer in one call, K1 untouched
+        std::vector<long long> off;
+        std::vector<double> xL, xU, xM;
+        freeSpace_.getFreeSegmentsAll(off, xL, xU, xM);
+        const double dx = (lim[1] - lim[0]) / static_cast<double>(Lx - 1), dy = (lim[3] - lim[2]) / static_cast<double>(Ly - 1);
+        std::vector<double> tx(Lx), ty(Ly);
+        for (int i = 0; i < Lx; ++i) tx[i] = lim[0] + static_cast<double>(i) * dx;
+        for (int i = 0; i < Ly; ++i) ty[i] = lim[2] + static_cast<double>(i) * dy;
+        const double thx = 2.0 * std::fabs(lim[1] - lim[0]) / static_cast<double>(param_.numLineX);
+        const double thy = 2.0 * std::fabs(lim[3] - lim[2]) / static_cast<double>(param_.numLineY);
+        for (size_t k = 0; k < q_.size(); ++k) {
+            connectOneSlice3D(static_cast<int>(k), baseQ_[k], tx, ty, off.data() + k * static_cast<size_t>(Lx) * Ly, xL, xU, xM);
+            const auto& V = res_.graphStructure.vertex;
+            connectExistSliceReplay(
+                k, [&](const std::vector<Coordinate>& a, const std::vector<Coordinate>& b) { return !(std::fabs(a[0] - b[0]) > thx) && !(std::fabs(a[1] - b[1]) > thy); },
+                [&](const std::vector<std::pair<Index, Index>>& cand) {
+                    std::vector<double> A, Bq;
+                    for (const auto& c : cand)
+                        for (int d = 0; d < 3; ++d) A.push_back(V[c.first][d]), Bq.push_back(V[c.second][d]);
+                    return freeSpace_.testEdges(static_cast<int>(k), A, Bq, 3);
+                });
+            search();
+            if (res_.solved) return;
+        }
     }
 
     /** generateVertices + connectOneSlice2D per plane + cross-plane connections (HRM3D.cpp:93-156), edge tests batched on the GPU */
@@ -885,6 +965,7 @@ class HRM3D : public HighwayRoadMapBase {
     FreeSpaceGPU3D freeSpace_;
     std::vector<Quaternion> q_;
     std::vector<Coordinate> vertexTail_;  // appended to every vertex of the slice under construction (empty for rigid bodies)
+    std::vector<Quaternion> baseQ_;       // base quaternion of every layer as the vertices carry it
 };
 
 /** src/planners/HRM2D.cpp */
@@ -903,7 +984,8 @@ class HRM2D : public HighwayRoadMapBase {
         for (size_t i = 0; i < param_.numSlice; ++i) headings_.push_back(-PI + dr * static_cast<double>(i));
         freeSpace_.setup(lim, 1, param_.numLineY);
         std::vector<MultiBodyTree2D> poses;
-        std::vector<double> baseAngle;
+        std::vector<double>& baseAngle = baseAngle_;
+        baseAngle.clear();
         MultiBodyTree2D rb = robot_;
         for (double th : headings_) {
             rb.robotTF(th, 0.0, 0.0);
@@ -917,39 +999,75 @@ class HRM2D : public HighwayRoadMapBase {
         const double dy = (lim[3] - lim[2]) / (static_cast<double>(Ly) - 1);  // :56-61
         std::vector<double> ty(Ly);
         for (int i = 0; i < Ly; ++i) ty[i] = lim[2] + static_cast<double>(i) * dy;
-        auto& V = res_.graphStructure.vertex;
-        for (size_t k = 0; k < headings_.size(); ++k) {
-            const long long* o = off.data() + k * Ly;
-            auto cnt = [&](int iy) { return static_cast<int>(o[iy + 1] - o[iy]); };
-            std::vector<double> A, Bq;
-            for (int iy = 0; iy + 1 < Ly; ++iy)
-                for (int j1 = 0; j1 < cnt(iy); ++j1)
-                    for (int j2 = 0; j2 < cnt(iy + 1); ++j2) {
-                        A.push_back(xM[o[iy] + j1]), A.push_back(ty[iy]);
-                        Bq.push_back(xM[o[iy + 1] + j2]), Bq.push_back(ty[iy + 1]);
-                    }
-            // bridgeVertex swaps index 2 = theta in 2D: vNew1 == v1, vNew2 == v2 as points, so it can never add a vertex (App. C8)
-            const auto f = freeSpace_.testEdges(static_cast<int>(k), A, Bq, 2);
-            numEdgeTests_ += static_cast<long>(f.size());
-            const Index startId = V.size();
-            std::vector<Index> plane;
-            for (int iy = 0; iy < Ly; ++iy) {  // generateVertices (:72-89)
-                plane.push_back(V.size());
-                for (int j = 0; j < cnt(iy); ++j) V.push_back({xM[o[iy] + j], ty[iy], baseAngle[k]});
-            }
-            size_t pi = 0;
-            for (int iy = 0; iy < Ly; ++iy) {  // connectOneSlice2D
-                const Index n1 = plane[iy];
-                for (int j1 = 0; j1 < cnt(iy); ++j1) {
-                    if (j1 != cnt(iy) - 1 && std::fabs(xU[o[iy] + j1] - xL[o[iy] + j1 + 1]) < 1e-6) addEdge(n1 + j1, n1 + j1 + 1);
-                    if (iy != Ly - 1)
-                        for (int j2 = 0; j2 < cnt(iy + 1); ++j2)
-                            if (f[pi++]) addEdge(n1 + j1, plane[iy + 1] + j2);
-                }
-            }
-            vertexIdx_.push_back({startId, V.size()});
-        }
+        for (size_t k = 0; k < headings_.size(); ++k) connectOneSliceLayer(k, Ly, ty, off, xL, xU, xM);
         connectMultiSlice();
+    }
+
+    /** generateVertices (:72-89) + connectOneSlice2D of layer k: edge tests of the layer in one K4 batch, host replay */
+    void connectOneSliceLayer(size_t k, int Ly, const std::vector<double>& ty, const std::vector<long long>& off, const std::vector<double>& xL,
+                              const std::vector<double>& xU, const std::vector<double>& xM) {
+        auto& V = res_.graphStructure.vertex;
+        const std::vector<double>& baseAngle = baseAngle_;
+        const long long* o = off.data() + k * Ly;
+        auto cnt = [&](int iy) { return static_cast<int>(o[iy + 1] - o[iy]); };
+        std::vector<double> A, Bq;
+        for (int iy = 0; iy + 1 < Ly; ++iy)
+            for (int j1 = 0; j1 < cnt(iy); ++j1)
+                for (int j2 = 0; j2 < cnt(iy + 1); ++j2) {
+                    A.push_back(xM[o[iy] + j1]), A.push_back(ty[iy]);
+                    Bq.push_back(xM[o[iy + 1] + j2]), Bq.push_back(ty[iy + 1]);
+                }
+        // bridgeVertex swaps index 2 = theta in 2D: vNew1 == v1, vNew2 == v2 as points, so it can never add a vertex (App. C8)
+        const auto f = freeSpace_.testEdges(static_cast<int>(k), A, Bq, 2);
+        numEdgeTests_ += static_cast<long>(f.size());
+        const Index startId = V.size();
+        std::vector<Index> plane;
+        for (int iy = 0; iy < Ly; ++iy) {  // generateVertices (:72-89)
+            plane.push_back(V.size());
+            for (int j = 0; j < cnt(iy); ++j) V.push_back({xM[o[iy] + j], ty[iy], baseAngle[k]});
+        }
+        size_t pi = 0;
+        for (int iy = 0; iy < Ly; ++iy) {  // connectOneSlice2D
+            const Index n1 = plane[iy];
+            for (int j1 = 0; j1 < cnt(iy); ++j1) {
+                if (j1 != cnt(iy) - 1 && std::fabs(xU[o[iy] + j1] - xL[o[iy] + j1 + 1]) < 1e-6) addEdge(n1 + j1, n1 + j1 + 1);
+                if (iy != Ly - 1)
+                    for (int j2 = 0; j2 < cnt(iy + 1); ++j2)
+                        if (f[pi++]) addEdge(n1 + j1, plane[iy + 1] + j2);
+            }
+        }
+        vertexIdx_.push_back({startId, V.size()});
+    }
+
+    void refineExistRoadmap() override {
+        vertexIdxAll_.push_back(vertexIdx_);
+        vertexIdx_.clear();
+        param_.numLineX *= 2;
+        param_.numLineY *= 2;
+        const auto& lim = param_.boundaryLimits;
+        const int Ly = static_cast<int>(param_.numLineY);
+        freeSpace_.resweep(lim, 1, param_.numLineY);
+        std::vector<long long> off;
+        std::vector<double> xL, xU, xM;
+        freeSpace_.getFreeSegmentsAll(off, xL, xU, xM);
+        const double dy = (lim[3] - lim[2]) / (static_cast<double>(Ly) - 1);
+        std::vector<double> ty(Ly);
+        for (int i = 0; i < Ly; ++i) ty[i] = lim[2] + static_cast<double>(i) * dy;
+        const double th = 2.0 * std::fabs(lim[3] - lim[2]) / static_cast<double>(param_.numLineY);
+        for (size_t k = 0; k < headings_.size(); ++k) {
+            connectOneSliceLayer(k, Ly, ty, off, xL, xU, xM);
+            const auto& V = res_.graphStructure.vertex;
+            connectExistSliceReplay(
+                k, [&](const std::vector<Coordinate>& a, const std::vector<Coordinate>& b) { return !(std::fabs(a[1] - b[1]) > th); },
+                [&](const std::vector<std::pair<Index, Index>>& cand) {
+                    std::vector<double> A, Bq;
+                    for (const auto& c : cand)
+                        for (int d = 0; d < 2; ++d) A.push_back(V[c.first][d]), Bq.push_back(V[c.second][d]);
+                    return freeSpace_.testEdges(static_cast<int>(k), A, Bq, 2);
+                });
+            search();
+            if (res_.solved) return;
+        }
     }
 
     void connectMultiSlice() {  // HRM2D.cpp:91-156
@@ -1058,6 +1176,7 @@ class HRM2D : public HighwayRoadMapBase {
     MultiBodyTree2D robot_;
     FreeSpaceGPU2D freeSpace_;
     std::vector<double> headings_;
+    std::vector<double> baseAngle_;  // base angle of every layer as the vertices carry it
 };
 
 }  // namespace planners

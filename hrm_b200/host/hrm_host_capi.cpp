@@ -16,6 +16,7 @@ static SuperEllipse seFromRow(const double* r, int num) {
     return SuperEllipse({r[0], r[1]}, r[2], {r[3], r[4]}, r[5], static_cast<Index>(num));
 }
 static thread_local std::string g_err;
+static int g_max_refine = 0;  // refinement rounds hrmhost_plan3d / plan2d may run (HighwayRoadMap-inl.h:78-81); info[4] = rounds done
 
 template <class Planner>
 static void exportResult(Planner& hrm, long* info, double* vertex, long cap_v, int vdim, long* edge, long cap_e, long* path, long cap_p) {
@@ -39,6 +40,7 @@ static void exportResult(Planner& hrm, long* info, double* vertex, long cap_v, i
 extern "C" {
 
 const char* hrmhost_last_error(void) { return g_err.c_str(); }
+void hrmhost_set_max_refine(int rounds) { g_max_refine = rounds < 0 ? 0 : rounds; }
 
 // hrm::planners::HRM3D(robot, arena, obs, req).plan().  Returns 0, or -1 with hrmhost_last_error() set.
 // info[8]: solved, n_vertex, n_edge, n_path, -, n_edge_tests, gpu_kernel_launches, total_time_us.
@@ -64,8 +66,10 @@ int hrmhost_plan3d(int n_arena, int n_obs, const double* sq, int n, int B, const
         req.start.assign(start, start + 7);
         req.goal.assign(goal, goal + 7);
         planners::HRM3D hrm(rb, arena, obs, req, device, precision, per_orientation != 0);
+        hrm.setMaxRefine(static_cast<size_t>(g_max_refine));
         hrm.plan();
         exportResult(hrm, info, vertex, cap_v, 7, edge, cap_e, path, cap_p);
+        info[4] = static_cast<long>(hrm.numRefineDone());
         return 0;
     } catch (const std::exception& e) {
         g_err = e.what();
@@ -91,8 +95,10 @@ int hrmhost_plan2d(int n_arena, int n_obs, const double* se, int num, int B, con
         req.start.assign(start, start + 3);
         req.goal.assign(goal, goal + 3);
         planners::HRM2D hrm(rb, arena, obs, req, device, precision, per_orientation != 0);
+        hrm.setMaxRefine(static_cast<size_t>(g_max_refine));
         hrm.plan();
         exportResult(hrm, info, vertex, cap_v, 3, edge, cap_e, path, cap_p);
+        info[4] = static_cast<long>(hrm.numRefineDone());
         return 0;
     } catch (const std::exception& e) {
         g_err = e.what();

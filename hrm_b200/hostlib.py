@@ -31,7 +31,12 @@ def _p(a):
 def _out(info, vertex, edge, path):
     nv, ne, npth = int(info[1]), int(info[2]), int(info[3])
     return {"solved": bool(info[0]), "vertex": vertex[:nv].copy(), "edge": edge[:ne].copy(), "path": path[:npth].copy(),
-            "edge_tests": int(info[5]), "gpu_launches": int(info[6]), "total_time_s": info[7] * 1e-6}
+            "edge_tests": int(info[5]), "gpu_launches": int(info[6]), "total_time_s": info[7] * 1e-6, "refine_rounds": int(info[4])}
+
+
+def set_max_refine(rounds):
+    """Refinement rounds (doubled sweep lines on the cached C-boundaries) plan3d / plan2d may run while unsolved; default 0."""
+    load().hrmhost_set_max_refine(C.c_int(rounds))
 
 
 def plan3d(n_arena, n_obs, sq12, n, robot_rows, quats, lim, Lx, Ly, num_point, start, goal, per_orientation=False, precision=0, device=0,

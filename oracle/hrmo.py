@@ -310,7 +310,12 @@ def pt_in_cfree2d(bounds, pts):
 def _plan_out(info, vertex, edge, path):
     nv, ne, npth = int(info[1]), int(info[2]), int(info[3])
     return {"solved": bool(info[0]), "vertex": vertex[:nv].copy(), "edge": edge[:ne].copy(), "path": path[:npth].copy(),
-            "single_hits": int(info[4]), "edge_tests": int(info[5])}
+            "single_hits": int(info[4]), "edge_tests": int(info[5]), "refine_rounds": int(info[7])}
+
+
+def set_max_refine(n):
+    """Refinement rounds plan3d / plan2d may run when the first roadmap does not connect start and goal (default 0)."""
+    lib().hrmo_set_max_refine(C.c_int(n))
 
 
 def plan3d(n_arena, n_obs, sq, n, robot_rows, quats, lim, Lx, Ly, num_point, start, goal, per_orientation=False,

@@ -405,6 +405,11 @@ long hrmo_pt_in_cfree2d(const double* bound, int num, int count, int Q, const do
 // quats [numSlice][4] (w,x,y,z).  lim[6], Lx, Ly, numPoint.  start/goal: 7 doubles (x,y,z,qw,qx,qy,qz).
 // per_orientation = 0 reproduces the reference snapshot (frozen FreeSpace robot copy).
 // out_info[8]: solved, n_vertex, n_edge, n_path, single_hits, n_edge_tests, -, -.   vertex [cap_v][7], edge [cap_e][2].
+// Refinement rounds allowed in hrmo_plan3d / hrmo_plan2d (HighwayRoadMap::plan refines while unsolved and within the time
+// limit; rounds are counted here to keep the runs deterministic).  out_info[7] = rounds done.
+static int g_max_refine = 0;
+void hrmo_set_max_refine(int n) { g_max_refine = n < 0 ? 0 : n; }
+
 int hrmo_plan3d(int n_arena, int n_obs, const double* sq, int n, int B, const double* robot, int numSlice, const double* quats,
                 const double lim[6], int Lx, int Ly, int numPoint, const double* start, const double* goal, int per_orientation,
                 long* out_info, double* vertex, long cap_v, long* edge, long cap_e, long* path, long cap_p) {
@@ -425,7 +430,8 @@ int hrmo_plan3d(int n_arena, int n_obs, const double* sq, int n, int B, const do
     req.start.assign(start, start + 7);
     req.goal.assign(goal, goal + 7);
     HRM3D hrm(rb, arena, obs, req, qs, per_orientation != 0);
-    hrm.plan();
+    hrm.plan(static_cast<size_t>(g_max_refine));
+    out_info[7] = static_cast<long>(hrm.numRefineDone);
     const auto& g = hrm.res_.graphStructure;
     out_info[0] = hrm.res_.solved ? 1 : 0;
     out_info[1] = static_cast<long>(g.vertex.size());
@@ -458,7 +464,8 @@ int hrmo_plan2d(int n_arena, int n_obs, const double* se, int num, int B, const 
     req.start.assign(start, start + 3);
     req.goal.assign(goal, goal + 3);
     HRM2D hrm(rb, arena, obs, req, per_orientation != 0);
-    hrm.plan();
+    hrm.plan(static_cast<size_t>(g_max_refine));
+    out_info[7] = static_cast<long>(hrm.numRefineDone);
     const auto& g = hrm.res_.graphStructure;
     out_info[0] = hrm.res_.solved ? 1 : 0;
     out_info[1] = static_cast<long>(g.vertex.size());

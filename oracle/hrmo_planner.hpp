@@ -157,6 +157,9 @@ struct HighwayRoadMap {
     std::vector<VertexIdx> vertexIdx_;
     long singleHitCount = 0;
     long numEdgeTests = 0;
+    bool isRefine_ = false;
+    std::vector<std::vector<VertexIdx>> vertexIdxAll_;  // vertex index records of the previous refinement rounds
+    size_t numRefineDone = 0;
 
     HighwayRoadMap(const RobotType& robot, const std::vector<ObjectType>& arena, const std::vector<ObjectType>& obs,
                    const PlanningRequest& req)
@@ -167,6 +170,7 @@ struct HighwayRoadMap {
     virtual void sampleOrientations() = 0;
     virtual void constructOneSlice(size_t sliceIdx) = 0;
     virtual void connectMultiSlice() = 0;
+    virtual void connectExistSlice(size_t sliceId) = 0;
     virtual bool isSameSliceTransitionFree(const std::vector<double>& v1, const std::vector<double>& v2) = 0;
     virtual std::vector<size_t> getNearestNeighborsOnGraph(const std::vector<double>& vertex, size_t k, double radius) = 0;
 
@@ -207,14 +211,38 @@ struct HighwayRoadMap {
             }
     }
 
-    // :65-89 without the refinement loop (the reference's refinement throws, SURVEY.md finding 6)
-    void plan() {
+    // :178-215.  "Done right" (SURVEY.md finding 6 / §8 f.4): the interval tables are re-sized for the doubled line count
+    // (the reference overruns them and throws) and every slice is re-swept on ITS OWN cached boundary (the reference's
+    // FreeSpace object would still hold the mesh of the last slice built).  Returns as soon as a path exists.
+    void refineExistRoadmap() {
+        isRefine_ = true;
+        vertexIdxAll_.push_back(vertexIdx_);
+        vertexIdx_.clear();
+        param_.numLineX *= 2;
+        param_.numLineY *= 2;
+        for (size_t i = 0; i < param_.numSlice; ++i) {
+            constructOneSlice(i);
+            numVertex_.slice = res_.graphStructure.vertex.size();
+            vertexIdx_.push_back(numVertex_);
+            connectExistSlice(i);
+            search();
+            if (res_.solved) return;
+        }
+        isRefine_ = false;
+    }
+
+    // :65-89; the reference refines `while (!solved && time < limit)`: here at most maxRefine rounds (0 = none)
+    void plan(size_t maxRefine = 0) {
         auto t0 = std::chrono::high_resolution_clock::now();
         buildRoadmap();
         res_.buildTime = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
         t0 = std::chrono::high_resolution_clock::now();
         search();
         res_.searchTime = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+        while (!res_.solved && numRefineDone < maxRefine) {
+            refineExistRoadmap();
+            ++numRefineDone;
+        }
         res_.totalTime = res_.buildTime + res_.searchTime;
         if (res_.solved) {
             const size_t poseSize = res_.graphStructure.vertex.at(0).size();
@@ -288,6 +316,7 @@ struct HRM3D : HighwayRoadMap<MultiBodyTree3D, SuperQuadrics> {
     BoundaryInfo sliceBound_;
     BoundaryMesh sliceBoundMesh_;
     std::vector<BoundaryInfo> sliceBoundAll_;
+    std::vector<BoundaryMesh> sliceBoundMeshAll_;
     FreeSegment3D freeSegOneSlice_;
     std::vector<Ellipsoid3> tfe_;
     std::vector<std::vector<MeshMatrix>> bridgeSliceBound_;
@@ -320,12 +349,21 @@ struct HRM3D : HighwayRoadMap<MultiBodyTree3D, SuperQuadrics> {
             setTransform({0.0, 0.0, 0.0, q_.at(sliceIdx).w, q_.at(sliceIdx).x, q_.at(sliceIdx).y, q_.at(sliceIdx).z});
         else
             setTransform(v_.at(sliceIdx));  // articulated: base pose + joint angles (ProbHRM3D)
-        if (perOrientationFreeSpace_) freeSpace_.setRobot(robot_);
-        freeSpace_.computeCSpaceBoundary();
-        sliceBound_ = freeSpace_.cSpaceBoundary_;
-        sliceBoundAll_.push_back(sliceBound_);
-        freeSpace_.computeCSpaceBoundaryMesh(sliceBound_);
-        sliceBoundMesh_ = freeSpace_.cSpaceBoundaryMesh_;
+        if (!isRefine_) {
+            if (perOrientationFreeSpace_) freeSpace_.setRobot(robot_);
+            freeSpace_.computeCSpaceBoundary();
+            sliceBound_ = freeSpace_.cSpaceBoundary_;
+            sliceBoundAll_.push_back(sliceBound_);
+            freeSpace_.computeCSpaceBoundaryMesh(sliceBound_);
+            sliceBoundMesh_ = freeSpace_.cSpaceBoundaryMesh_;
+            sliceBoundMeshAll_.push_back(sliceBoundMesh_);
+        } else {  // :44-47: cached boundary of this slice, re-swept with the current (doubled) line counts
+            sliceBound_ = sliceBoundAll_.at(sliceIdx);
+            sliceBoundMesh_ = sliceBoundMeshAll_.at(sliceIdx);
+            freeSpace_.cSpaceBoundary_ = sliceBound_;
+            freeSpace_.cSpaceBoundaryMesh_ = sliceBoundMesh_;
+            freeSpace_.setup(static_cast<unsigned>(param_.numLineY), param_.boundaryLimits[4], param_.boundaryLimits[5]);
+        }
         sweepLineProcess();
         connectOneSlice3D(freeSegOneSlice_);
     }
@@ -458,6 +496,31 @@ struct HRM3D : HighwayRoadMap<MultiBodyTree3D, SuperQuadrics> {
         }
     }
 
+    // :226-270
+    void connectExistSlice(size_t sliceId) override {
+        const size_t startIdCur = vertexIdx_.at(sliceId).startId, endIdCur = vertexIdx_.at(sliceId).slice;
+        size_t startIdExist = vertexIdxAll_.back().at(sliceId).startId;
+        const size_t endIdExist = vertexIdxAll_.back().at(sliceId).slice;
+        for (size_t m0 = startIdCur; m0 < endIdCur; ++m0) {
+            const auto v1 = res_.graphStructure.vertex[m0];
+            for (size_t m1 = startIdExist; m1 < endIdExist; ++m1) {
+                const auto v2 = res_.graphStructure.vertex[m1];
+                if (std::fabs(v1.at(0) - v2.at(0)) >
+                    2.0 * std::fabs(param_.boundaryLimits[1] - param_.boundaryLimits[0]) / static_cast<double>(param_.numLineX))
+                    continue;
+                if (std::fabs(v1.at(1) - v2.at(1)) >
+                    2.0 * std::fabs(param_.boundaryLimits[3] - param_.boundaryLimits[2]) / static_cast<double>(param_.numLineY))
+                    continue;
+                if (isSameSliceTransitionFree(v1, v2)) {
+                    res_.graphStructure.edge.push_back({m0, m1});
+                    res_.graphStructure.weight.push_back(vectorEuclidean(v1, v2));
+                    startIdExist = m1;
+                    break;
+                }
+            }
+        }
+    }
+
     // :443-508 with C18 (minQuat initialised to q_[0])
     std::vector<size_t> getNearestNeighborsOnGraph(const std::vector<double>& vertex, size_t k, double radius) override {
         std::vector<size_t> idx;
@@ -502,6 +565,7 @@ struct HRM2D : HighwayRoadMap<MultiBodyTree2D, SuperEllipse> {
     FreeSpace2D freeSpace_;
     std::vector<double> headings_;
     BoundaryInfo sliceBound_;
+    std::vector<BoundaryInfo> sliceBoundAll_;
     FreeSegment2D freeSegOneSlice_;
     std::vector<Ellipse2> tfe_;
     std::vector<std::vector<Points>> bridgeSliceBound_;
@@ -530,9 +594,16 @@ struct HRM2D : HighwayRoadMap<MultiBodyTree2D, SuperEllipse> {
     // :20-42
     void constructOneSlice(size_t sliceIdx) override {
         setTransform({0.0, 0.0, headings_.at(sliceIdx)});
-        if (perOrientationFreeSpace_) freeSpace_.setRobot(robot_);
-        freeSpace_.computeCSpaceBoundary();
-        sliceBound_ = freeSpace_.cSpaceBoundary_;
+        if (!isRefine_) {
+            if (perOrientationFreeSpace_) freeSpace_.setRobot(robot_);
+            freeSpace_.computeCSpaceBoundary();
+            sliceBound_ = freeSpace_.cSpaceBoundary_;
+            sliceBoundAll_.push_back(sliceBound_);
+        } else {  // HRM2D.cpp:29-31: cached boundary of this slice, re-swept with the doubled line count
+            sliceBound_ = sliceBoundAll_.at(sliceIdx);
+            freeSpace_.cSpaceBoundary_ = sliceBound_;
+            freeSpace_.setup(static_cast<unsigned>(param_.numLineY), param_.boundaryLimits[0], param_.boundaryLimits[1]);
+        }
         freeSegOneSlice_ = sweepLineProcess2D(freeSpace_, param_.boundaryLimits.data(), param_.numLineY);
         singleHitCount = freeSpace_.singleHitCount;
         generateVertices(0.0, freeSegOneSlice_);
@@ -628,6 +699,29 @@ struct HRM2D : HighwayRoadMap<MultiBodyTree2D, SuperEllipse> {
                         startIdAdj = m1;
                         break;
                     }
+                }
+            }
+        }
+    }
+
+    // HRM2D.cpp:158-197
+    void connectExistSlice(size_t sliceId) override {
+        const size_t startIdCur = vertexIdx_.at(sliceId).startId, endIdCur = vertexIdx_.at(sliceId).slice;
+        size_t startIdExist = vertexIdxAll_.back().at(sliceId).startId;
+        const size_t endIdExist = vertexIdxAll_.back().at(sliceId).slice;
+        const double distAdjacency = 2.0;
+        for (size_t m0 = startIdCur; m0 < endIdCur; ++m0) {
+            const auto v1 = res_.graphStructure.vertex[m0];
+            for (size_t m1 = startIdExist; m1 < endIdExist; ++m1) {
+                const auto v2 = res_.graphStructure.vertex[m1];
+                if (std::fabs(v1[1] - v2[1]) >
+                    distAdjacency * std::fabs(param_.boundaryLimits[3] - param_.boundaryLimits[2]) / static_cast<double>(param_.numLineY))
+                    continue;
+                if (isSameSliceTransitionFree(v1, v2)) {
+                    res_.graphStructure.edge.push_back({m0, m1});
+                    res_.graphStructure.weight.push_back(vectorEuclidean(v1, v2));
+                    startIdExist = m1;
+                    break;
                 }
             }
         }

@@ -182,3 +182,60 @@ def test_prob_hrm3d_stops_when_draws_run_out(oracle):
     assert not ref["solved"] and not got["solved"]
     assert got["slices"] == ref["slices"] == 5
     assert np.array_equal(got["vertex"], ref["vertex"]) and np.array_equal(got["edge"], ref["edge"])
+
+
+# ---- refinement path: hrmgpu_resweep + connectExistSlice ----------------------------------------------------
+@pytest.fixture
+def refine_rounds(oracle):
+    from hrm_b200 import hostlib
+
+    def set_rounds(n):
+        oracle.set_max_refine(n)
+        hostlib.set_max_refine(n)
+
+    yield set_rounds
+    set_rounds(0)
+
+
+@pytest.mark.parametrize("name,nq,Lx,Ly,per_orientation,rounds", [("3D_superquadrics_narrow_rabbit", 60, 5, 3, False, 2),
+                                                                  ("3D_superquadrics_maze_rabbit", 12, 4, 2, True, 2),
+                                                                  ("3D_superquadrics_cluttered_rabbit", 8, 3, 2, True, 1)])
+def test_hrm3d_refinement_identical(oracle, refine_rounds, name, nq, Lx, Ly, per_orientation, rounds):
+    """Too few sweep lines for the first roadmap -> refineExistRoadmap: the C++ host planner re-sweeps all cached layers in one
+    hrmgpu_resweep call per round and must reproduce the oracle's slice-by-slice refinement (vertices, edges, early stop)."""
+    from hrm_b200 import hostlib
+
+    sc = util.scenes()[name]
+    rows = np.array(sc["arena"] + sc["obstacle"])
+    args = (1, len(sc["obstacle"]), rows, 10, np.array(sc["robot"]), np.array(sc["quats"][:nq]), sc["lim"], Lx, Ly, 5, sc["end_points"][0],
+            sc["end_points"][1])
+    refine_rounds(rounds)
+    ref = oracle.plan3d(*args, per_orientation=per_orientation)
+    got = hostlib.plan3d(*args, per_orientation=per_orientation, precision=capi.F64_STRICT)
+    if name.endswith("cluttered_rabbit"):
+        assert ref["refine_rounds"] == 0  # solved at once: the refinement loop must not run
+    else:
+        assert ref["refine_rounds"] >= 1
+    assert got["refine_rounds"] == ref["refine_rounds"]
+    assert np.array_equal(got["vertex"], ref["vertex"])
+    assert np.array_equal(got["edge"], ref["edge"])
+    assert got["solved"] == ref["solved"]
+    assert np.array_equal(got["path"], ref["path"])
+    if name.endswith("narrow_rabbit"):
+        assert ref["solved"] and ref["refine_rounds"] == 1  # found during the first refinement round
+
+
+@pytest.mark.parametrize("name,Ly,per_orientation", [("2D_superellipse_maze2_rabbit", 6, False), ("2D_superellipse_cluttered_rabbit", 5, True)])
+def test_hrm2d_refinement_identical(oracle, refine_rounds, name, Ly, per_orientation):
+    from hrm_b200 import hostlib
+
+    sc = util.scenes()[name]
+    rows = np.array(sc["arena"] + sc["obstacle"])
+    args = (len(sc["arena"]), len(sc["obstacle"]), rows, 50, np.array(sc["robot"]), 10, sc["lim"], Ly, 5, sc["end_points"][0], sc["end_points"][1])
+    refine_rounds(3)
+    ref = oracle.plan2d(*args, per_orientation=per_orientation)
+    got = hostlib.plan2d(*args, per_orientation=per_orientation, precision=capi.F64_STRICT)
+    assert ref["refine_rounds"] == 3 and got["refine_rounds"] == 3
+    assert np.array_equal(got["vertex"], ref["vertex"])
+    assert np.array_equal(got["edge"], ref["edge"])
+    assert got["solved"] == ref["solved"]

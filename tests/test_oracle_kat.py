@@ -283,3 +283,26 @@ def test_prob_hrm3d_home_snake_needs_several_slices(oracle):
     joints = np.unique(res["vertex"][:, 7:], axis=0)
     assert len(joints) == res["slices"]  # one joint configuration per slice
     assert np.all(np.abs(joints) <= np.pi / 2 + 1e-6)
+
+
+def test_refinement_solves_when_first_roadmap_does_not(oracle):
+    """HighwayRoadMap::plan refines (doubled sweep lines on the cached C-boundaries, connectExistSlice) while unsolved.  The
+    reference itself throws here (interval tables keep their initial size, SURVEY.md finding 6); the restatement sizes them by
+    the current line count: 5 x 3 lines do not connect start and goal on the narrow map, the first refinement round does."""
+    sc = util.scenes()["3D_superquadrics_narrow_rabbit"]
+    rows = np.array(sc["arena"] + sc["obstacle"])
+    args = (1, len(sc["obstacle"]), rows, 10, np.array(sc["robot"]), np.array(sc["quats"]), sc["lim"], 5, 3, 5, sc["end_points"][0],
+            sc["end_points"][1])
+    try:
+        oracle.set_max_refine(0)
+        first = oracle.plan3d(*args)
+        oracle.set_max_refine(2)
+        refined = oracle.plan3d(*args)
+    finally:
+        oracle.set_max_refine(0)
+    assert not first["solved"] and first["refine_rounds"] == 0
+    assert refined["solved"] and refined["refine_rounds"] == 1
+    nv = len(first["vertex"])
+    assert np.array_equal(refined["vertex"][:nv], first["vertex"])  # the first roadmap is kept, refinement only appends
+    assert np.array_equal(refined["edge"][: len(first["edge"])], first["edge"])
+    assert len(refined["vertex"]) > nv
