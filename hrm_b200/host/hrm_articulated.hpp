@@ -228,7 +228,7 @@ class ProbHRM3D : public HRM3D {
             res_.solutionPath.solvedPath.push_back(start_);
             for (Index id : res_.solutionPath.PathId) res_.solutionPath.solvedPath.push_back(res_.graphStructure.vertex.at(id));
             res_.solutionPath.solvedPath.push_back(goal_);
-            res_.solutionPath.interpolatedPath = res_.solutionPath.solvedPath;
+            res_.solutionPath.interpolatedPath = getInterpolatedSolutionPath(param_.numPoint);
         }
     }
 

@@ -516,7 +516,8 @@ struct Graph {  // include/hrm/planners/PlanningResult.h:14-23
 struct SolutionPathInfo {  // :26-38
     std::vector<Index> PathId;
     std::vector<std::vector<Coordinate>> solvedPath, interpolatedPath;
-    double cost = 0;
+    double cost = 0;             // sum of the Euclidean lengths of the path's edges
+    double costAsReference = 0;  // what the reference accumulates: edge weights indexed by VERTEX id
 };
 struct Time {  // :41-50
     double buildTime = 0, searchTime = 0, totalTime = 0;
@@ -593,9 +594,11 @@ class HighwayRoadMapBase {
             res_.solutionPath.solvedPath.push_back(start_);
             for (Index id : res_.solutionPath.PathId) res_.solutionPath.solvedPath.push_back(res_.graphStructure.vertex.at(id));
             res_.solutionPath.solvedPath.push_back(goal_);
-            res_.solutionPath.interpolatedPath = res_.solutionPath.solvedPath;
+            res_.solutionPath.interpolatedPath = getInterpolatedSolutionPath(param_.numPoint);
         }
     }
+    /** HighwayRoadMap-inl.h:284-291: the solved path itself (HRM3D overrides) */
+    virtual std::vector<std::vector<Coordinate>> getInterpolatedSolutionPath(Index /*num*/) { return res_.solutionPath.solvedPath; }
     const PlanningResult& getPlanningResult() const { return res_; }
     const PlannerParameter& getPlannerParameters() const { return param_; }
     long numEdgeTests() const { return numEdgeTests_; }
@@ -620,11 +623,12 @@ class HighwayRoadMapBase {
                 if (astar(g, s, t, p)) {
                     auto& sp = res_.solutionPath;
                     sp.PathId.clear();
-                    sp.cost = 0;
+                    sp.cost = 0, sp.costAsReference = 0;
                     Index cur = t;
                     sp.PathId.push_back(cur);
                     while (cur != s) {
                         sp.cost += vectorEuclidean(g.vertex[cur], g.vertex[p[cur]]);
+                        if (cur < g.weight.size()) sp.costAsReference += g.weight[cur];  // HighwayRoadMap-inl.h:155-157
                         cur = p[cur];
                         sp.PathId.push_back(cur);
                     }
@@ -706,6 +710,28 @@ class HRM3D : public HighwayRoadMapBase {
         param_.numSlice = q_.size();
     }
     FreeSpaceGPU3D& freeSpace() { return freeSpace_; }
+
+    /** HRM3D.cpp:272-299: about `num` interpolated poses per unit of average edge length along the solved path.  The step
+     * length uses the geometric path cost (the reference divides its vertex-indexed cost, App. C11); a segment shorter than one
+     * step contributes its two end poses (the reference interpolates with 1/0 there). */
+    std::vector<std::vector<Coordinate>> getInterpolatedSolutionPath(Index num) override {
+        const auto& sp = res_.solutionPath.solvedPath;
+        std::vector<std::vector<Coordinate>> out;
+        if (sp.size() < 2 || num == 0) return sp;
+        double length = 0.0;
+        for (size_t i = 0; i + 1 < sp.size(); ++i) length += vectorEuclidean(sp[i], sp[i + 1]);
+        const double distanceStep = length / (static_cast<double>(num) * (static_cast<double>(sp.size()) - 1.0));
+        for (size_t i = 0; i + 1 < sp.size(); ++i) {
+            const int numStep = distanceStep > 0.0 ? static_cast<int>(vectorEuclidean(sp[i], sp[i + 1]) / distanceStep) : 0;
+            if (numStep <= 0) {
+                out.push_back(sp[i]), out.push_back(sp[i + 1]);
+                continue;
+            }
+            const auto step = interpolateCompoundSE3Rn(sp[i], sp[i + 1], static_cast<Index>(numStep));
+            out.insert(out.end(), step.begin(), step.end());
+        }
+        return out;
+    }
 
   protected:
     void buildRoadmap() override {

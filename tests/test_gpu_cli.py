@@ -79,6 +79,12 @@ def test_bench_hrm3d_cli(oracle, name, tmp_path):
     assert np.array_equal(E, ref["edge"])
     ids = [int(v) for v in (out / "details" / "path_id_hrm_3D.csv").read_text().rstrip(",").split(",") if v]
     assert ids == [int(v) for v in ref["path"]]
+    if ref["solved"]:  # HRM3D::getInterpolatedSolutionPath: start, path vertices, goal, densified
+        sol = (out / "details" / "solution_path_hrm_3D.csv").read_text().strip().split("\n")
+        ip = (out / "details" / "interpolated_path_hrm_3D.csv").read_text().strip().split("\n")
+        assert len(sol) == len(ids) + 2 and len(ip) >= len(sol)
+        assert all(len(l.rstrip(",").split(",")) == 7 for l in ip)
+        assert ip[0] == sol[0] and ip[-1] == sol[-1]
     seg = (out / "details" / "segment_hrm_3D.csv").read_text().strip().split("\n")
     assert len(seg) > 0 and all(len(l.split(",")) == 5 for l in seg)
     bound = (out / "details" / "mink_bound_hrm_3D.csv").read_text().rstrip("\n").split("\n")
