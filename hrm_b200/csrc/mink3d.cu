@@ -142,7 +142,13 @@ struct alignas(2 * sizeof(Real)) Real2 {
     Real a, b;
 };
 
-constexpr int kColStride = 30;  // Reals per column in the constant table: 3 groups (U, W, P) of 9 values + 1 pad
+// Fast modes split every boundary term into a row (omega) factor and a column (eta) factor:
+//   x0 - off = ce1_c * V_r + C_c,   V_r = R1[:,0] a cw1_r + R1[:,1] b sw1_r,        C_c = R1[:,2] c se1_c + (p - off)
+//   u        = ce2_c * U_r + UZ_c,  U_r = M1[:,0] cw2_r / a + M1[:,1] sw2_r / b,    UZ_c = M1[:,2] se2_c / c
+//   w        = ce2_c * W_r + WZ_c,  W_r, WZ_c likewise with M2
+// so a point costs 9 FMAs + the normalisation instead of 18.  A thread keeps V, U, W of its rows in registers; the column
+// table holds {ce1, ce2, C, UZ, WZ} (11 values + pad), the 18 row-base coefficients live in `rowb`.
+constexpr int kColStride = 12;
 
 template <int MODE, bool SWEEP, bool CODE8>
 __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k_minksweep3d(const MinkParams p) {
@@ -186,6 +192,7 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
     // ---- shared memory carve-up (every region 16-byte aligned) ------------------------------
     Real* tab = reinterpret_cast<Real*>(smem_raw);                             // [8][n]
     double* mats = reinterpret_cast<double*>(smem_raw + p.o_mats);             // M1[9] M2[9] + scratch T[9] KTT[9]
+    Real* rowb = reinterpret_cast<Real*>(mats + 36);                           // RA[3] RB[3] UA[3] UB[3] WA[3] WB[3]
     Real* cc = reinterpret_cast<Real*>(smem_raw + p.o_cc);                     // [n][kColStride] per-column constants (fast modes)
     double* txs = reinterpret_cast<double*>(smem_raw + p.o_txs);               // [Lx+2]
     double* tys = reinterpret_cast<double*>(smem_raw + p.o_tys);               // [Ly+2]
@@ -299,32 +306,31 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
 
     __syncthreads();
     if constexpr (MODE != HRMGPU_F64_STRICT) {
-        // per-column constants: group U = M1 * diag(ga, gb, gc), group W = M2 * diag(..), group P = R1 * diag(A, B, Z) + shift.
-        // Two threads per column: the first writes U and W (18 values), the second P (9 values).
+        // column table and row-base coefficients.  Two threads per column: the even one writes {ce2, UZ, WZ}, the odd one
+        // {ce1, C}; the first six threads also write the row base.
         const int part = tid & 1;
+        if (tid < 6) {
+            const int d = tid >> 1;
+            if (part) {
+                rowb[d] = Real(pre_R[d] * pre_a), rowb[3 + d] = Real(pre_R[3 + d] * pre_b);
+            } else {
+                rowb[6 + d] = Real(mats[3 * d] * pre_ia), rowb[9 + d] = Real(mats[3 * d + 1] * pre_ib);
+                rowb[12 + d] = Real(mats[9 + 3 * d] * pre_ia), rowb[15 + d] = Real(mats[9 + 3 * d + 1] * pre_ib);
+            }
+        }
         for (int c = tid >> 1; c < n; c += kThreads >> 1) {
-            const Real ce1 = tab[c], se1 = tab[n + c], ce2 = tab[2 * n + c], se2 = tab[3 * n + c];
             Real* k = cc + c * kColStride;
             if (part == 0) {
-                const Real ga = ce2 * Real(pre_ia), gb = ce2 * Real(pre_ib), gc = se2 * Real(pre_ic);
+                const Real ce2 = tab[2 * n + c], gz = tab[3 * n + c] * Real(pre_ic);  // se2 / c
+                k[1] = ce2;
 #pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    k[i] = Real(mats[3 * i]) * ga;
-                    k[3 + i] = Real(mats[3 * i + 1]) * gb;
-                    k[6 + i] = Real(mats[3 * i + 2]) * gc;
-                    k[10 + i] = Real(mats[9 + 3 * i]) * ga;
-                    k[13 + i] = Real(mats[9 + 3 * i + 1]) * gb;
-                    k[16 + i] = Real(mats[9 + 3 * i + 2]) * gc;
-                }
+                for (int i = 0; i < 3; ++i) k[5 + i] = Real(mats[3 * i + 2]) * gz, k[8 + i] = Real(mats[9 + 3 * i + 2]) * gz;
             } else {
-                const Real Ac = Real(pre_a) * ce1, Bc = Real(pre_b) * ce1, Zc = Real(pre_c) * se1;
+                const Real ce1 = tab[c], Zc = Real(pre_c) * tab[n + c];  // c * se1
                 const Real tr[3] = {Real(pre_px - offx), Real(pre_py - offy), Real(pre_pz - offz)};
+                k[0] = ce1;
 #pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    k[20 + i] = Real(pre_R[i]) * Ac;
-                    k[23 + i] = Real(pre_R[3 + i]) * Bc;
-                    k[26 + i] = Real(pre_R[6 + i]) * Zc + tr[i];
-                }
+                for (int i = 0; i < 3; ++i) k[2 + i] = Real(pre_R[6 + i]) * Zc + tr[i];
             }
         }
         __syncthreads();
@@ -398,52 +404,40 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
                 const uint32_t lx2 = static_cast<uint32_t>(p.Lx) * 0x00010001u, ly2 = static_cast<uint32_t>(p.Ly) * 0x00010001u;
                 for (int h = 0; h < npass; ++h) {
                     const int r0 = 2 * (ln + h * p.lpc);
-                    Real cw1[2], sw1[2], cw2[2], sw2[2];
-                    lds_pair(smem_u32(tab + 4 * n + r0), cw1[0], cw1[1]);
-                    lds_pair(smem_u32(tab + 5 * n + r0), sw1[0], sw1[1]);
-                    lds_pair(smem_u32(tab + 6 * n + r0), cw2[0], cw2[1]);
-                    lds_pair(smem_u32(tab + 7 * n + r0), sw2[0], sw2[1]);
+                    Real V[2][3], U[2][3], W[2][3];  // row factors of the two rows (see kColStride)
+                    {
+                        Real cw1[2], sw1[2], cw2[2], sw2[2];
+                        lds_pair(smem_u32(tab + 4 * n + r0), cw1[0], cw1[1]);
+                        lds_pair(smem_u32(tab + 5 * n + r0), sw1[0], sw1[1]);
+                        lds_pair(smem_u32(tab + 6 * n + r0), cw2[0], cw2[1]);
+                        lds_pair(smem_u32(tab + 7 * n + r0), sw2[0], sw2[1]);
+#pragma unroll
+                        for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+                            for (int d = 0; d < 3; ++d) {
+                                V[h2][d] = rowb[d] * cw1[h2] + rowb[3 + d] * sw1[h2];
+                                U[h2][d] = rowb[6 + d] * cw2[h2] + rowb[9 + d] * sw2[h2];
+                                W[h2][d] = rowb[12 + d] * cw2[h2] + rowb[15 + d] * sw2[h2];
+                            }
+                    }
                     uint32_t ca = smem_u32(cc) + static_cast<uint32_t>(grp * kColStride * sizeof(Real));
                     uint32_t va = smem_u32(vcode) + static_cast<uint32_t>((grp * n + r0) * sizeof(Code));
                     Real* gx = mx + grp * n + r0;
                     for (int c = grp; c < n; c += p.groups, ca += cc_step, va += v_step, gx += g_step) {
-                        Real o[2][3], inv[2];
-                        {
-                            Real U[10];
+                        Real k[12];  // ce1, ce2, C[3], UZ[3], WZ[3], pad
 #pragma unroll
-                            for (int i = 0; i < 5; ++i) lds_pair(ca + i * 2 * sizeof(Real), U[2 * i], U[2 * i + 1]);
+                        for (int i = 0; i < 6; ++i) lds_pair(ca + i * 2 * sizeof(Real), k[2 * i], k[2 * i + 1]);
+                        Real o[2][3];
 #pragma unroll
-                            for (int h2 = 0; h2 < 2; ++h2) {
-                                const Real ux = U[0] * cw2[h2] + (U[3] * sw2[h2] + U[6]);
-                                const Real uy = U[1] * cw2[h2] + (U[4] * sw2[h2] + U[7]);
-                                const Real uz = U[2] * cw2[h2] + (U[5] * sw2[h2] + U[8]);
-                                if constexpr (MODE == HRMGPU_F32)
-                                    inv[h2] = rsqrtf(ux * ux + uy * uy + uz * uz);
-                                else
-                                    inv[h2] = fast_rsqrt(ux * ux + uy * uy + uz * uz);
-                            }
-                        }
-                        {
-                            Real P[10];
+                        for (int h2 = 0; h2 < 2; ++h2) {
+                            const Real ux = k[1] * U[h2][0] + k[5], uy = k[1] * U[h2][1] + k[6], uz = k[1] * U[h2][2] + k[7];
+                            Real inv;
+                            if constexpr (MODE == HRMGPU_F32)
+                                inv = rsqrtf(ux * ux + uy * uy + uz * uz);
+                            else
+                                inv = fast_rsqrt(ux * ux + uy * uy + uz * uz);
 #pragma unroll
-                            for (int i = 0; i < 5; ++i) lds_pair(ca + (20 + 2 * i) * sizeof(Real), P[2 * i], P[2 * i + 1]);
-#pragma unroll
-                            for (int h2 = 0; h2 < 2; ++h2) {
-                                o[h2][0] = P[0] * cw1[h2] + (P[3] * sw1[h2] + P[6]);
-                                o[h2][1] = P[1] * cw1[h2] + (P[4] * sw1[h2] + P[7]);
-                                o[h2][2] = P[2] * cw1[h2] + (P[5] * sw1[h2] + P[8]);
-                            }
-                        }
-                        {
-                            Real W[10];
-#pragma unroll
-                            for (int i = 0; i < 5; ++i) lds_pair(ca + (10 + 2 * i) * sizeof(Real), W[2 * i], W[2 * i + 1]);
-#pragma unroll
-                            for (int h2 = 0; h2 < 2; ++h2) {
-                                o[h2][0] = (W[0] * cw2[h2] + (W[3] * sw2[h2] + W[6])) * inv[h2] + o[h2][0];
-                                o[h2][1] = (W[1] * cw2[h2] + (W[4] * sw2[h2] + W[7])) * inv[h2] + o[h2][1];
-                                o[h2][2] = (W[2] * cw2[h2] + (W[5] * sw2[h2] + W[8])) * inv[h2] + o[h2][2];
-                            }
+                            for (int d = 0; d < 3; ++d) o[h2][d] = (k[1] * W[h2][d] + k[8 + d]) * inv + (k[0] * V[h2][d] + k[2 + d]);
                         }
                         *reinterpret_cast<R2*>(gx) = R2{o[0][0], o[1][0]};
                         *reinterpret_cast<R2*>(gx + M) = R2{o[0][1], o[1][1]};
@@ -478,64 +472,41 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
             for (int h0 = 0; h0 < nh; h0 += kRows) {
                 int rr[kRows];
                 bool rvalid[kRows];
-                Real cw1[kRows], sw1[kRows], cw2[kRows], sw2[kRows];
+                Real V[kRows][3], U[kRows][3], W[kRows][3];  // row factors (see kColStride)
 #pragma unroll
                 for (int h = 0; h < kRows; ++h) {
                     const int r = ln + (h0 + h) * p.lpc;
                     rvalid[h] = r < n;
                     rr[h] = rvalid[h] ? r : ln;  // rows past the end compute the thread's first row again and store nothing
-                    cw1[h] = tab[4 * n + rr[h]], sw1[h] = tab[5 * n + rr[h]], cw2[h] = tab[6 * n + rr[h]], sw2[h] = tab[7 * n + rr[h]];
+                    const Real cw1 = tab[4 * n + rr[h]], sw1 = tab[5 * n + rr[h]], cw2 = tab[6 * n + rr[h]], sw2 = tab[7 * n + rr[h]];
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        V[h][d] = rowb[d] * cw1 + rowb[3 + d] * sw1;
+                        U[h][d] = rowb[6 + d] * cw2 + rowb[9 + d] * sw2;
+                        W[h][d] = rowb[12 + d] * cw2 + rowb[15 + d] * sw2;
+                    }
                 }
                 int koff = grp * n;  // c * n
                 const int kstep = p.groups * n;
                 for (int c = grp; c < n; c += p.groups, koff += kstep) {
                     const R2* k2 = reinterpret_cast<const R2*>(cc + c * kColStride);
-                    Real o[kRows][3], inv[kRows];
-                    {
-                        Real U[10];
+                    Real k[12];  // ce1, ce2, C[3], UZ[3], WZ[3], pad
 #pragma unroll
-                        for (int i = 0; i < 5; ++i) {
-                            const R2 v = k2[i];
-                            U[2 * i] = v.a, U[2 * i + 1] = v.b;
-                        }
-#pragma unroll
-                        for (int h = 0; h < kRows; ++h) {
-                            const Real ux = U[0] * cw2[h] + (U[3] * sw2[h] + U[6]);
-                            const Real uy = U[1] * cw2[h] + (U[4] * sw2[h] + U[7]);
-                            const Real uz = U[2] * cw2[h] + (U[5] * sw2[h] + U[8]);
-                            if constexpr (MODE == HRMGPU_F32)
-                                inv[h] = rsqrtf(ux * ux + uy * uy + uz * uz);
-                            else
-                                inv[h] = fast_rsqrt(ux * ux + uy * uy + uz * uz);
-                        }
+                    for (int i = 0; i < 6; ++i) {
+                        const R2 v = k2[i];
+                        k[2 * i] = v.a, k[2 * i + 1] = v.b;
                     }
-                    {
-                        Real P[10];
+                    Real o[kRows][3];
 #pragma unroll
-                        for (int i = 0; i < 5; ++i) {
-                            const R2 v = k2[10 + i];
-                            P[2 * i] = v.a, P[2 * i + 1] = v.b;
-                        }
+                    for (int h = 0; h < kRows; ++h) {
+                        const Real ux = k[1] * U[h][0] + k[5], uy = k[1] * U[h][1] + k[6], uz = k[1] * U[h][2] + k[7];
+                        Real inv;
+                        if constexpr (MODE == HRMGPU_F32)
+                            inv = rsqrtf(ux * ux + uy * uy + uz * uz);
+                        else
+                            inv = fast_rsqrt(ux * ux + uy * uy + uz * uz);
 #pragma unroll
-                        for (int h = 0; h < kRows; ++h) {
-                            o[h][0] = P[0] * cw1[h] + (P[3] * sw1[h] + P[6]);
-                            o[h][1] = P[1] * cw1[h] + (P[4] * sw1[h] + P[7]);
-                            o[h][2] = P[2] * cw1[h] + (P[5] * sw1[h] + P[8]);
-                        }
-                    }
-                    {
-                        Real W[10];
-#pragma unroll
-                        for (int i = 0; i < 5; ++i) {
-                            const R2 v = k2[5 + i];
-                            W[2 * i] = v.a, W[2 * i + 1] = v.b;
-                        }
-#pragma unroll
-                        for (int h = 0; h < kRows; ++h) {
-                            o[h][0] = (W[0] * cw2[h] + (W[3] * sw2[h] + W[6])) * inv[h] + o[h][0];
-                            o[h][1] = (W[1] * cw2[h] + (W[4] * sw2[h] + W[7])) * inv[h] + o[h][1];
-                            o[h][2] = (W[2] * cw2[h] + (W[5] * sw2[h] + W[8])) * inv[h] + o[h][2];
-                        }
+                        for (int d = 0; d < 3; ++d) o[h][d] = (k[1] * W[h][d] + k[8 + d]) * inv + (k[0] * V[h][d] + k[2 + d]);
                     }
                     uint32_t cx[kRows], cy[kRows];
                     bool all_ok = true;
@@ -866,7 +837,7 @@ static size_t smem_layout(MinkParams& p, int MODE, bool sweep, bool code8, int n
     const size_t real = (MODE == HRMGPU_F32) ? 4 : 8;
     auto al = [](size_t v) { return (v + 15) & ~size_t(15); };
     size_t b = al(real * 8 * n);  // tab
-    p.o_mats = static_cast<int>(b), b += sizeof(double) * 36;
+    p.o_mats = static_cast<int>(b), b += sizeof(double) * (36 + 18);  // + 18 row-base coefficients (fast modes)
     p.o_cc = static_cast<int>(b);
     if (MODE != HRMGPU_F64_STRICT) b += al(real * kColStride * n);
     p.o_txs = static_cast<int>(b), p.o_tys = static_cast<int>(b + (sweep ? sizeof(double) * (Lx + 2) : 0));
