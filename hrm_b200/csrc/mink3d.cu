@@ -307,15 +307,17 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k
     __syncthreads();
     if constexpr (MODE != HRMGPU_F64_STRICT) {
         // column table and row-base coefficients.  Two threads per column: the even one writes {ce2, UZ, WZ}, the odd one
-        // {ce1, C}; the first six threads also write the row base.
+        // {ce1, C}; the first two threads also write the row base.
         const int part = tid & 1;
-        if (tid < 6) {
-            const int d = tid >> 1;
-            if (part) {
-                rowb[d] = Real(pre_R[d] * pre_a), rowb[3 + d] = Real(pre_R[3 + d] * pre_b);
-            } else {
-                rowb[6 + d] = Real(mats[3 * d] * pre_ia), rowb[9 + d] = Real(mats[3 * d + 1] * pre_ib);
-                rowb[12 + d] = Real(mats[9 + 3 * d] * pre_ia), rowb[15 + d] = Real(mats[9 + 3 * d + 1] * pre_ib);
+        if (tid < 2) {  // (static indices only: pre_R must stay in registers)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                if (part) {
+                    rowb[d] = Real(pre_R[d] * pre_a), rowb[3 + d] = Real(pre_R[3 + d] * pre_b);
+                } else {
+                    rowb[6 + d] = Real(mats[3 * d] * pre_ia), rowb[9 + d] = Real(mats[3 * d + 1] * pre_ib);
+                    rowb[12 + d] = Real(mats[9 + 3 * d] * pre_ia), rowb[15 + d] = Real(mats[9 + 3 * d + 1] * pre_ib);
+                }
             }
         }
         for (int c = tid >> 1; c < n; c += kThreads >> 1) {
