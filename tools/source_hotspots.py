@@ -48,10 +48,10 @@ for k in keys:
 
 # phase roll-up for hrm_b200/csrc/mink3d.cu (+ device helpers): edit the ranges when the kernel moves
 if len(sys.argv) > 3 and sys.argv[3] == "phases":
-    ranges = [("line-code helpers (phase A)", "mink3d.cu", 1, 146), ("entry + smem carve-up", "mink3d.cu", 147, 203),
-              ("prologue", "mink3d.cu", 204, 315), ("phase A", "mink3d.cu", 316, 560), ("face load/test lambdas (drain)", "mink3d.cu", 561, 587),
-              ("scan B1 (face tests)", "mink3d.cu", 588, 641), ("scan B2 (expansion + queue)", "mink3d.cu", 642, 761),
-              ("drain", "mink3d.cu", 762, 781), ("commit", "mink3d.cu", 782, 807), ("phase D", "mink3d.cu", 808, 900),
+    ranges = [("line-code helpers (phase A)", "mink3d.cu", 1, 153), ("entry + smem carve-up + reload", "mink3d.cu", 154, 234),
+              ("prologue", "mink3d.cu", 235, 341), ("phase A", "mink3d.cu", 342, 552), ("face load/test lambdas (drain)", "mink3d.cu", 553, 579),
+              ("scan B1 (face tests)", "mink3d.cu", 580, 633), ("scan B2 (expansion + queue)", "mink3d.cu", 634, 753),
+              ("drain", "mink3d.cu", 754, 773), ("commit", "mink3d.cu", 774, 799), ("phase D", "mink3d.cu", 800, 900),
               ("rsqrt (phase A)", "devmath.cuh", 30, 50), ("triangle test (drain)", "devmath.cuh", 51, 129),
               ("face_vertices / insert (drain)", "devmath.cuh", 130, 200)]
     print("\nphase roll-up: share of warp instructions / of stall samples, top stall reasons")
