@@ -53,6 +53,9 @@ def load():
         "hrmgpu_get_segments_all": (i, [vp, vp, vp, vp, vp, ll]),
         "hrmgpu_get_single_hit_count": (i, [vp, vp]),
         "hrmgpu_test_edges": (i, [vp, i, i, vp, vp, vp]),
+        "hrmgpu_test_edges_multi": (i, [vp, i, vp, vp, vp, vp]),
+        "hrmgpu_test_bridge_multi": (i, [vp, i, vp, vp, vp]),
+        "hrmgpu_test_transitions": (i, [vp, i, vp, vp, vp, i, vp, vp, vp, vp]),
         "hrmgpu_build_bridge": (i, [vp, i, i, vp, vp, i]),
         "hrmgpu_build_bridge2d": (i, [vp, i, i, vp, vp, i]),
         "hrmgpu_test_bridge": (i, [vp, i, i, vp, vp]),
@@ -209,6 +212,18 @@ class Context:
             self._chk(self.lib.hrmgpu_test_edges(self.h, k, v1.shape[0], _p(v1), _p(v2), _p(out)))
         return out.astype(bool)
 
+    def test_edges_multi(self, layer, v1, v2):
+        """Edge e against the C-obstacles of layer layer[e]; one launch for all layers."""
+        d = self.dims()
+        v1 = _d(v1).reshape(-1, d["dim"])
+        v2 = _d(v2).reshape(-1, d["dim"])
+        layer = np.ascontiguousarray(layer, dtype=np.int32)
+        assert layer.shape[0] == v1.shape[0]
+        out = np.zeros(v1.shape[0], dtype=np.uint8)
+        if v1.shape[0]:
+            self._chk(self.lib.hrmgpu_test_edges_multi(self.h, v1.shape[0], _p(layer), _p(v1), _p(v2), _p(out)))
+        return out.astype(bool)
+
     def build_bridge(self, tfe_semi, tfe_R, precision=F64_STRICT):
         tfe_semi = _d(tfe_semi)
         P, B = tfe_semi.shape[0], tfe_semi.shape[1]
@@ -227,6 +242,27 @@ class Context:
         out = np.zeros(Q, dtype=np.uint8)
         if Q:
             self._chk(self.lib.hrmgpu_test_bridge(self.h, p, Q, _p(centres), _p(out)))
+        return out.astype(bool)
+
+    def test_bridge_multi(self, pair, centres):
+        """Pose q against the bridge layer of pair pair[q]; one launch for all pairs."""
+        centres = _d(centres)
+        pair = np.ascontiguousarray(pair, dtype=np.int32)
+        Q = centres.shape[0]
+        assert pair.shape[0] == Q
+        out = np.zeros(Q, dtype=np.uint8)
+        if Q:
+            self._chk(self.lib.hrmgpu_test_bridge_multi(self.h, Q, _p(pair), _p(centres), _p(out)))
+        return out.astype(bool)
+
+    def test_transitions(self, pair, v0, v1, w0, w1, link_off):
+        """isMultiSliceTransitionFree for candidate vertex pairs, interpolation on the device (see include/hrmgpu.h)."""
+        pair = np.ascontiguousarray(pair, dtype=np.int32)
+        v0, v1, w0, w1, link_off = _d(v0), _d(v1), _d(w0), _d(w1), _d(link_off)
+        Cn = pair.shape[0]
+        out = np.zeros(Cn, dtype=np.uint8)
+        if Cn:
+            self._chk(self.lib.hrmgpu_test_transitions(self.h, Cn, _p(pair), _p(v0), _p(v1), w0.shape[0], _p(w0), _p(w1), _p(link_off), _p(out)))
         return out.astype(bool)
 
     def pack_segments_dev(self, d_ptr=None, cap_bytes=0):

@@ -144,6 +144,10 @@ void hrmgpu_destroy(hrmgpu_ctx* c) {
     release(c->q_out);
     release(c->bbox);
     release(c->q_flag);
+    release(c->q_set);
+    release(c->q_w);
+    release(c->q_loff);
+    release(c->bridge_bbox);
     release(c->bridge_semi);
     release(c->bridge_R);
     release(c->bridge_off);
@@ -412,6 +416,26 @@ int hrmgpu_test_edges(hrmgpu_ctx* c, int k, int E, const double* v1, const doubl
     return HRMGPU_OK;
 }
 
+int hrmgpu_test_edges_multi(hrmgpu_ctx* c, int E, const int* layer, const double* v1, const double* v2, unsigned char* free_out) {
+    if (!c) return HRMGPU_E_ARG;
+    int rc = check_built(c, 0);
+    if (rc) return rc;
+    if (E < 0 || (E > 0 && (!layer || !v1 || !v2 || !free_out))) return fail(c, HRMGPU_E_ARG, "test_edges_multi: bad arguments");
+    if (E == 0) return HRMGPU_OK;
+    for (int e = 0; e < E; ++e)
+        if (layer[e] < 0 || layer[e] >= c->K) return fail(c, HRMGPU_E_ARG, "test_edges_multi: layer index out of range");
+    HRMGPU_CUDA(c, cudaSetDevice(c->device));
+    const size_t cnt = static_cast<size_t>(E) * c->dim;
+    if ((rc = upload(c, c->q_a, v1, cnt))) return rc;
+    if ((rc = upload(c, c->q_b, v2, cnt))) return rc;
+    if ((rc = upload(c, c->q_set, layer, static_cast<size_t>(E)))) return rc;
+    if ((rc = ensure(c, c->q_out, static_cast<size_t>(E)))) return rc;
+    if ((rc = launch_edges(c, -1, E, c->q_a.p, c->q_b.p, c->q_out.p, c->q_set.p))) return rc;
+    HRMGPU_CUDA(c, cudaMemcpyAsync(free_out, c->q_out.p, static_cast<size_t>(E), cudaMemcpyDeviceToHost, c->stream));
+    HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));
+    return HRMGPU_OK;
+}
+
 static int build_bridge_common(hrmgpu_ctx* c, int P, int B, const double* semi, const double* rot, int precision, int dim) {
     if (!c) return HRMGPU_E_ARG;
     if (c->dim != dim) return fail(c, HRMGPU_E_STATE, "build_bridge: scene dimension mismatch");
@@ -445,10 +469,11 @@ static int build_bridge_common(hrmgpu_ctx* c, int P, int B, const double* semi, 
                                     c->bridge_R.p + static_cast<size_t>(pi) * B * 2, c->bridge_off.p, precision, mesh, nullptr, nullptr, false);
         if (rc) return rc;
     }
-    HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));
     c->P = P;
     c->bridge_B = B;
     c->bridge_prec = precision;
+    if ((rc = launch_bridge_bbox(c))) return rc;
+    HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));
     c->bridge_built = true;
     return HRMGPU_OK;
 }
@@ -473,6 +498,50 @@ int hrmgpu_test_bridge(hrmgpu_ctx* c, int p, int Q, const double* centres, unsig
     if ((rc = launch_bridge_test(c, p, Q, c->q_a.p, c->q_out.p))) return rc;
     HRMGPU_CUDA(c, cudaMemcpyAsync(free_out, c->q_out.p, static_cast<size_t>(Q), cudaMemcpyDeviceToHost, c->stream));
     HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));
+    return HRMGPU_OK;
+}
+
+int hrmgpu_test_bridge_multi(hrmgpu_ctx* c, int Q, const int* pair, const double* centres, unsigned char* free_out) {
+    if (!c) return HRMGPU_E_ARG;
+    if (!c->bridge_built) return fail(c, HRMGPU_E_STATE, "test_bridge_multi: no bridge layers built");
+    if (Q < 0 || (Q > 0 && (!pair || !centres || !free_out))) return fail(c, HRMGPU_E_ARG, "test_bridge_multi: bad arguments");
+    if (Q == 0) return HRMGPU_OK;
+    for (int q = 0; q < Q; ++q)
+        if (pair[q] < 0 || pair[q] >= c->P) return fail(c, HRMGPU_E_ARG, "test_bridge_multi: pair index out of range");
+    HRMGPU_CUDA(c, cudaSetDevice(c->device));
+    int rc;
+    if ((rc = upload(c, c->q_a, centres, static_cast<size_t>(Q) * c->bridge_B * c->dim))) return rc;
+    if ((rc = upload(c, c->q_set, pair, static_cast<size_t>(Q)))) return rc;
+    if ((rc = ensure(c, c->q_out, static_cast<size_t>(Q)))) return rc;
+    if ((rc = launch_bridge_test(c, -1, Q, c->q_a.p, c->q_out.p, c->q_set.p))) return rc;
+    HRMGPU_CUDA(c, cudaMemcpyAsync(free_out, c->q_out.p, static_cast<size_t>(Q), cudaMemcpyDeviceToHost, c->stream));
+    HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));
+    return HRMGPU_OK;
+}
+
+int hrmgpu_test_transitions(hrmgpu_ctx* c, int C, const int* pair, const double* v0, const double* v1, int T, const double* w0,
+                            const double* w1, const double* link_off, unsigned char* free_out) {
+    if (!c) return HRMGPU_E_ARG;
+    if (!c->bridge_built) return fail(c, HRMGPU_E_STATE, "test_transitions: no bridge layers built");
+    if (C < 0 || T < 1 || (C > 0 && (!pair || !v0 || !v1 || !w0 || !w1 || !link_off || !free_out)))
+        return fail(c, HRMGPU_E_ARG, "test_transitions: bad arguments");
+    if (C == 0) return HRMGPU_OK;
+    for (int i = 0; i < C; ++i)
+        if (pair[i] < 0 || pair[i] >= c->P) return fail(c, HRMGPU_E_ARG, "test_transitions: pair index out of range");
+    HRMGPU_CUDA(c, cudaSetDevice(c->device));
+    int rc;
+    const size_t cnt = static_cast<size_t>(C) * c->dim;
+    if ((rc = upload(c, c->q_a, v0, cnt))) return rc;
+    if ((rc = upload(c, c->q_b, v1, cnt))) return rc;
+    if ((rc = upload(c, c->q_set, pair, static_cast<size_t>(C)))) return rc;
+    std::vector<double> w(2 * static_cast<size_t>(T));
+    for (int s = 0; s < T; ++s) w[s] = w0[s], w[T + s] = w1[s];
+    if ((rc = upload(c, c->q_w, w.data(), w.size()))) return rc;
+    if ((rc = upload(c, c->q_loff, link_off, static_cast<size_t>(c->P) * T * c->bridge_B * c->dim))) return rc;
+    if ((rc = ensure(c, c->q_out, static_cast<size_t>(C)))) return rc;
+    if ((rc = launch_transitions(c, C, T, c->q_set.p, c->q_a.p, c->q_b.p, c->q_w.p, c->q_w.p + T, c->q_loff.p, c->q_out.p))) return rc;
+    HRMGPU_CUDA(c, cudaMemcpyAsync(free_out, c->q_out.p, static_cast<size_t>(C), cudaMemcpyDeviceToHost, c->stream));
+    HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));  // (w is pageable host memory: its copy has completed when the call returns)
     return HRMGPU_OK;
 }
 
@@ -603,14 +672,6 @@ long long hrmgpu_debug_phase_times(hrmgpu_ctx* c, int enable, long long n_cta, l
     if (cudaSetDevice(c->device) != cudaSuccess) return HRMGPU_E_CUDA;
     if (!enable) {
         release(c->dbg);
-    release(c->q_a);
-    release(c->q_b);
-    release(c->q_out);
-    release(c->bbox);
-    release(c->q_flag);
-    release(c->bridge_semi);
-    release(c->bridge_R);
-    release(c->bridge_off);
         return 0;
     }
     if (out && c->dbg.p && c->dbg.n >= static_cast<size_t>(n_cta) * 8) {

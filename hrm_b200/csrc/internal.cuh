@@ -69,6 +69,7 @@ struct Ctx {
     DevBuf<unsigned char> q_out;                 // staged query results
     DevBuf<double> bbox;                         // [meshes][6] min/max per axis of the queried meshes
     DevBuf<unsigned int> q_flag;                 // per-query blocked flags
+    DevBuf<int> q_set;                           // multi-layer queries: layer / pair index of every query
     DevBuf<char> mesh;                           // [K][S][dim][M] planar, double (or float in F32 mode)
     DevBuf<double> ivl_lo, ivl_up;               // [K][S][L]
     int seg_fast_cap = 0;                        // test hook: list capacity of the 4-line segment pass (0 = default 256)
@@ -88,6 +89,8 @@ struct Ctx {
     bool bridge_built = false;
     DevBuf<char> bridge_mesh;  // [P][n_obs][B][dim][M]
     DevBuf<double> bridge_semi, bridge_R, bridge_off;
+    DevBuf<double> bridge_bbox;                  // [P][n_obs * B][6] (3D)
+    DevBuf<double> q_w, q_loff;                  // transition tests: interpolation weights [2][T], link offsets [P][T][B][dim]
 };
 
 #define HRMGPU_CUDA(ctx, expr)                                                                        \
@@ -124,7 +127,10 @@ int launch_minksweep3d(Ctx* c, int K, int B, int n_first_obj, int n_objs, const 
 int launch_minksweep2d(Ctx* c, int K, int B, int n_first_obj, int n_objs, const double* d_semi, const double* d_angle,
                        const double* d_off, int precision, char* d_mesh, double* d_lo, double* d_up, bool do_sweep, bool reload = false);
 int launch_segments(Ctx* c);
-int launch_edges(Ctx* c, int k, int E, const double* d_v1, const double* d_v2, unsigned char* d_out);
-int launch_bridge_test(Ctx* c, int p, int Q, const double* d_centres, unsigned char* d_out);
+int launch_edges(Ctx* c, int k, int E, const double* d_v1, const double* d_v2, unsigned char* d_out, const int* d_layer = nullptr);
+int launch_bridge_test(Ctx* c, int p, int Q, const double* d_centres, unsigned char* d_out, const int* d_pair = nullptr);
+int launch_bridge_bbox(Ctx* c);
+int launch_transitions(Ctx* c, int C, int T, const int* d_pair, const double* d_v0, const double* d_v1, const double* d_w0, const double* d_w1,
+                       const double* d_link_off, unsigned char* d_out);
 
 }  // namespace hrmgpu

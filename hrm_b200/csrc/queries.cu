@@ -16,9 +16,11 @@
 namespace hrmgpu {
 
 // min / max of every coordinate row of `count` meshes (planar [dim][M]): the reference's maxCoeff()/minCoeff().
+// Block b covers mesh (b % per_set) of set (b / per_set); consecutive sets are `set_stride` values apart.
 template <class Real>
-__global__ void k_mesh_bbox(const Real* mesh, int dim, int M, double* bbox) {
-    const Real* m = mesh + static_cast<size_t>(blockIdx.x) * dim * M;
+__global__ void k_mesh_bbox(const Real* mesh, int dim, int M, double* bbox, int per_set, size_t set_stride) {
+    const int set = blockIdx.x / per_set;
+    const Real* m = mesh + static_cast<size_t>(set) * set_stride + static_cast<size_t>(blockIdx.x - set * per_set) * dim * M;
     __shared__ double smin[3][32], smax[3][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int d = 0; d < dim; ++d) {
@@ -96,6 +98,8 @@ struct QueryParams {
     const double* b;       // edges: v2 [E][dim]
     unsigned int* flag;    // [n_query] set to 1 when blocked
     unsigned long long* counters;
+    const int* qset;       // multi-set calls: [n_query] mesh set (layer / layer pair) of every query; nullptr = set 0
+    size_t set_stride;     // values between the first meshes of consecutive sets
     int n, M, n_mesh, n_query, B, n_obs;
 };
 
@@ -114,13 +118,14 @@ __global__ void __launch_bounds__(128) k_edges3d(const QueryParams p) {
         const double s = A::sqrt(z);
         d.x = A::div(d.x, s), d.y = A::div(d.y, s), d.z = A::div(d.z, s);
     }
+    const int set = p.qset ? __ldg(p.qset + e) : 0;
     // LineIntersection.cpp:12-30: reject on the mesh bounding box only along (nearly) axis-parallel directions
-    const double* bb = p.bbox + static_cast<size_t>(m) * 6;
+    const double* bb = p.bbox + (static_cast<size_t>(set) * p.n_mesh + m) * 6;
     const double oc[3] = {t1.x, t1.y, t1.z}, dc[3] = {d.x, d.y, d.z};
 #pragma unroll
     for (int i = 0; i < 3; ++i)
         if (fabs(dc[i]) < 1e-6 && (oc[i] > bb[2 * i + 1] || oc[i] < bb[2 * i])) return;
-    const Real* mesh = reinterpret_cast<const Real*>(p.mesh) + static_cast<size_t>(m) * 3 * p.M;
+    const Real* mesh = reinterpret_cast<const Real*>(p.mesh) + static_cast<size_t>(set) * p.set_stride + static_cast<size_t>(m) * 3 * p.M;
     D3 h0, h1;
     const int cnt = warp_first_two_hits<A, Real, false>(mesh, p.n, p.M, t1, d, h0, h1);
     if (lane == 0) {
@@ -169,7 +174,8 @@ __global__ void __launch_bounds__(128) k_edges2d(const QueryParams p) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= p.n_query * p.n_mesh) return;
     const int e = t / p.n_mesh, m = t - e * p.n_mesh;
-    const double* sx = reinterpret_cast<const double*>(p.mesh) + static_cast<size_t>(m) * 2 * p.M;
+    const int set = p.qset ? __ldg(p.qset + e) : 0;
+    const double* sx = reinterpret_cast<const double*>(p.mesh) + static_cast<size_t>(set) * p.set_stride + static_cast<size_t>(m) * 2 * p.M;
     const double* sy = sx + p.M;
     const double px1 = p.a[2 * e], py1 = p.a[2 * e + 1], px2 = p.b[2 * e], py2 = p.b[2 * e + 1];
     double Am[2][2], b[2], sol[2];
@@ -202,7 +208,8 @@ __global__ void __launch_bounds__(128) k_bridge3d(const QueryParams p) {
     const double* v = p.a + (static_cast<size_t>(q) * p.B + b) * 3;
     const D3 org = {v[0], v[1], v[2]};
     const D3 dir = {0.0, 0.0, 1.0};
-    const Real* mesh = reinterpret_cast<const Real*>(p.mesh) + (static_cast<size_t>(o) * p.B + b) * 3 * p.M;
+    const int set = p.qset ? __ldg(p.qset + q) : 0;
+    const Real* mesh = reinterpret_cast<const Real*>(p.mesh) + static_cast<size_t>(set) * p.set_stride + (static_cast<size_t>(o) * p.B + b) * 3 * p.M;
     D3 h0, h1;
     const int cnt = warp_first_two_hits<A, Real, true>(mesh, p.n, p.M, org, dir, h0, h1);
     if (lane == 0) {
@@ -223,7 +230,8 @@ __global__ void __launch_bounds__(128) k_bridge2d(const QueryParams p) {
     const int q = t / per_q, rem = t - q * per_q;
     const int b = rem / p.n_obs, o = rem - b * p.n_obs;
     const double* v = p.a + (static_cast<size_t>(q) * p.B + b) * 2;
-    const double* sx = reinterpret_cast<const double*>(p.mesh) + (static_cast<size_t>(o) * p.B + b) * 2 * p.M;
+    const int set = p.qset ? __ldg(p.qset + q) : 0;
+    const double* sx = reinterpret_cast<const double*>(p.mesh) + static_cast<size_t>(set) * p.set_stride + (static_cast<size_t>(o) * p.B + b) * 2 * p.M;
     const double* sy = sx + p.M;
     const double ty = v[1];
     double h[2];
@@ -243,6 +251,120 @@ __global__ void __launch_bounds__(128) k_bridge2d(const QueryParams p) {
     }
 }
 
+// ---- K5 over candidate vertex pairs: isMultiSliceTransitionFree (HRM3D.cpp:367-392, HRM2D.cpp:235-265) -------------------
+// The robot moves from v0[c] to v1[c] in T interpolated poses.  Pose s has base centre t = w0[s]*v0 + w1[s]*v1 (two products,
+// one sum, each rounded, like InterpolateSE3.cpp:5-29 on the host) and body b > 0 sits at link_off[pair][s][b] + t
+// (MultiBodyTree3D.cpp:34-53: R_s * t_link + t; the interpolated rotation is the same for every candidate of a layer pair).
+// Work item = (candidate c, pose s, body b, obstacle o), o fastest.
+struct TransParams {
+    const void* mesh;        // bridge meshes [P][n_obs][B][dim][M]
+    const double* bbox;      // [P][n_obs * B][6] (3D)
+    const int* pair;         // [C]
+    const double* v0;        // [C][dim]
+    const double* v1;        // [C][dim]
+    const double* w0;        // [T]
+    const double* w1;        // [T]
+    const double* link_off;  // [P][T][B][dim]
+    unsigned int* flag;      // [C] set to 1 when some pose is blocked
+    unsigned long long* counters;
+    size_t set_stride;
+    long long items;         // C * T * B * n_obs
+    int n, M, C, T, B, n_obs;
+};
+
+// 3D: a warp takes 32 consecutive items.  Every lane forms its item's body centre and applies the mesh-level xy bounding-box
+// reject of intersectVerticalLineMesh3D (LineIntersection.cpp:60-67), which removes most (centre, obstacle) combinations;
+// the survivors are then walked by the whole warp one after the other (faces in order, first two hits).
+template <class A, class Real>
+__global__ void __launch_bounds__(128) k_transitions3d(const TransParams p) {
+    const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long item = warp_global * 32 + lane;
+    bool live = false;
+    int c = 0, set = 0, m = 0;
+    double ox = 0, oy = 0, oz = 0;
+    if (item < p.items) {
+        const int per_pose = p.B * p.n_obs;
+        const long long pose = item / per_pose;
+        const int rem = static_cast<int>(item - pose * per_pose);
+        const int b = rem / p.n_obs, o = rem - b * p.n_obs;
+        c = static_cast<int>(pose / p.T);
+        const int s = static_cast<int>(pose - static_cast<long long>(c) * p.T);
+        if (*reinterpret_cast<volatile unsigned int*>(p.flag + c) == 0u) {  // an earlier pose already blocked this candidate: nothing to add
+            set = __ldg(p.pair + c);
+            const double w0 = __ldg(p.w0 + s), w1 = __ldg(p.w1 + s);
+            const double* a0 = p.v0 + static_cast<size_t>(c) * 3;
+            const double* a1 = p.v1 + static_cast<size_t>(c) * 3;
+            ox = __dadd_rn(__dmul_rn(w0, __ldg(a0)), __dmul_rn(w1, __ldg(a1)));
+            oy = __dadd_rn(__dmul_rn(w0, __ldg(a0 + 1)), __dmul_rn(w1, __ldg(a1 + 1)));
+            oz = __dadd_rn(__dmul_rn(w0, __ldg(a0 + 2)), __dmul_rn(w1, __ldg(a1 + 2)));
+            if (b > 0) {
+                const double* lo = p.link_off + ((static_cast<size_t>(set) * p.T + s) * p.B + b) * 3;
+                ox = __dadd_rn(__ldg(lo), ox), oy = __dadd_rn(__ldg(lo + 1), oy), oz = __dadd_rn(__ldg(lo + 2), oz);
+            }
+            m = o * p.B + b;
+            const double* bb = p.bbox + (static_cast<size_t>(set) * per_pose + m) * 6;
+            live = !(ox > __ldg(bb + 1) || ox < __ldg(bb) || oy > __ldg(bb + 3) || oy < __ldg(bb + 2));
+        }
+    }
+    unsigned todo = __ballot_sync(0xFFFFFFFFu, live);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int cs = __shfl_sync(0xFFFFFFFFu, c, src), ss = __shfl_sync(0xFFFFFFFFu, set, src), ms = __shfl_sync(0xFFFFFFFFu, m, src);
+        const D3 org = {__shfl_sync(0xFFFFFFFFu, ox, src), __shfl_sync(0xFFFFFFFFu, oy, src), __shfl_sync(0xFFFFFFFFu, oz, src)};
+        const D3 dir = {0.0, 0.0, 1.0};
+        const Real* mesh = reinterpret_cast<const Real*>(p.mesh) + static_cast<size_t>(ss) * p.set_stride + static_cast<size_t>(ms) * 3 * p.M;
+        D3 h0, h1;
+        const int cnt = warp_first_two_hits<A, Real, true>(mesh, p.n, p.M, org, dir, h0, h1);
+        if (lane == 0) {
+            if (cnt == 2) {
+                if (org.z > fmin(h0.z, h1.z) && org.z < fmax(h0.z, h1.z)) p.flag[cs] = 1u;  // HRM3D.cpp:409-413
+            } else if (cnt == 1) {
+                atomicAdd(p.counters + 3, 1ULL);
+            }
+        }
+    }
+}
+
+// 2D: thread per item
+template <class A>
+__global__ void __launch_bounds__(128) k_transitions2d(const TransParams p) {
+    const long long item = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (item >= p.items) return;
+    const int per_pose = p.B * p.n_obs;
+    const long long pose = item / per_pose;
+    const int rem = static_cast<int>(item - pose * per_pose);
+    const int b = rem / p.n_obs, o = rem - b * p.n_obs;
+    const int c = static_cast<int>(pose / p.T);
+    const int s = static_cast<int>(pose - static_cast<long long>(c) * p.T);
+    const int set = __ldg(p.pair + c);
+    const double w0 = __ldg(p.w0 + s), w1 = __ldg(p.w1 + s);
+    double vx = __dadd_rn(__dmul_rn(w0, __ldg(p.v0 + 2 * static_cast<size_t>(c))), __dmul_rn(w1, __ldg(p.v1 + 2 * static_cast<size_t>(c))));
+    double vy = __dadd_rn(__dmul_rn(w0, __ldg(p.v0 + 2 * static_cast<size_t>(c) + 1)), __dmul_rn(w1, __ldg(p.v1 + 2 * static_cast<size_t>(c) + 1)));
+    if (b > 0) {
+        const double* lo = p.link_off + ((static_cast<size_t>(set) * p.T + s) * p.B + b) * 2;
+        vx = __dadd_rn(__ldg(lo), vx), vy = __dadd_rn(__ldg(lo + 1), vy);
+    }
+    const double* sx = reinterpret_cast<const double*>(p.mesh) + static_cast<size_t>(set) * p.set_stride + (static_cast<size_t>(o) * p.B + b) * 2 * p.M;
+    const double* sy = sx + p.M;
+    double h[2];
+    int cnt = 0;
+    for (int i = 0; i < p.M && cnt < 2; ++i) {
+        const int i2 = (i == p.M - 1) ? 0 : i + 1;
+        const double x1 = sx[i], y1 = sy[i], x2 = sx[i2], y2 = sy[i2];
+        if (vy >= fmin(y1, y2) && vy <= fmax(y1, y2)) {
+            const double tt = A::div(A::sub(vy, y2), A::sub(y1, y2));
+            if (tt >= 0.0 && tt <= 1.0) h[cnt++] = A::add(A::mul(tt, x1), A::mul(A::sub(1.0, tt), x2));
+        }
+    }
+    if (cnt == 2) {
+        if (vx > fmin(h[0], h[1]) && vx < fmax(h[0], h[1])) p.flag[c] = 1u;  // HRM2D.cpp:273-277
+    } else if (cnt == 1) {
+        atomicAdd(p.counters + 3, 1ULL);
+    }
+}
+
 __global__ void k_flags_to_free(const unsigned int* flag, unsigned char* out, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = flag[i] ? 0 : 1;
@@ -255,8 +377,12 @@ static int finish_flags(Ctx* c, int n, unsigned char* d_out) {
     return HRMGPU_OK;
 }
 
-int launch_edges(Ctx* c, int k, int E, const double* d_v1, const double* d_v2, unsigned char* d_out) {
+// k >= 0: all edges against layer k; k < 0: edge e against layer d_layer[e] (one launch for every layer of the build)
+int launch_edges(Ctx* c, int k, int E, const double* d_v1, const double* d_v2, unsigned char* d_out, const int* d_layer) {
     const int So = c->S - c->Sa;
+    const bool multi = k < 0;
+    const int nset = multi ? c->K : 1;
+    if (multi) k = 0;
     int rc;
     if ((rc = ensure(c, c->q_flag, static_cast<size_t>(E)))) return rc;
     HRMGPU_CUDA(c, cudaMemsetAsync(c->q_flag.p, 0, sizeof(unsigned int) * E, c->stream));
@@ -272,17 +398,20 @@ int launch_edges(Ctx* c, int k, int E, const double* d_v1, const double* d_v2, u
         p.n_query = E;
         p.B = c->B;
         p.n_obs = c->n_obs;
+        p.qset = multi ? d_layer : nullptr;
+        p.set_stride = static_cast<size_t>(c->S) * c->dim * c->M;
         const size_t real = (c->prec == HRMGPU_F32) ? 4 : 8;
         const char* mesh = c->mesh.p + (static_cast<size_t>(k) * c->S + c->Sa) * c->dim * c->M * real;
         p.mesh = mesh;
         const long long work = static_cast<long long>(E) * So;
+        if ((c->dim == 3 ? work * 32 + 127 : work + 127) / 128 > 0x7FFFFFFFLL) return fail(c, HRMGPU_E_CAP, "test_edges: too many (edge, mesh) pairs for one launch");
         if (c->dim == 3) {
-            if ((rc = ensure(c, c->bbox, static_cast<size_t>(So) * 6))) return rc;
+            if ((rc = ensure(c, c->bbox, static_cast<size_t>(nset) * So * 6))) return rc;
             p.bbox = c->bbox.p;
             if (c->prec == HRMGPU_F32)
-                k_mesh_bbox<float><<<So, 128, 0, c->stream>>>(reinterpret_cast<const float*>(mesh), 3, c->M, c->bbox.p);
+                k_mesh_bbox<float><<<nset * So, 128, 0, c->stream>>>(reinterpret_cast<const float*>(mesh), 3, c->M, c->bbox.p, So, p.set_stride);
             else
-                k_mesh_bbox<double><<<So, 128, 0, c->stream>>>(reinterpret_cast<const double*>(mesh), 3, c->M, c->bbox.p);
+                k_mesh_bbox<double><<<nset * So, 128, 0, c->stream>>>(reinterpret_cast<const double*>(mesh), 3, c->M, c->bbox.p, So, p.set_stride);
             HRMGPU_CUDA(c, cudaGetLastError());
             const unsigned grid = static_cast<unsigned>((work * 32 + 127) / 128);
             if (c->prec == HRMGPU_F64_STRICT)
@@ -306,8 +435,11 @@ int launch_edges(Ctx* c, int k, int E, const double* d_v1, const double* d_v2, u
     return finish_flags(c, E, d_out);
 }
 
-int launch_bridge_test(Ctx* c, int pidx, int Q, const double* d_centres, unsigned char* d_out) {
+// pidx >= 0: all poses against the bridge layer of pair pidx; pidx < 0: pose q against pair d_pair[q]
+int launch_bridge_test(Ctx* c, int pidx, int Q, const double* d_centres, unsigned char* d_out, const int* d_pair) {
     int rc;
+    const bool multi = pidx < 0;
+    if (multi) pidx = 0;
     if ((rc = ensure(c, c->q_flag, static_cast<size_t>(Q)))) return rc;
     HRMGPU_CUDA(c, cudaMemsetAsync(c->q_flag.p, 0, sizeof(unsigned int) * Q, c->stream));
     if (c->n_obs > 0) {
@@ -323,9 +455,12 @@ int launch_bridge_test(Ctx* c, int pidx, int Q, const double* d_centres, unsigne
         p.n_query = Q;
         p.B = c->bridge_B;
         p.n_obs = c->n_obs;
+        p.qset = multi ? d_pair : nullptr;
+        p.set_stride = static_cast<size_t>(c->n_obs) * c->bridge_B * c->dim * p.M;
         const size_t real = (c->bridge_prec == HRMGPU_F32) ? 4 : 8;
         p.mesh = c->bridge_mesh.p + static_cast<size_t>(pidx) * c->n_obs * c->bridge_B * c->dim * p.M * real;
         const long long work = static_cast<long long>(Q) * c->bridge_B * c->n_obs;
+        if ((c->dim == 3 ? work * 32 + 127 : work + 127) / 128 > 0x7FFFFFFFLL) return fail(c, HRMGPU_E_CAP, "test_bridge: too many (pose, mesh) pairs for one launch");
         if (c->dim == 3) {
             const unsigned grid = static_cast<unsigned>((work * 32 + 127) / 128);
             if (c->bridge_prec == HRMGPU_F64_STRICT)
@@ -345,6 +480,60 @@ int launch_bridge_test(Ctx* c, int pidx, int Q, const double* d_centres, unsigne
         c->launches += 1;
     }
     return finish_flags(c, Q, d_out);
+}
+
+// bounding boxes of all bridge meshes of the last build_bridge (3D): the mesh-level reject of the vertical-line test
+int launch_bridge_bbox(Ctx* c) {
+    const int total = c->P * c->n_obs * c->bridge_B;
+    int rc;
+    if ((rc = ensure(c, c->bridge_bbox, static_cast<size_t>(total > 0 ? total : 1) * 6))) return rc;
+    if (total == 0 || c->dim != 3) return HRMGPU_OK;
+    if (c->bridge_prec == HRMGPU_F32)
+        k_mesh_bbox<float><<<total, 128, 0, c->stream>>>(reinterpret_cast<const float*>(c->bridge_mesh.p), 3, c->n * c->n, c->bridge_bbox.p, total, 0);
+    else
+        k_mesh_bbox<double><<<total, 128, 0, c->stream>>>(reinterpret_cast<const double*>(c->bridge_mesh.p), 3, c->n * c->n, c->bridge_bbox.p, total, 0);
+    HRMGPU_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    return HRMGPU_OK;
+}
+
+int launch_transitions(Ctx* c, int C, int T, const int* d_pair, const double* d_v0, const double* d_v1, const double* d_w0, const double* d_w1,
+                       const double* d_link_off, unsigned char* d_out) {
+    int rc;
+    if ((rc = ensure(c, c->q_flag, static_cast<size_t>(C)))) return rc;
+    HRMGPU_CUDA(c, cudaMemsetAsync(c->q_flag.p, 0, sizeof(unsigned int) * C, c->stream));
+    if (c->n_obs > 0) {
+        TransParams p;
+        p.pair = d_pair, p.v0 = d_v0, p.v1 = d_v1, p.w0 = d_w0, p.w1 = d_w1, p.link_off = d_link_off;
+        p.flag = c->q_flag.p;
+        p.counters = c->counters.p;
+        p.bbox = c->bridge_bbox.p;
+        p.n = c->n;
+        p.M = (c->dim == 3) ? c->n * c->n : c->n;
+        p.C = C, p.T = T, p.B = c->bridge_B, p.n_obs = c->n_obs;
+        p.set_stride = static_cast<size_t>(c->n_obs) * c->bridge_B * c->dim * p.M;
+        p.mesh = c->bridge_mesh.p;
+        p.items = static_cast<long long>(C) * T * c->bridge_B * c->n_obs;
+        const long long blocks = (p.items + 127) / 128;  // 3D: 32 items per warp, 4 warps per block; 2D: one item per thread
+        if (blocks > 0x7FFFFFFFLL) return fail(c, HRMGPU_E_CAP, "test_transitions: too many (pose, body, obstacle) items for one launch");
+        const unsigned grid = static_cast<unsigned>(blocks);
+        if (c->dim == 3) {
+            if (c->bridge_prec == HRMGPU_F64_STRICT)
+                k_transitions3d<Strict, double><<<grid, 128, 0, c->stream>>>(p);
+            else if (c->bridge_prec == HRMGPU_F64)
+                k_transitions3d<Fast, double><<<grid, 128, 0, c->stream>>>(p);
+            else
+                k_transitions3d<Fast, float><<<grid, 128, 0, c->stream>>>(p);
+        } else {
+            if (c->bridge_prec == HRMGPU_F64_STRICT)
+                k_transitions2d<Strict><<<grid, 128, 0, c->stream>>>(p);
+            else
+                k_transitions2d<Fast><<<grid, 128, 0, c->stream>>>(p);
+        }
+        HRMGPU_CUDA(c, cudaGetLastError());
+        c->launches += 1;
+    }
+    return finish_flags(c, C, d_out);
 }
 
 }  // namespace hrmgpu

@@ -17,6 +17,8 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <functional>
 #include <map>
 #include <queue>
@@ -408,6 +410,28 @@ class FreeSpaceGPU {
         if (Q > 0) check(hrmgpu_test_bridge(ctx_, p, Q, centres.data(), out.data()));
         return out;
     }
+    /** the same for the candidate edges of several layers in one launch: edge e against layer layer[e] */
+    std::vector<unsigned char> testEdgesMulti(const std::vector<int>& layer, const std::vector<double>& v1, const std::vector<double>& v2) {
+        std::vector<unsigned char> out(layer.size());
+        if (!out.empty()) check(hrmgpu_test_edges_multi(ctx_, static_cast<int>(out.size()), layer.data(), v1.data(), v2.data(), out.data()));
+        return out;
+    }
+    /** the same for poses of several layer pairs in one launch: pose q against the bridge layer of pair pair[q] */
+    std::vector<unsigned char> testBridgeMulti(const std::vector<int>& pair, const std::vector<double>& centres) {
+        std::vector<unsigned char> out(pair.size());
+        if (!out.empty()) check(hrmgpu_test_bridge_multi(ctx_, static_cast<int>(out.size()), pair.data(), centres.data(), out.data()));
+        return out;
+    }
+    /** isMultiSliceTransitionFree for candidate vertex pairs of any layer pairs in one launch, interpolation on the device:
+     * v0, v1 [C][dim] vertex positions, w0/w1 [T] interpolation weights, linkOff [P][T][B][dim] rotated link translations */
+    std::vector<unsigned char> testTransitions(const std::vector<int>& pair, const std::vector<double>& v0, const std::vector<double>& v1,
+                                               const std::vector<double>& w0, const std::vector<double>& w1, const std::vector<double>& linkOff) {
+        std::vector<unsigned char> out(pair.size());
+        if (!out.empty())
+            check(hrmgpu_test_transitions(ctx_, static_cast<int>(out.size()), pair.data(), v0.data(), v1.data(), static_cast<int>(w0.size()), w0.data(),
+                                          w1.data(), linkOff.data(), out.data()));
+        return out;
+    }
     long long kernelLaunches() { return hrmgpu_kernel_launches(ctx_, 0); }
     /** {K, B, S, n_arena, L, M, total segments, dim} of the last build (hrmgpu_get_dims) */
     void dims(long long d[8]) { check(hrmgpu_get_dims(ctx_, d)); }
@@ -565,6 +589,30 @@ inline bool astar(const Graph& g, Index s, Index t, std::vector<Index>& pred) {
     return false;
 }
 
+/** Wall-clock per planner stage, printed at the end of plan() when the environment variable HRM_HOST_TIMING is set. */
+struct StageTimes {
+    std::vector<std::pair<std::string, double>> acc;
+    void add(const char* name, double sec) {
+        for (auto& a : acc)
+            if (a.first == name) {
+                a.second += sec;
+                return;
+            }
+        acc.push_back({name, sec});
+    }
+    void print() const {
+        if (!std::getenv("HRM_HOST_TIMING")) return;
+        for (const auto& a : acc) std::fprintf(stderr, "[hrm timing] %-28s %9.3f ms\n", a.first.c_str(), a.second * 1e3);
+    }
+};
+struct StageScope {
+    StageTimes& t;
+    const char* name;
+    std::chrono::high_resolution_clock::time_point t0 = std::chrono::high_resolution_clock::now();
+    StageScope(StageTimes& t_, const char* n) : t(t_), name(n) {}
+    ~StageScope() { t.add(name, std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count()); }
+};
+
 class HighwayRoadMapBase {
   public:
     HighwayRoadMapBase(const PlanningRequest& req, int precision, bool perOrientation)
@@ -578,6 +626,7 @@ class HighwayRoadMapBase {
         res_.planningTime.buildTime = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
         t0 = std::chrono::high_resolution_clock::now();
         search();
+        stage_.add("search", std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count());
         res_.planningTime.searchTime = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
         // HighwayRoadMap-inl.h:78-81: refine while unsolved (the reference is bounded by the time limit only; here also by a
         // round count so that runs are reproducible -- 0 rounds by default, like a reference run that solves at once)
@@ -596,6 +645,8 @@ class HighwayRoadMapBase {
             res_.solutionPath.solvedPath.push_back(goal_);
             res_.solutionPath.interpolatedPath = getInterpolatedSolutionPath(param_.numPoint);
         }
+        stage_.add("plan total", res_.planningTime.totalTime);
+        stage_.print();
     }
     /** HighwayRoadMap-inl.h:284-291: the solved path itself (HRM3D overrides) */
     virtual std::vector<std::vector<Coordinate>> getInterpolatedSolutionPath(Index /*num*/) { return res_.solutionPath.solvedPath; }
@@ -668,6 +719,7 @@ class HighwayRoadMapBase {
     int precision_;
     bool perOrientation_;
     long numEdgeTests_ = 0;
+    StageTimes stage_;
     size_t maxRefine_ = 0, numRefineDone_ = 0;
     std::vector<std::vector<std::pair<Index, Index>>> vertexIdxAll_;  // vertexIdx_ of the previous refinement rounds
 
@@ -750,15 +802,41 @@ class HRM3D : public HighwayRoadMapBase {
             baseQ.push_back(rb.getBase().getQuaternion());
             poses.push_back(perOrientation_ ? rb : robot_);  // the reference's FreeSpace copy keeps the as-loaded pose (finding 1)
         }
-        freeSpace_.buildLayers(poses, precision_);
+        {
+            StageScope ss(stage_, "buildLayers (K1-K3)");
+            freeSpace_.buildLayers(poses, precision_);
+        }
         std::vector<long long> off;
         std::vector<double> xL, xU, xM;
-        freeSpace_.getFreeSegmentsAll(off, xL, xU, xM);
+        {
+            StageScope ss(stage_, "getFreeSegmentsAll");
+            freeSpace_.getFreeSegmentsAll(off, xL, xU, xM);
+        }
         const double dx = (lim[1] - lim[0]) / static_cast<double>(Lx - 1), dy = (lim[3] - lim[2]) / static_cast<double>(Ly - 1);
         std::vector<double> tx(Lx), ty(Ly);
         for (int i = 0; i < Lx; ++i) tx[i] = lim[0] + static_cast<double>(i) * dx;
         for (int i = 0; i < Ly; ++i) ty[i] = lim[2] + static_cast<double>(i) * dy;
-        for (size_t k = 0; k < q_.size(); ++k) connectOneSlice3D(static_cast<int>(k), baseQ[k], tx, ty, off.data() + k * Lx * Ly, xL, xU, xM);
+        {
+            // connectOneSlice for every layer: the candidate segments depend on the free segments only, so they are collected
+            // for ALL layers, tested in ONE K4 launch, and the reference's loops are replayed layer by layer on the answers
+            StageScope ss(stage_, "connectOneSlice (all)");
+            std::vector<double> A, Bq;
+            std::vector<int> layerOf;
+            std::vector<SlicePairs> sp(q_.size());
+            for (size_t k = 0; k < q_.size(); ++k) {
+                sp[k] = gatherSlicePairs3D(tx, ty, off.data() + k * Lx * Ly, xM, A, Bq);
+                layerOf.insert(layerOf.end(), 5 * sp[k].P, static_cast<int>(k));
+            }
+            std::vector<unsigned char> f;
+            {
+                StageScope st(stage_, "  K4 testEdges");
+                f = freeSpace_.testEdgesMulti(layerOf, A, Bq);
+            }
+            numEdgeTests_ += static_cast<long>(f.size());
+            for (size_t k = 0; k < q_.size(); ++k)
+                replaySlice3D(baseQ[k], tx, ty, off.data() + k * Lx * Ly, xL, xU, xM, sp[k], pairCodes(f.data() + sp[k].first, sp[k].P));
+        }
+        StageScope ss(stage_, "connectMultiSlice");
         connectMultiSlice();
     }
 
@@ -795,45 +873,81 @@ class HRM3D : public HighwayRoadMapBase {
         }
     }
 
-    /** generateVertices + connectOneSlice2D per plane + cross-plane connections (HRM3D.cpp:93-156), edge tests batched on the GPU */
-    void connectOneSlice3D(int k, const Quaternion& q, const std::vector<double>& tx, const std::vector<double>& ty, const long long* o,
-                           const std::vector<double>& xL, const std::vector<double>& xU, const std::vector<double>& xM) {
+    /** Candidate segments of one layer in connectOneSlice's enumeration order: P pairs, each expanded into the 5 segments
+     * {v1-v2, v1-vNew1, vNew1-v2, v1-vNew2, vNew2-v2} of bridgeVertex (HighwayRoadMap-inl.h:295-326), stored variant-major:
+     * segment (t, i) is entry first + t * P + i of the global arrays. */
+    struct SlicePairs {
+        size_t first = 0, nInPlane = 0, P = 0;
+    };
+    SlicePairs gatherSlicePairs3D(const std::vector<double>& tx, const std::vector<double>& ty, const long long* o, const std::vector<double>& xM,
+                                  std::vector<double>& A, std::vector<double>& Bq) const {
         const int Lx = static_cast<int>(tx.size()), Ly = static_cast<int>(ty.size());
         auto seg0 = [&](int ix, int iy) { return o[ix * Ly + iy]; };
         auto segN = [&](int ix, int iy) { return static_cast<int>(o[ix * Ly + iy + 1] - o[ix * Ly + iy]); };
-        struct Pair {
-            double a[3], b[3];
+        SlicePairs sp;
+        sp.first = A.size() / 3;
+        for (int ix = 0; ix < Lx; ++ix)
+            for (int iy = 0; iy + 1 < Ly; ++iy) sp.nInPlane += static_cast<size_t>(segN(ix, iy)) * segN(ix, iy + 1);
+        sp.P = sp.nInPlane;
+        for (int ix = 0; ix + 1 < Lx; ++ix)
+            for (int iy = 0; iy < Ly; ++iy) sp.P += static_cast<size_t>(segN(ix, iy)) * segN(ix + 1, iy);
+        const size_t P = sp.P;
+        A.resize(3 * (sp.first + 5 * P));
+        Bq.resize(3 * (sp.first + 5 * P));
+        double* a = A.data() + 3 * sp.first;
+        double* b = Bq.data() + 3 * sp.first;
+        size_t i = 0;
+        auto put = [&](double x1, double y1, double z1, double x2, double y2, double z2) {
+            const double v1[3] = {x1, y1, z1}, v2[3] = {x2, y2, z2};
+            const double n1[3] = {x1, y1, z2}, n2[3] = {x2, y2, z1};  // vNew1, vNew2 (HighwayRoadMap-inl.h:301-304)
+            const double* as[5] = {v1, v1, n1, v1, n2};
+            const double* bs[5] = {v2, n1, v2, n2, v2};
+            for (int t = 0; t < 5; ++t)
+                for (int d = 0; d < 3; ++d) a[(t * P + i) * 3 + d] = as[t][d], b[(t * P + i) * 3 + d] = bs[t][d];
+            ++i;
         };
-        std::vector<Pair> pairs;
         for (int ix = 0; ix < Lx; ++ix)
             for (int iy = 0; iy + 1 < Ly; ++iy)
                 for (int j1 = 0; j1 < segN(ix, iy); ++j1)
                     for (int j2 = 0; j2 < segN(ix, iy + 1); ++j2)
-                        pairs.push_back({{tx[ix], ty[iy], xM[seg0(ix, iy) + j1]}, {tx[ix], ty[iy + 1], xM[seg0(ix, iy + 1) + j2]}});
-        const size_t nInPlane = pairs.size();
+                        put(tx[ix], ty[iy], xM[seg0(ix, iy) + j1], tx[ix], ty[iy + 1], xM[seg0(ix, iy + 1) + j2]);
         for (int ix = 0; ix + 1 < Lx; ++ix)
             for (int iy = 0; iy < Ly; ++iy)
                 for (int k1 = 0; k1 < segN(ix, iy); ++k1)
                     for (int k2 = 0; k2 < segN(ix + 1, iy); ++k2)
-                        pairs.push_back({{tx[ix], ty[iy], xM[seg0(ix, iy) + k1]}, {tx[ix + 1], ty[iy], xM[seg0(ix + 1, iy) + k2]}});
-        std::vector<int> codes(pairs.size(), 3);
-        if (!pairs.empty()) {
-            const size_t P = pairs.size();
-            std::vector<double> A(15 * P), Bq(15 * P);
-            for (size_t i = 0; i < P; ++i) {
-                const double* v1 = pairs[i].a;
-                const double* v2 = pairs[i].b;
-                const double n1[3] = {v1[0], v1[1], v2[2]}, n2[3] = {v2[0], v2[1], v1[2]};  // vNew1, vNew2 (HighwayRoadMap-inl.h:301-304)
-                const double* as[5] = {v1, v1, n1, v1, n2};
-                const double* bs[5] = {v2, n1, v2, n2, v2};
-                for (int t = 0; t < 5; ++t)
-                    for (int d = 0; d < 3; ++d) A[(t * P + i) * 3 + d] = as[t][d], Bq[(t * P + i) * 3 + d] = bs[t][d];
-            }
-            const auto f = freeSpace_.testEdges(k, A, Bq, 3);
-            numEdgeTests_ += static_cast<long>(5 * P);
-            for (size_t i = 0; i < P; ++i) codes[i] = pairCode(f[i], f[P + i], f[2 * P + i], f[3 * P + i], f[4 * P + i]);
+                        put(tx[ix], ty[iy], xM[seg0(ix, iy) + k1], tx[ix + 1], ty[iy], xM[seg0(ix + 1, iy) + k2]);
+        return sp;
+    }
+    /** connection code of every pair from the 5 answers of its segments (variant-major, see SlicePairs) */
+    static std::vector<int> pairCodes(const unsigned char* f, size_t P) {
+        std::vector<int> codes(P);
+        for (size_t i = 0; i < P; ++i) codes[i] = pairCode(f[i], f[P + i], f[2 * P + i], f[3 * P + i], f[4 * P + i]);
+        return codes;
+    }
+
+    /** generateVertices + connectOneSlice2D per plane + cross-plane connections (HRM3D.cpp:93-156) of ONE layer with its own
+     * K4 call (refinement and ProbHRM3D build layer by layer; HRM3D::buildRoadmap batches all layers instead) */
+    void connectOneSlice3D(int k, const Quaternion& q, const std::vector<double>& tx, const std::vector<double>& ty, const long long* o,
+                           const std::vector<double>& xL, const std::vector<double>& xU, const std::vector<double>& xM) {
+        std::vector<double> A, Bq;
+        const SlicePairs sp = gatherSlicePairs3D(tx, ty, o, xM, A, Bq);
+        std::vector<unsigned char> f;
+        if (sp.P) {
+            StageScope ss(stage_, "  K4 testEdges");
+            f = freeSpace_.testEdges(k, A, Bq, 3);
         }
-        // replay in the reference's order
+        numEdgeTests_ += static_cast<long>(5 * sp.P);
+        replaySlice3D(q, tx, ty, o, xL, xU, xM, sp, pairCodes(f.data(), sp.P));
+    }
+
+    /** the reference's loops of one layer replayed on the pair codes, so that vertex ids and edge order are the reference's */
+    void replaySlice3D(const Quaternion& q, const std::vector<double>& tx, const std::vector<double>& ty, const long long* o,
+                       const std::vector<double>& xL, const std::vector<double>& xU, const std::vector<double>& xM, const SlicePairs& sp,
+                       const std::vector<int>& codes) {
+        const int Lx = static_cast<int>(tx.size()), Ly = static_cast<int>(ty.size());
+        auto seg0 = [&](int ix, int iy) { return o[ix * Ly + iy]; };
+        auto segN = [&](int ix, int iy) { return static_cast<int>(o[ix * Ly + iy + 1] - o[ix * Ly + iy]); };
+        const size_t nInPlane = sp.nInPlane;
         auto& V = res_.graphStructure.vertex;
         const Index startId = V.size();
         std::vector<std::vector<Index>> lineIds;
@@ -887,6 +1001,7 @@ class HRM3D : public HighwayRoadMapBase {
         const auto bodies = robot_.getBodyShapes();
         std::vector<int> nearest;
         std::vector<std::vector<Ellipsoid>> tfe;
+        auto tTfe = std::chrono::high_resolution_clock::now();
         for (size_t i = 0; i < vertexIdx_.size(); ++i) {
             double minDist = INFINITY;
             int minIdx = 0;
@@ -908,51 +1023,84 @@ class HRM3D : public HighwayRoadMapBase {
             }
             tfe.push_back(pr);
         }
-        freeSpace_.buildBridge(tfe, precision_);
+        stage_.add("  TFE (host)", std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - tTfe).count());
+        {
+            StageScope ss(stage_, "  K5a buildBridge");
+            freeSpace_.buildBridge(tfe, precision_);
+        }
         const double thx = 2.0 * (lim[1] - lim[0]) / static_cast<double>(param_.numLineX);
         const double thy = 2.0 * (lim[3] - lim[2]) / static_cast<double>(param_.numLineY);
         const size_t steps = param_.numPoint;
-        MultiBodyTree3D rb = robot_;
-        for (size_t i = 0; i < vertexIdx_.size(); ++i) {
-            const Index cur0 = vertexIdx_[i].first, cur1 = vertexIdx_[i].second;
-            const Index start = vertexIdx_[nearest[i]].first, n2 = vertexIdx_[nearest[i]].second;
-            if (n2 <= start || cur1 <= cur0) continue;
-            std::vector<std::pair<Index, Index>> cand;
-            std::vector<double> centres;
-            for (Index m0 = start; m0 < n2; ++m0)
-                for (Index m1 = cur0; m1 < cur1; ++m1) {
-                    if (std::fabs(V[m0][0] - V[m1][0]) > thx || std::fabs(V[m0][1] - V[m1][1]) > thy) continue;
-                    cand.push_back({m0, m1});
-                    for (const auto& vs : interpolateSE3(V[m0], V[m1], steps)) {  // numPoint+1 poses incl. both ends
-                        SE3Transform g;
-                        g.R = toRotationMatrix({vs[3], vs[4], vs[5], vs[6]});
-                        g.t = {vs[0], vs[1], vs[2]};
-                        rb.robotTF(g);  // setTransform
-                        for (double v : rb.getBase().getPosition()) centres.push_back(v);
-                        for (const auto& l : rb.getLinks())
-                            for (double v : l.getPosition()) centres.push_back(v);
+        // Candidates of every layer pair (vertices within two line spacings, HRM3D.cpp:195-206), tested in ONE K5 launch.
+        // isMultiSliceTransitionFree (:367-392) interpolates v1 -> v2 and moves the robot to every pose (setTransform): all
+        // vertices of a layer carry the layer's quaternion, so the slerp rotations R_s and the rotated link offsets R_s * t_l
+        // are the same for every candidate of a pair; they are evaluated once per pair with the operations robotTF performs,
+        // and the kernel forms the body centres (interpolated position + offset) itself.
+        struct PairCand {
+            Index start = 0, n2 = 0, cur0 = 0, cur1 = 0;
+            size_t first = 0, count = 0;       // candidates [first, first + count) in pair order (m0 outer, m1 inner)
+            std::vector<unsigned char> state;  // [(m0 - start) * (cur1 - cur0) + (m1 - cur0)]: 0 no candidate, 1 blocked, 2 free
+        };
+        const size_t P = vertexIdx_.size(), T = steps + 1;
+        std::vector<PairCand> pc(P);
+        std::vector<int> pairOf;
+        std::vector<double> v0s, v1s, w0(T), w1(T), linkOff(P * T * B * 3, 0.0);
+        std::vector<std::pair<Index, Index>> cand;
+        const auto& tf = robot_.getTF();
+        const double dt = 1.0 / static_cast<double>(steps);
+        for (size_t s = 0; s < T; ++s) w1[s] = static_cast<double>(s) * dt, w0[s] = 1.0 - static_cast<double>(s) * dt;  // InterpolateSE3.cpp:5-29
+        {
+            StageScope ss(stage_, "  bridge candidates (host)");
+            for (size_t i = 0; i < P; ++i) {
+                PairCand& c = pc[i];
+                c.cur0 = vertexIdx_[i].first, c.cur1 = vertexIdx_[i].second;
+                c.start = vertexIdx_[nearest[i]].first, c.n2 = vertexIdx_[nearest[i]].second;
+                c.first = cand.size();
+                if (c.n2 <= c.start || c.cur1 <= c.cur0) continue;
+                c.state.assign((c.n2 - c.start) * (c.cur1 - c.cur0), 0);
+                const auto& va = V[c.start];
+                const auto& vb = V[c.cur0];
+                const auto qs = interpolateSlerp({va[3], va[4], va[5], va[6]}, {vb[3], vb[4], vb[5], vb[6]}, steps);
+                for (size_t s = 0; s < T; ++s) {
+                    const Mat3 R = toRotationMatrix(qs[s]);
+                    for (size_t l = 0; l < tf.size(); ++l) {
+                        const Vec3 v = matVec(R, tf[l].t);
+                        for (int d = 0; d < 3; ++d) linkOff[((i * T + s) * B + (l + 1)) * 3 + d] = v[d];
                     }
                 }
-            std::map<std::pair<Index, Index>, bool> freePair;
-            if (!cand.empty()) {
-                const auto ok = freeSpace_.testBridge(static_cast<int>(i), centres, static_cast<int>(cand.size() * (steps + 1)));
-                for (size_t c = 0; c < cand.size(); ++c) {
-                    bool all = true;
-                    for (size_t s = 0; s <= steps; ++s) all = all && ok[c * (steps + 1) + s];
-                    freePair[cand[c]] = all;
-                }
+                for (Index m0 = c.start; m0 < c.n2; ++m0)
+                    for (Index m1 = c.cur0; m1 < c.cur1; ++m1) {
+                        const auto& v0 = V[m0];
+                        const auto& v1 = V[m1];
+                        if (std::fabs(v0[0] - v1[0]) > thx || std::fabs(v0[1] - v1[1]) > thy) continue;
+                        c.state[(m0 - c.start) * (c.cur1 - c.cur0) + (m1 - c.cur0)] = 1;
+                        cand.push_back({m0, m1});
+                        v0s.insert(v0s.end(), v0.begin(), v0.begin() + 3);
+                        v1s.insert(v1s.end(), v1.begin(), v1.begin() + 3);
+                        pairOf.push_back(static_cast<int>(i));
+                    }
+                c.count = cand.size() - c.first;
             }
-            Index n22 = cur0;  // replay with the reference's moving lower bound
-            for (Index m0 = start; m0 < n2; ++m0)
-                for (Index m1 = n22; m1 < cur1; ++m1) {
-                    auto it = freePair.find({m0, m1});
-                    if (it == freePair.end()) continue;
-                    if (it->second) {
+        }
+        std::vector<unsigned char> ok;
+        {
+            StageScope ss(stage_, "  K5b testTransitions");
+            ok = freeSpace_.testTransitions(pairOf, v0s, v1s, w0, w1, linkOff);
+        }
+        for (size_t i = 0; i < P; ++i) {
+            PairCand& c = pc[i];
+            if (c.count == 0) continue;
+            const Index w = c.cur1 - c.cur0;
+            for (size_t j = 0; j < c.count; ++j)
+                if (ok[c.first + j]) c.state[(cand[c.first + j].first - c.start) * w + (cand[c.first + j].second - c.cur0)] = 2;
+            Index n22 = c.cur0;  // replay with the reference's moving lower bound
+            for (Index m0 = c.start; m0 < c.n2; ++m0)
+                for (Index m1 = n22; m1 < c.cur1; ++m1)
+                    if (c.state[(m0 - c.start) * w + (m1 - c.cur0)] == 2) {
                         addEdge(m0, m1);
                         n22 = m1;
                         break;
                     }
-                }
         }
     }
 
@@ -1130,46 +1278,63 @@ class HRM2D : public HighwayRoadMapBase {
         const double th = 2.0 * std::fabs(lim[3] - lim[2]) / static_cast<double>(param_.numLineY);
         const size_t steps = param_.numPoint;
         const double dt = 1.0 / (static_cast<double>(steps) - 1);
-        MultiBodyTree2D rb = robot_;
-        for (size_t i = 0; i < vertexIdx_.size(); ++i) {
-            const Index sCur = vertexIdx_[i].first, eCur = vertexIdx_[i].second;
-            const Index sAdj0 = vertexIdx_[adj[i]].first, eAdj = vertexIdx_[adj[i]].second;
-            if (eCur <= sCur || eAdj <= sAdj0) continue;
-            std::vector<std::pair<Index, Index>> cand;
-            std::vector<double> centres;
-            for (Index m0 = sCur; m0 < eCur; ++m0)
-                for (Index m1 = sAdj0; m1 < eAdj; ++m1) {
-                    if (std::fabs(V[m0][1] - V[m1][1]) > th) continue;
-                    cand.push_back({m0, m1});
-                    for (size_t s = 0; s < steps; ++s) {  // :237-247
-                        double vs[3];
-                        for (int j = 0; j < 3; ++j) vs[j] = (1.0 - static_cast<double>(s) * dt) * V[m0][j] + static_cast<double>(s) * dt * V[m1][j];
-                        rb.robotTF(vs[2], vs[0], vs[1]);
-                        for (double v : rb.getBase().getPosition()) centres.push_back(v);
-                        for (const auto& l : rb.getLinks())
-                            for (double v : l.getPosition()) centres.push_back(v);
-                    }
-                }
-            std::map<std::pair<Index, Index>, bool> freePair;
-            if (!cand.empty()) {
-                const auto ok = freeSpace_.testBridge(static_cast<int>(i), centres, static_cast<int>(cand.size() * steps));
-                for (size_t c = 0; c < cand.size(); ++c) {
-                    bool all = true;
-                    for (size_t s = 0; s < steps; ++s) all = all && ok[c * steps + s];
-                    freePair[cand[c]] = all;
+        // All layer pairs in one K5 launch (see HRM3D::connectMultiSlice): the interpolated heading of step s is the same for
+        // every candidate of a pair (the vertices of a layer share their heading), so the rotated link translations
+        // Rot(theta_s) * t_l of robotTF (:24-41) are evaluated once per pair; the kernel adds the interpolated position.
+        struct PairCand {
+            Index sCur = 0, eCur = 0, sAdj = 0, eAdj = 0;
+            size_t first = 0, count = 0;
+            std::vector<unsigned char> state;  // [(m0 - sCur) * (eAdj - sAdj) + (m1 - sAdj)]: 0 no candidate, 1 blocked, 2 free
+        };
+        const size_t P = vertexIdx_.size(), T = steps;
+        std::vector<PairCand> pc(P);
+        std::vector<int> pairOf;
+        std::vector<double> v0s, v1s, w0(T), w1(T), linkOff(P * T * B * 2, 0.0);
+        std::vector<std::pair<Index, Index>> cand;
+        const auto& tf = robot_.getTF();
+        for (size_t s = 0; s < T; ++s) w1[s] = static_cast<double>(s) * dt, w0[s] = 1.0 - static_cast<double>(s) * dt;  // :237-247
+        for (size_t i = 0; i < P; ++i) {
+            PairCand& c = pc[i];
+            c.sCur = vertexIdx_[i].first, c.eCur = vertexIdx_[i].second;
+            c.sAdj = vertexIdx_[adj[i]].first, c.eAdj = vertexIdx_[adj[i]].second;
+            c.first = cand.size();
+            if (c.eCur <= c.sCur || c.eAdj <= c.sAdj) continue;
+            c.state.assign((c.eCur - c.sCur) * (c.eAdj - c.sAdj), 0);
+            for (size_t s = 0; s < T; ++s) {
+                const double theta = w0[s] * V[c.sCur][2] + w1[s] * V[c.sAdj][2];
+                const double cs = std::cos(theta), sn = std::sin(theta);
+                const double R[2][2] = {{cs, -sn}, {sn, cs}};
+                for (size_t l = 0; l < tf.size(); ++l) {
+                    linkOff[((i * T + s) * B + (l + 1)) * 2] = R[0][0] * tf[l].t[0] + R[0][1] * tf[l].t[1];
+                    linkOff[((i * T + s) * B + (l + 1)) * 2 + 1] = R[1][0] * tf[l].t[0] + R[1][1] * tf[l].t[1];
                 }
             }
-            Index sAdj = sAdj0;
-            for (Index m0 = sCur; m0 < eCur; ++m0)
-                for (Index m1 = sAdj; m1 < eAdj; ++m1) {
-                    auto it = freePair.find({m0, m1});
-                    if (it == freePair.end()) continue;
-                    if (it->second) {
+            for (Index m0 = c.sCur; m0 < c.eCur; ++m0)
+                for (Index m1 = c.sAdj; m1 < c.eAdj; ++m1) {
+                    if (std::fabs(V[m0][1] - V[m1][1]) > th) continue;
+                    c.state[(m0 - c.sCur) * (c.eAdj - c.sAdj) + (m1 - c.sAdj)] = 1;
+                    cand.push_back({m0, m1});
+                    v0s.insert(v0s.end(), V[m0].begin(), V[m0].begin() + 2);
+                    v1s.insert(v1s.end(), V[m1].begin(), V[m1].begin() + 2);
+                    pairOf.push_back(static_cast<int>(i));
+                }
+            c.count = cand.size() - c.first;
+        }
+        const auto ok = freeSpace_.testTransitions(pairOf, v0s, v1s, w0, w1, linkOff);
+        for (size_t i = 0; i < P; ++i) {
+            PairCand& c = pc[i];
+            if (c.count == 0) continue;
+            const Index w = c.eAdj - c.sAdj;
+            for (size_t j = 0; j < c.count; ++j)
+                if (ok[c.first + j]) c.state[(cand[c.first + j].first - c.sCur) * w + (cand[c.first + j].second - c.sAdj)] = 2;
+            Index sAdj = c.sAdj;
+            for (Index m0 = c.sCur; m0 < c.eCur; ++m0)
+                for (Index m1 = sAdj; m1 < c.eAdj; ++m1)
+                    if (c.state[(m0 - c.sCur) * w + (m1 - c.sAdj)] == 2) {
                         addEdge(m0, m1);
                         sAdj = m1;
                         break;
                     }
-                }
         }
     }
 

@@ -130,6 +130,11 @@ int hrmgpu_get_single_hit_count(hrmgpu_ctx* ctx, long long* out);
  * LineIntersection.cpp:173-213) for a 2D build.  v1,v2: [E][3] ([E][2] in 2D) segment end points.
  * free_out[e] = 1 if the transition is collision-free. */
 int hrmgpu_test_edges(hrmgpu_ctx* ctx, int k, int E, const double* v1, const double* v2, unsigned char* free_out);
+/* The same test for the candidate edges of SEVERAL layers in one launch: edge e is tested against the C-obstacles of layer
+ * layer[e] of the last build.  The candidate edges of connectOneSlice (HighwayRoadMap-inl.h:218-261, HRM3D.cpp:116-156)
+ * depend on the free segments only, not on the graph, so a planner collects them for every layer, asks once, and replays
+ * the reference's loops on the answers. */
+int hrmgpu_test_edges_multi(hrmgpu_ctx* ctx, int E, const int* layer, const double* v1, const double* v2, unsigned char* free_out);
 
 /* ---- bridge layers (K5) ----------------------------------------------------------------------- */
 /* Replaces HRM3D::bridgeSlice (HRM3D.cpp:301-317): for P layer pairs, the Minkowski sums of every
@@ -142,6 +147,19 @@ int hrmgpu_build_bridge2d(hrmgpu_ctx* ctx, int P, int B, const double* tfe_semi,
  * HRM2D.cpp:235-282): centres [Q][B][3] ([Q][B][2] in 2D) are the body centres at each pose;
  * free_out[q] = 1 iff every body centre is outside every bridge C-obstacle of its body. */
 int hrmgpu_test_bridge(hrmgpu_ctx* ctx, int p, int Q, const double* centres, unsigned char* free_out);
+/* The same test for poses of SEVERAL layer pairs in one launch (connectMultiSlice, HRM3D.cpp:158-224): pose q is tested
+ * against the bridge layer of pair pair[q]. */
+int hrmgpu_test_bridge_multi(hrmgpu_ctx* ctx, int Q, const int* pair, const double* centres, unsigned char* free_out);
+
+/* Replaces isMultiSliceTransitionFree (HRM3D.cpp:367-392, HRM2D.cpp:235-265) for C candidate vertex pairs of any layer
+ * pairs in ONE launch, with the interpolation done on the device.  The robot moves from v0[c] to v1[c] ([C][3], 2D [C][2]:
+ * the positions of the two vertices) through T poses; pose s has the base centre  t = w0[s]*v0 + w1[s]*v1  (two rounded
+ * products and one rounded sum, as interpolateSE3 / the 2D loop evaluate it with w1 = s*dt, w0 = 1 - s*dt) and body b > 0 sits
+ * at link_off[pair[c]][s][b] + t, where link_off [P][T][B][dim] holds the link translations rotated by the pair's s-th
+ * interpolated orientation (MultiBodyTree3D.cpp:34-53; every vertex of a layer carries the layer's orientation, so these are
+ * the same for all candidates of a pair; row b = 0 is ignored).  free_out[c] = 1 iff every pose is free for every body. */
+int hrmgpu_test_transitions(hrmgpu_ctx* ctx, int C, const int* pair, const double* v0, const double* v1, int T, const double* w0,
+                            const double* w1, const double* link_off, unsigned char* free_out);
 
 /* ---- multi-GPU exchange ------------------------------------------------------------------------ */
 /* Packs the last build's free segments into one contiguous DEVICE buffer owned by the caller's

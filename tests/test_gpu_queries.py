@@ -34,6 +34,7 @@ def test_edges3d_match_oracle(oracle, gpu_ctx, name, n):
     gpu_ctx.build_layers(semi, R, off, capi.F64_STRICT)
     rng = np.random.default_rng(5)
     B = semi.shape[0]
+    all_a, all_b, all_k, all_want = [], [], [], []
     for k in range(3):
         ref = oracle.layer3d(n_arena, n_obs, np.array(rows), n, semi, quat[k], off[k], sc["lim"], sc["Lx"], sc["Ly"])
         o, xL, xU, xM = gpu_ctx.segments(k)
@@ -54,6 +55,13 @@ def test_edges3d_match_oracle(oracle, gpu_ctx, name, n):
         want, _ = oracle.edges3d(ref["bound"][n_arena * B:], n, a, b)
         assert np.array_equal(got, want)
         assert 0 < want.sum() < len(want)
+        all_a.append(a), all_b.append(b), all_k.append(np.full(len(a), k)), all_want.append(want)
+    # the same edges of all layers, interleaved, in ONE launch (hrmgpu_test_edges_multi)
+    a, b, kk, want = np.concatenate(all_a), np.concatenate(all_b), np.concatenate(all_k), np.concatenate(all_want)
+    perm = rng.permutation(len(a))
+    assert np.array_equal(gpu_ctx.test_edges_multi(kk[perm], a[perm], b[perm]), want[perm])
+    with pytest.raises(RuntimeError):
+        gpu_ctx.test_edges_multi(np.full(len(a), 3), a, b)  # layer index out of range
 
 
 def test_edges2d_match_oracle(oracle, gpu_ctx):
@@ -68,6 +76,7 @@ def test_edges2d_match_oracle(oracle, gpu_ctx):
     rng = np.random.default_rng(11)
     lim = np.array(sc["lim"])
     B = semi.shape[0]
+    all_a, all_b, all_k, all_want = [], [], [], []
     for k in range(3):
         ref = oracle.layer2d(n_arena, n_obs, np.array(rows), 50, semi, ang[k], off[k], sc["lim"], 12)
         a = rng.uniform(lim[0::2], lim[1::2], size=(500, 2))
@@ -76,6 +85,10 @@ def test_edges2d_match_oracle(oracle, gpu_ctx):
         want = oracle.edges2d(ref["bound"][n_arena * B:], a, b)
         assert np.array_equal(got, want)
         assert 0 < want.sum() < len(want)
+        all_a.append(a), all_b.append(b), all_k.append(np.full(len(a), k)), all_want.append(want)
+    a, b, kk, want = np.concatenate(all_a), np.concatenate(all_b), np.concatenate(all_k), np.concatenate(all_want)
+    perm = rng.permutation(len(a))
+    assert np.array_equal(gpu_ctx.test_edges_multi(kk[perm], a[perm], b[perm]), want[perm])
 
 
 def test_bridge3d_match_oracle(oracle, gpu_ctx):
@@ -107,17 +120,48 @@ def test_bridge3d_match_oracle(oracle, gpu_ctx):
     gpu_ctx.build_bridge(np.array(tfe_semi), np.array(tfe_R), capi.F64_STRICT)
     rng = np.random.default_rng(3)
     lim = np.array(sc["lim"])
+    all_c, all_p, all_want = [], [], []
+    bounds = [[[oracle.minksum3d(rows[n_arena + o], tfe_semi[p][b], tfe_q[p][b], n, +1) for o in range(n_obs)] for b in range(B)]
+              for p in range(len(pairs))]
+
+    def want_for(p, centres):
+        want = np.ones(len(centres), dtype=bool)
+        for b in range(B):
+            w, _ = oracle.pt_in_cfree3d(bounds[p][b], n, centres[:, b, :])
+            want &= w
+        return want
+
     for p in range(len(pairs)):
         Q = 400
         centres = rng.uniform(lim[0::2] - 5, lim[1::2] + 5, size=(Q, B, 3))
         got = gpu_ctx.test_bridge(p, centres)
-        want = np.ones(Q, dtype=bool)
-        for b in range(B):
-            bounds = [oracle.minksum3d(rows[n_arena + o], tfe_semi[p][b], tfe_q[p][b], n, +1) for o in range(n_obs)]
-            w, _ = oracle.pt_in_cfree3d(bounds, n, centres[:, b, :])
-            want &= w
+        want = want_for(p, centres)
         assert np.array_equal(got, want)
         assert 0 < want.sum() < Q
+        all_c.append(centres), all_p.append(np.full(Q, p)), all_want.append(want)
+    # all pairs in ONE launch (hrmgpu_test_bridge_multi)
+    c, pp, want = np.concatenate(all_c), np.concatenate(all_p), np.concatenate(all_want)
+    perm = rng.permutation(len(c))
+    assert np.array_equal(gpu_ctx.test_bridge_multi(pp[perm], c[perm]), want[perm])
+    # candidate vertex pairs with the interpolation on the device (hrmgpu_test_transitions): body centres of pose s are
+    # w0[s]*v0 + w1[s]*v1 (+ the pair's rotated link translation), a candidate is free iff every pose is
+    T, C = 6, 500
+    w1 = np.arange(T) * (1.0 / 5.0)
+    w0 = 1.0 - w1
+    link_off = rng.uniform(-6, 6, size=(len(pairs), T, B, 3))
+    pair = rng.integers(0, len(pairs), C)
+    v0 = rng.uniform(lim[0::2], lim[1::2], size=(C, 3))
+    v1 = v0 + rng.normal(scale=4.0, size=(C, 3))
+    got = gpu_ctx.test_transitions(pair, v0, v1, w0, w1, link_off)
+    want = np.ones(C, dtype=bool)
+    for p in range(len(pairs)):
+        sel = np.nonzero(pair == p)[0]
+        for s_ in range(T):
+            t = w0[s_] * v0[sel] + w1[s_] * v1[sel]
+            centres = np.stack([t if b == 0 else link_off[p, s_, b] + t for b in range(B)], axis=1)
+            want[sel] &= want_for(p, centres)
+    assert np.array_equal(got, want)
+    assert 0 < want.sum() < C
 
 
 def test_bridge2d_match_oracle(oracle, gpu_ctx):
@@ -133,14 +177,42 @@ def test_bridge2d_match_oracle(oracle, gpu_ctx):
     gpu_ctx.build_bridge2d(tfe[:, :, :2], tfe[:, :, 2], capi.F64_STRICT)
     rng = np.random.default_rng(9)
     lim = np.array(sc["lim"])
+    bounds = [[[oracle.minksum2d(rows[n_arena + o], tfe[p, b, :2], tfe[p, b, 2], 50, +1) for o in range(n_obs)] for b in range(B)] for p in range(2)]
+
+    def want_for(p, centres):
+        want = np.ones(len(centres), dtype=bool)
+        for b in range(B):
+            w, _ = oracle.pt_in_cfree2d(bounds[p][b], centres[:, b, :])
+            want &= w
+        return want
+
+    all_c, all_p, all_want = [], [], []
     for p in range(2):
         Q = 500
         centres = rng.uniform(lim[0::2], lim[1::2], size=(Q, B, 2))
         got = gpu_ctx.test_bridge(p, centres)
-        want = np.ones(Q, dtype=bool)
-        for b in range(B):
-            bounds = [oracle.minksum2d(rows[n_arena + o], tfe[p, b, :2], tfe[p, b, 2], 50, +1) for o in range(n_obs)]
-            w, _ = oracle.pt_in_cfree2d(bounds, centres[:, b, :])
-            want &= w
+        want = want_for(p, centres)
         assert np.array_equal(got, want)
         assert 0 < want.sum() < Q
+        all_c.append(centres), all_p.append(np.full(Q, p)), all_want.append(want)
+    c, pp, want = np.concatenate(all_c), np.concatenate(all_p), np.concatenate(all_want)
+    perm = rng.permutation(len(c))
+    assert np.array_equal(gpu_ctx.test_bridge_multi(pp[perm], c[perm]), want[perm])
+    # candidate vertex pairs, interpolation on the device (hrmgpu_test_transitions)
+    T, C = 5, 600
+    w1 = np.arange(T) * (1.0 / 4.0)
+    w0 = 1.0 - w1
+    link_off = rng.uniform(-4, 4, size=(2, T, B, 2))
+    pair = rng.integers(0, 2, C)
+    v0 = rng.uniform(lim[0::2], lim[1::2], size=(C, 2))
+    v1 = v0 + rng.normal(scale=3.0, size=(C, 2))
+    got = gpu_ctx.test_transitions(pair, v0, v1, w0, w1, link_off)
+    want = np.ones(C, dtype=bool)
+    for p in range(2):
+        sel = np.nonzero(pair == p)[0]
+        for s_ in range(T):
+            t = w0[s_] * v0[sel] + w1[s_] * v1[sel]
+            centres = np.stack([t if b == 0 else link_off[p, s_, b] + t for b in range(B)], axis=1)
+            want[sel] &= want_for(p, centres)
+    assert np.array_equal(got, want)
+    assert 0 < want.sum() < C
