@@ -96,6 +96,7 @@ int hrmgpu_create(hrmgpu_ctx** out, int device, unsigned flags) {
     hrmgpu_ctx* c = new (std::nothrow) hrmgpu_ctx();
     if (!c) return HRMGPU_E_NOMEM;
     c->device = device;
+    c->num_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
         delete c;

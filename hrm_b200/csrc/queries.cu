@@ -104,37 +104,57 @@ struct QueryParams {
 };
 
 // ---- K4 3D ----
+// Work item = (edge e, mesh m), m fastest.  A warp takes 32 consecutive items: every lane forms its edge's direction and
+// applies the reference's mesh-level reject (LineIntersection.cpp:12-30: bounding box, only along (nearly) axis-parallel
+// directions -- which is the common case, the candidate segments of connectOneSlice run between neighbouring sweep lines);
+// the surviving items are then walked by the whole warp one after the other (faces in order, first two hits).
 template <class A, class Real>
 __global__ void __launch_bounds__(128) k_edges3d(const QueryParams p) {
-    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (warp_global >= p.n_query * p.n_mesh) return;
-    const int e = warp_global / p.n_mesh, m = warp_global - e * p.n_mesh;
-    const D3 t1 = {p.a[3 * e], p.a[3 * e + 1], p.a[3 * e + 2]};
-    const D3 t2 = {p.b[3 * e], p.b[3 * e + 1], p.b[3 * e + 2]};
-    D3 d = sub3<A>(t2, t1);                           // HRM3D.cpp:322-325
-    const double z = dot3<A>(d, d);
-    if (z > 0.0) {
-        const double s = A::sqrt(z);
-        d.x = A::div(d.x, s), d.y = A::div(d.y, s), d.z = A::div(d.z, s);
-    }
-    const int set = p.qset ? __ldg(p.qset + e) : 0;
-    // LineIntersection.cpp:12-30: reject on the mesh bounding box only along (nearly) axis-parallel directions
-    const double* bb = p.bbox + (static_cast<size_t>(set) * p.n_mesh + m) * 6;
-    const double oc[3] = {t1.x, t1.y, t1.z}, dc[3] = {d.x, d.y, d.z};
+    const long long item = warp_global * 32 + lane;
+    const long long items = static_cast<long long>(p.n_query) * p.n_mesh;
+    bool live = false;
+    int e = 0, m = 0, set = 0;
+    D3 t1 = {0, 0, 0}, t2 = {0, 0, 0}, d = {0, 0, 0};
+    if (item < items) {
+        e = static_cast<int>(item / p.n_mesh);
+        m = static_cast<int>(item - static_cast<long long>(e) * p.n_mesh);
+        t1 = {p.a[3 * static_cast<size_t>(e)], p.a[3 * static_cast<size_t>(e) + 1], p.a[3 * static_cast<size_t>(e) + 2]};
+        t2 = {p.b[3 * static_cast<size_t>(e)], p.b[3 * static_cast<size_t>(e) + 1], p.b[3 * static_cast<size_t>(e) + 2]};
+        d = sub3<A>(t2, t1);                           // HRM3D.cpp:322-325
+        const double z = dot3<A>(d, d);
+        if (z > 0.0) {
+            const double s = A::sqrt(z);
+            d.x = A::div(d.x, s), d.y = A::div(d.y, s), d.z = A::div(d.z, s);
+        }
+        set = p.qset ? __ldg(p.qset + e) : 0;
+        const double* bb = p.bbox + (static_cast<size_t>(set) * p.n_mesh + m) * 6;
+        const double oc[3] = {t1.x, t1.y, t1.z}, dc[3] = {d.x, d.y, d.z};
+        live = true;
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
-        if (fabs(dc[i]) < 1e-6 && (oc[i] > bb[2 * i + 1] || oc[i] < bb[2 * i])) return;
-    const Real* mesh = reinterpret_cast<const Real*>(p.mesh) + static_cast<size_t>(set) * p.set_stride + static_cast<size_t>(m) * 3 * p.M;
-    D3 h0, h1;
-    const int cnt = warp_first_two_hits<A, Real, false>(mesh, p.n, p.M, t1, d, h0, h1);
-    if (lane == 0) {
-        if (cnt == 2) {
-            const double s0 = dot3<A>(sub3<A>(h0, t1), sub3<A>(h0, t2));  // HRM3D.cpp:344-351
-            const double s1 = dot3<A>(sub3<A>(h1, t1), sub3<A>(h1, t2));
-            if ((s0 < 0) || (s1 < 0)) p.flag[e] = 1u;
-        } else if (cnt == 1) {
-            atomicAdd(p.counters + 2, 1ULL);  // single hit: reference reads out of bounds; defined as not blocking
+        for (int i = 0; i < 3; ++i)
+            if (fabs(dc[i]) < 1e-6 && (oc[i] > bb[2 * i + 1] || oc[i] < bb[2 * i])) live = false;
+    }
+    unsigned todo = __ballot_sync(0xFFFFFFFFu, live);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int es = __shfl_sync(0xFFFFFFFFu, e, src), ms = __shfl_sync(0xFFFFFFFFu, m, src), ss = __shfl_sync(0xFFFFFFFFu, set, src);
+        const D3 a1 = {__shfl_sync(0xFFFFFFFFu, t1.x, src), __shfl_sync(0xFFFFFFFFu, t1.y, src), __shfl_sync(0xFFFFFFFFu, t1.z, src)};
+        const D3 a2 = {__shfl_sync(0xFFFFFFFFu, t2.x, src), __shfl_sync(0xFFFFFFFFu, t2.y, src), __shfl_sync(0xFFFFFFFFu, t2.z, src)};
+        const D3 dd = {__shfl_sync(0xFFFFFFFFu, d.x, src), __shfl_sync(0xFFFFFFFFu, d.y, src), __shfl_sync(0xFFFFFFFFu, d.z, src)};
+        const Real* mesh = reinterpret_cast<const Real*>(p.mesh) + static_cast<size_t>(ss) * p.set_stride + static_cast<size_t>(ms) * 3 * p.M;
+        D3 h0, h1;
+        const int cnt = warp_first_two_hits<A, Real, false>(mesh, p.n, p.M, a1, dd, h0, h1);
+        if (lane == 0) {
+            if (cnt == 2) {
+                const double s0 = dot3<A>(sub3<A>(h0, a1), sub3<A>(h0, a2));  // HRM3D.cpp:344-351
+                const double s1 = dot3<A>(sub3<A>(h1, a1), sub3<A>(h1, a2));
+                if ((s0 < 0) || (s1 < 0)) p.flag[es] = 1u;
+            } else if (cnt == 1) {
+                atomicAdd(p.counters + 2, 1ULL);  // single hit: reference reads out of bounds; defined as not blocking
+            }
         }
     }
 }
@@ -404,7 +424,7 @@ int launch_edges(Ctx* c, int k, int E, const double* d_v1, const double* d_v2, u
         const char* mesh = c->mesh.p + (static_cast<size_t>(k) * c->S + c->Sa) * c->dim * c->M * real;
         p.mesh = mesh;
         const long long work = static_cast<long long>(E) * So;
-        if ((c->dim == 3 ? work * 32 + 127 : work + 127) / 128 > 0x7FFFFFFFLL) return fail(c, HRMGPU_E_CAP, "test_edges: too many (edge, mesh) pairs for one launch");
+        if ((work + 127) / 128 > 0x7FFFFFFFLL) return fail(c, HRMGPU_E_CAP, "test_edges: too many (edge, mesh) pairs for one launch");
         if (c->dim == 3) {
             if ((rc = ensure(c, c->bbox, static_cast<size_t>(nset) * So * 6))) return rc;
             p.bbox = c->bbox.p;
@@ -413,7 +433,7 @@ int launch_edges(Ctx* c, int k, int E, const double* d_v1, const double* d_v2, u
             else
                 k_mesh_bbox<double><<<nset * So, 128, 0, c->stream>>>(reinterpret_cast<const double*>(mesh), 3, c->M, c->bbox.p, So, p.set_stride);
             HRMGPU_CUDA(c, cudaGetLastError());
-            const unsigned grid = static_cast<unsigned>((work * 32 + 127) / 128);
+            const unsigned grid = static_cast<unsigned>((work + 127) / 128);  // 32 items per warp, 4 warps per block
             if (c->prec == HRMGPU_F64_STRICT)
                 k_edges3d<Strict, double><<<grid, 128, 0, c->stream>>>(p);
             else if (c->prec == HRMGPU_F64)

@@ -1036,12 +1036,21 @@ class HRM3D : public HighwayRoadMapBase {
         // vertices of a layer carry the layer's quaternion, so the slerp rotations R_s and the rotated link offsets R_s * t_l
         // are the same for every candidate of a pair; they are evaluated once per pair with the operations robotTF performs,
         // and the kernel forms the body centres (interpolated position + offset) itself.
+        // The reference scans all |layer i| x |layer j| vertex pairs for the ones within two line spacings; here every layer's
+        // vertices are bucketed by sweep line (their x, y are grid values), a vertex looks only into the buckets around its own
+        // line, and the exact distance test and the ascending vertex order of the reference's inner loop are kept.
         struct PairCand {
             Index start = 0, n2 = 0, cur0 = 0, cur1 = 0;
-            size_t first = 0, count = 0;       // candidates [first, first + count) in pair order (m0 outer, m1 inner)
-            std::vector<unsigned char> state;  // [(m0 - start) * (cur1 - cur0) + (m1 - cur0)]: 0 no candidate, 1 blocked, 2 free
+            std::vector<size_t> first;  // candidates of vertex m0 = start + r: [first[r], first[r + 1]) of `cand`, ascending in m1
         };
         const size_t P = vertexIdx_.size(), T = steps + 1;
+        const int Lx = static_cast<int>(param_.numLineX), Ly = static_cast<int>(param_.numLineY);
+        const double dx = (lim[1] - lim[0]) / static_cast<double>(Lx - 1), dy = (lim[3] - lim[2]) / static_cast<double>(Ly - 1);
+        auto cellOf = [&](const std::vector<Coordinate>& v, int& ix, int& iy) {
+            ix = std::min(std::max(static_cast<int>(std::lround((v[0] - lim[0]) / dx)), 0), Lx - 1);
+            iy = std::min(std::max(static_cast<int>(std::lround((v[1] - lim[2]) / dy)), 0), Ly - 1);
+        };
+        const int wx = static_cast<int>(std::floor(thx / dx)) + 1, wy = static_cast<int>(std::floor(thy / dy)) + 1;  // window half-widths (lines)
         std::vector<PairCand> pc(P);
         std::vector<int> pairOf;
         std::vector<double> v0s, v1s, w0(T), w1(T), linkOff(P * T * B * 3, 0.0);
@@ -1051,13 +1060,13 @@ class HRM3D : public HighwayRoadMapBase {
         for (size_t s = 0; s < T; ++s) w1[s] = static_cast<double>(s) * dt, w0[s] = 1.0 - static_cast<double>(s) * dt;  // InterpolateSE3.cpp:5-29
         {
             StageScope ss(stage_, "  bridge candidates (host)");
+            std::vector<std::vector<Index>> cell(static_cast<size_t>(Lx) * Ly);
+            std::vector<Index> near;
             for (size_t i = 0; i < P; ++i) {
                 PairCand& c = pc[i];
                 c.cur0 = vertexIdx_[i].first, c.cur1 = vertexIdx_[i].second;
                 c.start = vertexIdx_[nearest[i]].first, c.n2 = vertexIdx_[nearest[i]].second;
-                c.first = cand.size();
                 if (c.n2 <= c.start || c.cur1 <= c.cur0) continue;
-                c.state.assign((c.n2 - c.start) * (c.cur1 - c.cur0), 0);
                 const auto& va = V[c.start];
                 const auto& vb = V[c.cur0];
                 const auto qs = interpolateSlerp({va[3], va[4], va[5], va[6]}, {vb[3], vb[4], vb[5], vb[6]}, steps);
@@ -1068,18 +1077,36 @@ class HRM3D : public HighwayRoadMapBase {
                         for (int d = 0; d < 3; ++d) linkOff[((i * T + s) * B + (l + 1)) * 3 + d] = v[d];
                     }
                 }
-                for (Index m0 = c.start; m0 < c.n2; ++m0)
-                    for (Index m1 = c.cur0; m1 < c.cur1; ++m1) {
-                        const auto& v0 = V[m0];
+                for (auto& cl : cell) cl.clear();
+                for (Index m1 = c.cur0; m1 < c.cur1; ++m1) {  // ascending ids: every bucket stays sorted
+                    int ix, iy;
+                    cellOf(V[m1], ix, iy);
+                    cell[static_cast<size_t>(ix) * Ly + iy].push_back(m1);
+                }
+                c.first.assign(c.n2 - c.start + 1, cand.size());
+                for (Index m0 = c.start; m0 < c.n2; ++m0) {
+                    const auto& v0 = V[m0];
+                    int ix0, iy0;
+                    cellOf(v0, ix0, iy0);
+                    near.clear();
+                    for (int ix = std::max(ix0 - wx, 0); ix <= std::min(ix0 + wx, Lx - 1); ++ix)
+                        for (int iy = std::max(iy0 - wy, 0); iy <= std::min(iy0 + wy, Ly - 1); ++iy)
+                            for (Index m1 : cell[static_cast<size_t>(ix) * Ly + iy]) {
+                                const auto& v1 = V[m1];
+                                if (std::fabs(v0[0] - v1[0]) > thx || std::fabs(v0[1] - v1[1]) > thy) continue;  // HRM3D.cpp:195-200
+                                near.push_back(m1);
+                            }
+                    std::sort(near.begin(), near.end());
+                    c.first[m0 - c.start] = cand.size();
+                    for (Index m1 : near) {
                         const auto& v1 = V[m1];
-                        if (std::fabs(v0[0] - v1[0]) > thx || std::fabs(v0[1] - v1[1]) > thy) continue;
-                        c.state[(m0 - c.start) * (c.cur1 - c.cur0) + (m1 - c.cur0)] = 1;
                         cand.push_back({m0, m1});
                         v0s.insert(v0s.end(), v0.begin(), v0.begin() + 3);
                         v1s.insert(v1s.end(), v1.begin(), v1.begin() + 3);
                         pairOf.push_back(static_cast<int>(i));
                     }
-                c.count = cand.size() - c.first;
+                }
+                c.first[c.n2 - c.start] = cand.size();
             }
         }
         std::vector<unsigned char> ok;
@@ -1088,19 +1115,17 @@ class HRM3D : public HighwayRoadMapBase {
             ok = freeSpace_.testTransitions(pairOf, v0s, v1s, w0, w1, linkOff);
         }
         for (size_t i = 0; i < P; ++i) {
-            PairCand& c = pc[i];
-            if (c.count == 0) continue;
-            const Index w = c.cur1 - c.cur0;
-            for (size_t j = 0; j < c.count; ++j)
-                if (ok[c.first + j]) c.state[(cand[c.first + j].first - c.start) * w + (cand[c.first + j].second - c.cur0)] = 2;
+            const PairCand& c = pc[i];
+            if (c.first.empty()) continue;
             Index n22 = c.cur0;  // replay with the reference's moving lower bound
             for (Index m0 = c.start; m0 < c.n2; ++m0)
-                for (Index m1 = n22; m1 < c.cur1; ++m1)
-                    if (c.state[(m0 - c.start) * w + (m1 - c.cur0)] == 2) {
-                        addEdge(m0, m1);
-                        n22 = m1;
-                        break;
-                    }
+                for (size_t j = c.first[m0 - c.start]; j < c.first[m0 - c.start + 1]; ++j) {
+                    const Index m1 = cand[j].second;
+                    if (m1 < n22 || !ok[j]) continue;
+                    addEdge(m0, m1);
+                    n22 = m1;
+                    break;
+                }
         }
     }
 
