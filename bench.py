@@ -60,30 +60,40 @@ def cpu_layers_per_s(n_obs_sample, layers, threads):
 
 
 def plan_ms_block():
-    """Secondary metric of BASELINE.json ('end-to-end plan ms'): HRM3D::plan() on the bundled cluttered map (configs[1]:
-    1+7 superquadrics, rabbit robot, q_icosahedron_60, n=10, 11x5 lines) through the C++ host layer + GPU kernels, next to the
-    CPU oracle planner on one core.  Roadmaps are identical (tests/test_gpu_planner.py)."""
+    """Secondary metric of BASELINE.json ('end-to-end plan ms'): HRM3D::plan() through the C++ host layer + GPU kernels next to
+    the CPU oracle planner on one core, on the bundled cluttered map (configs[1]: 1+7 superquadrics, rabbit robot,
+    q_icosahedron_60, n=10, 11x5 lines) and on the maze map with dense sweep lines (configs[2]: 44x20 lines).  The wall clock
+    of the GPU arm includes creating the context and uploading the scene.  Roadmaps are identical (tests/test_gpu_planner.py)."""
     import json as _json
 
     from hrm_b200 import hostlib
     from oracle import hrmo
 
-    sc = _json.load(open(os.path.join(ROOT, "tests", "golden", "scenes.json")))["3D_superquadrics_cluttered_rabbit"]
-    rows = np.array(sc["arena"] + sc["obstacle"])
-    a = (1, len(sc["obstacle"]), rows, 10, np.array(sc["robot"]), np.array(sc["quats"]), sc["lim"], sc["Lx"], sc["Ly"], 5, sc["end_points"][0],
-         sc["end_points"][1])
-    t = []
-    for _ in range(4):
+    scenes = _json.load(open(os.path.join(ROOT, "tests", "golden", "scenes.json")))
+
+    def one(name, Lx, Ly, label):
+        sc = scenes[name]
+        rows = np.array(sc["arena"] + sc["obstacle"])
+        a = (1, len(sc["obstacle"]), rows, 10, np.array(sc["robot"]), np.array(sc["quats"]), sc["lim"], Lx or sc["Lx"], Ly or sc["Ly"], 5,
+             sc["end_points"][0], sc["end_points"][1])
+        t = []
+        for _ in range(4):
+            t0 = time.perf_counter()
+            got = hostlib.plan3d(*a, per_orientation=True, precision=0)
+            t.append((time.perf_counter() - t0) * 1e3)
         t0 = time.perf_counter()
-        got = hostlib.plan3d(*a, per_orientation=True, precision=0)
-        t.append((time.perf_counter() - t0) * 1e3)
-    t0 = time.perf_counter()
-    ref = hrmo.plan3d(*a, per_orientation=True)
-    cpu_ms = (time.perf_counter() - t0) * 1e3
-    return {"scene": "HRM3D cluttered/rabbit (BASELINE.json configs[1]), 60 C-layers, n=10, 11x5 lines, per-orientation, F64_STRICT",
-            "gpu_plan_ms": sorted(t[1:])[len(t[1:]) // 2], "cpu_oracle_plan_ms": cpu_ms, "cpu_cores": 1, "solved": bool(got["solved"]),
-            "vertices": int(len(got["vertex"])), "edges": int(len(got["edge"])), "identical_roadmap": bool(
-                np.array_equal(got["vertex"], ref["vertex"]) and np.array_equal(got["edge"], ref["edge"]))}
+        ref = hrmo.plan3d(*a, per_orientation=True)
+        cpu_ms = (time.perf_counter() - t0) * 1e3
+        return {"scene": label, "gpu_plan_ms": sorted(t[1:])[len(t[1:]) // 2], "gpu_plan_ms_planner_clock": got["total_time_s"] * 1e3,
+                "cpu_oracle_plan_ms": cpu_ms, "cpu_cores": 1, "solved": bool(got["solved"]), "vertices": int(len(got["vertex"])),
+                "edges": int(len(got["edge"])), "edge_tests": int(got["edge_tests"]), "gpu_launches": int(got["gpu_launches"]),
+                "identical_roadmap": bool(np.array_equal(got["vertex"], ref["vertex"]) and np.array_equal(got["edge"], ref["edge"]))}
+
+    out = one("3D_superquadrics_cluttered_rabbit", 0, 0,
+              "HRM3D cluttered/rabbit (BASELINE.json configs[1]), 60 C-layers, n=10, 11x5 lines, per-orientation, F64_STRICT")
+    out["dense"] = one("3D_superquadrics_maze_rabbit", 44, 20,
+                       "HRM3D maze/rabbit with dense sweep lines (BASELINE.json configs[2]), 60 C-layers, n=10, 44x20 lines, per-orientation, F64_STRICT")
+    return out
 
 
 def run_reference(args):
@@ -306,6 +316,11 @@ def run_gpu(args):
             cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": "%d full layers (1 per host thread, %d threads) of the same workload, %.1f s; oracle = CPU restatement "
                              "of the reference (reference not buildable here: Eigen absent)" % (threads, threads, sec)}
+            # the reference itself is single-threaded: the same oracle on ONE core, bounded sample
+            v1, sec1 = cpu_layers_per_s(124, 1, 1)
+            cpu["single_core"] = {"value": v1, "unit": UNIT, "cores": 1,
+                                  "sample": "1 layer over the arena + first 124 obstacles (125/1001 of a layer's surfaces), %.1f s, scaled "
+                                            "to full-layer equivalents" % sec1}
         plan = None
         if world == 1 and not args.no_cpu_baseline:
             try:
