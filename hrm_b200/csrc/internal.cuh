@@ -73,7 +73,7 @@ struct Ctx {
     DevBuf<char> mesh;                           // [K][S][dim][M] planar, double (or float in F32 mode)
     DevBuf<double> ivl_lo, ivl_up;               // [K][S][L]
     int num_sms = 148;                           // multiprocessors of the device
-    int seg_fast_cap = 0;                        // test hook: list capacity of the 4-line segment pass (0 = default 256)
+    int seg_fast_cap = 0;                        // test hook: list capacity of the 4-line segment pass (0 = default 128)
     bool force_seg_fallback = false;             // test hook: always use the one-line-per-warp pass
     DevBuf<double> orig;                         // [K][L][So+1][2] original (pre-enhancement) segments
     DevBuf<int> orig_cnt;                        // [K][L]

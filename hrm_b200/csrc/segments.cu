@@ -21,7 +21,7 @@
 namespace hrmgpu {
 
 constexpr int kSegWarps = 8;
-constexpr int kSeg4Warps = 7;  // 4-line pass: 7 warps x 16 KB of lists = 112 KB per CTA, two CTAs per SM
+constexpr int kSeg4Warps = 7;  // 4-line pass: 7 warps x 8 KB of lists (128 intervals per line) = 56 KB per CTA; 256-entry lists measured 3% slower per step
 
 struct SegParams {
     const double* lo;   // [K][S][L]
@@ -514,7 +514,7 @@ int launch_segments(Ctx* c) {
     p.only_flagged = 0;
     if (c->L % 4 == 0 && !c->force_seg_fallback) {
         // fast path: a warp per 4 lines with short lists, then the full-size kernel on a small grid for flagged lines
-        const int cap4 = std::min(p.sort_cap, c->seg_fast_cap > 0 ? c->seg_fast_cap : 256);
+        const int cap4 = std::min(p.sort_cap, c->seg_fast_cap > 0 ? c->seg_fast_cap : 128);
         const size_t smem4 = static_cast<size_t>(kSeg4Warps) * 8 * cap4 * sizeof(double);
         HRMGPU_CUDA(c, cudaFuncSetAttribute(k_line_segments4, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem4)));
         const long long groups = nl / 4;
