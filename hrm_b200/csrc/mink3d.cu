@@ -151,7 +151,9 @@ struct alignas(2 * sizeof(Real)) Real2 {
 constexpr int kColStride = 12;
 
 template <int MODE, bool SWEEP, bool CODE8>
-__global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : 3) k_minksweep3d(const MinkParams p) {
+// CTAs per SM: 2 (strict: 128 registers), 3 (f64: 80 registers), 4 (f32: 64 registers without spills; measured +11 % over 3.
+// The f64 variant spills in phase A at 64 registers and loses 25 %).
+__global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : (MODE == HRMGPU_F32 ? 4 : 3)) k_minksweep3d(const MinkParams p) {
     using Code = typename std::conditional<CODE8, uint16_t, uint32_t>::type;  // packed line codes: 2 x 8 or 2 x 16 bits
     using A = typename std::conditional<MODE == HRMGPU_F64_STRICT, Strict, Fast>::type;
     using Real = typename RealOf<MODE>::type;
@@ -840,12 +842,16 @@ static size_t smem_layout(MinkParams& p, int MODE, bool sweep, bool code8, int n
     auto al = [](size_t v) { return (v + 15) & ~size_t(15); };
     size_t b = al(real * 8 * n);  // tab
     p.o_mats = static_cast<int>(b), b += sizeof(double) * (36 + 18);  // + 18 row-base coefficients (fast modes)
-    p.o_cc = static_cast<int>(b);
-    if (MODE != HRMGPU_F64_STRICT) b += al(real * kColStride * n);
     p.o_txs = static_cast<int>(b), p.o_tys = static_cast<int>(b + (sweep ? sizeof(double) * (Lx + 2) : 0));
     if (sweep) b += al(sizeof(double) * (Lx + Ly + 4));
-    p.o_zq = static_cast<int>(b), b += sweep ? sizeof(double) * kQueueCap : 0;
-    p.o_queue = static_cast<int>(b), b += sweep ? sizeof(uint2) * kQueueCap : 0;
+    // the column table is read in phase A only, the candidate queue is used behind the barrier that ends phase A: one region
+    p.o_cc = static_cast<int>(b);
+    p.o_zq = static_cast<int>(b), p.o_queue = static_cast<int>(b + (sweep ? sizeof(double) * kQueueCap : 0));
+    {
+        const size_t cc_bytes = (MODE != HRMGPU_F64_STRICT) ? al(real * kColStride * n) : 0;
+        const size_t q_bytes = sweep ? (sizeof(double) + sizeof(uint2)) * kQueueCap : 0;
+        b += cc_bytes > q_bytes ? cc_bytes : q_bytes;
+    }
     p.o_vcode = static_cast<int>(b), b += sweep ? al((code8 ? 2 : 4) * (static_cast<size_t>(n) * n + 8)) : 0;
     const size_t L = static_cast<size_t>(Lx) * Ly;
     p.o_zc0 = static_cast<int>(b), p.o_zc1 = static_cast<int>(b + (sweep ? sizeof(double) * L : 0)), b += sweep ? sizeof(double) * 2 * L : 0;
