@@ -116,6 +116,10 @@ class Context:
         return rc
 
     # ---- setup ----
+    def last_error(self):
+        """Message of the last failed call (hrmgpu_last_error)."""
+        return self.lib.hrmgpu_last_error(self.h).decode()
+
     def set_stream(self, cuda_stream_ptr):
         self._chk(self.lib.hrmgpu_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
 

@@ -684,6 +684,22 @@ long long hrmgpu_debug_phase_times(hrmgpu_ctx* c, int enable, long long n_cta, l
     return rc ? rc : 0;
 }
 
+// Profiling aid: re-runs K1 alone (boundary points of the last 3D build's poses, no sweep, meshes overwritten in place)
+// and returns the kernel time in ms -- the ceiling of the fused kernel if the sweep were free.
+double hrmgpu_debug_k1_only_ms(hrmgpu_ctx* c) {
+    if (!c || !c->built || c->dim != 3) return -1.0;
+    if (cudaSetDevice(c->device) != cudaSuccess) return -1.0;
+    cudaEventRecord(c->ev0, c->stream);
+    if (launch_minksweep3d(c, c->K, c->B, 0, c->n_arena + c->n_obs, c->body_semi.p, c->body_R.p, c->body_off.p, c->prec, c->mesh.p, nullptr,
+                           nullptr, false))
+        return -1.0;
+    cudaEventRecord(c->ev1, c->stream);
+    if (cudaEventSynchronize(c->ev1) != cudaSuccess) return -1.0;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) != cudaSuccess) return -1.0;
+    return static_cast<double>(ms);
+}
+
 long long hrmgpu_kernel_launches(hrmgpu_ctx* c, int reset) {
     if (!c) return HRMGPU_E_ARG;
     const long long v = c->launches;

@@ -589,48 +589,48 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : (MOD
     const uint32_t upr_magic = (UPR > 1) ? 0xFFFFFFFFu / static_cast<uint32_t>(UPR) + 1u : 0u;  // u / UPR == umulhi(u, magic), u < 2^16
     const bool vec_ok = (n & 3) == 0;
     constexpr int kUPL = 4;  // units per lane and batch: smaller batches balance the warps better, larger ones amortise the prefix scan
+    static_assert(kUPL <= 4, "unit_cells packs the cells of unit uu at bits 7 + 2 * uu, 8 + 2 * uu, 23 + 2 * uu, 24 + 2 * uu");
     const int lane = tid & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
-    // keep bits of the 8 faces of unit u
-    auto unit_bits = [&](int unit) -> uint32_t {
+    // B1: cells of unit u whose inclusive xy bounding box (over the 4 corners) may contain a sweep line.  Per axis the set of
+    // lines inside the box of a vertex set is empty  <=>  all codes (2*lo + eq) are equal and even, so a cell is kept iff on
+    // BOTH axes some corner code differs from the first one or is odd: XOR / OR over packed codes, no min/max.  The two faces
+    // of a kept cell are tested exactly in B2.  Result layout (per unit, before the batch shift): cell 0 -> bit 7, cell 2 ->
+    // bit 8, cell 1 -> bit 23, cell 3 -> bit 24 (where the SWAR form leaves them).
+    auto unit_cells = [&](int unit) -> uint32_t {
         const int i = (UPR > 1) ? static_cast<int>(__umulhi(static_cast<uint32_t>(unit), upr_magic)) : unit;
         const int j0 = 4 * (unit - i * UPR);
         const int q = i * n + j0;
-        uint32_t r0[5], r1[5];
-        if (vec_ok && !CODE8) {
-            const uint4 a = *reinterpret_cast<const uint4*>(vcode + q);
-            const uint4 b = *reinterpret_cast<const uint4*>(vcode + q + n);
-            r0[0] = a.x, r0[1] = a.y, r0[2] = a.z, r0[3] = a.w;
-            r1[0] = b.x, r1[1] = b.y, r1[2] = b.z, r1[3] = b.w;
-        } else if (vec_ok) {  // four 2x8-bit codes per 64-bit load, expanded to the 2x16-bit SIMD form
+        uint32_t g;
+        if (vec_ok && CODE8) {
+            // four vertices (x byte, y byte each) per 64-bit load; sa / sb = the same rows advanced by one vertex
             const uint2 a = *reinterpret_cast<const uint2*>(vcode + q);
             const uint2 b = *reinterpret_cast<const uint2*>(vcode + q + n);
-            r0[0] = __byte_perm(a.x, 0u, 0x4140), r0[1] = __byte_perm(a.x, 0u, 0x4342);
-            r0[2] = __byte_perm(a.y, 0u, 0x4140), r0[3] = __byte_perm(a.y, 0u, 0x4342);
-            r1[0] = __byte_perm(b.x, 0u, 0x4140), r1[1] = __byte_perm(b.x, 0u, 0x4342);
-            r1[2] = __byte_perm(b.y, 0u, 0x4140), r1[3] = __byte_perm(b.y, 0u, 0x4342);
+            const uint32_t a4 = static_cast<uint32_t>(vcode[q + 4]), b4 = static_cast<uint32_t>(vcode[q + n + 4]);
+            const uint32_t sax = __funnelshift_r(a.x, a.y, 16), say = __funnelshift_r(a.y, a4, 16);
+            const uint32_t sbx = __funnelshift_r(b.x, b.y, 16), sby = __funnelshift_r(b.y, b4, 16);
+            const uint32_t dx = (a.x ^ b.x) | (a.x ^ sax) | (a.x ^ sbx) | ((a.x | b.x | sax | sbx) & 0x01010101u);
+            const uint32_t dy = (a.y ^ b.y) | (a.y ^ say) | (a.y ^ sby) | ((a.y | b.y | say | sby) & 0x01010101u);
+            // bit 7 of every non-zero byte, then both bytes of a vertex field
+            const uint32_t nx = (((dx & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | dx), ny = (((dy & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | dy);
+            const uint32_t fx = nx & (nx >> 8) & 0x00800080u, fy = ny & (ny >> 8) & 0x00800080u;
+            g = fx + (fy << 1);
         } else {
+            uint32_t r0[5], r1[5];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) r0[e] = code_at(q + e), r1[e] = code_at(q + n + e);
-        }
-        r0[4] = code_at(q + 4);
-        r1[4] = code_at(q + n + 4);
-        uint32_t bits = 0;
+            for (int e = 0; e < 5; ++e) r0[e] = code_at(q + e), r1[e] = code_at(q + n + e);
+            g = 0;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const uint32_t c00 = r0[e], c01 = r0[e + 1], c10 = r1[e], c11 = r1[e + 1];
-            // Per axis with mn = min code, mx = max code (code = 2*lo + eq): the face covers lines [mn >> 1, (mx + 1) >> 1),
-            // non-empty  <=>  (mn | 1) < mx + (mx & 1)  <=>  no borrow out of bit 14 in (mx + (mx & 1)) - (mn | 1) - 1,
-            // evaluated as a packed add of the complement (codes < 2^15).
-            const uint32_t mnA = __vimin3_u16x2(c00, c11, c10), mxA = __vimax3_u16x2(c00, c11, c10);
-            const uint32_t mnB = __vimin3_u16x2(c00, c11, c01), mxB = __vimax3_u16x2(c00, c11, c01);
-            const uint32_t dA = __vadd2(__vadd2(mxA, mxA & 0x00010001u), ~(mnA | 0x00010001u));
-            const uint32_t dB = __vadd2(__vadd2(mxB, mxB & 0x00010001u), ~(mnB | 0x00010001u));
-            if ((dA & 0x80008000u) == 0u) bits |= 1u << (2 * e);
-            if ((dB & 0x80008000u) == 0u) bits |= 2u << (2 * e);
+            for (int e = 0; e < 4; ++e) {
+                const uint32_t d = (r0[e] ^ r1[e]) | (r0[e] ^ r0[e + 1]) | (r0[e] ^ r1[e + 1]) | ((r0[e] | r1[e] | r0[e + 1] | r1[e + 1]) & 0x00010001u);
+                if ((d & 0xFFFFu) != 0u && (d >> 16) != 0u) g |= 1u << ((e & 1 ? 23 : 7) + (e >> 1));
+            }
         }
-        if (j0 + 4 > nc1) bits &= (1u << (2 * (nc1 - j0))) - 1u;  // cells past the end of the mesh row
-        return bits;
+        if (j0 + 4 > nc1) {  // cells past the end of the mesh row
+            const int v = nc1 - j0;
+            g &= (v == 1) ? 0x00000080u : ((v == 2) ? 0x00800080u : 0x00800180u);
+        }
+        return g;
     };
 
     // B2 state of a warp: batch of 32 words [bw*32, bw*32+32), its words / popcount prefix, the rank chunk r0, and per lane
@@ -641,7 +641,8 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : (MOD
     uint32_t r0c = 0;              // first rank of the current chunk of 32 set bits
     bool chunk_started = false;    // warp-uniform: the lanes have taken their set bit of the current chunk
     bool face_open = false;
-    uint32_t six = 0, siy = 0, f_lox = 0, f_loy = 0, f_hix = 0, f_hiy = 0, f_id = 0;
+    uint32_t cur = 0, f_lo2 = 0, f_hi2 = 0, f_id = 0;  // packed (ix | iy << 16): next line, first lines, end lines of the open face
+    uint32_t pend_lo = 0, pend_hi = 0;  // line set of the cell's second face while the first one is being pushed (pend_hi != 0)
     bool scanning = true;          // warp-uniform
     for (;;) {
         long long tb2 = 0;
@@ -658,7 +659,7 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : (MOD
 #pragma unroll
                 for (int uu = 0; uu < kUPL; ++uu) {
                     const int unit = (bw * 32 + lane) * kUPL + uu;
-                    if (unit < nunits) w_bits |= unit_bits(unit) << (8 * uu);
+                    if (unit < nunits) w_bits += unit_cells(unit) << (2 * uu);
                 }
                 w_cnt = __popc(w_bits);
                 w_incl = w_cnt;
@@ -696,20 +697,27 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : (MOD
                         uint32_t x = wsrc;
                         for (uint32_t k = rank - excl; k > 0; --k) x &= x - 1;  // drop the lower set bits of that word
                         const int bit = __ffs(x) - 1;
-                        const int unit = (bw * 32 + src) * kUPL + (bit >> 3), half = bit & 1;
+                        // decode (see unit_cells): bits 7.. hold cells 0 / 2, bits 23.. cells 1 / 3 of the lane's kUPL units
+                        const int hi = bit >= 23 ? 1 : 0, pb = bit - (hi ? 23 : 7);
+                        const int unit = (bw * 32 + src) * kUPL + (pb >> 1);
                         const int i = (UPR > 1) ? static_cast<int>(__umulhi(static_cast<uint32_t>(unit), upr_magic)) : unit;
-                        const int j = 4 * (unit - i * UPR) + ((bit >> 1) & 3);
+                        const int j = 4 * (unit - i * UPR) + (((pb & 1) << 1) | hi);
                         const int q = i * n + j;
-                        const uint32_t c00 = code_at(q), c11 = code_at(q + n + 1);
-                        const uint32_t cm = half ? code_at(q + 1) : code_at(q + n);
-                        const uint32_t mn = __vminu2(__vminu2(c00, c11), cm), mxx = __vmaxu2(__vmaxu2(c00, c11), cm);
-                        // lo = min(2*lo+eq) >> 1 ; hi+1 = (max(2*lo+eq) + 1) >> 1  (per 16-bit half): lines [lo, hi)
-                        const uint32_t lo2 = (mn >> 1) & 0x7FFF7FFFu;
-                        const uint32_t hi2 = ((mxx + 0x00010001u) >> 1) & 0x7FFF7FFFu;
-                        f_lox = lo2 & 0xFFFFu, f_loy = lo2 >> 16, f_hix = hi2 & 0xFFFFu, f_hiy = hi2 >> 16;
-                        f_id = static_cast<uint32_t>(i * nc1 + j + (half ? ncell : 0));
-                        six = f_lox, siy = f_loy;
-                        face_open = true;  // B1's test is exact: the line set of a set bit is never empty
+                        // exact line sets of the cell's two faces (q, q+n, q+n+1) and (q, q+1, q+n+1): per 16-bit half,
+                        // lo = min(2*lo+eq) >> 1 ; hi+1 = (max(2*lo+eq) + 1) >> 1, lines [lo, hi)
+                        const uint32_t c00 = code_at(q), c11 = code_at(q + n + 1), c10 = code_at(q + n), c01 = code_at(q + 1);
+                        const uint32_t mnA = __vimin3_u16x2(c00, c11, c10), mxA = __vimax3_u16x2(c00, c11, c10);
+                        const uint32_t mnB = __vimin3_u16x2(c00, c11, c01), mxB = __vimax3_u16x2(c00, c11, c01);
+                        const uint32_t loA = (mnA >> 1) & 0x7FFF7FFFu, hiA = ((mxA + 0x00010001u) >> 1) & 0x7FFF7FFFu;
+                        const uint32_t loB = (mnB >> 1) & 0x7FFF7FFFu, hiB = ((mxB + 0x00010001u) >> 1) & 0x7FFF7FFFu;
+                        const bool okA = (loA & 0xFFFFu) < (hiA & 0xFFFFu) && (loA >> 16) < (hiA >> 16);
+                        const bool okB = (loB & 0xFFFFu) < (hiB & 0xFFFFu) && (loB >> 16) < (hiB >> 16);
+                        f_lo2 = okA ? loA : loB, f_hi2 = okA ? hiA : hiB;
+                        f_id = static_cast<uint32_t>(i * nc1 + j + (okA ? 0 : ncell));
+                        cur = f_lo2;
+                        face_open = okA || okB;  // the cell test is a superset of the two face tests
+                        pend_lo = loB;
+                        pend_hi = (okA && okB) ? hiB : 0u;  // != 0: the second face of the cell follows the first one
                     }
                 }
                 // push the lines of the open faces, one per lane per iteration, one atomic per warp
@@ -725,9 +733,18 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : (MOD
                     if (has) {
                         const int pos = base + __popc(bal & lt_mask);
                         if (pos < static_cast<int>(kPosMask)) {  // slots 0..kPosMask-1; kPosMask is the 'committed' marker
-                            queue[pos] = make_uint2(f_id, six | (siy << 16));
-                            if (++siy == f_hiy) siy = f_loy, ++six;
-                            if (six >= f_hix) face_open = false;
+                            queue[pos] = make_uint2(f_id, cur);
+                            cur += 0x10000u;  // y fastest
+                            if ((cur >> 16) == (f_hi2 >> 16)) cur = ((cur & 0xFFFFu) + 1u) | (f_lo2 & 0xFFFF0000u);
+                            if ((cur & 0xFFFFu) >= (f_hi2 & 0xFFFFu)) {
+                                if (pend_hi != 0u) {  // go on with face (q, q+1, q+n+1) of the same cell
+                                    f_lo2 = pend_lo, f_hi2 = pend_hi, pend_hi = 0u;
+                                    f_id += static_cast<uint32_t>(ncell);
+                                    cur = f_lo2;
+                                } else {
+                                    face_open = false;
+                                }
+                            }
                         } else {
                             over = true;  // queue full: keep the position, resume after the drain
                         }
@@ -867,7 +884,11 @@ static void pick_mapping(int n, int& lpc, int& groups, int& paired) {
     groups = kThreads / 32;
     paired = 0;
     if ((n & 1) == 0) {  // paired rows: lanes-per-column must divide n / 2
-        for (int l = 32; l >= 2; --l) {
+        // A group may be wider than a warp: with lpc = n / 2 a group stores a whole eta-column (n values, contiguous) per
+        // iteration and the CTA `groups` adjacent columns -- whole 32-byte sectors only.  (A column split over two passes
+        // leaves a half-written sector per column and plane whenever lpc * 16 bytes is not a multiple of 32: the L2 fills
+        // it from DRAM, and those reads inside the write stream cost ~40 % of the store bandwidth; measured.)
+        for (int l = (n / 2 < kThreads / 2 ? n / 2 : kThreads / 2); l >= 2; --l) {
             if ((n / 2) % l) continue;
             const int g = kThreads / l;
             const double steps = static_cast<double>(n / (2 * l)) * ((n + g - 1) / g);
