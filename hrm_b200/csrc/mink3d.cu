@@ -658,7 +658,7 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : (MOD
                 w_bits = 0u;
 #pragma unroll
                 for (int uu = 0; uu < kUPL; ++uu) {
-                    const int unit = (bw * 32 + lane) * kUPL + uu;
+                    const int unit = (bw * kUPL + uu) * 32 + lane;  // consecutive lanes read consecutive 8-byte words: no bank conflicts
                     if (unit < nunits) w_bits += unit_cells(unit) << (2 * uu);
                 }
                 w_cnt = __popc(w_bits);
@@ -699,7 +699,7 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : (MOD
                         const int bit = __ffs(x) - 1;
                         // decode (see unit_cells): bits 7.. hold cells 0 / 2, bits 23.. cells 1 / 3 of the lane's kUPL units
                         const int hi = bit >= 23 ? 1 : 0, pb = bit - (hi ? 23 : 7);
-                        const int unit = (bw * 32 + src) * kUPL + (pb >> 1);
+                        const int unit = (bw * kUPL + (pb >> 1)) * 32 + src;
                         const int i = (UPR > 1) ? static_cast<int>(__umulhi(static_cast<uint32_t>(unit), upr_magic)) : unit;
                         const int j = 4 * (unit - i * UPR) + (((pb & 1) << 1) | hi);
                         const int q = i * n + j;
