@@ -12,7 +12,7 @@
 namespace hrmgpu {
 
 constexpr int kThreads = 256;          // CTA size of the fused Minkowski+sweep kernel
-constexpr int kQueueCap = 512;         // candidate (face,line) queue entries in shared memory
+constexpr int kCellCap = 2048;         // kept mesh cells listed per scan round in shared memory
 constexpr int kMaxGrid = 200;          // n_grid limit (vertex line codes: 4*n^2 bytes of shared memory)
 constexpr int kMaxLinesAxis = 16383;   // per-axis sweep-line limit (15-bit line codes)
 constexpr int kMaxLines = 8192;        // Lx*Ly limit (two-slot hit tables in shared memory)

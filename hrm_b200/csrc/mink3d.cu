@@ -54,15 +54,13 @@ struct MinkParams {
     int reload;                             // re-sweep: the boundary points are read back from `mesh` instead of being computed
     // byte offsets of the shared-memory regions (host-computed, see smem_layout): read from the constant bank instead of
     // being re-derived from n, Lx, Ly wherever the compiler rematerialises a pointer
-    int o_mats, o_cc, o_txs, o_tys, o_zq, o_queue, o_vcode, o_zc0, o_zc1, o_m0, o_m1, o_qcount;
+    int o_mats, o_cc, o_txs, o_tys, o_queue, o_vcode, o_m0, o_m1, o_qcount;
     double inv_dx, bias_x, inv_dy, bias_y;  // line-index guess g = x*inv_d + bias
     double bias_xq, bias_yq;                // bias + 1.5 * 2^36 + (1 - 2^-16): Q15.16 conversion and ceil folded into the FMA
     double zlow, zup;
 };
 
-constexpr uint32_t kPosBits = 9;
-constexpr uint32_t kPosMask = (1u << kPosBits) - 1u;  // == "not queued"
-static_assert((1u << kPosBits) == kQueueCap, "queue slots must fit the packed hit entries");
+static_assert(kMaxGrid * kMaxGrid <= 65536, "cell ids are listed as 16-bit values");
 
 // Exact classification of a coordinate against the sweep grid: smallest line index i in [0, Lc] with
 // t_i >= x (Lc if none) and whether t_i == x, packed as 2*i + eq.  ts is sentinel padded:
@@ -186,7 +184,7 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : (MOD
     const int ln = tid - grp * p.lpc;
     const bool worker = grp < p.groups;
 
-    long long t_start = 0, t_pro = 0, t_a = 0, t_scan = 0, t_drain = 0, acc_b2 = 0;
+    long long t_start = 0, t_pro = 0, t_a = 0, t_scan = 0, t_drain = 0;
     __shared__ unsigned long long dbg_max[4];
     if (threadIdx.x < 4) dbg_max[threadIdx.x] = 0;
     int rounds = 0;
@@ -198,18 +196,15 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : (MOD
     Real* cc = reinterpret_cast<Real*>(smem_raw + p.o_cc);                     // [n][kColStride] per-column constants (fast modes)
     double* txs = reinterpret_cast<double*>(smem_raw + p.o_txs);               // [Lx+2]
     double* tys = reinterpret_cast<double*>(smem_raw + p.o_tys);               // [Ly+2]
-    double* zq = reinterpret_cast<double*>(smem_raw + p.o_zq);                 // [kQueueCap] z of queued hits
-    uint2* queue = reinterpret_cast<uint2*>(smem_raw + p.o_queue);             // [kQueueCap] (face, ix | iy << 16)
+    uint16_t* cellq = reinterpret_cast<uint16_t*>(smem_raw + p.o_queue);       // [kCellCap] kept cells (cell = i * (n-1) + j)
+    uint16_t* heavyq = cellq + kCellCap;                                       // [kCellCap] of which: many candidates
     Code* vcode = reinterpret_cast<Code*>(smem_raw + p.o_vcode);               // [M + 8]: the 5th code of the last unit
     auto pack_code = [](uint32_t cx, uint32_t cy) -> Code { return static_cast<Code>(CODE8 ? (cx | (cy << 8)) : (cx | (cy << 16))); };
     // expanded form used by the SIMD min/max tests: x code in bits 0..15, y code in bits 16..31
     auto code_at = [&](int q) -> uint32_t { return CODE8 ? __byte_perm(static_cast<uint32_t>(vcode[q]), 0u, 0x4140) : static_cast<uint32_t>(vcode[q]); };
-    double* zc0 = reinterpret_cast<double*>(smem_raw + p.o_zc0);               // [L] committed z of the two lowest hit faces
-    double* zc1 = reinterpret_cast<double*>(smem_raw + p.o_zc1);               // [L]
     uint32_t* m0 = reinterpret_cast<uint32_t*>(smem_raw + p.o_m0);             // [L]
     uint32_t* m1 = reinterpret_cast<uint32_t*>(smem_raw + p.o_m1);             // [L]
-    int* qcount = reinterpret_cast<int*>(smem_raw + p.o_qcount);               // [0] queue fill, [1] next scan batch
-    int* batch_ctr = qcount + 1;
+    int* qcount = reinterpret_cast<int*>(smem_raw + p.o_qcount);               // [0] listed cells, [1] next scan batch, [2] heavy cells
 
     const Obj3& ob = p.obj[obj_id];
     const bool sign_neg = __ldg(&ob.sign) < 0.0;  // arena surface (requested here, consumed in phase D)
@@ -225,7 +220,7 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : (MOD
             for (int i = tid; i < p.Lx + 2; i += kThreads) txs[i] = __ldg(p.txs + i);
             for (int i = tid; i < p.Ly + 2; i += kThreads) tys[i] = __ldg(p.tys + i);
             for (int i = tid; i < p.L; i += kThreads) m0[i] = kNoFace, m1[i] = kNoFace;
-            if (tid == 0) *qcount = 0, *batch_ctr = 0;
+            if (tid == 0) qcount[0] = 0, qcount[1] = 0, qcount[2] = 0;
             __syncthreads();
             for (int i = tid; i < M; i += kThreads) {
                 const uint32_t cx = line_code(static_cast<double>(mx[i]), txs, p.Lx, p.inv_dx, p.bias_x);
@@ -258,7 +253,7 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : (MOD
             if (tid < p.Lx + 2) vx = __ldg(p.txs + tid);
             if (tid < p.Ly + 2) vy = __ldg(p.tys + tid);
             for (int i = tid; i < p.L; i += kThreads) m0[i] = kNoFace, m1[i] = kNoFace;
-            if (tid == 0) *qcount = 0, *batch_ctr = 0;
+            if (tid == 0) qcount[0] = 0, qcount[1] = 0, qcount[2] = 0;
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -572,31 +567,31 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : (MOD
         }
     };
 
-    // ---- phases B + C, interleaved: scan cells -> queue candidates -> cooperative drain ----------
-    // A thread scans its cells and pushes (face, line) candidates until the shared queue is full, then
-    // parks its scan position.  The whole CTA drains the queue (one candidate per thread at a time, so
-    // even faces that cover hundreds of lines -- the eps=0.1 arena -- are spread over all threads),
-    // commits the per-line two lowest hit faces with their z, and resumes scanning.
+    // ---- phases B + C: scan cells -> list of kept cells -> per-cell triangle tests ----------------------------
+    // B1 (warps, dynamic batches): SWAR test of every mesh cell, kept cells appended to a shared list.
+    // C  (threads): a thread takes kept cells, forms the exact line sets of the cell's two faces from the vertex codes
+    //    (LineIntersection.cpp:77-101), loads the four corners once and tests the few (face, line) candidates itself; a hit
+    //    enters the line's ordered two-slot table by its FACE INDEX (the reference keeps the first two hits in face order,
+    //    SURVEY finding 2).  Cells with many candidates (the eps = 0.1 arena: a few faces cover hundreds of lines) go to a
+    //    second list whose lines are spread over the whole CTA.
+    // D  re-evaluates the two surviving faces of a line for their z (their vertices were just read by this SM: L1 hits), so
+    //    no per-hit storage, no commit rounds and no capacity limit on hits exist.
     const int nc1 = n - 1;
     const int ncell = nc1 * nc1;
-    // Scan: the cells of the mesh are grouped in units of 4 consecutive cells of a mesh row (8 faces), 4 units per lane,
-    // 128 units per warp batch; warps claim batches from a shared counter.  B1 (per lane): exact, branch-free test of
-    // every face's line set for emptiness on packed (x, y) vertex codes -> one keep bit per face, a 32-bit word per lane.
-    // B2 (per warp): the few set bits of the 32 words are balanced over the lanes (prefix sum of popcounts + rank search),
-    // so no lane works through a long private list, and every queue reservation is one shared-memory atomic per warp.
-    const int UPR = (nc1 + 3) >> 2;            // units per mesh row
+    const int UPR = (nc1 + 3) >> 2;            // units (4 consecutive cells of a mesh row) per mesh row
     const int nunits = nc1 * UPR;
     const uint32_t upr_magic = (UPR > 1) ? 0xFFFFFFFFu / static_cast<uint32_t>(UPR) + 1u : 0u;  // u / UPR == umulhi(u, magic), u < 2^16
+    const uint32_t nc1_magic = 0xFFFFFFFFu / static_cast<uint32_t>(nc1) + 1u;                   // cell / nc1 likewise (nc1 >= 2)
     const bool vec_ok = (n & 3) == 0;
-    constexpr int kUPL = 4;  // units per lane and batch: smaller batches balance the warps better, larger ones amortise the prefix scan
+    constexpr int kUPL = 4;  // units per lane and batch
     static_assert(kUPL <= 4, "unit_cells packs the cells of unit uu at bits 7 + 2 * uu, 8 + 2 * uu, 23 + 2 * uu, 24 + 2 * uu");
     const int lane = tid & 31;
-    const unsigned lt_mask = (1u << lane) - 1u;
+    int* hcount = qcount + 2;
     // B1: cells of unit u whose inclusive xy bounding box (over the 4 corners) may contain a sweep line.  Per axis the set of
     // lines inside the box of a vertex set is empty  <=>  all codes (2*lo + eq) are equal and even, so a cell is kept iff on
-    // BOTH axes some corner code differs from the first one or is odd: XOR / OR over packed codes, no min/max.  The two faces
-    // of a kept cell are tested exactly in B2.  Result layout (per unit, before the batch shift): cell 0 -> bit 7, cell 2 ->
-    // bit 8, cell 1 -> bit 23, cell 3 -> bit 24 (where the SWAR form leaves them).
+    // BOTH axes some corner code differs from the first one or is odd: XOR / OR over packed codes, no min/max.
+    // Result layout (per unit, before the batch shift): cell 0 -> bit 7, cell 2 -> bit 8, cell 1 -> bit 23, cell 3 -> bit 24
+    // (where the SWAR form leaves them).
     auto unit_cells = [&](int unit) -> uint32_t {
         const int i = (UPR > 1) ? static_cast<int>(__umulhi(static_cast<uint32_t>(unit), upr_magic)) : unit;
         const int j0 = 4 * (unit - i * UPR);
@@ -609,8 +604,9 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : (MOD
             const uint32_t a4 = static_cast<uint32_t>(vcode[q + 4]), b4 = static_cast<uint32_t>(vcode[q + n + 4]);
             const uint32_t sax = __funnelshift_r(a.x, a.y, 16), say = __funnelshift_r(a.y, a4, 16);
             const uint32_t sbx = __funnelshift_r(b.x, b.y, 16), sby = __funnelshift_r(b.y, b4, 16);
-            const uint32_t dx = (a.x ^ b.x) | (a.x ^ sax) | (a.x ^ sbx) | ((a.x | b.x | sax | sbx) & 0x01010101u);
-            const uint32_t dy = (a.y ^ b.y) | (a.y ^ say) | (a.y ^ sby) | ((a.y | b.y | say | sby) & 0x01010101u);
+            // (all four equal and odd is caught by the first corner's own low bits: unequal corners set a difference bit)
+            const uint32_t dx = (a.x ^ b.x) | (a.x ^ sax) | (a.x ^ sbx) | (a.x & 0x01010101u);
+            const uint32_t dy = (a.y ^ b.y) | (a.y ^ say) | (a.y ^ sby) | (a.y & 0x01010101u);
             // bit 7 of every non-zero byte, then both bytes of a vertex field
             const uint32_t nx = (((dx & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | dx), ny = (((dy & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | dy);
             const uint32_t fx = nx & (nx >> 8) & 0x00800080u, fy = ny & (ny >> 8) & 0x00800080u;
@@ -622,7 +618,7 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : (MOD
             g = 0;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const uint32_t d = (r0[e] ^ r1[e]) | (r0[e] ^ r0[e + 1]) | (r0[e] ^ r1[e + 1]) | ((r0[e] | r1[e] | r0[e + 1] | r1[e + 1]) & 0x00010001u);
+                const uint32_t d = (r0[e] ^ r1[e]) | (r0[e] ^ r0[e + 1]) | (r0[e] ^ r1[e + 1]) | (r0[e] & 0x00010001u);
                 if ((d & 0xFFFFu) != 0u && (d >> 16) != 0u) g |= 1u << ((e & 1 ? 23 : 7) + (e >> 1));
             }
         }
@@ -632,187 +628,153 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : (MOD
         }
         return g;
     };
-
-    // B2 state of a warp: batch of 32 words [bw*32, bw*32+32), its words / popcount prefix, the rank chunk r0, and per lane
-    // the open face with the next line to push.
-    int bw = 0;                    // current batch (warp-uniform)
-    bool batch_loaded = false;
-    uint32_t w_bits = 0, w_cnt = 0, w_incl = 0, w_total = 0;
-    uint32_t r0c = 0;              // first rank of the current chunk of 32 set bits
-    bool chunk_started = false;    // warp-uniform: the lanes have taken their set bit of the current chunk
-    bool face_open = false;
-    uint32_t cur = 0, f_lo2 = 0, f_hi2 = 0, f_id = 0;  // packed (ix | iy << 16): next line, first lines, end lines of the open face
-    uint32_t pend_lo = 0, pend_hi = 0;  // line set of the cell's second face while the first one is being pushed (pend_hi != 0)
-    bool scanning = true;          // warp-uniform
-    for (;;) {
-        long long tb2 = 0;
-        if (p.dbg) tb2 = clock64();
-        while (scanning) {
-            if (!batch_loaded) {
-                if (lane == 0) bw = atomicAdd(batch_ctr, 1);
-                bw = __shfl_sync(0xFFFFFFFFu, bw, 0);
-                if (bw * (32 * kUPL) >= nunits) {
-                    scanning = false;
-                    break;
+    // exact line sets of the two faces of cell (i, j), q = i*n + j: per 16-bit half lo = min(2*lo+eq) >> 1,
+    // hi+1 = (max(2*lo+eq) + 1) >> 1, lines [lo, hi); n* = number of (face, line) candidates
+    auto cell_sets = [&](int q, uint32_t& loA, uint32_t& hiA, uint32_t& loB, uint32_t& hiB, uint32_t& nA, uint32_t& nB) {
+        const uint32_t c00 = code_at(q), c11 = code_at(q + n + 1), c10 = code_at(q + n), c01 = code_at(q + 1);
+        const uint32_t mnA = __vimin3_u16x2(c00, c11, c10), mxA = __vimax3_u16x2(c00, c11, c10);
+        const uint32_t mnB = __vimin3_u16x2(c00, c11, c01), mxB = __vimax3_u16x2(c00, c11, c01);
+        loA = (mnA >> 1) & 0x7FFF7FFFu, hiA = ((mxA + 0x00010001u) >> 1) & 0x7FFF7FFFu;
+        loB = (mnB >> 1) & 0x7FFF7FFFu, hiB = ((mxB + 0x00010001u) >> 1) & 0x7FFF7FFFu;
+        const uint32_t dA = __vsub2(hiA, loA), dB = __vsub2(hiB, loB);  // hi >= lo in both halves
+        nA = (dA & 0xFFFFu) * (dA >> 16), nB = (dB & 0xFFFFu) * (dB >> 16);
+    };
+    auto vert = [&](int v) -> D3 { return {static_cast<double>(mx[v]), static_cast<double>(my[v]), static_cast<double>(mz[v])}; };
+    auto test_lines = [&](uint32_t face, uint32_t lo2, uint32_t hi2, const D3& t0, const D3& t1, const D3& t2) {
+        for (uint32_t ix = lo2 & 0xFFFFu; ix < (hi2 & 0xFFFFu); ++ix)
+            for (uint32_t iy = lo2 >> 16; iy < (hi2 >> 16); ++iy) {
+                double z;
+                if (test_loaded(ix, iy, t0, t1, t2, z)) {
+                    const uint32_t l = ix * p.Ly + iy;
+                    insert_two_smallest(&m0[l], &m1[l], face);
                 }
+            }
+    };
+    constexpr uint32_t kLight = 16;  // cells with more candidates than this get a whole warp
+
+    constexpr int kWarps = kThreads / 32;
+    constexpr int kSegCap = kCellCap / kWarps;  // every warp lists its kept cells in its own segment: no atomics in the scan
+    const int warp = tid >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    uint16_t* seg = cellq + warp * kSegCap;
+    int* segcnt = qcount + 4;          // [kWarps]
+    int bw = warp;                 // current batch (warp-uniform); batches are dealt round-robin (their cost is uniform)
+    bool batch_loaded = false;
+    uint32_t w_bits = 0;           // kept cells of the lane's units that are not listed yet
+    for (;;) {
+        long long tb1 = 0;
+        if (p.dbg) tb1 = clock64();
+        int wcnt = 0;
+        bool parked = false;
+        while (bw * (32 * kUPL) < nunits) {
+            if (!batch_loaded) {
                 w_bits = 0u;
 #pragma unroll
                 for (int uu = 0; uu < kUPL; ++uu) {
                     const int unit = (bw * kUPL + uu) * 32 + lane;  // consecutive lanes read consecutive 8-byte words: no bank conflicts
                     if (unit < nunits) w_bits += unit_cells(unit) << (2 * uu);
                 }
-                w_cnt = __popc(w_bits);
-                w_incl = w_cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, w_incl, o);
-                    if (lane >= o) w_incl += t;
-                }
-                w_total = __shfl_sync(0xFFFFFFFFu, w_incl, 31);
                 batch_loaded = true;
-                r0c = 0;
-                chunk_started = false;
-                face_open = false;
-                if (w_total == 0u) {  // nothing in these 32 words
-                    batch_loaded = false;
-                    continue;
-                }
             }
-            bool parked = false;
-            while (r0c < w_total) {
-                if (!chunk_started) {  // warp-uniform branch: every lane takes set bit number r0c + lane of the batch
-                    chunk_started = true;
-                    const uint32_t rank = r0c + lane;
-                    // smallest source lane whose inclusive prefix exceeds rank (binary search with shuffles)
-                    int src = 0;
-#pragma unroll
-                    for (int step = 16; step > 0; step >>= 1) {
-                        const uint32_t v = __shfl_sync(0xFFFFFFFFu, w_incl, (src + step - 1) & 31);
-                        if (v <= rank) src += step;
-                    }
-                    src &= 31;
-                    const uint32_t wsrc = __shfl_sync(0xFFFFFFFFu, w_bits, src);
-                    const uint32_t excl = __shfl_sync(0xFFFFFFFFu, w_incl - w_cnt, src);
-                    if (rank < w_total) {
-                        uint32_t x = wsrc;
-                        for (uint32_t k = rank - excl; k > 0; --k) x &= x - 1;  // drop the lower set bits of that word
-                        const int bit = __ffs(x) - 1;
-                        // decode (see unit_cells): bits 7.. hold cells 0 / 2, bits 23.. cells 1 / 3 of the lane's kUPL units
-                        const int hi = bit >= 23 ? 1 : 0, pb = bit - (hi ? 23 : 7);
-                        const int unit = (bw * kUPL + (pb >> 1)) * 32 + src;
-                        const int i = (UPR > 1) ? static_cast<int>(__umulhi(static_cast<uint32_t>(unit), upr_magic)) : unit;
-                        const int j = 4 * (unit - i * UPR) + (((pb & 1) << 1) | hi);
-                        const int q = i * n + j;
-                        // exact line sets of the cell's two faces (q, q+n, q+n+1) and (q, q+1, q+n+1): per 16-bit half,
-                        // lo = min(2*lo+eq) >> 1 ; hi+1 = (max(2*lo+eq) + 1) >> 1, lines [lo, hi)
-                        const uint32_t c00 = code_at(q), c11 = code_at(q + n + 1), c10 = code_at(q + n), c01 = code_at(q + 1);
-                        const uint32_t mnA = __vimin3_u16x2(c00, c11, c10), mxA = __vimax3_u16x2(c00, c11, c10);
-                        const uint32_t mnB = __vimin3_u16x2(c00, c11, c01), mxB = __vimax3_u16x2(c00, c11, c01);
-                        const uint32_t loA = (mnA >> 1) & 0x7FFF7FFFu, hiA = ((mxA + 0x00010001u) >> 1) & 0x7FFF7FFFu;
-                        const uint32_t loB = (mnB >> 1) & 0x7FFF7FFFu, hiB = ((mxB + 0x00010001u) >> 1) & 0x7FFF7FFFu;
-                        const bool okA = (loA & 0xFFFFu) < (hiA & 0xFFFFu) && (loA >> 16) < (hiA >> 16);
-                        const bool okB = (loB & 0xFFFFu) < (hiB & 0xFFFFu) && (loB >> 16) < (hiB >> 16);
-                        f_lo2 = okA ? loA : loB, f_hi2 = okA ? hiA : hiB;
-                        f_id = static_cast<uint32_t>(i * nc1 + j + (okA ? 0 : ncell));
-                        cur = f_lo2;
-                        face_open = okA || okB;  // the cell test is a superset of the two face tests
-                        pend_lo = loB;
-                        pend_hi = (okA && okB) ? hiB : 0u;  // != 0: the second face of the cell follows the first one
-                    }
+            // append the kept cells: per round every lane that still has one writes its lowest; what does not fit into the
+            // segment stays in w_bits for the next round
+            unsigned any = __ballot_sync(0xFFFFFFFFu, w_bits != 0u);
+            while (any != 0u) {
+                const int pos = wcnt + __popc(any & lt_mask);
+                if (w_bits != 0u && pos < kSegCap) {
+                    const int bit = __ffs(w_bits) - 1;
+                    w_bits &= w_bits - 1u;
+                    // decode (see unit_cells): bits 7.. hold cells 0 / 2, bits 23.. cells 1 / 3 of the lane's kUPL units
+                    const int hi = bit >= 23 ? 1 : 0, pb = bit - (hi ? 23 : 7);
+                    const int unit = (bw * kUPL + (pb >> 1)) * 32 + lane;
+                    const int i = (UPR > 1) ? static_cast<int>(__umulhi(static_cast<uint32_t>(unit), upr_magic)) : unit;
+                    const int j = 4 * (unit - i * UPR) + (((pb & 1) << 1) | hi);
+                    seg[pos] = static_cast<uint16_t>(i * nc1 + j);
                 }
-                // push the lines of the open faces, one per lane per iteration, one atomic per warp
-                for (;;) {
-                    const bool has = face_open;
-                    const unsigned bal = __ballot_sync(0xFFFFFFFFu, has);
-                    if (bal == 0u) break;
-                    int base = 0;
-                    const int leader = __ffs(bal) - 1;
-                    if (lane == leader) base = atomicAdd(qcount, __popc(bal));
-                    base = __shfl_sync(0xFFFFFFFFu, base, leader);
-                    bool over = false;
-                    if (has) {
-                        const int pos = base + __popc(bal & lt_mask);
-                        if (pos < static_cast<int>(kPosMask)) {  // slots 0..kPosMask-1; kPosMask is the 'committed' marker
-                            queue[pos] = make_uint2(f_id, cur);
-                            cur += 0x10000u;  // y fastest
-                            if ((cur >> 16) == (f_hi2 >> 16)) cur = ((cur & 0xFFFFu) + 1u) | (f_lo2 & 0xFFFF0000u);
-                            if ((cur & 0xFFFFu) >= (f_hi2 & 0xFFFFu)) {
-                                if (pend_hi != 0u) {  // go on with face (q, q+1, q+n+1) of the same cell
-                                    f_lo2 = pend_lo, f_hi2 = pend_hi, pend_hi = 0u;
-                                    f_id += static_cast<uint32_t>(ncell);
-                                    cur = f_lo2;
-                                } else {
-                                    face_open = false;
-                                }
-                            }
-                        } else {
-                            over = true;  // queue full: keep the position, resume after the drain
-                        }
-                    }
-                    if (__any_sync(0xFFFFFFFFu, over)) {
-                        parked = true;
-                        break;
-                    }
+                wcnt += __popc(any);
+                if (wcnt >= kSegCap) {
+                    wcnt = kSegCap;
+                    break;
                 }
-                if (parked) break;
-                r0c += 32;  // all lanes finished their face of this chunk
-                chunk_started = false;
+                any = __ballot_sync(0xFFFFFFFFu, w_bits != 0u);
             }
-            if (parked) break;
+            __syncwarp();
+            if (__any_sync(0xFFFFFFFFu, w_bits != 0u)) {  // segment full: the tests come first
+                parked = true;
+                break;
+            }
             batch_loaded = false;
+            bw += kWarps;
         }
-        if (p.dbg) acc_b2 += clock64() - tb2;
-        if (p.dbg && rounds == 0) {
-            atomicMax(&dbg_max[1], (unsigned long long)acc_b2);
-            atomicMax(&dbg_max[2], (unsigned long long)(clock64() - t_a));
-        }
-        __syncwarp();  // the scan loop exits lane by lane: the drain below must run with full warps
-        const int more = __syncthreads_or(scanning ? 1 : 0);  // no warp has cells left: this drain is the last one
+        if (lane == 0) segcnt[warp] = wcnt;
+        if (p.dbg && rounds == 0) atomicMax(&dbg_max[0], (unsigned long long)(clock64() - tb1));
+        __syncwarp();
+        const int more = __syncthreads_or(parked ? 1 : 0);  // no warp has cells left: this round is the last one
         long long tq0 = 0;
         if (p.dbg) tq0 = clock64();
-        // drain
-        const int nq = min(*qcount, static_cast<int>(kPosMask));
-        for (int i = tid; i < nq; i += kThreads) {
-            const uint2 e = queue[i];
-            const uint32_t ix = e.y & 0xFFFFu, iy = e.y >> 16;
-            D3 t0, t1, t2;
-            load_face(e.x, t0, t1, t2);
-            double z;
-            if (test_loaded(ix, iy, t0, t1, t2, z)) {
-                zq[i] = z;
-                const uint32_t l = ix * p.Ly + iy;
-                insert_two_smallest(&m0[l], &m1[l], (e.x << kPosBits) | static_cast<uint32_t>(i));
+        // C: one kept cell per thread and pass
+        int sc[kWarps + 1];
+        sc[0] = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) sc[w + 1] = sc[w] + segcnt[w];
+        const int ncq = sc[kWarps];
+        for (int base = 0; base < ncq; base += kThreads) {
+            const int ci = base + tid;
+            if (ci < ncq) {
+                int w = 0;
+#pragma unroll
+                for (int ww = 1; ww < kWarps; ++ww) w += (ci >= sc[ww]) ? 1 : 0;
+                int off_w = 0;
+#pragma unroll
+                for (int ww = 1; ww < kWarps; ++ww) off_w = (ci >= sc[ww]) ? sc[ww] : off_w;
+                const uint32_t cell = cellq[w * kSegCap + (ci - off_w)];
+                const uint32_t i = __umulhi(cell, nc1_magic);
+                const int q = static_cast<int>(i) * n + static_cast<int>(cell - i * nc1);
+                uint32_t loA, hiA, loB, hiB, nA, nB;
+                cell_sets(q, loA, hiA, loB, hiB, nA, nB);
+                if (nA + nB > kLight) {
+                    heavyq[atomicAdd(hcount, 1)] = static_cast<uint16_t>(cell);
+                } else if (nA + nB != 0u) {  // (the cell test is a superset of the two face tests)
+                    const D3 c00 = vert(q), c11 = vert(q + n + 1);
+                    if (nA != 0u) test_lines(cell, loA, hiA, c00, vert(q + n), c11);                                  // (q, q+n, q+n+1)
+                    if (nB != 0u) test_lines(cell + static_cast<uint32_t>(ncell), loB, hiB, c00, vert(q + 1), c11);  // (q, q+1, q+n+1)
+                }
             }
         }
         __syncwarp();
         __syncthreads();
-        if (!more) {  // last round: phase D resolves the z of the fresh entries from the queue itself
-            if (p.dbg) t_drain += clock64() - tq0;
-            break;
-        }
-        // commit: bind z to the surviving entries of every line (entries from earlier rounds carry the
-        // marker kPosMask and already own zc0/zc1; an older entry can only have moved from slot 0 to slot 1)
-        for (int l = tid; l < p.L; l += kThreads) {
-            const uint32_t e0 = m0[l], e1 = m1[l];
-            if (e0 == kNoFace) continue;
-            const double old0 = zc0[l];
-            double z0, z1 = 0.0;
-            const bool fresh0 = (e0 & kPosMask) != kPosMask;
-            z0 = fresh0 ? zq[e0 & kPosMask] : old0;
-            if (e1 != kNoFace) {
-                const bool fresh1 = (e1 & kPosMask) != kPosMask;
-                // a committed entry in slot 1 is either the old slot-1 entry (slot 0 unchanged) or the old slot-0 entry
-                z1 = fresh1 ? zq[e1 & kPosMask] : (fresh0 ? old0 : zc1[l]);
-                zc1[l] = z1;
-                m1[l] = e1 | kPosMask;
+        const int nh = *hcount;  // (at most one entry per listed cell)
+        if (nh != 0) {
+            // a warp per heavy cell, its (face, line) candidates over the lanes
+            for (int h = warp; h < nh; h += kWarps) {
+                const uint32_t cell = heavyq[h];
+                const uint32_t i = __umulhi(cell, nc1_magic);
+                const int q = static_cast<int>(i) * n + static_cast<int>(cell - i * nc1);
+                uint32_t loA, hiA, loB, hiB, nA, nB;
+                cell_sets(q, loA, hiA, loB, hiB, nA, nB);
+                const D3 c00 = vert(q), c10 = vert(q + n), c11 = vert(q + n + 1), c01 = vert(q + 1);
+                for (uint32_t idx = lane; idx < nA + nB; idx += 32) {
+                    const bool second = idx >= nA;
+                    const uint32_t k2 = second ? idx - nA : idx;
+                    const uint32_t lo2 = second ? loB : loA, hi2 = second ? hiB : hiA;
+                    const uint32_t wy = (hi2 >> 16) - (lo2 >> 16);
+                    const uint32_t dxl = k2 / wy;
+                    const uint32_t ix = (lo2 & 0xFFFFu) + dxl, iy = (lo2 >> 16) + (k2 - dxl * wy);
+                    double z;
+                    if (test_loaded(ix, iy, c00, second ? c01 : c10, c11, z)) {
+                        const uint32_t l = ix * p.Ly + iy;
+                        insert_two_smallest(&m0[l], &m1[l], cell + (second ? static_cast<uint32_t>(ncell) : 0u));
+                    }
+                }
             }
-            zc0[l] = z0;
-            m0[l] = e0 | kPosMask;
+            __syncwarp();
+            __syncthreads();
         }
-        if (tid == 0) *qcount = 0;
+        if (p.dbg) t_drain += clock64() - tq0;
+        if (!more) break;
+        if (tid == 0) *hcount = 0;
         ++rounds;
         __syncthreads();
-        if (p.dbg) t_drain += clock64() - tq0;
     }
 
     if (p.dbg) t_scan = clock64();
@@ -826,10 +788,14 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : (MOD
         double a = is_arena ? p.zlow : __longlong_as_double(0x7FF8000000000000LL);
         double bb = is_arena ? p.zup : __longlong_as_double(0x7FF8000000000000LL);
         if (e1 != kNoFace) {
-            // same resolution as the commit step: fresh entries (slot != kPosMask) take their z from the queue
-            const bool fresh0 = (e0 & kPosMask) != kPosMask, fresh1 = (e1 & kPosMask) != kPosMask;
-            const double z0 = fresh0 ? zq[e0 & kPosMask] : zc0[l];
-            const double z1 = fresh1 ? zq[e1 & kPosMask] : (fresh0 ? zc0[l] : zc1[l]);
+            // z of the two lowest hit faces: the same test on the same vertices as in phase C
+            const uint32_t ix = static_cast<uint32_t>(l) / static_cast<uint32_t>(p.Ly), iy = static_cast<uint32_t>(l) - ix * static_cast<uint32_t>(p.Ly);
+            D3 a0, a1, a2, b0, b1, b2;
+            load_face(e0, a0, a1, a2);
+            load_face(e1, b0, b1, b2);
+            double z0 = 0.0, z1 = 0.0;
+            test_loaded(ix, iy, a0, a1, a2, z0);
+            test_loaded(ix, iy, b0, b1, b2, z1);
             const double zl = fmin(z0, z1), zu = fmax(z0, z1);
             a = is_arena ? fmin(p.zlow, zl) : zl;  // FreeSpace3D.cpp:44-49 / 61-64
             bb = is_arena ? fmax(p.zup, zu) : zu;
@@ -842,12 +808,12 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : (MOD
     if (single) atomicAdd(p.counters, static_cast<unsigned long long>(single));
     if (p.dbg && tid == 0) {
         long long* d = p.dbg + static_cast<size_t>(slot) * 8;
-        d[3] = t_drain;              // of which drain + commit
+        d[3] = t_drain;              // of which phase C (cell tests)
         d[0] = t_pro - t_start;      // prologue
         d[1] = t_a - t_pro;          // phase A
-        d[2] = t_scan - t_a;         // scan + drain + commit
-        d[4] = (long long)dbg_max[0];   // max over threads: B1 time in the first round
-        d[6] = (long long)dbg_max[1];   // max over threads: B2 time in the first round
+        d[2] = t_scan - t_a;         // scan + tests
+        d[4] = (long long)dbg_max[0];   // max over warps: B1 time in the first round
+        d[6] = 0;
         d[5] = rounds;
         d[7] = clock64() - t_start;
     }
@@ -861,20 +827,19 @@ static size_t smem_layout(MinkParams& p, int MODE, bool sweep, bool code8, int n
     p.o_mats = static_cast<int>(b), b += sizeof(double) * (36 + 18);  // + 18 row-base coefficients (fast modes)
     p.o_txs = static_cast<int>(b), p.o_tys = static_cast<int>(b + (sweep ? sizeof(double) * (Lx + 2) : 0));
     if (sweep) b += al(sizeof(double) * (Lx + Ly + 4));
-    // the column table is read in phase A only, the candidate queue is used behind the barrier that ends phase A: one region
+    // the column table is read in phase A only, the cell lists are used behind the barrier that ends phase A: one region
     p.o_cc = static_cast<int>(b);
-    p.o_zq = static_cast<int>(b), p.o_queue = static_cast<int>(b + (sweep ? sizeof(double) * kQueueCap : 0));
+    p.o_queue = static_cast<int>(b);
     {
         const size_t cc_bytes = (MODE != HRMGPU_F64_STRICT) ? al(real * kColStride * n) : 0;
-        const size_t q_bytes = sweep ? (sizeof(double) + sizeof(uint2)) * kQueueCap : 0;
+        const size_t q_bytes = sweep ? 2 * sizeof(uint16_t) * kCellCap : 0;
         b += cc_bytes > q_bytes ? cc_bytes : q_bytes;
     }
     p.o_vcode = static_cast<int>(b), b += sweep ? al((code8 ? 2 : 4) * (static_cast<size_t>(n) * n + 8)) : 0;
     const size_t L = static_cast<size_t>(Lx) * Ly;
-    p.o_zc0 = static_cast<int>(b), p.o_zc1 = static_cast<int>(b + (sweep ? sizeof(double) * L : 0)), b += sweep ? sizeof(double) * 2 * L : 0;
     p.o_m0 = static_cast<int>(b), p.o_m1 = static_cast<int>(b + (sweep ? sizeof(uint32_t) * L : 0)), b += sweep ? al(sizeof(uint32_t) * 2 * L) : 0;
     p.o_qcount = static_cast<int>(b);
-    return b + 16;
+    return b + 16 + 32;  // counters: listed cells, scan batch, heavy cells, pad, cells per warp segment [8]
 }
 
 // Lanes per column group: maximise n^2 / (threads * ceil(n/lpc) * ceil(n/groups)).
