@@ -592,12 +592,13 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : (MOD
     // BOTH axes some corner code differs from the first one or is odd: XOR / OR over packed codes, no min/max.
     // Result layout (per unit, before the batch shift): cell 0 -> bit 7, cell 2 -> bit 8, cell 1 -> bit 23, cell 3 -> bit 24
     // (where the SWAR form leaves them).
-    auto unit_cells = [&](int unit) -> uint32_t {
+    auto unit_cells = [&](int unit_raw, bool fast) -> uint32_t {
+        const int unit = min(unit_raw, nunits - 1);  // (units past the end are evaluated on the last one and dropped: no branch)
         const int i = (UPR > 1) ? static_cast<int>(__umulhi(static_cast<uint32_t>(unit), upr_magic)) : unit;
         const int j0 = 4 * (unit - i * UPR);
         const int q = i * n + j0;
         uint32_t g;
-        if (vec_ok && CODE8) {
+        if (fast) {
             // four vertices (x byte, y byte each) per 64-bit load; sa / sb = the same rows advanced by one vertex
             const uint2 a = *reinterpret_cast<const uint2*>(vcode + q);
             const uint2 b = *reinterpret_cast<const uint2*>(vcode + q + n);
@@ -622,11 +623,10 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : (MOD
                 if ((d & 0xFFFFu) != 0u && (d >> 16) != 0u) g |= 1u << ((e & 1 ? 23 : 7) + (e >> 1));
             }
         }
-        if (j0 + 4 > nc1) {  // cells past the end of the mesh row
-            const int v = nc1 - j0;
-            g &= (v == 1) ? 0x00000080u : ((v == 2) ? 0x00800080u : 0x00800180u);
-        }
-        return g;
+        // cells past the end of the mesh row (v = cells left in the row) and units past the end of the mesh
+        const int v = nc1 - j0;
+        const uint32_t keep = (v >= 4) ? 0x01800180u : ((v == 3) ? 0x00800180u : ((v == 2) ? 0x00800080u : 0x00000080u));
+        return (unit_raw < nunits) ? (g & keep) : 0u;
     };
     // exact line sets of the two faces of cell (i, j), q = i*n + j: per 16-bit half lo = min(2*lo+eq) >> 1,
     // hi+1 = (max(2*lo+eq) + 1) >> 1, lines [lo, hi); n* = number of (face, line) candidates
@@ -668,11 +668,15 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : (MOD
         bool parked = false;
         while (bw * (32 * kUPL) < nunits) {
             if (!batch_loaded) {
+                // consecutive lanes read consecutive 8-byte words (no bank conflicts); the kUPL units of a lane are independent
+                // straight-line code, so their loads and SWAR chains interleave
                 w_bits = 0u;
+                if (vec_ok && CODE8) {
 #pragma unroll
-                for (int uu = 0; uu < kUPL; ++uu) {
-                    const int unit = (bw * kUPL + uu) * 32 + lane;  // consecutive lanes read consecutive 8-byte words: no bank conflicts
-                    if (unit < nunits) w_bits += unit_cells(unit) << (2 * uu);
+                    for (int uu = 0; uu < kUPL; ++uu) w_bits += unit_cells((bw * kUPL + uu) * 32 + lane, true) << (2 * uu);
+                } else {
+#pragma unroll
+                    for (int uu = 0; uu < kUPL; ++uu) w_bits += unit_cells((bw * kUPL + uu) * 32 + lane, false) << (2 * uu);
                 }
                 batch_loaded = true;
             }
