@@ -21,6 +21,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# torch initialises CUDA before libhrmgpu.so is loaded: ask for eager module loading here (see hrm_b200/csrc/ctx.cu)
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 
 from hrm_b200 import workload as wl  # noqa: E402
 

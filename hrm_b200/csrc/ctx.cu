@@ -68,6 +68,12 @@ int check_built(Ctx* c, int k) {
 
 extern "C" {
 
+// The library holds ~40 kernel variants; with CUDA's default lazy module loading their first uses cost tens of milliseconds
+// spread over the first planner calls (measured: HRM3D::plan() 29 / 30 / 17 ms before settling at 12.8 ms; 15 / 13 / 13 ms with
+// eager loading).  Ask for eager loading when the library is loaded, unless the process has chosen a mode itself; it takes
+// effect if the CUDA driver is not initialised yet (a host that initialises CUDA first sets CUDA_MODULE_LOADING itself).
+__attribute__((constructor)) static void hrmgpu_prefer_eager_module_loading() { setenv("CUDA_MODULE_LOADING", "EAGER", 0); }
+
 int hrmgpu_abi_version(void) { return HRMGPU_ABI_VERSION; }
 
 int hrmgpu_device_count(void) {

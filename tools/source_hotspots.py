@@ -48,12 +48,13 @@ for k in keys:
 
 # phase roll-up for hrm_b200/csrc/mink3d.cu (+ device helpers): edit the ranges when the kernel moves
 if len(sys.argv) > 3 and sys.argv[3] == "phases":
-    ranges = [("line-code helpers (phase A)", "mink3d.cu", 1, 153), ("entry + smem carve-up + reload", "mink3d.cu", 154, 234),
-              ("prologue", "mink3d.cu", 235, 341), ("phase A", "mink3d.cu", 342, 552), ("face load/test lambdas (drain)", "mink3d.cu", 553, 579),
-              ("scan B1 (face tests)", "mink3d.cu", 580, 633), ("scan B2 (expansion + queue)", "mink3d.cu", 634, 753),
-              ("drain", "mink3d.cu", 754, 773), ("commit", "mink3d.cu", 774, 799), ("phase D", "mink3d.cu", 800, 900),
-              ("rsqrt (phase A)", "devmath.cuh", 30, 50), ("triangle test (drain)", "devmath.cuh", 51, 129),
-              ("face_vertices / insert (drain)", "devmath.cuh", 130, 200)]
+    ranges = [("line-code helpers (phase A)", "mink3d.cu", 1, 150), ("entry + smem carve-up + reload", "mink3d.cu", 151, 231),
+              ("prologue", "mink3d.cu", 232, 338), ("phase A", "mink3d.cu", 339, 548), ("face load/test lambdas (C, D)", "mink3d.cu", 549, 569),
+              ("scan B1 (SWAR cell test)", "mink3d.cu", 570, 632), ("cell line sets / test_lines (C)", "mink3d.cu", 633, 654),
+              ("scan loop + cell lists (B1)", "mink3d.cu", 655, 718), ("phase C (per-cell tests)", "mink3d.cu", 719, 750),
+              ("heavy cells (C)", "mink3d.cu", 751, 784), ("phase D (re-test + intervals)", "mink3d.cu", 785, 826),
+              ("rsqrt (phase A)", "devmath.cuh", 30, 50), ("triangle test (C, D)", "devmath.cuh", 51, 129),
+              ("face_vertices / insert (C, D)", "devmath.cuh", 130, 200)]
     print("\nphase roll-up: share of warp instructions / of stall samples, top stall reasons")
     for name, f, a, b in ranges:
         inst = samp = 0.0
