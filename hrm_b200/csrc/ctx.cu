@@ -112,6 +112,8 @@ int hrmgpu_create(hrmgpu_ctx** out, int device, unsigned flags) {
     // test hooks of the segment pass (tests/test_gpu_layers3d.py): list capacity of the 4-line kernel / one-line kernel only
     if (const char* e = std::getenv("HRMGPU_SEG_FAST_CAP")) c->seg_fast_cap = std::atoi(e);
     if (const char* e = std::getenv("HRMGPU_SEG_ONE_LINE")) c->force_seg_fallback = std::atoi(e) != 0;
+    // test hook of the fused kernel: capacity of a warp's kept-cell list (small values force the multi-round path)
+    if (const char* e = std::getenv("HRMGPU_CELL_SEG_CAP")) c->cell_seg_cap = std::atoi(e);
     if (ensure(c, c->counters, 4) != HRMGPU_OK) {
         delete c;
         return HRMGPU_E_NOMEM;

@@ -75,6 +75,7 @@ struct Ctx {
     int num_sms = 148;                           // multiprocessors of the device
     int seg_fast_cap = 0;                        // test hook: list capacity of the 4-line segment pass (0 = default 128)
     bool force_seg_fallback = false;             // test hook: always use the one-line-per-warp pass
+    int cell_seg_cap = 0;                        // test hook: kept-cell list capacity per warp of the fused kernel (0 = default)
     DevBuf<double> orig;                         // [K][L][So+1][2] original (pre-enhancement) segments
     DevBuf<int> orig_cnt;                        // [K][L]
     DevBuf<int> seg_cnt;                         // [K][L]

@@ -8,24 +8,22 @@
 //   FreeSpace3D::computeIntersectionInterval           src/datastructure/FreeSpace3D.cpp:29-68
 //   intersectVerticalLineMesh3D / intersectLineTriangle3D  src/geometry/LineIntersection.cpp:56-171
 //
-// Thread mapping: the CTA's 256 threads form G groups of LPC lanes (LPC chosen on the host so that
-// n / (LPC*ceil(n/LPC)) and n / (G*ceil(n/G)) are close to 1).  A group owns whole eta-columns c of
-// the parameter grid; its lanes stride over the omega index r.  Point index k = r + c*n (omega fastest,
-// SuperQuadrics.cpp:63-72), so a group's stores are LPC consecutive values.
+// Thread mapping: the CTA's 256 threads form G groups of LPC lanes (LPC chosen on the host: a whole eta-column per group
+// where possible, so that a group stores complete 32-byte sectors).  A group owns whole eta-columns c of the parameter
+// grid; its lanes stride over the omega index r.  Point index k = r + c*n (omega fastest, SuperQuadrics.cpp:63-72), so
+// a group's stores are contiguous.
 //
 // Phases inside one CTA:
-//   A  boundary points.  All transcendental factors are separable (8 host-built tables per object), and
-//      in the fast modes everything that depends on the column only (R1*X-part, M1*g-part, M2*g-part: 27
-//      values) is hoisted into registers, leaving 24 FMAs + one rsqrt per point.  Points are stored planar
-//      (x[M] y[M] z[M]); each vertex is classified against the sweep grid into a packed 2x16-bit
-//      "line code" (2*lo+eq per axis, lo = first grid line >= coordinate) kept in shared memory.
-//   B  per mesh cell, integer SIMD min/max over the 4 corner codes give the exact set of sweep lines
-//      inside each of the two faces' inclusive xy bounding boxes (LineIntersection.cpp:77-101); the rare
-//      (face, line) candidates go to a shared-memory queue.
-//   C  the queue is drained densely: triangle test per candidate, hits recorded with an ordered
-//      two-slot atomicMin so that the two LOWEST face indices per line survive (the reference's
-//      "first two hits in face order" rule, SURVEY.md finding 2); z of each hit is parked in shared memory.
-//   D  per line the [lo, up] interval is formed from the two surviving hits and written.
+//   A  boundary points.  All transcendental factors are separable (8 host-built tables per object); in the fast modes
+//      every term is split into a row factor (kept in registers) and a column factor (shared table): 22 FP64 operations
+//      per point.  Points are stored planar (x[M] y[M] z[M]); each vertex is classified against the sweep grid into a
+//      packed "line code" (2*lo+eq per axis, lo = first grid line >= coordinate) kept in shared memory.
+//   B  per mesh cell a SWAR test on the 4 corner codes keeps the cells whose inclusive xy bounding box can contain a sweep
+//      line (LineIntersection.cpp:77-101); kept cells go to per-warp lists in shared memory.
+//   C  a thread per kept cell: exact line sets of the two faces, triangle test per (face, line) candidate, hits recorded
+//      with an ordered two-slot atomicMin on the FACE INDEX so that the two LOWEST face indices per line survive (the
+//      reference's "first two hits in face order" rule, SURVEY.md finding 2).
+//   D  per line the two surviving faces are evaluated again for their z and the [lo, up] interval is written.
 #include "devmath.cuh"
 #include "internal.cuh"
 
@@ -51,6 +49,7 @@ struct MinkParams {
     int Lx, Ly, L;
     int lpc, groups;                        // thread mapping
     int paired;                             // phase A handles rows in adjacent pairs (n even, lpc divides n/2)
+    int seg_cap;                            // kept cells a warp can list per scan round (kCellCap / warps; smaller in tests)
     int reload;                             // re-sweep: the boundary points are read back from `mesh` instead of being computed
     // byte offsets of the shared-memory regions (host-computed, see smem_layout): read from the constant bank instead of
     // being re-derived from n, Lx, Ly wherever the compiler rematerialises a pointer
@@ -653,10 +652,11 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : (MOD
     constexpr uint32_t kLight = 16;  // cells with more candidates than this get a whole warp
 
     constexpr int kWarps = kThreads / 32;
-    constexpr int kSegCap = kCellCap / kWarps;  // every warp lists its kept cells in its own segment: no atomics in the scan
+    constexpr int kSegStride = kCellCap / kWarps;  // every warp lists its kept cells in its own segment: no atomics in the scan
+    const int kSegCap = p.seg_cap;                 // (<= kSegStride)
     const int warp = tid >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
-    uint16_t* seg = cellq + warp * kSegCap;
+    uint16_t* seg = cellq + warp * kSegStride;
     int* segcnt = qcount + 4;          // [kWarps]
     int bw = warp;                 // current batch (warp-uniform); batches are dealt round-robin (their cost is uniform)
     bool batch_loaded = false;
@@ -731,7 +731,7 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : (MOD
                 int off_w = 0;
 #pragma unroll
                 for (int ww = 1; ww < kWarps; ++ww) off_w = (ci >= sc[ww]) ? sc[ww] : off_w;
-                const uint32_t cell = cellq[w * kSegCap + (ci - off_w)];
+                const uint32_t cell = cellq[w * kSegStride + (ci - off_w)];
                 const uint32_t i = __umulhi(cell, nc1_magic);
                 const int q = static_cast<int>(i) * n + static_cast<int>(cell - i * nc1);
                 uint32_t loA, hiA, loB, hiB, nA, nB;
@@ -911,6 +911,7 @@ int launch_minksweep3d(Ctx* c, int K, int B, int n_first_obj, int n_objs, const 
     p.L = c->Lx * c->Ly;
     pick_mapping(c->n, p.lpc, p.groups, p.paired);
     p.reload = reload ? 1 : 0;
+    p.seg_cap = (c->cell_seg_cap > 0 && c->cell_seg_cap < kCellCap / (kThreads / 32)) ? c->cell_seg_cap : kCellCap / (kThreads / 32);
     const double dx = (c->lim[1] - c->lim[0]) / static_cast<double>(c->Lx - 1);
     const double dy = (c->lim[3] - c->lim[2]) / static_cast<double>(c->Ly - 1);
     p.inv_dx = 1.0 / dx;

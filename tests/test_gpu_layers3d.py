@@ -141,6 +141,51 @@ def test_roundtrip_properties_full_size(gpu_ctx):
         assert b.shape == (3, 10000) and np.isfinite(b).all()
 
 
+def test_bench_sizes_strict_bit_exact_on_a_sample(oracle, gpu_ctx):
+    """The bench's own grid (n = 100, 32 x 16 lines, rabbit base body) on the arena + the first 40 obstacles of the bench
+    scene: every point, interval and segment of one layer bit-identical to the oracle (the full 1001 surfaces take the oracle minutes)."""
+    rows = util.synthetic_scene3d(20220726, 1000)[:41]
+    rng = np.random.default_rng(11)
+    robot = [[10, 5, 4, 1, 1, 0, 0, 0, 1, 0, 0, 0]]
+    semi, R, off, quat = util.body_poses3d(robot, util.random_unit_quats(rng, 1))
+    lim = [-58.0, 58.0, -28.0, 28.0, -18.0, 18.0]
+    (ref, got), = run_both(oracle, gpu_ctx, rows.tolist(), 1, 100, semi, R, off, quat, lim, 32, 16, capi.F64_STRICT)
+    assert_bit_exact(ref, got)
+    assert got["off"][-1] > 100
+
+
+def test_bench_mode_against_strict_full_size(gpu_ctx):
+    """The bench's headline mode (F64) against the bit-exact STRICT mode at the full BASELINE sizes (1001 surfaces x 10^4 points
+    x 512 lines, 2 layers): points within 1e-12 of the surface scale, the same hit decisions, the same segment structure,
+    end points within 1e-6; the F32 variant within 1e-5 on the points."""
+    rows = util.synthetic_scene3d(20220726, 1000)
+    rng = np.random.default_rng(13)
+    robot = [[10, 5, 4, 1, 1, 0, 0, 0, 1, 0, 0, 0]]
+    semi, R, off, quat = util.body_poses3d(robot, util.random_unit_quats(rng, 2))
+    lim = [-58.0, 58.0, -28.0, 28.0, -18.0, 18.0]
+    gpu_ctx.set_scene3d(1, 1000, util.sq17(rows.tolist(), 100), 100)
+    gpu_ctx.set_sweep(lim, 32, 16)
+    res = {}
+    sample = list(range(0, 1001, 37))
+    for prec in (capi.F64_STRICT, capi.F64, capi.F32):
+        gpu_ctx.build_layers(semi, R, off, prec)
+        res[prec] = [(gpu_ctx.intervals(k), gpu_ctx.segments(k), [gpu_ctx.boundary(k, s) for s in sample]) for k in range(2)]
+    for k in range(2):
+        (lo0, up0), (o0, xL0, xU0, xM0), b0 = res[capi.F64_STRICT][k]
+        (lo1, up1), (o1, xL1, xU1, xM1), b1 = res[capi.F64][k]
+        assert np.array_equal(np.isnan(lo0), np.isnan(lo1))
+        assert np.nanmax(np.abs(lo0 - lo1)) <= SEG_TOL and np.nanmax(np.abs(up0 - up1)) <= SEG_TOL
+        assert np.array_equal(o0, o1)
+        assert max(np.max(np.abs(xL0 - xL1)), np.max(np.abs(xU0 - xU1)), np.max(np.abs(xM0 - xM1))) <= SEG_TOL
+        b2 = res[capi.F32][k][2]
+        for i, s in enumerate(sample):
+            scale = max(rows[s][:3]) + 10.0
+            assert np.max(np.abs(b0[i] - b1[i])) / scale <= REL64, s
+            assert np.max(np.abs(b0[i] - b2[i])) / scale <= REL32, s
+        (lo2, up2), _, _ = res[capi.F32][k]
+        assert (np.isnan(lo0) == np.isnan(lo2)).mean() > 0.9995  # FP32 points may flip a hit next to a sweep line
+
+
 @pytest.mark.parametrize("env", [{"HRMGPU_SEG_FAST_CAP": "2"}, {"HRMGPU_SEG_ONE_LINE": "1"}])
 def test_segment_pass_variants_bit_exact(oracle, env, monkeypatch):
     """K3 pass 1 has a 4-lines-per-warp fast path with short interval lists and a one-line-per-warp pass with full-size
@@ -156,6 +201,25 @@ def test_segment_pass_variants_bit_exact(oracle, env, monkeypatch):
     assert any((np.diff(ref["off"]) > 2).any() for ref, _ in res)
     for ref, got in res:
         assert_bit_exact(ref, got)
+
+
+@pytest.mark.parametrize("cap", ["1", "5"])
+def test_cell_list_overflow_rounds_bit_exact(oracle, cap, monkeypatch):
+    """The fused kernel lists the kept mesh cells of a surface in per-warp segments (256 cells each) and tests them behind a
+    barrier; when a segment is full the scan parks and another round follows.  No realistic surface fills a segment, so a
+    capacity of 1 / 5 cells forces tens of rounds (incl. the heavy-cell list of the arena): results stay bit-identical."""
+    monkeypatch.setenv("HRMGPU_CELL_SEG_CAP", cap)
+    ctx = capi.Context(0)  # the hook is read when the context is created
+    rows = util.synthetic_scene3d(21, 10)
+    rng = np.random.default_rng(121)
+    robot = [[10, 5, 4, 1, 1, 0, 0, 0, 1, 0, 0, 0], [6, 3, 2, 1, 1, -7, 0, 4, 0.70710599, 0, 0.70710802, 0]]
+    semi, R, off, quat = util.body_poses3d(robot, util.random_unit_quats(rng, 2))
+    lim = [-58.0, 58.0, -28.0, 28.0, -18.0, 18.0]
+    for n, Lx, Ly in ((24, 16, 8), (13, 5, 140)):
+        for ref, got in run_both(oracle, ctx, rows.tolist(), 1, n, semi, R, off, quat, lim, Lx, Ly, capi.F64_STRICT):
+            assert_bit_exact(ref, got)
+            assert got["off"][-1] > 10
+    ctx.close()
 
 
 @pytest.mark.parametrize("precision", [capi.F64_STRICT, capi.F64, capi.F32])
