@@ -301,6 +301,7 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : (MOD
     }
 
     __syncthreads();
+    if (p.dbg && tid == 0) dbg_max[2] = (unsigned long long)(clock64() - t_start);
     if constexpr (MODE != HRMGPU_F64_STRICT) {
         // column table and row-base coefficients.  Two threads per column: the even one writes {ce2, UZ, WZ}, the odd one
         // {ce1, C}; the first two threads also write the row base.
@@ -810,6 +811,10 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : (MOD
         up[l] = bb;
     }
     if (single) atomicAdd(p.counters, static_cast<unsigned long long>(single));
+    if (p.dbg) {
+        atomicMax(&dbg_max[1], (unsigned long long)(clock64() - t_scan));
+        __syncthreads();
+    }
     if (p.dbg && tid == 0) {
         long long* d = p.dbg + static_cast<size_t>(slot) * 8;
         d[3] = t_drain;              // of which phase C (cell tests)
@@ -817,8 +822,8 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : (MOD
         d[1] = t_a - t_pro;          // phase A
         d[2] = t_scan - t_a;         // scan + tests
         d[4] = (long long)dbg_max[0];   // max over warps: B1 time in the first round
-        d[6] = 0;
-        d[5] = rounds;
+        d[6] = (long long)dbg_max[1];   // max over threads: phase D
+        d[5] = (long long)dbg_max[2];   // prologue up to the first barrier (loads arrived, matrices built)
         d[7] = clock64() - t_start;
     }
 }

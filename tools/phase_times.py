@@ -28,7 +28,7 @@ for rep in range(3):
     print("rep", rep, "kernel ms", ctx.last_minksweep_ms())
 out = np.zeros((n_cta, 8), dtype=np.int64)
 lib.hrmgpu_debug_phase_times(ctx.h, 1, n_cta, out.ctypes.data_as(C.c_void_p))
-names = ["prologue", "phase A", "scan + tests", "of which C", "max B1 (warp)", "extra rounds", "(unused)", "total"]
+names = ["prologue", "phase A", "scan + tests", "of which C", "max B1 (warp)", "prologue: loads", "max D (thread)", "total"]
 arena = (np.arange(n_cta) % (wl.N_OBS + 1)) == 0
 for label, sel in (("obstacle CTAs", ~arena), ("arena CTAs", arena)):
     print(label, sel.sum())
