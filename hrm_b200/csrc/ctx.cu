@@ -52,8 +52,8 @@ int upload(Ctx* c, DevBuf<T>& buf, const T* h, size_t n) {
 }
 
 template <class T>
-void release(DevBuf<T>& b) {
-    if (b.p) cudaFree(b.p);
+void release(Ctx* c, DevBuf<T>& b) {
+    if (b.p) cudaFreeAsync(b.p, c->stream);
     b.p = nullptr;
     b.n = 0;
 }
@@ -109,6 +109,14 @@ int hrmgpu_create(hrmgpu_ctx** out, int device, unsigned flags) {
         return HRMGPU_E_CUDA;
     }
     c->stream = c->own_stream;
+    {
+        // keep freed blocks in the pool (see ensure()); hrmgpu_destroy trims what exceeds kPoolKeepBytes
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long thr = ~0ULL;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
     // test hooks of the segment pass (tests/test_gpu_layers3d.py): list capacity of the 4-line kernel / one-line kernel only
     if (const char* e = std::getenv("HRMGPU_SEG_FAST_CAP")) c->seg_fast_cap = std::atoi(e);
     if (const char* e = std::getenv("HRMGPU_SEG_ONE_LINE")) c->force_seg_fallback = std::atoi(e) != 0;
@@ -127,39 +135,45 @@ void hrmgpu_destroy(hrmgpu_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    release(c->obj3);
-    release(c->obj2);
-    release(c->tab);
-    release(c->txs);
-    release(c->tys);
-    release(c->body_semi);
-    release(c->body_R);
-    release(c->body_off);
-    release(c->mesh);
-    release(c->ivl_lo);
-    release(c->ivl_up);
-    release(c->orig);
-    release(c->orig_cnt);
-    release(c->seg_cnt);
-    release(c->seg_off);
-    release(c->segL);
-    release(c->segU);
-    release(c->segM);
-    release(c->counters);
-    release(c->bridge_mesh);
-    release(c->dbg);
-    release(c->q_a);
-    release(c->q_b);
-    release(c->q_out);
-    release(c->bbox);
-    release(c->q_flag);
-    release(c->q_set);
-    release(c->q_w);
-    release(c->q_loff);
-    release(c->bridge_bbox);
-    release(c->bridge_semi);
-    release(c->bridge_R);
-    release(c->bridge_off);
+    c->stream = c->own_stream;  // (an external stream may not outlive this call: free on the context's own stream)
+    release(c, c->obj3);
+    release(c, c->obj2);
+    release(c, c->tab);
+    release(c, c->txs);
+    release(c, c->tys);
+    release(c, c->body_semi);
+    release(c, c->body_R);
+    release(c, c->body_off);
+    release(c, c->mesh);
+    release(c, c->ivl_lo);
+    release(c, c->ivl_up);
+    release(c, c->orig);
+    release(c, c->orig_cnt);
+    release(c, c->seg_cnt);
+    release(c, c->seg_off);
+    release(c, c->segL);
+    release(c, c->segU);
+    release(c, c->segM);
+    release(c, c->counters);
+    release(c, c->bridge_mesh);
+    release(c, c->dbg);
+    release(c, c->q_a);
+    release(c, c->q_b);
+    release(c, c->q_out);
+    release(c, c->bbox);
+    release(c, c->q_flag);
+    release(c, c->q_set);
+    release(c, c->q_w);
+    release(c, c->q_loff);
+    release(c, c->bridge_bbox);
+    release(c, c->bridge_semi);
+    release(c, c->bridge_R);
+    release(c, c->bridge_off);
+    if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+    {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) cudaMemPoolTrimTo(pool, kPoolKeepBytes);
+    }
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -680,7 +694,7 @@ long long hrmgpu_debug_phase_times(hrmgpu_ctx* c, int enable, long long n_cta, l
     if (!c) return HRMGPU_E_ARG;
     if (cudaSetDevice(c->device) != cudaSuccess) return HRMGPU_E_CUDA;
     if (!enable) {
-        release(c->dbg);
+        release(c, c->dbg);
         return 0;
     }
     if (out && c->dbg.p && c->dbg.n >= static_cast<size_t>(n_cta) * 8) {

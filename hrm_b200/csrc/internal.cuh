@@ -17,6 +17,7 @@ constexpr int kMaxGrid = 200;          // n_grid limit (vertex line codes: 4*n^2
 constexpr int kMaxLinesAxis = 16383;   // per-axis sweep-line limit (15-bit line codes)
 constexpr int kMaxLines = 8192;        // Lx*Ly limit (two-slot hit tables in shared memory)
 constexpr uint32_t kNoFace = 0xFFFFFFFFu;
+constexpr size_t kPoolKeepBytes = size_t(1) << 30;  // freed device memory kept in the pool across contexts (hrmgpu_destroy trims the rest)
 
 // Device-side description of one arena/obstacle superquadric (SoA would not help: 17 doubles read
 // once per CTA through the read-only path).
@@ -104,16 +105,20 @@ struct Ctx {
         }                                                                                             \
     } while (0)
 
+// Device buffers come from the device's default stream-ordered memory pool (cudaMallocAsync on the context's stream): a planner
+// object creates a context, grows ~30 buffers and destroys it again, and with plain cudaMalloc / cudaFree some of those calls take
+// tens of milliseconds (measured: sporadic 20-60 ms inside K4 / K5a / buildLayers of HRM3D::plan()).  hrmgpu_create raises the
+// pool's release threshold so that freed blocks are reused by the next context instead of going back to the driver.
 template <class T>
 inline int ensure(Ctx* c, DevBuf<T>& b, size_t n) {
     if (b.n >= n && b.p) return HRMGPU_OK;
     if (b.p) {
-        cudaFree(b.p);
+        cudaFreeAsync(b.p, c->stream);  // stream-ordered: work already queued on the stream may still use it
         b.p = nullptr;
         b.n = 0;
     }
     if (n == 0) n = 1;
-    HRMGPU_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&b.p), n * sizeof(T)));
+    HRMGPU_CUDA(c, cudaMallocAsync(reinterpret_cast<void**>(&b.p), n * sizeof(T), c->stream));
     b.n = n;
     return HRMGPU_OK;
 }

@@ -1,5 +1,5 @@
 """Repeats HRM3D::plan() on the bundled cluttered map and prints the wall clock of every call (stall hunting aid):
-    python tools/plan_repeat.py [calls]"""
+    python tools/plan_repeat.py [calls] [scene] [Lx Ly]"""
 import json
 import os
 import sys
@@ -12,7 +12,10 @@ sys.path.insert(0, ROOT)
 from hrm_b200 import hostlib  # noqa: E402
 
 calls = int(sys.argv[1]) if len(sys.argv) > 1 else 12
-sc = json.load(open(os.path.join(ROOT, "tests", "golden", "scenes.json")))["3D_superquadrics_cluttered_rabbit"]
+name = sys.argv[2] if len(sys.argv) > 2 else "3D_superquadrics_cluttered_rabbit"
+sc = json.load(open(os.path.join(ROOT, "tests", "golden", "scenes.json")))[name]
+if len(sys.argv) > 4:
+    sc["Lx"], sc["Ly"] = int(sys.argv[3]), int(sys.argv[4])
 rows = np.array(sc["arena"] + sc["obstacle"])
 a = (len(sc["arena"]), len(sc["obstacle"]), rows, 10, np.array(sc["robot"]), np.array(sc["quats"]), sc["lim"], sc["Lx"], sc["Ly"], 5, sc["end_points"][0],
      sc["end_points"][1])
