@@ -48,11 +48,11 @@ for k in keys:
 
 # phase roll-up for hrm_b200/csrc/mink3d.cu (+ device helpers): edit the ranges when the kernel moves
 if len(sys.argv) > 3 and sys.argv[3] == "phases":
-    ranges = [("line-code helpers (phase A)", "mink3d.cu", 1, 150), ("entry + smem carve-up + reload", "mink3d.cu", 151, 231),
-              ("prologue", "mink3d.cu", 232, 338), ("phase A", "mink3d.cu", 339, 548), ("face load/test lambdas (C, D)", "mink3d.cu", 549, 569),
+    ranges = [("line-code helpers (phase A)", "mink3d.cu", 1, 149), ("entry + smem carve-up + reload", "mink3d.cu", 150, 230),
+              ("prologue", "mink3d.cu", 231, 338), ("phase A", "mink3d.cu", 339, 548), ("face load/test lambdas (C, D)", "mink3d.cu", 549, 569),
               ("scan B1 (SWAR cell test)", "mink3d.cu", 570, 632), ("cell line sets / test_lines (C)", "mink3d.cu", 633, 654),
-              ("scan loop + cell lists (B1)", "mink3d.cu", 655, 718), ("phase C (per-cell tests)", "mink3d.cu", 719, 750),
-              ("heavy cells (C)", "mink3d.cu", 751, 784), ("phase D (re-test + intervals)", "mink3d.cu", 785, 826),
+              ("scan loop + cell lists (B1)", "mink3d.cu", 655, 719), ("phase C (per-cell tests)", "mink3d.cu", 720, 751),
+              ("heavy cells (C)", "mink3d.cu", 752, 785), ("phase D (re-test + intervals)", "mink3d.cu", 786, 831),
               ("rsqrt (phase A)", "devmath.cuh", 30, 50), ("triangle test (C, D)", "devmath.cuh", 51, 129),
               ("face_vertices / insert (C, D)", "devmath.cuh", 130, 200)]
     print("\nphase roll-up: share of warp instructions / of stall samples, top stall reasons")
