@@ -91,10 +91,50 @@ def plan_ms_block():
                 "edges": int(len(got["edge"])), "edge_tests": int(got["edge_tests"]), "gpu_launches": int(got["gpu_launches"]),
                 "identical_roadmap": bool(np.array_equal(got["vertex"], ref["vertex"]) and np.array_equal(got["edge"], ref["edge"]))}
 
+    def timed(gpu_call, cpu_call, label, extra=None):
+        t = []
+        for _ in range(4):
+            t0 = time.perf_counter()
+            got = gpu_call()
+            t.append((time.perf_counter() - t0) * 1e3)
+        t0 = time.perf_counter()
+        ref = cpu_call()
+        cpu_ms = (time.perf_counter() - t0) * 1e3
+        r = {"scene": label, "gpu_plan_ms": sorted(t[1:])[len(t[1:]) // 2], "gpu_plan_ms_planner_clock": got["total_time_s"] * 1e3,
+             "cpu_oracle_plan_ms": cpu_ms, "cpu_cores": 1, "solved": bool(got["solved"]), "vertices": int(len(got["vertex"])),
+             "edges": int(len(got["edge"])), "gpu_launches": int(got["gpu_launches"]),
+             "identical_roadmap": bool(np.array_equal(got["vertex"], ref["vertex"]) and np.array_equal(got["edge"], ref["edge"]))}
+        if extra:
+            r.update(extra(got))
+        return r
+
+    def hrm2d():
+        # configs[0]: TestHRM2D's scene (sparse map, rabbit robot, 50 points per curve) with the README bench's 20 slices x 30 lines
+        sc = scenes["2D_superellipse_sparse_rabbit"]
+        rows = np.array(sc["arena"] + sc["obstacle"])
+        a = (len(sc["arena"]), len(sc["obstacle"]), rows, 50, np.array(sc["robot"]), 20, sc["lim"], 30, 5, sc["end_points"][0], sc["end_points"][1])
+        return timed(lambda: hostlib.plan2d(*a, per_orientation=False, precision=0), lambda: hrmo.plan2d(*a, per_orientation=False),
+                     "HRM2D sparse/rabbit (BASELINE.json configs[0]), 20 C-layers, 50 points per curve, 30 sweep lines, F64_STRICT")
+
+    def prob3d():
+        # configs[3]: ProbHRM3D on the home map with the snake robot (URDF chain, TFE bridge layers); the random draws are a fixed
+        # Halton sequence injected into both planners (the reference seeds from the clock)
+        from tests.test_oracle_kat import GOLDEN, prob_samples
+
+        sc = scenes["3D_superquadrics_home_snake"]
+        rows = np.array(sc["arena"] + sc["obstacle"])
+        a = (len(sc["arena"]), len(sc["obstacle"]), rows, 10, np.array(sc["robot"]), os.path.join(GOLDEN, "snake.urdf"), prob_samples(30, 3),
+             sc["lim"], sc["Lx"], sc["Ly"], 5, sc["end_points"][0], sc["end_points"][1])
+        return timed(lambda: hostlib.plan_prob3d(*a, per_orientation=True, precision=0, batch=8), lambda: hrmo.plan_prob3d(*a, per_orientation=True),
+                     "ProbHRM3D home/snake (BASELINE.json configs[3]), n=10, %dx%d lines, injected draws, F64_STRICT" % (sc["Lx"], sc["Ly"]),
+                     lambda got: {"slices": int(got["slices"])})
+
     out = one("3D_superquadrics_cluttered_rabbit", 0, 0,
               "HRM3D cluttered/rabbit (BASELINE.json configs[1]), 60 C-layers, n=10, 11x5 lines, per-orientation, F64_STRICT")
     out["dense"] = one("3D_superquadrics_maze_rabbit", 44, 20,
                        "HRM3D maze/rabbit with dense sweep lines (BASELINE.json configs[2]), 60 C-layers, n=10, 44x20 lines, per-orientation, F64_STRICT")
+    out["hrm2d"] = hrm2d()
+    out["prob3d"] = prob3d()
     return out
 
 

@@ -56,6 +56,7 @@ def load():
         "hrmgpu_test_edges_multi": (i, [vp, i, vp, vp, vp, vp]),
         "hrmgpu_test_bridge_multi": (i, [vp, i, vp, vp, vp]),
         "hrmgpu_test_transitions": (i, [vp, i, vp, vp, vp, i, vp, vp, vp, vp]),
+        "hrmgpu_test_transitions_articulated": (i, [vp, i, vp, vp, vp, i, vp, vp, vp, vp, vp]),
         "hrmgpu_build_bridge": (i, [vp, i, i, vp, vp, i]),
         "hrmgpu_build_bridge2d": (i, [vp, i, i, vp, vp, i]),
         "hrmgpu_test_bridge": (i, [vp, i, i, vp, vp]),
@@ -259,14 +260,19 @@ class Context:
             self._chk(self.lib.hrmgpu_test_bridge_multi(self.h, Q, _p(pair), _p(centres), _p(out)))
         return out.astype(bool)
 
-    def test_transitions(self, pair, v0, v1, w0, w1, link_off):
-        """isMultiSliceTransitionFree for candidate vertex pairs, interpolation on the device (see include/hrmgpu.h)."""
+    def test_transitions(self, pair, v0, v1, w0, w1, link_off, chain_off=None):
+        """isMultiSliceTransitionFree for candidate vertex pairs, interpolation on the device (see include/hrmgpu.h);
+        chain_off selects the articulated variant (body centre = link_off + (chain_off + t))."""
         pair = np.ascontiguousarray(pair, dtype=np.int32)
         v0, v1, w0, w1, link_off = _d(v0), _d(v1), _d(w0), _d(w1), _d(link_off)
         Cn = pair.shape[0]
         out = np.zeros(Cn, dtype=np.uint8)
-        if Cn:
+        if Cn and chain_off is None:
             self._chk(self.lib.hrmgpu_test_transitions(self.h, Cn, _p(pair), _p(v0), _p(v1), w0.shape[0], _p(w0), _p(w1), _p(link_off), _p(out)))
+        elif Cn:
+            chain_off = _d(chain_off)
+            self._chk(self.lib.hrmgpu_test_transitions_articulated(self.h, Cn, _p(pair), _p(v0), _p(v1), w0.shape[0], _p(w0), _p(w1), _p(link_off),
+                                                                   _p(chain_off), _p(out)))
         return out.astype(bool)
 
     def pack_segments_dev(self, d_ptr=None, cap_bytes=0):

@@ -165,6 +165,7 @@ void hrmgpu_destroy(hrmgpu_ctx* c) {
     release(c, c->q_set);
     release(c, c->q_w);
     release(c, c->q_loff);
+    release(c, c->q_loff2);
     release(c, c->bridge_bbox);
     release(c, c->bridge_semi);
     release(c, c->bridge_R);
@@ -542,12 +543,13 @@ int hrmgpu_test_bridge_multi(hrmgpu_ctx* c, int Q, const int* pair, const double
     return HRMGPU_OK;
 }
 
-int hrmgpu_test_transitions(hrmgpu_ctx* c, int C, const int* pair, const double* v0, const double* v1, int T, const double* w0,
-                            const double* w1, const double* link_off, unsigned char* free_out) {
+static int test_transitions_common(hrmgpu_ctx* c, int C, const int* pair, const double* v0, const double* v1, int T, const double* w0,
+                                   const double* w1, const double* link_off, const double* link_off2, unsigned char* free_out) {
     if (!c) return HRMGPU_E_ARG;
     if (!c->bridge_built) return fail(c, HRMGPU_E_STATE, "test_transitions: no bridge layers built");
     if (C < 0 || T < 1 || (C > 0 && (!pair || !v0 || !v1 || !w0 || !w1 || !link_off || !free_out)))
         return fail(c, HRMGPU_E_ARG, "test_transitions: bad arguments");
+    if (link_off2 && c->dim != 3) return fail(c, HRMGPU_E_ARG, "test_transitions_articulated: 3D scenes only");
     if (C == 0) return HRMGPU_OK;
     for (int i = 0; i < C; ++i)
         if (pair[i] < 0 || pair[i] >= c->P) return fail(c, HRMGPU_E_ARG, "test_transitions: pair index out of range");
@@ -560,12 +562,27 @@ int hrmgpu_test_transitions(hrmgpu_ctx* c, int C, const int* pair, const double*
     std::vector<double> w(2 * static_cast<size_t>(T));
     for (int s = 0; s < T; ++s) w[s] = w0[s], w[T + s] = w1[s];
     if ((rc = upload(c, c->q_w, w.data(), w.size()))) return rc;
-    if ((rc = upload(c, c->q_loff, link_off, static_cast<size_t>(c->P) * T * c->bridge_B * c->dim))) return rc;
+    const size_t nl = static_cast<size_t>(c->P) * T * c->bridge_B * c->dim;
+    if ((rc = upload(c, c->q_loff, link_off, nl))) return rc;
+    if (link_off2 && (rc = upload(c, c->q_loff2, link_off2, nl))) return rc;
     if ((rc = ensure(c, c->q_out, static_cast<size_t>(C)))) return rc;
-    if ((rc = launch_transitions(c, C, T, c->q_set.p, c->q_a.p, c->q_b.p, c->q_w.p, c->q_w.p + T, c->q_loff.p, c->q_out.p))) return rc;
+    if ((rc = launch_transitions(c, C, T, c->q_set.p, c->q_a.p, c->q_b.p, c->q_w.p, c->q_w.p + T, c->q_loff.p, c->q_out.p,
+                                 link_off2 ? c->q_loff2.p : nullptr)))
+        return rc;
     HRMGPU_CUDA(c, cudaMemcpyAsync(free_out, c->q_out.p, static_cast<size_t>(C), cudaMemcpyDeviceToHost, c->stream));
     HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));  // (w is pageable host memory: its copy has completed when the call returns)
     return HRMGPU_OK;
+}
+
+int hrmgpu_test_transitions(hrmgpu_ctx* c, int C, const int* pair, const double* v0, const double* v1, int T, const double* w0,
+                            const double* w1, const double* link_off, unsigned char* free_out) {
+    return test_transitions_common(c, C, pair, v0, v1, T, w0, w1, link_off, nullptr, free_out);
+}
+
+int hrmgpu_test_transitions_articulated(hrmgpu_ctx* c, int C, const int* pair, const double* v0, const double* v1, int T, const double* w0,
+                                        const double* w1, const double* link_off, const double* chain_off, unsigned char* free_out) {
+    if (c && !chain_off) return fail(c, HRMGPU_E_ARG, "test_transitions_articulated: bad arguments");
+    return test_transitions_common(c, C, pair, v0, v1, T, w0, w1, link_off, chain_off, free_out);
 }
 
 int hrmgpu_get_dims(hrmgpu_ctx* c, long long* out) {

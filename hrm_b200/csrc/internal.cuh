@@ -93,7 +93,7 @@ struct Ctx {
     DevBuf<char> bridge_mesh;  // [P][n_obs][B][dim][M]
     DevBuf<double> bridge_semi, bridge_R, bridge_off;
     DevBuf<double> bridge_bbox;                  // [P][n_obs * B][6] (3D)
-    DevBuf<double> q_w, q_loff;                  // transition tests: interpolation weights [2][T], link offsets [P][T][B][dim]
+    DevBuf<double> q_w, q_loff, q_loff2;         // transition tests: interpolation weights [2][T], link offsets [P][T][B][dim] (+ chain offsets)
 };
 
 #define HRMGPU_CUDA(ctx, expr)                                                                        \
@@ -138,6 +138,6 @@ int launch_edges(Ctx* c, int k, int E, const double* d_v1, const double* d_v2, u
 int launch_bridge_test(Ctx* c, int p, int Q, const double* d_centres, unsigned char* d_out, const int* d_pair = nullptr);
 int launch_bridge_bbox(Ctx* c);
 int launch_transitions(Ctx* c, int C, int T, const int* d_pair, const double* d_v0, const double* d_v1, const double* d_w0, const double* d_w1,
-                       const double* d_link_off, unsigned char* d_out);
+                       const double* d_link_off, unsigned char* d_out, const double* d_link_off2 = nullptr);
 
 }  // namespace hrmgpu

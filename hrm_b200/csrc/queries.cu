@@ -285,6 +285,7 @@ struct TransParams {
     const double* w0;        // [T]
     const double* w1;        // [T]
     const double* link_off;  // [P][T][B][dim]
+    const double* link_off2; // [P][T][B][dim] or NULL: articulated robots, centre = link_off + (link_off2 + t)
     unsigned int* flag;      // [C] set to 1 when some pose is blocked
     unsigned long long* counters;
     size_t set_stride;
@@ -319,7 +320,12 @@ __global__ void __launch_bounds__(128) k_transitions3d(const TransParams p) {
             oy = __dadd_rn(__dmul_rn(w0, __ldg(a0 + 1)), __dmul_rn(w1, __ldg(a1 + 1)));
             oz = __dadd_rn(__dmul_rn(w0, __ldg(a0 + 2)), __dmul_rn(w1, __ldg(a1 + 2)));
             if (b > 0) {
-                const double* lo = p.link_off + ((static_cast<size_t>(set) * p.T + s) * p.B + b) * 3;
+                const size_t li = ((static_cast<size_t>(set) * p.T + s) * p.B + b) * 3;
+                if (p.link_off2) {  // gBase * FK * tf_i: the chain's translation is added to the base position first (MultiBodyTree3D.cpp:63-89)
+                    const double* l2 = p.link_off2 + li;
+                    ox = __dadd_rn(__ldg(l2), ox), oy = __dadd_rn(__ldg(l2 + 1), oy), oz = __dadd_rn(__ldg(l2 + 2), oz);
+                }
+                const double* lo = p.link_off + li;
                 ox = __dadd_rn(__ldg(lo), ox), oy = __dadd_rn(__ldg(lo + 1), oy), oz = __dadd_rn(__ldg(lo + 2), oz);
             }
             m = o * p.B + b;
@@ -518,13 +524,13 @@ int launch_bridge_bbox(Ctx* c) {
 }
 
 int launch_transitions(Ctx* c, int C, int T, const int* d_pair, const double* d_v0, const double* d_v1, const double* d_w0, const double* d_w1,
-                       const double* d_link_off, unsigned char* d_out) {
+                       const double* d_link_off, unsigned char* d_out, const double* d_link_off2) {
     int rc;
     if ((rc = ensure(c, c->q_flag, static_cast<size_t>(C)))) return rc;
     HRMGPU_CUDA(c, cudaMemsetAsync(c->q_flag.p, 0, sizeof(unsigned int) * C, c->stream));
     if (c->n_obs > 0) {
         TransParams p;
-        p.pair = d_pair, p.v0 = d_v0, p.v1 = d_v1, p.w0 = d_w0, p.w1 = d_w1, p.link_off = d_link_off;
+        p.pair = d_pair, p.v0 = d_v0, p.v1 = d_v1, p.w0 = d_w0, p.w1 = d_w1, p.link_off = d_link_off, p.link_off2 = d_link_off2;
         p.flag = c->q_flag.p;
         p.counters = c->counters.p;
         p.bbox = c->bridge_bbox.p;

@@ -204,20 +204,30 @@ class ProbHRM3D : public HRM3D {
                     ++have;
                 }
                 if (have == 0) break;  // injected draws exhausted
-                freeSpace_.buildLayers(poses, precision_);
-                freeSpace_.getFreeSegmentsAll(off, xL, xU, xM);
+                {
+                    StageScope ss(stage_, "buildLayers (K1-K3)");
+                    freeSpace_.buildLayers(poses, precision_);
+                    freeSpace_.getFreeSegmentsAll(off, xL, xU, xM);
+                }
                 batchStart = s, batchEnd = s + have;
             }
             // constructOneSlice: vertices + intra-layer edges of slice s
             const size_t k = s - batchStart;
             vertexTail_.assign(v_.at(s).begin() + 7, v_.at(s).end());
             q_.push_back({v_.at(s)[3], v_.at(s)[4], v_.at(s)[5], v_.at(s)[6]});
-            connectOneSlice3D(static_cast<int>(k), baseQ.at(k), tx, ty, off.data() + k * static_cast<size_t>(Lx) * Ly, xL, xU, xM);
+            {
+                StageScope ss(stage_, "connectOneSlice");
+                connectOneSlice3D(static_cast<int>(k), baseQ.at(k), tx, ty, off.data() + k * static_cast<size_t>(Lx) * Ly, xL, xU, xM);
+            }
             param_.numSlice++;
-            if (param_.numSlice >= 2) connectNearestSlice();
+            if (param_.numSlice >= 2) {
+                StageScope ss(stage_, "connectNearestSlice");
+                connectNearestSlice();
+            }
             res_.planningTime.buildTime += seconds(t0);
             t0 = std::chrono::high_resolution_clock::now();
             search();
+            stage_.add("search", seconds(t0));
             res_.planningTime.searchTime += seconds(t0);
             t0 = std::chrono::high_resolution_clock::now();
             res_.planningTime.totalTime = res_.planningTime.buildTime + res_.planningTime.searchTime;
@@ -230,6 +240,8 @@ class ProbHRM3D : public HRM3D {
             res_.solutionPath.solvedPath.push_back(goal_);
             res_.solutionPath.interpolatedPath = getInterpolatedSolutionPath(param_.numPoint);
         }
+        stage_.add("plan total", res_.planningTime.totalTime);
+        stage_.print();
     }
 
   protected:
@@ -300,45 +312,69 @@ class ProbHRM3D : public HRM3D {
         }
         const Index new0 = vertexIdx_.at(param_.numSlice - 1).first, new1 = vertexIdx_.at(param_.numSlice - 1).second;
         const Index start = vertexIdx_.at(minIdx).first, n1 = vertexIdx_.at(minIdx).second;
+        auto tT = std::chrono::high_resolution_clock::now();
         const auto tfe = computeTFE(v_.at(param_.numSlice - 1), v_.at(minIdx));
+        stage_.add("  TFE (host)", seconds(tT));
         if (n1 <= start || new1 <= new0) return;
-        freeSpace_.buildBridge({tfe}, precision_);
+        {
+            StageScope ss(stage_, "  K5a buildBridge");
+            freeSpace_.buildBridge({tfe}, precision_);
+        }
+        tT = std::chrono::high_resolution_clock::now();
         const double thx = 2.0 * (lim[1] - lim[0]) / static_cast<double>(param_.numLineX);
         const double thy = 2.0 * (lim[3] - lim[2]) / static_cast<double>(param_.numLineY);
-        const size_t steps = param_.numPoint;
+        const size_t steps = param_.numPoint, T = steps + 1;
+        // isMultiSliceTransitionFree (HRM3D.cpp:367-392) for every candidate pair in ONE launch with the interpolation on the device.
+        // Every vertex of a slice carries the slice's base orientation and joint angles, so the interpolated rotations, joint
+        // angles and with them the chain / link offsets of robotTF(urdf, gBase, joints) are the same for all candidates of the
+        // slice pair: T forward-kinematics evaluations per link instead of one per (candidate, pose).  Body centre of link i at
+        // pose s = linkOff + (chainOff + t) exactly as robotTF adds them (a.t = R fk.t + t; position = (a.R tf.t) + a.t).
+        const size_t B = robot_.getNumLinks() + 1;
+        std::vector<double> w0(T), w1(T), linkOff(T * B * 3, 0.0), chainOff(T * B * 3, 0.0);
+        {
+            const double dt = 1.0 / static_cast<double>(steps);
+            for (size_t s = 0; s < T; ++s) w1[s] = static_cast<double>(s) * dt, w0[s] = 1.0 - static_cast<double>(s) * dt;  // InterpolateSE3.cpp:5-29
+            const auto vi = interpolateCompoundSE3Rn(V[start], V[new0], steps);  // rotation and joint part only depend on the slices
+            const auto& tf = robot_.getTF();
+            const size_t nj = kdl_.getNrOfJoints();
+            for (size_t s = 0; s < T; ++s) {
+                const Mat3 R = toRotationMatrix({vi[s][3], vi[s][4], vi[s][5], vi[s][6]});
+                const std::vector<double> joints(vi[s].begin() + 7, vi[s].begin() + 7 + static_cast<long>(nj));
+                for (size_t l = 0; l + 1 < B; ++l) {
+                    const SE3Transform fk = kdl_.getTransform(joints, "body" + std::to_string(l + 1));
+                    const Vec3 c = matVec(R, fk.t);
+                    const Vec3 v = matVec(matMul(R, fk.R), tf[l].t);
+                    for (int d = 0; d < 3; ++d) chainOff[(s * B + (l + 1)) * 3 + d] = c[d], linkOff[(s * B + (l + 1)) * 3 + d] = v[d];
+                }
+            }
+        }
         std::vector<std::pair<Index, Index>> cand;
-        std::vector<double> centres;
+        std::vector<double> v0s, v1s;
         for (Index m0 = start; m0 < n1; ++m0)
             for (Index m1 = new0; m1 < new1; ++m1) {
                 if (std::fabs(V[m0][0] - V[m1][0]) > thx || std::fabs(V[m0][1] - V[m1][1]) > thy) continue;
                 cand.push_back({m0, m1});
-                for (const auto& vs : interpolateCompoundSE3Rn(V[m0], V[m1], steps)) {  // isMultiSliceTransitionFree (HRM3D.cpp:367-392)
-                    setTransform(vs);
-                    for (double v : robot_.getBase().getPosition()) centres.push_back(v);
-                    for (const auto& l : robot_.getLinks())
-                        for (double v : l.getPosition()) centres.push_back(v);
-                }
+                v0s.insert(v0s.end(), V[m0].begin(), V[m0].begin() + 3);
+                v1s.insert(v1s.end(), V[m1].begin(), V[m1].begin() + 3);
             }
-        std::map<std::pair<Index, Index>, bool> freePair;
+        stage_.add("  bridge candidates + FK (host)", seconds(tT));
+        std::vector<unsigned char> ok;
         if (!cand.empty()) {
-            const auto ok = freeSpace_.testBridge(0, centres, static_cast<int>(cand.size() * (steps + 1)));
-            for (size_t c = 0; c < cand.size(); ++c) {
-                bool all = true;
-                for (size_t s = 0; s <= steps; ++s) all = all && ok[c * (steps + 1) + s];
-                freePair[cand[c]] = all;
+            StageScope ss(stage_, "  K5b testTransitions");
+            ok = freeSpace_.testTransitions(std::vector<int>(cand.size(), 0), v0s, v1s, w0, w1, linkOff, &chainOff);
+        }
+        // replay with the reference's moving lower bound (candidates are listed by m0, ascending in m1)
+        Index n12 = new0;
+        size_t j = 0;
+        for (Index m0 = start; m0 < n1; ++m0) {
+            bool done = false;
+            for (; j < cand.size() && cand[j].first == m0; ++j) {
+                if (done || cand[j].second < n12 || !ok[j]) continue;
+                addEdge(m0, cand[j].second);
+                n12 = cand[j].second;
+                done = true;  // (break in the reference: the first free partner at or above the bound)
             }
         }
-        Index n12 = new0;  // replay with the reference's moving lower bound
-        for (Index m0 = start; m0 < n1; ++m0)
-            for (Index m1 = n12; m1 < new1; ++m1) {
-                const auto it = freePair.find({m0, m1});
-                if (it == freePair.end()) continue;
-                if (it->second) {
-                    addEdge(m0, m1);
-                    n12 = m1;
-                    break;
-                }
-            }
     }
 
     std::string urdfFile_;

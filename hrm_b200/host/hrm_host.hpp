@@ -425,11 +425,16 @@ class FreeSpaceGPU {
     /** isMultiSliceTransitionFree for candidate vertex pairs of any layer pairs in one launch, interpolation on the device:
      * v0, v1 [C][dim] vertex positions, w0/w1 [T] interpolation weights, linkOff [P][T][B][dim] rotated link translations */
     std::vector<unsigned char> testTransitions(const std::vector<int>& pair, const std::vector<double>& v0, const std::vector<double>& v1,
-                                               const std::vector<double>& w0, const std::vector<double>& w1, const std::vector<double>& linkOff) {
+                                               const std::vector<double>& w0, const std::vector<double>& w1, const std::vector<double>& linkOff,
+                                               const std::vector<double>* chainOff = nullptr) {
         std::vector<unsigned char> out(pair.size());
-        if (!out.empty())
+        if (out.empty()) return out;
+        if (!chainOff)
             check(hrmgpu_test_transitions(ctx_, static_cast<int>(out.size()), pair.data(), v0.data(), v1.data(), static_cast<int>(w0.size()), w0.data(),
                                           w1.data(), linkOff.data(), out.data()));
+        else  // articulated robot: body centre = linkOff + (chainOff + t)
+            check(hrmgpu_test_transitions_articulated(ctx_, static_cast<int>(out.size()), pair.data(), v0.data(), v1.data(),
+                                                      static_cast<int>(w0.size()), w0.data(), w1.data(), linkOff.data(), chainOff->data(), out.data()));
         return out;
     }
     long long kernelLaunches() { return hrmgpu_kernel_launches(ctx_, 0); }
@@ -555,14 +560,42 @@ struct PlanningResult {  // :53-65
 
 namespace planners {
 
-/** A* with the Euclidean heuristic of HighwayRoadMap-inl.h:135-147 (Boost.Graph replaced by a binary heap). */
-inline bool astar(const Graph& g, Index s, Index t, std::vector<Index>& pred) {
-    const Index n = g.vertex.size();
-    std::vector<std::vector<std::pair<Index, double>>> adj(n);
-    for (size_t i = 0; i < g.edge.size(); ++i) {
-        adj[g.edge[i].first].push_back({g.edge[i].second, g.weight[i]});
-        adj[g.edge[i].second].push_back({g.edge[i].first, g.weight[i]});
+/** Adjacency of the roadmap in CSR form (neighbours of a vertex in edge order, as pushing both directions of every edge in
+ * turn produces them) + connected components: built once per search() and shared by its A* runs. */
+struct GraphIndex {
+    std::vector<size_t> off;
+    std::vector<std::pair<Index, double>> nbr;
+    std::vector<Index> comp;
+    explicit GraphIndex(const Graph& g) {
+        const Index n = g.vertex.size();
+        off.assign(n + 1, 0);
+        for (const auto& e : g.edge) ++off[e.first + 1], ++off[e.second + 1];
+        for (Index i = 0; i < n; ++i) off[i + 1] += off[i];
+        nbr.resize(off[n]);
+        std::vector<size_t> fill(off.begin(), off.end() - 1);
+        for (size_t i = 0; i < g.edge.size(); ++i) {
+            nbr[fill[g.edge[i].first]++] = {g.edge[i].second, g.weight[i]};
+            nbr[fill[g.edge[i].second]++] = {g.edge[i].first, g.weight[i]};
+        }
+        comp.resize(n);
+        for (Index i = 0; i < n; ++i) comp[i] = i;
+        auto find = [&](Index x) {
+            while (comp[x] != x) comp[x] = comp[comp[x]], x = comp[x];
+            return x;
+        };
+        for (const auto& e : g.edge) {
+            const Index a = find(e.first), b = find(e.second);
+            if (a != b) comp[a < b ? b : a] = a < b ? a : b;
+        }
+        for (Index i = 0; i < n; ++i) comp[i] = find(i);
     }
+    bool connected(Index a, Index b) const { return comp[a] == comp[b]; }
+};
+
+/** A* with the Euclidean heuristic of HighwayRoadMap-inl.h:135-147 (Boost.Graph replaced by a binary heap). */
+inline bool astar(const Graph& g, const GraphIndex& gi, Index s, Index t, std::vector<Index>& pred) {
+    const Index n = g.vertex.size();
+    if (!gi.connected(s, t)) return false;  // (the search below would exhaust s's component and fail)
     std::vector<double> d(n, INFINITY);
     pred.assign(n, n);
     using QE = std::pair<double, Index>;
@@ -577,7 +610,8 @@ inline bool astar(const Graph& g, Index s, Index t, std::vector<Index>& pred) {
         if (closed[u]) continue;
         closed[u] = 1;
         if (u == t) return true;
-        for (const auto& e : adj[u]) {
+        for (size_t k = gi.off[u]; k < gi.off[u + 1]; ++k) {
+            const auto& e = gi.nbr[k];
             const double nd = d[u] + e.second;
             if (nd < d[e.first]) {
                 d[e.first] = nd;
@@ -588,6 +622,7 @@ inline bool astar(const Graph& g, Index s, Index t, std::vector<Index>& pred) {
     }
     return false;
 }
+inline bool astar(const Graph& g, Index s, Index t, std::vector<Index>& pred) { return astar(g, GraphIndex(g), s, t, pred); }
 
 /** Wall-clock per planner stage, printed at the end of plan() when the environment variable HRM_HOST_TIMING is set. */
 struct StageTimes {
@@ -668,10 +703,11 @@ class HighwayRoadMapBase {
         if (g.vertex.empty()) return;
         const auto idxS = getNearestNeighborsOnGraph(start_, param_.numSearchNeighbor, param_.searchRadius);
         const auto idxG = getNearestNeighborsOnGraph(goal_, param_.numSearchNeighbor, param_.searchRadius);
+        const GraphIndex gi(g);
         for (Index s : idxS)
             for (Index t : idxG) {
                 std::vector<Index> p;
-                if (astar(g, s, t, p)) {
+                if (astar(g, gi, s, t, p)) {
                     auto& sp = res_.solutionPath;
                     sp.PathId.clear();
                     sp.cost = 0, sp.costAsReference = 0;

@@ -160,6 +160,13 @@ int hrmgpu_test_bridge_multi(hrmgpu_ctx* ctx, int Q, const int* pair, const doub
  * the same for all candidates of a pair; row b = 0 is ignored).  free_out[c] = 1 iff every pose is free for every body. */
 int hrmgpu_test_transitions(hrmgpu_ctx* ctx, int C, const int* pair, const double* v0, const double* v1, int T, const double* w0,
                             const double* w1, const double* link_off, unsigned char* free_out);
+/* The same for an articulated robot (ProbHRM3D::connectMultiSlice, ProbHRM3D.cpp:105-162; poses set by
+ * MultiBodyTree3D::robotTF(urdf, gBase, joints), MultiBodyTree3D.cpp:55-89): link i sits at gBase * FK(body i) * tf_i, whose position is
+ * evaluated as  link_off + (chain_off + t)  with chain_off[pair][s][b] = R_s * FK_s(b).t (the chain's translation in the base frame of
+ * pose s, added to the base position first) and link_off[pair][s][b] = (R_s * FK_s(b).R) * tf_b.t.  All vertices of a slice share the
+ * slice's base orientation and joint angles, so both tables are per (pair, pose, body) like link_off above.  3D only. */
+int hrmgpu_test_transitions_articulated(hrmgpu_ctx* ctx, int C, const int* pair, const double* v0, const double* v1, int T, const double* w0,
+                                        const double* w1, const double* link_off, const double* chain_off, unsigned char* free_out);
 
 /* ---- multi-GPU exchange ------------------------------------------------------------------------ */
 /* Packs the last build's free segments into one contiguous DEVICE buffer owned by the caller's
