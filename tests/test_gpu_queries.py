@@ -162,6 +162,18 @@ def test_bridge3d_match_oracle(oracle, gpu_ctx):
             want[sel] &= want_for(p, centres)
     assert np.array_equal(got, want)
     assert 0 < want.sum() < C
+    # articulated variant (hrmgpu_test_transitions_articulated): body centre = link_off + (chain_off + t), in that order
+    chain_off = rng.uniform(-4, 4, size=(len(pairs), T, B, 3))
+    got = gpu_ctx.test_transitions(pair, v0, v1, w0, w1, link_off, chain_off)
+    want = np.ones(C, dtype=bool)
+    for p in range(len(pairs)):
+        sel = np.nonzero(pair == p)[0]
+        for s_ in range(T):
+            t = w0[s_] * v0[sel] + w1[s_] * v1[sel]
+            centres = np.stack([t if b == 0 else link_off[p, s_, b] + (chain_off[p, s_, b] + t) for b in range(B)], axis=1)
+            want[sel] &= want_for(p, centres)
+    assert np.array_equal(got, want)
+    assert 0 < want.sum() < C
 
 
 def test_bridge2d_match_oracle(oracle, gpu_ctx):
