@@ -173,7 +173,14 @@ void hrmgpu_destroy(hrmgpu_ctx* c) {
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     {
         cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) cudaMemPoolTrimTo(pool, kPoolKeepBytes);
+        if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) {
+            // give back what exceeds (memory still in use by other contexts + kPoolKeepBytes of free blocks); trimming below the
+            // used size would release every free block and send the next context's allocations to the driver again
+            unsigned long long reserved = 0, used = 0;
+            if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+                cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used + kPoolKeepBytes)
+                cudaMemPoolTrimTo(pool, static_cast<size_t>(used + kPoolKeepBytes));
+        }
     }
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
