@@ -59,7 +59,7 @@ class SuperEllipse {
   public:
     SuperEllipse() = default;
     SuperEllipse(std::vector<double> semiAxis, double epsilon, std::vector<double> position, double angle, Index num)
-        : semiAxis_(std::move(semiAxis)), epsilon_(epsilon), position_(std::move(position)), angle_(angle), num_(num) {}
+        : semiAxis_(std::move(semiAxis)), position_(std::move(position)), epsilon_(epsilon), angle_(angle), num_(num) {}
     const std::vector<double>& getSemiAxis() const { return semiAxis_; }
     double getEpsilon() const { return epsilon_; }
     const std::vector<double>& getPosition() const { return position_; }
