@@ -109,7 +109,8 @@ struct QueryParams {
 // directions -- which is the common case, the candidate segments of connectOneSlice run between neighbouring sweep lines);
 // the surviving items are then walked by the whole warp one after the other (faces in order, first two hits).
 template <class A, class Real>
-__global__ void __launch_bounds__(128) k_edges3d(const QueryParams p) {
+// (6 blocks per SM: 80 registers instead of 107; measured 7-13 % faster on the bundled maps, the same bound slows k_transitions3d down)
+__global__ void __launch_bounds__(128, 6) k_edges3d(const QueryParams p) {
     const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const long long item = warp_global * 32 + lane;
