@@ -1,5 +1,6 @@
-"""End-to-end run of hrm_b200/lib/BenchHRM3D (command-line twin of the reference's test/benchmark/BenchHRM3D.cpp): resources
-tree -> parsePlanningConfig -> loadEnvironment -> GPU-backed HRM3D -> time_high_3D.csv + vertex/edge/path/segment dumps.
+"""End-to-end run of hrm_b200/lib/hrm_run (one table-driven driver for HRM3D / HRM2D / ProbHRM3D): resources tree ->
+parsePlanningConfig -> loadEnvironment -> GPU-backed planner -> result/benchmark/time_*.csv (the column schema the reference's
+plotting scripts read) + vertex/edge/path/segment dumps.
 The resources tree is rebuilt from tests/golden/scenes.json (the reference's own files are not on the GPU box); the oracle
 plans on exactly the numbers the CLI parsed (hostlib.load_scene on the same config directory)."""
 import math
@@ -14,7 +15,7 @@ from tests import util
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-EXE = os.path.join(ROOT, "hrm_b200", "lib", "BenchHRM3D")
+EXE = os.path.join(ROOT, "hrm_b200", "lib", "hrm_run")
 
 
 def _angle_axis_row(row):
@@ -51,11 +52,12 @@ def test_bench_hrm3d_cli(oracle, name, tmp_path):
     res, cfg, out = tmp_path / "resources", tmp_path / "config", tmp_path / "result"
     make_resources(sc, res)
     os.makedirs(cfg), os.makedirs(out / "details"), os.makedirs(out / "benchmark")
-    env = dict(os.environ, HRM_RESOURCES_PATH=str(res), HRM_CONFIG_PATH=str(cfg), HRM_RESULT_PATH=str(out), HRM_STORE_DETAILS="1")
+    env = dict(os.environ, HRM_RESOURCES_PATH=str(res), HRM_CONFIG_PATH=str(cfg), HRM_RESULT_PATH=str(out))
     ns = len(sc["quats"])
-    p = subprocess.run([EXE, "t", "r", "2", "60", str(ns), "icosahedron"], env=env, capture_output=True, text=True, timeout=600)
+    p = subprocess.run([EXE, "hrm3d", "map=t", "robot=r", "trials=2", "time=60", f"slices={ns}", "so3=icosahedron", "details=1"], env=env,
+                       capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout + p.stderr
-    assert f"Initial number of C-slices: {ns}" in p.stdout and "Number of valid configurations:" in p.stdout
+    assert f"{ns} C-slices" in p.stdout and "trial 2/2: solved=" in p.stdout
 
     # what the CLI planned on, and the oracle's roadmap for exactly those numbers
     got = hostlib.load_scene("3D", str(cfg) + "/", str(res / "SO3_sequence" / f"q_icosahedron_{ns}.csv"))
@@ -93,7 +95,7 @@ def test_bench_hrm3d_cli(oracle, name, tmp_path):
 
 
 def test_bench_prob_hrm3d_cli(tmp_path):
-    """BenchProbHRM3D on the home map with the snake robot: resources -> config (robot type "snake" keeps 3 joint angles in
+    """hrm_run prob3d on the home map with the snake robot: resources -> config (robot type "snake" keeps 3 joint angles in
     the end points) -> URDF FK -> batched C-layers -> solved, with the reference's CSV columns."""
     import shutil
 
@@ -102,12 +104,11 @@ def test_bench_prob_hrm3d_cli(tmp_path):
     make_resources(sc, res, env="home", robot="snake")
     shutil.copy(os.path.join(ROOT, "tests", "golden", "snake.urdf"), res / "3D" / "urdf" / "snake.urdf")
     os.makedirs(cfg), os.makedirs(out / "details"), os.makedirs(out / "benchmark")
-    env = dict(os.environ, HRM_RESOURCES_PATH=str(res), HRM_CONFIG_PATH=str(cfg), HRM_RESULT_PATH=str(out), HRM_PER_ORIENTATION="1",
-               HRM_SEED="5")
-    exe = os.path.join(ROOT, "hrm_b200", "lib", "BenchProbHRM3D")
-    p = subprocess.run([exe, "home", "snake", "2", "120"], env=env, capture_output=True, text=True, timeout=900)
+    env = dict(os.environ, HRM_RESOURCES_PATH=str(res), HRM_CONFIG_PATH=str(cfg), HRM_RESULT_PATH=str(out))
+    p = subprocess.run([EXE, "prob3d", "map=home", "robot=snake", "trials=2", "time=120", "per_orientation=1", "seed=5"], env=env,
+                       capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stdout + p.stderr
-    assert "Final number of C-slices:" in p.stdout
+    assert "trial 2/2: solved=1" in p.stdout
     ends = (cfg / "end_points_3D.csv").read_text().strip().split("\n")
     assert all(len(l.split(",")) == 10 for l in ends)  # x,y,z, quaternion, 3 joints (parseStartGoalConfig, robotType == "snake")
     stats = (out / "benchmark" / "time_prob_high_3D.csv").read_text().strip().split("\n")
@@ -119,7 +120,7 @@ def test_bench_prob_hrm3d_cli(tmp_path):
 
 
 def test_bench_hrm2d_cli(oracle, tmp_path):
-    """BenchHRM2D (README example: sparse rabbit, 20 slices, 30 sweep lines): same roadmap size as the oracle planning on the
+    """hrm_run hrm2d (the reference README's example: sparse rabbit, 20 slices, 30 sweep lines): same roadmap size as the oracle planning on the
     numbers the CLI parsed; 2D resource rows are already in their final form (a,b,eps,x,y,angle)."""
     from hrm_b200 import hostlib
 
@@ -131,8 +132,7 @@ def test_bench_hrm2d_cli(oracle, tmp_path):
     _write(res / "2D" / "robot_r_2D.csv", sc["robot"])
     _write(res / "2D" / "setting_superellipse_t_2D.csv", sc["end_points"])
     env = dict(os.environ, HRM_RESOURCES_PATH=str(res), HRM_CONFIG_PATH=str(cfg), HRM_RESULT_PATH=str(out))
-    exe = os.path.join(ROOT, "hrm_b200", "lib", "BenchHRM2D")
-    p = subprocess.run([exe, "t", "r", "2", "20", "30"], env=env, capture_output=True, text=True, timeout=600)
+    p = subprocess.run([EXE, "hrm2d", "map=t", "robot=r", "trials=2", "slices=20", "ly=30"], env=env, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout + p.stderr
     got = hostlib.load_scene("2D", str(cfg) + "/", num_param=50, num_line_y=30)
     rows = np.vstack([got["arena"], got["obstacle"]])
@@ -143,4 +143,4 @@ def test_bench_hrm2d_cli(oracle, tmp_path):
     for line in stats[1:]:
         c = line.split(",")
         assert int(c[3]) == len(ref["vertex"]) and int(c[4]) == len(ref["edge"]) and int(c[5]) == len(ref["path"])
-    assert ref["solved"] and "Number of configurations in Path:" in p.stdout
+    assert ref["solved"] and "path_nodes=%d" % len(ref["path"]) in p.stdout
