@@ -61,6 +61,18 @@ def load():
         "hrmgpu_build_bridge2d": (i, [vp, i, i, vp, vp, i]),
         "hrmgpu_test_bridge": (i, [vp, i, i, vp, vp]),
         "hrmgpu_pack_segments_dev": (ll, [vp, vp, ll]),
+        "hrmgpu_join": (i, [vp]),
+        "hrmgpu_get_boundary_layer": (i, [vp, i, vp]),
+        "hrmgpu_fetch_segments_async": (ll, [vp, vp, vp, vp, vp, ll]),
+        "hrmgpu_wait_segments": (ll, [vp]),
+        "hrmgpu_comm_unique_id": (i, [vp]),
+        "hrmgpu_comm_init": (i, [vp, i, i, vp]),
+        "hrmgpu_comm_destroy": (i, [vp]),
+        "hrmgpu_allgather_layers": (i, [vp, vp, vp, ll, ll]),
+        "hrmgpu_gathered_info": (i, [vp, vp, vp]),
+        "hrmgpu_get_gathered": (ll, [vp, i, vp, vp, vp, vp, vp, ll]),
+        "hrmgpu_last_segments_ms": (C.c_double, [vp]),
+        "hrmgpu_segment_redos": (ll, [vp, i]),
         "hrmgpu_kernel_launches": (ll, [vp, i]),
         "hrmgpu_last_minksweep_ms": (C.c_double, [vp]),
     }
@@ -127,6 +139,10 @@ class Context:
     def synchronize(self):
         self._chk(self.lib.hrmgpu_synchronize(self.h))
 
+    def join(self):
+        """Main stream waits (on the device) for the side stream: free-segment passes, exchange."""
+        self._chk(self.lib.hrmgpu_join(self.h))
+
     def set_scene3d(self, n_arena, n_obs, sq17, n_grid):
         sq17 = _d(sq17).reshape(-1, 17)
         assert sq17.shape[0] == n_arena + n_obs
@@ -179,6 +195,13 @@ class Context:
         self._chk(self.lib.hrmgpu_get_boundary(self.h, k, surface, _p(out)))
         return out.T.copy()  # dim x M like the reference's BoundaryPoints
 
+    def boundary_layer(self, k):
+        """All S boundaries of layer k in one call: [S, dim, M] (each dim x M like the reference's BoundaryPoints)."""
+        d = self.dims()
+        out = np.zeros((d["S"], d["M"], d["dim"]))
+        self._chk(self.lib.hrmgpu_get_boundary_layer(self.h, k, _p(out)))
+        return np.ascontiguousarray(out.transpose(0, 2, 1))
+
     def intervals(self, k):
         d = self.dims()
         lo = np.zeros((d["L"], d["S"]))
@@ -202,6 +225,15 @@ class Context:
         xL, xU, xM = np.zeros(tot), np.zeros(tot), np.zeros(tot)
         self._chk(self.lib.hrmgpu_get_segments_all(self.h, _p(off), _p(xL), _p(xU), _p(xM), tot))
         return off, xL, xU, xM
+
+    def fetch_segments_async(self, off, xL, xU, xM):
+        """Queues the read-back of the last build into the given (pinned) numpy arrays and returns; see wait_segments()."""
+        assert off.dtype == np.int64 and xL.dtype == xU.dtype == xM.dtype == np.float64
+        return self._chk(self.lib.hrmgpu_fetch_segments_async(self.h, _p(off), _p(xL), _p(xU), _p(xM), min(len(xL), len(xU), len(xM))))
+
+    def wait_segments(self):
+        """Blocks until the queued read-back is complete; returns the segment count (HrmGpuError E_CAP if it did not fit)."""
+        return self._chk(self.lib.hrmgpu_wait_segments(self.h))
 
     def single_hit_count(self):
         out = np.zeros(1, dtype=np.int64)
@@ -277,6 +309,49 @@ class Context:
 
     def pack_segments_dev(self, d_ptr=None, cap_bytes=0):
         return self._chk(self.lib.hrmgpu_pack_segments_dev(self.h, C.c_void_p(d_ptr) if d_ptr else None, cap_bytes))
+
+    # ---- multi-GPU exchange ----
+    def comm_unique_id(self):
+        buf = np.zeros(128, dtype=np.uint8)
+        rc = self.lib.hrmgpu_comm_unique_id(_p(buf))
+        if rc != OK:
+            raise HrmGpuError(rc, "hrmgpu_comm_unique_id failed (NCCL not loadable?)")
+        return buf
+
+    def comm_init(self, n_ranks, rank, id128):
+        id128 = np.ascontiguousarray(id128, dtype=np.uint8)
+        assert id128.size == 128
+        self._chk(self.lib.hrmgpu_comm_init(self.h, n_ranks, rank, _p(id128)))
+
+    def comm_destroy(self):
+        self._chk(self.lib.hrmgpu_comm_destroy(self.h))
+
+    def allgather_layers(self, line_cap, seg_cap, nccl_comm=None, cuda_stream=None):
+        self._chk(self.lib.hrmgpu_allgather_layers(self.h, C.c_void_p(nccl_comm) if nccl_comm else None,
+                                                   C.c_void_p(cuda_stream) if cuda_stream else None, line_cap, seg_cap))
+
+    def gathered_info(self):
+        out = np.zeros(4, dtype=np.int64)
+        ptr = C.c_void_p()
+        self._chk(self.lib.hrmgpu_gathered_info(self.h, _p(out), C.byref(ptr)))
+        return {"world": int(out[0]), "rank": int(out[1]), "line_cap": int(out[2]), "seg_cap": int(out[3]), "d_blocks": ptr.value}
+
+    def gathered(self, rank):
+        """(off[lines+1], xL, xU, xM) of rank `rank` from the last exchange."""
+        info = self.gathered_info()
+        off = np.zeros(info["line_cap"] + 1, dtype=np.int64)
+        lines = C.c_longlong(0)
+        tot = self._chk(self.lib.hrmgpu_get_gathered(self.h, rank, C.byref(lines), _p(off), None, None, None, 0))
+        xL, xU, xM = np.zeros(tot), np.zeros(tot), np.zeros(tot)
+        if tot:
+            self._chk(self.lib.hrmgpu_get_gathered(self.h, rank, C.byref(lines), _p(off), _p(xL), _p(xU), _p(xM), tot))
+        return off[: lines.value + 1].copy(), xL, xU, xM
+
+    def last_segments_ms(self):
+        return float(self.lib.hrmgpu_last_segments_ms(self.h))
+
+    def segment_redos(self, reset=False):
+        return int(self.lib.hrmgpu_segment_redos(self.h, int(reset)))
 
     def kernel_launches(self, reset=False):
         return int(self.lib.hrmgpu_kernel_launches(self.h, int(reset)))

@@ -3,15 +3,15 @@
 // HRMGPU_E_NODEVICE and nothing else can be called.
 #include "internal.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <new>
 
 using namespace hrmgpu;
-
-struct hrmgpu_ctx : public Ctx {};
 
 namespace {
 
@@ -58,6 +58,29 @@ void release(Ctx* c, DevBuf<T>& b) {
     b.n = 0;
 }
 
+// Flips to the other interval-table buffer and sizes it.  The free-segment passes that read this buffer two builds ago run on
+// the side stream: the main stream waits for them (normally long finished) before the fused kernel overwrites the tables.
+int next_interval_tables(Ctx* c, size_t cnt) {
+    c->ivl_cur ^= 1;
+    const int cur = c->ivl_cur;
+    HRMGPU_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_k3[cur], 0));
+    int rc;
+    if ((rc = ensure(c, c->ivl_lo[cur], cnt))) return rc;
+    return ensure(c, c->ivl_up[cur], cnt);
+}
+
+// planar Real[S][dim][M] of one layer -> double[S][M][dim] (the reference's column-major dim x M per surface)
+template <class Real>
+__global__ void __launch_bounds__(256) k_interleave_boundary(const Real* __restrict__ planar, double* __restrict__ out, int dim, int M, long long total) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long surf = i / (static_cast<long long>(dim) * M);
+        const int r = static_cast<int>(i - surf * dim * M);
+        const int pt = r / dim, d = r - pt * dim;
+        out[i] = static_cast<double>(planar[surf * dim * M + static_cast<long long>(d) * M + pt]);
+    }
+}
+
 int check_built(Ctx* c, int k) {
     if (!c->built) return fail(c, HRMGPU_E_STATE, "no layers built yet");
     if (k < 0 || k >= c->K) return fail(c, HRMGPU_E_ARG, "layer index out of range");
@@ -66,14 +89,38 @@ int check_built(Ctx* c, int k) {
 
 }  // namespace
 
+namespace hrmgpu {
+cudaMemPool_t library_pool(int device) {
+    static std::mutex mu;
+    static std::vector<cudaMemPool_t> pools;
+    std::lock_guard<std::mutex> lock(mu);
+    if (device < 0) return nullptr;
+    if (pools.size() <= static_cast<size_t>(device)) pools.resize(static_cast<size_t>(device) + 1, nullptr);
+    if (!pools[device]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        cudaMemPool_t pool = nullptr;
+        if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        unsigned long long thr = ~0ULL;  // keep freed blocks; hrmgpu_destroy trims what exceeds kPoolKeepBytes
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        pools[device] = pool;
+    }
+    return pools[device];
+}
+}  // namespace hrmgpu
+
 extern "C" {
 
 // The library holds ~40 kernel variants; with CUDA's default lazy module loading their first uses cost tens of milliseconds
-// spread over the first planner calls (measured: HRM3D::plan() 29 / 30 / 17 ms before settling at 12.8 ms; 15 / 13 / 13 ms with
-// eager loading).  Ask for eager loading when the library is loaded, unless the process has chosen a mode itself; it takes
-// effect if the CUDA driver is not initialised yet (a host that initialises CUDA first sets CUDA_MODULE_LOADING itself).
-__attribute__((constructor)) static void hrmgpu_prefer_eager_module_loading() { setenv("CUDA_MODULE_LOADING", "EAGER", 0); }
-
+// spread over the first planner calls (measured: HRM3D::plan() 29 / 30 / 17 ms before settling at 12.8 ms; 15 / 13 / 13 ms when
+// loaded up front).  The first hrmgpu_create of the process therefore loads the library's OWN kernels explicitly
+// (cudaFuncGetAttributes per kernel, preload_*); nothing process-wide (CUDA_MODULE_LOADING, the default memory pool) is changed.
 int hrmgpu_abi_version(void) { return HRMGPU_ABI_VERSION; }
 
 int hrmgpu_device_count(void) {
@@ -103,27 +150,42 @@ int hrmgpu_create(hrmgpu_ctx** out, int device, unsigned flags) {
     if (!c) return HRMGPU_E_NOMEM;
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
-        delete c;
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // (numerically lower = higher priority)
+    // the side stream gets the higher priority: its short kernels are dispatched as soon as the fused kernel frees CTA slots
+    bool ok = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&c->s2, cudaStreamNonBlocking, prio_hi) == cudaSuccess && cudaEventCreate(&c->ev0) == cudaSuccess &&
+              cudaEventCreate(&c->ev1) == cudaSuccess && cudaEventCreate(&c->ev2) == cudaSuccess && cudaEventCreate(&c->ev3) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c->ev_fused, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c->ev_k3[0], cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c->ev_k3[1], cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c->ev_fetch, cudaEventDisableTiming) == cudaSuccess &&
+              cudaMallocHost(reinterpret_cast<void**>(&c->h_info), 4 * sizeof(unsigned long long)) == cudaSuccess;
+    if (!ok) {
+        cudaGetLastError();
+        hrmgpu_destroy(c);
         return HRMGPU_E_CUDA;
     }
+    c->h_info[0] = c->h_info[1] = c->h_info[2] = c->h_info[3] = 0;
     c->stream = c->own_stream;
+    c->pool = library_pool(device);
+    if (!c->pool) {
+        hrmgpu_destroy(c);
+        return HRMGPU_E_CUDA;
+    }
     {
-        // keep freed blocks in the pool (see ensure()); hrmgpu_destroy trims what exceeds kPoolKeepBytes
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-            unsigned long long thr = ~0ULL;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-        }
+        static std::once_flag once;
+        std::call_once(once, [] { preload_mink3d(), preload_mink2d(), preload_segments(), preload_queries(), preload_exchange(); });
     }
     // test hooks of the segment pass (tests/test_gpu_layers3d.py): list capacity of the 4-line kernel / one-line kernel only
     if (const char* e = std::getenv("HRMGPU_SEG_FAST_CAP")) c->seg_fast_cap = std::atoi(e);
     if (const char* e = std::getenv("HRMGPU_SEG_ONE_LINE")) c->force_seg_fallback = std::atoi(e) != 0;
+    if (const char* e = std::getenv("HRMGPU_SEG_INIT_CAP")) c->seg_init_cap = std::atoll(e);
     // test hook of the fused kernel: capacity of a warp's kept-cell list (small values force the multi-round path)
     if (const char* e = std::getenv("HRMGPU_CELL_SEG_CAP")) c->cell_seg_cap = std::atoi(e);
     if (ensure(c, c->counters, 4) != HRMGPU_OK) {
-        delete c;
+        hrmgpu_destroy(c);
         return HRMGPU_E_NOMEM;
     }
     cudaMemsetAsync(c->counters.p, 0, 4 * sizeof(unsigned long long), c->stream);
@@ -134,8 +196,19 @@ int hrmgpu_create(hrmgpu_ctx** out, int device, unsigned flags) {
 void hrmgpu_destroy(hrmgpu_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->s2) cudaStreamSynchronize(c->s2);
+    hrmgpu_comm_destroy(c);
     c->stream = c->own_stream;  // (an external stream may not outlive this call: free on the context's own stream)
+    if (!c->stream || !c->pool) {  // creation failed half-way: nothing was allocated from the pool yet
+        if (c->own_stream) cudaStreamDestroy(c->own_stream);
+        if (c->s2) cudaStreamDestroy(c->s2);
+        if (c->h_info) cudaFreeHost(c->h_info);
+        for (cudaEvent_t e : {c->ev0, c->ev1, c->ev2, c->ev3, c->ev_fused, c->ev_k3[0], c->ev_k3[1], c->ev_join, c->ev_fetch})
+            if (e) cudaEventDestroy(e);
+        delete c;
+        return;
+    }
     release(c, c->obj3);
     release(c, c->obj2);
     release(c, c->tab);
@@ -145,15 +218,20 @@ void hrmgpu_destroy(hrmgpu_ctx* c) {
     release(c, c->body_R);
     release(c, c->body_off);
     release(c, c->mesh);
-    release(c, c->ivl_lo);
-    release(c, c->ivl_up);
+    release(c, c->ivl_lo[0]);
+    release(c, c->ivl_lo[1]);
+    release(c, c->ivl_up[0]);
+    release(c, c->ivl_up[1]);
     release(c, c->orig);
+    release(c, c->orig_off);
     release(c, c->orig_cnt);
     release(c, c->seg_cnt);
     release(c, c->seg_off);
-    release(c, c->segL);
-    release(c, c->segU);
-    release(c, c->segM);
+    release(c, c->segdata);
+    release(c, c->seg_info);
+    release(c, c->xchg_send);
+    release(c, c->xchg_recv);
+    release(c, c->bound_tmp);
     release(c, c->counters);
     release(c, c->bridge_mesh);
     release(c, c->dbg);
@@ -172,8 +250,8 @@ void hrmgpu_destroy(hrmgpu_ctx* c) {
     release(c, c->bridge_off);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     {
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) {
+        cudaMemPool_t pool = c->pool;
+        if (pool) {
             // give back what exceeds (memory still in use by other contexts + kPoolKeepBytes of free blocks); trimming below the
             // used size would release every free block and send the next context's allocations to the driver again
             unsigned long long reserved = 0, used = 0;
@@ -182,8 +260,11 @@ void hrmgpu_destroy(hrmgpu_ctx* c) {
                 cudaMemPoolTrimTo(pool, static_cast<size_t>(used + kPoolKeepBytes));
         }
     }
-    if (c->ev0) cudaEventDestroy(c->ev0);
-    if (c->ev1) cudaEventDestroy(c->ev1);
+    for (cudaEvent_t e : {c->ev0, c->ev1, c->ev2, c->ev3, c->ev_fused, c->ev_k3[0], c->ev_k3[1], c->ev_join, c->ev_fetch})
+        if (e) cudaEventDestroy(e);
+    if (c->h_info) cudaFreeHost(c->h_info);
+    if (c->h_off) cudaFreeHost(c->h_off);
+    if (c->s2) cudaStreamDestroy(c->s2);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -193,6 +274,7 @@ const char* hrmgpu_last_error(const hrmgpu_ctx* c) { return c ? c->err.c_str() :
 int hrmgpu_set_stream(hrmgpu_ctx* c, void* s) {
     if (!c) return HRMGPU_E_ARG;
     HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));
+    HRMGPU_CUDA(c, cudaStreamSynchronize(c->s2));
     c->stream = s ? static_cast<cudaStream_t>(s) : c->own_stream;
     return HRMGPU_OK;
 }
@@ -200,6 +282,14 @@ int hrmgpu_set_stream(hrmgpu_ctx* c, void* s) {
 int hrmgpu_synchronize(hrmgpu_ctx* c) {
     if (!c) return HRMGPU_E_ARG;
     HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));
+    HRMGPU_CUDA(c, cudaStreamSynchronize(c->s2));
+    return HRMGPU_OK;
+}
+
+int hrmgpu_join(hrmgpu_ctx* c) {
+    if (!c) return HRMGPU_E_ARG;
+    HRMGPU_CUDA(c, cudaEventRecord(c->ev_join, c->s2));
+    HRMGPU_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     return HRMGPU_OK;
 }
 
@@ -239,6 +329,7 @@ int hrmgpu_set_scene3d(hrmgpu_ctx* c, int n_arena, int n_obs, const double* sq, 
     if ((rc = upload(c, c->obj3, objs.data(), objs.size()))) return rc;
     if ((rc = upload(c, c->tab, tab.data(), tab.size()))) return rc;
     HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));  // host vectors go out of scope
+    if (c->dim != 3) c->sweep_set = false;  // a 2D sweep grid (Lx forced to 1) is not a valid 3D grid
     c->dim = 3;
     c->n_arena = n_arena;
     c->n_obs = n_obs;
@@ -306,15 +397,14 @@ int hrmgpu_resweep(hrmgpu_ctx* c, const double* lim, int Lx, int Ly) {
     c->built = false;
     const int S0 = c->n_arena + c->n_obs;
     c->L = c->Lx * c->Ly;
-    if ((rc = ensure(c, c->ivl_lo, static_cast<size_t>(c->K) * c->S * c->L))) return rc;
-    if ((rc = ensure(c, c->ivl_up, static_cast<size_t>(c->K) * c->S * c->L))) return rc;
+    if ((rc = next_interval_tables(c, static_cast<size_t>(c->K) * c->S * c->L))) return rc;
+    double *lo = c->ivl_lo[c->ivl_cur].p, *up = c->ivl_up[c->ivl_cur].p;
     HRMGPU_CUDA(c, cudaMemsetAsync(c->counters.p, 0, 4 * sizeof(unsigned long long), c->stream));
     HRMGPU_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     if (c->dim == 3)
-        rc = launch_minksweep3d(c, c->K, c->B, 0, S0, nullptr, nullptr, nullptr, c->prec, c->mesh.p, c->ivl_lo.p, c->ivl_up.p, true, true);
+        rc = launch_minksweep3d(c, c->K, c->B, 0, S0, nullptr, nullptr, nullptr, c->prec, c->mesh.p, lo, up, true, true);
     else
-        rc = launch_minksweep2d(c, c->K, c->B, 0, S0, c->body_semi.p, c->body_R.p, c->body_off.p, c->prec, c->mesh.p, c->ivl_lo.p, c->ivl_up.p,
-                                true, true);
+        rc = launch_minksweep2d(c, c->K, c->B, 0, S0, c->body_semi.p, c->body_R.p, c->body_off.p, c->prec, c->mesh.p, lo, up, true, true);
     if (rc) return rc;
     HRMGPU_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     if ((rc = launch_segments(c))) return rc;
@@ -326,7 +416,7 @@ int hrmgpu_build_layers_dev(hrmgpu_ctx* c, int K, int B, const double* d_semi, c
                             int precision) {
     if (!c) return HRMGPU_E_ARG;
     if (c->dim != 3) return fail(c, HRMGPU_E_STATE, "build_layers: no 3D scene set");
-    if (!c->sweep_set) return fail(c, HRMGPU_E_STATE, "build_layers: set_sweep first");
+    if (!c->sweep_set || c->Lx < 2 || c->Ly < 2) return fail(c, HRMGPU_E_STATE, "build_layers: set_sweep first");
     if (K < 0 || B < 1 || !d_semi || (K > 0 && (!d_R || !d_off))) return fail(c, HRMGPU_E_ARG, "build_layers: bad arguments");
     if (precision < HRMGPU_F64_STRICT || precision > HRMGPU_F32) return fail(c, HRMGPU_E_ARG, "build_layers: unknown precision");
     HRMGPU_CUDA(c, cudaSetDevice(c->device));
@@ -335,13 +425,14 @@ int hrmgpu_build_layers_dev(hrmgpu_ctx* c, int K, int B, const double* d_semi, c
     const size_t real = (precision == HRMGPU_F32) ? 4 : 8;
     int rc;
     if ((rc = ensure(c, c->mesh, static_cast<size_t>(K) * S * 3 * M * real))) return rc;
-    if ((rc = ensure(c, c->ivl_lo, static_cast<size_t>(K) * S * L))) return rc;
-    if ((rc = ensure(c, c->ivl_up, static_cast<size_t>(K) * S * L))) return rc;
+    if ((rc = next_interval_tables(c, static_cast<size_t>(K) * S * L))) return rc;
     HRMGPU_CUDA(c, cudaMemsetAsync(c->counters.p, 0, 4 * sizeof(unsigned long long), c->stream));
     c->K = K, c->B = B, c->S = S, c->Sa = Sa, c->L = L, c->M = M, c->prec = precision;
     c->built = false;
+    c->last_semi = d_semi, c->last_R = d_R, c->last_off = d_off;
     HRMGPU_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-    if ((rc = launch_minksweep3d(c, K, B, 0, S0, d_semi, d_R, d_off, precision, c->mesh.p, c->ivl_lo.p, c->ivl_up.p, true))) return rc;
+    if ((rc = launch_minksweep3d(c, K, B, 0, S0, d_semi, d_R, d_off, precision, c->mesh.p, c->ivl_lo[c->ivl_cur].p, c->ivl_up[c->ivl_cur].p, true)))
+        return rc;
     HRMGPU_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     if ((rc = launch_segments(c))) return rc;
     c->built = true;
@@ -414,14 +505,13 @@ int hrmgpu_build_layers2d(hrmgpu_ctx* c, int K, int B, const double* semi, const
     const int S0 = c->n_arena + c->n_obs;
     const int S = S0 * B, Sa = c->n_arena * B, L = c->Ly, M = c->n;
     if ((rc = ensure(c, c->mesh, static_cast<size_t>(K) * S * 2 * M * 8))) return rc;
-    if ((rc = ensure(c, c->ivl_lo, static_cast<size_t>(K) * S * L))) return rc;
-    if ((rc = ensure(c, c->ivl_up, static_cast<size_t>(K) * S * L))) return rc;
+    if ((rc = next_interval_tables(c, static_cast<size_t>(K) * S * L))) return rc;
     HRMGPU_CUDA(c, cudaMemsetAsync(c->counters.p, 0, 4 * sizeof(unsigned long long), c->stream));
     c->K = K, c->B = B, c->S = S, c->Sa = Sa, c->L = L, c->M = M, c->prec = precision;
     c->built = false;
     HRMGPU_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-    if ((rc = launch_minksweep2d(c, K, B, 0, S0, c->body_semi.p, c->body_R.p, c->body_off.p, precision, c->mesh.p, c->ivl_lo.p,
-                                 c->ivl_up.p, true)))
+    if ((rc = launch_minksweep2d(c, K, B, 0, S0, c->body_semi.p, c->body_R.p, c->body_off.p, precision, c->mesh.p, c->ivl_lo[c->ivl_cur].p,
+                                 c->ivl_up[c->ivl_cur].p, true)))
         return rc;
     HRMGPU_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));  // cs goes out of scope
@@ -595,6 +685,7 @@ int hrmgpu_test_transitions_articulated(hrmgpu_ctx* c, int C, const int* pair, c
 int hrmgpu_get_dims(hrmgpu_ctx* c, long long* out) {
     if (!c || !out) return HRMGPU_E_ARG;
     if (!c->built) return fail(c, HRMGPU_E_STATE, "no layers built yet");
+    if (int rc = finalize_segments(c)) return rc;
     out[0] = c->K, out[1] = c->B, out[2] = c->S, out[3] = c->Sa, out[4] = c->L, out[5] = c->M, out[6] = c->seg_total, out[7] = c->dim;
     return HRMGPU_OK;
 }
@@ -623,6 +714,26 @@ int hrmgpu_get_boundary(hrmgpu_ctx* c, int k, int surface, double* xyz) {
     return HRMGPU_OK;
 }
 
+int hrmgpu_get_boundary_layer(hrmgpu_ctx* c, int k, double* xyz) {
+    if (!c || !xyz) return HRMGPU_E_ARG;
+    int rc = check_built(c, k);
+    if (rc) return rc;
+    HRMGPU_CUDA(c, cudaSetDevice(c->device));
+    const int D = c->dim, M = c->M;
+    const long long total = static_cast<long long>(c->S) * D * M;
+    if ((rc = ensure(c, c->bound_tmp, static_cast<size_t>(total)))) return rc;
+    const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 8LL * c->num_sms));
+    if (c->prec == HRMGPU_F32)
+        k_interleave_boundary<float><<<grid, 256, 0, c->stream>>>(reinterpret_cast<const float*>(c->mesh.p) + static_cast<size_t>(k) * total, c->bound_tmp.p, D, M, total);
+    else
+        k_interleave_boundary<double><<<grid, 256, 0, c->stream>>>(reinterpret_cast<const double*>(c->mesh.p) + static_cast<size_t>(k) * total, c->bound_tmp.p, D, M, total);
+    HRMGPU_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    HRMGPU_CUDA(c, cudaMemcpyAsync(xyz, c->bound_tmp.p, static_cast<size_t>(total) * 8, cudaMemcpyDeviceToHost, c->stream));
+    HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));
+    return HRMGPU_OK;
+}
+
 int hrmgpu_get_intervals(hrmgpu_ctx* c, int k, double* lo, double* up) {
     if (!c || !lo || !up) return HRMGPU_E_ARG;
     int rc = check_built(c, k);
@@ -630,8 +741,8 @@ int hrmgpu_get_intervals(hrmgpu_ctx* c, int k, double* lo, double* up) {
     HRMGPU_CUDA(c, cudaSetDevice(c->device));
     const size_t cnt = static_cast<size_t>(c->S) * c->L;
     std::vector<double> a(cnt), b(cnt);
-    HRMGPU_CUDA(c, cudaMemcpyAsync(a.data(), c->ivl_lo.p + static_cast<size_t>(k) * cnt, cnt * 8, cudaMemcpyDeviceToHost, c->stream));
-    HRMGPU_CUDA(c, cudaMemcpyAsync(b.data(), c->ivl_up.p + static_cast<size_t>(k) * cnt, cnt * 8, cudaMemcpyDeviceToHost, c->stream));
+    HRMGPU_CUDA(c, cudaMemcpyAsync(a.data(), c->ivl_lo[c->ivl_cur].p + static_cast<size_t>(k) * cnt, cnt * 8, cudaMemcpyDeviceToHost, c->stream));
+    HRMGPU_CUDA(c, cudaMemcpyAsync(b.data(), c->ivl_up[c->ivl_cur].p + static_cast<size_t>(k) * cnt, cnt * 8, cudaMemcpyDeviceToHost, c->stream));
     HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));
     for (int s = 0; s < c->S; ++s)
         for (int l = 0; l < c->L; ++l) {
@@ -641,24 +752,48 @@ int hrmgpu_get_intervals(hrmgpu_ctx* c, int k, double* lo, double* up) {
     return HRMGPU_OK;
 }
 
+// Host mirror of the CSR offsets (pinned), fetched the first time a getter needs it after a build.
+static int fetch_offsets(hrmgpu_ctx* c) {
+    int rc = finalize_segments(c);
+    if (rc) return rc;
+    if (c->h_off_valid) return HRMGPU_OK;
+    const size_t nl = static_cast<size_t>(c->K) * c->L;
+    if (c->h_off_cap < nl + 1) {
+        if (c->h_off) cudaFreeHost(c->h_off);
+        c->h_off = nullptr, c->h_off_cap = 0;
+        HRMGPU_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&c->h_off), (nl + 1) * sizeof(long long)));
+        c->h_off_cap = nl + 1;
+    }
+    if (nl == 0) {
+        c->h_off[0] = 0;
+    } else {
+        HRMGPU_CUDA(c, cudaMemcpyAsync(c->h_off, c->seg_off.p, sizeof(long long) * (nl + 1), cudaMemcpyDeviceToHost, c->s2));
+        HRMGPU_CUDA(c, cudaStreamSynchronize(c->s2));
+    }
+    c->h_off_valid = true;
+    return HRMGPU_OK;
+}
+
 int hrmgpu_get_segments(hrmgpu_ctx* c, int k, int* off, double* xL, double* xU, double* xM, int cap) {
     if (!c) return HRMGPU_E_ARG;
     int rc = check_built(c, k);
     if (rc) return rc;
     HRMGPU_CUDA(c, cudaSetDevice(c->device));
+    if ((rc = fetch_offsets(c))) return rc;
     const size_t l0 = static_cast<size_t>(k) * c->L;
-    const long long b0 = c->h_seg_off[l0], b1 = c->h_seg_off[l0 + c->L];
+    const long long b0 = c->h_off[l0], b1 = c->h_off[l0 + c->L];
     const long long cnt = b1 - b0;
     if (off)
-        for (int l = 0; l <= c->L; ++l) off[l] = static_cast<int>(c->h_seg_off[l0 + l] - b0);
+        for (int l = 0; l <= c->L; ++l) off[l] = static_cast<int>(c->h_off[l0 + l] - b0);
     if (xL) {
         if (!xU || !xM) return fail(c, HRMGPU_E_ARG, "get_segments: xU/xM are NULL");
         if (cap < cnt) return fail(c, HRMGPU_E_CAP, "get_segments: buffer too small");
         if (cnt) {
-            HRMGPU_CUDA(c, cudaMemcpyAsync(xL, c->segL.p + b0, cnt * 8, cudaMemcpyDeviceToHost, c->stream));
-            HRMGPU_CUDA(c, cudaMemcpyAsync(xU, c->segU.p + b0, cnt * 8, cudaMemcpyDeviceToHost, c->stream));
-            HRMGPU_CUDA(c, cudaMemcpyAsync(xM, c->segM.p + b0, cnt * 8, cudaMemcpyDeviceToHost, c->stream));
-            HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));
+            const double* d = c->segdata.p;
+            HRMGPU_CUDA(c, cudaMemcpyAsync(xL, d + b0, cnt * 8, cudaMemcpyDeviceToHost, c->s2));
+            HRMGPU_CUDA(c, cudaMemcpyAsync(xU, d + c->seg_cap + b0, cnt * 8, cudaMemcpyDeviceToHost, c->s2));
+            HRMGPU_CUDA(c, cudaMemcpyAsync(xM, d + 2 * c->seg_cap + b0, cnt * 8, cudaMemcpyDeviceToHost, c->s2));
+            HRMGPU_CUDA(c, cudaStreamSynchronize(c->s2));
         }
     }
     return static_cast<int>(cnt);
@@ -668,19 +803,67 @@ int hrmgpu_get_segments_all(hrmgpu_ctx* c, long long* off, double* xL, double* x
     if (!c) return HRMGPU_E_ARG;
     if (!c->built) return fail(c, HRMGPU_E_STATE, "no layers built yet");
     HRMGPU_CUDA(c, cudaSetDevice(c->device));
+    int rc = finalize_segments(c);
+    if (rc) return rc;
     const size_t nl = static_cast<size_t>(c->K) * c->L;
-    if (off) std::memcpy(off, c->h_seg_off.data(), sizeof(long long) * (nl + 1));
-    if (xL) {
-        if (!xU || !xM) return fail(c, HRMGPU_E_ARG, "get_segments_all: xU/xM are NULL");
-        if (cap < c->seg_total) return fail(c, HRMGPU_E_CAP, "get_segments_all: buffer too small");
-        if (c->seg_total) {
-            HRMGPU_CUDA(c, cudaMemcpyAsync(xL, c->segL.p, c->seg_total * 8, cudaMemcpyDeviceToHost, c->stream));
-            HRMGPU_CUDA(c, cudaMemcpyAsync(xU, c->segU.p, c->seg_total * 8, cudaMemcpyDeviceToHost, c->stream));
-            HRMGPU_CUDA(c, cudaMemcpyAsync(xM, c->segM.p, c->seg_total * 8, cudaMemcpyDeviceToHost, c->stream));
-        }
-        HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (xL && (!xU || !xM)) return fail(c, HRMGPU_E_ARG, "get_segments_all: xU/xM are NULL");
+    if (xL && cap < c->seg_total) return fail(c, HRMGPU_E_CAP, "get_segments_all: buffer too small");
+    // offsets straight into the caller's buffer (no staging), payload behind them on the same stream
+    if (off) {
+        if (nl == 0)
+            off[0] = 0;
+        else
+            HRMGPU_CUDA(c, cudaMemcpyAsync(off, c->seg_off.p, sizeof(long long) * (nl + 1), cudaMemcpyDeviceToHost, c->s2));
     }
+    if (xL && c->seg_total) {
+        const double* d = c->segdata.p;
+        HRMGPU_CUDA(c, cudaMemcpyAsync(xL, d, c->seg_total * 8, cudaMemcpyDeviceToHost, c->s2));
+        HRMGPU_CUDA(c, cudaMemcpyAsync(xU, d + c->seg_cap, c->seg_total * 8, cudaMemcpyDeviceToHost, c->s2));
+        HRMGPU_CUDA(c, cudaMemcpyAsync(xM, d + 2 * c->seg_cap, c->seg_total * 8, cudaMemcpyDeviceToHost, c->s2));
+    }
+    HRMGPU_CUDA(c, cudaStreamSynchronize(c->s2));
     return HRMGPU_OK;
+}
+
+// Pipelined read-back: the copies are queued on the side stream right behind the free-segment passes of the last build and the
+// call returns; the next hrmgpu_build_layers* may be issued at once (its fused kernel runs on the main stream meanwhile).
+long long hrmgpu_fetch_segments_async(hrmgpu_ctx* c, long long* off, double* xL, double* xU, double* xM, long long cap) {
+    if (!c) return HRMGPU_E_ARG;
+    if (!c->built) return fail(c, HRMGPU_E_STATE, "no layers built yet");
+    if (!off || cap < 0 || (cap > 0 && (!xL || !xU || !xM))) return fail(c, HRMGPU_E_ARG, "fetch_segments_async: bad arguments");
+    HRMGPU_CUDA(c, cudaSetDevice(c->device));
+    const size_t nl = static_cast<size_t>(c->K) * c->L;
+    c->fetch_cap = cap;
+    c->fetch_pending = true;
+    if (nl == 0) {
+        off[0] = 0;
+        return 0;
+    }
+    HRMGPU_CUDA(c, cudaMemcpyAsync(off, c->seg_off.p, sizeof(long long) * (nl + 1), cudaMemcpyDeviceToHost, c->s2));
+    const long long cnt = cap < c->seg_cap ? cap : c->seg_cap;
+    if (cnt > 0) {
+        const double* d = c->segdata.p;
+        HRMGPU_CUDA(c, cudaMemcpyAsync(xL, d, cnt * 8, cudaMemcpyDeviceToHost, c->s2));
+        HRMGPU_CUDA(c, cudaMemcpyAsync(xU, d + c->seg_cap, cnt * 8, cudaMemcpyDeviceToHost, c->s2));
+        HRMGPU_CUDA(c, cudaMemcpyAsync(xM, d + 2 * c->seg_cap, cnt * 8, cudaMemcpyDeviceToHost, c->s2));
+    }
+    // the sizes of THIS build in their own pinned slot (h_info[0..1] belongs to the build queued last)
+    HRMGPU_CUDA(c, cudaMemcpyAsync(c->h_info + 2, c->seg_info.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->s2));
+    HRMGPU_CUDA(c, cudaEventRecord(c->ev_fetch, c->s2));
+    return cnt;
+}
+
+long long hrmgpu_wait_segments(hrmgpu_ctx* c) {
+    if (!c) return HRMGPU_E_ARG;
+    if (!c->fetch_pending) return fail(c, HRMGPU_E_STATE, "wait_segments: no fetch in flight");
+    HRMGPU_CUDA(c, cudaSetDevice(c->device));
+    c->fetch_pending = false;
+    if (static_cast<size_t>(c->K) * c->L == 0) return 0;
+    HRMGPU_CUDA(c, cudaEventSynchronize(c->ev_fetch));
+    const long long need_orig = static_cast<long long>(c->h_info[2]), need_seg = static_cast<long long>(c->h_info[3]);
+    if (need_orig > c->orig_cap || need_seg > c->seg_cap || need_seg > c->fetch_cap)
+        return fail(c, HRMGPU_E_CAP, "wait_segments: capacity exceeded (read the build with hrmgpu_get_segments_all, which grows the buffers)");
+    return need_seg;
 }
 
 int hrmgpu_get_single_hit_count(hrmgpu_ctx* c, long long* out) {
@@ -696,19 +879,26 @@ int hrmgpu_get_single_hit_count(hrmgpu_ctx* c, long long* out) {
 long long hrmgpu_pack_segments_dev(hrmgpu_ctx* c, void* d_buf, long long cap_bytes) {
     if (!c) return HRMGPU_E_ARG;
     if (!c->built) return fail(c, HRMGPU_E_STATE, "no layers built yet");
+    if (int rc = finalize_segments(c)) return rc;
     const long long nl = static_cast<long long>(c->K) * c->L;
     const long long need = (nl + 1) * 8 + 3 * c->seg_total * 8;
     if (!d_buf) return need;
     if (cap_bytes < need) return fail(c, HRMGPU_E_CAP, "pack_segments_dev: buffer too small");
     HRMGPU_CUDA(c, cudaSetDevice(c->device));
     char* dst = static_cast<char*>(d_buf);
+    // on the context's MAIN stream (the one hrmgpu_set_stream installed), behind the free-segment passes
+    HRMGPU_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_k3[c->ivl_cur], 0));
     HRMGPU_CUDA(c, cudaMemcpyAsync(dst, c->seg_off.p, (nl + 1) * 8, cudaMemcpyDeviceToDevice, c->stream));
     dst += (nl + 1) * 8;
     if (c->seg_total) {
-        HRMGPU_CUDA(c, cudaMemcpyAsync(dst, c->segL.p, c->seg_total * 8, cudaMemcpyDeviceToDevice, c->stream));
-        HRMGPU_CUDA(c, cudaMemcpyAsync(dst + c->seg_total * 8, c->segU.p, c->seg_total * 8, cudaMemcpyDeviceToDevice, c->stream));
-        HRMGPU_CUDA(c, cudaMemcpyAsync(dst + 2 * c->seg_total * 8, c->segM.p, c->seg_total * 8, cudaMemcpyDeviceToDevice, c->stream));
+        const double* d = c->segdata.p;
+        HRMGPU_CUDA(c, cudaMemcpyAsync(dst, d, c->seg_total * 8, cudaMemcpyDeviceToDevice, c->stream));
+        HRMGPU_CUDA(c, cudaMemcpyAsync(dst + c->seg_total * 8, d + c->seg_cap, c->seg_total * 8, cudaMemcpyDeviceToDevice, c->stream));
+        HRMGPU_CUDA(c, cudaMemcpyAsync(dst + 2 * c->seg_total * 8, d + 2 * c->seg_cap, c->seg_total * 8, cudaMemcpyDeviceToDevice, c->stream));
     }
+    // Stream semantics (see hrmgpu.h): with the context's own stream the call returns when the buffer is complete; with a
+    // caller-installed stream the copies are ordered on THAT stream and the caller keeps using it.
+    if (c->stream == c->own_stream) HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));
     return need;
 }
 
@@ -731,13 +921,14 @@ long long hrmgpu_debug_phase_times(hrmgpu_ctx* c, int enable, long long n_cta, l
 }
 
 // Profiling aid: re-runs K1 alone (boundary points of the last 3D build's poses, no sweep, meshes overwritten in place)
-// and returns the kernel time in ms -- the ceiling of the fused kernel if the sweep were free.
+// and returns the kernel time in ms -- the ceiling of the fused kernel if the sweep were free.  The pose arrays of the last
+// build must still be alive (they are the caller's for hrmgpu_build_layers_dev).
 double hrmgpu_debug_k1_only_ms(hrmgpu_ctx* c) {
-    if (!c || !c->built || c->dim != 3) return -1.0;
+    if (!c || !c->built || c->dim != 3 || !c->last_semi || !c->last_R || !c->last_off) return -1.0;
     if (cudaSetDevice(c->device) != cudaSuccess) return -1.0;
     cudaEventRecord(c->ev0, c->stream);
-    if (launch_minksweep3d(c, c->K, c->B, 0, c->n_arena + c->n_obs, c->body_semi.p, c->body_R.p, c->body_off.p, c->prec, c->mesh.p, nullptr,
-                           nullptr, false))
+    if (launch_minksweep3d(c, c->K, c->B, 0, c->n_arena + c->n_obs, c->last_semi, c->last_R, c->last_off, c->prec, c->mesh.p, nullptr, nullptr,
+                           false))
         return -1.0;
     cudaEventRecord(c->ev1, c->stream);
     if (cudaEventSynchronize(c->ev1) != cudaSuccess) return -1.0;
@@ -750,6 +941,22 @@ long long hrmgpu_kernel_launches(hrmgpu_ctx* c, int reset) {
     if (!c) return HRMGPU_E_ARG;
     const long long v = c->launches;
     if (reset) c->launches = 0;
+    return v;
+}
+
+double hrmgpu_last_segments_ms(hrmgpu_ctx* c) {
+    if (!c || !c->built) return -1.0;
+    if (cudaSetDevice(c->device) != cudaSuccess) return -1.0;
+    if (cudaEventSynchronize(c->ev3) != cudaSuccess) return -1.0;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c->ev2, c->ev3) != cudaSuccess) return -1.0;
+    return static_cast<double>(ms);
+}
+
+long long hrmgpu_segment_redos(hrmgpu_ctx* c, int reset) {
+    if (!c) return HRMGPU_E_ARG;
+    const long long v = c->seg_redos;
+    if (reset) c->seg_redos = 0;
     return v;
 }
 

@@ -46,7 +46,13 @@ struct Ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaMemPool_t pool = nullptr;  // the library's private pool of this device (see ensure())
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // around the fused kernel of the last build (main stream)
+    // Side stream of the free-segment passes (K3) and of the exchange: the passes of build i run behind `ev_fused` while the main
+    // stream already runs the fused kernel of build i+1 into the other interval-table buffer.
+    cudaStream_t s2 = nullptr;
+    cudaEvent_t ev_fused = nullptr, ev2 = nullptr, ev3 = nullptr;  // fused kernel done; around the K3 passes (side stream)
+    cudaEvent_t ev_k3[2] = {nullptr, nullptr};                     // K3 passes that read interval buffer [i] are done
     std::string err;
     long long launches = 0;
 
@@ -66,26 +72,48 @@ struct Ctx {
     int K = 0, B = 0, S = 0, Sa = 0, L = 0, M = 0, prec = 0;
     bool built = false;
     DevBuf<double> body_semi, body_R, body_off;  // staged copies of host inputs
+    const double *last_semi = nullptr, *last_R = nullptr, *last_off = nullptr;  // device pose arrays of the last 3D build
     DevBuf<double> q_a, q_b;                     // staged query inputs (edge end points, body centres)
     DevBuf<unsigned char> q_out;                 // staged query results
     DevBuf<double> bbox;                         // [meshes][6] min/max per axis of the queried meshes
     DevBuf<unsigned int> q_flag;                 // per-query blocked flags
     DevBuf<int> q_set;                           // multi-layer queries: layer / pair index of every query
     DevBuf<char> mesh;                           // [K][S][dim][M] planar, double (or float in F32 mode)
-    DevBuf<double> ivl_lo, ivl_up;               // [K][S][L]
+    DevBuf<double> ivl_lo[2], ivl_up[2];         // [K][S][L], double-buffered (see s2)
+    int ivl_cur = 0;                             // buffer of the last build
     int num_sms = 148;                           // multiprocessors of the device
     int seg_fast_cap = 0;                        // test hook: list capacity of the 4-line segment pass (0 = default 128)
+    long long seg_init_cap = 0;                  // test hook: first capacity of the segment pool / payload (forces the grow-and-repeat path)
     bool force_seg_fallback = false;             // test hook: always use the one-line-per-warp pass
     int cell_seg_cap = 0;                        // test hook: kept-cell list capacity per warp of the fused kernel (0 = default)
-    DevBuf<double> orig;                         // [K][L][So+1][2] original (pre-enhancement) segments
+    DevBuf<double> orig;                         // pool of original (pre-enhancement) segments [orig_cap][2]
+    DevBuf<long long> orig_off;                  // [K][L] first pool entry of a line
     DevBuf<int> orig_cnt;                        // [K][L]
     DevBuf<int> seg_cnt;                         // [K][L]
     DevBuf<long long> seg_off;                   // [K*L+1]
-    DevBuf<double> segL, segU, segM;             // [total]
+    DevBuf<double> segdata;                      // xL[seg_cap] xU[seg_cap] xM[seg_cap]
+    DevBuf<unsigned long long> seg_info;         // [0] pool entries needed, [1] total segments
+    long long orig_cap = 0, seg_cap = 0;         // capacities (entries) of orig / of each array in segdata
+    long long orig_hint = 0, seg_hint = 0;       // what earlier builds needed (x1.5): first guess of the next build
+    unsigned long long* h_info = nullptr;        // pinned host copy of seg_info
+    long long* h_off = nullptr;                  // pinned host mirror of seg_off, fetched on demand
+    size_t h_off_cap = 0;
+    bool h_off_valid = false;
+    bool seg_pending = false;                    // passes queued, sizes not yet checked by finalize_segments()
+    long long seg_redos = 0;                     // passes repeated because a capacity was too small
+    cudaEvent_t ev_join = nullptr;               // side-stream marker (hrmgpu_join, exchange on a caller's stream)
+    cudaEvent_t ev_fetch = nullptr;              // end of the copies of hrmgpu_fetch_segments_async
+    long long fetch_cap = 0;                     // capacity of the host arrays of the fetch in flight
+    bool fetch_pending = false;
+    DevBuf<char> xchg_send, xchg_recv;           // multi-GPU exchange (hrmgpu_allgather_layers): packed send / receive buffers
+    DevBuf<double> bound_tmp;                    // hrmgpu_get_boundary_layer: transposed copy of one layer
+    void* comm = nullptr;                        // ncclComm_t created by hrmgpu_comm_init (exchange.cu)
+    int xchg_world = 0, xchg_rank = 0;           // last exchange
+    long long xchg_line_cap = 0, xchg_seg_cap = 0;
+    void* xchg_stream = nullptr;
     DevBuf<unsigned long long> counters;         // [0] single-hit count, [1] capacity overflow flag
     DevBuf<long long> dbg;                       // optional per-CTA phase timings (hrmgpu_debug_phase_times)
-    long long seg_total = 0;
-    std::vector<long long> h_seg_off;            // host mirror of seg_off (filled on build)
+    long long seg_total = 0;                     // valid after finalize_segments()
 
     // bridge layers
     int P = 0, bridge_B = 0, bridge_prec = 0;
@@ -96,6 +124,10 @@ struct Ctx {
     DevBuf<double> q_w, q_loff, q_loff2;         // transition tests: interpolation weights [2][T], link offsets [P][T][B][dim] (+ chain offsets)
 };
 
+}  // namespace hrmgpu
+struct hrmgpu_ctx : public hrmgpu::Ctx {};
+namespace hrmgpu {
+
 #define HRMGPU_CUDA(ctx, expr)                                                                        \
     do {                                                                                              \
         cudaError_t _e = (expr);                                                                      \
@@ -105,10 +137,13 @@ struct Ctx {
         }                                                                                             \
     } while (0)
 
-// Device buffers come from the device's default stream-ordered memory pool (cudaMallocAsync on the context's stream): a planner
-// object creates a context, grows ~30 buffers and destroys it again, and with plain cudaMalloc / cudaFree some of those calls take
-// tens of milliseconds (measured: sporadic 20-60 ms inside K4 / K5a / buildLayers of HRM3D::plan()).  hrmgpu_create raises the
-// pool's release threshold so that freed blocks are reused by the next context instead of going back to the driver.
+// Device buffers come from a stream-ordered memory pool PRIVATE to this library (one per device, created by the first
+// hrmgpu_create on that device, cudaMallocFromPoolAsync on the context's stream): a planner object creates a context, grows
+// ~30 buffers and destroys it again, and with plain cudaMalloc / cudaFree some of those calls take tens of milliseconds
+// (measured: sporadic 20-60 ms inside K4 / K5a / buildLayers of HRM3D::plan()).  The pool keeps freed blocks (release
+// threshold raised) so the next context reuses them; hrmgpu_destroy trims it to kPoolKeepBytes of free blocks.  The device's
+// DEFAULT pool -- shared with every other cudaMallocAsync user of the process, e.g. PyTorch -- is never touched.
+cudaMemPool_t library_pool(int device);  // ctx.cu; nullptr if the pool could not be created
 template <class T>
 inline int ensure(Ctx* c, DevBuf<T>& b, size_t n) {
     if (b.n >= n && b.p) return HRMGPU_OK;
@@ -118,9 +153,18 @@ inline int ensure(Ctx* c, DevBuf<T>& b, size_t n) {
         b.n = 0;
     }
     if (n == 0) n = 1;
-    HRMGPU_CUDA(c, cudaMallocAsync(reinterpret_cast<void**>(&b.p), n * sizeof(T), c->stream));
+    HRMGPU_CUDA(c, cudaMallocFromPoolAsync(reinterpret_cast<void**>(&b.p), n * sizeof(T), c->pool, c->stream));
     b.n = n;
     return HRMGPU_OK;
+}
+
+template <class T>
+inline int ensure_on(Ctx* c, cudaStream_t st, DevBuf<T>& b, size_t n) {  // ensure() ordered on another stream of the context
+    cudaStream_t keep = c->stream;
+    c->stream = st;
+    const int rc = ensure(c, b, n);
+    c->stream = keep;
+    return rc;
 }
 
 inline int fail(Ctx* c, int code, const std::string& msg) {
@@ -128,12 +172,21 @@ inline int fail(Ctx* c, int code, const std::string& msg) {
     return code;
 }
 
+// Loads every kernel of a translation unit (cudaFuncGetAttributes) so that CUDA's lazy module loading does not spread
+// 15-90 ms stalls over the first planner calls; called once per process by the first hrmgpu_create.
+void preload_mink3d();
+void preload_mink2d();
+void preload_segments();
+void preload_queries();
+void preload_exchange();
+
 // kernels / launchers implemented in the other translation units
 int launch_minksweep3d(Ctx* c, int K, int B, int n_first_obj, int n_objs, const double* d_semi, const double* d_R,
                        const double* d_off, int precision, char* d_mesh, double* d_lo, double* d_up, bool do_sweep, bool reload = false);
 int launch_minksweep2d(Ctx* c, int K, int B, int n_first_obj, int n_objs, const double* d_semi, const double* d_angle,
                        const double* d_off, int precision, char* d_mesh, double* d_lo, double* d_up, bool do_sweep, bool reload = false);
 int launch_segments(Ctx* c);
+int finalize_segments(Ctx* c);
 int launch_edges(Ctx* c, int k, int E, const double* d_v1, const double* d_v2, unsigned char* d_out, const int* d_layer = nullptr);
 int launch_bridge_test(Ctx* c, int p, int Q, const double* d_centres, unsigned char* d_out, const int* d_pair = nullptr);
 int launch_bridge_bbox(Ctx* c);

@@ -185,4 +185,15 @@ int launch_minksweep2d(Ctx* c, int K, int B, int n_first_obj, int n_objs, const 
     return HRMGPU_OK;
 }
 
+// Loads this file's kernels up front (see preload_* in internal.cuh).
+template <class K>
+static void touch_kernel(K k) {
+    cudaFuncAttributes a;
+    if (cudaFuncGetAttributes(&a, k) != cudaSuccess) cudaGetLastError();
+}
+void preload_mink2d() {
+    touch_kernel(k_minksweep2d<Strict, true>), touch_kernel(k_minksweep2d<Strict, false>);
+    touch_kernel(k_minksweep2d<Fast, true>), touch_kernel(k_minksweep2d<Fast, false>);
+}
+
 }  // namespace hrmgpu

@@ -115,12 +115,15 @@ __device__ __forceinline__ void sts_codes(uint32_t addr, uint32_t c0, uint32_t c
 }
 // Fixed-point line index of the paired fast path.  t = fma(x, inv_d, bias_q) with bias_q = bias + 1.5 * 2^36 + (1 - 2^-16):
 // the low word of t is w = rint(g * 2^16) + 0xFFFF (two's complement, g in line units), so its upper half is ceil(g);
-// that holds while the high word of t is 0x42380000 (g >= 0) or 0x4237FFFF (g < 0), i.e. |g| < 2^15.  ok = false when g
-// is within 4 * 2^-16 of a grid line (the computed w is off by at most one unit) or out of range: exact search instead.
+// that holds while the high word of t is 0x42380000 with w's sign bit clear (0 <= g < 2^15) or 0x4237FFFF with it set
+// (-2^15 <= g < 0): the signed 16-bit SIMD clamp that follows needs |g| < 2^15, not just the two high words (which alone
+// would admit |g| < 2^16).  ok = false when g is within 4 * 2^-16 of a grid line (the computed w is off by at most one
+// unit) or out of range: exact search instead.
 __device__ __forceinline__ uint32_t line_q(double x, double inv_d, double bias_q, bool& ok) {
     const double t = fma(x, inv_d, bias_q);
     const uint32_t w = static_cast<uint32_t>(__double2loint(t));
-    ok = (((w + 5u) & 0xFFF8u) != 0u) && (static_cast<uint32_t>(__double2hiint(t)) - 0x4237FFFFu < 2u);
+    const uint32_t hi = static_cast<uint32_t>(__double2hiint(t)) - 0x4237FFFFu;  // 1: g >= 0, 0: g < 0, else out of range
+    ok = (((w + 5u) & 0xFFF8u) != 0u) && (hi < 2u) && ((hi ^ (w >> 31)) == 1u);
     return w;
 }
 
@@ -952,5 +955,17 @@ int launch_minksweep3d(Ctx* c, int K, int B, int n_first_obj, int n_objs, const 
     }
 #undef HRMGPU_LAUNCH3D
 }
+
+// Loads this file's kernels up front (see preload_* in internal.cuh).
+template <class K>
+static void touch_kernel(K k) {
+    cudaFuncAttributes a;
+    if (cudaFuncGetAttributes(&a, k) != cudaSuccess) cudaGetLastError();
+}
+template <int MODE>
+static void touch_mode() {
+    touch_kernel(k_minksweep3d<MODE, false, false>), touch_kernel(k_minksweep3d<MODE, true, true>), touch_kernel(k_minksweep3d<MODE, true, false>);
+}
+void preload_mink3d() { touch_mode<HRMGPU_F64_STRICT>(), touch_mode<HRMGPU_F64>(), touch_mode<HRMGPU_F32>(); }
 
 }  // namespace hrmgpu

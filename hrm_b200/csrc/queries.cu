@@ -563,4 +563,20 @@ int launch_transitions(Ctx* c, int C, int T, const int* d_pair, const double* d_
     return finish_flags(c, C, d_out);
 }
 
+// Loads this file's kernels up front (see preload_* in internal.cuh).
+template <class K>
+static void touch_kernel(K k) {
+    cudaFuncAttributes a;
+    if (cudaFuncGetAttributes(&a, k) != cudaSuccess) cudaGetLastError();
+}
+void preload_queries() {
+    touch_kernel(k_flags_to_free), touch_kernel(k_mesh_bbox<float>), touch_kernel(k_mesh_bbox<double>);
+    touch_kernel(k_edges3d<Strict, double>), touch_kernel(k_edges3d<Fast, double>), touch_kernel(k_edges3d<Fast, float>);
+    touch_kernel(k_edges2d<Strict>), touch_kernel(k_edges2d<Fast>);
+    touch_kernel(k_bridge3d<Strict, double>), touch_kernel(k_bridge3d<Fast, double>), touch_kernel(k_bridge3d<Fast, float>);
+    touch_kernel(k_bridge2d<Strict>), touch_kernel(k_bridge2d<Fast>);
+    touch_kernel(k_transitions3d<Strict, double>), touch_kernel(k_transitions3d<Fast, double>), touch_kernel(k_transitions3d<Fast, float>);
+    touch_kernel(k_transitions2d<Strict>), touch_kernel(k_transitions2d<Fast>);
+}
+
 }  // namespace hrmgpu

@@ -6,13 +6,19 @@
 //   FreeSpaceComputator::computeFreeSegment            FreeSpace-inl.h:63-97
 //   FreeSpaceComputator::enhanceFreeSegment            FreeSpace-inl.h:132-174
 //
-// One WARP per sweep line.  Pass 1 (k_line_segments): compact the non-NaN C-obstacle intervals of the
-// line into shared memory, sort by start with an arbitrary-n bitonic network, prefix-max the ends with
-// shuffles, and emit the gaps clipped to the arena interval ("original" segments).  Pass 2
-// (k_enhance_count) counts the degenerate segments enhanceFreeSegment appends from the two adjacent
-// lines of the same x-plane; a scan turns the counts into CSR offsets; pass 3 (k_enhance_fill) writes
-// originals + appended values in the reference's (j1, j2) loop order and sorts xL, xU, xM of every line
-// but the last one of a plane independently, exactly like the reference.
+// One WARP per sweep line.  Pass 1 (k_line_segments / k_line_segments4): compact the non-NaN C-obstacle intervals of the
+// line into shared memory, sort by start, prefix-max the ends with shuffles, and emit the gaps clipped to the arena
+// interval ("original" segments) into a compact pool (a line allocates exactly its count with one atomicAdd).  Pass 2
+// (k_enhance<false>) counts the degenerate segments enhanceFreeSegment appends from the two adjacent lines of the same
+// x-plane; a scan turns the counts into CSR offsets; pass 3 (k_enhance<true>) writes originals + appended values in the
+// reference's (j1, j2) loop order and sorts xL, xU, xM of every line but the last one of a plane independently, exactly
+// like the reference.
+//
+// Nothing here synchronises with the host.  The pool and the payload have CAPACITIES (grown from the sizes of earlier
+// builds); a pass that would overrun one writes nothing and only reports the size it needs (info[0] = pool entries,
+// info[1] = segments), and finalize_segments() -- called by the first getter that needs the results -- grows the buffer
+// and repeats the passes.  All passes run on the context's side stream `s2`, behind the event the fused kernel records, so
+// that the free segments of build i are formed while the fused kernel of build i+1 runs (interval tables double-buffered).
 #include "internal.cuh"
 
 #include <algorithm>
@@ -26,14 +32,17 @@ constexpr int kSeg4Warps = 7;  // 4-line pass: 7 warps x 8 KB of lists (128 inte
 struct SegParams {
     const double* lo;   // [K][S][L]
     const double* up;
-    double* orig;       // [K][L][cap][2]
+    double* orig;       // pool of original segments [orig_cap][2]
+    long long* orig_off;  // [K][L] first pool entry of the line
     int* orig_cnt;      // [K][L]
     int* seg_cnt;       // [K][L]
     const long long* seg_off;  // [K*L+1]
     double* segL;
     double* segU;
     double* segM;
-    int K, S, Sa, L, Lx, Ly, cap;  // cap = So + 1 original segments per line at most
+    unsigned long long* info;  // [0] pool entries needed (allocation cursor), [1] total segments (written by the scan)
+    long long orig_cap, seg_cap;  // capacities of the pool / of segL, segU, segM (entries)
+    int K, S, Sa, L, Lx, Ly;
     int warps;                     // warps per CTA in pass 1
     int sort_cap;                  // intervals per warp in shared memory
     int only_flagged;              // pass 1 fallback: process only the lines k_line_segments4 marked with orig_cnt = -1
@@ -117,19 +126,20 @@ __device__ __forceinline__ void warp_sort_pairs(double* ks, double* ke, int m, i
 }
 
 // Original free segments of one line from its m compacted C-obstacle intervals (ks = starts, ke = ends, in shared
-// memory) and its arena interval [as, ae]: sort by start, gaps of the union clipped to the arena, count to orig_cnt.
+// memory) and its arena interval [as, ae]: sort by start, gaps of the union clipped to the arena.  The gaps are counted
+// first, the line then takes exactly that many entries of the pool (one atomicAdd) and writes them; with at most 32
+// candidates (the common case) the values stay in registers between the two steps.  A line that does not fit into the
+// pool writes nothing: the cursor keeps counting, and the host repeats the pass with a pool of that size.
 __device__ __forceinline__ void emit_line(const SegParams& p, long long gl, double* ks, double* ke, int m, double as, double ae,
                                           bool arena_ok, int lane) {
-    double* out = p.orig + (static_cast<size_t>(gl) * p.cap) * 2;
     int cnt = 0;
-    if (!arena_ok) {
-        cnt = 0;  // complements(): empty outer -> nothing
-    } else if (m == 0) {
-        if (lane == 0) out[0] = as, out[1] = ae;  // complements(): empty inner -> outer
-        cnt = 1;
-    } else {
-        warp_sort_pairs(ks, ke, m, lane);
-        // gaps of the union: before interval i iff (running max of earlier ends) < start_i   (Interval.cpp:21-29)
+    const bool trivial = !arena_ok || m == 0;  // complements(): empty outer -> nothing; empty inner -> outer
+    if (!trivial) warp_sort_pairs(ks, ke, m, lane);
+    // gaps of the union: before interval i iff (running max of earlier ends) < start_i   (Interval.cpp:21-29)
+    double gs = 0, ge = 0;
+    bool keep = false;
+    auto sweep = [&](double* out) -> int {  // out == nullptr: count only
+        int c = 0;
         double carry = -DBL_MAX;  // running max of ends of intervals [0, base)
         for (int base = 0; base < m + 1; base += 32) {
             const int i = base + lane;
@@ -142,8 +152,7 @@ __device__ __forceinline__ void emit_line(const SegParams& p, long long gl, doub
             }
             double excl = __shfl_up_sync(0xFFFFFFFFu, inc, 1);
             excl = (lane == 0) ? carry : fmax(carry, excl);  // max of ends of intervals [0, i)
-            bool keep = false;
-            double gs = 0, ge = 0;
+            keep = false;
             if (i <= m) {
                 const bool is_gap = (i == 0) || (i == m) || (excl < ks[i]);
                 if (is_gap) {
@@ -155,16 +164,45 @@ __device__ __forceinline__ void emit_line(const SegParams& p, long long gl, doub
                 }
             }
             const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
-            if (keep) {
-                const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
+            if (out && keep) {
+                const int pos = c + __popc(bal & ((1u << lane) - 1u));
                 out[2 * pos] = gs;
                 out[2 * pos + 1] = ge;
             }
-            cnt += __popc(bal);
+            c += __popc(bal);
             carry = fmax(carry, __shfl_sync(0xFFFFFFFFu, inc, 31));
         }
+        return c;
+    };
+    if (!arena_ok)
+        cnt = 0;
+    else if (m == 0)
+        cnt = 1;
+    else
+        cnt = sweep(nullptr);
+    long long base = 0;
+    if (lane == 0 && cnt > 0) base = static_cast<long long>(atomicAdd(p.info, static_cast<unsigned long long>(cnt)));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    const bool fits = base + cnt <= p.orig_cap;
+    if (fits && cnt > 0) {
+        double* out = p.orig + 2 * base;
+        if (trivial) {
+            if (lane == 0) out[0] = as, out[1] = ae;
+        } else if (m + 1 <= 32) {  // single chunk: keep / gs / ge of the counting sweep are still in registers
+            const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
+            if (keep) {
+                const int pos = __popc(bal & ((1u << lane) - 1u));
+                out[2 * pos] = gs;
+                out[2 * pos + 1] = ge;
+            }
+        } else {
+            sweep(out);
+        }
     }
-    if (lane == 0) p.orig_cnt[gl] = cnt;
+    if (lane == 0) {
+        p.orig_off[gl] = base;
+        p.orig_cnt[gl] = fits ? cnt : 0;
+    }
 }
 
 // Pass 1: original free segments of every line.  grid = ceil(K*L / warps) CTAs of `warps` warps.
@@ -353,8 +391,9 @@ __global__ void __launch_bounds__(kSegWarps * 32) k_enhance(const SegParams p) {
     if (gl >= static_cast<long long>(p.K) * p.L) return;
     const int l = static_cast<int>(gl % p.L);
     const int iy = l % p.Ly;
+    if (FILL && static_cast<long long>(p.info[1]) > p.seg_cap) return;  // payload too small: the host grows it and repeats this pass
     const int n0 = p.orig_cnt[gl];
-    const double* s0 = p.orig + static_cast<size_t>(gl) * p.cap * 2;
+    const double* s0 = p.orig + 2 * p.orig_off[gl];
     int cnt = n0;
     long long base_off = 0;
     double *oL = nullptr, *oU = nullptr, *oM = nullptr;
@@ -373,7 +412,7 @@ __global__ void __launch_bounds__(kSegWarps * 32) k_enhance(const SegParams p) {
     // (a) this line in the role "i+1" of the pair (iy-1, iy): reference processes that pair first
     if (iy > 0) {
         const int np = p.orig_cnt[gl - 1];
-        const double* sp = p.orig + static_cast<size_t>(gl - 1) * p.cap * 2;
+        const double* sp = p.orig + 2 * p.orig_off[gl - 1];
         const long long tot = static_cast<long long>(np) * n0;  // (j1 over previous line) x (j2 over this line)
         for (long long b0 = 0; b0 < tot; b0 += 32) {
             const long long q = b0 + lane;
@@ -399,7 +438,7 @@ __global__ void __launch_bounds__(kSegWarps * 32) k_enhance(const SegParams p) {
     // (b) this line in the role "i" of the pair (iy, iy+1)
     if (iy < p.Ly - 1) {
         const int nn = p.orig_cnt[gl + 1];
-        const double* sn = p.orig + static_cast<size_t>(gl + 1) * p.cap * 2;
+        const double* sn = p.orig + 2 * p.orig_off[gl + 1];
         const long long tot = static_cast<long long>(n0) * nn;
         for (long long b0 = 0; b0 < tot; b0 += 32) {
             const long long q = b0 + lane;
@@ -436,7 +475,7 @@ __global__ void __launch_bounds__(kSegWarps * 32) k_enhance(const SegParams p) {
 }
 
 // Exclusive scan of K*L counts into 64-bit CSR offsets; single CTA (K*L is at most a few 10^5..10^6).
-__global__ void __launch_bounds__(1024) k_scan_counts(const int* cnt, long long* off, long long n) {
+__global__ void __launch_bounds__(1024) k_scan_counts(const int* cnt, long long* off, long long n, unsigned long long* info) {
     __shared__ long long wsum[32];
     __shared__ long long carry_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -469,13 +508,18 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const int* cnt, long long*
         if (tid == 1023) carry_s = prefix + v;
         __syncthreads();
     }
-    if (tid == 0) off[n] = carry_s;
+    if (tid == 0) {
+        off[n] = carry_s;
+        info[1] = static_cast<unsigned long long>(carry_s);
+    }
 }
 
-int launch_segments(Ctx* c) {
+// Enqueues pass 1 .. 3 on the side stream (no host synchronisation).  `from_pass`: 1 = everything, 3 = the fill pass only
+// (after the payload was grown).
+static int enqueue_passes(Ctx* c, int from_pass) {
     SegParams p;
-    p.lo = c->ivl_lo.p;
-    p.up = c->ivl_up.p;
+    p.lo = c->ivl_lo[c->ivl_cur].p;
+    p.up = c->ivl_up[c->ivl_cur].p;
     p.K = c->K;
     p.S = c->S;
     p.Sa = c->Sa;
@@ -483,77 +527,145 @@ int launch_segments(Ctx* c) {
     p.Lx = (c->dim == 3) ? c->Lx : 1;
     p.Ly = c->Ly;
     const int So = c->S - c->Sa;
-    p.cap = So + 1;
     const long long nl = static_cast<long long>(c->K) * c->L;
-    if (nl == 0) {
-        c->seg_total = 0;
-        c->h_seg_off.assign(1, 0);
-        return HRMGPU_OK;
-    }
-    int rc;
-    if ((rc = ensure(c, c->orig, static_cast<size_t>(nl) * p.cap * 2))) return rc;
-    if ((rc = ensure(c, c->orig_cnt, static_cast<size_t>(nl)))) return rc;
-    if ((rc = ensure(c, c->seg_cnt, static_cast<size_t>(nl)))) return rc;
-    if ((rc = ensure(c, c->seg_off, static_cast<size_t>(nl) + 1))) return rc;
     p.orig = c->orig.p;
+    p.orig_off = c->orig_off.p;
     p.orig_cnt = c->orig_cnt.p;
     p.seg_cnt = c->seg_cnt.p;
     p.seg_off = c->seg_off.p;
-    p.segL = p.segU = p.segM = nullptr;
-
-    // pass 1: shared memory holds `warps` x sort_cap (start,end) pairs
-    p.sort_cap = So > 0 ? So : 1;
-    const size_t per_warp = static_cast<size_t>(p.sort_cap) * 16;
-    int warps = static_cast<int>((200 * 1024) / per_warp);
-    if (warps < 1) return fail(c, HRMGPU_E_CAP, "more than 12800 C-obstacle surfaces per layer are not supported");
-    if (warps > kSegWarps) warps = kSegWarps;
-    p.warps = warps;
-    const size_t smem = per_warp * warps;
-    HRMGPU_CUDA(c, cudaFuncSetAttribute(k_line_segments, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    const long long g1 = (nl + warps - 1) / warps;
-    p.only_flagged = 0;
-    if (c->L % 4 == 0 && !c->force_seg_fallback) {
-        // fast path: a warp per 4 lines with short lists, then the full-size kernel on a small grid for flagged lines
-        const int cap4 = std::min(p.sort_cap, c->seg_fast_cap > 0 ? c->seg_fast_cap : 128);
-        const size_t smem4 = static_cast<size_t>(kSeg4Warps) * 8 * cap4 * sizeof(double);
-        HRMGPU_CUDA(c, cudaFuncSetAttribute(k_line_segments4, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem4)));
-        const long long groups = nl / 4;
-        k_line_segments4<<<static_cast<unsigned>((groups + kSeg4Warps - 1) / kSeg4Warps), kSeg4Warps * 32, smem4, c->stream>>>(p, cap4);
-        HRMGPU_CUDA(c, cudaGetLastError());
-        c->launches += 1;
-        if (cap4 < p.sort_cap) {
-            p.only_flagged = 1;
-            k_line_segments<<<static_cast<unsigned>(std::min<long long>(g1, 148)), warps * 32, smem, c->stream>>>(p);
+    p.segL = c->segdata.p;
+    p.segU = c->segdata.p + c->seg_cap;
+    p.segM = c->segdata.p + 2 * c->seg_cap;
+    p.info = c->seg_info.p;
+    p.orig_cap = c->orig_cap;
+    p.seg_cap = c->seg_cap;
+    cudaStream_t st = c->s2;
+    const long long g2 = (nl + kSegWarps - 1) / kSegWarps;
+    if (from_pass <= 1) {
+        HRMGPU_CUDA(c, cudaMemsetAsync(c->seg_info.p, 0, 2 * sizeof(unsigned long long), st));
+        // pass 1: shared memory holds `warps` x sort_cap (start,end) pairs
+        p.sort_cap = So > 0 ? So : 1;
+        const size_t per_warp = static_cast<size_t>(p.sort_cap) * 16;
+        int warps = static_cast<int>((200 * 1024) / per_warp);
+        if (warps < 1) return fail(c, HRMGPU_E_CAP, "more than 12800 C-obstacle surfaces per layer are not supported");
+        if (warps > kSegWarps) warps = kSegWarps;
+        p.warps = warps;
+        const size_t smem = per_warp * warps;
+        HRMGPU_CUDA(c, cudaFuncSetAttribute(k_line_segments, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        const long long g1 = (nl + warps - 1) / warps;
+        p.only_flagged = 0;
+        if (c->L % 4 == 0 && !c->force_seg_fallback) {
+            // fast path: a warp per 4 lines with short lists, then the full-size kernel on a small grid for flagged lines
+            const int cap4 = std::min(p.sort_cap, c->seg_fast_cap > 0 ? c->seg_fast_cap : 128);
+            const size_t smem4 = static_cast<size_t>(kSeg4Warps) * 8 * cap4 * sizeof(double);
+            HRMGPU_CUDA(c, cudaFuncSetAttribute(k_line_segments4, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem4)));
+            const long long groups = nl / 4;
+            k_line_segments4<<<static_cast<unsigned>((groups + kSeg4Warps - 1) / kSeg4Warps), kSeg4Warps * 32, smem4, st>>>(p, cap4);
+            HRMGPU_CUDA(c, cudaGetLastError());
+            c->launches += 1;
+            if (cap4 < p.sort_cap) {
+                p.only_flagged = 1;
+                k_line_segments<<<static_cast<unsigned>(std::min<long long>(g1, c->num_sms)), warps * 32, smem, st>>>(p);
+                HRMGPU_CUDA(c, cudaGetLastError());
+                c->launches += 1;
+            }
+        } else {
+            k_line_segments<<<static_cast<unsigned>(g1), warps * 32, smem, st>>>(p);
             HRMGPU_CUDA(c, cudaGetLastError());
             c->launches += 1;
         }
-        c->launches -= 1;  // (the common tail below counts one pass-1 launch)
-    } else {
-        k_line_segments<<<static_cast<unsigned>(g1), warps * 32, smem, c->stream>>>(p);
+        k_enhance<false><<<static_cast<unsigned>(g2), kSegWarps * 32, 0, st>>>(p);
         HRMGPU_CUDA(c, cudaGetLastError());
+        k_scan_counts<<<1, 1024, 0, st>>>(c->seg_cnt.p, c->seg_off.p, nl, c->seg_info.p);
+        HRMGPU_CUDA(c, cudaGetLastError());
+        c->launches += 2;
     }
-    const long long g2 = (nl + kSegWarps - 1) / kSegWarps;
-    k_enhance<false><<<static_cast<unsigned>(g2), kSegWarps * 32, 0, c->stream>>>(p);
-    HRMGPU_CUDA(c, cudaGetLastError());
-    k_scan_counts<<<1, 1024, 0, c->stream>>>(c->seg_cnt.p, c->seg_off.p, nl);
-    HRMGPU_CUDA(c, cudaGetLastError());
-    c->launches += 3;
-    // the payload size is data dependent: read the offsets back (they are an API output anyway)
-    c->h_seg_off.resize(static_cast<size_t>(nl) + 1);
-    HRMGPU_CUDA(c, cudaMemcpyAsync(c->h_seg_off.data(), c->seg_off.p, sizeof(long long) * (nl + 1), cudaMemcpyDeviceToHost, c->stream));
-    HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));
-    c->seg_total = c->h_seg_off[static_cast<size_t>(nl)];
-    const size_t tot = static_cast<size_t>(c->seg_total);
-    if ((rc = ensure(c, c->segL, tot))) return rc;
-    if ((rc = ensure(c, c->segU, tot))) return rc;
-    if ((rc = ensure(c, c->segM, tot))) return rc;
-    p.segL = c->segL.p;
-    p.segU = c->segU.p;
-    p.segM = c->segM.p;
-    k_enhance<true><<<static_cast<unsigned>(g2), kSegWarps * 32, 0, c->stream>>>(p);
+    k_enhance<true><<<static_cast<unsigned>(g2), kSegWarps * 32, 0, st>>>(p);
     HRMGPU_CUDA(c, cudaGetLastError());
     c->launches += 1;
+    // the two sizes the host needs (16 bytes, pinned): read when a getter finalises the build
+    HRMGPU_CUDA(c, cudaMemcpyAsync(c->h_info, c->seg_info.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     return HRMGPU_OK;
+}
+
+// Queues the free-segment passes of the build whose fused kernel was just enqueued on the main stream.
+int launch_segments(Ctx* c) {
+    const long long nl = static_cast<long long>(c->K) * c->L;
+    c->seg_pending = false;
+    c->h_off_valid = false;
+    c->seg_total = 0;
+    if (nl == 0) return HRMGPU_OK;
+    int rc;
+    cudaStream_t st = c->s2;
+    // capacities: what the previous builds needed (x1.5), at least a few entries per line; a pass that overruns them reports
+    // the size it needs and finalize_segments() repeats it
+    long long want_orig = std::max<long long>(std::max(c->orig_cap, c->orig_hint), std::max<long long>(nl * 4, 4096));
+    long long want_seg = std::max<long long>(std::max(c->seg_cap, c->seg_hint), std::max<long long>(nl * 6, 4096));
+    if (c->seg_init_cap > 0) want_orig = std::max(c->orig_cap, c->seg_init_cap), want_seg = std::max(c->seg_cap, c->seg_init_cap);  // test hook
+    // the side stream owns these buffers: (re)allocations are ordered on it
+    if ((rc = ensure_on(c, st, c->orig, static_cast<size_t>(want_orig) * 2))) return rc;
+    c->orig_cap = want_orig;
+    if ((rc = ensure_on(c, st, c->segdata, static_cast<size_t>(want_seg) * 3))) return rc;
+    c->seg_cap = want_seg;
+    if ((rc = ensure_on(c, st, c->orig_off, static_cast<size_t>(nl)))) return rc;
+    if ((rc = ensure_on(c, st, c->orig_cnt, static_cast<size_t>(nl)))) return rc;
+    if ((rc = ensure_on(c, st, c->seg_cnt, static_cast<size_t>(nl)))) return rc;
+    if ((rc = ensure_on(c, st, c->seg_off, static_cast<size_t>(nl) + 1))) return rc;
+    if ((rc = ensure_on(c, st, c->seg_info, 2))) return rc;
+    // behind the fused kernel of this build
+    HRMGPU_CUDA(c, cudaEventRecord(c->ev_fused, c->stream));
+    HRMGPU_CUDA(c, cudaStreamWaitEvent(st, c->ev_fused, 0));
+    HRMGPU_CUDA(c, cudaEventRecord(c->ev2, st));
+    if ((rc = enqueue_passes(c, 1))) return rc;
+    HRMGPU_CUDA(c, cudaEventRecord(c->ev3, st));
+    HRMGPU_CUDA(c, cudaEventRecord(c->ev_k3[c->ivl_cur], st));
+    c->seg_pending = true;
+    return HRMGPU_OK;
+}
+
+// Host side of the capacity protocol: waits for the passes of the last build, and if the pool or the payload was too small
+// grows it and repeats them.  Every getter / consumer of the free segments calls this first.
+int finalize_segments(Ctx* c) {
+    if (!c->seg_pending) return HRMGPU_OK;
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        HRMGPU_CUDA(c, cudaEventSynchronize(c->ev_k3[c->ivl_cur]));
+        const long long need_orig = static_cast<long long>(c->h_info[0]), need_seg = static_cast<long long>(c->h_info[1]);
+        int rc;
+        if (need_orig > c->orig_cap) {
+            c->orig_cap = need_orig + need_orig / 2;
+            if ((rc = ensure_on(c, c->s2, c->orig, static_cast<size_t>(c->orig_cap) * 2))) return rc;
+            if (need_seg > c->seg_cap) {  // (a lower bound: lines that did not fit counted as empty)
+                c->seg_cap = need_seg + need_seg / 2;
+                if ((rc = ensure_on(c, c->s2, c->segdata, static_cast<size_t>(c->seg_cap) * 3))) return rc;
+            }
+            if ((rc = enqueue_passes(c, 1))) return rc;
+        } else if (need_seg > c->seg_cap) {
+            c->seg_cap = need_seg + need_seg / 2;
+            if ((rc = ensure_on(c, c->s2, c->segdata, static_cast<size_t>(c->seg_cap) * 3))) return rc;
+            if ((rc = enqueue_passes(c, 3))) return rc;
+        } else {
+            c->seg_total = need_seg;
+            c->seg_pending = false;
+            // remember what this workload needs (with slack) so that the next build of a similar size fits at once
+            c->orig_hint = std::max<long long>(c->orig_hint, need_orig + need_orig / 2);
+            c->seg_hint = std::max<long long>(c->seg_hint, need_seg + need_seg / 2);
+            return HRMGPU_OK;
+        }
+        c->seg_redos += 1;
+        HRMGPU_CUDA(c, cudaEventRecord(c->ev_k3[c->ivl_cur], c->s2));
+    }
+    return fail(c, HRMGPU_E_CUDA, "free-segment passes did not converge");
+}
+
+// Loads this file's kernels up front (see preload_* in internal.cuh).
+template <class K>
+static void touch_kernel(K k) {
+    cudaFuncAttributes a;
+    if (cudaFuncGetAttributes(&a, k) != cudaSuccess) cudaGetLastError();
+}
+void preload_segments() {
+    touch_kernel(k_line_segments), touch_kernel(k_line_segments4), touch_kernel(k_enhance<false>), touch_kernel(k_enhance<true>);
+    touch_kernel(k_scan_counts);
 }
 
 }  // namespace hrmgpu

@@ -43,8 +43,31 @@ def merge_shards(shards):
     return np.concatenate(offs), np.concatenate(Ls), np.concatenate(Us), np.concatenate(Ms)
 
 
+def init_exchange(ctx, dist, device=None):
+    """Creates the context's NCCL communicator (hrmgpu_comm_init): rank 0 draws the NCCL unique id and torch.distributed
+    broadcasts its 128 bytes -- torch is only the bootstrap, the exchange itself is hrmgpu_allgather_layers."""
+    import torch
+
+    rank, world = dist.get_rank(), dist.get_world_size()
+    use_dev = device is not None and dist.get_backend() == "nccl"
+    ident = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        ident = torch.from_numpy(ctx.comm_unique_id().copy())
+    if use_dev:
+        ident = ident.to(device)
+    dist.broadcast(ident, src=0)
+    ctx.comm_init(world, rank, ident.cpu().numpy())
+
+
+def gathered_csr(ctx):
+    """Global CSR (off, xL, xU, xM) over the layers of all ranks, in rank order, from the last hrmgpu_allgather_layers."""
+    info = ctx.gathered_info()
+    return merge_shards([ctx.gathered(r) for r in range(info["world"])])
+
+
 def allgather_bytes(local_u8, dist, device):
-    """All-gather of variable-length byte tensors: sizes first, then payload padded to the max."""
+    """All-gather of variable-length byte tensors through torch.distributed: sizes first, then payload padded to the max.
+    (Exact-size variant for host frameworks that want torch tensors; the hot path uses hrmgpu_allgather_layers.)"""
     import torch
 
     world = dist.get_world_size()
@@ -61,10 +84,13 @@ def allgather_bytes(local_u8, dist, device):
 
 
 def allgather_segments(ctx, dist, device):
-    """Packs the context's last build on the device and exchanges it; returns per-rank uint8 device tensors."""
+    """Packs the context's last build on the device and exchanges it with torch.distributed; returns per-rank uint8 device
+    tensors.  hrmgpu_pack_segments_dev copies on the context's main stream: unless that IS torch's current stream (installed
+    with ctx.set_stream), the context is synchronised before torch touches the buffer."""
     import torch
 
     need = ctx.pack_segments_dev()
     buf = torch.empty(need, dtype=torch.uint8, device=device)
     ctx.pack_segments_dev(buf.data_ptr(), need)
+    ctx.synchronize()
     return allgather_bytes(buf, dist, device)

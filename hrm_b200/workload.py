@@ -14,17 +14,22 @@ BODY_SEMI = [[10.0, 5.0, 4.0]]
 N_GRID = 100
 LX, LY = 32, 16
 N_OBS = 1000
+# Obstacle semi-axis ranges.  "scaling" is SURVEY.md §8(d)'s scene (U[2,10]): with the 10 x 5 x 4 robot body its 1000 C-obstacles
+# cover nearly the whole arena, so a layer keeps ~0-6 free segments in 512 sweep lines.  "freespace" is the same generator and
+# seed with semi-axes U[0.5,2]: the same 1001 surfaces / bytes per layer, but ~45-75 % of the sweep lines carry free segments
+# (300-800 segments per layer), which loads the free-segment kernels, the D2H payload and the all-gather.
+SEMI_RANGE = {"scaling": (2.0, 10.0), "freespace": (0.5, 2.0)}
 
 
 def f32round(a):
     return np.asarray(a, dtype=np.float32).astype(np.float64)
 
 
-def scene_rows12(n_obs=N_OBS, seed=SEED):
+def scene_rows12(n_obs=N_OBS, seed=SEED, workload="scaling"):
     """[1+n_obs][12] = a,b,c,e1,e2,px,py,pz,qw,qx,qy,qz (arena first)."""
     rng = np.random.default_rng(seed)
     rows = [[ARENA[0], ARENA[1], ARENA[2], 0.1, 0.1, 0, 0, 0, 1, 0, 0, 0]]
-    semi = rng.uniform(2.0, 10.0, size=(n_obs, 3))
+    semi = rng.uniform(SEMI_RANGE[workload][0], SEMI_RANGE[workload][1], size=(n_obs, 3))
     eps = rng.uniform(0.1, 1.8, size=(n_obs, 2))
     pos = rng.uniform(-1, 1, size=(n_obs, 3)) * np.array([60.0, 32.0, 22.0])
     q = rng.normal(size=(n_obs, 4))

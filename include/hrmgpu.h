@@ -12,6 +12,12 @@
  *  - A context is bound to one CUDA device and is NOT thread-safe (like the reference objects).
  *  - Caller owns host buffers; the context owns all device buffers.  Results of a build call stay
  *    resident in HBM until the next build call of the same kind or hrmgpu_destroy().
+ *  - Streams.  A context has a MAIN stream (its own, or the one installed with hrmgpu_set_stream) and an internal SIDE
+ *    stream.  hrmgpu_build_layers* / hrmgpu_resweep only QUEUE work and return: the fused Minkowski + sweep kernel on the
+ *    main stream, the free-segment passes (and hrmgpu_allgather_layers, hrmgpu_fetch_segments_async) on the side stream
+ *    behind it, so they overlap the fused kernel of the NEXT build (interval tables are double-buffered).  Every getter
+ *    waits for what it returns; hrmgpu_join() makes the main stream wait for the side stream on the device (no host
+ *    sync); hrmgpu_synchronize() waits for both on the host.
  *  - Surfaces are ordered j = object * B + body, arena objects first, then obstacles
  *    (FreeSpace-inl.h:42-60).  Sa = n_arena*B, So = n_obs*B, S = Sa+So.
  *  - 3D sweep lines are ordered l = ix * Ly + iy (HRM3D.cpp:63-91);  2D: l = iy.
@@ -27,7 +33,7 @@
 extern "C" {
 #endif
 
-#define HRMGPU_ABI_VERSION 1
+#define HRMGPU_ABI_VERSION 2
 
 typedef struct hrmgpu_ctx hrmgpu_ctx;
 
@@ -60,6 +66,9 @@ const char* hrmgpu_last_error(const hrmgpu_ctx* ctx);
  * NULL = the context's own stream.  Lets a host framework time / order the work with its own events. */
 int hrmgpu_set_stream(hrmgpu_ctx* ctx, void* cuda_stream);
 int hrmgpu_synchronize(hrmgpu_ctx* ctx);
+/* Device-side join: work queued on the main stream after this call runs after everything queued so far on the side stream
+ * (free-segment passes, exchange).  No host synchronisation.  Use it before recording an event that must cover a whole build. */
+int hrmgpu_join(hrmgpu_ctx* ctx);
 
 /* ---- scene --------------------------------------------------------------------------------- */
 /* Replaces: the arena_/obstacle_ vectors a FreeSpace3D is constructed with (FreeSpace3D.cpp:6-10) and
@@ -111,6 +120,10 @@ int hrmgpu_resweep(hrmgpu_ctx* ctx, const double* boundaryLimits, int numLineX, 
 int hrmgpu_get_dims(hrmgpu_ctx* ctx, long long* out8);
 /* Replaces getCSpaceBoundary() (FreeSpace.h:70): boundary of one surface of layer k, dim x M column-major. */
 int hrmgpu_get_boundary(hrmgpu_ctx* ctx, int k, int surface, double* xyz);
+/* getCSpaceBoundary() for ALL surfaces of layer k in one call (what HRM3D::constructOneSlice copies into sliceBoundAll_,
+ * HRM3D.cpp:36-42): xyz [S][M][dim] doubles, i.e. S consecutive dim x M column-major BoundaryPoints, arena surfaces first.
+ * One device transpose + one device-to-host copy. */
+int hrmgpu_get_boundary_layer(hrmgpu_ctx* ctx, int k, double* xyz);
 /* Replaces getIntersectionInterval() (FreeSpace.h:74): lo/up [L][S] of layer k; NaN = no hit. */
 int hrmgpu_get_intervals(hrmgpu_ctx* ctx, int k, double* lo, double* up);
 /* Replaces getFreeSegment() (FreeSpace.h:80) for all lines of layer k: CSR offsets off[L+1] and
@@ -119,6 +132,15 @@ int hrmgpu_get_intervals(hrmgpu_ctx* ctx, int k, double* lo, double* up);
 int hrmgpu_get_segments(hrmgpu_ctx* ctx, int k, int* off, double* xL, double* xU, double* xM, int cap);
 /* All layers at once: off [K*L+1] (global CSR, 64-bit), payload arrays sized out8[6]. */
 int hrmgpu_get_segments_all(hrmgpu_ctx* ctx, long long* off, double* xL, double* xU, double* xM, long long cap);
+/* Pipelined read-back of getFreeSegment() for all layers: queues, on the side stream behind the free-segment passes of the
+ * last build, the copies of off [K*L+1] and of the first min(cap, internal capacity) entries of xL / xU / xM into the caller's
+ * (pinned, for real overlap) host arrays, and returns at once (the number of entries per array it will copy, or a negative
+ * status) -- the next hrmgpu_build_layers* may be issued immediately.
+ * hrmgpu_wait_segments() blocks until those copies are done and returns the segment count (entries past it are unspecified),
+ * or HRMGPU_E_CAP when the build held more segments than `cap` / the internal capacities: then read that build with
+ * hrmgpu_get_segments_all(), which grows them (only possible before the next build call). */
+long long hrmgpu_fetch_segments_async(hrmgpu_ctx* ctx, long long* off, double* xL, double* xU, double* xM, long long cap);
+long long hrmgpu_wait_segments(hrmgpu_ctx* ctx);
 /* Count of (line, surface) pairs that saw exactly ONE mesh hit in the last build.  The reference reads
  * hit[1] out of bounds there (FreeSpace3D.cpp:44-49,61-64); this library defines it as "no interval". */
 int hrmgpu_get_single_hit_count(hrmgpu_ctx* ctx, long long* out);
@@ -169,10 +191,34 @@ int hrmgpu_test_transitions_articulated(hrmgpu_ctx* ctx, int C, const int* pair,
                                         const double* w1, const double* link_off, const double* chain_off, unsigned char* free_out);
 
 /* ---- multi-GPU exchange ------------------------------------------------------------------------ */
-/* Packs the last build's free segments into one contiguous DEVICE buffer owned by the caller's
- * framework (e.g. a torch tensor) so that an NCCL all-gather can exchange them between ranks:
- * header [K*L+1] int64 CSR offsets followed by xL, xU, xM (doubles).  With d_buf == NULL returns the
- * required size in bytes.  See INTEGRATION.md §multi-GPU. */
+/* C-layers shard by orientation: every rank (one process, one context, one GPU) builds its own block of layers with no
+ * collective on the way.  The one exchange gives every rank the free segments (= roadmap vertices, HRM3D.cpp:93-113) of ALL
+ * layers, which bridge-layer pairing and connectMultiSlice (HRM3D.cpp:158-224) need.  Meshes are never exchanged.
+ *
+ * hrmgpu_allgather_layers packs the last build into a fixed-size block
+ *     int64 lines (= K*L of the sender), int64 total segments, int64 off[line_cap+1], double xL[seg_cap], xU[seg_cap], xM[seg_cap]
+ * and issues ONE ncclAllGather of those blocks, all on the side stream (or on `cuda_stream`, a cudaStream_t, if non-NULL)
+ * behind the free-segment passes: no size round trip, no host synchronisation, overlapped with the next build.  line_cap and
+ * seg_cap must be the same on all ranks and line_cap >= K*L; a sender with more than seg_cap segments still sends its true
+ * total, so every receiver sees that the capacity must be raised (hrmgpu_get_gathered returns HRMGPU_E_CAP).
+ * nccl_comm: an ncclComm_t of the host framework, or NULL for the communicator hrmgpu_comm_init created.  NCCL is bound at run
+ * time: the libnccl.so.2 already loaded in the process (e.g. PyTorch's) is used, else $HRMGPU_NCCL_LIB, else the system one. */
+int hrmgpu_comm_unique_id(void* id128);                       /* ncclGetUniqueId: 128 bytes, to be broadcast by the host framework */
+int hrmgpu_comm_init(hrmgpu_ctx* ctx, int n_ranks, int rank, const void* id128);   /* ncclCommInitRank on the context's device */
+int hrmgpu_comm_destroy(hrmgpu_ctx* ctx);
+int hrmgpu_allgather_layers(hrmgpu_ctx* ctx, void* nccl_comm, void* cuda_stream, long long line_cap, long long seg_cap);
+/* Last exchange: out4 = {world size, own rank, line_cap, seg_cap}; *d_blocks (if non-NULL) = device address of the world-size
+ * received blocks (layout above), valid until the next exchange. */
+int hrmgpu_gathered_info(hrmgpu_ctx* ctx, long long* out4, void** d_blocks);
+/* Rank `rank`'s block of the last exchange on the host: *lines_out = its K*L, off [lines+1] (capacity line_cap+1), xL/xU/xM
+ * [cap].  Two-call convention as hrmgpu_get_segments.  Returns that rank's segment count or a negative status. */
+long long hrmgpu_get_gathered(hrmgpu_ctx* ctx, int rank, long long* lines_out, long long* off, double* xL, double* xU, double* xM,
+                              long long cap);
+/* Packs the last build's free segments into one contiguous DEVICE buffer owned by the caller's framework (e.g. a torch
+ * tensor): header [K*L+1] int64 CSR offsets followed by xL, xU, xM (doubles), exact sizes.  With d_buf == NULL returns the
+ * required size in bytes.  Waits on the host for the free-segment passes (the size is data dependent).  The copies run on the
+ * context's MAIN stream: with the context's own stream the call returns when the buffer is complete; with a stream installed
+ * by hrmgpu_set_stream they are ordered on that stream and the caller must consume the buffer on it (or synchronise). */
 long long hrmgpu_pack_segments_dev(hrmgpu_ctx* ctx, void* d_buf, long long cap_bytes);
 
 /* ---- instrumentation ---------------------------------------------------------------------------- */
@@ -181,6 +227,10 @@ long long hrmgpu_kernel_launches(hrmgpu_ctx* ctx, int reset);
 /* Device time of the dominant kernel (fused Minkowski + sweep) of the last build call, measured with
  * CUDA events on the launching stream.  Synchronises.  Returns < 0 on error. */
 double hrmgpu_last_minksweep_ms(hrmgpu_ctx* ctx);
+/* Device time of the free-segment passes of the last build (CUDA events on the side stream).  Synchronises. */
+double hrmgpu_last_segments_ms(hrmgpu_ctx* ctx);
+/* How often free-segment passes had to be repeated because an internal capacity (grown from earlier builds) was too small. */
+long long hrmgpu_segment_redos(hrmgpu_ctx* ctx, int reset);
 
 #ifdef __cplusplus
 }

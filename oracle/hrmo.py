@@ -236,6 +236,47 @@ def layer3d(n_arena, n_obs, sq, n, body_semi, body_quat, body_off, lim, Lx, Ly, 
     }
 
 
+def layer3d_parallel(n_arena, n_obs, sq, n, body_semi, body_quat, body_off, lim, Lx, Ly, threads=None, want_bound=False):
+    """layer3d() for layers with ~10^3 surfaces: the surfaces of a layer are independent (FreeSpace-inl.h:42-60,
+    FreeSpace3D.cpp:29-68), so chunks of objects go through hrmo_layer3d on separate threads (ctypes releases the GIL) and
+    the free segments are then formed from the merged interval tables, plane by plane, with hrmo_free_segments -- the same
+    code path layer3d() runs on the whole tables.  Same return value as layer3d()."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+
+    sq = _d(sq).reshape(n_arena + n_obs, 12)
+    body_semi = _d(body_semi)
+    B = body_semi.shape[0]
+    threads = threads or len(os.sched_getaffinity(0))
+    S0 = n_arena + n_obs
+    cuts = np.linspace(0, S0, min(4 * threads, S0) + 1).astype(int)
+    chunks = [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+
+    def run(ab):
+        a, b = ab
+        na = max(0, min(b, n_arena) - a)  # arena objects in this chunk (they come first)
+        return layer3d(na, (b - a) - na, sq[a:b], n, body_semi, body_quat, body_off, lim, Lx, Ly, want_bound=want_bound)
+
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        parts = list(ex.map(run, chunks))
+    lo = np.concatenate([p_["lo"] for p_ in parts], axis=1)
+    up = np.concatenate([p_["up"] for p_ in parts], axis=1)
+    Sa = n_arena * B
+    off = [0]
+    xs = ([], [], [])
+    for ix in range(Lx):
+        r = slice(ix * Ly, (ix + 1) * Ly)
+        o, xL, xU, xM = free_segments(lo[r, :Sa], up[r, :Sa], lo[r, Sa:], up[r, Sa:])
+        off.extend((o[1:] + off[ix * Ly]).tolist())
+        for dst, src in zip(xs, (xL, xU, xM)):
+            dst.append(src)
+    return {
+        "bound": np.concatenate([p_["bound"] for p_ in parts]) if want_bound else None,
+        "lo": lo, "up": up, "off": np.array(off, dtype=np.int32), "xL": np.concatenate(xs[0]), "xU": np.concatenate(xs[1]),
+        "xM": np.concatenate(xs[2]), "single_hits": sum(p_["single_hits"] for p_ in parts),
+    }
+
+
 def layer2d(n_arena, n_obs, se, num, body_semi, body_angle, body_off, lim, Ly, seg_cap=1 << 16):
     se, body_semi, body_angle, body_off, lim = _d(se), _d(body_semi), _d(body_angle), _d(body_off), _d(lim)
     B = body_semi.shape[0]

@@ -15,10 +15,10 @@ from tests import util
 def test_library_exports_every_declared_symbol():
     lib = capi.load()
     names = capi.declared_symbols()
-    assert len(names) >= 25
+    assert len(names) >= 40
     for n in names:
         assert hasattr(lib, n), n
-    assert lib.hrmgpu_abi_version() == 1
+    assert lib.hrmgpu_abi_version() == 2
 
 
 def test_cpp_host_library_loads_and_exports_planners():
