@@ -320,7 +320,10 @@ def run_gpu(args):
     prec = {"f64": capi.F64, "f64_strict": capi.F64_STRICT, "f32": capi.F32}[args.precision]
     layers, bps, n_obs = args.layers, args.builds_per_step, args.obstacles
     ctx = capi.Context(local)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: the library queues everything on it and returns, and the CUDA events below are recorded on it
+    # (the legacy default stream has handle 0, which hrmgpu_set_stream reads as "the context's own stream")
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     if world > 1:
         hdist.init_exchange(ctx, dist, dev)  # NCCL communicator of the library; torch.distributed only broadcasts the id
@@ -394,6 +397,12 @@ def run_gpu(args):
             st.append(ctx.last_segments_ms())
         res["kernel_ms"] = sum(kt) / len(kt)
         res["segments_ms"] = sum(st) / len(st)
+        ki = []
+        for j in range(3):  # the same kernel with nothing else on the GPU (no free-segment passes of a previous build beside it)
+            ctx.synchronize()
+            build_resident(warmup * bps + j)
+            ki.append(ctx.last_minksweep_ms())
+        res["kernel_ms_alone"] = sum(ki) / len(ki)
         d = ctx.dims()
         res["dims"] = d
         res["segments_per_layer"] = d["segments"] / float(layers)
@@ -528,7 +537,7 @@ def run_gpu(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "kernel": "k_minksweep3d", "kernel_ms": kernel_ms,
                          "launches_per_step": bps, "algorithmic_bytes_per_launch": alg_bytes,
-                         "segments_ms_per_launch": head["segments_ms"], "step_minus_kernels_ms": ms_step - bps * kernel_ms,
+                         "segments_ms_per_launch": head["segments_ms"], "kernel_ms_alone": head["kernel_ms_alone"], "step_minus_kernels_ms": ms_step - bps * kernel_ms,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
             "cpu_baseline": cpu, "e2e": head["e2e"], "gpu_launches": head["launches"], "clocks": head["clocks"],
             "segments_per_layer": head["segments_per_layer"], "segment_pass_redos_in_timed_region": head["segment_pass_redos_in_timed_region"],

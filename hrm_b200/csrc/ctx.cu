@@ -182,6 +182,9 @@ int hrmgpu_create(hrmgpu_ctx** out, int device, unsigned flags) {
     if (const char* e = std::getenv("HRMGPU_SEG_FAST_CAP")) c->seg_fast_cap = std::atoi(e);
     if (const char* e = std::getenv("HRMGPU_SEG_ONE_LINE")) c->force_seg_fallback = std::atoi(e) != 0;
     if (const char* e = std::getenv("HRMGPU_SEG_INIT_CAP")) c->seg_init_cap = std::atoll(e);
+    if (const char* e = std::getenv("HRMGPU_BUCKET_CAP")) c->bucket_cap_hook = std::atoi(e);
+    if (const char* e = std::getenv("HRMGPU_CLASSIC")) c->force_classic = std::atoi(e) != 0;
+    if (const char* e = std::getenv("HRMGPU_WS_REBAL")) c->ws_rebalance = std::atoi(e) != 0;
     // test hook of the fused kernel: capacity of a warp's kept-cell list (small values force the multi-round path)
     if (const char* e = std::getenv("HRMGPU_CELL_SEG_CAP")) c->cell_seg_cap = std::atoi(e);
     if (ensure(c, c->counters, 4) != HRMGPU_OK) {
@@ -222,6 +225,10 @@ void hrmgpu_destroy(hrmgpu_ctx* c) {
     release(c, c->ivl_lo[1]);
     release(c, c->ivl_up[0]);
     release(c, c->ivl_up[1]);
+    release(c, c->bcnt[0]);
+    release(c, c->bcnt[1]);
+    release(c, c->bucket[0]);
+    release(c, c->bucket[1]);
     release(c, c->orig);
     release(c, c->orig_off);
     release(c, c->orig_cnt);

@@ -81,6 +81,15 @@ struct Ctx {
     DevBuf<char> mesh;                           // [K][S][dim][M] planar, double (or float in F32 mode)
     DevBuf<double> ivl_lo[2], ivl_up[2];         // [K][S][L], double-buffered (see s2)
     int ivl_cur = 0;                             // buffer of the last build
+    // Per-line buckets of the obstacle intervals, filled by the warp-specialised fused kernel beside the dense tables (same double
+    // buffering): bcnt [K][L] entries appended (may exceed bucket_cap: that line then takes the dense path), bucket [K][L][cap][2].
+    DevBuf<int> bcnt[2];
+    DevBuf<double> bucket[2];
+    bool bucket_valid[2] = {false, false};
+    int bucket_cap = 0;
+    int bucket_cap_hook = 0;                     // test hook: bucket capacity (small values force the dense fallback per line)
+    bool ws_rebalance = false;                   // experiment hook: producers 72 / consumers 96 registers (setmaxnreg) instead of 80 / 80
+    bool force_classic = false;                  // test / profiling hook: never use the warp-specialised kernel
     int num_sms = 148;                           // multiprocessors of the device
     int seg_fast_cap = 0;                        // test hook: list capacity of the 4-line segment pass (0 = default 128)
     long long seg_init_cap = 0;                  // test hook: first capacity of the segment pool / payload (forces the grow-and-repeat path)

@@ -360,6 +360,52 @@ __global__ void __launch_bounds__(kSeg4Warps * 32, 2) k_line_segments4(const Seg
     }
 }
 
+// Pass 1 from the per-line buckets the warp-specialised fused kernel fills (mink3d_ws.cu): a line's obstacle intervals are
+// `m` compact (lo, up) pairs instead of a stride over all S surfaces of the dense tables -- ~65 x 16 bytes per line at the
+// bench sizes instead of 1001 x 2 sectors.  One warp per line; a line whose bucket overflowed (m > bcap) is flagged and redone
+// from the dense tables by k_line_segments.  The order of the pairs inside a bucket is arbitrary (atomic append), which the
+// union does not depend on (see warp_rank_sort).  The arena interval still comes from the dense tables (Sa entries).
+constexpr int kBucketWarps = 8;
+constexpr int kBucketMax = 128;
+__global__ void __launch_bounds__(kBucketWarps * 32) k_line_segments_b(const SegParams p, const int* __restrict__ bcnt, const double* __restrict__ bucket,
+                                                                        int bcap) {
+    __shared__ __align__(16) double lists[kBucketWarps][2][kBucketMax];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long gl = static_cast<long long>(blockIdx.x) * kBucketWarps + warp;
+    if (gl >= static_cast<long long>(p.K) * p.L) return;
+    const int m = bcnt[gl];
+    if (m > bcap) {
+        if (lane == 0) p.orig_cnt[gl] = -1;
+        return;
+    }
+    const int k = static_cast<int>(gl / p.L);
+    const int l = static_cast<int>(gl - static_cast<long long>(k) * p.L);
+    const double* lo = p.lo + static_cast<size_t>(k) * p.S * p.L + l;
+    const double* up = p.up + static_cast<size_t>(k) * p.S * p.L + l;
+    double as = -DBL_MAX, ae = DBL_MAX;
+    int na = 0;
+    for (int j = lane; j < p.Sa; j += 32) {
+        const double a = lo[static_cast<size_t>(j) * p.L], b = up[static_cast<size_t>(j) * p.L];
+        if (!isnan(a) && !isnan(b)) as = fmax(as, a), ae = fmin(ae, b), ++na;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        as = fmax(as, __shfl_xor_sync(0xFFFFFFFFu, as, o));
+        ae = fmin(ae, __shfl_xor_sync(0xFFFFFFFFu, ae, o));
+        na += __shfl_xor_sync(0xFFFFFFFFu, na, o);
+    }
+    double* ks = lists[warp][0];
+    double* ke = lists[warp][1];
+    const double2* src = reinterpret_cast<const double2*>(bucket) + static_cast<size_t>(gl) * bcap;
+    for (int i = lane; i < m; i += 32) {
+        const double2 v = __ldg(src + i);
+        ks[i] = v.x;
+        ke[i] = v.y;
+    }
+    __syncwarp();
+    emit_line(p, gl, ks, ke, m, as, ae, (na > 0) && !(as > ae), lane);
+}
+
 // The four append rules of enhanceFreeSegment for the ordered pair (line i, line i+1), segment j1 of
 // line i = (s1,e1), segment j2 of line i+1 = (s2,e2).  Returns bit0: append to line i (value v_i),
 // bit1: append to line i+1 (value v_n).                                      FreeSpace-inl.h:139-161
@@ -554,7 +600,16 @@ static int enqueue_passes(Ctx* c, int from_pass) {
         HRMGPU_CUDA(c, cudaFuncSetAttribute(k_line_segments, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         const long long g1 = (nl + warps - 1) / warps;
         p.only_flagged = 0;
-        if (c->L % 4 == 0 && !c->force_seg_fallback) {
+        if (c->bucket_valid[c->ivl_cur] && c->bucket_cap <= kBucketMax && !c->force_seg_fallback) {
+            // compact per-line buckets from the warp-specialised fused kernel; overflowed lines redone from the dense tables
+            const long long gb = (nl + kBucketWarps - 1) / kBucketWarps;
+            k_line_segments_b<<<static_cast<unsigned>(gb), kBucketWarps * 32, 0, st>>>(p, c->bcnt[c->ivl_cur].p, c->bucket[c->ivl_cur].p, c->bucket_cap);
+            HRMGPU_CUDA(c, cudaGetLastError());
+            p.only_flagged = 1;
+            k_line_segments<<<static_cast<unsigned>(std::min<long long>(g1, c->num_sms)), warps * 32, smem, st>>>(p);
+            HRMGPU_CUDA(c, cudaGetLastError());
+            c->launches += 2;
+        } else if (c->L % 4 == 0 && !c->force_seg_fallback) {
             // fast path: a warp per 4 lines with short lists, then the full-size kernel on a small grid for flagged lines
             const int cap4 = std::min(p.sort_cap, c->seg_fast_cap > 0 ? c->seg_fast_cap : 128);
             const size_t smem4 = static_cast<size_t>(kSeg4Warps) * 8 * cap4 * sizeof(double);
@@ -664,7 +719,7 @@ static void touch_kernel(K k) {
     if (cudaFuncGetAttributes(&a, k) != cudaSuccess) cudaGetLastError();
 }
 void preload_segments() {
-    touch_kernel(k_line_segments), touch_kernel(k_line_segments4), touch_kernel(k_enhance<false>), touch_kernel(k_enhance<true>);
+    touch_kernel(k_line_segments), touch_kernel(k_line_segments4), touch_kernel(k_line_segments_b), touch_kernel(k_enhance<false>), touch_kernel(k_enhance<true>);
     touch_kernel(k_scan_counts);
 }
 
