@@ -88,7 +88,7 @@ struct Ctx {
     bool bucket_valid[2] = {false, false};
     int bucket_cap = 0;
     int bucket_cap_hook = 0;                     // test hook: bucket capacity (small values force the dense fallback per line)
-    bool ws_rebalance = false;                   // experiment hook: producers 72 / consumers 96 registers (setmaxnreg) instead of 80 / 80
+    int ws_variant = 1;                          // experiment hook: warp / register split of the warp-specialised kernel (mink3d_ws.cu)
     bool force_classic = false;                  // test / profiling hook: never use the warp-specialised kernel
     int num_sms = 148;                           // multiprocessors of the device
     int seg_fast_cap = 0;                        // test hook: list capacity of the 4-line segment pass (0 = default 128)

@@ -508,9 +508,12 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : (MOD
             }
         }
         // cells past the end of the mesh row (v = cells left in the row) and units past the end of the mesh
-        const int v = nc1 - j0;
-        const uint32_t keep = (v >= 4) ? 0x01800180u : ((v == 3) ? 0x00800180u : ((v == 2) ? 0x00800080u : 0x00000080u));
-        return (unit_raw < nunits) ? (g & keep) : 0u;
+        // cells 0 .. v-1 of the unit are bits 7, 23, 8, 24 (v = 0: unit past the end).  Mask arithmetic, not a ladder of selects:
+        // the compiler turns that into jumps (even a jump table), which serialises the independent units of a lane.
+        const int v = (unit_raw < nunits) ? nc1 - j0 : 0;
+        const uint32_t keep = (0x00000080u & (0u - static_cast<uint32_t>(v > 0))) | (0x00800000u & (0u - static_cast<uint32_t>(v > 1))) |
+                              (0x00000100u & (0u - static_cast<uint32_t>(v > 2))) | (0x01000000u & (0u - static_cast<uint32_t>(v > 3)));
+        return g & keep;
     };
     // exact line sets of the two faces of cell (i, j), q = i*n + j: per 16-bit half lo = min(2*lo+eq) >> 1,
     // hi+1 = (max(2*lo+eq) + 1) >> 1, lines [lo, hi); n* = number of (face, line) candidates

@@ -105,8 +105,10 @@ __device__ __forceinline__ void sts_codes(uint32_t addr, uint32_t c0, uint32_t c
 __device__ __forceinline__ uint32_t line_q(double x, double inv_d, double bias_q, bool& ok) {
     const double t = fma(x, inv_d, bias_q);
     const uint32_t w = static_cast<uint32_t>(__double2loint(t));
-    const uint32_t hi = static_cast<uint32_t>(__double2hiint(t)) - 0x4237FFFFu;  // 1: g >= 0, 0: g < 0, else out of range
-    ok = (((w + 5u) & 0xFFF8u) != 0u) && (hi < 2u) && ((hi ^ (w >> 31)) == 1u);
+    // (high word << 1) | sign bit of w is 0x84700000 for 0 <= g < 2^15 and 0x846FFFFF for -2^15 <= g < 0: one funnel shift
+    // tests the range and the sign agreement at once
+    const uint32_t u = __funnelshift_l(w, static_cast<uint32_t>(__double2hiint(t)), 1) - 0x846FFFFFu;
+    ok = (((w + 5u) & 0xFFF8u) != 0u) && (u < 2u);
     return w;
 }
 

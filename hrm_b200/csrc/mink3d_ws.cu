@@ -20,15 +20,25 @@
 //     free-segment pass reads ~65 compact entries per line instead of striding over all 1001 surfaces.
 #include "mink3d_common.cuh"
 
+#include <cstdlib>
+
 namespace hrmgpu {
 
 constexpr int kPW = 8;                 // producer warps
-constexpr int kCW = 4;                 // consumer warps
-constexpr int kPT = 32 * kPW, kCT = 32 * kCW, kWsThreads = kPT + kCT;
-// Registers: the CTA is launched with 80 per thread (2 CTAs x 384 threads per SM); the 8 producer warps give 8 each to the
-// 4 consumer warps (setmaxnreg), whose triangle tests + re-evaluation need more than the streaming phase A.
-// Variant REBAL = false keeps 80 / 80.
-constexpr int kProdRegs = 72, kConsRegs = 96;
+constexpr int kPT = 32 * kPW;          // (consumer warps: template parameter CW = 4 or 8)
+constexpr int kDeferLines = 512;       // sweep lines whose bucket appends are deferred to the next surface (CT * lines per thread)
+// Registers (2 CTAs per SM).  CW = 4: 384 threads launched with 80 registers each; VAR 0 keeps 80 / 80, VAR 1 moves 8 per
+// producer thread to the consumers (72 / 96, setmaxnreg).  CW = 8: 512 threads launched with 64 each; the consumers give
+// registers to the producers: VAR 1 = 80 / 48, VAR 2 = 72 / 56.
+template <int CW, int VAR>
+struct RegSplit {
+    static constexpr int prod = CW == 4 ? (VAR == 1 ? 72 : 0) : (VAR == 2 ? 72 : 80);
+    static constexpr int cons = CW == 4 ? (VAR == 1 ? 96 : 0) : (VAR == 2 ? 56 : 48);
+};
+constexpr int kWsCellCap = 1024;       // kept mesh cells listed per scan round (256 per consumer warp, as in the one-surface kernel)
+constexpr int kZCap = 512;             // hit heights remembered per surface (phase C -> phase D)
+constexpr uint32_t kZBits = 15, kZNone = (1u << kZBits) - 1u;  // hit key = face << 15 | pool index (kZNone: height not stored)
+static_assert(kZCap < (1 << 15) && 2 * (kMaxGrid - 1) * (kMaxGrid - 1) < (1 << 17), "hit keys are 32-bit");
 constexpr int kRowStride = 10;         // per-row factors V[3] U[3] W[3] + pad
 constexpr int kRawExtra = 36;          // doubles behind the table in a raw input buffer: Obj3 (19, padded to 20), R[9], off[3], semi[3]
 static_assert(sizeof(Obj3) == 19 * sizeof(double), "raw input layout");
@@ -42,7 +52,8 @@ struct WsParams {
     int* bcnt;                     // [K][L] entries appended to a line's bucket (may exceed bcap: the line then takes the dense path)
     double* bucket;                // [K][L][bcap][2]
     int bcap;
-    int o_raw[2], o_cc[2], o_rowf[2], o_vcode[2], o_hdr, o_items;
+    int skip_a;                    // profiling builds only: producers skip phase A (what do the consumers cost on their own?)
+    int o_raw[2], o_cc[2], o_rowf[2], o_vcode[2], o_hdr, o_items, o_zpool, o_stash, o_wtab;
     // (o_mats, o_txs, o_tys, o_queue, o_m0, o_m1, o_qcount of `m` are single copies: consumer- or setup-private)
 };
 
@@ -62,6 +73,18 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 }
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+// Work-item claim whose issue point the compiler may not move (the answer is consumed a whole phase later).
+__device__ __forceinline__ int claim_next(unsigned long long* counter) {
+    unsigned long long old;
+    asm volatile("atom.global.add.u64 %0, [%1], 1;" : "=l"(old) : "l"(counter) : "memory");
+    return static_cast<int>(old);
+}
+// Bucket-slot request, likewise pinned to its place in the instruction stream.
+__device__ __forceinline__ int bucket_slot(int* counter) {
+    int old;
+    asm volatile("atom.global.add.s32 %0, [%1], 1;" : "=r"(old) : "l"(counter) : "memory");
+    return old;
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
@@ -86,8 +109,68 @@ __device__ __forceinline__ void eval_point(const Real* k, const Real* V, const R
     for (int d = 0; d < 3; ++d) o[d] = fm(fm(k[1], W[d], k[8 + d]), inv, fm(k[0], V[d], k[2 + d]));
 }
 
-template <int MODE, bool REBAL>
-__global__ void __launch_bounds__(kWsThreads, 2) k_minksweep3d_ws(const WsParams P) {
+// The four corners of mesh cell (i, j) at once -- the same operations as four eval_point calls (bit-identical results), ordered
+// for instruction-level parallelism: the four normalisations first (independent rsqrt chains), then the coordinates one axis
+// at a time, so that a consumer thread waits for ONE dependent chain per stage instead of four whole evaluations in a row.
+// cc_i = column constants of column i (the next column follows at +kColStride), rf_j = row factors of row j (next: +kRowStride).
+template <class Real>
+__device__ __forceinline__ void eval_cell(const Real* cc_i, const Real* rf_j, D3 (&c)[2][2]) {  // c[col][row]
+    Real k01[2][2], inv[2][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) lds_pair(smem_u32(cc_i + a * kColStride), k01[a][0], k01[a][1]);
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        Real k45[2], k67[2];
+        lds_pair(smem_u32(cc_i + a * kColStride + 4), k45[0], k45[1]);
+        lds_pair(smem_u32(cc_i + a * kColStride + 6), k67[0], k67[1]);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const Real* f = rf_j + r * kRowStride;
+            const Real ux = fm(k01[a][1], f[3], k45[1]), uy = fm(k01[a][1], f[4], k67[0]), uz = fm(k01[a][1], f[5], k67[1]);
+            const Real nn = fm(uz, uz, fm(uy, uy, mu(ux, ux)));
+            if constexpr (sizeof(Real) == 4)
+                inv[a][r] = rsqrtf(nn);
+            else
+                inv[a][r] = fast_rsqrt(nn);
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        double o[2][2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const Real kC = cc_i[a * kColStride + 2 + d], kW = cc_i[a * kColStride + 8 + d];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const Real* f = rf_j + r * kRowStride;
+                o[a][r] = static_cast<double>(fm(fm(k01[a][1], f[6 + d], kW), inv[a][r], fm(k01[a][0], f[d], kC)));
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) (d == 0 ? c[a][r].x : (d == 1 ? c[a][r].y : c[a][r].z)) = o[a][r];
+    }
+}
+
+// Height of the sweep line (ix, iy) on face f, evaluated from the shared tables (phase D's rare path: the hit pool was full).
+template <class Real>
+__device__ __noinline__ double face_height(const Real* cc, const Real* rowf, const double* txs, const double* tys, int n, uint32_t f, uint32_t ix, uint32_t iy) {
+    const uint32_t nc1 = static_cast<uint32_t>(n - 1), ncell = nc1 * nc1;
+    const uint32_t cell = (f < ncell) ? f : f - ncell;
+    const uint32_t i = cell / nc1, j = cell - i * nc1;
+    D3 cn[2][2];
+    eval_cell<Real>(cc + i * kColStride, rowf + j * kRowStride, cn);
+    double z = 0.0;
+    vertical_hit_fast(txs[ix + 1], tys[iy + 1], cn[0][0], (f < ncell) ? cn[1][0] : cn[0][1], cn[1][1], z);  // the same test on the same vertices as in phase C
+    return z;
+}
+
+template <int MODE, int CW, int VAR, bool DBG>
+__global__ void __launch_bounds__(kPT + 32 * CW, 2) k_minksweep3d_ws(const WsParams P) {
+    constexpr int kCW = CW, kCT = 32 * CW, kWsThreads = kPT + kCT;
+    constexpr int kDU = kDeferLines / kCT;  // deferred lines per consumer thread
+    using Regs = RegSplit<CW, VAR>;
     using Real = typename RealOf<MODE>::type;
     using Code = uint16_t;  // 2 x 8-bit line codes (both axes <= 127 lines)
     using A = Fast;
@@ -102,96 +185,125 @@ __global__ void __launch_bounds__(kWsThreads, 2) k_minksweep3d_ws(const WsParams
     double* txs = reinterpret_cast<double*>(smem_raw + p.o_txs);
     double* tys = reinterpret_cast<double*>(smem_raw + p.o_tys);
     int* hdr = reinterpret_cast<int*>(smem_raw + P.o_hdr);      // [2][8]: item, slot, is_arena, k
-    int* items = reinterpret_cast<int*>(smem_raw + P.o_items);  // [4] claimed work items, ring
+    int* items = reinterpret_cast<int*>(smem_raw + P.o_items);  // [4][4] ring of claimed work items: item, object, pose (k * B + body), output slot
     for (int i = tid; i < p.Lx + 2; i += kWsThreads) txs[i] = __ldg(p.txs + i);
     for (int i = tid; i < p.Ly + 2; i += kWsThreads) tys[i] = __ldg(p.tys + i);
+    // claim + decode by one thread (the integer divisions run once per surface, not once per thread)
+    auto claim = [&](int ring, int item) {
+        int k = 0, s = 0;
+        if (item < P.total) {
+            if (item < nk * heavy) {
+                k = item / heavy;
+                s = item - k * heavy;
+            } else {
+                const int rem = item - nk * heavy, light = per_layer - heavy;
+                k = rem / light;
+                s = heavy + (rem - k * light);
+            }
+        }
+        const int oi = s / p.B;
+        int* e = items + 4 * ring;
+        e[0] = item, e[1] = p.first_obj + oi, e[2] = k * p.B + (s - oi * p.B), e[3] = k * per_layer + s;
+    };
     if (tid == 0) {
-        items[0] = static_cast<int>(atomicAdd(P.work, 1ULL));
-        items[1] = static_cast<int>(atomicAdd(P.work, 1ULL));
+        const int i0 = static_cast<int>(atomicAdd(P.work, 1ULL)), i1 = static_cast<int>(atomicAdd(P.work, 1ULL));
+        claim(0, i0), claim(1, i1);
     }
     __syncthreads();
 
-    auto decode = [&](int item, int& k, int& s) {
-        if (item < nk * heavy) {
-            k = item / heavy;
-            s = item - k * heavy;
-        } else {
-            const int rem = item - nk * heavy, light = per_layer - heavy;
-            k = rem / light;
-            s = heavy + (rem - k * light);
-        }
-    };
-
     if (tid < kPT) {
         // =============================== PRODUCERS: inputs -> tables -> boundary points ===============================
-        if constexpr (REBAL) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProdRegs));
+        if constexpr (CW == 4 && Regs::prod != 0) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Regs::prod));
+        if constexpr (CW == 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Regs::prod));
         const int grp = tid / p.lpc;
         const int ln = tid - grp * p.lpc;
         const bool worker = grp < p.groups;
         const int lane = tid & 31;
-        double* mats = reinterpret_cast<double*>(smem_raw + p.o_mats);  // M1[9] M2[9] + scratch T[9] KTT[9]
 
-        auto issue_load = [&](int item, int rb) {
-            int k, s;
-            decode(item, k, s);
-            const int oi = s / p.B, b = s - oi * p.B, obj_id = p.first_obj + oi;
+        auto issue_load = [&](int ring, int rb) {
+            const int obj_id = items[4 * ring + 1];
+            const size_t pose = static_cast<size_t>(items[4 * ring + 2]);
             double* dst = reinterpret_cast<double*>(smem_raw + P.o_raw[rb]);
             const double* gtab = p.tab + static_cast<size_t>(obj_id) * 8 * n;
             for (int i = tid; i < 4 * n; i += kPT) cp_async16(dst + 2 * i, gtab + 2 * i);
             double* ex = dst + 8 * n;
-            const size_t pose = static_cast<size_t>(k) * p.B + b;
             if (tid < 19) cp_async8(ex + tid, reinterpret_cast<const double*>(p.obj + obj_id) + tid);
             else if (tid >= 32 && tid < 41) cp_async8(ex + 20 + (tid - 32), p.R + pose * 9 + (tid - 32));
             else if (tid >= 64 && tid < 67) cp_async8(ex + 29 + (tid - 64), p.off + pose * 3 + (tid - 64));
-            else if (tid >= 96 && tid < 99) cp_async8(ex + 32 + (tid - 96), p.semi + 3 * b + (tid - 96));
+            else if (tid >= 96 && tid < 99) cp_async8(ex + 32 + (tid - 96), p.semi + 3 * (pose % p.B) + (tid - 96));
         };
 
-        if (items[0] < P.total) issue_load(items[0], 0);
+        // profiling builds (p.dbg): cycles of thread 0 in [1] waiting for inputs + the consumers, [2] tables, [3] phase A
+        long long t_wait = 0, t_setup = 0, t_a = 0, t0 = 0, t_begin = 0;
+        int done = 0;
+        if (DBG) t_begin = clock64();
+        if (items[0] < P.total) issue_load(0, 0);
         for (int it = 0;; ++it) {
             const int b = it & 1;
-            const int item = items[it & 3];
-            if (tid == 0) items[(it + 2) & 3] = static_cast<int>(atomicAdd(P.work, 1ULL));  // consumed two iterations from now
+            const int item = items[4 * (it & 3)];
+            const int slot = items[4 * (it & 3) + 3];
+            // the item for iteration it + 2 is requested now (global atomic) and decoded behind phase A, when the answer is back:
+            // nobody waits for the round trip
+            int claimed = 0;
+            if (tid == 0) claimed = claim_next(P.work);
+            if (DBG) t0 = clock64();
             cp_async_wait_all();
             if (it >= 2) bar_sync(kBarEmpty + b, kWsThreads);  // the consumers are done with buffer b (surface it - 2)
             bar_sync(kBarProd, kPT);                           // raw[b] complete and visible to all producers
+            if (DBG) {
+                const long long t1 = clock64();
+                t_wait += t1 - t0;
+                t0 = t1;
+            }
             if (item >= P.total) {
                 if (tid == 0) hdr[8 * b] = -1;
-                __threadfence_block();
                 bar_arrive(kBarFull + b, kWsThreads);
                 break;
             }
-            int k, s;
-            decode(item, k, s);
-            const int slot = k * per_layer + s;
             const double* raw = reinterpret_cast<const double*>(smem_raw + P.o_raw[b]);
             const double* ro = raw + 8 * n;  // a b c px py pz R[9] sign ia ib ic | R2[9] @20 | off[3] @29 | semi[3] @32
             Real* cc = reinterpret_cast<Real*>(smem_raw + P.o_cc[b]);
             Real* rowf = reinterpret_cast<Real*>(smem_raw + P.o_rowf[b]);
             Code* vcode = reinterpret_cast<Code*>(smem_raw + P.o_vcode[b]);
 
-            // ---- per-surface matrices: Tinv = (R2 diag) R2^T, M1 = Tinv R1, M2 = ((K Tinv) Tinv) R1  (SuperQuadrics.cpp:115,137-140)
-            if (tid < 32) {
+            // ---- per-surface matrices: Tinv = (R2 diag) R2^T, M1 = Tinv R1, M2 = ((K Tinv) Tinv) R1  (SuperQuadrics.cpp:115,137-140).
+            // Every warp evaluates them itself (entry e on lane e < 9, three dependent steps through shuffles, the reference's
+            // association order), so no warp waits for another one here.
+            double m1e, m2e;
+            {
                 const int me = lane < 9 ? lane : 0;
                 const int i = me / 3, j = me - 3 * i;
                 const double* r2 = ro + 20;
-                const double mi0 = r2[3 * i], mi1 = r2[3 * i + 1], mi2 = r2[3 * i + 2];
-                const double mj0 = r2[3 * j], mj1 = r2[3 * j + 1], mj2 = r2[3 * j + 2];
                 const double md0 = ro[32], md1 = ro[33], md2 = ro[34], msign = ro[15];
+                const double t = A::mad(A::mul(r2[3 * i + 2], md2), r2[3 * j + 2], A::mad(A::mul(r2[3 * i + 1], md1), r2[3 * j + 1], A::mul(A::mul(r2[3 * i], md0), r2[3 * j])));
+                const double ti0 = __shfl_sync(0xFFFFFFFFu, t, 3 * i), ti1 = __shfl_sync(0xFFFFFFFFu, t, 3 * i + 1), ti2 = __shfl_sync(0xFFFFFFFFu, t, 3 * i + 2);
+                const double tj0 = __shfl_sync(0xFFFFFFFFu, t, j), tj1 = __shfl_sync(0xFFFFFFFFu, t, 3 + j), tj2 = __shfl_sync(0xFFFFFFFFu, t, 6 + j);
+                const double ktt = A::mad(A::mul(msign, ti2), tj2, A::mad(A::mul(msign, ti1), tj1, A::mul(A::mul(msign, ti0), tj0)));
+                const double ki0 = __shfl_sync(0xFFFFFFFFu, ktt, 3 * i), ki1 = __shfl_sync(0xFFFFFFFFu, ktt, 3 * i + 1), ki2 = __shfl_sync(0xFFFFFFFFu, ktt, 3 * i + 2);
                 const double r1a = ro[6 + j], r1b = ro[9 + j], r1c = ro[12 + j];
-                double* Ts = mats + 18;
-                const double t = A::mad(A::mul(mi2, md2), mj2, A::mad(A::mul(mi1, md1), mj1, A::mul(A::mul(mi0, md0), mj0)));
-                if (lane < 9) Ts[me] = t;
-                __syncwarp();
-                const double ktt = A::mad(A::mul(msign, Ts[3 * i + 2]), Ts[6 + j],
-                                          A::mad(A::mul(msign, Ts[3 * i + 1]), Ts[3 + j], A::mul(A::mul(msign, Ts[3 * i]), Ts[j])));
-                if (lane < 9) Ts[9 + me] = ktt;
-                __syncwarp();
-                if (lane < 9) {
-                    mats[me] = A::mad(Ts[3 * i + 2], r1c, A::mad(Ts[3 * i + 1], r1b, A::mul(Ts[3 * i], r1a)));
-                    mats[9 + me] = A::mad(Ts[9 + 3 * i + 2], r1c, A::mad(Ts[9 + 3 * i + 1], r1b, A::mul(Ts[9 + 3 * i], r1a)));
-                }
+                m1e = A::mad(ti2, r1c, A::mad(ti1, r1b, A::mul(ti0, r1a)));
+                m2e = A::mad(ki2, r1c, A::mad(ki1, r1b, A::mul(ki0, r1a)));
             }
-            bar_sync(kBarProd, kPT);
+            // The 18 row-base coefficients (R1[:,0] a, R1[:,1] b, M1[:,0] / a, M1[:,1] / b, M2[:,0] / a, M2[:,1] / b) and the third
+            // columns of M1 / M2, one per lane, into the warp's own 24 doubles of shared memory: the table tasks below read them
+            // with broadcast loads instead of every thread forming the products again.
+            double* wb = reinterpret_cast<double*>(smem_raw + P.o_wtab) + (tid >> 5) * 24;
+            {
+                const int d = lane % 3, kind = lane / 3;  // lanes 0..17: kind 0..5, component d; lanes 18..23: third columns
+                const int src = lane < 18 ? 3 * d + (kind & 1) : 3 * d + 2;
+                const double s1 = __shfl_sync(0xFFFFFFFFu, m1e, src), s2 = __shfl_sync(0xFFFFFFFFu, m2e, src);
+                double val = 0.0;
+                if (kind == 0) val = ro[6 + 3 * d] * ro[0];
+                else if (kind == 1) val = ro[6 + 3 * d + 1] * ro[1];
+                else if (kind == 2) val = s1 * ro[16];
+                else if (kind == 3) val = s1 * ro[17];
+                else if (kind == 4) val = s2 * ro[16];
+                else if (kind == 5) val = s2 * ro[17];
+                else if (kind == 6) val = s1;
+                else val = s2;
+                if (lane < 24) wb[lane] = val;
+                __syncwarp();
+            }
             // ---- factor tables: rows  V_r = R1[:,0] a cw1_r + R1[:,1] b sw1_r,  U_r = M1[:,0] cw2_r / a + M1[:,1] sw2_r / b,  W_r likewise (M2);
             //      columns {ce1, ce2, C = R1[:,2] c se1 + (p - off), UZ = M1[:,2] se2 / c, WZ = M2[:,2] se2 / c}
             for (int task = tid; task < 3 * n; task += kPT) {
@@ -201,12 +313,9 @@ __global__ void __launch_bounds__(kWsThreads, 2) k_minksweep3d_ws(const WsParams
                     Real* f = rowf + r * kRowStride;
 #pragma unroll
                     for (int d = 0; d < 3; ++d) {
-                        const Real ra = Real(ro[6 + 3 * d] * ro[0]), rb = Real(ro[6 + 3 * d + 1] * ro[1]);
-                        const Real ua = Real(mats[3 * d] * ro[16]), ub = Real(mats[3 * d + 1] * ro[17]);
-                        const Real wa = Real(mats[9 + 3 * d] * ro[16]), wb = Real(mats[9 + 3 * d + 1] * ro[17]);
-                        f[d] = fm(ra, cw1, mu(rb, sw1));
-                        f[3 + d] = fm(ua, cw2, mu(ub, sw2));
-                        f[6 + d] = fm(wa, cw2, mu(wb, sw2));
+                        f[d] = fm(Real(wb[d]), cw1, mu(Real(wb[3 + d]), sw1));
+                        f[3 + d] = fm(Real(wb[6 + d]), cw2, mu(Real(wb[9 + d]), sw2));
+                        f[6 + d] = fm(Real(wb[12 + d]), cw2, mu(Real(wb[15 + d]), sw2));
                     }
                     f[9] = Real(0);
                 } else {
@@ -221,7 +330,7 @@ __global__ void __launch_bounds__(kWsThreads, 2) k_minksweep3d_ws(const WsParams
                         const Real ce2 = Real(raw[2 * n + c]), gz = mu(Real(raw[3 * n + c]), Real(ro[18]));  // se2 / c
                         kc[1] = ce2;
 #pragma unroll
-                        for (int i = 0; i < 3; ++i) kc[5 + i] = mu(Real(mats[3 * i + 2]), gz), kc[8 + i] = mu(Real(mats[9 + 3 * i + 2]), gz);
+                        for (int i = 0; i < 3; ++i) kc[5 + i] = mu(Real(wb[18 + i]), gz), kc[8 + i] = mu(Real(wb[21 + i]), gz);
                         kc[11] = Real(0);
                     }
                 }
@@ -230,16 +339,20 @@ __global__ void __launch_bounds__(kWsThreads, 2) k_minksweep3d_ws(const WsParams
                 hdr[8 * b] = item;
                 hdr[8 * b + 1] = slot;
                 hdr[8 * b + 2] = ro[15] < 0.0 ? 1 : 0;  // arena surface (sign = -1)
-                hdr[8 * b + 3] = k;
+                hdr[8 * b + 3] = slot / per_layer;      // layer
             }
             bar_sync(kBarProd, kPT);
             // ---- inputs of the next surface: requested now, consumed after phase A
-            {
-                const int next = items[(it + 1) & 3];
-                if (next < P.total) issue_load(next, b ^ 1);
+            if (items[4 * ((it + 1) & 3)] < P.total) issue_load((it + 1) & 3, b ^ 1);
+            if (DBG) {
+                const long long t1 = clock64();
+                t_setup += t1 - t0;
+                t0 = t1;
             }
             // ---- phase A: a thread owns the adjacent rows (r0, r0 + 1) and walks the columns of its group
-            if (worker) {
+            if (DBG && P.skip_a) {
+                for (int i = tid; i < M + 8; i += kPT) vcode[i] = 0;  // no vertex near a sweep line: the scan keeps nothing
+            } else if (worker) {
                 using R2 = Real2<Real>;
                 Real* mx = reinterpret_cast<Real*>(p.mesh) + static_cast<size_t>(slot) * 3 * M;
                 const int npass = n / (2 * p.lpc);
@@ -291,42 +404,70 @@ __global__ void __launch_bounds__(kWsThreads, 2) k_minksweep3d_ws(const WsParams
                     }
                 }
             }
+            if (tid == 0) claim((it + 2) & 3, claimed);
             __syncwarp();
-            __threadfence_block();
-            bar_arrive(kBarFull + b, kWsThreads);  // codes and tables of this surface are in shared memory
+            bar_arrive(kBarFull + b, kWsThreads);  // codes and tables of this surface are in shared memory (bar.arrive orders them)
+            if (DBG) t_a += clock64() - t0, ++done;
         }
         cp_async_wait_all();
+        if (DBG && tid == 0) {
+            long long* d = p.dbg + static_cast<size_t>(blockIdx.x) * 8;
+            d[1] = t_wait, d[2] = t_setup, d[3] = t_a, d[7] = done;
+        }
         return;
     }
 
     // ======================================= CONSUMERS: scan -> cell tests -> intervals =======================================
-    if constexpr (REBAL) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kConsRegs));
+    if constexpr (CW == 4 && Regs::cons != 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Regs::cons));
+    if constexpr (CW == 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Regs::cons));
     const int ctid = tid - kPT;
     const int lane = ctid & 31, warp = ctid >> 5;
-    uint16_t* cellq = reinterpret_cast<uint16_t*>(smem_raw + p.o_queue);  // [kCellCap] kept cells (cell = i * (n-1) + j)
-    uint16_t* heavyq = cellq + kCellCap;                                   // [kCellCap] of which: many candidates
+    uint16_t* cellq = reinterpret_cast<uint16_t*>(smem_raw + p.o_queue);  // [kWsCellCap] kept cells (cell = i * (n-1) + j)
+    uint16_t* heavyq = cellq + kWsCellCap;                                 // [kWsCellCap] of which: many candidates
+    double* zpool = reinterpret_cast<double*>(smem_raw + P.o_zpool);       // [kZCap] heights of the hits found in phase C
+    double2* stash = reinterpret_cast<double2*>(smem_raw + P.o_stash);     // [kCT][4] intervals whose bucket slot is still on its way
+    // Bucket appends of the PREVIOUS surface: the slot of an interval comes from a global atomic, whose round trip (~2k cycles
+    // under the write stream) nobody waits for -- the interval is parked in shared memory, the slot stays in a register, and the
+    // append is completed when the next surface arrives.
+    int ppos[kDU];
+#pragma unroll
+    for (int u = 0; u < kDU; ++u) ppos[u] = -1;
+    size_t pbase = 0;
+    auto flush_pending = [&]() {
+#pragma unroll
+        for (int u = 0; u < kDU; ++u) {
+            if (ppos[u] >= 0 && ppos[u] < P.bcap) {
+                const size_t gl = pbase + ctid + u * kCT;
+                *reinterpret_cast<double2*>(P.bucket + (gl * P.bcap + ppos[u]) * 2) = stash[ctid * kDU + u];
+            }
+            ppos[u] = -1;
+        }
+    };
     uint32_t* m0 = reinterpret_cast<uint32_t*>(smem_raw + p.o_m0);         // [L] lowest hit face per line
     uint32_t* m1 = reinterpret_cast<uint32_t*>(smem_raw + p.o_m1);         // [L] second lowest
     int* qcount = reinterpret_cast<int*>(smem_raw + p.o_qcount);           // [2] heavy cells; [4..] cells per warp segment
+    int* zcount = qcount;
     int* hcount = qcount + 2;
     int* segcnt = qcount + 4;
     const int nc1 = n - 1;
     const int ncell = nc1 * nc1;
-    const int UPR = (nc1 + 3) >> 2;  // units (4 consecutive cells of a mesh row) per mesh row
-    const int nunits = nc1 * UPR;
-    const uint32_t upr_magic = (UPR > 1) ? 0xFFFFFFFFu / static_cast<uint32_t>(UPR) + 1u : 0u;
     const uint32_t nc1_magic = 0xFFFFFFFFu / static_cast<uint32_t>(nc1) + 1u;
-    const bool vec_ok = (n & 3) == 0;
     constexpr int kUPL = 4;
-    constexpr int kSegStride = kCellCap / kCW;
+    constexpr int kSegStride = kWsCellCap / kCW;
     const int kSegCap = p.seg_cap < kSegStride ? p.seg_cap : kSegStride;
-    const unsigned lt_mask = (1u << lane) - 1u;
     uint16_t* seg = cellq + warp * kSegStride;
     constexpr uint32_t kLight = 16;  // cells with more candidates than this get a whole warp
 
+    long long c_wait = 0, c_sweep = 0, c_cells = 0, c_d = 0, c0 = 0;  // profiling builds: [4] waiting for the producers, [5] scan + cell tests, [6] phase D
     for (int it = 0;; ++it) {
         const int b = it & 1;
+        if (DBG) c0 = clock64();
         bar_sync(kBarFull + b, kWsThreads);
+        if (DBG) {
+            const long long c1 = clock64();
+            c_wait += c1 - c0;
+            c0 = c1;
+        }
         const int item = hdr[8 * b];
         if (item < 0) break;
         const int slot = hdr[8 * b + 1];
@@ -336,58 +477,33 @@ __global__ void __launch_bounds__(kWsThreads, 2) k_minksweep3d_ws(const WsParams
         const Real* rowf = reinterpret_cast<const Real*>(smem_raw + P.o_rowf[b]);
         const Code* vcode = reinterpret_cast<const Code*>(smem_raw + P.o_vcode[b]);
         auto code_at = [&](int q) -> uint32_t { return __byte_perm(static_cast<uint32_t>(vcode[q]), 0u, 0x4140); };
-        // vertex (i, j) of the parameter grid (point index i * n + j): the producers' arithmetic again
-        auto vertex = [&](int i, int j) -> D3 {
-            Real kk[12], F[9], o[3];
-            const uint32_t ca = smem_u32(cc + i * kColStride), fa = smem_u32(rowf + j * kRowStride);
-#pragma unroll
-            for (int t = 0; t < 6; ++t) lds_pair(ca + t * 2 * sizeof(Real), kk[2 * t], kk[2 * t + 1]);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) lds_pair(fa + t * 2 * sizeof(Real), F[2 * t], F[2 * t + 1]);
-            F[8] = rowf[j * kRowStride + 8];
-            eval_point<Real>(kk, F, F + 3, F + 6, o);
-            return {static_cast<double>(o[0]), static_cast<double>(o[1]), static_cast<double>(o[2])};
-        };
         auto hit = [&](uint32_t ix, uint32_t iy, const D3& t0, const D3& t1, const D3& t2, double& z) -> bool {
             return vertical_hit_fast(txs[ix + 1], tys[iy + 1], t0, t1, t2, z);
         };
 
         for (int i = ctid; i < p.L; i += kCT) m0[i] = kNoFace, m1[i] = kNoFace;
-        if (ctid == 0) *hcount = 0;
+        if (ctid == 0) *hcount = 0, *zcount = 0;
         bar_sync(kBarCons, kCT);
+        // A hit enters the line's ordered two-slot table keyed by its FACE INDEX (the reference keeps the first two hits in face
+        // order, SURVEY finding 2); the low bits of the key say where its height is kept for phase D.
+        auto record_hit = [&](uint32_t l, uint32_t face, double z) {
+            const int zi = atomicAdd(zcount, 1);
+            uint32_t key = (face << kZBits) | kZNone;
+            if (zi < kZCap) zpool[zi] = z, key = (face << kZBits) | static_cast<uint32_t>(zi);
+            insert_two_smallest(&m0[l], &m1[l], key);
+        };
 
-        // B1: cells of unit u whose inclusive xy bounding box may contain a sweep line (see mink3d.cu for the SWAR form)
-        auto unit_cells = [&](int unit_raw, bool fast) -> uint32_t {
-            const int unit = min(unit_raw, nunits - 1);
-            const int i = (UPR > 1) ? static_cast<int>(__umulhi(static_cast<uint32_t>(unit), upr_magic)) : unit;
-            const int j0 = 4 * (unit - i * UPR);
-            const int q = i * n + j0;
-            uint32_t g;
-            if (fast) {
-                const uint2 a = *reinterpret_cast<const uint2*>(vcode + q);
-                const uint2 bq = *reinterpret_cast<const uint2*>(vcode + q + n);
-                const uint32_t a4 = static_cast<uint32_t>(vcode[q + 4]), b4 = static_cast<uint32_t>(vcode[q + n + 4]);
-                const uint32_t sax = __funnelshift_r(a.x, a.y, 16), say = __funnelshift_r(a.y, a4, 16);
-                const uint32_t sbx = __funnelshift_r(bq.x, bq.y, 16), sby = __funnelshift_r(bq.y, b4, 16);
-                const uint32_t dx = (a.x ^ bq.x) | (a.x ^ sax) | (a.x ^ sbx) | (a.x & 0x01010101u);
-                const uint32_t dy = (a.y ^ bq.y) | (a.y ^ say) | (a.y ^ sby) | (a.y & 0x01010101u);
-                const uint32_t nx = (((dx & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | dx), ny = (((dy & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | dy);
-                const uint32_t fx = nx & (nx >> 8) & 0x00800080u, fy = ny & (ny >> 8) & 0x00800080u;
-                g = fx + (fy << 1);
-            } else {
-                uint32_t r0[5], r1[5];
-#pragma unroll
-                for (int e = 0; e < 5; ++e) r0[e] = code_at(q + e), r1[e] = code_at(q + n + e);
-                g = 0;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const uint32_t d = (r0[e] ^ r1[e]) | (r0[e] ^ r0[e + 1]) | (r0[e] ^ r1[e + 1]) | (r0[e] & 0x00010001u);
-                    if ((d & 0xFFFFu) != 0u && (d >> 16) != 0u) g |= 1u << ((e & 1 ? 23 : 7) + (e >> 1));
-                }
-            }
-            const int v = nc1 - j0;
-            const uint32_t keep = (v >= 4) ? 0x01800180u : ((v == 3) ? 0x00800180u : ((v == 2) ? 0x00800080u : 0x00000080u));
-            return (unit_raw < nunits) ? (g & keep) : 0u;
+        // B1: cells whose inclusive xy bounding box (over the 4 corners) may contain a sweep line -- the SWAR test of mink3d.cu
+        // (per axis the set of lines inside the box is empty <=> all four codes are equal and even).
+        // Result bits of a unit: cell 0 -> bit 7, cell 2 -> 8, cell 1 -> 23, cell 3 -> 24 (where the SWAR form leaves them); four
+        // units share one 32-bit word, unit uu shifted left by 2 * uu.
+        // (a, bq: the two vertex rows; sa*, sb*: the same rows advanced by one vertex)
+        auto swar4 = [](uint2 a, uint32_t sax, uint32_t say, uint2 bq, uint32_t sbx, uint32_t sby) -> uint32_t {
+            const uint32_t dx = (a.x ^ bq.x) | (a.x ^ sax) | (a.x ^ sbx) | (a.x & 0x01010101u);
+            const uint32_t dy = (a.y ^ bq.y) | (a.y ^ say) | (a.y ^ sby) | (a.y & 0x01010101u);
+            const uint32_t nx = (((dx & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | dx), ny = (((dy & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | dy);
+            const uint32_t fx = nx & (nx >> 8) & 0x00800080u, fy = ny & (ny >> 8) & 0x00800080u;
+            return fx + (fy << 1);
         };
         auto cell_sets = [&](int q, uint32_t& loA, uint32_t& hiA, uint32_t& loB, uint32_t& hiB, uint32_t& nA, uint32_t& nB) {
             const uint32_t c00 = code_at(q), c11 = code_at(q + n + 1), c10 = code_at(q + n), c01 = code_at(q + 1);
@@ -402,61 +518,101 @@ __global__ void __launch_bounds__(kWsThreads, 2) k_minksweep3d_ws(const WsParams
             for (uint32_t ix = lo2 & 0xFFFFu; ix < (hi2 & 0xFFFFu); ++ix)
                 for (uint32_t iy = lo2 >> 16; iy < (hi2 >> 16); ++iy) {
                     double z;
-                    if (hit(ix, iy, t0, t1, t2, z)) {
-                        const uint32_t l = ix * p.Ly + iy;
-                        insert_two_smallest(&m0[l], &m1[l], face);
-                    }
+                    if (hit(ix, iy, t0, t1, t2, z)) record_hit(ix * p.Ly + iy, face, z);
                 }
         };
 
-        int bw = warp;
-        bool batch_loaded = false;
-        uint32_t w_bits = 0;
+        // Scan.  The code is straight-line on purpose (mask arithmetic instead of selects the compiler would turn into jumps):
+        // the consumers are bound by instruction issue, so what counts is the number of instructions per cell and that the loads
+        // and logic of independent cells interleave.  A lane owns the 4 cells j0 = 4 * lane .. j0 + 3 of every mesh row (n <= 128,
+        // n % 4 == 0: one 8-byte load per vertex row), a warp a band of consecutive mesh rows; the lower vertex row of one step is
+        // the upper row of the next, and the lane's cell mask is loop-invariant.  (1) all SWAR tests of a chunk (kWR words x 4
+        // rows per lane) back to back; (2) ONE prefix sum over the lanes' kept-cell counts, then every lane writes its own cells.
+        // What does not fit into the warp's list segment stays in w[] for the next round (after the tests of this round).
+        constexpr int kWR = 7;  // words per lane and chunk: 7 x 4 rows x kCW warps >= 99 mesh rows (n = 100, 4 consumer warps)
+        const int rows_per_warp = (nc1 + kCW - 1) / kCW;
+        const int nchunk = (rows_per_warp + kWR * kUPL - 1) / (kWR * kUPL);
+        const int j0 = 4 * lane;
+        const int jl = min(j0, n - 4);  // (lanes past the end of a row load its last unit and keep nothing)
+        const int vcells = nc1 - j0;    // cells of this lane's unit inside a mesh row
+        // cells 0 .. v-1 of a unit are bits 7, 23, 8, 24
+        const uint32_t keep = (0x00000080u & (0u - static_cast<uint32_t>(vcells > 0))) | (0x00800000u & (0u - static_cast<uint32_t>(vcells > 1))) |
+                              (0x00000100u & (0u - static_cast<uint32_t>(vcells > 2))) | (0x01000000u & (0u - static_cast<uint32_t>(vcells > 3)));
+        auto chunk_row0 = [&](int chunk) { return warp * rows_per_warp + chunk * (kWR * kUPL); };
+        int chunk = 0;
+        bool loaded = false;
+        uint32_t w[kWR];
+#pragma unroll
+        for (int r = 0; r < kWR; ++r) w[r] = 0u;
         for (;;) {
             int wcnt = 0;
             bool parked = false;
-            while (bw * (32 * kUPL) < nunits) {
-                if (!batch_loaded) {
-                    w_bits = 0u;
-                    if (vec_ok) {
+            while (chunk < nchunk) {
+                if (!loaded) {
+                    const int row0 = chunk_row0(chunk);
+                    const int band_end = min(nc1, (warp + 1) * rows_per_warp);  // first mesh row that is not this warp's
+                    int row = min(row0, nc1 - 1);
+                    uint2 ra = *reinterpret_cast<const uint2*>(vcode + row * n + jl);
+                    uint32_t sax = __funnelshift_r(ra.x, ra.y, 16), say = __funnelshift_r(ra.y, static_cast<uint32_t>(vcode[row * n + jl + 4]), 16);
 #pragma unroll
-                        for (int uu = 0; uu < kUPL; ++uu) w_bits += unit_cells((bw * kUPL + uu) * 32 + lane, true) << (2 * uu);
-                    } else {
+                    for (int r = 0; r < kWR; ++r) {
+                        uint32_t acc = 0u;
 #pragma unroll
-                        for (int uu = 0; uu < kUPL; ++uu) w_bits += unit_cells((bw * kUPL + uu) * 32 + lane, false) << (2 * uu);
+                        for (int uu = 0; uu < kUPL; ++uu) {
+                            const int i = row0 + r * kUPL + uu;  // mesh row (vertex rows i, i + 1)
+                            const int ib = min(i + 1, n - 1);
+                            const uint2 rb = *reinterpret_cast<const uint2*>(vcode + ib * n + jl);
+                            const uint32_t sbx = __funnelshift_r(rb.x, rb.y, 16), sby = __funnelshift_r(rb.y, static_cast<uint32_t>(vcode[ib * n + jl + 4]), 16);
+                            const uint32_t on = 0u - static_cast<uint32_t>(i < band_end);
+                            acc += (swar4(ra, sax, say, rb, sbx, sby) & keep & on) << (2 * uu);
+                            ra = rb, sax = sbx, say = sby;
+                        }
+                        w[r] = acc;
                     }
-                    batch_loaded = true;
+                    loaded = true;
                 }
-                unsigned any = __ballot_sync(0xFFFFFFFFu, w_bits != 0u);
-                while (any != 0u) {
-                    const int pos = wcnt + __popc(any & lt_mask);
-                    if (w_bits != 0u && pos < kSegCap) {
-                        const int bit = __ffs(w_bits) - 1;
-                        w_bits &= w_bits - 1u;
+                int mine = 0;
+#pragma unroll
+                for (int r = 0; r < kWR; ++r) mine += __popc(w[r]);
+                int incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                const int room = kSegCap - wcnt;
+                int pos = incl - mine;  // rank of this lane's first remaining cell
+                const int row0 = chunk_row0(chunk);
+#pragma unroll
+                for (int r = 0; r < kWR; ++r) {
+                    while (w[r] != 0u && pos < room) {
+                        const int bit = __ffs(w[r]) - 1;
+                        w[r] &= w[r] - 1u;
+                        // bits 7.. hold cells 0 / 2, bits 23.. cells 1 / 3 of the word's four rows
                         const int hi = bit >= 23 ? 1 : 0, pb = bit - (hi ? 23 : 7);
-                        const int unit = (bw * kUPL + (pb >> 1)) * 32 + lane;
-                        const int i = (UPR > 1) ? static_cast<int>(__umulhi(static_cast<uint32_t>(unit), upr_magic)) : unit;
-                        const int j = 4 * (unit - i * UPR) + (((pb & 1) << 1) | hi);
-                        seg[pos] = static_cast<uint16_t>(i * nc1 + j);
+                        seg[wcnt + pos] = static_cast<uint16_t>((row0 + r * kUPL + (pb >> 1)) * nc1 + j0 + (((pb & 1) << 1) | hi));
+                        ++pos;
                     }
-                    wcnt += __popc(any);
-                    if (wcnt >= kSegCap) {
-                        wcnt = kSegCap;
-                        break;
-                    }
-                    any = __ballot_sync(0xFFFFFFFFu, w_bits != 0u);
                 }
                 __syncwarp();
-                if (__any_sync(0xFFFFFFFFu, w_bits != 0u)) {
+                if (total > room) {  // segment full: the tests come first, the rest of w[] follows in the next round
+                    wcnt = kSegCap;
                     parked = true;
                     break;
                 }
-                batch_loaded = false;
-                bw += kCW;
+                wcnt += total;
+                loaded = false;
+                ++chunk;
             }
             if (lane == 0) segcnt[warp] = wcnt;
             __syncwarp();
             const int more = bar_or(kBarCons, kCT, parked ? 1 : 0);
+            if (DBG) {
+                const long long c1 = clock64();
+                c_sweep += c1 - c0;
+                c0 = c1;
+            }
             // C: one kept cell per thread and pass
             int sc[kCW + 1];
             sc[0] = 0;
@@ -478,9 +634,10 @@ __global__ void __launch_bounds__(kWsThreads, 2) k_minksweep3d_ws(const WsParams
                     if (nA + nB > kLight) {
                         heavyq[atomicAdd(hcount, 1)] = static_cast<uint16_t>(cell);
                     } else if (nA + nB != 0u) {
-                        const D3 c00 = vertex(i, j), c11 = vertex(i + 1, j + 1);
-                        if (nA != 0u) test_lines(cell, loA, hiA, c00, vertex(i + 1, j), c11);                                  // (q, q+n, q+n+1)
-                        if (nB != 0u) test_lines(cell + static_cast<uint32_t>(ncell), loB, hiB, c00, vertex(i, j + 1), c11);  // (q, q+1, q+n+1)
+                        D3 cn[2][2];  // [column offset][row offset]: vertex (i + a, j + r) = point q + a * n + r
+                        eval_cell<Real>(cc + i * kColStride, rowf + j * kRowStride, cn);
+                        if (nA != 0u) test_lines(cell, loA, hiA, cn[0][0], cn[1][0], cn[1][1]);                                  // (q, q+n, q+n+1)
+                        if (nB != 0u) test_lines(cell + static_cast<uint32_t>(ncell), loB, hiB, cn[0][0], cn[0][1], cn[1][1]);  // (q, q+1, q+n+1)
                     }
                 }
             }
@@ -495,7 +652,9 @@ __global__ void __launch_bounds__(kWsThreads, 2) k_minksweep3d_ws(const WsParams
                     const int q = i * n + j;
                     uint32_t loA, hiA, loB, hiB, nA, nB;
                     cell_sets(q, loA, hiA, loB, hiB, nA, nB);
-                    const D3 c00 = vertex(i, j), c10 = vertex(i + 1, j), c11 = vertex(i + 1, j + 1), c01 = vertex(i, j + 1);
+                    D3 cn[2][2];
+                    eval_cell<Real>(cc + i * kColStride, rowf + j * kRowStride, cn);
+                    const D3 c00 = cn[0][0], c10 = cn[1][0], c11 = cn[1][1], c01 = cn[0][1];
                     for (uint32_t idx = lane; idx < nA + nB; idx += 32) {
                         const bool second = idx >= nA;
                         const uint32_t k2 = second ? idx - nA : idx;
@@ -504,59 +663,87 @@ __global__ void __launch_bounds__(kWsThreads, 2) k_minksweep3d_ws(const WsParams
                         const uint32_t dxl = k2 / wy;
                         const uint32_t ix = (lo2 & 0xFFFFu) + dxl, iy = (lo2 >> 16) + (k2 - dxl * wy);
                         double z;
-                        if (hit(ix, iy, c00, second ? c01 : c10, c11, z)) {
-                            const uint32_t l = ix * p.Ly + iy;
-                            insert_two_smallest(&m0[l], &m1[l], cell + (second ? static_cast<uint32_t>(ncell) : 0u));
-                        }
+                        if (hit(ix, iy, c00, second ? c01 : c10, c11, z)) record_hit(ix * p.Ly + iy, cell + (second ? static_cast<uint32_t>(ncell) : 0u), z);
                     }
                 }
                 __syncwarp();
                 bar_sync(kBarCons, kCT);
+            }
+            if (DBG) {
+                const long long c1 = clock64();
+                c_cells += c1 - c0;
+                c0 = c1;
             }
             if (!more) break;
             if (ctid == 0) *hcount = 0;
             bar_sync(kBarCons, kCT);
         }
 
+        if (DBG) {
+            const long long c1 = clock64();
+            c_sweep += c1 - c0;
+            c0 = c1;
+        }
+        flush_pending();  // (the previous surface's bucket slots were requested a whole scan + test phase ago)
         // ---- phase D: intervals (FreeSpace3D.cpp:44-49 / 61-64) ----
         double* lo = p.lo + static_cast<size_t>(slot) * p.L;
         double* up = p.up + static_cast<size_t>(slot) * p.L;
         unsigned single = 0;
-        auto face_z = [&](uint32_t f, uint32_t ix, uint32_t iy) -> double {
-            const uint32_t cell = (f < static_cast<uint32_t>(ncell)) ? f : f - static_cast<uint32_t>(ncell);
-            const int i = static_cast<int>(__umulhi(cell, nc1_magic));
-            const int j = static_cast<int>(cell) - i * nc1;
-            const D3 t0 = vertex(i, j), t2 = vertex(i + 1, j + 1);
-            const D3 t1 = (f < static_cast<uint32_t>(ncell)) ? vertex(i + 1, j) : vertex(i, j + 1);
-            double z = 0.0;
-            hit(ix, iy, t0, t1, t2, z);  // the same test on the same vertices as in phase C
-            return z;
+        auto face_z = [&](uint32_t key, uint32_t ix, uint32_t iy) -> double {
+            if ((key & kZNone) != kZNone) return zpool[key & kZNone];  // found in phase C
+            return face_height<Real>(cc, rowf, txs, tys, n, key >> kZBits, ix, iy);  // (pool full: evaluate the face again)
         };
-        for (int l = ctid; l < p.L; l += kCT) {
+        auto interval = [&](int l, double& a, double& bb) -> bool {  // true: an obstacle interval that goes into the line's bucket
+            a = is_arena ? p.zlow : __longlong_as_double(0x7FF8000000000000LL);
+            bb = is_arena ? p.zup : __longlong_as_double(0x7FF8000000000000LL);
             const uint32_t e0 = m0[l], e1 = m1[l];
-            double a = is_arena ? p.zlow : __longlong_as_double(0x7FF8000000000000LL);
-            double bb = is_arena ? p.zup : __longlong_as_double(0x7FF8000000000000LL);
             if (e1 != kNoFace) {
                 const uint32_t ix = static_cast<uint32_t>(l) / static_cast<uint32_t>(p.Ly), iy = static_cast<uint32_t>(l) - ix * static_cast<uint32_t>(p.Ly);
                 const double z0 = face_z(e0, ix, iy), z1 = face_z(e1, ix, iy);
                 const double zl = fmin(z0, z1), zu = fmax(z0, z1);
                 a = is_arena ? fmin(p.zlow, zl) : zl;
                 bb = is_arena ? fmax(p.zup, zu) : zu;
-                if (!is_arena && P.bcnt && !isnan(zl) && !isnan(zu)) {  // compact copy for the free-segment pass
-                    const size_t gl = static_cast<size_t>(k_layer) * p.L + l;
-                    const int pos = atomicAdd(P.bcnt + gl, 1);
-                    if (pos < P.bcap) *reinterpret_cast<double2*>(P.bucket + (gl * P.bcap + pos) * 2) = make_double2(zl, zu);
-                }
-            } else if (e0 != kNoFace) {
-                ++single;  // exactly one hit: reference reads out of bounds; defined here as "no interval"
+                return !is_arena && P.bcnt != nullptr && !isnan(zl) && !isnan(zu);
             }
+            if (e0 != kNoFace) ++single;  // exactly one hit: reference reads out of bounds; defined here as "no interval"
+            return false;
+        };
+        // first kDU lines of the thread (all of them when L <= 512): bucket appends deferred, see ppos
+        pbase = static_cast<size_t>(k_layer) * p.L;
+#pragma unroll
+        for (int u = 0; u < kDU; ++u) {
+            const int l = ctid + u * kCT;
+            if (l < p.L) {
+                double a, bb;
+                if (interval(l, a, bb)) {
+                    stash[ctid * kDU + u] = make_double2(a, bb);
+                    ppos[u] = bucket_slot(P.bcnt + pbase + l);  // not read before flush_pending()
+                }
+                lo[l] = a;
+                up[l] = bb;
+            }
+        }
+        for (int l = ctid + kDU * kCT; l < p.L; l += kCT) {  // more than 512 sweep lines: the remaining ones append at once
+            double a, bb;
+            const bool app = interval(l, a, bb);
             lo[l] = a;
             up[l] = bb;
+            if (app) {
+                const size_t gl = pbase + l;
+                const int pos = bucket_slot(P.bcnt + gl);
+                if (pos < P.bcap) *reinterpret_cast<double2*>(P.bucket + (gl * P.bcap + pos) * 2) = make_double2(a, bb);
+            }
         }
         if (single) atomicAdd(p.counters, static_cast<unsigned long long>(single));
         __syncwarp();
-        __threadfence_block();
-        bar_arrive(kBarEmpty + b, kWsThreads);
+        bar_arrive(kBarEmpty + b, kWsThreads);  // (no fence: nothing the consumers wrote is read by the producers)
+        if (DBG) c_d += clock64() - c0;
+    }
+    flush_pending();
+    if (DBG && ctid == 0) {
+        long long* d = p.dbg + static_cast<size_t>(blockIdx.x) * 8;
+        d[4] = c_wait, d[5] = c_sweep, d[6] = c_d;
+        atomicExch(reinterpret_cast<unsigned long long*>(d), static_cast<unsigned long long>(c_cells));  // ([0] is written by the producers first)
     }
 }
 
@@ -570,33 +757,36 @@ static size_t ws_layout(WsParams& P, int MODE, int n, int Lx, int Ly) {
     for (int i = 0; i < 2; ++i) P.o_cc[i] = static_cast<int>(b), b += al(real * kColStride * n);
     for (int i = 0; i < 2; ++i) P.o_rowf[i] = static_cast<int>(b), b += al(real * kRowStride * n);
     for (int i = 0; i < 2; ++i) P.o_vcode[i] = static_cast<int>(b), b += al(2 * (static_cast<size_t>(n) * n + 8));
-    p.o_mats = static_cast<int>(b), b += sizeof(double) * 36;
+    p.o_mats = 0;
+    P.o_wtab = static_cast<int>(b), b += sizeof(double) * 24 * kPW;
     p.o_txs = static_cast<int>(b), b += al(sizeof(double) * (Lx + 2));
     p.o_tys = static_cast<int>(b), b += al(sizeof(double) * (Ly + 2));
-    p.o_queue = static_cast<int>(b), b += 2 * sizeof(uint16_t) * kCellCap;
+    p.o_queue = static_cast<int>(b), b += 2 * sizeof(uint16_t) * kWsCellCap;
+    P.o_zpool = static_cast<int>(b), b += sizeof(double) * kZCap;
+    P.o_stash = static_cast<int>(b), b += sizeof(double2) * kDeferLines;
     const size_t L = static_cast<size_t>(Lx) * Ly;
     p.o_m0 = static_cast<int>(b), b += al(sizeof(uint32_t) * L);
     p.o_m1 = static_cast<int>(b), b += al(sizeof(uint32_t) * L);
-    p.o_qcount = static_cast<int>(b), b += 16 + 4 * kCW + 16;
+    p.o_qcount = static_cast<int>(b), b += 16 + 4 * 8 + 16;
     b = al(b);
     P.o_hdr = static_cast<int>(b), b += 2 * 8 * sizeof(int);
-    P.o_items = static_cast<int>(b), b += 4 * sizeof(int);
+    P.o_items = static_cast<int>(b), b += 16 * sizeof(int);
     return al(b);
 }
 
 // Whether a build of this shape runs on the warp-specialised kernel (otherwise mink3d.cu's one-surface kernel).
 bool ws_supported(const Ctx* c, int precision, bool do_sweep, bool reload, int lpc, int groups, int paired) {
     if (c->force_classic || !do_sweep || reload || precision == HRMGPU_F64_STRICT) return false;
-    if (!paired || c->n < 32 || lpc * groups > kPT) return false;
+    if (!paired || c->n < 32 || c->n > 128 || (c->n & 3) != 0 || lpc * groups > kPT) return false;  // (scan: 8-byte rows, one unit per lane)
     if (c->Lx > 127 || c->Ly > 127) return false;  // 2 x 8-bit line codes
     return true;
 }
 
-template <int MODE, bool REBAL>
+template <int MODE, int CW, int VAR, bool DBG>
 static int launch_ws_t(Ctx* c, const WsParams& P, int grid, size_t smem) {
-    auto kern = k_minksweep3d_ws<MODE, REBAL>;
+    auto kern = k_minksweep3d_ws<MODE, CW, VAR, DBG>;
     HRMGPU_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    kern<<<grid, kWsThreads, smem, c->stream>>>(P);
+    kern<<<grid, kPT + 32 * CW, smem, c->stream>>>(P);
     HRMGPU_CUDA(c, cudaGetLastError());
     c->launches += 1;
     return HRMGPU_OK;
@@ -611,19 +801,38 @@ int launch_minksweep3d_ws(Ctx* c, const MinkParams& base, int precision, long lo
     P.bcnt = d_bcnt;
     P.bucket = d_bucket;
     P.bcap = bcap;
+    P.skip_a = std::getenv("HRMGPU_WS_SKIPA") ? 1 : 0;
     const size_t smem = ws_layout(P, precision, c->n, c->Lx, c->Ly);
     if (smem > 113 * 1024) return -1000;  // does not fit twice per SM: the caller falls back to the one-surface kernel
     HRMGPU_CUDA(c, cudaMemsetAsync(c->counters.p + 2, 0, sizeof(unsigned long long), c->stream));
     const int grid = static_cast<int>(std::min<long long>(items, 2LL * c->num_sms));
-    if (precision == HRMGPU_F32) return launch_ws_t<HRMGPU_F32, false>(c, P, grid, smem);
-    return c->ws_rebalance ? launch_ws_t<HRMGPU_F64, true>(c, P, grid, smem) : launch_ws_t<HRMGPU_F64, false>(c, P, grid, smem);
+    const int v = c->ws_variant;  // experiment hook (HRMGPU_WS_VARIANT): 0 = 4 consumer warps 80/80, 1 = 4 x 72/96, 2 = 8 x 80/48, 3 = 8 x 72/56
+    if (precision == HRMGPU_F32) return launch_ws_t<HRMGPU_F32, 4, 0, false>(c, P, grid, smem);
+    if (P.m.dbg) {  // profiling builds (tools/phase_times.py): per-role cycle counters
+        switch (v) {
+            case 0: return launch_ws_t<HRMGPU_F64, 4, 0, true>(c, P, grid, smem);
+            case 1: return launch_ws_t<HRMGPU_F64, 4, 1, true>(c, P, grid, smem);
+            case 2: return launch_ws_t<HRMGPU_F64, 8, 1, true>(c, P, grid, smem);
+            default: return launch_ws_t<HRMGPU_F64, 8, 2, true>(c, P, grid, smem);
+        }
+    }
+    switch (v) {
+        case 0: return launch_ws_t<HRMGPU_F64, 4, 0, false>(c, P, grid, smem);
+        case 1: return launch_ws_t<HRMGPU_F64, 4, 1, false>(c, P, grid, smem);
+        case 2: return launch_ws_t<HRMGPU_F64, 8, 1, false>(c, P, grid, smem);
+        default: return launch_ws_t<HRMGPU_F64, 8, 2, false>(c, P, grid, smem);
+    }
 }
 
-void preload_mink3d_ws() {
+template <class K>
+static void touch_ws(K k) {
     cudaFuncAttributes a;
-    if (cudaFuncGetAttributes(&a, k_minksweep3d_ws<HRMGPU_F64, false>) != cudaSuccess) cudaGetLastError();
-    if (cudaFuncGetAttributes(&a, k_minksweep3d_ws<HRMGPU_F64, true>) != cudaSuccess) cudaGetLastError();
-    if (cudaFuncGetAttributes(&a, k_minksweep3d_ws<HRMGPU_F32, false>) != cudaSuccess) cudaGetLastError();
+    if (cudaFuncGetAttributes(&a, k) != cudaSuccess) cudaGetLastError();
+}
+void preload_mink3d_ws() {
+    touch_ws(k_minksweep3d_ws<HRMGPU_F64, 4, 0, false>), touch_ws(k_minksweep3d_ws<HRMGPU_F64, 4, 1, false>);
+    touch_ws(k_minksweep3d_ws<HRMGPU_F64, 8, 1, false>), touch_ws(k_minksweep3d_ws<HRMGPU_F64, 8, 2, false>);
+    touch_ws(k_minksweep3d_ws<HRMGPU_F32, 4, 0, false>);
 }
 
 }  // namespace hrmgpu

@@ -64,7 +64,7 @@ def test_ws_f32_points_within_tolerance(oracle, gpu_ctx):
     check_against_oracle(oracle, gpu_ctx, rows, 48, 16, 8, semi, R, off, quat, capi.F32, [0, 3])
 
 
-@pytest.mark.parametrize("env", [{}, {"HRMGPU_CELL_SEG_CAP": "3"}, {"HRMGPU_BUCKET_CAP": "2"}, {"HRMGPU_WS_REBAL": "1"}])
+@pytest.mark.parametrize("env", [{}, {"HRMGPU_CELL_SEG_CAP": "3"}, {"HRMGPU_BUCKET_CAP": "2"}, {"HRMGPU_WS_VARIANT": "0"}, {"HRMGPU_WS_VARIANT": "2"}, {"HRMGPU_WS_VARIANT": "3"}])
 def test_ws_equals_one_surface_kernel(env, monkeypatch):
     """Same intervals (bit for bit: both kernels evaluate the same FMA sequence on the same tables? no -- the tables are built
     slightly differently, so: same hit decisions, <= 1e-9 on end points) and the same free segments as the classic kernel; with

@@ -28,6 +28,17 @@ for rep in range(3):
     print("rep", rep, "kernel ms", ctx.last_minksweep_ms())
 out = np.zeros((n_cta, 8), dtype=np.int64)
 lib.hrmgpu_debug_phase_times(ctx.h, 1, n_cta, out.ctypes.data_as(C.c_void_p))
+if not os.environ.get("HRMGPU_CLASSIC"):
+    # warp-specialised persistent kernel: one row per resident CTA, cycles of thread 0 of each role summed over its surfaces
+    names = ["C: cell tests (+ heavy)", "P: wait (inputs + consumers)", "P: tables", "P: phase A", "C: wait for producers", "C: scan",
+             "C: phase D", "surfaces"]
+    rows_ = out[out[:, 7] > 0]
+    print("resident CTAs", len(rows_), "surfaces", rows_[:, 7].sum())
+    for i, nm in enumerate(names):
+        v = rows_[:, i] / (rows_[:, 7] if i < 7 else 1)
+        print("   %-30s per surface: mean %10.1f  p50 %10.1f  max %10.1f" % (nm, v.mean(), np.percentile(v, 50), v.max()))
+    ctx.close()
+    sys.exit(0)
 names = ["prologue", "phase A", "scan + tests", "of which C", "max B1 (warp)", "prologue: loads", "max D (thread)", "total"]
 arena = (np.arange(n_cta) % (wl.N_OBS + 1)) == 0
 for label, sel in (("obstacle CTAs", ~arena), ("arena CTAs", arena)):
