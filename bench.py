@@ -55,13 +55,13 @@ def workload_config(layers, builds_per_step, n_obs=wl.N_OBS):
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the CPU oracle (the reference itself cannot be compiled here: no Eigen)
 # ------------------------------------------------------------------------------------------------
-def cpu_layers_per_s(n_obs_sample, layers, threads):
+def cpu_layers_per_s(n_obs_sample, layers, threads, fast=False):
     from oracle import hrmo
 
     rows = wl.scene_rows12(wl.N_OBS)[: 1 + n_obs_sample]
     q = wl.orientations(layers, seed=wl.SEED + 7).reshape(layers, 1, 4)
     off = np.zeros((layers, 1, 3))
-    sec, _ = hrmo.time_layers3d(1, n_obs_sample, rows, wl.N_GRID, np.array(wl.BODY_SEMI), q, off, wl.LIM, wl.LX, wl.LY, threads=threads)
+    sec, _ = hrmo.time_layers3d(1, n_obs_sample, rows, wl.N_GRID, np.array(wl.BODY_SEMI), q, off, wl.LIM, wl.LX, wl.LY, threads=threads, fast=fast)
     frac = (1 + n_obs_sample) / float(1 + wl.N_OBS)  # share of one full layer's surfaces in the sample
     return layers * frac / sec, sec
 
@@ -77,6 +77,12 @@ def cpu_baseline_block(n_obs):
     cpu["single_core"] = {"value": v1, "unit": UNIT, "cores": 1,
                           "sample": "1 layer over the arena + first 124 obstacles (125/1001 of a layer's surfaces), %.1f s, scaled "
                                     "to full-layer equivalents" % sec1}
+    # SURVEY.md §8(d) asks for both builds: `faithful` above keeps the reference's operation counts, `fast` hoists the loop-invariant
+    # work (power function on n instead of n^2 values, mesh bounding boxes once per mesh); results are bit-identical
+    vf, secf = cpu_layers_per_s(wl.N_OBS if n_obs == wl.N_OBS else n_obs, threads, threads, fast=True)
+    cpu["fast"] = {"value": vf, "unit": UNIT, "cores": threads, "kind": "port (hoisted build, -DHRMO_FAST)",
+                   "sample": "%d full layers (1 per host thread), %.1f s" % (threads, secf)}
+    cpu["build"] = "faithful"
     return cpu
 
 

@@ -18,10 +18,24 @@ _ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
 def build(force=False):
     so = os.path.join(_HERE, "libhrm_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".hpp", ".cpp"))]
-    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+    fast = os.path.join(_HERE, "libhrm_oracle_fast.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".hpp", ".cpp")) and not f.startswith("ref_")]
+    if force or not os.path.exists(so) or not os.path.exists(fast) or any(os.path.getmtime(s) > min(os.path.getmtime(so), os.path.getmtime(fast)) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return so
+
+
+_FAST = None
+
+
+def fast_lib():
+    """The hoisted build (libhrm_oracle_fast.so, -DHRMO_FAST): same results, loop-invariant work done once."""
+    global _FAST
+    if _FAST is None:
+        build()
+        _FAST = C.CDLL(os.path.join(_HERE, "libhrm_oracle_fast.so"))
+        _FAST.hrmo_time_layers3d.restype = C.c_double
+    return _FAST
 
 
 def lib():
@@ -196,6 +210,54 @@ def free_segments(alo, aup, olo, oup, cap=1 << 16):
     return off, xL[:tot].copy(), xU[:tot].copy(), xM[:tot].copy()
 
 
+def interval_op(op, a, b=None, impl="oracle"):
+    """Interval::unions ("unions"), intersects, complements on lists of (start, end) pairs.  impl = "oracle" runs the
+    restatement, impl = "reference" the reference's own object code (oracle/_ref/libhrm_ref.so, see oracle/ref_build.mk)."""
+    code = {"unions": 0, "intersects": 1, "complements": 2}[op]
+    a = _d(a).reshape(-1, 2)
+    b = _d(b if b is not None else np.zeros((0, 2))).reshape(-1, 2)
+    cap = 2 * (len(a) + len(b)) + 4
+    out = np.zeros((cap, 2))
+    fn = lib().hrmo_interval_op if impl == "oracle" else ref_lib().hrmref_interval_op
+    n = fn(C.c_int(code), _p(a), C.c_int(len(a)), _p(b), C.c_int(len(b)), _p(out), C.c_int(cap))
+    assert 0 <= n <= cap
+    return out[:n].copy()
+
+
+_REF = None
+
+
+def ref_path():
+    return os.path.join(_HERE, "_ref", "libhrm_ref.so")
+
+
+def build_ref(reference="/root/reference"):
+    """Compiles the reference's own Interval.cpp / Parse2dCsvFile.cpp into oracle/_ref (only where the reference tree exists:
+    in the build container; the GPU box receives the prebuilt library with the repo snapshot)."""
+    if os.path.isdir(reference):
+        subprocess.check_call(["make", "-s", "-f", os.path.join("oracle", "ref_build.mk"), "REF=" + reference], cwd=os.path.dirname(_HERE))
+    return ref_path() if os.path.exists(ref_path()) else None
+
+
+def ref_lib():
+    global _REF
+    if _REF is None:
+        if not os.path.exists(ref_path()):
+            raise RuntimeError("oracle/_ref/libhrm_ref.so not built (make -f oracle/ref_build.mk needs /root/reference)")
+        _REF = C.CDLL(ref_path())
+        _REF.hrmref_parse_csv.restype = C.c_long
+    return _REF
+
+
+def ref_parse_csv(filename, stride=64, cap_rows=1 << 16):
+    """hrm::parse2DCsvFile of the reference's own object code: list of rows."""
+    out = np.zeros((cap_rows, stride))
+    row_len = np.zeros(cap_rows, dtype=np.int32)
+    n = ref_lib().hrmref_parse_csv(filename.encode(), _p(out), C.c_int(stride), _p(row_len), C.c_long(cap_rows))
+    assert n <= cap_rows
+    return [out[r, : row_len[r]].copy() for r in range(n)]
+
+
 def robot3d_body_poses(robot_rows, q):
     robot_rows = _d(robot_rows)
     B = robot_rows.shape[0]
@@ -213,7 +275,7 @@ def robot2d_body_poses(robot_rows, theta):
     return ba, bo
 
 
-def layer3d(n_arena, n_obs, sq, n, body_semi, body_quat, body_off, lim, Lx, Ly, want_bound=True, seg_cap=1 << 18):
+def layer3d(n_arena, n_obs, sq, n, body_semi, body_quat, body_off, lim, Lx, Ly, want_bound=True, seg_cap=1 << 18, fast=False):
     """One 3D C-layer. Returns dict(bound[S,3,M], lo[L,S], up[L,S], off[L+1], xL, xU, xM, single_hits)."""
     sq, body_semi, body_quat, body_off, lim = _d(sq), _d(body_semi), _d(body_quat), _d(body_off), _d(lim)
     B = body_semi.shape[0]
@@ -225,7 +287,7 @@ def layer3d(n_arena, n_obs, sq, n, body_semi, body_quat, body_off, lim, Lx, Ly, 
     off = np.zeros(L + 1, dtype=np.int32)
     xL, xU, xM = np.zeros(seg_cap), np.zeros(seg_cap), np.zeros(seg_cap)
     sh = C.c_long(0)
-    tot = lib().hrmo_layer3d(C.c_int(n_arena), C.c_int(n_obs), _p(sq), C.c_int(n), C.c_int(B), _p(body_semi), _p(body_quat),
+    tot = (fast_lib() if fast else lib()).hrmo_layer3d(C.c_int(n_arena), C.c_int(n_obs), _p(sq), C.c_int(n), C.c_int(B), _p(body_semi), _p(body_quat),
                              _p(body_off), _p(lim), C.c_int(Lx), C.c_int(Ly), _p(bound), _p(lo), _p(up), _p(off), _p(xL), _p(xU),
                              _p(xM), C.c_int(seg_cap), C.byref(sh))
     assert 0 <= tot <= seg_cap, tot
@@ -296,12 +358,12 @@ def layer2d(n_arena, n_obs, se, num, body_semi, body_angle, body_off, lim, Ly, s
     }
 
 
-def time_layers3d(n_arena, n_obs, sq, n, body_semi, body_quat, body_off, lim, Lx, Ly, threads=1):
-    """CPU baseline: seconds to build K layers (body_quat [K,B,4], body_off [K,B,3])."""
+def time_layers3d(n_arena, n_obs, sq, n, body_semi, body_quat, body_off, lim, Lx, Ly, threads=1, fast=False):
+    """CPU baseline: seconds to build K layers (body_quat [K,B,4], body_off [K,B,3]); fast = the hoisted build."""
     sq, body_semi, body_quat, body_off, lim = _d(sq), _d(body_semi), _d(body_quat), _d(body_off), _d(lim)
     K, B = body_quat.shape[0], body_quat.shape[1]
     cs = C.c_long(0)
-    sec = lib().hrmo_time_layers3d(C.c_int(n_arena), C.c_int(n_obs), _p(sq), C.c_int(n), C.c_int(B), _p(body_semi), _p(body_quat),
+    sec = (fast_lib() if fast else lib()).hrmo_time_layers3d(C.c_int(n_arena), C.c_int(n_obs), _p(sq), C.c_int(n), C.c_int(B), _p(body_semi), _p(body_quat),
                                    _p(body_off), _p(lim), C.c_int(Lx), C.c_int(Ly), C.c_int(K), C.c_int(threads), C.byref(cs))
     return sec, cs.value
 

@@ -168,6 +168,23 @@ int hrmo_seg_polygon(const double* bound, int num, const double s1[2], const dou
     return isIntersectSegPolygon2D(s1, s2, p) ? 1 : 0;
 }
 
+// Interval algebra of the restatement alone (Interval.cpp:10-100), same calling convention as oracle/ref_shim.cpp so that
+// tests/test_ref_pin.py can run both on the same inputs.  op: 0 unions(a), 1 intersects(a), 2 complements(a = outer, b = inner).
+int hrmo_interval_op(int op, const double* a, int na, const double* b, int nb, double* out, int cap) {
+    auto make = [](const double* se, int n) {
+        std::vector<Interval> v;
+        for (int i = 0; i < n; ++i) v.push_back(Interval{se[2 * i], se[2 * i + 1]});
+        return v;
+    };
+    std::vector<Interval> r;
+    if (op == 0) r = unions(make(a, na));
+    else if (op == 1) r = intersects(make(a, na));
+    else r = complements(make(a, na), make(b, nb));
+    const int n = static_cast<int>(r.size());
+    for (int i = 0; i < n && i < cap; ++i) out[2 * i] = r[i].s, out[2 * i + 1] = r[i].e;
+    return n;
+}
+
 // Free segments of one sweep plane from interval tables (Interval algebra + enhanceFreeSegment).
 // lo/up are [Ly][Sa] arena and [Ly][So] obstacle tables. Output CSR over the Ly lines.
 int hrmo_free_segments(int Ly, int Sa, int So, const double* alo, const double* aup, const double* olo, const double* oup,

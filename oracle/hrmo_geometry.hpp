@@ -82,14 +82,29 @@ struct SuperQuadrics {
     int getNum() const { return num * num; }
     int getNumParam() const { return num; }
 
+    // The power function on the n x n parameter grid.  Faithful build: evaluated on all n^2 entries per call, like the
+    // reference's exponentialFunctionMatrixForm on eta_ / omega_ (ExponentialFunction.cpp:12-25).  HRMO_FAST build ("hoisted",
+    // SURVEY.md §8d): the grids are replications of n values, so n evaluations are replicated -- bit-identical values.
+    std::vector<double> powerGrid(bool alongEta, double power, bool isSine) const {
+#ifdef HRMO_FAST
+        const std::vector<double> v = exponentialFunctionMatrixForm(alongEta ? etaLin : omegaLin, power, isSine);
+        std::vector<double> out(static_cast<size_t>(num) * num);
+        for (int c = 0; c < num; ++c)
+            for (int r = 0; r < num; ++r) out[static_cast<size_t>(c) * num + r] = alongEta ? v[c] : v[r];
+        return out;
+#else
+        return exponentialFunctionMatrixForm(alongEta ? eta : omega, power, isSine);
+#endif
+    }
+
     // SuperQuadrics.cpp:46-81
     Points getOriginShape() const {
         const int M = num * num;
-        const std::vector<double> ce1 = exponentialFunctionMatrixForm(eta, epsilon[0], false);
-        const std::vector<double> cw2 = exponentialFunctionMatrixForm(omega, epsilon[1], false);
-        const std::vector<double> ce1b = exponentialFunctionMatrixForm(eta, epsilon[0], false);
-        const std::vector<double> sw2 = exponentialFunctionMatrixForm(omega, epsilon[1], true);
-        const std::vector<double> se1 = exponentialFunctionMatrixForm(eta, epsilon[0], true);
+        const std::vector<double> ce1 = powerGrid(true, epsilon[0], false);
+        const std::vector<double> cw2 = powerGrid(false, epsilon[1], false);
+        const std::vector<double> ce1b = powerGrid(true, epsilon[0], false);
+        const std::vector<double> sw2 = powerGrid(false, epsilon[1], true);
+        const std::vector<double> se1 = powerGrid(true, epsilon[0], true);
         const Mat3 R = quat_to_rot(quat);
         Points out;
         out.dim = 3;
@@ -117,11 +132,11 @@ struct SuperQuadrics {
         const Mat3 Tinv = mul_diag(R2, semiB) * transpose(R2);  // :115
 
         // :118-135 gradient, matrix-form power function evaluated per call like the reference
-        const std::vector<double> ce = exponentialFunctionMatrixForm(eta, 2 - eps1, false);
-        const std::vector<double> cw = exponentialFunctionMatrixForm(omega, 2 - eps2, false);
-        const std::vector<double> ceb = exponentialFunctionMatrixForm(eta, 2 - eps1, false);
-        const std::vector<double> sw = exponentialFunctionMatrixForm(omega, 2 - eps2, true);
-        const std::vector<double> se = exponentialFunctionMatrixForm(eta, 2 - eps1, true);
+        const std::vector<double> ce = powerGrid(true, 2 - eps1, false);
+        const std::vector<double> cw = powerGrid(false, 2 - eps2, false);
+        const std::vector<double> ceb = powerGrid(true, 2 - eps1, false);
+        const std::vector<double> sw = powerGrid(false, 2 - eps2, true);
+        const std::vector<double> se = powerGrid(true, 2 - eps1, true);
 
         // :137-140  (K*Tinv*Tinv*R1*gradPhi) ./ ||Tinv*R1*gradPhi||, products associated left to right
         const Mat3 M2 = (scale(static_cast<double>(K), Tinv) * Tinv) * R1;
@@ -225,6 +240,10 @@ struct MeshMatrix {
     std::vector<double> faces;  // F x 3, stored as doubles like the reference, row-major here
     int numFaces = 0;
     int f(int i, int c) const { return static_cast<int>(faces[static_cast<size_t>(i) * 3 + c]); }
+#ifdef HRMO_FAST
+    mutable bool bboxKnown = false;  // HRMO_FAST: the per-call maxCoeff / minCoeff scans of LineIntersection.cpp:12-30,58-65 once per mesh
+    mutable double bbox[3][2];
+#endif
 };
 
 inline MeshMatrix getMeshFromParamSurface(const Points& surfBound, int n) {
@@ -291,13 +310,26 @@ inline void rowMinMax(const Points& p, int row, double& mn, double& mx) {
     }
 }
 
+// Bounding box of a mesh along one axis: scanned per call like the reference, or (HRMO_FAST) once per mesh -- same values.
+inline void meshMinMax(const MeshMatrix& shape, int row, double& mn, double& mx) {
+#ifdef HRMO_FAST
+    if (!shape.bboxKnown) {
+        for (int r = 0; r < 3; ++r) rowMinMax(shape.vertices, r, shape.bbox[r][0], shape.bbox[r][1]);
+        shape.bboxKnown = true;
+    }
+    mn = shape.bbox[row][0], mx = shape.bbox[row][1];
+#else
+    rowMinMax(shape.vertices, row, mn, mx);
+#endif
+}
+
 // LineIntersection.cpp:56-124 — first two hits in FACE-INDEX order (SURVEY.md finding 2).
 inline std::vector<Vec3> intersectVerticalLineMesh3D(const Line3D& line, const MeshMatrix& shape) {
     std::vector<Vec3> points;
     double mn, mx;
-    rowMinMax(shape.vertices, 0, mn, mx);
+    meshMinMax(shape, 0, mn, mx);
     if (line.v[0] > mx || line.v[0] < mn) return points;
-    rowMinMax(shape.vertices, 1, mn, mx);
+    meshMinMax(shape, 1, mn, mx);
     if (line.v[1] > mx || line.v[1] < mn) return points;
     Vec3 pt;
     const Points& V = shape.vertices;
@@ -326,7 +358,7 @@ inline std::vector<Vec3> intersectLineMesh3D(const Line3D& line, const MeshMatri
         const double di = line.v[3 + i];
         if (std::fabs(di) < 1e-6) {
             double mn, mx;
-            rowMinMax(shape.vertices, i, mn, mx);
+            meshMinMax(shape, i, mn, mx);
             if (line.v[i] > mx || line.v[i] < mn) return points;
         }
     }

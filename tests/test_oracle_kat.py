@@ -306,3 +306,21 @@ def test_refinement_solves_when_first_roadmap_does_not(oracle):
     assert np.array_equal(refined["vertex"][:nv], first["vertex"])  # the first roadmap is kept, refinement only appends
     assert np.array_equal(refined["edge"][: len(first["edge"])], first["edge"])
     assert len(refined["vertex"]) > nv
+
+
+def test_hoisted_oracle_build_is_bit_identical(oracle):
+    """oracle/libhrm_oracle_fast.so (-DHRMO_FAST: power function on n values instead of the n x n grids, mesh bounding boxes once
+    per mesh -- the `fast` CPU baseline of SURVEY.md §8d) against the faithful build: every point, interval and segment equal."""
+    from tests import util
+
+    rows = util.synthetic_scene3d(9, 12)
+    rng = np.random.default_rng(9)
+    robot = [[10, 5, 4, 1, 1, 0, 0, 0, 1, 0, 0, 0], [6, 3, 2, 1, 1, -7, 0, 4, 0.70710599, 0, 0.70710802, 0]]
+    semi, R, off, quat = util.body_poses3d(robot, util.random_unit_quats(rng, 2))
+    lim = [-58.0, 58.0, -28.0, 28.0, -18.0, 18.0]
+    for k in range(2):
+        a = oracle.layer3d(1, 12, rows, 18, semi, quat[k], off[k], lim, 12, 6)
+        b = oracle.layer3d(1, 12, rows, 18, semi, quat[k], off[k], lim, 12, 6, fast=True)
+        assert a["single_hits"] == b["single_hits"] and a["off"][-1] > 0
+        for key in ("bound", "lo", "up", "off", "xL", "xU", "xM"):
+            assert np.array_equal(a[key], b[key], equal_nan=True), key
