@@ -373,21 +373,32 @@ class FreeSpaceGPU {
     /** setup(numLine, low, up) of the reference + the sweep grids of sweepLineProcess */
     void setup(const std::vector<Coordinate>& boundaryLimits, Index numLineX, Index numLineY) {
         check(hrmgpu_set_sweep(ctx_, boundaryLimits.data(), static_cast<int>(numLineX), static_cast<int>(numLineY)));
+        lim_ = boundaryLimits, Lx_ = numLineX, Ly_ = numLineY;
+    }
+    /** the sweep-line coordinates of HRM3D::sweepLineProcess (HRM3D.cpp:66-81): t_i = lo + double(i) * d */
+    void sweepGrid(std::vector<Coordinate>& tx, std::vector<Coordinate>& ty) const {
+        tx.assign(Lx_, 0.0), ty.assign(Ly_, 0.0);
+        if (lim_.size() >= 6) {
+            const double dx = (lim_[1] - lim_[0]) / static_cast<double>(Lx_ - 1), dy = (lim_[3] - lim_[2]) / static_cast<double>(Ly_ - 1);
+            for (Index i = 0; i < Lx_; ++i) tx[i] = lim_[0] + static_cast<double>(i) * dx;
+            for (Index i = 0; i < Ly_; ++i) ty[i] = lim_[2] + static_cast<double>(i) * dy;
+        }
     }
     /** refinement (HighwayRoadMap-inl.h:178-215): sweep + free segments of all built layers redone on their cached boundaries */
     void resweep(const std::vector<Coordinate>& boundaryLimits, Index numLineX, Index numLineY) {
         check(hrmgpu_resweep(ctx_, boundaryLimits.data(), static_cast<int>(numLineX), static_cast<int>(numLineY)));
+        lim_ = boundaryLimits, Lx_ = numLineX, Ly_ = numLineY;
     }
     /** getCSpaceBoundary() of layer k */
     BoundaryInfo getCSpaceBoundary(int k) {
         long long d[8];
         check(hrmgpu_get_dims(ctx_, d));
         BoundaryInfo out;
-        for (int s = 0; s < d[2]; ++s) {
-            BoundaryPoints p(static_cast<size_t>(d[7] * d[5]));
-            check(hrmgpu_get_boundary(ctx_, k, s, p.data()));
-            (s < d[3] ? out.arena : out.obstacle).push_back(std::move(p));
-        }
+        const size_t per = static_cast<size_t>(d[7] * d[5]);
+        std::vector<double> all(per * static_cast<size_t>(d[2]));
+        check(hrmgpu_get_boundary_layer(ctx_, k, all.data()));  // one device transpose + one copy for the whole layer
+        for (int s = 0; s < d[2]; ++s)
+            (s < d[3] ? out.arena : out.obstacle).emplace_back(all.begin() + static_cast<std::ptrdiff_t>(per * s), all.begin() + static_cast<std::ptrdiff_t>(per * (s + 1)));
         return out;
     }
     /** all free segments of the last build: global CSR over (layer, line) */
@@ -441,12 +452,14 @@ class FreeSpaceGPU {
     /** {K, B, S, n_arena, L, M, total segments, dim} of the last build (hrmgpu_get_dims) */
     void dims(long long d[8]) { check(hrmgpu_get_dims(ctx_, d)); }
     hrmgpu_ctx* handle() { return ctx_; }
-
-  protected:
     void check(int rc) {
         if (rc < 0) throw std::runtime_error(std::string("hrmgpu: ") + hrmgpu_last_error(ctx_));
     }
+
+  protected:
     hrmgpu_ctx* ctx_ = nullptr;
+    std::vector<Coordinate> lim_;
+    Index Lx_ = 0, Ly_ = 0;
 };
 
 class FreeSpaceGPU3D : public FreeSpaceGPU {
@@ -490,6 +503,85 @@ class FreeSpaceGPU3D : public FreeSpaceGPU {
             }
         check(hrmgpu_build_bridge(ctx_, static_cast<int>(tfe.size()), static_cast<int>(tfe.at(0).size()), semi.data(), R.data(), precision));
     }
+};
+
+struct IntersectionInterval {  // include/hrm/datastructure/FreeSpace.h:14-26: [line][surface] tables of one sweep plane
+    std::vector<std::vector<Coordinate>> arenaLow, arenaUpp, obstacleLow, obstacleUpp;
+};
+
+/** One C-layer of a FreeSpaceGPU3D build behind the reference's per-layer FreeSpaceComputator / FreeSpace3D method set
+ *  (FreeSpace.h:45-128, FreeSpace3D.h:29-55), in the call order of HRM3D::constructOneSlice / sweepLineProcess (HRM3D.cpp:24-54,63-91):
+ *      computeCSpaceBoundary(); getCSpaceBoundary(); computeCSpaceBoundaryMesh(b); getCSpaceBoundaryMesh();
+ *      for every x-plane: computeIntersectionInterval({tx, ty}); computeFreeSegment(ty); getFreeSegment();
+ *  The arithmetic already ran for ALL layers in FreeSpaceGPU3D::buildLayers(); these methods hand out that layer's cached results
+ *  (fetched from the device once, on first use), so the reference's planner loop can run on top of it unchanged. */
+class FreeSpaceLayer3D {
+  public:
+    FreeSpaceLayer3D(FreeSpaceGPU3D& fs, int layer) : fs_(fs), k_(layer) { fs_.dims(d_); }
+    void computeCSpaceBoundary() {}                                    // (done for all layers by buildLayers)
+    const BoundaryInfo& getCSpaceBoundary() {
+        if (bound_.arena.empty() && bound_.obstacle.empty()) bound_ = fs_.getCSpaceBoundary(k_);
+        return bound_;
+    }
+    void computeCSpaceBoundaryMesh(const BoundaryInfo&) {}            // (the mesh connectivity is implicit on the device)
+    /** tLine = {tx, ty} as the reference passes it: the x-plane is tx.back() (FreeSpace3D.cpp:29-33) */
+    void computeIntersectionInterval(const std::vector<std::vector<Coordinate>>& tLine) {
+        fetch();
+        plane_ = planeOf(tLine.at(0).back());
+        const int Ly = static_cast<int>(ty_.size()), S = static_cast<int>(d_[2]), Sa = static_cast<int>(d_[3]);
+        auto fill = [&](std::vector<std::vector<Coordinate>>& t, const std::vector<double>& src, int s0, int s1) {
+            t.assign(static_cast<size_t>(Ly), std::vector<Coordinate>(static_cast<size_t>(s1 - s0)));
+            for (int iy = 0; iy < Ly; ++iy)
+                for (int s = s0; s < s1; ++s) t[iy][s - s0] = src[(static_cast<size_t>(plane_) * Ly + iy) * S + s];
+        };
+        fill(intersect_.arenaLow, lo_, 0, Sa), fill(intersect_.arenaUpp, up_, 0, Sa);
+        fill(intersect_.obstacleLow, lo_, Sa, S), fill(intersect_.obstacleUpp, up_, Sa, S);
+    }
+    const IntersectionInterval& getIntersectionInterval() const { return intersect_; }
+    /** free segments of the plane selected by the last computeIntersectionInterval (FreeSpace-inl.h:63-97 incl. enhanceFreeSegment) */
+    void computeFreeSegment(const std::vector<Coordinate>& ty) {
+        fetch();
+        const size_t Ly = ty_.size();
+        segment_.ty = ty;
+        segment_.xL.assign(Ly, {}), segment_.xU.assign(Ly, {}), segment_.xM.assign(Ly, {});
+        for (size_t iy = 0; iy < Ly; ++iy) {
+            const size_t l = static_cast<size_t>(plane_) * Ly + iy;
+            segment_.xL[iy].assign(xL_.begin() + off_[l], xL_.begin() + off_[l + 1]);
+            segment_.xU[iy].assign(xU_.begin() + off_[l], xU_.begin() + off_[l + 1]);
+            segment_.xM[iy].assign(xM_.begin() + off_[l], xM_.begin() + off_[l + 1]);
+        }
+    }
+    const FreeSegment2D& getFreeSegment() const { return segment_; }
+    const std::vector<Coordinate>& tx() { fetch(); return tx_; }
+    const std::vector<Coordinate>& ty() { fetch(); return ty_; }
+
+  private:
+    void fetch() {
+        if (!off_.empty()) return;
+        const int L = static_cast<int>(d_[4]), S = static_cast<int>(d_[2]);
+        lo_.resize(static_cast<size_t>(L) * S), up_.resize(static_cast<size_t>(L) * S);
+        fs_.check(hrmgpu_get_intervals(fs_.handle(), k_, lo_.data(), up_.data()));
+        off_.resize(static_cast<size_t>(L) + 1);
+        const int cnt = hrmgpu_get_segments(fs_.handle(), k_, off_.data(), nullptr, nullptr, nullptr, 0);
+        fs_.check(cnt < 0 ? cnt : 0);
+        xL_.resize(static_cast<size_t>(cnt)), xU_.resize(static_cast<size_t>(cnt)), xM_.resize(static_cast<size_t>(cnt));
+        if (cnt > 0) fs_.check(hrmgpu_get_segments(fs_.handle(), k_, off_.data(), xL_.data(), xU_.data(), xM_.data(), cnt) < 0 ? -1 : 0);
+        fs_.sweepGrid(tx_, ty_);
+    }
+    int planeOf(Coordinate x) const {
+        for (size_t i = 0; i < tx_.size(); ++i)
+            if (tx_[i] == x) return static_cast<int>(i);
+        throw std::invalid_argument("computeIntersectionInterval: x is not a sweep plane of the grid given to setup()");
+    }
+    FreeSpaceGPU3D& fs_;
+    int k_;
+    long long d_[8];
+    int plane_ = 0;
+    BoundaryInfo bound_;
+    IntersectionInterval intersect_;
+    FreeSegment2D segment_;
+    std::vector<double> lo_, up_, xL_, xU_, xM_, tx_, ty_;
+    std::vector<int> off_;
 };
 
 class FreeSpaceGPU2D : public FreeSpaceGPU {
@@ -654,8 +746,10 @@ class HighwayRoadMapBase {
         : start_(req.start), goal_(req.goal), param_(req.parameters), precision_(precision), perOrientation_(perOrientation) {}
     virtual ~HighwayRoadMapBase() = default;
 
-    /** HighwayRoadMap-inl.h:65-89 (no refinement loop: the reference's refinement throws, SURVEY.md finding 6) */
-    virtual void plan(double /*timeLim*/ = 0.0) {
+    /** HighwayRoadMap-inl.h:65-89: build, search, then -- exactly like the reference -- refine the roadmap while it is unsolved and
+     *  the planning time is below timeLim (:78-81).  setMaxRefine(rounds) is an ADDITIONAL bound (default: none) that makes runs
+     *  reproducible for the parity tests; it never replaces the time limit. */
+    virtual void plan(double timeLim = 0.0) {
         auto t0 = std::chrono::high_resolution_clock::now();
         buildRoadmap();
         res_.planningTime.buildTime = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
@@ -663,15 +757,15 @@ class HighwayRoadMapBase {
         search();
         stage_.add("search", std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count());
         res_.planningTime.searchTime = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
-        // HighwayRoadMap-inl.h:78-81: refine while unsolved (the reference is bounded by the time limit only; here also by a
-        // round count so that runs are reproducible -- 0 rounds by default, like a reference run that solves at once)
-        while (!res_.solved && numRefineDone_ < maxRefine_) {
+        res_.planningTime.totalTime = res_.planningTime.buildTime + res_.planningTime.searchTime;
+        // HighwayRoadMap-inl.h:78-81
+        while (!res_.solved && res_.planningTime.totalTime < timeLim && numRefineDone_ < maxRefine_) {
             t0 = std::chrono::high_resolution_clock::now();
             refineExistRoadmap();
             ++numRefineDone_;
             res_.planningTime.buildTime += std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+            res_.planningTime.totalTime = res_.planningTime.buildTime + res_.planningTime.searchTime;
         }
-        res_.planningTime.totalTime = res_.planningTime.buildTime + res_.planningTime.searchTime;
         if (res_.solved) {
             const size_t pose = res_.graphStructure.vertex.at(0).size();
             start_.resize(pose), goal_.resize(pose);
@@ -756,7 +850,7 @@ class HighwayRoadMapBase {
     bool perOrientation_;
     long numEdgeTests_ = 0;
     StageTimes stage_;
-    size_t maxRefine_ = 0, numRefineDone_ = 0;
+    size_t maxRefine_ = static_cast<size_t>(-1), numRefineDone_ = 0;  // (no round bound unless setMaxRefine is called)
     std::vector<std::vector<std::pair<Index, Index>>> vertexIdxAll_;  // vertexIdx_ of the previous refinement rounds
 
     /** connectExistSlice (HRM3D.cpp:226-270, HRM2D.cpp:158-197): vertices of the refined layer against the same layer's

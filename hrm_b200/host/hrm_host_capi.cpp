@@ -67,9 +67,74 @@ int hrmhost_plan3d(int n_arena, int n_obs, const double* sq, int n, int B, const
         req.goal.assign(goal, goal + 7);
         planners::HRM3D hrm(rb, arena, obs, req, device, precision, per_orientation != 0);
         hrm.setMaxRefine(static_cast<size_t>(g_max_refine));
-        hrm.plan();
+        hrm.plan(g_max_refine > 0 ? 3600.0 : 0.0);  // the parity tests bound refinement by rounds; the time limit only has to be generous
         exportResult(hrm, info, vertex, cap_v, 7, edge, cap_e, path, cap_p);
         info[4] = static_cast<long>(hrm.numRefineDone());
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+// The reference's per-layer call sequence (HRM3D.cpp:24-54,63-91) on a FreeSpaceLayer3D view of every built layer: per x-plane
+// computeIntersectionInterval({tx, ty}) -> computeFreeSegment(ty) -> getFreeSegment().  Outputs, per layer, what the oracle's
+// layer3d returns: lo / up [K][L][S], CSR off [K][L+1] and xL / xU / xM (capacity cap per layer, counts in cnt[K]).
+int hrmhost_layer_views3d(int n_arena, int n_obs, const double* sq, int n, int B, const double* robot, int K, const double* quats,
+                          const double* lim, int Lx, int Ly, int precision, int device, double* lo, double* up, int* off, double* xL, double* xU,
+                          double* xM, long cap, long* cnt, double* bound0) {
+    try {
+        std::vector<SuperQuadrics> arena, obs;
+        for (int i = 0; i < n_arena; ++i) arena.push_back(sqFromRow(sq + 12 * i, n));
+        for (int i = 0; i < n_obs; ++i) obs.push_back(sqFromRow(sq + 12 * (n_arena + i), n));
+        MultiBodyTree3D rb(sqFromRow(robot, n));
+        for (int b = 1; b < B; ++b) rb.addBody(sqFromRow(robot + 12 * b, n));
+        std::vector<MultiBodyTree3D> poses;
+        for (int k = 0; k < K; ++k) {
+            MultiBodyTree3D r = rb;
+            SE3Transform g;
+            g.R = toRotationMatrix(Quaternion{quats[4 * k], quats[4 * k + 1], quats[4 * k + 2], quats[4 * k + 3]});
+            r.robotTF(g);
+            poses.push_back(r);
+        }
+        FreeSpaceGPU3D fs(arena, obs, device);
+        fs.setup(std::vector<Coordinate>(lim, lim + 6), static_cast<Index>(Lx), static_cast<Index>(Ly));
+        fs.buildLayers(poses, precision);
+        const int S = (n_arena + n_obs) * B, Sa = n_arena * B, L = Lx * Ly;
+        for (int k = 0; k < K; ++k) {
+            FreeSpaceLayer3D layer(fs, k);
+            layer.computeCSpaceBoundary();
+            const BoundaryInfo& b = layer.getCSpaceBoundary();
+            layer.computeCSpaceBoundaryMesh(b);
+            if (k == 0 && bound0) {
+                size_t at = 0;
+                for (const auto* grp : {&b.arena, &b.obstacle})
+                    for (const auto& p : *grp) std::copy(p.begin(), p.end(), bound0 + at), at += p.size();
+            }
+            const std::vector<Coordinate> ty = layer.ty();
+            long tot = 0;
+            std::vector<Coordinate> txSoFar;
+            for (int ix = 0; ix < Lx; ++ix) {
+                txSoFar.push_back(layer.tx()[ix]);  // the reference grows tx plane by plane and sweeps at tx.back()
+                layer.computeIntersectionInterval({txSoFar, ty});
+                layer.computeFreeSegment(ty);
+                const IntersectionInterval& iv = layer.getIntersectionInterval();
+                const FreeSegment2D& seg = layer.getFreeSegment();
+                for (int iy = 0; iy < Ly; ++iy) {
+                    const size_t l = static_cast<size_t>(ix) * Ly + iy, base = (static_cast<size_t>(k) * L + l) * S;
+                    for (int s = 0; s < Sa; ++s) lo[base + s] = iv.arenaLow[iy][s], up[base + s] = iv.arenaUpp[iy][s];
+                    for (int s = Sa; s < S; ++s) lo[base + s] = iv.obstacleLow[iy][s - Sa], up[base + s] = iv.obstacleUpp[iy][s - Sa];
+                    off[static_cast<size_t>(k) * (L + 1) + l] = static_cast<int>(tot);
+                    for (size_t j = 0; j < seg.xM[iy].size(); ++j, ++tot)
+                        if (tot < cap) {
+                            const size_t o = static_cast<size_t>(k) * cap + tot;
+                            xL[o] = seg.xL[iy][j], xU[o] = seg.xU[iy][j], xM[o] = seg.xM[iy][j];
+                        }
+                }
+            }
+            off[static_cast<size_t>(k) * (L + 1) + L] = static_cast<int>(tot);
+            cnt[k] = tot;
+        }
         return 0;
     } catch (const std::exception& e) {
         g_err = e.what();
@@ -96,7 +161,7 @@ int hrmhost_plan2d(int n_arena, int n_obs, const double* se, int num, int B, con
         req.goal.assign(goal, goal + 3);
         planners::HRM2D hrm(rb, arena, obs, req, device, precision, per_orientation != 0);
         hrm.setMaxRefine(static_cast<size_t>(g_max_refine));
-        hrm.plan();
+        hrm.plan(g_max_refine > 0 ? 3600.0 : 0.0);  // the parity tests bound refinement by rounds; the time limit only has to be generous
         exportResult(hrm, info, vertex, cap_v, 3, edge, cap_e, path, cap_p);
         info[4] = static_cast<long>(hrm.numRefineDone());
         return 0;

@@ -55,6 +55,28 @@ def plan3d(n_arena, n_obs, sq12, n, robot_rows, quats, lim, Lx, Ly, num_point, s
     return _out(info, vertex, edge, path)
 
 
+def layer_views3d(n_arena, n_obs, sq12, n, robot_rows, quats, lim, Lx, Ly, precision=0, device=0, cap=1 << 16):
+    """Builds one C-layer per quaternion with FreeSpaceGPU3D::buildLayers, then walks every layer through a FreeSpaceLayer3D view in
+    the reference's per-layer call order (computeIntersectionInterval({tx, ty}) -> computeFreeSegment(ty) -> getFreeSegment() per
+    x-plane).  Returns one dict per layer: lo, up [L][S], off [L+1], xL, xU, xM (and bound [S][3][M] for layer 0)."""
+    sq12, robot_rows, quats, lim = _d(sq12), _d(robot_rows), _d(quats).reshape(-1, 4), _d(lim)
+    K, B = quats.shape[0], robot_rows.shape[0]
+    S, L, M = (n_arena + n_obs) * B, Lx * Ly, n * n
+    lo, up = np.zeros((K, L, S)), np.zeros((K, L, S))
+    off = np.zeros((K, L + 1), dtype=np.int32)
+    xL, xU, xM = np.zeros((K, cap)), np.zeros((K, cap)), np.zeros((K, cap))
+    cnt = np.zeros(K, dtype=np.int64)
+    bound0 = np.zeros((S, M, 3))
+    rc = load().hrmhost_layer_views3d(C.c_int(n_arena), C.c_int(n_obs), _p(sq12), C.c_int(n), C.c_int(B), _p(robot_rows), C.c_int(K), _p(quats),
+                                      _p(lim), C.c_int(Lx), C.c_int(Ly), C.c_int(precision), C.c_int(device), _p(lo), _p(up), _p(off), _p(xL),
+                                      _p(xU), _p(xM), C.c_long(cap), _p(cnt), _p(bound0))
+    if rc != 0:
+        raise _err()
+    assert (cnt <= cap).all()
+    return [{"lo": lo[k], "up": up[k], "off": off[k], "xL": xL[k, :cnt[k]].copy(), "xU": xU[k, :cnt[k]].copy(), "xM": xM[k, :cnt[k]].copy(),
+             "bound": np.ascontiguousarray(bound0.transpose(0, 2, 1)) if k == 0 else None} for k in range(K)]
+
+
 def plan2d(n_arena, n_obs, se6, num, robot_rows, num_slice, lim, Ly, num_point, start, goal, per_orientation=False, precision=0, device=0,
            cap_v=1 << 16, cap_e=1 << 20):
     """hrm::planners::HRM2D(robot, arena, obstacle, request).plan()."""

@@ -239,3 +239,26 @@ def test_hrm2d_refinement_identical(oracle, refine_rounds, name, Ly, per_orienta
     assert np.array_equal(got["vertex"], ref["vertex"])
     assert np.array_equal(got["edge"], ref["edge"])
     assert got["solved"] == ref["solved"]
+
+
+def test_free_space_layer_view_follows_the_reference_call_order(oracle):
+    """hrm::FreeSpaceLayer3D (host/hrm_host.hpp) presents one C-layer of a batched GPU build behind the reference's
+    FreeSpaceComputator method set; driven in the order of HRM3D::constructOneSlice / sweepLineProcess (HRM3D.cpp:24-54,63-91) --
+    per x-plane computeIntersectionInterval({tx, ty}), computeFreeSegment(ty), getFreeSegment() -- it must hand out exactly the
+    oracle's boundary points, interval tables and free segments of every layer."""
+    from hrm_b200 import hostlib
+
+    sc = util.scenes()["3D_superquadrics_cluttered_rabbit"]
+    rows = np.array(sc["arena"] + sc["obstacle"])
+    quats = np.array(sc["quats"][:5])
+    got = hostlib.layer_views3d(1, len(sc["obstacle"]), rows, 10, np.array(sc["robot"]), quats, sc["lim"], sc["Lx"], sc["Ly"], precision=0)
+    semi, R, off, bq = util.body_poses3d(sc["robot"], quats)
+    for k in range(5):
+        ref = oracle.layer3d(1, len(sc["obstacle"]), rows, 10, semi, bq[k], off[k], sc["lim"], sc["Lx"], sc["Ly"])
+        assert np.array_equal(got[k]["lo"], ref["lo"], equal_nan=True) and np.array_equal(got[k]["up"], ref["up"], equal_nan=True)
+        assert np.array_equal(got[k]["off"], ref["off"])
+        for key in ("xL", "xU", "xM"):
+            assert np.array_equal(got[k][key], ref[key]), key
+        if k == 0:
+            assert np.array_equal(got[0]["bound"], ref["bound"])
+    assert sum(len(g["xM"]) for g in got) > 100
