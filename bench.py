@@ -312,6 +312,7 @@ def run_gpu(args):
     from hrm_b200 import capi
     from hrm_b200 import dist as hdist
 
+    t_start = time.perf_counter()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -338,6 +339,10 @@ def run_gpu(args):
     L = wl.LX * wl.LY
     line_cap = layers * L
 
+    def stage(msg):  # progress on stderr (HRM_BENCH_VERBOSE=1): where a multi-rank run is, should it ever stall
+        if os.environ.get("HRM_BENCH_VERBOSE"):
+            print("[bench rank %d %.1fs] %s" % (rank, time.perf_counter() - t_start, msg), file=sys.stderr, flush=True)
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -355,6 +360,7 @@ def run_gpu(args):
         ctx.set_scene3d(1, n_obs, wl.scene_rows17(rows12), wl.N_GRID)
         ctx.set_sweep(wl.LIM, wl.LX, wl.LY)
         builds = (warmup + steps) * bps
+        stage("measure(%s): setup" % workload)
         # every build (and every rank) sees different orientations: nothing can be cached across builds
         quats = wl.orientations(builds * layers, seed=wl.SEED + seed_base + 1000 * rank)
         R_all = wl.body_rotations(quats)                                   # [builds*layers][1][9]
@@ -373,10 +379,12 @@ def run_gpu(args):
         build_resident(0)
         tot = ctx.dims()["segments"]
         xcap[0] = int(max_over_ranks(float(tot)) * 1.5) + 4096
+        stage("first build done, capacity %d" % xcap[0])
         for i in range(1, warmup * bps):
             build_resident(i)
         ctx.join()
         barrier()
+        stage("warm-up done")
         ctx.kernel_launches(reset=True)
         ctx.segment_redos(reset=True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -390,6 +398,7 @@ def run_gpu(args):
             barrier()
         launches = ctx.kernel_launches()
         ms = max_over_ranks(e0.elapsed_time(e1))
+        stage("timed region done: %.2f ms" % ms)
         res = {"value": world * layers * bps * steps / (ms * 1e-3), "ms_per_step": ms / steps, "launches": launches, "clocks": clocks.summary(),
                "segment_pass_redos_in_timed_region": ctx.segment_redos()}
 
@@ -416,6 +425,7 @@ def run_gpu(args):
         # end to end through the C ABI with (pinned) HOST buffers, pipelined the way a planner would drive it: H2D of the
         # build's body poses, the build, [the exchange], D2H of its free segments into one of two host buffers while the next
         # build already runs; every build's result is waited for and touched on the host
+        stage("kernel timings done")
         e2e_builds = max(2, min(steps * bps, 12))
         pin_R = torch.tensor(R_all).pin_memory()
         pin_off = torch.tensor(off_all).pin_memory()
@@ -451,6 +461,7 @@ def run_gpu(args):
                       "host_checksum": chk}
         res["allgather_bytes_per_build_per_rank"] = (8 * (2 + line_cap + 1) + 24 * xcap[0]) if world > 1 else 0
         res["rows12"] = rows12
+        stage("e2e done")
         return res
 
     head = measure("scaling", args.steps, args.warmup, 1)
@@ -503,7 +514,8 @@ def run_gpu(args):
         quats = wl.orientations(K, seed=wl.SEED + 77)[k0:k1]
         dR = torch.tensor(wl.body_rotations(quats), dtype=torch.float64, device=dev)
         dO = torch.zeros((k1 - k0, 1, 3), dtype=torch.float64, device=dev)
-        xc = int(head["segments_per_layer"] * layers * 1.5) + 4096
+        # the exchange capacity is part of the collective's size: it has to be the SAME number on every rank
+        xc = int(max_over_ranks(head["segments_per_layer"]) * layers * 1.5) + 4096
 
         def one_pass():
             for a in range(0, k1 - k0, layers):
@@ -512,8 +524,10 @@ def run_gpu(args):
                 ctx.allgather_layers(line_cap, xc)
             ctx.join()
 
+        stage("strong scaling: capacity %d" % xc)
         one_pass()
         barrier()
+        stage("strong scaling: warm-up pass done")
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         one_pass()
@@ -575,7 +589,13 @@ def main():
     ap.add_argument("--obstacles", type=int, default=wl.N_OBS)
     ap.add_argument("--precision", default="f64", choices=["f64", "f64_strict", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--watchdog", type=int, default=int(os.environ.get("HRM_BENCH_WATCHDOG", "1500")),
+                    help="seconds after which a stuck run dumps every thread's Python stack to stderr and exits (0 = off)")
     args = ap.parse_args()
+    if args.watchdog > 0:
+        import faulthandler
+
+        faulthandler.dump_traceback_later(args.watchdog, exit=True)
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3  # timing rule: at least 3 warm-up steps
     if args.impl == "reference":
