@@ -313,6 +313,10 @@ def run_gpu(args):
     from hrm_b200 import dist as hdist
 
     t_start = time.perf_counter()
+    # stdout carries the ONE JSON line and nothing else: libraries that print there (NCCL's version banner) go to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -569,8 +573,10 @@ def run_gpu(args):
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+    sys.stdout.flush()
     if line is not None:
-        print(json.dumps(line))
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    os.close(json_fd)
     return 0
 
 
