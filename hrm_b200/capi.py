@@ -27,9 +27,10 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("HRMGPU_LIB", LIB_PATH)  # (experiment builds of the same library: tools/build_variant.sh)
+    if not os.path.exists(path):
         raise RuntimeError("libhrmgpu.so not built: run `python -m hrm_b200.build` (there is no CPU fallback)")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     vp, i, ll = C.c_void_p, C.c_int, C.c_longlong
     sig = {
         "hrmgpu_abi_version": (i, []),

@@ -185,6 +185,7 @@ int hrmgpu_create(hrmgpu_ctx** out, int device, unsigned flags) {
     if (const char* e = std::getenv("HRMGPU_BUCKET_CAP")) c->bucket_cap_hook = std::atoi(e);
     if (const char* e = std::getenv("HRMGPU_CLASSIC")) c->force_classic = std::atoi(e) != 0;
     if (const char* e = std::getenv("HRMGPU_WS_VARIANT")) c->ws_variant = std::atoi(e);
+    if (const char* e = std::getenv("HRMGPU_WS_GENERIC")) c->ws_generic = std::atoi(e) != 0;
     // test hook of the fused kernel: capacity of a warp's kept-cell list (small values force the multi-round path)
     if (const char* e = std::getenv("HRMGPU_CELL_SEG_CAP")) c->cell_seg_cap = std::atoi(e);
     if (ensure(c, c->counters, 4) != HRMGPU_OK) {

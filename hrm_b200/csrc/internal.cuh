@@ -90,6 +90,7 @@ struct Ctx {
     int bucket_cap_hook = 0;                     // test hook: bucket capacity (small values force the dense fallback per line)
     int ws_variant = 1;                          // experiment hook: warp / register split of the warp-specialised kernel (mink3d_ws.cu)
     bool force_classic = false;                  // test / profiling hook: never use the warp-specialised kernel
+    bool ws_generic = false;                     // test hook (HRMGPU_WS_GENERIC): run-time grid size even where a fixed-n instantiation exists
     int num_sms = 148;                           // multiprocessors of the device
     int seg_fast_cap = 0;                        // test hook: list capacity of the 4-line segment pass (0 = default 128)
     long long seg_init_cap = 0;                  // test hook: first capacity of the segment pool / payload (forces the grow-and-repeat path)

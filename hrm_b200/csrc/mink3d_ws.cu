@@ -18,6 +18,12 @@
 //     (eval_point), hence bit-identical to the stored points.
 //   * Every obstacle interval is also appended to a per-line bucket (one atomicAdd on the line's counter), so the
 //     free-segment pass reads ~65 compact entries per line instead of striding over all 1001 surfaces.
+//   * FP64 fast mode only (HRMGPU_F64; strict and FP32 builds run on mink3d.cu).  The squared norm of the gradient-like
+//     vector u = ce2_c U_r + gz_c m (m = M1[:,2]) is evaluated in its expanded form a_c P_r + b_c Q_r + d_c with
+//     P_r = |U_r|^2, Q_r = 2 U_r.m, a_c = ce2_c^2, b_c = ce2_c gz_c, d_c = gz_c^2 |m|^2: two FMAs instead of six, and U_r
+//     never occupies registers.  Rounding differs from the direct form by a few ulps times the conditioning of M1
+//     (<= 4 (max / min body semi-axis)^2); the points stay within the 1e-12 of HRMGPU_F64.
+//   * The bench grid size n = 100 has its own instantiation (NF): strides and plane offsets become immediates.
 #include "mink3d_common.cuh"
 
 #include <cstdlib>
@@ -25,21 +31,24 @@
 namespace hrmgpu {
 
 constexpr int kPW = 8;                 // producer warps
-constexpr int kPT = 32 * kPW;          // (consumer warps: template parameter CW = 4 or 8)
+constexpr int kPT = 32 * kPW;
+constexpr int kCW = 4;                 // consumer warps
+constexpr int kCT = 32 * kCW;
+constexpr int kWsThreads = kPT + kCT;
 constexpr int kDeferLines = 512;       // sweep lines whose bucket appends are deferred to the next surface (CT * lines per thread)
-// Registers (2 CTAs per SM).  CW = 4: 384 threads launched with 80 registers each; VAR 0 keeps 80 / 80, VAR 1 moves 8 per
-// producer thread to the consumers (72 / 96, setmaxnreg).  CW = 8: 512 threads launched with 64 each; the consumers give
-// registers to the producers: VAR 1 = 80 / 48, VAR 2 = 72 / 56.
-template <int CW, int VAR>
+// Registers (2 CTAs per SM): 384 threads launched with 80 registers each; VAR 0 keeps 80 / 80, VAR 1 moves 8 per producer
+// thread to the consumers (72 / 96, setmaxnreg).  (8 consumer warps at 48 / 56 registers were measured: 20-30 % slower.)
+template <int VAR>
 struct RegSplit {
-    static constexpr int prod = CW == 4 ? (VAR == 1 ? 72 : 0) : (VAR == 2 ? 72 : 80);
-    static constexpr int cons = CW == 4 ? (VAR == 1 ? 96 : 0) : (VAR == 2 ? 56 : 48);
+    static constexpr int prod = VAR == 1 ? 72 : 0;
+    static constexpr int cons = VAR == 1 ? 96 : 0;
 };
 constexpr int kWsCellCap = 1024;       // kept mesh cells listed per scan round (256 per consumer warp, as in the one-surface kernel)
 constexpr int kZCap = 512;             // hit heights remembered per surface (phase C -> phase D)
 constexpr uint32_t kZBits = 15, kZNone = (1u << kZBits) - 1u;  // hit key = face << 15 | pool index (kZNone: height not stored)
 static_assert(kZCap < (1 << 15) && 2 * (kMaxGrid - 1) * (kMaxGrid - 1) < (1 << 17), "hit keys are 32-bit");
-constexpr int kRowStride = 10;         // per-row factors V[3] U[3] W[3] + pad
+constexpr int kRowStride = 8;          // per-row factors V[3] W[3] P Q
+constexpr int kWbStride = 24;          // per-warp scratch: 18 row-base coefficients, M1[:,2], M2[:,2]
 constexpr int kRawExtra = 36;          // doubles behind the table in a raw input buffer: Obj3 (19, padded to 20), R[9], off[3], semi[3]
 static_assert(sizeof(Obj3) == 19 * sizeof(double), "raw input layout");
 
@@ -93,57 +102,43 @@ __device__ __forceinline__ float fm(float a, float b, float c) { return __fmaf_r
 __device__ __forceinline__ double mu(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ float mu(float a, float b) { return __fmul_rn(a, b); }
 
-// One boundary point from its column constants k = {ce1, ce2, C[3], UZ[3], WZ[3]} and row factors V, U, W (see kColStride in
-// mink3d_common.cuh).  Every operation is an explicit fused multiply-add or multiply, so the producers (which store the
-// point) and the consumers (which re-evaluate it) get the same bits.
-template <class Real>
-__device__ __forceinline__ void eval_point(const Real* k, const Real* V, const Real* U, const Real* W, Real* o) {
-    const Real ux = fm(k[1], U[0], k[5]), uy = fm(k[1], U[1], k[6]), uz = fm(k[1], U[2], k[7]);
-    const Real nn = fm(uz, uz, fm(uy, uy, mu(ux, ux)));
-    Real inv;
-    if constexpr (sizeof(Real) == 4)
-        inv = rsqrtf(nn);
-    else
-        inv = fast_rsqrt(nn);
+// One boundary point from its column constants k = {ce1, ce2, C[3], WZ[3], a, b, d} and row factors f = {V[3], W[3], P, Q}
+// (kColStride / kRowStride).  Every operation is an explicit fused multiply-add or multiply, so the producers (which store
+// the point) and the consumers (which re-evaluate it) get the same bits.
+__device__ __forceinline__ void eval_point(const double* k, const double* f, double* o) {
+    const double nn = fm(k[8], f[6], fm(k[9], f[7], k[10]));
+    const double inv = fast_rsqrt(nn);
 #pragma unroll
-    for (int d = 0; d < 3; ++d) o[d] = fm(fm(k[1], W[d], k[8 + d]), inv, fm(k[0], V[d], k[2 + d]));
+    for (int d = 0; d < 3; ++d) o[d] = fm(fm(k[1], f[3 + d], k[5 + d]), inv, fm(k[0], f[d], k[2 + d]));
 }
 
 // The four corners of mesh cell (i, j) at once -- the same operations as four eval_point calls (bit-identical results), ordered
 // for instruction-level parallelism: the four normalisations first (independent rsqrt chains), then the coordinates one axis
 // at a time, so that a consumer thread waits for ONE dependent chain per stage instead of four whole evaluations in a row.
 // cc_i = column constants of column i (the next column follows at +kColStride), rf_j = row factors of row j (next: +kRowStride).
-template <class Real>
-__device__ __forceinline__ void eval_cell(const Real* cc_i, const Real* rf_j, D3 (&c)[2][2]) {  // c[col][row]
-    Real k01[2][2], inv[2][2];
+__device__ __forceinline__ void eval_cell(const double* cc_i, const double* rf_j, D3 (&c)[2][2]) {  // c[col][row]
+    double k01[2][2], inv[2][2], pq[2][2];
 #pragma unroll
-    for (int a = 0; a < 2; ++a) lds_pair(smem_u32(cc_i + a * kColStride), k01[a][0], k01[a][1]);
+    for (int r = 0; r < 2; ++r) lds_pair(smem_u32(rf_j + r * kRowStride + 6), pq[r][0], pq[r][1]);
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
-        Real k45[2], k67[2];
-        lds_pair(smem_u32(cc_i + a * kColStride + 4), k45[0], k45[1]);
-        lds_pair(smem_u32(cc_i + a * kColStride + 6), k67[0], k67[1]);
+        double k89[2];
+        lds_pair(smem_u32(cc_i + a * kColStride), k01[a][0], k01[a][1]);
+        lds_pair(smem_u32(cc_i + a * kColStride + 8), k89[0], k89[1]);
+        const double k10 = cc_i[a * kColStride + 10];
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const Real* f = rf_j + r * kRowStride;
-            const Real ux = fm(k01[a][1], f[3], k45[1]), uy = fm(k01[a][1], f[4], k67[0]), uz = fm(k01[a][1], f[5], k67[1]);
-            const Real nn = fm(uz, uz, fm(uy, uy, mu(ux, ux)));
-            if constexpr (sizeof(Real) == 4)
-                inv[a][r] = rsqrtf(nn);
-            else
-                inv[a][r] = fast_rsqrt(nn);
-        }
+        for (int r = 0; r < 2; ++r) inv[a][r] = fast_rsqrt(fm(k89[0], pq[r][0], fm(k89[1], pq[r][1], k10)));
     }
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
         double o[2][2];
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
-            const Real kC = cc_i[a * kColStride + 2 + d], kW = cc_i[a * kColStride + 8 + d];
+            const double kC = cc_i[a * kColStride + 2 + d], kW = cc_i[a * kColStride + 5 + d];
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
-                const Real* f = rf_j + r * kRowStride;
-                o[a][r] = static_cast<double>(fm(fm(k01[a][1], f[6 + d], kW), inv[a][r], fm(k01[a][0], f[d], kC)));
+                const double* f = rf_j + r * kRowStride;
+                o[a][r] = fm(fm(k01[a][1], f[3 + d], kW), inv[a][r], fm(k01[a][0], f[d], kC));
             }
         }
 #pragma unroll
@@ -154,29 +149,37 @@ __device__ __forceinline__ void eval_cell(const Real* cc_i, const Real* rf_j, D3
 }
 
 // Height of the sweep line (ix, iy) on face f, evaluated from the shared tables (phase D's rare path: the hit pool was full).
-template <class Real>
-__device__ __noinline__ double face_height(const Real* cc, const Real* rowf, const double* txs, const double* tys, int n, uint32_t f, uint32_t ix, uint32_t iy) {
+__device__ __noinline__ double face_height(const double* cc, const double* rowf, const double* txs, const double* tys, int n, int Ly, uint32_t f, uint32_t l) {
+    const uint32_t ix = l / static_cast<uint32_t>(Ly), iy = l - ix * static_cast<uint32_t>(Ly);
     const uint32_t nc1 = static_cast<uint32_t>(n - 1), ncell = nc1 * nc1;
     const uint32_t cell = (f < ncell) ? f : f - ncell;
     const uint32_t i = cell / nc1, j = cell - i * nc1;
     D3 cn[2][2];
-    eval_cell<Real>(cc + i * kColStride, rowf + j * kRowStride, cn);
+    eval_cell(cc + i * kColStride, rowf + j * kRowStride, cn);
     double z = 0.0;
     vertical_hit_fast(txs[ix + 1], tys[iy + 1], cn[0][0], (f < ncell) ? cn[1][0] : cn[0][1], cn[1][1], z);  // the same test on the same vertices as in phase C
     return z;
 }
 
-template <int MODE, int CW, int VAR, bool DBG>
-__global__ void __launch_bounds__(kPT + 32 * CW, 2) k_minksweep3d_ws(const WsParams P) {
-    constexpr int kCW = CW, kCT = 32 * CW, kWsThreads = kPT + kCT;
+// line_q (mink3d_common.cuh) without its range test, for surfaces whose vertices are PROVEN to lie within 2^15 line spacings
+// of the grid origin (see range_ok below): ok = false only when the coordinate is within 4 * 2^-16 spacings of a grid line.
+__device__ __forceinline__ uint32_t line_q_inrange(double x, double inv_d, double bias_q, bool& ok) {
+    const uint32_t w = static_cast<uint32_t>(__double2loint(fma(x, inv_d, bias_q)));
+    ok = ((w + 5u) & 0xFFF8u) != 0u;
+    return w;
+}
+
+// NF: grid size n fixed at compile time (0: taken from the parameters).
+template <int VAR, int NF, bool DBG>
+__global__ void __launch_bounds__(kWsThreads, 2) k_minksweep3d_ws(const WsParams P) {
     constexpr int kDU = kDeferLines / kCT;  // deferred lines per consumer thread
-    using Regs = RegSplit<CW, VAR>;
-    using Real = typename RealOf<MODE>::type;
+    using Regs = RegSplit<VAR>;
     using Code = uint16_t;  // 2 x 8-bit line codes (both axes <= 127 lines)
     using A = Fast;
     const MinkParams& p = P.m;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int n = p.n, M = p.M;
+    const int n = NF ? NF : p.n, M = NF ? NF * NF : p.M;
+    const int lpc = NF ? NF / 2 : p.lpc, groups = NF ? kPT / (NF / 2) : p.groups;  // (the host checks that pick_mapping agrees)
     const int tid = threadIdx.x;
     const int per_layer = p.n_objs * p.B;
     const int heavy = p.n_heavy * p.B;
@@ -205,6 +208,12 @@ __global__ void __launch_bounds__(kPT + 32 * CW, 2) k_minksweep3d_ws(const WsPar
         int* e = items + 4 * ring;
         e[0] = item, e[1] = p.first_obj + oi, e[2] = k * p.B + (s - oi * p.B), e[3] = k * per_layer + s;
     };
+    if (DBG && (tid & 31) == 0) {  // hardware warp slot of every warp of the CTA (rows 6g.. producers, 7g.. consumers)
+        unsigned wid;
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+        const int w = tid >> 5;
+        p.dbg[(static_cast<size_t>(gridDim.x) * (w < kPW ? 6 : 7) + blockIdx.x) * 8 + (w < kPW ? w : w - kPW)] = wid;
+    }
     if (tid == 0) {
         const int i0 = static_cast<int>(atomicAdd(P.work, 1ULL)), i1 = static_cast<int>(atomicAdd(P.work, 1ULL));
         claim(0, i0), claim(1, i1);
@@ -213,11 +222,10 @@ __global__ void __launch_bounds__(kPT + 32 * CW, 2) k_minksweep3d_ws(const WsPar
 
     if (tid < kPT) {
         // =============================== PRODUCERS: inputs -> tables -> boundary points ===============================
-        if constexpr (CW == 4 && Regs::prod != 0) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Regs::prod));
-        if constexpr (CW == 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Regs::prod));
-        const int grp = tid / p.lpc;
-        const int ln = tid - grp * p.lpc;
-        const bool worker = grp < p.groups;
+        if constexpr (Regs::prod != 0) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Regs::prod));
+        const int grp = tid / lpc;
+        const int ln = tid - grp * lpc;
+        const bool worker = grp < groups;
         const int lane = tid & 31;
 
         auto issue_load = [&](int ring, int rb) {
@@ -262,8 +270,8 @@ __global__ void __launch_bounds__(kPT + 32 * CW, 2) k_minksweep3d_ws(const WsPar
             }
             const double* raw = reinterpret_cast<const double*>(smem_raw + P.o_raw[b]);
             const double* ro = raw + 8 * n;  // a b c px py pz R[9] sign ia ib ic | R2[9] @20 | off[3] @29 | semi[3] @32
-            Real* cc = reinterpret_cast<Real*>(smem_raw + P.o_cc[b]);
-            Real* rowf = reinterpret_cast<Real*>(smem_raw + P.o_rowf[b]);
+            double* cc = reinterpret_cast<double*>(smem_raw + P.o_cc[b]);
+            double* rowf = reinterpret_cast<double*>(smem_raw + P.o_rowf[b]);
             Code* vcode = reinterpret_cast<Code*>(smem_raw + P.o_vcode[b]);
 
             // ---- per-surface matrices: Tinv = (R2 diag) R2^T, M1 = Tinv R1, M2 = ((K Tinv) Tinv) R1  (SuperQuadrics.cpp:115,137-140).
@@ -287,7 +295,7 @@ __global__ void __launch_bounds__(kPT + 32 * CW, 2) k_minksweep3d_ws(const WsPar
             // The 18 row-base coefficients (R1[:,0] a, R1[:,1] b, M1[:,0] / a, M1[:,1] / b, M2[:,0] / a, M2[:,1] / b) and the third
             // columns of M1 / M2, one per lane, into the warp's own 24 doubles of shared memory: the table tasks below read them
             // with broadcast loads instead of every thread forming the products again.
-            double* wb = reinterpret_cast<double*>(smem_raw + P.o_wtab) + (tid >> 5) * 24;
+            double* wb = reinterpret_cast<double*>(smem_raw + P.o_wtab) + (tid >> 5) * kWbStride;
             {
                 const int d = lane % 3, kind = lane / 3;  // lanes 0..17: kind 0..5, component d; lanes 18..23: third columns
                 const int src = lane < 18 ? 3 * d + (kind & 1) : 3 * d + 2;
@@ -304,34 +312,39 @@ __global__ void __launch_bounds__(kPT + 32 * CW, 2) k_minksweep3d_ws(const WsPar
                 if (lane < 24) wb[lane] = val;
                 __syncwarp();
             }
-            // ---- factor tables: rows  V_r = R1[:,0] a cw1_r + R1[:,1] b sw1_r,  U_r = M1[:,0] cw2_r / a + M1[:,1] sw2_r / b,  W_r likewise (M2);
-            //      columns {ce1, ce2, C = R1[:,2] c se1 + (p - off), UZ = M1[:,2] se2 / c, WZ = M2[:,2] se2 / c}
+            // ---- factor tables: rows  V_r = R1[:,0] a cw1_r + R1[:,1] b sw1_r,  W_r = M2[:,0] cw2_r / a + M2[:,1] sw2_r / b,
+            //      P_r = |U_r|^2, Q_r = 2 U_r . m  with U_r = M1[:,0] cw2_r / a + M1[:,1] sw2_r / b, m = M1[:,2];
+            //      columns {ce1, ce2, C = R1[:,2] c se1 + (p - off), WZ = M2[:,2] gz, a = ce2^2, b = ce2 gz, d = gz^2 |m|^2}, gz = se2 / c
             for (int task = tid; task < 3 * n; task += kPT) {
                 if (task < n) {
                     const int r = task;
-                    const Real cw1 = Real(raw[4 * n + r]), sw1 = Real(raw[5 * n + r]), cw2 = Real(raw[6 * n + r]), sw2 = Real(raw[7 * n + r]);
-                    Real* f = rowf + r * kRowStride;
+                    const double cw1 = raw[4 * n + r], sw1 = raw[5 * n + r], cw2 = raw[6 * n + r], sw2 = raw[7 * n + r];
+                    double* f = rowf + r * kRowStride;
+                    double U[3];
 #pragma unroll
                     for (int d = 0; d < 3; ++d) {
-                        f[d] = fm(Real(wb[d]), cw1, mu(Real(wb[3 + d]), sw1));
-                        f[3 + d] = fm(Real(wb[6 + d]), cw2, mu(Real(wb[9 + d]), sw2));
-                        f[6 + d] = fm(Real(wb[12 + d]), cw2, mu(Real(wb[15 + d]), sw2));
+                        f[d] = fm(wb[d], cw1, mu(wb[3 + d], sw1));
+                        U[d] = fm(wb[6 + d], cw2, mu(wb[9 + d], sw2));
+                        f[3 + d] = fm(wb[12 + d], cw2, mu(wb[15 + d], sw2));
                     }
-                    f[9] = Real(0);
+                    f[6] = fm(U[2], U[2], fm(U[1], U[1], mu(U[0], U[0])));
+                    f[7] = mu(2.0, fm(U[2], wb[20], fm(U[1], wb[19], mu(U[0], wb[18]))));
                 } else {
                     const int c = (task - n) >> 1;
-                    Real* kc = cc + c * kColStride;
+                    double* kc = cc + c * kColStride;
                     if ((task - n) & 1) {
-                        const Real ce1 = Real(raw[c]), Zc = mu(Real(ro[2]), Real(raw[n + c]));  // c * se1
+                        const double ce1 = raw[c], Zc = mu(ro[2], raw[n + c]);  // c * se1
                         kc[0] = ce1;
 #pragma unroll
-                        for (int i = 0; i < 3; ++i) kc[2 + i] = fm(Real(ro[6 + 3 * i + 2]), Zc, Real(ro[3 + i] - ro[29 + i]));
+                        for (int i = 0; i < 3; ++i) kc[2 + i] = fm(ro[6 + 3 * i + 2], Zc, ro[3 + i] - ro[29 + i]);
                     } else {
-                        const Real ce2 = Real(raw[2 * n + c]), gz = mu(Real(raw[3 * n + c]), Real(ro[18]));  // se2 / c
+                        const double ce2 = raw[2 * n + c], gz = mu(raw[3 * n + c], ro[18]);  // se2 / c
+                        const double mm = fm(wb[20], wb[20], fm(wb[19], wb[19], mu(wb[18], wb[18])));
                         kc[1] = ce2;
 #pragma unroll
-                        for (int i = 0; i < 3; ++i) kc[5 + i] = mu(Real(wb[18 + i]), gz), kc[8 + i] = mu(Real(wb[21 + i]), gz);
-                        kc[11] = Real(0);
+                        for (int i = 0; i < 3; ++i) kc[5 + i] = mu(wb[21 + i], gz);
+                        kc[8] = mu(ce2, ce2), kc[9] = mu(ce2, gz), kc[10] = mu(mu(gz, gz), mm);
+                        kc[11] = 0.0;
                     }
                 }
             }
@@ -340,6 +353,13 @@ __global__ void __launch_bounds__(kPT + 32 * CW, 2) k_minksweep3d_ws(const WsPar
                 hdr[8 * b + 1] = slot;
                 hdr[8 * b + 2] = ro[15] < 0.0 ? 1 : 0;  // arena surface (sign = -1)
                 hdr[8 * b + 3] = slot / per_layer;      // layer
+                // Every vertex lies within rad = a + b + c + max(body semi-axis) of p - off (|x0 - p| <= |(a, b, c)|, and the
+                // offset term is Tinv applied to a unit vector): if that keeps the line coordinate inside +-32000 spacings, phase A
+                // drops the per-vertex range test of line_q.  (NaN / inf inputs compare false: checked path.)
+                const double rad = ro[0] + ro[1] + ro[2] + fmax(ro[32], fmax(ro[33], ro[34]));
+                const double gxm = fma(fabs(ro[3] - ro[29]) + rad, p.inv_dx, fabs(p.bias_x));
+                const double gym = fma(fabs(ro[4] - ro[30]) + rad, p.inv_dy, fabs(p.bias_y));
+                hdr[8 * b + 4] = (gxm < 32000.0 && gym < 32000.0) ? 1 : 0;
             }
             bar_sync(kBarProd, kPT);
             // ---- inputs of the next surface: requested now, consumed after phase A
@@ -350,59 +370,66 @@ __global__ void __launch_bounds__(kPT + 32 * CW, 2) k_minksweep3d_ws(const WsPar
                 t0 = t1;
             }
             // ---- phase A: a thread owns the adjacent rows (r0, r0 + 1) and walks the columns of its group
-            if (DBG && P.skip_a) {
-                for (int i = tid; i < M + 8; i += kPT) vcode[i] = 0;  // no vertex near a sweep line: the scan keeps nothing
-            } else if (worker) {
-                using R2 = Real2<Real>;
-                Real* mx = reinterpret_cast<Real*>(p.mesh) + static_cast<size_t>(slot) * 3 * M;
-                const int npass = n / (2 * p.lpc);
-                const uint32_t cc_step = static_cast<uint32_t>(p.groups * kColStride * sizeof(Real));
-                const uint32_t v_step = static_cast<uint32_t>(p.groups * n * sizeof(Code));
-                const size_t g_step = static_cast<size_t>(p.groups) * n;
+            auto phase_a = [&](auto in_range_tag) {
+                constexpr bool kInRange = decltype(in_range_tag)::value;
+                using R2 = Real2<double>;
+                double* mx = reinterpret_cast<double*>(p.mesh) + static_cast<size_t>(slot) * 3 * M;
+                const int npass = n / (2 * lpc);
+                const uint32_t cc_step = static_cast<uint32_t>(groups * kColStride * sizeof(double));
+                const uint32_t v_step = static_cast<uint32_t>(groups * n * sizeof(Code));
+                const size_t g_step = static_cast<size_t>(groups) * n;
                 const uint32_t lx2 = static_cast<uint32_t>(p.Lx) * 0x00010001u, ly2 = static_cast<uint32_t>(p.Ly) * 0x00010001u;
                 for (int h = 0; h < npass; ++h) {
-                    const int r0 = 2 * (ln + h * p.lpc);
-                    Real F[2][9];  // V[3] U[3] W[3] of the two rows
+                    const int r0 = 2 * (ln + h * lpc);
+                    double F[2][8];  // V[3] W[3] P Q of the two rows
                     {
                         const uint32_t fa = smem_u32(rowf + r0 * kRowStride);
 #pragma unroll
-                        for (int h2 = 0; h2 < 2; ++h2) {
+                        for (int h2 = 0; h2 < 2; ++h2)
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) lds_pair(fa + (h2 * kRowStride + 2 * i) * sizeof(Real), F[h2][2 * i], F[h2][2 * i + 1]);
-                            F[h2][8] = rowf[(r0 + h2) * kRowStride + 8];
-                        }
+                            for (int i = 0; i < 4; ++i) lds_pair(fa + (h2 * kRowStride + 2 * i) * sizeof(double), F[h2][2 * i], F[h2][2 * i + 1]);
                     }
-                    uint32_t ca = smem_u32(cc) + static_cast<uint32_t>(grp * kColStride * sizeof(Real));
+                    uint32_t ca = smem_u32(cc) + static_cast<uint32_t>(grp * kColStride * sizeof(double));
                     uint32_t va = smem_u32(vcode) + static_cast<uint32_t>((grp * n + r0) * sizeof(Code));
-                    Real* gx = mx + grp * n + r0;
-                    for (int c = grp; c < n; c += p.groups, ca += cc_step, va += v_step, gx += g_step) {
-                        Real kk[12];
+                    double* gx = mx + grp * n + r0;
+                    for (int c = grp; c < n; c += groups, ca += cc_step, va += v_step, gx += g_step) {
+                        double kk[12];
 #pragma unroll
-                        for (int i = 0; i < 6; ++i) lds_pair(ca + i * 2 * sizeof(Real), kk[2 * i], kk[2 * i + 1]);
-                        Real o[2][3];
-                        eval_point<Real>(kk, F[0], F[0] + 3, F[0] + 6, o[0]);
-                        eval_point<Real>(kk, F[1], F[1] + 3, F[1] + 6, o[1]);
+                        for (int i = 0; i < 6; ++i) lds_pair(ca + i * 2 * sizeof(double), kk[2 * i], kk[2 * i + 1]);
+                        double o[2][3];
+                        eval_point(kk, F[0], o[0]);
+                        eval_point(kk, F[1], o[1]);
                         *reinterpret_cast<R2*>(gx) = R2{o[0][0], o[1][0]};
                         *reinterpret_cast<R2*>(gx + M) = R2{o[0][1], o[1][1]};
                         *reinterpret_cast<R2*>(gx + 2 * static_cast<size_t>(M)) = R2{o[0][2], o[1][2]};
                         bool k0, k1, k2, k3;
-                        const uint32_t wx0 = line_q(static_cast<double>(o[0][0]), p.inv_dx, p.bias_xq, k0);
-                        const uint32_t wy0 = line_q(static_cast<double>(o[0][1]), p.inv_dy, p.bias_yq, k1);
-                        const uint32_t wx1 = line_q(static_cast<double>(o[1][0]), p.inv_dx, p.bias_xq, k2);
-                        const uint32_t wy1 = line_q(static_cast<double>(o[1][1]), p.inv_dy, p.bias_yq, k3);
+                        uint32_t wx0, wy0, wx1, wy1;
+                        if constexpr (kInRange) {
+                            wx0 = line_q_inrange(o[0][0], p.inv_dx, p.bias_xq, k0), wy0 = line_q_inrange(o[0][1], p.inv_dy, p.bias_yq, k1);
+                            wx1 = line_q_inrange(o[1][0], p.inv_dx, p.bias_xq, k2), wy1 = line_q_inrange(o[1][1], p.inv_dy, p.bias_yq, k3);
+                        } else {
+                            wx0 = line_q(o[0][0], p.inv_dx, p.bias_xq, k0), wy0 = line_q(o[0][1], p.inv_dy, p.bias_yq, k1);
+                            wx1 = line_q(o[1][0], p.inv_dx, p.bias_xq, k2), wy1 = line_q(o[1][1], p.inv_dy, p.bias_yq, k3);
+                        }
                         if (k0 && k1 && k2 && k3) {
                             const uint32_t X = __vimin_s16x2_relu(__byte_perm(wx0, wx1, 0x7632), lx2);
                             const uint32_t Y = __vimin_s16x2_relu(__byte_perm(wy0, wy1, 0x7632), ly2);
                             asm volatile("st.shared.u32 [%0], %1;" ::"r"(va), "r"((X | (Y << 8)) << 1) : "memory");
                         } else {  // rare: a coordinate within rounding distance of a sweep line -> exact search
-                            const uint32_t cx0 = line_code(static_cast<double>(o[0][0]), txs, p.Lx, p.inv_dx, p.bias_x);
-                            const uint32_t cy0 = line_code(static_cast<double>(o[0][1]), tys, p.Ly, p.inv_dy, p.bias_y);
-                            const uint32_t cx1 = line_code(static_cast<double>(o[1][0]), txs, p.Lx, p.inv_dx, p.bias_x);
-                            const uint32_t cy1 = line_code(static_cast<double>(o[1][1]), tys, p.Ly, p.inv_dy, p.bias_y);
+                            const uint32_t cx0 = line_code(o[0][0], txs, p.Lx, p.inv_dx, p.bias_x);
+                            const uint32_t cy0 = line_code(o[0][1], tys, p.Ly, p.inv_dy, p.bias_y);
+                            const uint32_t cx1 = line_code(o[1][0], txs, p.Lx, p.inv_dx, p.bias_x);
+                            const uint32_t cy1 = line_code(o[1][1], tys, p.Ly, p.inv_dy, p.bias_y);
                             sts_codes(va, static_cast<uint16_t>(cx0 | (cy0 << 8)), static_cast<uint16_t>(cx1 | (cy1 << 8)));
                         }
                     }
                 }
+            };
+            if (DBG && P.skip_a) {
+                for (int i = tid; i < M + 8; i += kPT) vcode[i] = 0;  // no vertex near a sweep line: the scan keeps nothing
+            } else if (worker) {
+                if (hdr[8 * b + 4]) phase_a(std::true_type{});
+                else phase_a(std::false_type{});
             }
             if (tid == 0) claim((it + 2) & 3, claimed);
             __syncwarp();
@@ -418,8 +445,7 @@ __global__ void __launch_bounds__(kPT + 32 * CW, 2) k_minksweep3d_ws(const WsPar
     }
 
     // ======================================= CONSUMERS: scan -> cell tests -> intervals =======================================
-    if constexpr (CW == 4 && Regs::cons != 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Regs::cons));
-    if constexpr (CW == 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Regs::cons));
+    if constexpr (Regs::cons != 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Regs::cons));
     const int ctid = tid - kPT;
     const int lane = ctid & 31, warp = ctid >> 5;
     uint16_t* cellq = reinterpret_cast<uint16_t*>(smem_raw + p.o_queue);  // [kWsCellCap] kept cells (cell = i * (n-1) + j)
@@ -449,6 +475,8 @@ __global__ void __launch_bounds__(kPT + 32 * CW, 2) k_minksweep3d_ws(const WsPar
     int* zcount = qcount;
     int* hcount = qcount + 2;
     int* segcnt = qcount + 4;
+    int* scan_next = qcount + 8;  // next chunk of mesh rows / next batch of kept cells: the consumer warps claim their work, because the
+    int* cell_next = qcount + 9;  // warp that shares its scheduler with the busiest producer warps runs at less than half the others' pace
     const int nc1 = n - 1;
     const int ncell = nc1 * nc1;
     const uint32_t nc1_magic = 0xFFFFFFFFu / static_cast<uint32_t>(nc1) + 1u;
@@ -459,6 +487,9 @@ __global__ void __launch_bounds__(kPT + 32 * CW, 2) k_minksweep3d_ws(const WsPar
     constexpr uint32_t kLight = 16;  // cells with more candidates than this get a whole warp
 
     long long c_wait = 0, c_sweep = 0, c_cells = 0, c_d = 0, c0 = 0;  // profiling builds: [4] waiting for the producers, [5] scan + cell tests, [6] phase D
+    long long w_swar = 0, w_comp = 0, w_bar = 0, w_t = 0;            // per warp: SWAR tests, compaction, waiting for the other consumer warps
+    long long w_first = 0, w_nchunk = 0;                             // ... of which the first chunk of every surface; chunks taken
+    bool w_is_first = false;
     for (int it = 0;; ++it) {
         const int b = it & 1;
         if (DBG) c0 = clock64();
@@ -473,8 +504,8 @@ __global__ void __launch_bounds__(kPT + 32 * CW, 2) k_minksweep3d_ws(const WsPar
         const int slot = hdr[8 * b + 1];
         const bool is_arena = hdr[8 * b + 2] != 0;
         const int k_layer = hdr[8 * b + 3];
-        const Real* cc = reinterpret_cast<const Real*>(smem_raw + P.o_cc[b]);
-        const Real* rowf = reinterpret_cast<const Real*>(smem_raw + P.o_rowf[b]);
+        const double* cc = reinterpret_cast<const double*>(smem_raw + P.o_cc[b]);
+        const double* rowf = reinterpret_cast<const double*>(smem_raw + P.o_rowf[b]);
         const Code* vcode = reinterpret_cast<const Code*>(smem_raw + P.o_vcode[b]);
         auto code_at = [&](int q) -> uint32_t { return __byte_perm(static_cast<uint32_t>(vcode[q]), 0u, 0x4140); };
         auto hit = [&](uint32_t ix, uint32_t iy, const D3& t0, const D3& t1, const D3& t2, double& z) -> bool {
@@ -482,7 +513,8 @@ __global__ void __launch_bounds__(kPT + 32 * CW, 2) k_minksweep3d_ws(const WsPar
         };
 
         for (int i = ctid; i < p.L; i += kCT) m0[i] = kNoFace, m1[i] = kNoFace;
-        if (ctid == 0) *hcount = 0, *zcount = 0;
+        if (ctid == 0) *hcount = 0, *zcount = 0, *scan_next = 0;
+        if (DBG) w_is_first = true;
         bar_sync(kBarCons, kCT);
         // A hit enters the line's ordered two-slot table keyed by its FACE INDEX (the reference keeps the first two hits in face
         // order, SURVEY finding 2); the low bits of the key say where its height is kept for phase D.
@@ -529,28 +561,36 @@ __global__ void __launch_bounds__(kPT + 32 * CW, 2) k_minksweep3d_ws(const WsPar
         // the upper row of the next, and the lane's cell mask is loop-invariant.  (1) all SWAR tests of a chunk (kWR words x 4
         // rows per lane) back to back; (2) ONE prefix sum over the lanes' kept-cell counts, then every lane writes its own cells.
         // What does not fit into the warp's list segment stays in w[] for the next round (after the tests of this round).
-        constexpr int kWR = 7;  // words per lane and chunk: 7 x 4 rows x kCW warps >= 99 mesh rows (n = 100, 4 consumer warps)
-        const int rows_per_warp = (nc1 + kCW - 1) / kCW;
-        const int nchunk = (rows_per_warp + kWR * kUPL - 1) / (kWR * kUPL);
+#ifndef HRMGPU_WS_KWR
+#define HRMGPU_WS_KWR 2
+#endif
+        constexpr int kWR = HRMGPU_WS_KWR;  // words per lane and chunk (x 4 rows each): short on purpose, the unrolled body is ~30 instructions per row
+        const int nchunk = (nc1 + kWR * kUPL - 1) / (kWR * kUPL);
         const int j0 = 4 * lane;
         const int jl = min(j0, n - 4);  // (lanes past the end of a row load its last unit and keep nothing)
         const int vcells = nc1 - j0;    // cells of this lane's unit inside a mesh row
         // cells 0 .. v-1 of a unit are bits 7, 23, 8, 24
         const uint32_t keep = (0x00000080u & (0u - static_cast<uint32_t>(vcells > 0))) | (0x00800000u & (0u - static_cast<uint32_t>(vcells > 1))) |
                               (0x00000100u & (0u - static_cast<uint32_t>(vcells > 2))) | (0x01000000u & (0u - static_cast<uint32_t>(vcells > 3)));
-        auto chunk_row0 = [&](int chunk) { return warp * rows_per_warp + chunk * (kWR * kUPL); };
+        auto chunk_row0 = [&](int chunk) { return chunk * (kWR * kUPL); };
         int chunk = 0;
         bool loaded = false;
         uint32_t w[kWR];
 #pragma unroll
         for (int r = 0; r < kWR; ++r) w[r] = 0u;
         for (;;) {
-            int wcnt = 0;
             bool parked = false;
-            while (chunk < nchunk) {
+            if (lane == 0) segcnt[warp] = 0;
+            __syncwarp();
+            for (;;) {
+                if (DBG) w_t = clock64();
                 if (!loaded) {
+                    int claimed_chunk = 0;
+                    if (lane == 0) claimed_chunk = atomicAdd(scan_next, 1);
+                    chunk = __shfl_sync(0xFFFFFFFFu, claimed_chunk, 0);
+                    if (chunk >= nchunk) break;
                     const int row0 = chunk_row0(chunk);
-                    const int band_end = min(nc1, (warp + 1) * rows_per_warp);  // first mesh row that is not this warp's
+                    const int band_end = nc1;  // (rows past the mesh in the last chunk keep nothing)
                     int row = min(row0, nc1 - 1);
                     uint2 ra = *reinterpret_cast<const uint2*>(vcode + row * n + jl);
                     uint32_t sax = __funnelshift_r(ra.x, ra.y, 16), say = __funnelshift_r(ra.y, static_cast<uint32_t>(vcode[row * n + jl + 4]), 16);
@@ -571,43 +611,48 @@ __global__ void __launch_bounds__(kPT + 32 * CW, 2) k_minksweep3d_ws(const WsPar
                     }
                     loaded = true;
                 }
+                if (DBG) {
+                    const long long t = clock64();
+                    w_swar += t - w_t;
+                    if (w_is_first) w_first += t - w_t, w_is_first = false;
+                    w_t = t, ++w_nchunk;
+                }
+                // Kept cells are sparse (~2 %): a lane that has some takes its slots in the warp's list segment with ONE shared-memory
+                // atomic (the order inside the segment is irrelevant: hits are keyed by face index) -- no prefix sum over the lanes.
                 int mine = 0;
 #pragma unroll
                 for (int r = 0; r < kWR; ++r) mine += __popc(w[r]);
-                int incl = mine;
+                bool left = false;
+                if (mine != 0) {
+                    int pos = atomicAdd(&segcnt[warp], mine);
+                    const int row0 = chunk_row0(chunk);
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                    if (lane >= o) incl += t;
-                }
-                const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-                const int room = kSegCap - wcnt;
-                int pos = incl - mine;  // rank of this lane's first remaining cell
-                const int row0 = chunk_row0(chunk);
-#pragma unroll
-                for (int r = 0; r < kWR; ++r) {
-                    while (w[r] != 0u && pos < room) {
-                        const int bit = __ffs(w[r]) - 1;
-                        w[r] &= w[r] - 1u;
-                        // bits 7.. hold cells 0 / 2, bits 23.. cells 1 / 3 of the word's four rows
-                        const int hi = bit >= 23 ? 1 : 0, pb = bit - (hi ? 23 : 7);
-                        seg[wcnt + pos] = static_cast<uint16_t>((row0 + r * kUPL + (pb >> 1)) * nc1 + j0 + (((pb & 1) << 1) | hi));
-                        ++pos;
+                    for (int r = 0; r < kWR; ++r) {
+                        while (w[r] != 0u && pos < kSegCap) {
+                            const int bit = __ffs(w[r]) - 1;
+                            w[r] &= w[r] - 1u;
+                            // bits 7.. hold cells 0 / 2, bits 23.. cells 1 / 3 of the word's four rows
+                            const int hi = bit >= 23 ? 1 : 0, pb = bit - (hi ? 23 : 7);
+                            seg[pos] = static_cast<uint16_t>((row0 + r * kUPL + (pb >> 1)) * nc1 + j0 + (((pb & 1) << 1) | hi));
+                            ++pos;
+                        }
+                        left = left || (w[r] != 0u);
                     }
                 }
-                __syncwarp();
-                if (total > room) {  // segment full: the tests come first, the rest of w[] follows in the next round
-                    wcnt = kSegCap;
+                if (DBG) w_comp += clock64() - w_t;
+                if (__any_sync(0xFFFFFFFFu, left)) {  // segment full: the tests come first, the rest of w[] follows in the next round
                     parked = true;
                     break;
                 }
-                wcnt += total;
                 loaded = false;
-                ++chunk;
             }
-            if (lane == 0) segcnt[warp] = wcnt;
             __syncwarp();
+            if (lane == 0) segcnt[warp] = min(segcnt[warp], kSegCap);  // (a full segment: the counter ran past the capacity)
+            if (ctid == 0) *cell_next = 0;
+            __syncwarp();
+            if (DBG) w_t = clock64();
             const int more = bar_or(kBarCons, kCT, parked ? 1 : 0);
+            if (DBG) w_bar += clock64() - w_t;
             if (DBG) {
                 const long long c1 = clock64();
                 c_sweep += c1 - c0;
@@ -619,8 +664,12 @@ __global__ void __launch_bounds__(kPT + 32 * CW, 2) k_minksweep3d_ws(const WsPar
 #pragma unroll
             for (int w = 0; w < kCW; ++w) sc[w + 1] = sc[w] + segcnt[w];
             const int ncq = sc[kCW];
-            for (int base = 0; base < ncq; base += kCT) {
-                const int ci = base + ctid;
+            for (;;) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(cell_next, 32);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (base >= ncq) break;
+                const int ci = base + lane;
                 if (ci < ncq) {
                     int w = 0, off_w = 0;
 #pragma unroll
@@ -635,9 +684,15 @@ __global__ void __launch_bounds__(kPT + 32 * CW, 2) k_minksweep3d_ws(const WsPar
                         heavyq[atomicAdd(hcount, 1)] = static_cast<uint16_t>(cell);
                     } else if (nA + nB != 0u) {
                         D3 cn[2][2];  // [column offset][row offset]: vertex (i + a, j + r) = point q + a * n + r
-                        eval_cell<Real>(cc + i * kColStride, rowf + j * kRowStride, cn);
-                        if (nA != 0u) test_lines(cell, loA, hiA, cn[0][0], cn[1][0], cn[1][1]);                                  // (q, q+n, q+n+1)
-                        if (nB != 0u) test_lines(cell + static_cast<uint32_t>(ncell), loB, hiB, cn[0][0], cn[0][1], cn[1][1]);  // (q, q+1, q+n+1)
+                        eval_cell(cc + i * kColStride, rowf + j * kRowStride, cn);
+                        // faces (q, q+n, q+n+1) and (q, q+1, q+n+1): ONE copy of the line loop / triangle test in the code
+                        // (the consumers' per-surface instruction footprint has to stay inside the 32 KB L1.5 instruction cache)
+#pragma unroll 1
+                        for (int fb = 0; fb < 2; ++fb) {
+                            if ((fb ? nB : nA) == 0u) continue;
+                            const D3 t1 = fb ? cn[0][1] : cn[1][0];
+                            test_lines(cell + (fb ? static_cast<uint32_t>(ncell) : 0u), fb ? loB : loA, fb ? hiB : hiA, cn[0][0], t1, cn[1][1]);
+                        }
                     }
                 }
             }
@@ -653,7 +708,7 @@ __global__ void __launch_bounds__(kPT + 32 * CW, 2) k_minksweep3d_ws(const WsPar
                     uint32_t loA, hiA, loB, hiB, nA, nB;
                     cell_sets(q, loA, hiA, loB, hiB, nA, nB);
                     D3 cn[2][2];
-                    eval_cell<Real>(cc + i * kColStride, rowf + j * kRowStride, cn);
+                    eval_cell(cc + i * kColStride, rowf + j * kRowStride, cn);
                     const D3 c00 = cn[0][0], c10 = cn[1][0], c11 = cn[1][1], c01 = cn[0][1];
                     for (uint32_t idx = lane; idx < nA + nB; idx += 32) {
                         const bool second = idx >= nA;
@@ -689,17 +744,16 @@ __global__ void __launch_bounds__(kPT + 32 * CW, 2) k_minksweep3d_ws(const WsPar
         double* lo = p.lo + static_cast<size_t>(slot) * p.L;
         double* up = p.up + static_cast<size_t>(slot) * p.L;
         unsigned single = 0;
-        auto face_z = [&](uint32_t key, uint32_t ix, uint32_t iy) -> double {
+        auto face_z = [&](uint32_t key, int l) -> double {
             if ((key & kZNone) != kZNone) return zpool[key & kZNone];  // found in phase C
-            return face_height<Real>(cc, rowf, txs, tys, n, key >> kZBits, ix, iy);  // (pool full: evaluate the face again)
+            return face_height(cc, rowf, txs, tys, n, p.Ly, key >> kZBits, static_cast<uint32_t>(l));  // (pool full: evaluate the face again)
         };
         auto interval = [&](int l, double& a, double& bb) -> bool {  // true: an obstacle interval that goes into the line's bucket
             a = is_arena ? p.zlow : __longlong_as_double(0x7FF8000000000000LL);
             bb = is_arena ? p.zup : __longlong_as_double(0x7FF8000000000000LL);
             const uint32_t e0 = m0[l], e1 = m1[l];
             if (e1 != kNoFace) {
-                const uint32_t ix = static_cast<uint32_t>(l) / static_cast<uint32_t>(p.Ly), iy = static_cast<uint32_t>(l) - ix * static_cast<uint32_t>(p.Ly);
-                const double z0 = face_z(e0, ix, iy), z1 = face_z(e1, ix, iy);
+                const double z0 = face_z(e0, l), z1 = face_z(e1, l);
                 const double zl = fmin(z0, z1), zu = fmax(z0, z1);
                 a = is_arena ? fmin(p.zlow, zl) : zl;
                 bb = is_arena ? fmax(p.zup, zu) : zu;
@@ -708,30 +762,23 @@ __global__ void __launch_bounds__(kPT + 32 * CW, 2) k_minksweep3d_ws(const WsPar
             if (e0 != kNoFace) ++single;  // exactly one hit: reference reads out of bounds; defined here as "no interval"
             return false;
         };
-        // first kDU lines of the thread (all of them when L <= 512): bucket appends deferred, see ppos
-        pbase = static_cast<size_t>(k_layer) * p.L;
+        // blocks of kDeferLines lines (one block when L <= 512): bucket appends deferred, see ppos
+#pragma unroll 1
+        for (int lb = 0; lb < p.L; lb += kDeferLines) {
+            if (lb > 0) flush_pending();  // (more than 512 sweep lines: the slots of the previous block are awaited here)
+            pbase = static_cast<size_t>(k_layer) * p.L + lb;
 #pragma unroll
-        for (int u = 0; u < kDU; ++u) {
-            const int l = ctid + u * kCT;
-            if (l < p.L) {
-                double a, bb;
-                if (interval(l, a, bb)) {
-                    stash[ctid * kDU + u] = make_double2(a, bb);
-                    ppos[u] = bucket_slot(P.bcnt + pbase + l);  // not read before flush_pending()
+            for (int u = 0; u < kDU; ++u) {
+                const int l = lb + ctid + u * kCT;
+                if (l < p.L) {
+                    double a, bb;
+                    if (interval(l, a, bb)) {
+                        stash[ctid * kDU + u] = make_double2(a, bb);
+                        ppos[u] = bucket_slot(P.bcnt + pbase + ctid + u * kCT);  // not read before flush_pending()
+                    }
+                    lo[l] = a;
+                    up[l] = bb;
                 }
-                lo[l] = a;
-                up[l] = bb;
-            }
-        }
-        for (int l = ctid + kDU * kCT; l < p.L; l += kCT) {  // more than 512 sweep lines: the remaining ones append at once
-            double a, bb;
-            const bool app = interval(l, a, bb);
-            lo[l] = a;
-            up[l] = bb;
-            if (app) {
-                const size_t gl = pbase + l;
-                const int pos = bucket_slot(P.bcnt + gl);
-                if (pos < P.bcap) *reinterpret_cast<double2*>(P.bucket + (gl * P.bcap + pos) * 2) = make_double2(a, bb);
             }
         }
         if (single) atomicAdd(p.counters, static_cast<unsigned long long>(single));
@@ -743,22 +790,30 @@ __global__ void __launch_bounds__(kPT + 32 * CW, 2) k_minksweep3d_ws(const WsPar
     if (DBG && ctid == 0) {
         long long* d = p.dbg + static_cast<size_t>(blockIdx.x) * 8;
         d[4] = c_wait, d[5] = c_sweep, d[6] = c_d;
-        atomicExch(reinterpret_cast<unsigned long long*>(d), static_cast<unsigned long long>(c_cells));  // ([0] is written by the producers first)
+    }
+    if (DBG && lane == 0) {  // second block of rows: [warp] SWAR, [4 + warp] compaction of every consumer warp ... and warp 0's barrier wait behind them
+        long long* d = p.dbg + (static_cast<size_t>(gridDim.x) * 2 + blockIdx.x) * 8;
+        d[warp] = w_swar, d[4 + warp] = w_comp;
+        long long* d3 = p.dbg + (static_cast<size_t>(gridDim.x) * 3 + blockIdx.x) * 8;
+        d3[warp] = w_first, d3[4 + warp] = w_nchunk;
+        if (warp == 0) {
+            p.dbg[(static_cast<size_t>(gridDim.x) * 4 + blockIdx.x) * 8] = w_bar;
+            p.dbg[static_cast<size_t>(blockIdx.x) * 8] = c_cells;
+        }
     }
 }
 
 // Shared-memory layout; returns the total.
-static size_t ws_layout(WsParams& P, int MODE, int n, int Lx, int Ly) {
+static size_t ws_layout(WsParams& P, int n, int Lx, int Ly) {
     MinkParams& p = P.m;
-    const size_t real = (MODE == HRMGPU_F32) ? 4 : 8;
     auto al = [](size_t v) { return (v + 15) & ~size_t(15); };
     size_t b = 0;
     for (int i = 0; i < 2; ++i) P.o_raw[i] = static_cast<int>(b), b += al(sizeof(double) * (8 * n + kRawExtra));
-    for (int i = 0; i < 2; ++i) P.o_cc[i] = static_cast<int>(b), b += al(real * kColStride * n);
-    for (int i = 0; i < 2; ++i) P.o_rowf[i] = static_cast<int>(b), b += al(real * kRowStride * n);
+    for (int i = 0; i < 2; ++i) P.o_cc[i] = static_cast<int>(b), b += al(sizeof(double) * kColStride * n);
+    for (int i = 0; i < 2; ++i) P.o_rowf[i] = static_cast<int>(b), b += al(sizeof(double) * kRowStride * n);
     for (int i = 0; i < 2; ++i) P.o_vcode[i] = static_cast<int>(b), b += al(2 * (static_cast<size_t>(n) * n + 8));
     p.o_mats = 0;
-    P.o_wtab = static_cast<int>(b), b += sizeof(double) * 24 * kPW;
+    P.o_wtab = static_cast<int>(b), b += sizeof(double) * kWbStride * kPW;
     p.o_txs = static_cast<int>(b), b += al(sizeof(double) * (Lx + 2));
     p.o_tys = static_cast<int>(b), b += al(sizeof(double) * (Ly + 2));
     p.o_queue = static_cast<int>(b), b += 2 * sizeof(uint16_t) * kWsCellCap;
@@ -776,24 +831,27 @@ static size_t ws_layout(WsParams& P, int MODE, int n, int Lx, int Ly) {
 
 // Whether a build of this shape runs on the warp-specialised kernel (otherwise mink3d.cu's one-surface kernel).
 bool ws_supported(const Ctx* c, int precision, bool do_sweep, bool reload, int lpc, int groups, int paired) {
-    if (c->force_classic || !do_sweep || reload || precision == HRMGPU_F64_STRICT) return false;
+    if (c->force_classic || !do_sweep || reload || precision != HRMGPU_F64) return false;
     if (!paired || c->n < 32 || c->n > 128 || (c->n & 3) != 0 || lpc * groups > kPT) return false;  // (scan: 8-byte rows, one unit per lane)
     if (c->Lx > 127 || c->Ly > 127) return false;  // 2 x 8-bit line codes
     return true;
 }
 
-template <int MODE, int CW, int VAR, bool DBG>
+template <int VAR, int NF, bool DBG>
 static int launch_ws_t(Ctx* c, const WsParams& P, int grid, size_t smem) {
-    auto kern = k_minksweep3d_ws<MODE, CW, VAR, DBG>;
+    auto kern = k_minksweep3d_ws<VAR, NF, DBG>;
     HRMGPU_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    kern<<<grid, kPT + 32 * CW, smem, c->stream>>>(P);
+    kern<<<grid, kWsThreads, smem, c->stream>>>(P);
     HRMGPU_CUDA(c, cudaGetLastError());
     c->launches += 1;
     return HRMGPU_OK;
 }
 
+constexpr int kFixedN = 100;  // the grid size with its own instantiation (BASELINE.json configs[4]: 10^4 boundary points)
+
 // Called by launch_minksweep3d (mink3d.cu) with the common parameters filled in.
 int launch_minksweep3d_ws(Ctx* c, const MinkParams& base, int precision, long long items, int* d_bcnt, double* d_bucket, int bcap) {
+    (void)precision;  // HRMGPU_F64 (ws_supported)
     WsParams P;
     P.m = base;
     P.total = static_cast<int>(items);
@@ -802,26 +860,18 @@ int launch_minksweep3d_ws(Ctx* c, const MinkParams& base, int precision, long lo
     P.bucket = d_bucket;
     P.bcap = bcap;
     P.skip_a = std::getenv("HRMGPU_WS_SKIPA") ? 1 : 0;
-    const size_t smem = ws_layout(P, precision, c->n, c->Lx, c->Ly);
+    const size_t smem = ws_layout(P, c->n, c->Lx, c->Ly);
     if (smem > 113 * 1024) return -1000;  // does not fit twice per SM: the caller falls back to the one-surface kernel
     HRMGPU_CUDA(c, cudaMemsetAsync(c->counters.p + 2, 0, sizeof(unsigned long long), c->stream));
     const int grid = static_cast<int>(std::min<long long>(items, 2LL * c->num_sms));
-    const int v = c->ws_variant;  // experiment hook (HRMGPU_WS_VARIANT): 0 = 4 consumer warps 80/80, 1 = 4 x 72/96, 2 = 8 x 80/48, 3 = 8 x 72/56
-    if (precision == HRMGPU_F32) return launch_ws_t<HRMGPU_F32, 4, 0, false>(c, P, grid, smem);
+    const bool fixed = !c->ws_generic && c->n == kFixedN && base.lpc == kFixedN / 2 && base.groups == kPT / (kFixedN / 2);
+    const int v = c->ws_variant;  // experiment hook (HRMGPU_WS_VARIANT): 0 = registers 80 / 80, 1 = 72 / 96 (producers / consumers)
     if (P.m.dbg) {  // profiling builds (tools/phase_times.py): per-role cycle counters
-        switch (v) {
-            case 0: return launch_ws_t<HRMGPU_F64, 4, 0, true>(c, P, grid, smem);
-            case 1: return launch_ws_t<HRMGPU_F64, 4, 1, true>(c, P, grid, smem);
-            case 2: return launch_ws_t<HRMGPU_F64, 8, 1, true>(c, P, grid, smem);
-            default: return launch_ws_t<HRMGPU_F64, 8, 2, true>(c, P, grid, smem);
-        }
+        if (fixed) return v == 0 ? launch_ws_t<0, kFixedN, true>(c, P, grid, smem) : launch_ws_t<1, kFixedN, true>(c, P, grid, smem);
+        return v == 0 ? launch_ws_t<0, 0, true>(c, P, grid, smem) : launch_ws_t<1, 0, true>(c, P, grid, smem);
     }
-    switch (v) {
-        case 0: return launch_ws_t<HRMGPU_F64, 4, 0, false>(c, P, grid, smem);
-        case 1: return launch_ws_t<HRMGPU_F64, 4, 1, false>(c, P, grid, smem);
-        case 2: return launch_ws_t<HRMGPU_F64, 8, 1, false>(c, P, grid, smem);
-        default: return launch_ws_t<HRMGPU_F64, 8, 2, false>(c, P, grid, smem);
-    }
+    if (fixed) return v == 0 ? launch_ws_t<0, kFixedN, false>(c, P, grid, smem) : launch_ws_t<1, kFixedN, false>(c, P, grid, smem);
+    return v == 0 ? launch_ws_t<0, 0, false>(c, P, grid, smem) : launch_ws_t<1, 0, false>(c, P, grid, smem);
 }
 
 template <class K>
@@ -830,9 +880,8 @@ static void touch_ws(K k) {
     if (cudaFuncGetAttributes(&a, k) != cudaSuccess) cudaGetLastError();
 }
 void preload_mink3d_ws() {
-    touch_ws(k_minksweep3d_ws<HRMGPU_F64, 4, 0, false>), touch_ws(k_minksweep3d_ws<HRMGPU_F64, 4, 1, false>);
-    touch_ws(k_minksweep3d_ws<HRMGPU_F64, 8, 1, false>), touch_ws(k_minksweep3d_ws<HRMGPU_F64, 8, 2, false>);
-    touch_ws(k_minksweep3d_ws<HRMGPU_F32, 4, 0, false>);
+    touch_ws(k_minksweep3d_ws<0, 0, false>), touch_ws(k_minksweep3d_ws<1, 0, false>);
+    touch_ws(k_minksweep3d_ws<0, kFixedN, false>), touch_ws(k_minksweep3d_ws<1, kFixedN, false>);
 }
 
 }  // namespace hrmgpu

@@ -50,11 +50,23 @@ def check_against_oracle(oracle, ctx, rows, n, Lx, Ly, semi, R, off, quat, prec,
     return nseg
 
 
-@pytest.mark.parametrize("n,Lx,Ly,n_obs,layers", [(32, 16, 8, 40, 20), (64, 20, 12, 12, 3), (100, 32, 16, 5, 1)])
-def test_ws_f64_against_oracle(oracle, gpu_ctx, n, Lx, Ly, n_obs, layers):
+@pytest.mark.parametrize("n,Lx,Ly,n_obs,layers,generic", [(32, 16, 8, 40, 20, False), (64, 20, 12, 12, 3, False), (100, 32, 16, 5, 1, False),
+                                                          (100, 32, 16, 5, 1, True)])
+def test_ws_f64_against_oracle(oracle, monkeypatch, n, Lx, Ly, n_obs, layers, generic):
     """(32, ...): 820 surfaces, more than the 296 resident CTAs, so every CTA walks several surfaces of different layers;
-    (100, ...): fewer surfaces than CTAs."""
+    (100, ...): fewer surfaces than CTAs; n = 100 runs on the fixed-size instantiation, and once more (generic) on the
+    run-time-size one."""
+    if generic:
+        monkeypatch.setenv("HRMGPU_WS_GENERIC", "1")
     rows, semi, R, off, quat = scene(n, n_obs, layers)
+    gpu_ctx = capi.Context(0)
+    try:
+        _ws_oracle_case(oracle, gpu_ctx, rows, n, Lx, Ly, semi, R, off, quat, layers)
+    finally:
+        gpu_ctx.close()
+
+
+def _ws_oracle_case(oracle, gpu_ctx, rows, n, Lx, Ly, semi, R, off, quat, layers):
     nseg = check_against_oracle(oracle, gpu_ctx, rows, n, Lx, Ly, semi, R, off, quat, capi.F64, range(0, layers, max(1, layers // 3)))
     assert nseg > 0
 
@@ -64,7 +76,7 @@ def test_ws_f32_points_within_tolerance(oracle, gpu_ctx):
     check_against_oracle(oracle, gpu_ctx, rows, 48, 16, 8, semi, R, off, quat, capi.F32, [0, 3])
 
 
-@pytest.mark.parametrize("env", [{}, {"HRMGPU_CELL_SEG_CAP": "3"}, {"HRMGPU_BUCKET_CAP": "2"}, {"HRMGPU_WS_VARIANT": "0"}, {"HRMGPU_WS_VARIANT": "2"}, {"HRMGPU_WS_VARIANT": "3"}])
+@pytest.mark.parametrize("env", [{}, {"HRMGPU_CELL_SEG_CAP": "3"}, {"HRMGPU_BUCKET_CAP": "2"}, {"HRMGPU_WS_VARIANT": "0"}])
 def test_ws_equals_one_surface_kernel(env, monkeypatch):
     """Same intervals (bit for bit: both kernels evaluate the same FMA sequence on the same tables? no -- the tables are built
     slightly differently, so: same hit decisions, <= 1e-9 on end points) and the same free segments as the classic kernel; with
@@ -90,6 +102,28 @@ def test_ws_equals_one_surface_kernel(env, monkeypatch):
             assert np.max(np.abs(a - b), initial=0.0) <= 1e-9
         total += len(s0[1])
     assert total > 500
+
+
+def test_ws_far_away_surface_takes_the_range_checked_path(monkeypatch):
+    """Phase A drops the per-vertex range test of the fixed-point line index for surfaces it proves to be within 2^15 line
+    spacings of the grid; an obstacle 10^6 units away (and one 10^5 units long) fails the proof and must give the same
+    intervals as the one-surface kernel, as must all the other surfaces of the layer."""
+    rows, semi, R, off, quat = scene(13, 12, 3, semi_rng=(0.5, 4.0))
+    rows = np.array(rows, dtype=float)
+    rows[3, 5] = 1.0e6      # centre x of obstacle 2
+    rows[5, 0] = 1.0e5      # first semi-axis of obstacle 4: a needle through the arena
+    monkeypatch.setenv("HRMGPU_CLASSIC", "1")
+    classic = capi.Context(0)
+    ref = build(classic, rows, 40, 24, 12, semi, R, off, capi.F64)
+    classic.close()
+    monkeypatch.delenv("HRMGPU_CLASSIC")
+    ws = capi.Context(0)
+    got = build(ws, rows, 40, 24, 12, semi, R, off, capi.F64)
+    ws.close()
+    for ((lo0, up0), s0), ((lo1, up1), s1) in zip(ref, got):
+        assert np.array_equal(np.isnan(lo0), np.isnan(lo1))
+        assert np.nanmax(np.abs(lo0 - lo1)) <= 1e-6 and np.nanmax(np.abs(up0 - up1)) <= 1e-6
+        assert np.array_equal(s0[0], s1[0])
 
 
 def test_ws_resweep_and_queries_use_the_stored_points(gpu_ctx):

@@ -32,11 +32,20 @@ if not os.environ.get("HRMGPU_CLASSIC"):
     # warp-specialised persistent kernel: one row per resident CTA, cycles of thread 0 of each role summed over its surfaces
     names = ["C: cell tests (+ heavy)", "P: wait (inputs + consumers)", "P: tables", "P: phase A", "C: wait for producers", "C: scan",
              "C: phase D", "surfaces"]
-    rows_ = out[out[:, 7] > 0]
+    rows_ = out[:min(n_cta, 2 * 148)]  # one row per resident CTA (2 per SM); rows 2g.. / 4g.. hold the per-warp scan details
     print("resident CTAs", len(rows_), "surfaces", rows_[:, 7].sum())
     for i, nm in enumerate(names):
         v = rows_[:, i] / (rows_[:, 7] if i < 7 else 1)
         print("   %-30s per surface: mean %10.1f  p50 %10.1f  max %10.1f" % (nm, v.mean(), np.percentile(v, 50), v.max()))
+    g = len(rows_)
+    ex = out[2 * g:3 * g] / rows_[:, 7:8]
+    print("   scan per consumer warp (cycles per surface): SWAR tests %s | compaction %s | warp 0 waiting at the scan barrier %.0f"
+          % (np.round(ex[:, 0:4].mean(axis=0)), np.round(ex[:, 4:8].mean(axis=0)), (out[4 * g:5 * g, 0] / rows_[:, 7]).mean()))
+    e3 = out[3 * g:4 * g] / rows_[:, 7:8]
+    print("   first SWAR section of a surface, per warp: %s | SWAR sections (chunks incl. re-entries) per surface: %s"
+          % (np.round(e3[:, 0:4].mean(axis=0)), np.round(e3[:, 4:8].mean(axis=0), 2)))
+    for blk in (0, 1, g - 1):
+        print("   CTA %d hardware warp slots: producers %s consumers %s" % (blk, out[6 * g + blk].tolist(), out[7 * g + blk, :4].tolist()))
     ctx.close()
     sys.exit(0)
 names = ["prologue", "phase A", "scan + tests", "of which C", "max B1 (warp)", "prologue: loads", "max D (thread)", "total"]
