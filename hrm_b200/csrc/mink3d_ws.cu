@@ -32,7 +32,10 @@ namespace hrmgpu {
 
 constexpr int kPW = 8;                 // producer warps
 constexpr int kPT = 32 * kPW;
-constexpr int kCW = 4;                 // consumer warps
+#ifndef HRMGPU_WS_CW
+#define HRMGPU_WS_CW 4
+#endif
+constexpr int kCW = HRMGPU_WS_CW;      // consumer warps (4; 5 = experiment: all threads at 72 registers, no setmaxnreg)
 constexpr int kCT = 32 * kCW;
 constexpr int kWsThreads = kPT + kCT;
 constexpr int kDeferLines = 512;       // sweep lines whose bucket appends are deferred to the next surface (CT * lines per thread)
@@ -40,8 +43,8 @@ constexpr int kDeferLines = 512;       // sweep lines whose bucket appends are d
 // thread to the consumers (72 / 96, setmaxnreg).  (8 consumer warps at 48 / 56 registers were measured: 20-30 % slower.)
 template <int VAR>
 struct RegSplit {
-    static constexpr int prod = VAR == 1 ? 72 : 0;
-    static constexpr int cons = VAR == 1 ? 96 : 0;
+    static constexpr int prod = (VAR == 1 && kCW == 4) ? 72 : 0;
+    static constexpr int cons = (VAR == 1 && kCW == 4) ? 96 : 0;
 };
 constexpr int kWsCellCap = 1024;       // kept mesh cells listed per scan round (256 per consumer warp, as in the one-surface kernel)
 constexpr int kZCap = 512;             // hit heights remembered per surface (phase C -> phase D)
@@ -172,7 +175,7 @@ __device__ __forceinline__ uint32_t line_q_inrange(double x, double inv_d, doubl
 // NF: grid size n fixed at compile time (0: taken from the parameters).
 template <int VAR, int NF, bool DBG>
 __global__ void __launch_bounds__(kWsThreads, 2) k_minksweep3d_ws(const WsParams P) {
-    constexpr int kDU = kDeferLines / kCT;  // deferred lines per consumer thread
+    constexpr int kDU = (kDeferLines + kCT - 1) / kCT;  // deferred lines per consumer thread
     using Regs = RegSplit<VAR>;
     using Code = uint16_t;  // 2 x 8-bit line codes (both axes <= 127 lines)
     using A = Fast;
@@ -392,13 +395,28 @@ __global__ void __launch_bounds__(kWsThreads, 2) k_minksweep3d_ws(const WsParams
                     uint32_t ca = smem_u32(cc) + static_cast<uint32_t>(grp * kColStride * sizeof(double));
                     uint32_t va = smem_u32(vcode) + static_cast<uint32_t>((grp * n + r0) * sizeof(Code));
                     double* gx = mx + grp * n + r0;
+                    // Software pipeline over the columns (the loop is bound by the latency of its shared-memory loads, not by their
+                    // number): the three norm constants {a, b, d} of a column are fetched one iteration ahead, so an iteration opens
+                    // with its two rsqrt chains, and the other eight constants arrive underneath them.  Same operations on the same
+                    // values as eval_point (the consumers re-evaluate corners with it).
+                    double ka, kb, kd;
+                    lds_pair(ca + 8 * sizeof(double), ka, kb);
+                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(kd) : "r"(ca + 10 * static_cast<uint32_t>(sizeof(double))));
                     for (int c = grp; c < n; c += groups, ca += cc_step, va += v_step, gx += g_step) {
-                        double kk[12];
+                        const double nn0 = fm(ka, F[0][6], fm(kb, F[0][7], kd)), nn1 = fm(ka, F[1][6], fm(kb, F[1][7], kd));
+                        double kk[8];
 #pragma unroll
-                        for (int i = 0; i < 6; ++i) lds_pair(ca + i * 2 * sizeof(double), kk[2 * i], kk[2 * i + 1]);
+                        for (int i = 0; i < 4; ++i) lds_pair(ca + i * 2 * sizeof(double), kk[2 * i], kk[2 * i + 1]);
+                        const double inv0 = fast_rsqrt(nn0), inv1 = fast_rsqrt(nn1);
+                        // (the last iteration reads the 24 bytes behind the table: still inside this CTA's shared memory, never used)
+                        lds_pair(ca + cc_step + 8 * sizeof(double), ka, kb);
+                        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(kd) : "r"(ca + cc_step + 10 * static_cast<uint32_t>(sizeof(double))));
                         double o[2][3];
-                        eval_point(kk, F[0], o[0]);
-                        eval_point(kk, F[1], o[1]);
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) {
+                            o[0][d] = fm(fm(kk[1], F[0][3 + d], kk[5 + d]), inv0, fm(kk[0], F[0][d], kk[2 + d]));
+                            o[1][d] = fm(fm(kk[1], F[1][3 + d], kk[5 + d]), inv1, fm(kk[0], F[1][d], kk[2 + d]));
+                        }
                         *reinterpret_cast<R2*>(gx) = R2{o[0][0], o[1][0]};
                         *reinterpret_cast<R2*>(gx + M) = R2{o[0][1], o[1][1]};
                         *reinterpret_cast<R2*>(gx + 2 * static_cast<size_t>(M)) = R2{o[0][2], o[1][2]};
@@ -475,8 +493,8 @@ __global__ void __launch_bounds__(kWsThreads, 2) k_minksweep3d_ws(const WsParams
     int* zcount = qcount;
     int* hcount = qcount + 2;
     int* segcnt = qcount + 4;
-    int* scan_next = qcount + 8;  // next chunk of mesh rows / next batch of kept cells: the consumer warps claim their work, because the
-    int* cell_next = qcount + 9;  // warp that shares its scheduler with the busiest producer warps runs at less than half the others' pace
+    int* scan_next = qcount + 12;  // next chunk of mesh rows / next batch of kept cells: the consumer warps claim their work, because the
+    int* cell_next = qcount + 13;  // warp that shares its scheduler with the busiest producer warps runs at less than half the others' pace
     const int nc1 = n - 1;
     const int ncell = nc1 * nc1;
     const uint32_t nc1_magic = 0xFFFFFFFFu / static_cast<uint32_t>(nc1) + 1u;
@@ -770,7 +788,7 @@ __global__ void __launch_bounds__(kWsThreads, 2) k_minksweep3d_ws(const WsParams
 #pragma unroll
             for (int u = 0; u < kDU; ++u) {
                 const int l = lb + ctid + u * kCT;
-                if (l < p.L) {
+                if (l < p.L && ctid + u * kCT < kDeferLines) {
                     double a, bb;
                     if (interval(l, a, bb)) {
                         stash[ctid * kDU + u] = make_double2(a, bb);
@@ -818,7 +836,7 @@ static size_t ws_layout(WsParams& P, int n, int Lx, int Ly) {
     p.o_tys = static_cast<int>(b), b += al(sizeof(double) * (Ly + 2));
     p.o_queue = static_cast<int>(b), b += 2 * sizeof(uint16_t) * kWsCellCap;
     P.o_zpool = static_cast<int>(b), b += sizeof(double) * kZCap;
-    P.o_stash = static_cast<int>(b), b += sizeof(double2) * kDeferLines;
+    P.o_stash = static_cast<int>(b), b += sizeof(double2) * kCT * ((kDeferLines + kCT - 1) / kCT);
     const size_t L = static_cast<size_t>(Lx) * Ly;
     p.o_m0 = static_cast<int>(b), b += al(sizeof(uint32_t) * L);
     p.o_m1 = static_cast<int>(b), b += al(sizeof(uint32_t) * L);
