@@ -1,4 +1,5 @@
-"""Tiny deterministic run of every precision mode (for compute-sanitizer): bundled cluttered map, n=10, 3 layers."""
+"""Tiny deterministic run of every precision mode and both fused kernels (for compute-sanitizer): bundled cluttered map,
+n = 10 / 23 (one-surface kernel) and n = 36 in HRMGPU_F64 (persistent warp-specialised kernel), 3 layers, then a re-sweep."""
 import os
 import sys
 
@@ -16,4 +17,10 @@ for n in (10, 23):
     for prec in (capi.F64_STRICT, capi.F64, capi.F32):
         ctx.build_layers(semi, R, off, prec)
         print(n, prec, ctx.dims()["segments"], ctx.single_hit_count())
+ctx.set_scene3d(1, len(sc["obstacle"]), util.sq17(rows, 36), 36)
+ctx.set_sweep(sc["lim"], 20, 10)
+ctx.build_layers(semi, R, off, capi.F64)
+print(36, capi.F64, ctx.dims()["segments"], ctx.single_hit_count())
+ctx.resweep(sc["lim"], 12, 6)
+print("resweep", ctx.dims()["segments"])
 ctx.close()
