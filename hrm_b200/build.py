@@ -18,6 +18,8 @@ HOST_LIB = os.path.join(LIBDIR, "libhrmhost.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall", "--expt-relaxed-constexpr"]
+# per-file additions: tfe.cu mirrors host arithmetic operation for operation (no multiply-add contraction)
+FILE_FLAGS = {"tfe.cu": ["-fmad=false"]}
 
 
 def sources():
@@ -43,7 +45,7 @@ def build(force=False, verbose=False):
         obj = os.path.join(OBJ, s[:-3] + ".o")
         objs.append(obj)
         if force or _stale(obj, [src] + headers):
-            cmd = [NVCC] + ARCH + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            cmd = [NVCC] + ARCH + FLAGS + FILE_FLAGS.get(s, []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
             jobs.append(cmd)
 
     def run(cmd):

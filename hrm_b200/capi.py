@@ -58,7 +58,9 @@ def load():
         "hrmgpu_test_bridge_multi": (i, [vp, i, vp, vp, vp]),
         "hrmgpu_test_transitions": (i, [vp, i, vp, vp, vp, i, vp, vp, vp, vp]),
         "hrmgpu_test_transitions_articulated": (i, [vp, i, vp, vp, vp, i, vp, vp, vp, vp, vp]),
+        "hrmgpu_connect_pairs3d": (ll, [vp, ll, vp, i, vp, C.c_double, C.c_double, i, vp, vp, vp, vp, ll, vp]),
         "hrmgpu_build_bridge": (i, [vp, i, i, vp, vp, i]),
+        "hrmgpu_build_bridge_tfe": (i, [vp, i, i, vp, vp, vp, i, i, vp]),
         "hrmgpu_build_bridge2d": (i, [vp, i, i, vp, vp, i]),
         "hrmgpu_test_bridge": (i, [vp, i, i, vp, vp]),
         "hrmgpu_pack_segments_dev": (ll, [vp, vp, ll]),
@@ -268,6 +270,17 @@ class Context:
         tfe_R = _d(tfe_R).reshape(P, B, 9)
         self._chk(self.lib.hrmgpu_build_bridge(self.h, P, B, _p(tfe_semi), _p(tfe_R), precision))
 
+    def build_bridge_tfe(self, body_semi, quat_a, quat_b, num_step, precision=F64_STRICT):
+        """computeTFE + bridgeSlice on the device (hrmgpu_build_bridge_tfe): body_semi [B][3], quat_a / quat_b [P][B][4];
+        returns the fitted ellipsoids [P][B][7] (semi-axes, quaternion)."""
+        body_semi = _d(body_semi).reshape(-1, 3)
+        B = body_semi.shape[0]
+        quat_a, quat_b = _d(quat_a).reshape(-1, B, 4), _d(quat_b).reshape(-1, B, 4)
+        P = quat_a.shape[0]
+        out = np.zeros((P, B, 7))
+        self._chk(self.lib.hrmgpu_build_bridge_tfe(self.h, P, B, _p(body_semi), _p(quat_a), _p(quat_b), int(num_step), precision, _p(out)))
+        return out
+
     def build_bridge2d(self, tfe_semi, tfe_angle, precision=F64_STRICT):
         tfe_semi = _d(tfe_semi)
         P, B = tfe_semi.shape[0], tfe_semi.shape[1]
@@ -307,6 +320,19 @@ class Context:
             self._chk(self.lib.hrmgpu_test_transitions_articulated(self.h, Cn, _p(pair), _p(v0), _p(v1), w0.shape[0], _p(w0), _p(w1), _p(link_off),
                                                                    _p(chain_off), _p(out)))
         return out.astype(bool)
+
+    def connect_pairs3d(self, vertex_xyz, range4, thx, thy, w0, w1, link_off):
+        """connectMultiSlice's vertex matching on the device (see include/hrmgpu.h): vertex_xyz [V][3], range4 [P][4] =
+        {near begin, near end, cur begin, cur end}; returns (match, transition tests made), match[first(p) + (m0 - near begin)] =
+        id of the vertex that m0 connects to, or -1."""
+        xyz = _d(vertex_xyz).reshape(-1, 3)
+        r4 = np.ascontiguousarray(range4, dtype=np.int32).reshape(-1, 4)
+        w0, w1, link_off = _d(w0), _d(w1), _d(link_off)
+        match = np.full(max(1, int((r4[:, 1] - r4[:, 0]).sum())), -1, dtype=np.int32)
+        ncand = C.c_longlong(0)
+        n = self._chk(self.lib.hrmgpu_connect_pairs3d(self.h, xyz.shape[0], _p(xyz), r4.shape[0], _p(r4), float(thx), float(thy), w0.shape[0], _p(w0),
+                                                      _p(w1), _p(link_off), _p(match), match.shape[0], C.byref(ncand)))
+        return match[:n], int(ncand.value)
 
     def pack_segments_dev(self, d_ptr=None, cap_bytes=0):
         return self._chk(self.lib.hrmgpu_pack_segments_dev(self.h, C.c_void_p(d_ptr) if d_ptr else None, cap_bytes))

@@ -176,7 +176,7 @@ int hrmgpu_create(hrmgpu_ctx** out, int device, unsigned flags) {
     }
     {
         static std::once_flag once;
-        std::call_once(once, [] { preload_mink3d(), preload_mink2d(), preload_segments(), preload_queries(), preload_exchange(); });
+        std::call_once(once, [] { preload_mink3d(), preload_mink2d(), preload_segments(), preload_queries(), preload_exchange(), preload_connect(), preload_tfe(); });
     }
     // test hooks of the segment pass (tests/test_gpu_layers3d.py): list capacity of the 4-line kernel / one-line kernel only
     if (const char* e = std::getenv("HRMGPU_SEG_FAST_CAP")) c->seg_fast_cap = std::atoi(e);
@@ -252,6 +252,9 @@ void hrmgpu_destroy(hrmgpu_ctx* c) {
     release(c, c->q_w);
     release(c, c->q_loff);
     release(c, c->q_loff2);
+    release(c, c->pc_layers), release(c, c->pc_cnt), release(c, c->pc_m1), release(c, c->pc_match);
+    release(c, c->pc_m0_first), release(c, c->pc_first), release(c, c->pc_info), release(c, c->pc_vtx);
+    release(c, c->tfe_in), release(c, c->tfe_quat);
     release(c, c->bridge_bbox);
     release(c, c->bridge_semi);
     release(c, c->bridge_R);
@@ -565,6 +568,41 @@ int hrmgpu_test_edges_multi(hrmgpu_ctx* c, int E, const int* layer, const double
     return HRMGPU_OK;
 }
 
+// The Minkowski sums of every obstacle with the P x B ellipsoids in c->bridge_semi / c->bridge_R (already on the device).
+static int build_bridge_meshes(hrmgpu_ctx* c, int P, int B, int precision, int dim) {
+    const int M = (dim == 3) ? c->n * c->n : c->n;
+    const size_t real = (precision == HRMGPU_F32) ? 4 : 8;
+    int rc;
+    if ((rc = ensure(c, c->bridge_mesh, static_cast<size_t>(P) * c->n_obs * B * dim * M * real))) return rc;
+    if (dim == 3) {
+        // ONE launch for all pairs: layer = pair, with the pair's own body semi-axes (semi_per_layer)
+        if ((rc = ensure(c, c->bridge_off, static_cast<size_t>(P > 0 ? P : 1) * B * 3))) return rc;
+        HRMGPU_CUDA(c, cudaMemsetAsync(c->bridge_off.p, 0, sizeof(double) * static_cast<size_t>(P > 0 ? P : 1) * B * 3, c->stream));
+        if (P > 0) {
+            c->semi_per_layer = true;
+            rc = launch_minksweep3d(c, P, B, c->n_arena, c->n_obs, c->bridge_semi.p, c->bridge_R.p, c->bridge_off.p, precision, c->bridge_mesh.p, nullptr, nullptr, false);
+            c->semi_per_layer = false;
+            if (rc) return rc;
+        }
+    } else {
+        std::vector<double> zeros(static_cast<size_t>(B) * dim, 0.0);
+        if ((rc = upload(c, c->bridge_off, zeros.data(), zeros.size()))) return rc;
+        for (int pi = 0; pi < P; ++pi) {  // every pair has its own body shapes: one layer-batch per pair with that pair's semi-axes
+            char* mesh = c->bridge_mesh.p + static_cast<size_t>(pi) * c->n_obs * B * dim * M * real;
+            rc = launch_minksweep2d(c, 1, B, c->n_arena, c->n_obs, c->bridge_semi.p + static_cast<size_t>(pi) * B * 2,
+                                    c->bridge_R.p + static_cast<size_t>(pi) * B * 2, c->bridge_off.p, precision, mesh, nullptr, nullptr, false);
+            if (rc) return rc;
+        }
+    }
+    c->P = P;
+    c->bridge_B = B;
+    c->bridge_prec = precision;
+    if ((rc = launch_bridge_bbox(c))) return rc;
+    HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->bridge_built = true;
+    return HRMGPU_OK;
+}
+
 static int build_bridge_common(hrmgpu_ctx* c, int P, int B, const double* semi, const double* rot, int precision, int dim) {
     if (!c) return HRMGPU_E_ARG;
     if (c->dim != dim) return fail(c, HRMGPU_E_STATE, "build_bridge: scene dimension mismatch");
@@ -572,13 +610,7 @@ static int build_bridge_common(hrmgpu_ctx* c, int P, int B, const double* semi, 
     if (precision < HRMGPU_F64_STRICT || precision > HRMGPU_F32) return fail(c, HRMGPU_E_ARG, "build_bridge: unknown precision");
     if (dim == 2 && precision == HRMGPU_F32) precision = HRMGPU_F64;
     HRMGPU_CUDA(c, cudaSetDevice(c->device));
-    const int M = (dim == 3) ? c->n * c->n : c->n;
-    const size_t real = (precision == HRMGPU_F32) ? 4 : 8;
     int rc;
-    if ((rc = ensure(c, c->bridge_mesh, static_cast<size_t>(P) * c->n_obs * B * dim * M * real))) return rc;
-    // every pair has its own body shapes: launch one layer-batch per pair with that pair's semi-axes
-    std::vector<double> zeros(static_cast<size_t>(B) * dim, 0.0);
-    if ((rc = upload(c, c->bridge_off, zeros.data(), zeros.size()))) return rc;
     if ((rc = upload(c, c->bridge_semi, semi, static_cast<size_t>(P) * B * dim))) return rc;
     std::vector<double> cs;
     if (dim == 3) {
@@ -588,23 +620,42 @@ static int build_bridge_common(hrmgpu_ctx* c, int P, int B, const double* semi, 
         for (size_t i = 0; i < static_cast<size_t>(P) * B; ++i) cs[2 * i] = std::cos(rot[i]), cs[2 * i + 1] = std::sin(rot[i]);
         if ((rc = upload(c, c->bridge_R, cs.data(), cs.size()))) return rc;
     }
-    for (int pi = 0; pi < P; ++pi) {
-        char* mesh = c->bridge_mesh.p + static_cast<size_t>(pi) * c->n_obs * B * dim * M * real;
-        if (dim == 3)
-            rc = launch_minksweep3d(c, 1, B, c->n_arena, c->n_obs, c->bridge_semi.p + static_cast<size_t>(pi) * B * 3,
-                                    c->bridge_R.p + static_cast<size_t>(pi) * B * 9, c->bridge_off.p, precision, mesh, nullptr, nullptr, false);
-        else
-            rc = launch_minksweep2d(c, 1, B, c->n_arena, c->n_obs, c->bridge_semi.p + static_cast<size_t>(pi) * B * 2,
-                                    c->bridge_R.p + static_cast<size_t>(pi) * B * 2, c->bridge_off.p, precision, mesh, nullptr, nullptr, false);
-        if (rc) return rc;
+    return build_bridge_meshes(c, P, B, precision, dim);  // (synchronises: cs / the caller's arrays are pageable host memory)
+}
+
+int hrmgpu_build_bridge_tfe(hrmgpu_ctx* c, int P, int B, const double* body_semi, const double* quat_a, const double* quat_b, int num_step, int precision,
+                            double* tfe_out) {
+    if (!c) return HRMGPU_E_ARG;
+    if (c->dim != 3) return fail(c, HRMGPU_E_STATE, "build_bridge_tfe: 3D scenes only");
+    if (P < 0 || B < 1 || num_step < 1 || (P > 0 && (!body_semi || !quat_a || !quat_b))) return fail(c, HRMGPU_E_ARG, "build_bridge_tfe: bad arguments");
+    if (precision < HRMGPU_F64_STRICT || precision > HRMGPU_F32) return fail(c, HRMGPU_E_ARG, "build_bridge_tfe: unknown precision");
+    HRMGPU_CUDA(c, cudaSetDevice(c->device));
+    int rc;
+    const size_t PB = static_cast<size_t>(P) * B;
+    std::vector<double> in(3 * static_cast<size_t>(B) + 8 * PB);
+    std::copy(body_semi, body_semi + 3 * static_cast<size_t>(B), in.begin());
+    if (PB) {
+        std::copy(quat_a, quat_a + 4 * PB, in.begin() + 3 * static_cast<size_t>(B));
+        std::copy(quat_b, quat_b + 4 * PB, in.begin() + 3 * static_cast<size_t>(B) + 4 * PB);
     }
-    c->P = P;
-    c->bridge_B = B;
-    c->bridge_prec = precision;
-    if ((rc = launch_bridge_bbox(c))) return rc;
-    HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));
-    c->bridge_built = true;
-    return HRMGPU_OK;
+    if ((rc = upload(c, c->tfe_in, in.data(), in.size()))) return rc;
+    if ((rc = ensure(c, c->bridge_semi, 3 * PB))) return rc;
+    if ((rc = ensure(c, c->bridge_R, 9 * PB))) return rc;
+    if ((rc = ensure(c, c->tfe_quat, 4 * PB))) return rc;
+    if ((rc = launch_tfe3d(c, P, B, c->tfe_in.p, c->tfe_in.p + 3 * static_cast<size_t>(B), c->tfe_in.p + 3 * static_cast<size_t>(B) + 4 * PB, num_step,
+                           c->bridge_semi.p, c->bridge_R.p, c->tfe_quat.p)))
+        return rc;
+    if (tfe_out && PB) {  // [P][B][7]: semi-axes, quaternion (w, x, y, z)
+        std::vector<double> s(3 * PB), q(4 * PB);
+        HRMGPU_CUDA(c, cudaMemcpyAsync(s.data(), c->bridge_semi.p, sizeof(double) * 3 * PB, cudaMemcpyDeviceToHost, c->stream));
+        HRMGPU_CUDA(c, cudaMemcpyAsync(q.data(), c->tfe_quat.p, sizeof(double) * 4 * PB, cudaMemcpyDeviceToHost, c->stream));
+        HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (size_t i = 0; i < PB; ++i) {
+            for (int d = 0; d < 3; ++d) tfe_out[7 * i + d] = s[3 * i + d];
+            for (int d = 0; d < 4; ++d) tfe_out[7 * i + 3 + d] = q[4 * i + d];
+        }
+    }
+    return build_bridge_meshes(c, P, B, precision, 3);  // (synchronises: `in` is pageable host memory)
 }
 
 int hrmgpu_build_bridge(hrmgpu_ctx* c, int P, int B, const double* tfe_semi, const double* tfe_R, int precision) {
@@ -688,6 +739,74 @@ int hrmgpu_test_transitions_articulated(hrmgpu_ctx* c, int C, const int* pair, c
                                         const double* w1, const double* link_off, const double* chain_off, unsigned char* free_out) {
     if (c && !chain_off) return fail(c, HRMGPU_E_ARG, "test_transitions_articulated: bad arguments");
     return test_transitions_common(c, C, pair, v0, v1, T, w0, w1, link_off, chain_off, free_out);
+}
+
+long long hrmgpu_connect_pairs3d(hrmgpu_ctx* c, long long V, const double* vertex_xyz, int P, const int* range4, double thx, double thy, int T,
+                                 const double* w0, const double* w1, const double* link_off, int* match_out, long long match_cap,
+                                 long long* n_candidates_out) {
+    if (!c) return HRMGPU_E_ARG;
+    if (c->dim != 3 || !c->bridge_built) return fail(c, HRMGPU_E_STATE, "connect_pairs3d: no 3D bridge layers built");
+    if (V < 0 || V > 0x7FFFFFF0LL || P < 0 || P != c->P || T < 1 || (P > 0 && (!vertex_xyz || !range4 || !w0 || !w1 || !link_off || !match_out)))
+        return fail(c, HRMGPU_E_ARG, "connect_pairs3d: bad arguments (P must equal the number of bridge layers)");
+    if (n_candidates_out) *n_candidates_out = 0;
+    std::vector<long long> m0_first(static_cast<size_t>(P) + 1, 0);
+    long long max_n0 = 0;
+    for (int i = 0; i < P; ++i) {
+        const int* r = range4 + 4 * static_cast<size_t>(i);
+        if (r[0] < 0 || r[1] < r[0] || r[1] > V || r[2] < 0 || r[3] < r[2] || r[3] > V) return fail(c, HRMGPU_E_ARG, "connect_pairs3d: vertex range out of bounds");
+        m0_first[i + 1] = m0_first[i] + (r[1] - r[0]);
+        max_n0 = std::max<long long>(max_n0, r[1] - r[0]);
+    }
+    const long long M0 = m0_first[P];
+    if (M0 > match_cap) return fail(c, HRMGPU_E_CAP, "connect_pairs3d: match_out too small");
+    if (M0 == 0) return 0;
+    if (M0 > 0x7FFFFFF0LL) return fail(c, HRMGPU_E_CAP, "connect_pairs3d: too many vertices");
+    HRMGPU_CUDA(c, cudaSetDevice(c->device));
+    int rc;
+    if ((rc = upload(c, c->pc_vtx, vertex_xyz, 3 * static_cast<size_t>(V)))) return rc;
+    if ((rc = upload(c, c->pc_layers, range4, 4 * static_cast<size_t>(P)))) return rc;
+    if ((rc = upload(c, c->pc_m0_first, m0_first.data(), m0_first.size()))) return rc;
+    if ((rc = ensure(c, c->pc_cnt, static_cast<size_t>(M0)))) return rc;
+    if ((rc = ensure(c, c->pc_first, static_cast<size_t>(M0) + 1))) return rc;
+    if ((rc = ensure(c, c->pc_info, 2))) return rc;
+    PairParams p;
+    p.vtx = c->pc_vtx.p;
+    p.range = c->pc_layers.p;
+    p.m0_first = c->pc_m0_first.p;
+    p.cand_first = c->pc_first.p;
+    p.cnt = c->pc_cnt.p;
+    p.c_pair = nullptr, p.c_v0 = nullptr, p.c_v1 = nullptr, p.c_m1 = nullptr;
+    p.P = P;
+    p.thx = thx, p.thy = thy;
+    if ((rc = launch_pair_candidates(c, p, max_n0, false))) return rc;
+    if ((rc = launch_scan_counts(c, c->pc_cnt.p, c->pc_first.p, M0, c->pc_info.p, c->stream))) return rc;
+    long long total = 0;
+    HRMGPU_CUDA(c, cudaMemcpyAsync(&total, c->pc_first.p + M0, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));  // (also: the uploads above come from pageable host memory)
+    if (n_candidates_out) *n_candidates_out = total;
+    if (total > 0x7FFFFFF0LL) return fail(c, HRMGPU_E_CAP, "connect_pairs3d: too many candidate pairs for one launch");
+    const size_t C = static_cast<size_t>(total);
+    if ((rc = ensure(c, c->pc_match, static_cast<size_t>(M0)))) return rc;
+    if ((rc = ensure(c, c->pc_m1, C))) return rc;
+    if ((rc = ensure(c, c->q_out, C))) return rc;
+    if (C > 0) {
+        if ((rc = ensure(c, c->q_set, C))) return rc;
+        if ((rc = ensure(c, c->q_a, 3 * C))) return rc;
+        if ((rc = ensure(c, c->q_b, 3 * C))) return rc;
+        p.c_pair = c->q_set.p, p.c_v0 = c->q_a.p, p.c_v1 = c->q_b.p, p.c_m1 = c->pc_m1.p;
+        if ((rc = launch_pair_candidates(c, p, max_n0, true))) return rc;
+        std::vector<double> w(2 * static_cast<size_t>(T));
+        for (int s = 0; s < T; ++s) w[s] = w0[s], w[T + s] = w1[s];
+        if ((rc = upload(c, c->q_w, w.data(), w.size()))) return rc;
+        const size_t nl = static_cast<size_t>(c->P) * T * c->bridge_B * 3;
+        if ((rc = upload(c, c->q_loff, link_off, nl))) return rc;
+        if ((rc = launch_transitions(c, static_cast<int>(C), T, c->q_set.p, c->q_a.p, c->q_b.p, c->q_w.p, c->q_w.p + T, c->q_loff.p, c->q_out.p, nullptr)))
+            return rc;
+    }
+    if ((rc = launch_pair_replay(c, P, c->pc_m0_first.p, c->pc_first.p, c->pc_m1.p, c->q_out.p, c->pc_match.p))) return rc;
+    HRMGPU_CUDA(c, cudaMemcpyAsync(match_out, c->pc_match.p, sizeof(int) * static_cast<size_t>(M0), cudaMemcpyDeviceToHost, c->stream));
+    HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));  // (w is pageable host memory: its copy has completed when the call returns)
+    return M0;
 }
 
 int hrmgpu_get_dims(hrmgpu_ctx* c, long long* out) {

@@ -89,6 +89,7 @@ struct Ctx {
     int bucket_cap = 0;
     int bucket_cap_hook = 0;                     // test hook: bucket capacity (small values force the dense fallback per line)
     int ws_variant = 1;                          // experiment hook: warp / register split of the warp-specialised kernel (mink3d_ws.cu)
+    bool semi_per_layer = false;                 // set around the bridge build: body semi-axes per layer (pair), see MinkParams
     bool force_classic = false;                  // test / profiling hook: never use the warp-specialised kernel
     bool ws_generic = false;                     // test hook (HRMGPU_WS_GENERIC): run-time grid size even where a fixed-n instantiation exists
     int num_sms = 148;                           // multiprocessors of the device
@@ -131,6 +132,11 @@ struct Ctx {
     DevBuf<char> bridge_mesh;  // [P][n_obs][B][dim][M]
     DevBuf<double> bridge_semi, bridge_R, bridge_off;
     DevBuf<double> bridge_bbox;                  // [P][n_obs * B][6] (3D)
+    DevBuf<int> pc_layers, pc_cnt, pc_m1, pc_match;   // device-side vertex matching of connectMultiSlice (connect.cu)
+    DevBuf<double> pc_vtx;
+    DevBuf<double> tfe_in, tfe_quat;                  // device TFE: {body semi [B][3], quat a [P][B][4], quat b [P][B][4]}, result quaternions
+    DevBuf<long long> pc_m0_first, pc_first;
+    DevBuf<unsigned long long> pc_info;
     DevBuf<double> q_w, q_loff, q_loff2;         // transition tests: interpolation weights [2][T], link offsets [P][T][B][dim] (+ chain offsets)
 };
 
@@ -200,6 +206,29 @@ int finalize_segments(Ctx* c);
 int launch_edges(Ctx* c, int k, int E, const double* d_v1, const double* d_v2, unsigned char* d_out, const int* d_layer = nullptr);
 int launch_bridge_test(Ctx* c, int p, int Q, const double* d_centres, unsigned char* d_out, const int* d_pair = nullptr);
 int launch_bridge_bbox(Ctx* c);
+// connect.cu: connectMultiSlice's vertex matching from the CSR free segments (HRM3D.cpp:158-224)
+struct PairParams {
+    const double* vtx;         // [V][3] vertex positions of the roadmap
+    const int* range;          // [P][4] vertex id ranges {near begin, near end, cur begin, cur end}
+    const long long* m0_first; // [P + 1] running count of m0 over the pairs
+    long long* cand_first;     // [M0 + 1] offsets of every m0's candidates (fill pass)
+    int* cnt;                  // [M0] (count pass)
+    int* c_pair;               // [C]
+    double* c_v0;              // [C][3]
+    double* c_v1;              // [C][3]
+    int* c_m1;                 // [C] vertex id of the candidate m1
+    int P;
+    double thx, thy;
+};
+int launch_pair_candidates(Ctx* c, const PairParams& p, long long max_n0, bool fill);
+int launch_pair_replay(Ctx* c, int P, const long long* m0_first, const long long* cand_first, const int* c_m1, const unsigned char* free_flag, int* match);
+void preload_connect();
+// tfe.cu: tightly-fitted ellipsoids of all (pair, body) combinations (TightFitEllipsoid.cpp:43-114)
+int launch_tfe3d(Ctx* c, int P, int B, const double* d_body_semi, const double* d_quat_a, const double* d_quat_b, int num_step, double* d_semi,
+                 double* d_rot, double* d_quat);
+void preload_tfe();
+// segments.cu: exclusive scan of n counts into n + 1 64-bit offsets (single CTA), info[1] = total
+int launch_scan_counts(Ctx* c, const int* cnt, long long* off, long long n, unsigned long long* info, cudaStream_t st);
 int launch_transitions(Ctx* c, int C, int T, const int* d_pair, const double* d_v0, const double* d_v1, const double* d_w0, const double* d_w1,
                        const double* d_link_off, unsigned char* d_out, const double* d_link_off2 = nullptr);
 

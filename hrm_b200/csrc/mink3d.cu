@@ -121,7 +121,8 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : (MOD
         const double* r2 = p.R + (static_cast<size_t>(k) * p.B + b) * 9;
         mi0 = __ldg(r2 + 3 * i), mi1 = __ldg(r2 + 3 * i + 1), mi2 = __ldg(r2 + 3 * i + 2);
         mj0 = __ldg(r2 + 3 * j), mj1 = __ldg(r2 + 3 * j + 1), mj2 = __ldg(r2 + 3 * j + 2);
-        md0 = __ldg(p.semi + 3 * b), md1 = __ldg(p.semi + 3 * b + 1), md2 = __ldg(p.semi + 3 * b + 2);
+        const double* sm = p.semi + 3 * (p.semi_per_layer ? static_cast<size_t>(k) * p.B + b : static_cast<size_t>(b));
+        md0 = __ldg(sm), md1 = __ldg(sm + 1), md2 = __ldg(sm + 2);
         msign = __ldg(&ob.sign);
         r1a = __ldg(&ob.R[j]), r1b = __ldg(&ob.R[3 + j]), r1c = __ldg(&ob.R[6 + j]);
     }
@@ -803,6 +804,7 @@ int launch_minksweep3d(Ctx* c, int K, int B, int n_first_obj, int n_objs, const 
     p.L = c->Lx * c->Ly;
     pick_mapping(c->n, p.lpc, p.groups, p.paired);
     p.reload = reload ? 1 : 0;
+    p.semi_per_layer = c->semi_per_layer ? 1 : 0;
     p.seg_cap = (c->cell_seg_cap > 0 && c->cell_seg_cap < kCellCap / (kThreads / 32)) ? c->cell_seg_cap : kCellCap / (kThreads / 32);
     const double dx = (c->lim[1] - c->lim[0]) / static_cast<double>(c->Lx - 1);
     const double dy = (c->lim[3] - c->lim[2]) / static_cast<double>(c->Ly - 1);

@@ -28,6 +28,7 @@ struct MinkParams {
     int lpc, groups;                        // thread mapping
     int paired;                             // phase A handles rows in adjacent pairs (n even, lpc divides n/2)
     int seg_cap;                            // kept cells a warp can list per scan round (kCellCap / warps; smaller in tests)
+    int semi_per_layer;                     // bridge builds: every layer (pair) has its own body semi-axes, semi [K][B][3]
     int reload;                             // re-sweep: the boundary points are read back from `mesh` instead of being computed
     // byte offsets of the shared-memory regions (host-computed, see smem_layout): read from the constant bank instead of
     // being re-derived from n, Lx, Ly wherever the compiler rematerialises a pointer

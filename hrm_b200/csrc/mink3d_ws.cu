@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(kWsThreads, 2) k_minksweep3d_ws(const WsParams
             if (tid < 19) cp_async8(ex + tid, reinterpret_cast<const double*>(p.obj + obj_id) + tid);
             else if (tid >= 32 && tid < 41) cp_async8(ex + 20 + (tid - 32), p.R + pose * 9 + (tid - 32));
             else if (tid >= 64 && tid < 67) cp_async8(ex + 29 + (tid - 64), p.off + pose * 3 + (tid - 64));
-            else if (tid >= 96 && tid < 99) cp_async8(ex + 32 + (tid - 96), p.semi + 3 * (pose % p.B) + (tid - 96));
+            else if (tid >= 96 && tid < 99) cp_async8(ex + 32 + (tid - 96), p.semi + 3 * (p.semi_per_layer ? pose : pose % p.B) + (tid - 96));
         };
 
         // profiling builds (p.dbg): cycles of thread 0 in [1] waiting for inputs + the consumers, [2] tables, [3] phase A

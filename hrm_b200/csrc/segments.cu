@@ -560,6 +560,13 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const int* cnt, long long*
     }
 }
 
+int launch_scan_counts(Ctx* c, const int* cnt, long long* off, long long n, unsigned long long* info, cudaStream_t st) {
+    k_scan_counts<<<1, 1024, 0, st>>>(cnt, off, n, info);
+    HRMGPU_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    return HRMGPU_OK;
+}
+
 // Enqueues pass 1 .. 3 on the side stream (no host synchronisation).  `from_pass`: 1 = everything, 3 = the fill pass only
 // (after the payload was grown).
 static int enqueue_passes(Ctx* c, int from_pass) {

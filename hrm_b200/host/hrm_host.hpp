@@ -448,6 +448,23 @@ class FreeSpaceGPU {
                                                       static_cast<int>(w0.size()), w0.data(), w1.data(), linkOff.data(), chainOff->data(), out.data()));
         return out;
     }
+    /** connectMultiSlice's vertex matching in one call (hrmgpu_connect_pairs3d): vertexXYZ [V][3] roadmap vertex positions,
+     * range4 [P][4] = {near begin, near end, cur begin, cur end} vertex id ranges of every pair; match[first(p) + (m0 - near begin)] =
+     * id of the vertex m0 connects to, or -1.  Candidates, transition tests and the replay of the reference's moving lower bound run
+     * on the device */
+    std::vector<int> connectPairs3D(const std::vector<double>& vertexXYZ, const std::vector<int>& range4, double thx, double thy,
+                                    const std::vector<double>& w0, const std::vector<double>& w1, const std::vector<double>& linkOff,
+                                    long long* numCandidates = nullptr) {
+        size_t numNear = 0;
+        for (size_t i = 0; i + 3 < range4.size(); i += 4) numNear += static_cast<size_t>(range4[i + 1] - range4[i]);
+        std::vector<int> match(numNear > 0 ? numNear : 1, -1);
+        const long long n = hrmgpu_connect_pairs3d(ctx_, static_cast<long long>(vertexXYZ.size() / 3), vertexXYZ.data(), static_cast<int>(range4.size() / 4),
+                                                   range4.data(), thx, thy, static_cast<int>(w0.size()), w0.data(), w1.data(), linkOff.data(), match.data(),
+                                                   static_cast<long long>(match.size()), numCandidates);
+        if (n < 0) check(static_cast<int>(n));
+        match.resize(static_cast<size_t>(n));
+        return match;
+    }
     long long kernelLaunches() { return hrmgpu_kernel_launches(ctx_, 0); }
     /** {K, B, S, n_arena, L, M, total segments, dim} of the last build (hrmgpu_get_dims) */
     void dims(long long d[8]) { check(hrmgpu_get_dims(ctx_, d)); }
@@ -502,6 +519,13 @@ class FreeSpaceGPU3D : public FreeSpaceGPU {
                     for (int j = 0; j < 3; ++j) R.push_back(Rb[i][j]);
             }
         check(hrmgpu_build_bridge(ctx_, static_cast<int>(tfe.size()), static_cast<int>(tfe.at(0).size()), semi.data(), R.data(), precision));
+    }
+    /** computeTFE + bridgeSlice for P layer pairs on the device (hrmgpu_build_bridge_tfe): bodySemi [B][3], quatA / quatB [P][B][4] */
+    void buildBridgeTFE(const std::vector<double>& bodySemi, const std::vector<double>& quatA, const std::vector<double>& quatB, Index numStep,
+                        int precision) {
+        const int B = static_cast<int>(bodySemi.size() / 3);
+        check(hrmgpu_build_bridge_tfe(ctx_, static_cast<int>(quatA.size() / (4 * static_cast<size_t>(B))), B, bodySemi.data(), quatA.data(), quatB.data(),
+                                      static_cast<int>(numStep), precision, nullptr));
     }
 };
 
@@ -782,6 +806,11 @@ class HighwayRoadMapBase {
     const PlanningResult& getPlanningResult() const { return res_; }
     const PlannerParameter& getPlannerParameters() const { return param_; }
     long numEdgeTests() const { return numEdgeTests_; }
+    long long numBridgeCandidates() const { return numBridgeCandidates_; }
+    /** connectMultiSlice's vertex matching on the device (default) or enumerated on the host (the round-1 path; identical roadmaps) */
+    void setDeviceMatching(bool on) { deviceMatching_ = on; }
+    /** tightly-fitted ellipsoids of the bridge layers fitted on the device (default) or on the host (the round-1 path) */
+    void setDeviceTfe(bool on) { deviceTfe_ = on; }
     void setMaxRefine(size_t rounds) { maxRefine_ = rounds; }
     size_t numRefineDone() const { return numRefineDone_; }
 
@@ -849,6 +878,9 @@ class HighwayRoadMapBase {
     int precision_;
     bool perOrientation_;
     long numEdgeTests_ = 0;
+    long long numBridgeCandidates_ = 0;
+    bool deviceMatching_ = std::getenv("HRM_HOST_MATCHING") == nullptr;
+    bool deviceTfe_ = std::getenv("HRM_HOST_TFE") == nullptr;
     StageTimes stage_;
     size_t maxRefine_ = static_cast<size_t>(-1), numRefineDone_ = 0;  // (no round bound unless setMaxRefine is called)
     std::vector<std::vector<std::pair<Index, Index>>> vertexIdxAll_;  // vertexIdx_ of the previous refinement rounds
@@ -1131,6 +1163,9 @@ class HRM3D : public HighwayRoadMapBase {
         const auto bodies = robot_.getBodyShapes();
         std::vector<int> nearest;
         std::vector<std::vector<Ellipsoid>> tfe;
+        std::vector<double> tfeQa, tfeQb, bodySemi;  // device TFE: the two orientations of every (pair, body)
+        for (size_t b = 0; b < B; ++b)
+            for (int d = 0; d < 3; ++d) bodySemi.push_back(bodies[b].getSemiAxis()[d]);
         auto tTfe = std::chrono::high_resolution_clock::now();
         for (size_t i = 0; i < vertexIdx_.size(); ++i) {
             double minDist = INFINITY;
@@ -1140,6 +1175,19 @@ class HRM3D : public HighwayRoadMapBase {
                 if (d < minDist) minDist = d, minIdx = static_cast<int>(j);
             }
             nearest.push_back(minIdx);
+            if (deviceTfe_) {  // HRM3D.cpp:521-539: the orientations only; the ellipsoids are fitted on the device
+                for (size_t b = 0; b < B; ++b) {
+                    Quaternion qa = q_[i], qb = q_[minIdx];
+                    if (b > 0) {
+                        const Mat3& Rl = robot_.getTF()[b - 1].R;
+                        qa = toQuaternion(matMul(toRotationMatrix(q_[i]), Rl));
+                        qb = toQuaternion(matMul(toRotationMatrix(q_[minIdx]), Rl));
+                    }
+                    tfeQa.insert(tfeQa.end(), qa.begin(), qa.end());
+                    tfeQb.insert(tfeQb.end(), qb.begin(), qb.end());
+                }
+                continue;
+            }
             std::vector<Ellipsoid> pr;
             for (size_t b = 0; b < B; ++b) {
                 const Vec3 semi = {bodies[b].getSemiAxis()[0], bodies[b].getSemiAxis()[1], bodies[b].getSemiAxis()[2]};
@@ -1153,10 +1201,13 @@ class HRM3D : public HighwayRoadMapBase {
             }
             tfe.push_back(pr);
         }
-        stage_.add("  TFE (host)", std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - tTfe).count());
+        stage_.add(deviceTfe_ ? "  TFE orientations (host)" : "  TFE (host)", std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - tTfe).count());
         {
-            StageScope ss(stage_, "  K5a buildBridge");
-            freeSpace_.buildBridge(tfe, precision_);
+            StageScope ss(stage_, deviceTfe_ ? "  K5a TFE + buildBridge (device)" : "  K5a buildBridge");
+            if (deviceTfe_)
+                freeSpace_.buildBridgeTFE(bodySemi, tfeQa, tfeQb, param_.numPoint, precision_);
+            else
+                freeSpace_.buildBridge(tfe, precision_);
         }
         const double thx = 2.0 * (lim[1] - lim[0]) / static_cast<double>(param_.numLineX);
         const double thy = 2.0 * (lim[3] - lim[2]) / static_cast<double>(param_.numLineY);
@@ -1188,6 +1239,47 @@ class HRM3D : public HighwayRoadMapBase {
         const auto& tf = robot_.getTF();
         const double dt = 1.0 / static_cast<double>(steps);
         for (size_t s = 0; s < T; ++s) w1[s] = static_cast<double>(s) * dt, w0[s] = 1.0 - static_cast<double>(s) * dt;  // InterpolateSE3.cpp:5-29
+        if (deviceMatching_ && vertexTail_.empty()) {
+            // The candidate enumeration, the transition tests and the replay of the moving lower bound run on the device
+            // (hrmgpu_connect_pairs3d) from the vertex positions and the id range of every layer; the host only evaluates the
+            // per-pair link offsets and appends the matches as edges, in the reference's order.
+            std::vector<int> range4(4 * P);
+            std::vector<double> xyz(3 * V.size());
+            {
+                StageScope ss(stage_, "  link offsets (host)");
+                for (size_t m = 0; m < V.size(); ++m)
+                    for (int d = 0; d < 3; ++d) xyz[3 * m + d] = V[m][d];
+                for (size_t i = 0; i < P; ++i) {
+                    const Index start = vertexIdx_[nearest[i]].first, n2 = vertexIdx_[nearest[i]].second;
+                    range4[4 * i] = static_cast<int>(start), range4[4 * i + 1] = static_cast<int>(n2);
+                    range4[4 * i + 2] = static_cast<int>(vertexIdx_[i].first), range4[4 * i + 3] = static_cast<int>(vertexIdx_[i].second);
+                    if (n2 <= start || vertexIdx_[i].second <= vertexIdx_[i].first) {
+                        range4[4 * i + 1] = range4[4 * i];  // (an empty side: no candidates)
+                        continue;
+                    }
+                    const auto& va = V[start];
+                    const auto& vb = V[vertexIdx_[i].first];
+                    const auto qs = interpolateSlerp({va[3], va[4], va[5], va[6]}, {vb[3], vb[4], vb[5], vb[6]}, steps);
+                    for (size_t s = 0; s < T; ++s) {
+                        const Mat3 R = toRotationMatrix(qs[s]);
+                        for (size_t l = 0; l < tf.size(); ++l) {
+                            const Vec3 v = matVec(R, tf[l].t);
+                            for (int d = 0; d < 3; ++d) linkOff[((i * T + s) * B + (l + 1)) * 3 + d] = v[d];
+                        }
+                    }
+                }
+            }
+            std::vector<int> match;
+            {
+                StageScope ss(stage_, "  K5b connectPairs (device)");
+                match = freeSpace_.connectPairs3D(xyz, range4, thx, thy, w0, w1, linkOff, &numBridgeCandidates_);
+            }
+            size_t g = 0;
+            for (size_t i = 0; i < P; ++i)
+                for (int m0 = range4[4 * i]; m0 < range4[4 * i + 1]; ++m0, ++g)
+                    if (match[g] >= 0) addEdge(static_cast<Index>(m0), static_cast<Index>(match[g]));
+            return;
+        }
         {
             StageScope ss(stage_, "  bridge candidates (host)");
             std::vector<std::vector<Index>> cell(static_cast<size_t>(Lx) * Ly);

@@ -163,6 +163,12 @@ int hrmgpu_test_edges_multi(hrmgpu_ctx* ctx, int E, const int* layer, const doub
  * OBSTACLE with each body's tightly-fitted ellipsoid (centred at the origin).
  * tfe_semi [P][B][3], tfe_R [P][B][9].  Meshes stay resident until the next call. */
 int hrmgpu_build_bridge(hrmgpu_ctx* ctx, int P, int B, const double* tfe_semi, const double* tfe_R, int precision);
+/* computeTFE + bridgeSlice in one call (HRM3D.cpp:521-539, 301-317; TightFitEllipsoid.cpp:43-114): the tightly-fitted ellipsoid of
+ * body b between the orientations quat_a[p][b] and quat_b[p][b] ((w, x, y, z), [P][B][4]; for a link: the layer's rotation times
+ * the link's) with num_step interpolation steps is evaluated on the device for all (pair, body) in one launch and feeds the
+ * bridge-layer build directly.  body_semi [B][3].  tfe_out (optional, [P][B][7] = semi-axes + quaternion) returns the ellipsoids. */
+int hrmgpu_build_bridge_tfe(hrmgpu_ctx* ctx, int P, int B, const double* body_semi, const double* quat_a, const double* quat_b, int num_step,
+                            int precision, double* tfe_out);
 /* 2D twin (HRM2D.cpp:199-213): tfe_semi [P][B][2], tfe_angle [P][B]. */
 int hrmgpu_build_bridge2d(hrmgpu_ctx* ctx, int P, int B, const double* tfe_semi, const double* tfe_angle, int precision);
 /* Replaces isPtInCFree for all bodies of Q interpolated robot poses of pair p (HRM3D.cpp:367-425,
@@ -189,6 +195,20 @@ int hrmgpu_test_transitions(hrmgpu_ctx* ctx, int C, const int* pair, const doubl
  * slice's base orientation and joint angles, so both tables are per (pair, pose, body) like link_off above.  3D only. */
 int hrmgpu_test_transitions_articulated(hrmgpu_ctx* ctx, int C, const int* pair, const double* v0, const double* v1, int T, const double* w0,
                                         const double* w1, const double* link_off, const double* chain_off, unsigned char* free_out);
+
+/* connectMultiSlice's vertex matching as ONE call (HRM3D.cpp:158-224).  vertex_xyz [V][3] are the positions of the roadmap's
+ * vertices (a layer's vertices are its free-segment mid points plus the bridge vertices connectOneSlice inserted, so the host
+ * names them); pair p joins the vertices range4[p] = {near begin, near end, cur begin, cur end} (id ranges of the closest earlier
+ * layer, :161-176, and of the current one) and is tested against bridge layer p of the last hrmgpu_build_bridge (P must equal
+ * their number).  For every vertex m0 of the near range, in order, the vertices m1 of the cur range are scanned from the
+ * reference's moving lower bound: the first one with |x0 - x1| <= thx, |y0 - y1| <= thy (:195-200) whose interpolated
+ * transition is free (same T, w0, w1, link_off as hrmgpu_test_transitions) is its match, and the new lower bound.
+ * match_out[first(p) + (m0 - near begin)] = m1 (vertex id) or -1, pairs concatenated.  The candidate enumeration, the transition
+ * tests and the replay all run on the device; only the matches come back.  Returns the number of entries written, or a
+ * negative error code; n_candidates_out (optional) = transition tests made. */
+long long hrmgpu_connect_pairs3d(hrmgpu_ctx* ctx, long long V, const double* vertex_xyz, int P, const int* range4, double thx, double thy, int T,
+                                 const double* w0, const double* w1, const double* link_off, int* match_out, long long match_cap,
+                                 long long* n_candidates_out);
 
 /* ---- multi-GPU exchange ------------------------------------------------------------------------ */
 /* C-layers shard by orientation: every rank (one process, one context, one GPU) builds its own block of layers with no

@@ -228,3 +228,128 @@ def test_bridge2d_match_oracle(oracle, gpu_ctx):
             want[sel] &= want_for(p, centres)
     assert np.array_equal(got, want)
     assert 0 < want.sum() < C
+
+
+def test_connect_pairs3d_equals_the_reference_loop(oracle, gpu_ctx):
+    """hrmgpu_connect_pairs3d (candidate enumeration from the vertex positions, transition tests and the replay of the moving
+    lower bound, all on the device) against the reference's loop (HRM3D.cpp:186-222) written out on the host, with the
+    transition tests of hrmgpu_test_transitions (checked against the oracle above)."""
+    sc = util.scenes()["3D_superquadrics_cluttered_rabbit"]
+    rows = sc["arena"] + sc["obstacle"]
+    n_arena, n_obs = len(sc["arena"]), len(sc["obstacle"])
+    n = 10
+    rb = util.robot3d(sc["robot"])
+    semis = [rb.base.semiAxis] + [l.semiAxis for l in rb.link]
+    B = len(semis)
+    K = 6
+    quats = sc["quats"][:K]
+    Lx, Ly = 9, 6
+    semi, R, off, quat = util.body_poses3d(sc["robot"], quats)
+    pairs = [(0, 0), (0, 1), (1, 2), (1, 3), (3, 4), (2, 5)]  # (near, cur); P == number of bridge layers
+    tfe_semi, tfe_R = [], []
+    for (j, i) in pairs:
+        ps, pr = [], []
+        for b in range(B):
+            if b == 0:
+                qa, qb = quats[i], quats[j]
+            else:
+                Rl = rb.tf[b - 1][0]
+                qa = hm.rot_to_quat(hm.mat_mul(hm.quat_to_rot(quats[i]), Rl))
+                qb = hm.rot_to_quat(hm.mat_mul(hm.quat_to_rot(quats[j]), Rl))
+            t = oracle.tfe3d(semis[b], qa, qb, 5)
+            ps.append(t[:3])
+            pr.append(hm.flat9(hm.quat_to_rot(t[3:])))
+        tfe_semi.append(ps), tfe_R.append(pr)
+    gpu_ctx.set_scene3d(n_arena, n_obs, util.sq17(rows, n), n)
+    gpu_ctx.set_sweep(sc["lim"], Lx, Ly)
+    gpu_ctx.build_layers(semi, R, off, capi.F64_STRICT)
+    gpu_ctx.build_bridge(np.array(tfe_semi), np.array(tfe_R), capi.F64_STRICT)
+    lim = sc["lim"]
+    tx = [lim[0] + float(i) * ((lim[1] - lim[0]) / float(Lx - 1)) for i in range(Lx)]
+    ty = [lim[2] + float(i) * ((lim[3] - lim[2]) / float(Ly - 1)) for i in range(Ly)]
+    verts = []
+    for k in range(K):
+        o, xL, xU, xM = gpu_ctx.segments(k)
+        verts.append(np.array([[tx[l // Ly], ty[l % Ly], xM[s]] for l in range(Lx * Ly) for s in range(o[l], o[l + 1])]).reshape(-1, 3))
+    thx, thy = 2.0 * (lim[1] - lim[0]) / Lx, 2.0 * (lim[3] - lim[2]) / Ly
+    T = 6
+    w1 = np.arange(T) * (1.0 / 5.0)
+    w0 = 1.0 - w1
+    rng = np.random.default_rng(11)
+    link_off = rng.uniform(-3, 3, size=(len(pairs), T, B, 3))
+    # the reference loop on the host: all near candidates tested at once, then the replay
+    cand_pair, cand_v0, cand_v1, cand_key = [], [], [], []
+    for p, (j, i) in enumerate(pairs):
+        for m0, a in enumerate(verts[j]):
+            for m1, b in enumerate(verts[i]):
+                if abs(a[0] - b[0]) > thx or abs(a[1] - b[1]) > thy:
+                    continue
+                cand_pair.append(p), cand_v0.append(a), cand_v1.append(b), cand_key.append((p, m0, m1))
+    free = gpu_ctx.test_transitions(np.array(cand_pair), np.array(cand_v0), np.array(cand_v1), w0, w1, link_off)
+    ok = {key: bool(f) for key, f in zip(cand_key, free)}
+    want_of_pair = []
+    for p, (j, i) in enumerate(pairs):
+        n22 = 0
+        want = []
+        for m0 in range(len(verts[j])):
+            hit = -1
+            for m1 in range(n22, len(verts[i])):
+                if ok.get((p, m0, m1), False):
+                    hit = m1
+                    n22 = m1
+                    break
+            want.append(hit)
+        want_of_pair.append(want)
+    first = np.concatenate([[0], np.cumsum([len(v) for v in verts])])
+    xyz = np.concatenate(verts)
+    range4 = [[first[j], first[j + 1], first[i], first[i + 1]] for j, i in pairs]
+    got, ncand = gpu_ctx.connect_pairs3d(xyz, range4, thx, thy, w0, w1, link_off)
+    want_ids = np.array([first[pairs[p][1]] + w if w >= 0 else -1 for p in range(len(pairs)) for w in want_of_pair[p]])
+    assert ncand == len(cand_pair)
+    assert np.array_equal(got, want_ids)
+    assert (want_ids >= 0).sum() > 20 and (want_ids < 0).sum() > 0
+    # error behaviour: P has to be the number of bridge layers
+    with pytest.raises(capi.HrmGpuError):
+        gpu_ctx.connect_pairs3d(xyz, range4[:1], thx, thy, w0, w1, link_off[:1])
+
+
+def test_build_bridge_tfe_matches_the_host_ellipsoids(oracle, gpu_ctx):
+    """hrmgpu_build_bridge_tfe fits the tightly-fitted ellipsoids of all (pair, body) on the device (TightFitEllipsoid.cpp:43-114):
+    semi-axes and orientation against the oracle's to 1e-12 (its libm differs from glibc in the last bits), and the bridge
+    layers built from them answer point queries like the ones built from the host ellipsoids."""
+    sc = util.scenes()["3D_superquadrics_cluttered_rabbit"]
+    rows = sc["arena"] + sc["obstacle"]
+    n_arena, n_obs = len(sc["arena"]), len(sc["obstacle"])
+    n = 10
+    rb = util.robot3d(sc["robot"])
+    semis = [rb.base.semiAxis] + [l.semiAxis for l in rb.link]
+    B = len(semis)
+    quats = sc["quats"]
+    pairs = [(1, 0), (2, 1), (7, 3), (30, 12), (59, 58), (5, 5)]
+    qa_all, qb_all, want = [], [], []
+    for (i, j) in pairs:
+        for b in range(B):
+            if b == 0:
+                qa, qb = quats[i], quats[j]
+            else:
+                Rl = rb.tf[b - 1][0]
+                qa = hm.rot_to_quat(hm.mat_mul(hm.quat_to_rot(quats[i]), Rl))
+                qb = hm.rot_to_quat(hm.mat_mul(hm.quat_to_rot(quats[j]), Rl))
+            qa_all.append(qa), qb_all.append(qb)
+            want.append(oracle.tfe3d(semis[b], qa, qb, 5))
+    want = np.array(want).reshape(len(pairs), B, 7)
+    gpu_ctx.set_scene3d(n_arena, n_obs, util.sq17(rows, n), n)
+    got = gpu_ctx.build_bridge_tfe(np.array(semis), np.array(qa_all), np.array(qb_all), 5, capi.F64_STRICT)
+    assert np.max(np.abs(got[..., :3] - want[..., :3]) / want[..., :3]) < 1e-12
+    for g, w in zip(got.reshape(-1, 7), want.reshape(-1, 7)):  # the same rotation (q and -q are the same orientation)
+        Rg, Rw = np.array(hm.quat_to_rot(g[3:])), np.array(hm.quat_to_rot(w[3:]))
+        assert np.max(np.abs(Rg - Rw)) < 1e-10
+    # point queries against the device-built bridge layers == against layers built from the host ellipsoids
+    rng = np.random.default_rng(5)
+    lim = np.array(sc["lim"])
+    centres = rng.uniform(lim[0::2] - 5, lim[1::2] + 5, size=(600, B, 3))
+    pp = rng.integers(0, len(pairs), 600)
+    dev = gpu_ctx.test_bridge_multi(pp, centres)
+    gpu_ctx.build_bridge(want[..., :3], np.array([[hm.flat9(hm.quat_to_rot(w[3:])) for w in pr] for pr in want]), capi.F64_STRICT)
+    host = gpu_ctx.test_bridge_multi(pp, centres)
+    assert np.array_equal(dev, host) and 0 < host.sum() < 600
