@@ -58,6 +58,7 @@ def load():
         "hrmgpu_test_bridge_multi": (i, [vp, i, vp, vp, vp]),
         "hrmgpu_test_transitions": (i, [vp, i, vp, vp, vp, i, vp, vp, vp, vp]),
         "hrmgpu_test_transitions_articulated": (i, [vp, i, vp, vp, vp, i, vp, vp, vp, vp, vp]),
+        "hrmgpu_connect_slices3d": (ll, [vp, vp, ll, vp]),
         "hrmgpu_connect_pairs3d": (ll, [vp, ll, vp, i, vp, C.c_double, C.c_double, i, vp, vp, vp, vp, ll, vp]),
         "hrmgpu_build_bridge": (i, [vp, i, i, vp, vp, i]),
         "hrmgpu_build_bridge_tfe": (i, [vp, i, i, vp, vp, vp, i, i, vp]),
@@ -320,6 +321,14 @@ class Context:
             self._chk(self.lib.hrmgpu_test_transitions_articulated(self.h, Cn, _p(pair), _p(v0), _p(v1), w0.shape[0], _p(w0), _p(w1), _p(link_off),
                                                                    _p(chain_off), _p(out)))
         return out.astype(bool)
+
+    def connect_slices3d(self, cap):
+        """connectOneSlice's pair codes for all layers of the last build (see include/hrmgpu.h): returns (codes, layer_first)."""
+        K = self.dims()["K"]
+        code = np.zeros(max(1, int(cap)), dtype=np.uint8)
+        first = np.zeros(K + 1, dtype=np.int64)
+        n = self._chk(self.lib.hrmgpu_connect_slices3d(self.h, _p(code), int(cap), _p(first)))
+        return code[:n], first
 
     def connect_pairs3d(self, vertex_xyz, range4, thx, thy, w0, w1, link_off):
         """connectMultiSlice's vertex matching on the device (see include/hrmgpu.h): vertex_xyz [V][3], range4 [P][4] =

@@ -73,6 +73,81 @@ __global__ void __launch_bounds__(32) k_pair_replay(const long long* m0_first, c
     }
 }
 
+// ---- connectOneSlice's candidate segments on the device (HighwayRoadMap-inl.h:218-326, HRM3D.cpp:93-156) --------------------
+// Vertex pairs of a layer in the reference's enumeration order: first, plane by plane, every segment of line (ix, iy) with every
+// segment of line (ix, iy + 1); then every segment of line (ix, iy) with every segment of line (ix + 1, iy).  Item = (layer, part,
+// line) with part 0 = in-plane, 1 = cross-plane; its pairs are consecutive, so an exclusive scan over the item counts gives every
+// pair its place.  Each pair expands into the 5 segments of bridgeVertex {v1-v2, v1-vNew1, vNew1-v2, v1-vNew2, vNew2-v2}
+// (vNew1 = (x1, y1, z2), vNew2 = (x2, y2, z1), :295-326), query e = 5 * pair + t.
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_slice_pairs(const long long* off, const double* xM, const double* txs, const double* tys, int K, int Lx, int Ly,
+                                                     const long long* item_first, int* cnt, double* qa, double* qb, int* qlayer) {
+    const int L = Lx * Ly;
+    const long long item = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (item >= 2LL * K * L) return;
+    const int k = static_cast<int>(item / (2 * L));
+    const int rem = static_cast<int>(item - static_cast<long long>(k) * 2 * L);
+    const int part = rem / L, l = rem - part * L;
+    const int ix = l / Ly, iy = l - ix * Ly;
+    const bool has = part == 0 ? (iy + 1 < Ly) : (ix + 1 < Lx);
+    const int l2 = part == 0 ? l + 1 : l + Ly;
+    const long long* o = off + static_cast<long long>(k) * L;
+    const long long a0 = o[l], a1 = o[l + 1];
+    const long long b0 = has ? o[l2] : 0, b1 = has ? o[l2 + 1] : 0;
+    const long long n1 = a1 - a0, n2 = b1 - b0;
+    if (!FILL) {
+        cnt[item] = static_cast<int>(n1 * n2);
+        return;
+    }
+    if (n1 * n2 == 0) return;
+    const double x1 = txs[1 + ix], y1 = tys[1 + iy];
+    const double x2 = part == 0 ? x1 : txs[2 + ix], y2 = part == 0 ? tys[2 + iy] : y1;
+    long long pr = item_first[item];
+    for (long long j1 = a0; j1 < a1; ++j1) {
+        const double z1 = xM[j1];
+        for (long long j2 = b0; j2 < b1; ++j2, ++pr) {
+            const double z2 = xM[j2];
+            const double v1[3] = {x1, y1, z1}, v2[3] = {x2, y2, z2}, w1[3] = {x1, y1, z2}, w2[3] = {x2, y2, z1};
+            const double* as[5] = {v1, v1, w1, v1, w2};
+            const double* bs[5] = {v2, w1, v2, w2, v2};
+#pragma unroll
+            for (int t = 0; t < 5; ++t) {
+                const size_t e = static_cast<size_t>(5 * pr + t);
+#pragma unroll
+                for (int d = 0; d < 3; ++d) qa[3 * e + d] = as[t][d], qb[3 * e + d] = bs[t][d];
+                qlayer[e] = k;
+            }
+        }
+    }
+}
+// connection code of every pair from the 5 answers of its segments: 0 direct, 1 through vNew1, 2 through vNew2, 3 none (:295-326)
+__global__ void __launch_bounds__(256) k_pair_codes(const unsigned char* free5, long long n_pairs, unsigned char* code) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n_pairs) return;
+    const unsigned char* f = free5 + 5 * i;
+    code[i] = f[0] ? 0 : ((f[1] && f[2]) ? 1 : ((f[3] && f[4]) ? 2 : 3));
+}
+
+int launch_slice_pairs(Ctx* c, bool fill, const long long* item_first, int* cnt, double* qa, double* qb, int* qlayer) {
+    const long long items = 2LL * c->K * c->L;
+    const unsigned grid = static_cast<unsigned>((items + 127) / 128);
+    const double* xM = c->segdata.p + 2 * c->seg_cap;
+    if (fill)
+        k_slice_pairs<true><<<grid, 128, 0, c->stream>>>(c->seg_off.p, xM, c->txs.p, c->tys.p, c->K, c->Lx, c->Ly, item_first, cnt, qa, qb, qlayer);
+    else
+        k_slice_pairs<false><<<grid, 128, 0, c->stream>>>(c->seg_off.p, xM, c->txs.p, c->tys.p, c->K, c->Lx, c->Ly, item_first, cnt, qa, qb, qlayer);
+    HRMGPU_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    return HRMGPU_OK;
+}
+int launch_pair_codes(Ctx* c, const unsigned char* free5, long long n_pairs, unsigned char* code) {
+    if (n_pairs <= 0) return HRMGPU_OK;
+    k_pair_codes<<<static_cast<unsigned>((n_pairs + 255) / 256), 256, 0, c->stream>>>(free5, n_pairs, code);
+    HRMGPU_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    return HRMGPU_OK;
+}
+
 int launch_pair_candidates(Ctx* c, const PairParams& p, long long max_n0, bool fill) {
     const dim3 grid(static_cast<unsigned>((max_n0 + 127) / 128), static_cast<unsigned>(p.P));
     if (fill)
@@ -96,6 +171,9 @@ void preload_connect() {
     if (cudaFuncGetAttributes(&a, k_pair_candidates<false>) != cudaSuccess) cudaGetLastError();
     if (cudaFuncGetAttributes(&a, k_pair_candidates<true>) != cudaSuccess) cudaGetLastError();
     if (cudaFuncGetAttributes(&a, k_pair_replay) != cudaSuccess) cudaGetLastError();
+    if (cudaFuncGetAttributes(&a, k_slice_pairs<false>) != cudaSuccess) cudaGetLastError();
+    if (cudaFuncGetAttributes(&a, k_slice_pairs<true>) != cudaSuccess) cudaGetLastError();
+    if (cudaFuncGetAttributes(&a, k_pair_codes) != cudaSuccess) cudaGetLastError();
 }
 
 }  // namespace hrmgpu

@@ -254,7 +254,7 @@ void hrmgpu_destroy(hrmgpu_ctx* c) {
     release(c, c->q_loff2);
     release(c, c->pc_layers), release(c, c->pc_cnt), release(c, c->pc_m1), release(c, c->pc_match);
     release(c, c->pc_m0_first), release(c, c->pc_first), release(c, c->pc_info), release(c, c->pc_vtx);
-    release(c, c->tfe_in), release(c, c->tfe_quat);
+    release(c, c->tfe_in), release(c, c->tfe_quat), release(c, c->pc_code);
     release(c, c->bridge_bbox);
     release(c, c->bridge_semi);
     release(c, c->bridge_R);
@@ -739,6 +739,46 @@ int hrmgpu_test_transitions_articulated(hrmgpu_ctx* c, int C, const int* pair, c
                                         const double* w1, const double* link_off, const double* chain_off, unsigned char* free_out) {
     if (c && !chain_off) return fail(c, HRMGPU_E_ARG, "test_transitions_articulated: bad arguments");
     return test_transitions_common(c, C, pair, v0, v1, T, w0, w1, link_off, chain_off, free_out);
+}
+
+long long hrmgpu_connect_slices3d(hrmgpu_ctx* c, unsigned char* code_out, long long cap, long long* layer_first) {
+    if (!c) return HRMGPU_E_ARG;
+    int rc = check_built(c, 0);
+    if (rc) return rc;
+    if (c->dim != 3) return fail(c, HRMGPU_E_STATE, "connect_slices3d: 3D layers only");
+    if (cap < 0 || (cap > 0 && !code_out)) return fail(c, HRMGPU_E_ARG, "connect_slices3d: bad arguments");
+    HRMGPU_CUDA(c, cudaSetDevice(c->device));
+    if ((rc = finalize_segments(c))) return rc;
+    // the free-segment arrays live on the side stream's timeline: the main stream must see them finished
+    HRMGPU_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_k3[c->ivl_cur], 0));
+    const long long items = 2LL * c->K * c->L;
+    if ((rc = ensure(c, c->pc_cnt, static_cast<size_t>(items)))) return rc;
+    if ((rc = ensure(c, c->pc_first, static_cast<size_t>(items) + 1))) return rc;
+    if ((rc = ensure(c, c->pc_info, 2))) return rc;
+    if ((rc = launch_slice_pairs(c, false, nullptr, c->pc_cnt.p, nullptr, nullptr, nullptr))) return rc;
+    if ((rc = launch_scan_counts(c, c->pc_cnt.p, c->pc_first.p, items, c->pc_info.p, c->stream))) return rc;
+    // the first pair of every layer (and the total) is all the host needs to size and split the answer
+    std::vector<long long> first(static_cast<size_t>(c->K) + 1);
+    HRMGPU_CUDA(c, cudaMemcpy2DAsync(first.data(), sizeof(long long), c->pc_first.p, sizeof(long long) * 2 * static_cast<size_t>(c->L), sizeof(long long),
+                                     static_cast<size_t>(c->K) + 1, cudaMemcpyDeviceToHost, c->stream));
+    HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));
+    const long long total = first[c->K];
+    if (layer_first) std::copy(first.begin(), first.end(), layer_first);
+    if (total > cap) return fail(c, HRMGPU_E_CAP, "connect_slices3d: code_out too small");
+    if (5 * total > 0x7FFFFFF0LL) return fail(c, HRMGPU_E_CAP, "connect_slices3d: too many candidate segments for one launch");
+    if (total == 0) return 0;
+    const size_t E = static_cast<size_t>(5 * total);
+    if ((rc = ensure(c, c->q_a, 3 * E))) return rc;
+    if ((rc = ensure(c, c->q_b, 3 * E))) return rc;
+    if ((rc = ensure(c, c->q_set, E))) return rc;
+    if ((rc = ensure(c, c->q_out, E))) return rc;
+    if ((rc = ensure(c, c->pc_code, static_cast<size_t>(total)))) return rc;
+    if ((rc = launch_slice_pairs(c, true, c->pc_first.p, nullptr, c->q_a.p, c->q_b.p, c->q_set.p))) return rc;
+    if ((rc = launch_edges(c, -1, static_cast<int>(E), c->q_a.p, c->q_b.p, c->q_out.p, c->q_set.p))) return rc;
+    if ((rc = launch_pair_codes(c, c->q_out.p, total, c->pc_code.p))) return rc;
+    HRMGPU_CUDA(c, cudaMemcpyAsync(code_out, c->pc_code.p, static_cast<size_t>(total), cudaMemcpyDeviceToHost, c->stream));
+    HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));
+    return total;
 }
 
 long long hrmgpu_connect_pairs3d(hrmgpu_ctx* c, long long V, const double* vertex_xyz, int P, const int* range4, double thx, double thy, int T,

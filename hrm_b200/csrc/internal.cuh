@@ -134,6 +134,7 @@ struct Ctx {
     DevBuf<double> bridge_bbox;                  // [P][n_obs * B][6] (3D)
     DevBuf<int> pc_layers, pc_cnt, pc_m1, pc_match;   // device-side vertex matching of connectMultiSlice (connect.cu)
     DevBuf<double> pc_vtx;
+    DevBuf<unsigned char> pc_code;                    // connection code of every vertex pair of connectOneSlice
     DevBuf<double> tfe_in, tfe_quat;                  // device TFE: {body semi [B][3], quat a [P][B][4], quat b [P][B][4]}, result quaternions
     DevBuf<long long> pc_m0_first, pc_first;
     DevBuf<unsigned long long> pc_info;
@@ -222,6 +223,8 @@ struct PairParams {
 };
 int launch_pair_candidates(Ctx* c, const PairParams& p, long long max_n0, bool fill);
 int launch_pair_replay(Ctx* c, int P, const long long* m0_first, const long long* cand_first, const int* c_m1, const unsigned char* free_flag, int* match);
+int launch_slice_pairs(Ctx* c, bool fill, const long long* item_first, int* cnt, double* qa, double* qb, int* qlayer);
+int launch_pair_codes(Ctx* c, const unsigned char* free5, long long n_pairs, unsigned char* code);
 void preload_connect();
 // tfe.cu: tightly-fitted ellipsoids of all (pair, body) combinations (TightFitEllipsoid.cpp:43-114)
 int launch_tfe3d(Ctx* c, int P, int B, const double* d_body_semi, const double* d_quat_a, const double* d_quat_b, int num_step, double* d_semi,

@@ -520,6 +520,16 @@ class FreeSpaceGPU3D : public FreeSpaceGPU {
             }
         check(hrmgpu_build_bridge(ctx_, static_cast<int>(tfe.size()), static_cast<int>(tfe.at(0).size()), semi.data(), R.data(), precision));
     }
+    /** connectOneSlice's pair codes of ALL layers in one call (hrmgpu_connect_slices3d): code[layerFirst[k] + i] of pair i of layer k
+     * in the reference's enumeration order; 0 direct, 1 / 2 through a bridge vertex, 3 none */
+    std::vector<unsigned char> connectSlices3D(std::vector<long long>& layerFirst, size_t numPairs, size_t numLayers) {
+        std::vector<unsigned char> code(numPairs > 0 ? numPairs : 1);
+        layerFirst.assign(numLayers + 1, 0);
+        const long long n = hrmgpu_connect_slices3d(ctx_, code.data(), static_cast<long long>(numPairs), layerFirst.data());
+        if (n < 0) check(static_cast<int>(n));
+        code.resize(static_cast<size_t>(n));
+        return code;
+    }
     /** computeTFE + bridgeSlice for P layer pairs on the device (hrmgpu_build_bridge_tfe): bodySemi [B][3], quatA / quatB [P][B][4] */
     void buildBridgeTFE(const std::vector<double>& bodySemi, const std::vector<double>& quatA, const std::vector<double>& quatB, Index numStep,
                         int precision) {
@@ -982,6 +992,35 @@ class HRM3D : public HighwayRoadMapBase {
             // connectOneSlice for every layer: the candidate segments depend on the free segments only, so they are collected
             // for ALL layers, tested in ONE K4 launch, and the reference's loops are replayed layer by layer on the answers
             StageScope ss(stage_, "connectOneSlice (all)");
+            if (deviceMatching_) {
+                // the 5 candidate segments of every vertex pair are generated and tested on the device from the free segments
+                // (hrmgpu_connect_slices3d); the host counts the pairs of every layer and replays the reference's loops on the codes
+                std::vector<SlicePairs> sp(q_.size());
+                size_t total = 0;
+                for (size_t k = 0; k < q_.size(); ++k) {
+                    const long long* o = off.data() + k * Lx * Ly;
+                    auto segN = [&](int ix, int iy) { return static_cast<size_t>(o[ix * Ly + iy + 1] - o[ix * Ly + iy]); };
+                    sp[k].first = total;
+                    for (int ix = 0; ix < Lx; ++ix)
+                        for (int iy = 0; iy + 1 < Ly; ++iy) sp[k].nInPlane += segN(ix, iy) * segN(ix, iy + 1);
+                    sp[k].P = sp[k].nInPlane;
+                    for (int ix = 0; ix + 1 < Lx; ++ix)
+                        for (int iy = 0; iy < Ly; ++iy) sp[k].P += segN(ix, iy) * segN(ix + 1, iy);
+                    total += sp[k].P;
+                }
+                std::vector<unsigned char> code;
+                std::vector<long long> layerFirst;
+                {
+                    StageScope st(stage_, "  K4 connectSlices (device)");
+                    code = freeSpace_.connectSlices3D(layerFirst, total, q_.size());
+                }
+                numEdgeTests_ += static_cast<long>(5 * code.size());
+                for (size_t k = 0; k < q_.size(); ++k) {
+                    if (static_cast<size_t>(layerFirst[k]) != sp[k].first) throw std::runtime_error("connectSlices3D: pair count mismatch");
+                    const std::vector<int> codes(code.begin() + sp[k].first, code.begin() + sp[k].first + sp[k].P);
+                    replaySlice3D(baseQ[k], tx, ty, off.data() + k * Lx * Ly, xL, xU, xM, sp[k], codes);
+                }
+            } else {
             std::vector<double> A, Bq;
             std::vector<int> layerOf;
             std::vector<SlicePairs> sp(q_.size());
@@ -997,6 +1036,7 @@ class HRM3D : public HighwayRoadMapBase {
             numEdgeTests_ += static_cast<long>(f.size());
             for (size_t k = 0; k < q_.size(); ++k)
                 replaySlice3D(baseQ[k], tx, ty, off.data() + k * Lx * Ly, xL, xU, xM, sp[k], pairCodes(f.data() + sp[k].first, sp[k].P));
+            }
         }
         StageScope ss(stage_, "connectMultiSlice");
         connectMultiSlice();

@@ -196,6 +196,16 @@ int hrmgpu_test_transitions(hrmgpu_ctx* ctx, int C, const int* pair, const doubl
 int hrmgpu_test_transitions_articulated(hrmgpu_ctx* ctx, int C, const int* pair, const double* v0, const double* v1, int T, const double* w0,
                                         const double* w1, const double* link_off, const double* chain_off, unsigned char* free_out);
 
+/* connectOneSlice for ALL layers of the last build as ONE call (HighwayRoadMap-inl.h:218-326, HRM3D.cpp:93-156).  The vertices of a
+ * layer are its free segments (mid points) in CSR order; the reference tries to connect, plane by plane, every vertex of line
+ * (ix, iy) with every vertex of line (ix, iy + 1), then every vertex of line (ix, iy) with every vertex of line (ix + 1, iy), in
+ * that order -- the pair order of this call.  Each pair is tried directly and through the two detour vertices of bridgeVertex
+ * (:295-326): code_out[pair] = 0 the direct segment is free, 1 both segments through (x1, y1, z2) are, 2 both through
+ * (x2, y2, z1) are, 3 none.  The 5 candidate segments of every pair are generated on the device from the free segments and
+ * tested against the layer's C-obstacle meshes (same test as hrmgpu_test_edges); only the codes come back.
+ * layer_first [K + 1] (optional) = index of every layer's first pair.  Returns the number of pairs, or a negative error code. */
+long long hrmgpu_connect_slices3d(hrmgpu_ctx* ctx, unsigned char* code_out, long long cap, long long* layer_first);
+
 /* connectMultiSlice's vertex matching as ONE call (HRM3D.cpp:158-224).  vertex_xyz [V][3] are the positions of the roadmap's
  * vertices (a layer's vertices are its free-segment mid points plus the bridge vertices connectOneSlice inserted, so the host
  * names them); pair p joins the vertices range4[p] = {near begin, near end, cur begin, cur end} (id ranges of the closest earlier

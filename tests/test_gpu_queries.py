@@ -353,3 +353,48 @@ def test_build_bridge_tfe_matches_the_host_ellipsoids(oracle, gpu_ctx):
     gpu_ctx.build_bridge(want[..., :3], np.array([[hm.flat9(hm.quat_to_rot(w[3:])) for w in pr] for pr in want]), capi.F64_STRICT)
     host = gpu_ctx.test_bridge_multi(pp, centres)
     assert np.array_equal(dev, host) and 0 < host.sum() < 600
+
+
+def test_connect_slices3d_equals_host_enumeration(gpu_ctx):
+    """hrmgpu_connect_slices3d (candidate segments of connectOneSlice generated on the device from the free segments, all layers in
+    one call) against the same segments enumerated on the host in the reference's order and tested with hrmgpu_test_edges_multi."""
+    sc = util.scenes()["3D_superquadrics_cluttered_rabbit"]
+    rows = sc["arena"] + sc["obstacle"]
+    n = 10
+    K, Lx, Ly = 5, 8, 5
+    semi, R, off, quat = util.body_poses3d(sc["robot"], sc["quats"][:K])
+    gpu_ctx.set_scene3d(len(sc["arena"]), len(sc["obstacle"]), util.sq17(rows, n), n)
+    gpu_ctx.set_sweep(sc["lim"], Lx, Ly)
+    gpu_ctx.build_layers(semi, R, off, capi.F64_STRICT)
+    lim = sc["lim"]
+    tx = [lim[0] + float(i) * ((lim[1] - lim[0]) / float(Lx - 1)) for i in range(Lx)]
+    ty = [lim[2] + float(i) * ((lim[3] - lim[2]) / float(Ly - 1)) for i in range(Ly)]
+    A, Bq, layer, first = [], [], [], [0]
+    for k in range(K):
+        o, xL, xU, xM = gpu_ctx.segments(k)
+        pairs = []
+        for ix in range(Lx):
+            for iy in range(Ly - 1):
+                for j1 in range(o[ix * Ly + iy], o[ix * Ly + iy + 1]):
+                    for j2 in range(o[ix * Ly + iy + 1], o[ix * Ly + iy + 2]):
+                        pairs.append(((tx[ix], ty[iy], xM[j1]), (tx[ix], ty[iy + 1], xM[j2])))
+        for ix in range(Lx - 1):
+            for iy in range(Ly):
+                for k1 in range(o[ix * Ly + iy], o[ix * Ly + iy + 1]):
+                    for k2 in range(o[(ix + 1) * Ly + iy], o[(ix + 1) * Ly + iy + 1]):
+                        pairs.append(((tx[ix], ty[iy], xM[k1]), (tx[ix + 1], ty[iy], xM[k2])))
+        for v1, v2 in pairs:
+            w1, w2 = (v1[0], v1[1], v2[2]), (v2[0], v2[1], v1[2])
+            A += [v1, v1, w1, v1, w2]
+            Bq += [v2, w1, v2, w2, v2]
+            layer += [k] * 5
+        first.append(first[-1] + len(pairs))
+    f = gpu_ctx.test_edges_multi(np.array(layer), np.array(A), np.array(Bq)).reshape(-1, 5)
+    want = np.where(f[:, 0], 0, np.where(f[:, 1] & f[:, 2], 1, np.where(f[:, 3] & f[:, 4], 2, 3)))
+    got, got_first = gpu_ctx.connect_slices3d(first[-1])
+    assert np.array_equal(got_first, np.array(first))
+    assert np.array_equal(got, want)
+    assert len(set(want.tolist())) >= 3  # direct connections, detours and failures all occur
+    with pytest.raises(capi.HrmGpuError) as e:  # answer buffer too small
+        gpu_ctx.connect_slices3d(first[-1] - 1)
+    assert e.value.code == capi.E_CAP
