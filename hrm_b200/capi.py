@@ -37,6 +37,7 @@ def load():
         "hrmgpu_device_count": (i, []),
         "hrmgpu_create": (i, [C.POINTER(vp), i, C.c_uint]),
         "hrmgpu_destroy": (None, [vp]),
+        "hrmgpu_reset": (i, [vp]),
         "hrmgpu_last_error": (C.c_char_p, [vp]),
         "hrmgpu_set_stream": (i, [vp, vp]),
         "hrmgpu_synchronize": (i, [vp]),

@@ -197,6 +197,21 @@ int hrmgpu_create(hrmgpu_ctx** out, int device, unsigned flags) {
     return HRMGPU_OK;
 }
 
+int hrmgpu_reset(hrmgpu_ctx* c) {
+    if (!c) return HRMGPU_E_ARG;
+    HRMGPU_CUDA(c, cudaSetDevice(c->device));
+    HRMGPU_CUDA(c, cudaStreamSynchronize(c->stream));
+    HRMGPU_CUDA(c, cudaStreamSynchronize(c->s2));
+    c->stream = c->own_stream;
+    c->built = false, c->bridge_built = false, c->sweep_set = false;
+    c->dim = 0, c->K = 0, c->P = 0;
+    c->h_off_valid = false, c->seg_pending = false, c->fetch_pending = false;
+    c->seg_total = 0, c->xchg_world = 0;
+    c->launches = 0, c->seg_redos = 0;
+    c->err.clear();
+    return HRMGPU_OK;
+}
+
 void hrmgpu_destroy(hrmgpu_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);

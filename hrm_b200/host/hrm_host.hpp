@@ -19,6 +19,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 #include <functional>
 #include <map>
 #include <queue>
@@ -362,11 +363,35 @@ struct BoundaryInfo {
 
 class FreeSpaceGPU {
   public:
-    explicit FreeSpaceGPU(int device) {
+    /** The reference builds a FreeSpace3D per planner object; here the device context behind it is kept for the next planner
+     * object on the same device (hrmgpu_reset: no state survives, streams / events / buffers do) -- creating one costs several
+     * milliseconds, a whole plan() on the bundled maps about as much.  HRM_NO_CTX_CACHE=1 turns the cache off. */
+    explicit FreeSpaceGPU(int device) : device_(device) {
+        {
+            std::lock_guard<std::mutex> lk(cache().m);
+            auto& spare = cache().spare;
+            for (size_t i = 0; i < spare.size(); ++i)
+                if (spare[i].first == device) {
+                    ctx_ = spare[i].second;
+                    spare.erase(spare.begin() + static_cast<long>(i));
+                    break;
+                }
+        }
+        if (ctx_) return;
         const int rc = hrmgpu_create(&ctx_, device, 0);
         if (rc != HRMGPU_OK) throw std::runtime_error("hrmgpu_create failed (no sm_100 device? there is no CPU fallback), status " + std::to_string(rc));
     }
-    virtual ~FreeSpaceGPU() { hrmgpu_destroy(ctx_); }
+    virtual ~FreeSpaceGPU() {
+        if (!ctx_) return;
+        if (std::getenv("HRM_NO_CTX_CACHE") == nullptr && hrmgpu_reset(ctx_) == HRMGPU_OK) {
+            std::lock_guard<std::mutex> lk(cache().m);
+            if (cache().spare.size() < 2) {
+                cache().spare.push_back({device_, ctx_});
+                return;
+            }
+        }
+        hrmgpu_destroy(ctx_);
+    }
     FreeSpaceGPU(const FreeSpaceGPU&) = delete;
     FreeSpaceGPU& operator=(const FreeSpaceGPU&) = delete;
 
@@ -474,6 +499,18 @@ class FreeSpaceGPU {
     }
 
   protected:
+    struct CtxCache {
+        std::mutex m;
+        std::vector<std::pair<int, hrmgpu_ctx*>> spare;
+        ~CtxCache() {
+            for (auto& s : spare) hrmgpu_destroy(s.second);
+        }
+    };
+    static CtxCache& cache() {
+        static CtxCache c;
+        return c;
+    }
+    int device_ = 0;
     hrmgpu_ctx* ctx_ = nullptr;
     std::vector<Coordinate> lim_;
     Index Lx_ = 0, Ly_ = 0;
@@ -1407,13 +1444,26 @@ class HRM3D : public HighwayRoadMapBase {
             if (angularDistance(minQuat, q) < radius) list.push_back(q);
             if (list.size() >= k) break;
         }
+        // The reference scans every vertex for the ones whose orientation is (numerically) qc.  Vertices carry their layer's
+        // quaternion verbatim and are stored layer after layer, so the orientation test is made once per run of identical
+        // quaternions instead of once per vertex (same comparisons on the same values, same vertex order: same result).
+        std::vector<std::pair<size_t, size_t>> runs;
+        for (size_t i = 0; i < V.size();) {
+            size_t j = i + 1;
+            while (j < V.size() && V[j][3] == V[i][3] && V[j][4] == V[i][4] && V[j][5] == V[i][5] && V[j][6] == V[i][6]) ++j;
+            runs.push_back({i, j});
+            i = j;
+        }
         std::vector<Index> idx;
         for (const auto& qc : list) {
             Index idxSlice = 0;
             double best = INFINITY;
-            for (size_t i = 0; i < V.size(); ++i) {
-                const double d = vectorEuclidean(vertex, V[i]);
-                if (d < best && angularDistance(qc, {V[i][3], V[i][4], V[i][5], V[i][6]}) < 1e-6) best = d, idxSlice = i;
+            for (const auto& run : runs) {
+                if (!(angularDistance(qc, {V[run.first][3], V[run.first][4], V[run.first][5], V[run.first][6]}) < 1e-6)) continue;
+                for (size_t i = run.first; i < run.second; ++i) {
+                    const double d = vectorEuclidean(vertex, V[i]);
+                    if (d < best) best = d, idxSlice = i;
+                }
             }
             if (std::abs(vertex[0] - V[idxSlice][0]) < radius * (lim[1] - lim[0]) / static_cast<double>(param_.numLineX) &&
                 std::abs(vertex[1] - V[idxSlice][1]) < radius * (lim[3] - lim[2]) / static_cast<double>(param_.numLineY))

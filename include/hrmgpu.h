@@ -61,6 +61,10 @@ int hrmgpu_device_count(void);
 /* One context per GPU.  device = CUDA ordinal.  flags: reserved, pass 0. */
 int hrmgpu_create(hrmgpu_ctx** out, int device, unsigned flags);
 void hrmgpu_destroy(hrmgpu_ctx* ctx);
+/* Back to the state right after hrmgpu_create -- no scene, no sweep grid, no layers, no bridge layers, counters zero, the
+ * context's own stream -- but with its streams, events and device buffers kept: a planner object that is created per query
+ * (the reference builds a FreeSpace3D per planner) can hand its context to the next one instead of paying for creation. */
+int hrmgpu_reset(hrmgpu_ctx* ctx);
 const char* hrmgpu_last_error(const hrmgpu_ctx* ctx);
 /* Run all subsequent work of this context on an existing CUDA stream (cudaStream_t as void*);
  * NULL = the context's own stream.  Lets a host framework time / order the work with its own events. */

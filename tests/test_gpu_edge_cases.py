@@ -113,5 +113,16 @@ def test_errors_are_status_codes_not_crashes():
         assert len(ctx.last_error()) > 0
         o, xL, xU, xM = ctx.segments(0)  # the context is still usable after the failures
         assert o[-1] == len(xM)
+        # hrmgpu_reset: back to "no scene, nothing built" with the buffers kept; then usable again with the same results
+        assert ctx.lib.hrmgpu_reset(ctx.h) == 0
+        with pytest.raises(RuntimeError):
+            ctx.segments(0)
+        with pytest.raises(RuntimeError):
+            ctx.build_layers(semi, R, off, capi.F64_STRICT)
+        ctx.set_scene3d(1, 3, util.sq17(rows.tolist(), 10), 10)
+        ctx.set_sweep(LIM, 4, 3)
+        ctx.build_layers(semi, R, off, capi.F64_STRICT)
+        o2, xL2, xU2, xM2 = ctx.segments(0)
+        assert np.array_equal(o, o2) and np.array_equal(xM, xM2)
     finally:
         ctx.close()
