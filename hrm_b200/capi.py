@@ -60,7 +60,7 @@ def load():
         "hrmgpu_test_transitions": (i, [vp, i, vp, vp, vp, i, vp, vp, vp, vp]),
         "hrmgpu_test_transitions_articulated": (i, [vp, i, vp, vp, vp, i, vp, vp, vp, vp, vp]),
         "hrmgpu_connect_slices3d": (ll, [vp, vp, ll, vp]),
-        "hrmgpu_connect_pairs3d": (ll, [vp, ll, vp, i, vp, C.c_double, C.c_double, i, vp, vp, vp, vp, ll, vp]),
+        "hrmgpu_connect_pairs3d": (ll, [vp, ll, vp, i, vp, C.c_double, C.c_double, i, vp, vp, vp, vp, vp, ll, vp]),
         "hrmgpu_build_bridge": (i, [vp, i, i, vp, vp, i]),
         "hrmgpu_build_bridge_tfe": (i, [vp, i, i, vp, vp, vp, i, i, vp]),
         "hrmgpu_build_bridge2d": (i, [vp, i, i, vp, vp, i]),
@@ -331,17 +331,19 @@ class Context:
         n = self._chk(self.lib.hrmgpu_connect_slices3d(self.h, _p(code), int(cap), _p(first)))
         return code[:n], first
 
-    def connect_pairs3d(self, vertex_xyz, range4, thx, thy, w0, w1, link_off):
+    def connect_pairs3d(self, vertex_xyz, range4, thx, thy, w0, w1, link_off, chain_off=None):
         """connectMultiSlice's vertex matching on the device (see include/hrmgpu.h): vertex_xyz [V][3], range4 [P][4] =
         {near begin, near end, cur begin, cur end}; returns (match, transition tests made), match[first(p) + (m0 - near begin)] =
         id of the vertex that m0 connects to, or -1."""
         xyz = _d(vertex_xyz).reshape(-1, 3)
         r4 = np.ascontiguousarray(range4, dtype=np.int32).reshape(-1, 4)
         w0, w1, link_off = _d(w0), _d(w1), _d(link_off)
+        chain_off = None if chain_off is None else _d(chain_off)
         match = np.full(max(1, int((r4[:, 1] - r4[:, 0]).sum())), -1, dtype=np.int32)
         ncand = C.c_longlong(0)
         n = self._chk(self.lib.hrmgpu_connect_pairs3d(self.h, xyz.shape[0], _p(xyz), r4.shape[0], _p(r4), float(thx), float(thy), w0.shape[0], _p(w0),
-                                                      _p(w1), _p(link_off), _p(match), match.shape[0], C.byref(ncand)))
+                                                      _p(w1), _p(link_off), None if chain_off is None else _p(chain_off), _p(match), match.shape[0],
+                                                      C.byref(ncand)))
         return match[:n], int(ncand.value)
 
     def pack_segments_dev(self, d_ptr=None, cap_bytes=0):

@@ -797,8 +797,8 @@ long long hrmgpu_connect_slices3d(hrmgpu_ctx* c, unsigned char* code_out, long l
 }
 
 long long hrmgpu_connect_pairs3d(hrmgpu_ctx* c, long long V, const double* vertex_xyz, int P, const int* range4, double thx, double thy, int T,
-                                 const double* w0, const double* w1, const double* link_off, int* match_out, long long match_cap,
-                                 long long* n_candidates_out) {
+                                 const double* w0, const double* w1, const double* link_off, const double* chain_off, int* match_out,
+                                 long long match_cap, long long* n_candidates_out) {
     if (!c) return HRMGPU_E_ARG;
     if (c->dim != 3 || !c->bridge_built) return fail(c, HRMGPU_E_STATE, "connect_pairs3d: no 3D bridge layers built");
     if (V < 0 || V > 0x7FFFFFF0LL || P < 0 || P != c->P || T < 1 || (P > 0 && (!vertex_xyz || !range4 || !w0 || !w1 || !link_off || !match_out)))
@@ -855,7 +855,9 @@ long long hrmgpu_connect_pairs3d(hrmgpu_ctx* c, long long V, const double* verte
         if ((rc = upload(c, c->q_w, w.data(), w.size()))) return rc;
         const size_t nl = static_cast<size_t>(c->P) * T * c->bridge_B * 3;
         if ((rc = upload(c, c->q_loff, link_off, nl))) return rc;
-        if ((rc = launch_transitions(c, static_cast<int>(C), T, c->q_set.p, c->q_a.p, c->q_b.p, c->q_w.p, c->q_w.p + T, c->q_loff.p, c->q_out.p, nullptr)))
+        if (chain_off && (rc = upload(c, c->q_loff2, chain_off, nl))) return rc;
+        if ((rc = launch_transitions(c, static_cast<int>(C), T, c->q_set.p, c->q_a.p, c->q_b.p, c->q_w.p, c->q_w.p + T, c->q_loff.p, c->q_out.p,
+                                     chain_off ? c->q_loff2.p : nullptr)))
             return rc;
     }
     if ((rc = launch_pair_replay(c, P, c->pc_m0_first.p, c->pc_first.p, c->pc_m1.p, c->q_out.p, c->pc_match.p))) return rc;

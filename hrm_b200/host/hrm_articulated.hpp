@@ -210,6 +210,28 @@ class ProbHRM3D : public HRM3D {
                     freeSpace_.getFreeSegmentsAll(off, xL, xU, xM);
                 }
                 batchStart = s, batchEnd = s + have;
+                batchCode_.clear();
+                if (deviceMatching_) {
+                    // connectOneSlice's candidate segments of the WHOLE look-ahead batch in one call (they depend on the free
+                    // segments only); the slices below replay the reference's loops on the cached codes, one after the other
+                    StageScope ss(stage_, "K4 connectSlices (device, per batch)");
+                    batchSp_.assign(have, SlicePairs());
+                    size_t total = 0;
+                    for (size_t k = 0; k < have; ++k) {
+                        const long long* o = off.data() + k * static_cast<size_t>(Lx) * Ly;
+                        auto segN = [&](int ix, int iy) { return static_cast<size_t>(o[ix * Ly + iy + 1] - o[ix * Ly + iy]); };
+                        batchSp_[k].first = total;
+                        for (int ix = 0; ix < Lx; ++ix)
+                            for (int iy = 0; iy + 1 < Ly; ++iy) batchSp_[k].nInPlane += segN(ix, iy) * segN(ix, iy + 1);
+                        batchSp_[k].P = batchSp_[k].nInPlane;
+                        for (int ix = 0; ix + 1 < Lx; ++ix)
+                            for (int iy = 0; iy < Ly; ++iy) batchSp_[k].P += segN(ix, iy) * segN(ix + 1, iy);
+                        total += batchSp_[k].P;
+                    }
+                    std::vector<long long> layerFirst;
+                    batchCode_ = freeSpace_.connectSlices3D(layerFirst, total, have);
+                    if (batchCode_.size() != total) throw std::runtime_error("connectSlices3D: pair count mismatch");
+                }
             }
             // constructOneSlice: vertices + intra-layer edges of slice s
             const size_t k = s - batchStart;
@@ -217,7 +239,14 @@ class ProbHRM3D : public HRM3D {
             q_.push_back({v_.at(s)[3], v_.at(s)[4], v_.at(s)[5], v_.at(s)[6]});
             {
                 StageScope ss(stage_, "connectOneSlice");
-                connectOneSlice3D(static_cast<int>(k), baseQ.at(k), tx, ty, off.data() + k * static_cast<size_t>(Lx) * Ly, xL, xU, xM);
+                if (deviceMatching_) {
+                    const SlicePairs& sp = batchSp_.at(k);
+                    numEdgeTests_ += static_cast<long>(5 * sp.P);
+                    const std::vector<int> codes(batchCode_.begin() + static_cast<long>(sp.first), batchCode_.begin() + static_cast<long>(sp.first + sp.P));
+                    replaySlice3D(baseQ.at(k), tx, ty, off.data() + k * static_cast<size_t>(Lx) * Ly, xL, xU, xM, sp, codes);
+                } else {
+                    connectOneSlice3D(static_cast<int>(k), baseQ.at(k), tx, ty, off.data() + k * static_cast<size_t>(Lx) * Ly, xL, xU, xM);
+                }
             }
             param_.numSlice++;
             if (param_.numSlice >= 2) {
@@ -348,6 +377,22 @@ class ProbHRM3D : public HRM3D {
                 }
             }
         }
+        if (deviceMatching_) {
+            // candidate enumeration, transition tests (articulated variant) and the replay of the moving lower bound on the device
+            stage_.add("  FK of the interpolated poses (host)", seconds(tT));
+            std::vector<double> xyz(3 * V.size());
+            for (size_t m = 0; m < V.size(); ++m)
+                for (int d = 0; d < 3; ++d) xyz[3 * m + d] = V[m][d];
+            const std::vector<int> range4 = {static_cast<int>(start), static_cast<int>(n1), static_cast<int>(new0), static_cast<int>(new1)};
+            std::vector<int> match;
+            {
+                StageScope ss(stage_, "  K5b connectPairs (device)");
+                match = freeSpace_.connectPairs3D(xyz, range4, thx, thy, w0, w1, linkOff, &numBridgeCandidates_, &chainOff);
+            }
+            for (Index m0 = start; m0 < n1; ++m0)
+                if (match[m0 - start] >= 0) addEdge(m0, static_cast<Index>(match[m0 - start]));
+            return;
+        }
         std::vector<std::pair<Index, Index>> cand;
         std::vector<double> v0s, v1s;
         for (Index m0 = start; m0 < n1; ++m0)
@@ -377,6 +422,8 @@ class ProbHRM3D : public HRM3D {
         }
     }
 
+    std::vector<unsigned char> batchCode_;  // connectOneSlice pair codes of the look-ahead batch (device matching)
+    std::vector<SlicePairs> batchSp_;
     std::string urdfFile_;
     ParseURDF kdl_;
     MultiBodyTree3D robot0_ = robot_;  // the as-loaded robot

@@ -479,13 +479,13 @@ class FreeSpaceGPU {
      * on the device */
     std::vector<int> connectPairs3D(const std::vector<double>& vertexXYZ, const std::vector<int>& range4, double thx, double thy,
                                     const std::vector<double>& w0, const std::vector<double>& w1, const std::vector<double>& linkOff,
-                                    long long* numCandidates = nullptr) {
+                                    long long* numCandidates = nullptr, const std::vector<double>* chainOff = nullptr) {
         size_t numNear = 0;
         for (size_t i = 0; i + 3 < range4.size(); i += 4) numNear += static_cast<size_t>(range4[i + 1] - range4[i]);
         std::vector<int> match(numNear > 0 ? numNear : 1, -1);
         const long long n = hrmgpu_connect_pairs3d(ctx_, static_cast<long long>(vertexXYZ.size() / 3), vertexXYZ.data(), static_cast<int>(range4.size() / 4),
-                                                   range4.data(), thx, thy, static_cast<int>(w0.size()), w0.data(), w1.data(), linkOff.data(), match.data(),
-                                                   static_cast<long long>(match.size()), numCandidates);
+                                                   range4.data(), thx, thy, static_cast<int>(w0.size()), w0.data(), w1.data(), linkOff.data(),
+                                                   chainOff ? chainOff->data() : nullptr, match.data(), static_cast<long long>(match.size()), numCandidates);
         if (n < 0) check(static_cast<int>(n));
         match.resize(static_cast<size_t>(n));
         return match;

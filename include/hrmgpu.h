@@ -218,11 +218,12 @@ long long hrmgpu_connect_slices3d(hrmgpu_ctx* ctx, unsigned char* code_out, long
  * reference's moving lower bound: the first one with |x0 - x1| <= thx, |y0 - y1| <= thy (:195-200) whose interpolated
  * transition is free (same T, w0, w1, link_off as hrmgpu_test_transitions) is its match, and the new lower bound.
  * match_out[first(p) + (m0 - near begin)] = m1 (vertex id) or -1, pairs concatenated.  The candidate enumeration, the transition
- * tests and the replay all run on the device; only the matches come back.  Returns the number of entries written, or a
- * negative error code; n_candidates_out (optional) = transition tests made. */
+ * tests and the replay all run on the device; only the matches come back.  chain_off (NULL for rigid robots) selects the
+ * articulated variant of hrmgpu_test_transitions_articulated.  Returns the number of entries written, or a negative error
+ * code; n_candidates_out (optional) = transition tests made. */
 long long hrmgpu_connect_pairs3d(hrmgpu_ctx* ctx, long long V, const double* vertex_xyz, int P, const int* range4, double thx, double thy, int T,
-                                 const double* w0, const double* w1, const double* link_off, int* match_out, long long match_cap,
-                                 long long* n_candidates_out);
+                                 const double* w0, const double* w1, const double* link_off, const double* chain_off, int* match_out,
+                                 long long match_cap, long long* n_candidates_out);
 
 /* ---- multi-GPU exchange ------------------------------------------------------------------------ */
 /* C-layers shard by orientation: every rank (one process, one context, one GPU) builds its own block of layers with no
