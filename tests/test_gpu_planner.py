@@ -150,8 +150,9 @@ def _prob_case(oracle, name, per_orientation, n_samples, batch):
 
     sc = util.scenes()[name]
     rows = np.array(sc["arena"] + sc["obstacle"])
-    urdf = os.path.join(GOLDEN, "snake.urdf")
-    draws = prob_samples(n_samples, 3)
+    tree = name.endswith("_tree")  # tree.urdf: three chains off the base, 9 joints; snake.urdf: one chain, 3 joints
+    urdf = os.path.join(GOLDEN, "tree.urdf" if tree else "snake.urdf")
+    draws = prob_samples(n_samples, 9 if tree else 3)
     args = (len(sc["arena"]), len(sc["obstacle"]), rows, 10, np.array(sc["robot"]), urdf, draws, sc["lim"], sc["Lx"], sc["Ly"], 5,
             sc["end_points"][0], sc["end_points"][1])
     ref = oracle.plan_prob3d(*args, per_orientation=per_orientation)
@@ -160,7 +161,8 @@ def _prob_case(oracle, name, per_orientation, n_samples, batch):
 
 
 @pytest.mark.parametrize("name,per_orientation,batch", [("3D_superquadrics_sparse_snake", False, 8), ("3D_superquadrics_cluttered_snake", True, 4),
-                                                        ("3D_superquadrics_home_snake", True, 8), ("3D_superquadrics_home_snake", True, 3)])
+                                                        ("3D_superquadrics_home_snake", True, 8), ("3D_superquadrics_home_snake", True, 3),
+                                                        ("3D_superquadrics_sparse_tree", True, 4), ("3D_superquadrics_sparse_tree", False, 8)])
 def test_prob_hrm3d_roadmap_identical(oracle, name, per_orientation, batch):
     """Same draws -> the GPU-backed ProbHRM3D (layers built `batch` slices ahead) must reproduce the oracle's sequential
     planner: slice count, vertex list (with joint angles), edge list, solved, path."""
@@ -262,3 +264,27 @@ def test_free_space_layer_view_follows_the_reference_call_order(oracle):
         if k == 0:
             assert np.array_equal(got[0]["bound"], ref["bound"])
     assert sum(len(g["xM"]) for g in got) > 100
+
+
+def test_prob_hrm3d_tree_robot_bridges_identical(oracle):
+    """tree.urdf (three chains off the base) on the home map: 12 draws do not solve it, so all 14 slices are built and every one
+    is bridged to its nearest earlier slice through the articulated TFE / transition tests -- the GPU-backed planner (look-ahead
+    batches, device matching) must give the oracle's roadmap vertex for vertex and edge for edge."""
+    import os
+
+    from hrm_b200 import hostlib
+    from tests.test_oracle_kat import GOLDEN, prob_samples
+
+    S = util.scenes()
+    sc, tree = S["3D_superquadrics_home_snake"], S["3D_superquadrics_sparse_tree"]
+    rows = np.array(sc["arena"] + sc["obstacle"])
+    ep0 = list(sc["end_points"][0][:7]) + list(tree["end_points"][0][7:])
+    ep1 = list(sc["end_points"][1][:7]) + list(tree["end_points"][1][7:])
+    ep0, ep1 = ep0 + [0.0] * (16 - len(ep0)), ep1 + [0.0] * (16 - len(ep1))  # (the bundled end points name 6 of the 9 joints)
+    args = (len(sc["arena"]), len(sc["obstacle"]), rows, 10, np.array(tree["robot"]), os.path.join(GOLDEN, "tree.urdf"), prob_samples(12, 9), sc["lim"],
+            sc["Lx"], sc["Ly"], 5, ep0, ep1)
+    ref = oracle.plan_prob3d(*args, per_orientation=True)
+    got = hostlib.plan_prob3d(*args, per_orientation=True, precision=capi.F64_STRICT, batch=5)
+    assert ref["slices"] == got["slices"] == 14 and not ref["solved"] and not got["solved"]
+    assert np.array_equal(got["vertex"], ref["vertex"])
+    assert np.array_equal(got["edge"], ref["edge"]) and len(ref["edge"]) > 10000
