@@ -172,18 +172,25 @@ class ProbHRM3D : public HRM3D {
     void setSeed(unsigned long long seed) { rng_.seed(seed); }
     void setBatch(size_t batch) { batch_ = batch > 0 ? batch : 1; }
     void setMaxSlices(size_t n) { maxSlices_ = n; }
+    /** sweep lines of ALL slices doubled every `period` slices, at most numPoint times (ProbHRM3D.cpp:52-56: 60); 0 = never */
+    void setRefinePeriod(size_t period) { refinePeriod_ = period; }
     Index numSlices() const { return param_.numSlice; }
 
     /** ProbHRM3D.cpp:18-65 */
     void plan(double timeLim = 0.0) override {
         auto t0 = std::chrono::high_resolution_clock::now();
         const auto& lim = param_.boundaryLimits;
-        const int Lx = static_cast<int>(param_.numLineX), Ly = static_cast<int>(param_.numLineY);
-        freeSpace_.setup(lim, param_.numLineX, param_.numLineY);
-        const double dx = (lim[1] - lim[0]) / static_cast<double>(Lx - 1), dy = (lim[3] - lim[2]) / static_cast<double>(Ly - 1);
-        std::vector<double> tx(Lx), ty(Ly);
-        for (int i = 0; i < Lx; ++i) tx[i] = lim[0] + static_cast<double>(i) * dx;
-        for (int i = 0; i < Ly; ++i) ty[i] = lim[2] + static_cast<double>(i) * dy;
+        int Lx = 0, Ly = 0;
+        std::vector<double> tx, ty;
+        auto setGrid = [&]() {  // (again after every refinement: the line counts double)
+            Lx = static_cast<int>(param_.numLineX), Ly = static_cast<int>(param_.numLineY);
+            freeSpace_.setup(lim, param_.numLineX, param_.numLineY);
+            const double dx = (lim[1] - lim[0]) / static_cast<double>(Lx - 1), dy = (lim[3] - lim[2]) / static_cast<double>(Ly - 1);
+            tx.assign(Lx, 0.0), ty.assign(Ly, 0.0);
+            for (int i = 0; i < Lx; ++i) tx[i] = lim[0] + static_cast<double>(i) * dx;
+            for (int i = 0; i < Ly; ++i) ty[i] = lim[2] + static_cast<double>(i) * dy;
+        };
+        setGrid();
 
         param_.numSlice = 0;
         size_t batchStart = 0, batchEnd = 0;  // slices [batchStart, batchEnd) have their layers on the device
@@ -260,6 +267,12 @@ class ProbHRM3D : public HRM3D {
             res_.planningTime.searchTime += seconds(t0);
             t0 = std::chrono::high_resolution_clock::now();
             res_.planningTime.totalTime = res_.planningTime.buildTime + res_.planningTime.searchTime;
+            // ProbHRM3D.cpp:52-56: double the sweep lines of all slices every `refinePeriod_` slices (at most numPoint times)
+            if (refinePeriod_ > 0 && param_.numSlice % refinePeriod_ == 0 && vertexIdxAll_.size() < param_.numPoint) {
+                StageScope ss(stage_, "refineExistRoadmap");
+                refineAllSlices(setGrid, tx, ty, timeLim, t0);
+                batchStart = batchEnd = 0;  // the layers on the device are the refined ones: the next slice starts a new batch
+            }
         } while (!res_.solved && param_.numSlice < maxSlices_ && (timeLim <= 0.0 || res_.planningTime.totalTime < timeLim));
         if (res_.solved) {
             const size_t pose = res_.graphStructure.vertex.at(0).size();
@@ -276,6 +289,77 @@ class ProbHRM3D : public HRM3D {
   protected:
     static double seconds(std::chrono::high_resolution_clock::time_point t0) {
         return std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+    }
+
+    /** refineExistRoadmap (HighwayRoadMap-inl.h:176-215) for the articulated planner: the C-layers of ALL slices so far are
+     * rebuilt in ONE call at the doubled line counts (every slice on its own robot shape, SURVEY.md §8 f.4 -- the reference's
+     * FreeSpace object only remembers the last slice), their candidate segments tested in one device call, and the
+     * reference's per-slice loop (new vertices, connectOneSlice, connectExistSlice with the slice's previous vertices, search)
+     * is replayed on the answers. */
+    template <class SetGrid>
+    void refineAllSlices(SetGrid& setGrid, std::vector<double>& tx, std::vector<double>& ty, double timeLim,
+                         std::chrono::high_resolution_clock::time_point& t0) {
+        vertexIdxAll_.push_back(vertexIdx_);
+        vertexIdx_.clear();
+        param_.numLineX *= 2;
+        param_.numLineY *= 2;
+        setGrid();
+        const auto& lim = param_.boundaryLimits;
+        const int Lx = static_cast<int>(param_.numLineX), Ly = static_cast<int>(param_.numLineY);
+        const size_t K = param_.numSlice;
+        std::vector<MultiBodyTree3D> poses;
+        std::vector<Quaternion> baseQ;
+        for (size_t k = 0; k < K; ++k) {
+            setTransform(v_.at(k));
+            baseQ.push_back(robot_.getBase().getQuaternion());
+            poses.push_back(perOrientation_ ? robot_ : robot0_);
+        }
+        std::vector<long long> off;
+        std::vector<double> xL, xU, xM;
+        freeSpace_.buildLayers(poses, precision_);
+        freeSpace_.getFreeSegmentsAll(off, xL, xU, xM);
+        std::vector<SlicePairs> sp(K);
+        size_t total = 0;
+        for (size_t k = 0; k < K; ++k) {
+            const long long* o = off.data() + k * static_cast<size_t>(Lx) * Ly;
+            auto segN = [&](int ix, int iy) { return static_cast<size_t>(o[ix * Ly + iy + 1] - o[ix * Ly + iy]); };
+            sp[k].first = total;
+            for (int ix = 0; ix < Lx; ++ix)
+                for (int iy = 0; iy + 1 < Ly; ++iy) sp[k].nInPlane += segN(ix, iy) * segN(ix, iy + 1);
+            sp[k].P = sp[k].nInPlane;
+            for (int ix = 0; ix + 1 < Lx; ++ix)
+                for (int iy = 0; iy < Ly; ++iy) sp[k].P += segN(ix, iy) * segN(ix + 1, iy);
+            total += sp[k].P;
+        }
+        std::vector<long long> layerFirst;
+        const std::vector<unsigned char> code = freeSpace_.connectSlices3D(layerFirst, total, K);
+        if (code.size() != total) throw std::runtime_error("connectSlices3D: pair count mismatch");
+        const double thx = 2.0 * std::fabs(lim[1] - lim[0]) / static_cast<double>(param_.numLineX);
+        const double thy = 2.0 * std::fabs(lim[3] - lim[2]) / static_cast<double>(param_.numLineY);
+        for (size_t k = 0; k < K; ++k) {
+            // generateVertices (ProbHRM3D.cpp:164-194) copies the joint angles of v_.back(), i.e. of the NEWEST slice, also while an
+            // older slice is being refined: kept, so that the roadmap is the reference's (here v_ may already hold look-ahead draws)
+            vertexTail_.assign(v_.at(K - 1).begin() + 7, v_.at(K - 1).end());
+            numEdgeTests_ += static_cast<long>(5 * sp[k].P);
+            const std::vector<int> codes(code.begin() + static_cast<long>(sp[k].first), code.begin() + static_cast<long>(sp[k].first + sp[k].P));
+            replaySlice3D(baseQ[k], tx, ty, off.data() + k * static_cast<size_t>(Lx) * Ly, xL, xU, xM, sp[k], codes);
+            const auto& V = res_.graphStructure.vertex;
+            connectExistSliceReplay(
+                k, [&](const std::vector<Coordinate>& a, const std::vector<Coordinate>& b) { return !(std::fabs(a[0] - b[0]) > thx) && !(std::fabs(a[1] - b[1]) > thy); },
+                [&](const std::vector<std::pair<Index, Index>>& cand) {
+                    std::vector<double> A, Bq;
+                    for (const auto& c : cand)
+                        for (int d = 0; d < 3; ++d) A.push_back(V[c.first][d]), Bq.push_back(V[c.second][d]);
+                    return freeSpace_.testEdges(static_cast<int>(k), A, Bq, 3);
+                });
+            res_.planningTime.buildTime += seconds(t0);
+            t0 = std::chrono::high_resolution_clock::now();
+            search();
+            res_.planningTime.searchTime += seconds(t0);
+            t0 = std::chrono::high_resolution_clock::now();
+            res_.planningTime.totalTime = res_.planningTime.buildTime + res_.planningTime.searchTime;
+            if (res_.solved || (timeLim > 0.0 && res_.planningTime.totalTime > timeLim)) return;
+        }
     }
 
     /** sampleOrientations (:67-102) for slice s; false when the injected list has no more rows */
@@ -432,6 +516,7 @@ class ProbHRM3D : public HRM3D {
     bool injected_ = false;
     std::mt19937_64 rng_{20220726ULL};
     size_t batch_ = 8;
+    size_t refinePeriod_ = 60;
     size_t maxSlices_ = 4096;  // hard stop for the seeded-RNG mode without a time limit
     double maxJointAngle_ = PI / 2;
 };

@@ -41,6 +41,8 @@ extern "C" {
 
 const char* hrmhost_last_error(void) { return g_err.c_str(); }
 void hrmhost_set_max_refine(int rounds) { g_max_refine = rounds < 0 ? 0 : rounds; }
+static int g_prob_refine_period = 60;  // ProbHRM3D.cpp:52-56
+void hrmhost_set_prob_refine_period(int n) { g_prob_refine_period = n < 0 ? 0 : n; }
 
 // hrm::planners::HRM3D(robot, arena, obs, req).plan().  Returns 0, or -1 with hrmhost_last_error() set.
 // info[8]: solved, n_vertex, n_edge, n_path, -, n_edge_tests, gpu_kernel_launches, total_time_us.
@@ -336,6 +338,7 @@ int hrmhost_plan_prob3d(int n_arena, int n_obs, const double* sq, int n, int B, 
             hrm.setSeed(seed);
         }
         hrm.setBatch(static_cast<size_t>(batch));
+        hrm.setRefinePeriod(static_cast<size_t>(g_prob_refine_period));
         hrm.plan(time_limit);
         exportResult(hrm, info, vertex, cap_v, 7 + nj, edge, cap_e, path, cap_p);
         info[4] = static_cast<long>(hrm.numSlices());

@@ -39,6 +39,11 @@ def set_max_refine(rounds):
     load().hrmhost_set_max_refine(C.c_int(rounds))
 
 
+def set_prob_refine_period(n):
+    """ProbHRM3D doubles the sweep lines of all slices every `n` slices (60 in the reference, ProbHRM3D.cpp:52-56; 0 = never)."""
+    load().hrmhost_set_prob_refine_period(C.c_int(n))
+
+
 def plan3d(n_arena, n_obs, sq12, n, robot_rows, quats, lim, Lx, Ly, num_point, start, goal, per_orientation=False, precision=0, device=0,
            cap_v=1 << 18, cap_e=1 << 21):
     """hrm::planners::HRM3D(robot, arena, obstacle, request).plan() on the GPU-backed free space."""

@@ -421,6 +421,11 @@ def set_max_refine(n):
     lib().hrmo_set_max_refine(C.c_int(n))
 
 
+def set_prob_refine_period(n):
+    """ProbHRM3D doubles the sweep lines of all slices every `n` slices (60 in the reference, ProbHRM3D.cpp:52-56; 0 = never)."""
+    lib().hrmo_set_prob_refine_period(C.c_int(n))
+
+
 def plan3d(n_arena, n_obs, sq, n, robot_rows, quats, lim, Lx, Ly, num_point, start, goal, per_orientation=False,
            cap_v=1 << 18, cap_e=1 << 21):
     sq, robot_rows, quats, lim, start, goal = _d(sq), _d(robot_rows), _d(quats), _d(lim), _d(start)[:7].copy(), _d(goal)[:7].copy()

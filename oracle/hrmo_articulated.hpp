@@ -180,7 +180,8 @@ inline void robotTF(MultiBodyTree3D& robot, const KinematicTree& kdl, const Tf3&
 // The reference draws the base rotation (Quaterniond::UnitRandom) and the joint angles (ompl::RNG) of every slice after
 // the first two at run time (SURVEY.md finding 9); here the draws are an injected list, one row [qw,qx,qy,qz, joints...] per
 // slice >= 2, and plan() stops when the path is found or the list is exhausted.  The sweep-line refinement every 60 slices
-// (ProbHRM3D.cpp:52-56) is not restated.
+// (ProbHRM3D.cpp:52-56) is restated with the period as a parameter (60 in the reference; tests use small periods), on top of
+// the base class's refineExistRoadmap ("done right", SURVEY.md §8 f.4: every slice re-swept on its own cached boundary).
 struct ProbHRM3D : HRM3D {
     KinematicTree kdl_;
     std::vector<std::vector<double>> samples_;
@@ -193,17 +194,19 @@ struct ProbHRM3D : HRM3D {
     }
 
     // :18-65
-    void planProb() {
+    void planProb(size_t refinePeriod = 60) {
         param_.numSlice = 0;
         do {
             if (param_.numSlice >= 2 && param_.numSlice - 2 >= samples_.size()) break;  // injected draws exhausted
             sampleOrientations();
             constructOneSlice(param_.numSlice);
-            param_.numSlice++;
+            if (!isRefine_) param_.numSlice++;
             numVertex_.slice = res_.graphStructure.vertex.size();
             vertexIdx_.push_back(numVertex_);
             if (param_.numSlice >= 2) connectMultiSlice();
             search();
+            // :52-56 "Double the number of sweep lines for every 10 iterations" (the code says 60), at most numPoint times
+            if (refinePeriod > 0 && param_.numSlice % refinePeriod == 0 && vertexIdxAll_.size() < param_.numPoint) refineExistRoadmap();
         } while (!res_.solved);
         if (res_.solved) {
             const size_t poseSize = res_.graphStructure.vertex.at(0).size();

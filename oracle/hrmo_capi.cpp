@@ -426,6 +426,8 @@ long hrmo_pt_in_cfree2d(const double* bound, int num, int count, int Q, const do
 // limit; rounds are counted here to keep the runs deterministic).  out_info[7] = rounds done.
 static int g_max_refine = 0;
 void hrmo_set_max_refine(int n) { g_max_refine = n < 0 ? 0 : n; }
+static int g_prob_refine_period = 60;  // ProbHRM3D.cpp:52-56
+void hrmo_set_prob_refine_period(int n) { g_prob_refine_period = n < 0 ? 0 : n; }
 
 int hrmo_plan3d(int n_arena, int n_obs, const double* sq, int n, int B, const double* robot, int numSlice, const double* quats,
                 const double lim[6], int Lx, int Ly, int numPoint, const double* start, const double* goal, int per_orientation,
@@ -563,7 +565,7 @@ int hrmo_plan_prob3d(int n_arena, int n_obs, const double* sq, int n, int B, con
         for (int i = 0; i < n_samples; ++i) draws.emplace_back(samples + static_cast<size_t>(i) * (4 + nj), samples + static_cast<size_t>(i + 1) * (4 + nj));
         ProbHRM3D hrm(rb, urdf, arena, obs, req, draws, per_orientation != 0);
         if (static_cast<int>(hrm.kdl_.getNrOfJoints()) != nj) return -2;
-        hrm.planProb();
+        hrm.planProb(static_cast<size_t>(g_prob_refine_period));
         const auto& g = hrm.res_.graphStructure;
         const int W = 7 + nj;
         out_info[0] = hrm.res_.solved ? 1 : 0;

@@ -153,8 +153,9 @@ def _prob_case(oracle, name, per_orientation, n_samples, batch):
     tree = name.endswith("_tree")  # tree.urdf: three chains off the base, 9 joints; snake.urdf: one chain, 3 joints
     urdf = os.path.join(GOLDEN, "tree.urdf" if tree else "snake.urdf")
     draws = prob_samples(n_samples, 9 if tree else 3)
-    args = (len(sc["arena"]), len(sc["obstacle"]), rows, 10, np.array(sc["robot"]), urdf, draws, sc["lim"], sc["Lx"], sc["Ly"], 5,
-            sc["end_points"][0], sc["end_points"][1])
+    nj = draws.shape[1] - 4
+    ep = [list(e) + [0.0] * (7 + nj - len(e)) for e in sc["end_points"]]  # (tree: the bundled end points name 6 of the 9 joints)
+    args = (len(sc["arena"]), len(sc["obstacle"]), rows, 10, np.array(sc["robot"]), urdf, draws, sc["lim"], sc["Lx"], sc["Ly"], 5, ep[0], ep[1])
     ref = oracle.plan_prob3d(*args, per_orientation=per_orientation)
     got = hostlib.plan_prob3d(*args, per_orientation=per_orientation, precision=capi.F64_STRICT, batch=batch)
     return ref, got
@@ -288,3 +289,33 @@ def test_prob_hrm3d_tree_robot_bridges_identical(oracle):
     assert ref["slices"] == got["slices"] == 14 and not ref["solved"] and not got["solved"]
     assert np.array_equal(got["vertex"], ref["vertex"])
     assert np.array_equal(got["edge"], ref["edge"]) and len(ref["edge"]) > 10000
+
+
+@pytest.mark.parametrize("Lx,Ly,draws,period,batch", [(6, 6, 6, 4, 8), (6, 5, 7, 4, 3)])
+def test_prob_hrm3d_periodic_refinement_identical(oracle, Lx, Ly, draws, period, batch):
+    """ProbHRM3D doubles the sweep lines of all slices every 60 slices (ProbHRM3D.cpp:52-56); with the period set to 4 the home
+    map sees two refinements within 8-9 slices (6x6 -> 24x24 lines).  The GPU-backed planner rebuilds all slices in one call per
+    refinement and must reproduce the oracle's roadmap (vertex ids, bridge vertices, connectExistSlice edges) exactly -- once
+    unsolved after 8 slices, once solved at slice 9."""
+    import os
+
+    from hrm_b200 import hostlib
+    from tests.test_oracle_kat import GOLDEN, prob_samples
+
+    sc = util.scenes()["3D_superquadrics_home_snake"]
+    rows = np.array(sc["arena"] + sc["obstacle"])
+    args = (len(sc["arena"]), len(sc["obstacle"]), rows, 10, np.array(sc["robot"]), os.path.join(GOLDEN, "snake.urdf"), prob_samples(draws, 3), sc["lim"],
+            Lx, Ly, 5, sc["end_points"][0], sc["end_points"][1])
+    oracle.set_prob_refine_period(period)
+    hostlib.set_prob_refine_period(period)
+    try:
+        ref = oracle.plan_prob3d(*args, per_orientation=True)
+        got = hostlib.plan_prob3d(*args, per_orientation=True, precision=capi.F64_STRICT, batch=batch)
+    finally:
+        oracle.set_prob_refine_period(60)
+        hostlib.set_prob_refine_period(60)
+    assert got["slices"] == ref["slices"] and got["solved"] == ref["solved"]
+    assert len(ref["vertex"]) > 7000  # (two refinements happened: ~1500 vertices without them)
+    assert np.array_equal(got["vertex"], ref["vertex"])
+    assert np.array_equal(got["edge"], ref["edge"])
+    assert np.array_equal(got["path"], ref["path"])
