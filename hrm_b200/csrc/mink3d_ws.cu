@@ -504,6 +504,9 @@ __global__ void __launch_bounds__(kWsThreads, 2) k_minksweep3d_ws(const WsParams
     uint16_t* seg = cellq + warp * kSegStride;
     constexpr uint32_t kLight = 16;  // cells with more candidates than this get a whole warp
 
+    for (int i = ctid; i < p.L; i += kCT) m0[i] = kNoFace, m1[i] = kNoFace;  // (afterwards phase D leaves every entry reset)
+    if (ctid == 0) *scan_next = 0;
+    bar_sync(kBarCons, kCT);
     long long c_wait = 0, c_sweep = 0, c_cells = 0, c_d = 0, c0 = 0;  // profiling builds: [4] waiting for the producers, [5] scan + cell tests, [6] phase D
     long long w_swar = 0, w_comp = 0, w_bar = 0, w_t = 0;            // per warp: SWAR tests, compaction, waiting for the other consumer warps
     long long w_first = 0, w_nchunk = 0;                             // ... of which the first chunk of every surface; chunks taken
@@ -530,12 +533,15 @@ __global__ void __launch_bounds__(kWsThreads, 2) k_minksweep3d_ws(const WsParams
             return vertical_hit_fast(txs[ix + 1], tys[iy + 1], t0, t1, t2, z);
         };
 
-        for (int i = ctid; i < p.L; i += kCT) m0[i] = kNoFace, m1[i] = kNoFace;
-        if (ctid == 0) *hcount = 0, *zcount = 0, *scan_next = 0;
+        // (no barrier here: m0 / m1 were reset by phase D of the previous surface, scan_next when its scan ended, and the barrier
+        //  that ends the scan orders these two counters before the tests)
+        if (ctid == 0) *hcount = 0, *zcount = 0;
         if (DBG) w_is_first = true;
-        bar_sync(kBarCons, kCT);
         // A hit enters the line's ordered two-slot table keyed by its FACE INDEX (the reference keeps the first two hits in face
         // order, SURVEY finding 2); the low bits of the key say where its height is kept for phase D.
+        // (Measured and rejected, kernel ms at 125 layers against 6.24 for this form: per-thread static pool slots instead of the
+        //  shared counter 6.32; cell batches / scan chunks claimed one item ahead 6.94 / 6.36; ranks from ballots instead of the
+        //  list-segment atomic 6.56 -- the consumer code sits at its register budget, and each of these moved spills into the loops.)
         auto record_hit = [&](uint32_t l, uint32_t face, double z) {
             const int zi = atomicAdd(zcount, 1);
             uint32_t key = (face << kZBits) | kZNone;
@@ -580,7 +586,7 @@ __global__ void __launch_bounds__(kWsThreads, 2) k_minksweep3d_ws(const WsParams
         // rows per lane) back to back; (2) ONE prefix sum over the lanes' kept-cell counts, then every lane writes its own cells.
         // What does not fit into the warp's list segment stays in w[] for the next round (after the tests of this round).
 #ifndef HRMGPU_WS_KWR
-#define HRMGPU_WS_KWR 2
+#define HRMGPU_WS_KWR 3
 #endif
         constexpr int kWR = HRMGPU_WS_KWR;  // words per lane and chunk (x 4 rows each): short on purpose, the unrolled body is ~30 instructions per row
         const int nchunk = (nc1 + kWR * kUPL - 1) / (kWR * kUPL);
@@ -670,6 +676,7 @@ __global__ void __launch_bounds__(kWsThreads, 2) k_minksweep3d_ws(const WsParams
             __syncwarp();
             if (DBG) w_t = clock64();
             const int more = bar_or(kBarCons, kCT, parked ? 1 : 0);
+            if (!more && ctid == 0) *scan_next = 0;  // every warp is done claiming chunks of this surface
             if (DBG) w_bar += clock64() - w_t;
             if (DBG) {
                 const long long c1 = clock64();
@@ -766,33 +773,45 @@ __global__ void __launch_bounds__(kWsThreads, 2) k_minksweep3d_ws(const WsParams
             if ((key & kZNone) != kZNone) return zpool[key & kZNone];  // found in phase C
             return face_height(cc, rowf, txs, tys, n, p.Ly, key >> kZBits, static_cast<uint32_t>(l));  // (pool full: evaluate the face again)
         };
-        auto interval = [&](int l, double& a, double& bb) -> bool {  // true: an obstacle interval that goes into the line's bucket
-            a = is_arena ? p.zlow : __longlong_as_double(0x7FF8000000000000LL);
-            bb = is_arena ? p.zup : __longlong_as_double(0x7FF8000000000000LL);
-            const uint32_t e0 = m0[l], e1 = m1[l];
-            if (e1 != kNoFace) {
-                const double z0 = face_z(e0, l), z1 = face_z(e1, l);
-                const double zl = fmin(z0, z1), zu = fmax(z0, z1);
-                a = is_arena ? fmin(p.zlow, zl) : zl;
-                bb = is_arena ? fmax(p.zup, zu) : zu;
-                return !is_arena && P.bcnt != nullptr && !isnan(zl) && !isnan(zu);
-            }
-            if (e0 != kNoFace) ++single;  // exactly one hit: reference reads out of bounds; defined here as "no interval"
-            return false;
-        };
-        // blocks of kDeferLines lines (one block when L <= 512): bucket appends deferred, see ppos
+        // blocks of kDeferLines lines (one block when L <= 512): bucket appends deferred, see ppos.  Staged, so that the
+        // shared-memory round trips of a thread's lines overlap instead of following one another: (1) the hit-table entries of all
+        // its lines (reset for the next surface at once), (2) the hit heights, (3) intervals, stores and bucket-slot requests.
 #pragma unroll 1
         for (int lb = 0; lb < p.L; lb += kDeferLines) {
             if (lb > 0) flush_pending();  // (more than 512 sweep lines: the slots of the previous block are awaited here)
             pbase = static_cast<size_t>(k_layer) * p.L + lb;
+            uint32_t e0[kDU], e1[kDU];
+#pragma unroll
+            for (int u = 0; u < kDU; ++u) {
+                const int l = lb + ctid + u * kCT;
+                e0[u] = e1[u] = kNoFace;
+                if (l < p.L && ctid + u * kCT < kDeferLines) {
+                    e0[u] = m0[l], e1[u] = m1[l];
+                    m0[l] = kNoFace, m1[l] = kNoFace;
+                }
+            }
+            double z0[kDU], z1[kDU];
+#pragma unroll
+            for (int u = 0; u < kDU; ++u) {
+                z0[u] = z1[u] = 0.0;
+                if (e1[u] != kNoFace) z0[u] = face_z(e0[u], lb + ctid + u * kCT), z1[u] = face_z(e1[u], lb + ctid + u * kCT);
+            }
 #pragma unroll
             for (int u = 0; u < kDU; ++u) {
                 const int l = lb + ctid + u * kCT;
                 if (l < p.L && ctid + u * kCT < kDeferLines) {
-                    double a, bb;
-                    if (interval(l, a, bb)) {
-                        stash[ctid * kDU + u] = make_double2(a, bb);
-                        ppos[u] = bucket_slot(P.bcnt + pbase + ctid + u * kCT);  // not read before flush_pending()
+                    double a = is_arena ? p.zlow : __longlong_as_double(0x7FF8000000000000LL);
+                    double bb = is_arena ? p.zup : __longlong_as_double(0x7FF8000000000000LL);
+                    if (e1[u] != kNoFace) {
+                        const double zl = fmin(z0[u], z1[u]), zu = fmax(z0[u], z1[u]);
+                        a = is_arena ? fmin(p.zlow, zl) : zl;
+                        bb = is_arena ? fmax(p.zup, zu) : zu;
+                        if (!is_arena && P.bcnt != nullptr && !isnan(zl) && !isnan(zu)) {  // an obstacle interval: also into the line's bucket
+                            stash[ctid * kDU + u] = make_double2(a, bb);
+                            ppos[u] = bucket_slot(P.bcnt + pbase + ctid + u * kCT);  // not read before flush_pending()
+                        }
+                    } else if (e0[u] != kNoFace) {
+                        ++single;  // exactly one hit: reference reads out of bounds; defined here as "no interval"
                     }
                     lo[l] = a;
                     up[l] = bb;

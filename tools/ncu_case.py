@@ -17,8 +17,13 @@ ctx.set_scene3d(1, wl.N_OBS, wl.scene_rows17(rows), wl.N_GRID)
 ctx.set_sweep(wl.LIM, wl.LX, wl.LY)
 R = wl.body_rotations(wl.orientations(layers))
 off = np.zeros((layers, 1, 3))
-for rep in range(3):
+reps = int(os.environ.get("HRM_CASE_REPS", "3"))
+ms = []
+for rep in range(reps):
     ctx.build_layers(np.array(wl.BODY_SEMI), R, off, prec)
     ctx.synchronize()
-    print("rep", rep, "fused kernel ms", ctx.last_minksweep_ms(), "segments ms", ctx.last_segments_ms(), "segments", ctx.dims()["segments"])
+    ms.append(ctx.last_minksweep_ms())
+    print("rep", rep, "fused kernel ms", ms[-1], "segments ms", ctx.last_segments_ms(), "segments", ctx.dims()["segments"])
+if reps > 3:
+    print("steady state (reps 2..): min %.3f median %.3f ms" % (min(ms[2:]), float(np.median(ms[2:]))))
 ctx.close()
