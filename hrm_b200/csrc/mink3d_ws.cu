@@ -502,7 +502,10 @@ __global__ void __launch_bounds__(kWsThreads, 2) k_minksweep3d_ws(const WsParams
     constexpr int kSegStride = kWsCellCap / kCW;
     const int kSegCap = p.seg_cap < kSegStride ? p.seg_cap : kSegStride;
     uint16_t* seg = cellq + warp * kSegStride;
-    constexpr uint32_t kLight = 16;  // cells with more candidates than this get a whole warp
+#ifndef HRMGPU_WS_KLIGHT
+#define HRMGPU_WS_KLIGHT 16
+#endif
+    constexpr uint32_t kLight = HRMGPU_WS_KLIGHT;  // cells with more candidates than this get a whole warp
 
     for (int i = ctid; i < p.L; i += kCT) m0[i] = kNoFace, m1[i] = kNoFace;  // (afterwards phase D leaves every entry reset)
     if (ctid == 0) *scan_next = 0;
