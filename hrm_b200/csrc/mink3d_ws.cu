@@ -417,6 +417,7 @@ __global__ void __launch_bounds__(kWsThreads, 2) k_minksweep3d_ws(const WsParams
                             o[0][d] = fm(fm(kk[1], F[0][3 + d], kk[5 + d]), inv0, fm(kk[0], F[0][d], kk[2 + d]));
                             o[1][d] = fm(fm(kk[1], F[1][3 + d], kk[5 + d]), inv1, fm(kk[0], F[1][d], kk[2 + d]));
                         }
+                        // (evict-first stores, __stcs, were measured on this kernel: no difference, burst or sustained)
                         *reinterpret_cast<R2*>(gx) = R2{o[0][0], o[1][0]};
                         *reinterpret_cast<R2*>(gx + M) = R2{o[0][1], o[1][1]};
                         *reinterpret_cast<R2*>(gx + 2 * static_cast<size_t>(M)) = R2{o[0][2], o[1][2]};
