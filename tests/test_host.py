@@ -21,6 +21,26 @@ def test_library_exports_every_declared_symbol():
     assert lib.hrmgpu_abi_version() == 2
 
 
+def test_ctypes_signatures_match_the_header():
+    """Every prototype in include/hrmgpu.h has a ctypes signature in capi.load() with the same number of parameters (a drifted
+    binding would pass garbage through the C ABI without any error)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    txt = open(os.path.join(root, "include", "hrmgpu.h")).read()
+    txt = re.sub(r"/\*.*?\*/", " ", txt, flags=re.S)  # comments out
+    protos = dict(re.findall(r"\b(hrmgpu_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", txt, flags=re.S))
+    lib = capi.load()
+    assert set(protos) == set(capi.declared_symbols())
+    checked = 0
+    for name, args in protos.items():
+        fn = getattr(lib, name)
+        if fn.argtypes is None:
+            continue  # (debug hooks bound ad hoc by the tools)
+        n_params = 0 if args.strip() in ("", "void") else len(args.split(","))
+        assert len(fn.argtypes) == n_params, (name, n_params, len(fn.argtypes))
+        checked += 1
+    assert checked >= 40
+
+
 def test_cpp_host_library_loads_and_exports_planners():
     from hrm_b200 import hostlib
 
