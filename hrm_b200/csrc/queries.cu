@@ -51,6 +51,45 @@ __global__ void k_mesh_bbox(const Real* mesh, int dim, int M, double* bbox, int 
     }
 }
 
+// xy boxes of the bands and of the faces of every mesh (3D, n - 1 <= 32): band (0, i) = the cells of parameter column i (vertices
+// [i*n, (i+2)*n)), band (1, j) = the cells of parameter row j (vertices i*n + j, i*n + j + 1 for every i).  A face's own xy box --
+// the inclusive per-face test of intersectVerticalLineMesh3D (LineIntersection.cpp:77-101) -- lies inside the boxes of both of its
+// bands, so a vertical line outside a band's box cannot pass any face of that band.  Per mesh: [2][n-1][4] band boxes, then
+// [2 (n-1)^2][4] face boxes, each xmin xmax ymin ymax (min / max of the very doubles the face test compares).
+__host__ __device__ inline size_t mesh_boxes_stride(int n) { return 4 * (2 * static_cast<size_t>(n - 1) + 2 * static_cast<size_t>(n - 1) * (n - 1)); }
+template <class Real>
+__global__ void __launch_bounds__(128) k_mesh_bands(const Real* mesh, int n, double* boxes, int n_mesh) {
+    const int m = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int M = n * n;
+    const Real* mx = mesh + static_cast<size_t>(m) * 3 * M;
+    const Real* my = mx + M;
+    double* out = boxes + static_cast<size_t>(m) * mesh_boxes_stride(n);
+    for (int r = warp; r < 2 * (n - 1); r += 4) {  // one warp per band
+        const int kind = r / (n - 1), b = r - kind * (n - 1);
+        double x0 = 1.0 / 0.0, x1 = -x0, y0 = x0, y1 = -x0;
+        for (int t = lane; t < 2 * n; t += 32) {
+            const int q = kind == 0 ? b * n + t : (t >> 1) * n + b + (t & 1);
+            const double x = static_cast<double>(mx[q]), y = static_cast<double>(my[q]);
+            x0 = fmin(x0, x), x1 = fmax(x1, x), y0 = fmin(y0, y), y1 = fmax(y1, y);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            x0 = fmin(x0, __shfl_xor_sync(0xFFFFFFFFu, x0, o)), x1 = fmax(x1, __shfl_xor_sync(0xFFFFFFFFu, x1, o));
+            y0 = fmin(y0, __shfl_xor_sync(0xFFFFFFFFu, y0, o)), y1 = fmax(y1, __shfl_xor_sync(0xFFFFFFFFu, y1, o));
+        }
+        if (lane == 0) out[4 * r] = x0, out[4 * r + 1] = x1, out[4 * r + 2] = y0, out[4 * r + 3] = y1;
+    }
+    double* fo = out + 8 * (n - 1);
+    for (int f = threadIdx.x; f < 2 * (n - 1) * (n - 1); f += blockDim.x) {  // one thread per face
+        int v0, v1, v2;
+        face_vertices(f, n, v0, v1, v2);
+        const double xa = static_cast<double>(mx[v0]), xb = static_cast<double>(mx[v1]), xc = static_cast<double>(mx[v2]);
+        const double ya = static_cast<double>(my[v0]), yb = static_cast<double>(my[v1]), yc = static_cast<double>(my[v2]);
+        fo[4 * f] = fmin(xa, fmin(xb, xc)), fo[4 * f + 1] = fmax(xa, fmax(xb, xc));
+        fo[4 * f + 2] = fmin(ya, fmin(yb, yc)), fo[4 * f + 3] = fmax(ya, fmax(yb, yc));
+    }
+}
+
 // First two hits of line (o, d) on the implicit mesh in face order.  VERTICAL adds the inclusive per-face xy
 // bounding-box test of intersectVerticalLineMesh3D.  Returns the hit count (0..2); all lanes get h0, h1.
 template <class A, class Real, bool VERTICAL>
@@ -280,6 +319,7 @@ __global__ void __launch_bounds__(128) k_bridge2d(const QueryParams p) {
 struct TransParams {
     const void* mesh;        // bridge meshes [P][n_obs][B][dim][M]
     const double* bbox;      // [P][n_obs * B][6] (3D)
+    const double* bands;     // per mesh band + face boxes (3D, n - 1 <= 32) or NULL: k_mesh_bands
     const int* pair;         // [C]
     const double* v0;        // [C][dim]
     const double* v1;        // [C][dim]
@@ -297,6 +337,9 @@ struct TransParams {
 // 3D: a warp takes 32 consecutive items.  Every lane forms its item's body centre and applies the mesh-level xy bounding-box
 // reject of intersectVerticalLineMesh3D (LineIntersection.cpp:60-67), which removes most (centre, obstacle) combinations;
 // the survivors are then walked by the whole warp one after the other (faces in order, first two hits).
+#ifdef HRMGPU_K5_STATS
+__device__ unsigned long long g_k5_stats[8];
+#endif
 template <class A, class Real>
 __global__ void __launch_bounds__(128) k_transitions3d(const TransParams p) {
     const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -304,6 +347,7 @@ __global__ void __launch_bounds__(128) k_transitions3d(const TransParams p) {
     const long long item = warp_global * 32 + lane;
     bool live = false;
     int c = 0, set = 0, m = 0;
+    unsigned mi = 0u, mj = 0u;
     double ox = 0, oy = 0, oz = 0;
     if (item < p.items) {
         const int per_pose = p.B * p.n_obs;
@@ -332,14 +376,142 @@ __global__ void __launch_bounds__(128) k_transitions3d(const TransParams p) {
             m = o * p.B + b;
             const double* bb = p.bbox + (static_cast<size_t>(set) * per_pose + m) * 6;
             live = !(ox > __ldg(bb + 1) || ox < __ldg(bb) || oy > __ldg(bb + 3) || oy < __ldg(bb + 2));
+            if (live && p.bands) {  // which column / row bands of the mesh the vertical line can pass at all
+                const double2* bd = reinterpret_cast<const double2*>(p.bands + (static_cast<size_t>(set) * per_pose + m) * mesh_boxes_stride(p.n));
+                const int nm1 = p.n - 1;
+#pragma unroll 3
+                for (int t = 0; t < nm1; ++t) {
+                    const double2 ux = __ldg(bd + 2 * t), uy = __ldg(bd + 2 * t + 1);
+                    const double2 wx = __ldg(bd + 2 * (nm1 + t)), wy = __ldg(bd + 2 * (nm1 + t) + 1);
+                    const bool in_i = !((ox < ux.x) | (ox > ux.y) | (oy < uy.x) | (oy > uy.y));
+                    const bool in_j = !((ox < wx.x) | (ox > wx.y) | (oy < wy.x) | (oy > wy.y));
+                    mi |= in_i ? 1u << t : 0u;
+                    mj |= in_j ? 1u << t : 0u;
+                }
+                live = mi != 0u && mj != 0u;
+            }
         }
     }
     unsigned todo = __ballot_sync(0xFFFFFFFFu, live);
-    while (todo) {
+#ifdef HRMGPU_K5_STATS
+    {
+        const bool skipped = item < p.items && *reinterpret_cast<volatile unsigned int*>(p.flag + c) != 0u;
+        const int nf = live ? 2 * __popc(mi) * __popc(mj) : 0;
+        atomicAdd(g_k5_stats + 0, 1ULL);
+        atomicAdd(g_k5_stats + 1, live ? 1ULL : 0ULL);
+        atomicAdd(g_k5_stats + 2, static_cast<unsigned long long>(nf));
+        atomicAdd(g_k5_stats + 3, static_cast<unsigned long long>((nf + 31) / 32));
+        atomicAdd(g_k5_stats + 4, skipped ? 1ULL : 0ULL);
+        if (lane == 0) atomicAdd(g_k5_stats + 5, 1ULL);
+        int tot = nf;
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xFFFFFFFFu, tot, o);
+        if (lane == 0) atomicAdd(g_k5_stats + 6, static_cast<unsigned long long>((tot + 31) / 32));
+    }
+#endif
+    const unsigned full = 0xFFFFFFFFu;
+    if (p.bands) {
+        // Two stages, both with the whole warp.  (1) Per surviving item, the faces of its bands take the per-face xy box test (6 loads, no
+        // arithmetic); the (owner lane, face) pairs that pass are appended -- item by item, faces ascending -- to a queue in shared memory.
+        // (2) Whenever 32 pairs wait, every lane runs ONE line/triangle test (the expensive part: ~250 FP64 instructions with 7 divisions /
+        // square roots in strict mode) and the hits go back to their owner lane in queue order, which keeps the first two of every item in
+        // face order.  Testing per item instead leaves 2-3 of 32 lanes busy in the triangle test (measured: 1.43 -> see profiles/ ms).
+        __shared__ unsigned short s_queue[4][64];
+        __shared__ unsigned char s_tab[4][64];
+        unsigned short* queue = s_queue[(threadIdx.x >> 5) & 3];
+        unsigned char* tab = s_tab[(threadIdx.x >> 5) & 3];
+        const unsigned lt = (1u << lane) - 1u;
+        const int nm1 = p.n - 1, nc = nm1 * nm1;
+        int qn = 0, cnt = 0;
+        double hz0 = 0.0, hz1 = 0.0;
+        auto drain = [&](int take) {
+            int owner = lane, f = 0;
+            if (lane < take) {
+                const unsigned e = queue[lane];
+                owner = static_cast<int>(e >> 11), f = static_cast<int>(e & 2047u);
+            }
+            const D3 org = {__shfl_sync(full, ox, owner), __shfl_sync(full, oy, owner), __shfl_sync(full, oz, owner)};
+            const int ss = __shfl_sync(full, set, owner), ms = __shfl_sync(full, m, owner);
+            bool hit = false;
+            D3 pt = {0, 0, 0};
+            if (lane < take) {
+                const Real* mx = reinterpret_cast<const Real*>(p.mesh) + static_cast<size_t>(ss) * p.set_stride + static_cast<size_t>(ms) * 3 * p.M;
+                const Real* my = mx + p.M;
+                const Real* mz = my + p.M;
+                int v0, v1, v2;
+                face_vertices(f, p.n, v0, v1, v2);
+                const D3 t0 = {static_cast<double>(mx[v0]), static_cast<double>(my[v0]), static_cast<double>(mz[v0])};
+                const D3 t1 = {static_cast<double>(mx[v1]), static_cast<double>(my[v1]), static_cast<double>(mz[v1])};
+                const D3 t2 = {static_cast<double>(mx[v2]), static_cast<double>(my[v2]), static_cast<double>(mz[v2])};
+                const D3 dir = {0.0, 0.0, 1.0};
+                hit = line_triangle<A>(org, dir, t0, t1, t2, pt);
+            }
+            unsigned bal = __ballot_sync(full, hit);
+            while (bal) {
+                const int src = __ffs(bal) - 1;
+                bal &= bal - 1;
+                const int ow = __shfl_sync(full, owner, src);
+                const double z = __shfl_sync(full, pt.z, src);
+                if (lane == ow && cnt < 2) {  // (the reference stops at the second hit: LineIntersection.cpp:116-120)
+                    if (cnt == 0) hz0 = z; else hz1 = z;
+                    ++cnt;
+                }
+            }
+            unsigned short rest = 0;
+            if (take + lane < qn) rest = queue[take + lane];
+            __syncwarp();
+            if (take + lane < qn) queue[lane] = rest;
+            __syncwarp();
+            qn -= take;
+        };
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const unsigned mis = __shfl_sync(full, mi, src), mjs = __shfl_sync(full, mj, src);
+            const double x = __shfl_sync(full, ox, src), y = __shfl_sync(full, oy, src);
+            const int ss = __shfl_sync(full, set, src), ms = __shfl_sync(full, m, src);
+            const double2* fb = reinterpret_cast<const double2*>(p.bands + (static_cast<size_t>(ss) * (p.B * p.n_obs) + ms) * mesh_boxes_stride(p.n) + 8 * nm1);
+            // rank -> band tables of this item: lane t owns bit t of either mask
+            if ((mis >> lane) & 1u) tab[__popc(mis & lt)] = static_cast<unsigned char>(lane);
+            if ((mjs >> lane) & 1u) tab[32 + __popc(mjs & lt)] = static_cast<unsigned char>(lane);
+            __syncwarp();
+            const int nbj = __popc(mjs), per_kind = __popc(mis) * nbj, total = 2 * per_kind;
+            const float inv_nbj = 1.0f / static_cast<float>(nbj);
+            for (int base = 0; base < total; base += 32) {
+                const int cd = base + lane;
+                bool pass = false;
+                int f = 0;
+                if (cd < total) {
+                    const int kind = cd >= per_kind ? 1 : 0;
+                    const int r = cd - kind * per_kind;
+                    const int oi = __float2int_rd((static_cast<float>(r) + 0.5f) * inv_nbj);  // r / nbj: r < 1024, nbj <= 32, exact with the half offset
+                    const int oj = r - oi * nbj;
+                    f = kind * nc + tab[oi] * nm1 + tab[32 + oj];
+                    const double2 bx = __ldg(fb + 2 * f), by = __ldg(fb + 2 * f + 1);
+                    pass = !((x < bx.x) | (x > bx.y) | (y < by.x) | (y > by.y));  // LineIntersection.cpp:77-101
+                }
+                const unsigned bal = __ballot_sync(full, pass);
+                if (pass) queue[qn + __popc(bal & lt)] = static_cast<unsigned short>((src << 11) | f);
+                qn += __popc(bal);
+                __syncwarp();
+                if (qn >= 32) drain(32);
+            }
+            __syncwarp();  // (the tables are rewritten for the next item)
+        }
+        if (qn > 0) drain(qn);
+        if (live) {
+            if (cnt == 2) {
+                if (oz > fmin(hz0, hz1) && oz < fmax(hz0, hz1)) p.flag[c] = 1u;  // HRM3D.cpp:409-413
+            } else if (cnt == 1) {
+                atomicAdd(p.counters + 3, 1ULL);  // single hit: the reference reads out of bounds; defined as not blocking
+            }
+        }
+        return;
+    }
+    while (todo) {  // meshes with more than 32 bands per direction: the plain walk
         const int src = __ffs(todo) - 1;
         todo &= todo - 1;
-        const int cs = __shfl_sync(0xFFFFFFFFu, c, src), ss = __shfl_sync(0xFFFFFFFFu, set, src), ms = __shfl_sync(0xFFFFFFFFu, m, src);
-        const D3 org = {__shfl_sync(0xFFFFFFFFu, ox, src), __shfl_sync(0xFFFFFFFFu, oy, src), __shfl_sync(0xFFFFFFFFu, oz, src)};
+        const int cs = __shfl_sync(full, c, src), ss = __shfl_sync(full, set, src), ms = __shfl_sync(full, m, src);
+        const D3 org = {__shfl_sync(full, ox, src), __shfl_sync(full, oy, src), __shfl_sync(full, oz, src)};
         const D3 dir = {0.0, 0.0, 1.0};
         const Real* mesh = reinterpret_cast<const Real*>(p.mesh) + static_cast<size_t>(ss) * p.set_stride + static_cast<size_t>(ms) * 3 * p.M;
         D3 h0, h1;
@@ -521,6 +693,17 @@ int launch_bridge_bbox(Ctx* c) {
         k_mesh_bbox<double><<<total, 128, 0, c->stream>>>(reinterpret_cast<const double*>(c->bridge_mesh.p), 3, c->n * c->n, c->bridge_bbox.p, total, 0);
     HRMGPU_CUDA(c, cudaGetLastError());
     c->launches += 1;
+    c->bridge_bands_ok = false;
+    if (c->n - 1 <= 32 && !c->no_bands) {
+        if ((rc = ensure(c, c->bridge_bands, static_cast<size_t>(total) * mesh_boxes_stride(c->n)))) return rc;
+        if (c->bridge_prec == HRMGPU_F32)
+            k_mesh_bands<float><<<total, 128, 0, c->stream>>>(reinterpret_cast<const float*>(c->bridge_mesh.p), c->n, c->bridge_bands.p, total);
+        else
+            k_mesh_bands<double><<<total, 128, 0, c->stream>>>(reinterpret_cast<const double*>(c->bridge_mesh.p), c->n, c->bridge_bands.p, total);
+        HRMGPU_CUDA(c, cudaGetLastError());
+        c->launches += 1;
+        c->bridge_bands_ok = true;
+    }
     return HRMGPU_OK;
 }
 
@@ -535,6 +718,7 @@ int launch_transitions(Ctx* c, int C, int T, const int* d_pair, const double* d_
         p.flag = c->q_flag.p;
         p.counters = c->counters.p;
         p.bbox = c->bridge_bbox.p;
+        p.bands = (c->dim == 3 && c->bridge_bands_ok) ? c->bridge_bands.p : nullptr;
         p.n = c->n;
         p.M = (c->dim == 3) ? c->n * c->n : c->n;
         p.C = C, p.T = T, p.B = c->bridge_B, p.n_obs = c->n_obs;
@@ -559,6 +743,16 @@ int launch_transitions(Ctx* c, int C, int T, const int* d_pair, const double* d_
         }
         HRMGPU_CUDA(c, cudaGetLastError());
         c->launches += 1;
+#ifdef HRMGPU_K5_STATS
+        if (c->dim == 3) {
+            unsigned long long h[8], z[8] = {0};
+            cudaStreamSynchronize(c->stream);
+            cudaMemcpyFromSymbol(h, g_k5_stats, sizeof(h));
+            cudaMemcpyToSymbol(g_k5_stats, z, sizeof(z));
+            fprintf(stderr, "[k5 stats] C=%d T=%d items=%llu live=%llu faces=%llu iters(per item)=%llu flagged-skips=%llu warps=%llu iters(flattened)=%llu\n", C, T, h[0], h[1],
+                    h[2], h[3], h[4], h[5], h[6]);
+        }
+#endif
     }
     return finish_flags(c, C, d_out);
 }
@@ -571,6 +765,7 @@ static void touch_kernel(K k) {
 }
 void preload_queries() {
     touch_kernel(k_flags_to_free), touch_kernel(k_mesh_bbox<float>), touch_kernel(k_mesh_bbox<double>);
+    touch_kernel(k_mesh_bands<float>), touch_kernel(k_mesh_bands<double>);
     touch_kernel(k_edges3d<Strict, double>), touch_kernel(k_edges3d<Fast, double>), touch_kernel(k_edges3d<Fast, float>);
     touch_kernel(k_edges2d<Strict>), touch_kernel(k_edges2d<Fast>);
     touch_kernel(k_bridge3d<Strict, double>), touch_kernel(k_bridge3d<Fast, double>), touch_kernel(k_bridge3d<Fast, float>);
