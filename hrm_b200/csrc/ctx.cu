@@ -187,6 +187,7 @@ int hrmgpu_create(hrmgpu_ctx** out, int device, unsigned flags) {
     if (const char* e = std::getenv("HRMGPU_WS_VARIANT")) c->ws_variant = std::atoi(e);
     if (const char* e = std::getenv("HRMGPU_WS_GENERIC")) c->ws_generic = std::atoi(e) != 0;
     if (const char* e = std::getenv("HRMGPU_NO_BANDS")) c->no_bands = std::atoi(e) != 0;
+    if (const char* e = std::getenv("HRMGPU_NO_FACE_NORMALS")) c->no_face_normals = std::atoi(e) != 0;
     // test hook of the fused kernel: capacity of a warp's kept-cell list (small values force the multi-round path)
     if (const char* e = std::getenv("HRMGPU_CELL_SEG_CAP")) c->cell_seg_cap = std::atoi(e);
     if (ensure(c, c->counters, 4) != HRMGPU_OK) {
@@ -273,6 +274,7 @@ void hrmgpu_destroy(hrmgpu_ctx* c) {
     release(c, c->tfe_in), release(c, c->tfe_quat), release(c, c->pc_code);
     release(c, c->bridge_bbox);
     release(c, c->bridge_bands);
+    release(c, c->face_n);
     release(c, c->bridge_semi);
     release(c, c->bridge_R);
     release(c, c->bridge_off);

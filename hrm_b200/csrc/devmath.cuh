@@ -101,6 +101,53 @@ __device__ __forceinline__ bool line_triangle(const D3& o, const D3& d, const D3
     return !((t < -tol) || (A::add(s, t) > 1.0 + tol));
 }
 
+// The test above split at the point where the line comes in.  face_unit_normal() is everything that depends on the triangle
+// alone and is expensive (cross product, normalisation: one square root, three divisions, and the norm check with its second
+// square root); line_triangle_n() continues from there with the very same operations, so for n = face_unit_normal(t0, t1, t2)
+// it returns what line_triangle() returns, bit for bit.  A face the reference leaves at `nn > tol` gets n = 0: then b = 0 and
+// the test bails out at `fabs(b) > tol` instead, with the same answer.  K4 tabulates n once per face and layer (k_face_normals).
+template <class A>
+__device__ __forceinline__ D3 face_unit_normal(const D3& t0, const D3& t1, const D3& t2) {
+    const D3 u = sub3<A>(t1, t0);
+    const D3 v = sub3<A>(t2, t0);
+    D3 n = {A::sub(A::mul(u.y, v.z), A::mul(u.z, v.y)), A::sub(A::mul(u.z, v.x), A::mul(u.x, v.z)),
+            A::sub(A::mul(u.x, v.y), A::mul(u.y, v.x))};
+    const double z = dot3<A>(n, n);
+    if (z > 0.0) {
+        const double s = A::sqrt(z);
+        n.x = A::div(n.x, s);
+        n.y = A::div(n.y, s);
+        n.z = A::div(n.z, s);
+    }
+    const double nn = A::sqrt(dot3<A>(n, n));
+    if (!(nn > 1e-12)) n = {0.0, 0.0, 0.0};
+    return n;
+}
+template <class A>
+__device__ __forceinline__ bool line_triangle_n(const D3& o, const D3& d, const D3& t0, const D3& t1, const D3& t2, const D3& n, D3& pt) {
+    const double tol = 1e-12;
+    const D3 u = sub3<A>(t1, t0);
+    const D3 v = sub3<A>(t2, t0);
+    const double a = -dot3<A>(n, sub3<A>(o, t0));
+    const double b = dot3<A>(n, d);
+    if (!(fabs(b) > tol)) return false;
+    const double pos = A::div(a, b);
+    pt.x = A::add(o.x, A::mul(pos, d.x));
+    pt.y = A::add(o.y, A::mul(pos, d.y));
+    pt.z = A::add(o.z, A::mul(pos, d.z));
+    const double uu = dot3<A>(u, u);
+    const double uv = dot3<A>(u, v);
+    const double vv = dot3<A>(v, v);
+    const D3 w = sub3<A>(pt, t0);
+    const double wu = dot3<A>(u, w);
+    const double wv = dot3<A>(v, w);
+    const double D = A::sub(A::mul(uv, uv), A::mul(uu, vv));
+    const double s = A::div(A::sub(A::mul(uv, wv), A::mul(vv, wu)), D);
+    if ((s < -tol) || (s > 1.0 + tol)) return false;
+    const double t = A::div(A::sub(A::mul(uv, wu), A::mul(uu, wv)), D);
+    return !((t < -tol) || (A::add(s, t) > 1.0 + tol));
+}
+
 // Fast-mode variant of the test above for a VERTICAL line through (x, y): for a non-degenerate triangle the 3D
 // barycentric coordinates of the plane intersection equal those of (x, y) in the projected triangle, so one division
 // (by the projected area n_z) replaces the normalisation, the plane solve and the two barycentric divisions.  Same

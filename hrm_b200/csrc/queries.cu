@@ -91,9 +91,10 @@ __global__ void __launch_bounds__(128) k_mesh_bands(const Real* mesh, int n, dou
 }
 
 // First two hits of line (o, d) on the implicit mesh in face order.  VERTICAL adds the inclusive per-face xy
-// bounding-box test of intersectVerticalLineMesh3D.  Returns the hit count (0..2); all lanes get h0, h1.
-template <class A, class Real, bool VERTICAL>
-__device__ __forceinline__ int warp_first_two_hits(const Real* mesh, int n, int M, const D3& o, const D3& d, D3& h0, D3& h1) {
+// bounding-box test of intersectVerticalLineMesh3D.  Returns the hit count (0..2); all lanes get h0, h1.  fn = the mesh's
+// tabulated face normals [F][3] or NULL.
+template <class A, class Real, bool VERTICAL, bool HASN = false>
+__device__ __forceinline__ int warp_first_two_hits(const Real* mesh, int n, int M, const D3& o, const D3& d, D3& h0, D3& h1, const double* fn = nullptr) {
     const int lane = threadIdx.x & 31;
     const int F = 2 * (n - 1) * (n - 1);
     const Real* mx = mesh;
@@ -115,7 +116,14 @@ __device__ __forceinline__ int warp_first_two_hits(const Real* mesh, int n, int 
                 skip = (o.x < fmin(t0.x, fmin(t1.x, t2.x))) || (o.x > fmax(t0.x, fmax(t1.x, t2.x))) ||
                        (o.y < fmin(t0.y, fmin(t1.y, t2.y))) || (o.y > fmax(t0.y, fmax(t1.y, t2.y)));
             }
-            if (!skip) hit = line_triangle<A>(o, d, t0, t1, t2, pt);
+            if (!skip) {
+                if (HASN) {  // tabulated unit normal of the face (k_face_normals)
+                    const D3 nrm = {__ldg(fn + 3 * f), __ldg(fn + 3 * f + 1), __ldg(fn + 3 * f + 2)};
+                    hit = line_triangle_n<A>(o, d, t0, t1, t2, nrm, pt);
+                } else {
+                    hit = line_triangle<A>(o, d, t0, t1, t2, pt);
+                }
+            }
         }
         unsigned bal = __ballot_sync(0xFFFFFFFFu, hit);
         while (bal && cnt < 2) {
@@ -130,9 +138,31 @@ __device__ __forceinline__ int warp_first_two_hits(const Real* mesh, int n, int 
     return cnt;
 }
 
+// Unit normals of every face of `count` meshes (see face_unit_normal): [mesh][F][3].  Block b covers mesh (b % per_set) of set
+// (b / per_set), like k_mesh_bbox.
+template <class A, class Real>
+__global__ void __launch_bounds__(128) k_face_normals(const Real* mesh, int n, int M, double* out, int per_set, size_t set_stride) {
+    const int set = blockIdx.x / per_set;
+    const Real* mx = mesh + static_cast<size_t>(set) * set_stride + static_cast<size_t>(blockIdx.x - set * per_set) * 3 * M;
+    const Real* my = mx + M;
+    const Real* mz = my + M;
+    const int F = 2 * (n - 1) * (n - 1);
+    double* o = out + static_cast<size_t>(blockIdx.x) * F * 3;
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+        int v0, v1, v2;
+        face_vertices(f, n, v0, v1, v2);
+        const D3 t0 = {static_cast<double>(mx[v0]), static_cast<double>(my[v0]), static_cast<double>(mz[v0])};
+        const D3 t1 = {static_cast<double>(mx[v1]), static_cast<double>(my[v1]), static_cast<double>(mz[v1])};
+        const D3 t2 = {static_cast<double>(mx[v2]), static_cast<double>(my[v2]), static_cast<double>(mz[v2])};
+        const D3 nrm = face_unit_normal<A>(t0, t1, t2);
+        o[3 * f] = nrm.x, o[3 * f + 1] = nrm.y, o[3 * f + 2] = nrm.z;
+    }
+}
+
 struct QueryParams {
     const void* mesh;      // first mesh of the queried set, planar [dim][M] each
     const double* bbox;    // [n_mesh][6]
+    const double* face_n;  // K4 3D: [set][n_mesh][F][3] unit face normals (k_face_normals) or NULL
     const double* a;       // edges: v1 [E][dim]; bridge: centres [Q][B][dim]
     const double* b;       // edges: v2 [E][dim]
     unsigned int* flag;    // [n_query] set to 1 when blocked
@@ -147,7 +177,7 @@ struct QueryParams {
 // applies the reference's mesh-level reject (LineIntersection.cpp:12-30: bounding box, only along (nearly) axis-parallel
 // directions -- which is the common case, the candidate segments of connectOneSlice run between neighbouring sweep lines);
 // the surviving items are then walked by the whole warp one after the other (faces in order, first two hits).
-template <class A, class Real>
+template <class A, class Real, bool HASN>
 // (6 blocks per SM: 80 registers instead of 107; measured 7-13 % faster on the bundled maps, the same bound slows k_transitions3d down)
 __global__ void __launch_bounds__(128, 6) k_edges3d(const QueryParams p) {
     const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -186,7 +216,8 @@ __global__ void __launch_bounds__(128, 6) k_edges3d(const QueryParams p) {
         const D3 dd = {__shfl_sync(0xFFFFFFFFu, d.x, src), __shfl_sync(0xFFFFFFFFu, d.y, src), __shfl_sync(0xFFFFFFFFu, d.z, src)};
         const Real* mesh = reinterpret_cast<const Real*>(p.mesh) + static_cast<size_t>(ss) * p.set_stride + static_cast<size_t>(ms) * 3 * p.M;
         D3 h0, h1;
-        const int cnt = warp_first_two_hits<A, Real, false>(mesh, p.n, p.M, a1, dd, h0, h1);
+        const double* fn = HASN ? p.face_n + (static_cast<size_t>(ss) * p.n_mesh + ms) * (6 * static_cast<size_t>(p.n - 1) * (p.n - 1)) : nullptr;
+        const int cnt = warp_first_two_hits<A, Real, false, HASN>(mesh, p.n, p.M, a1, dd, h0, h1, fn);
         if (lane == 0) {
             if (cnt == 2) {
                 const double s0 = dot3<A>(sub3<A>(h0, a1), sub3<A>(h0, a2));  // HRM3D.cpp:344-351
@@ -586,7 +617,7 @@ int launch_edges(Ctx* c, int k, int E, const double* d_v1, const double* d_v2, u
     if ((rc = ensure(c, c->q_flag, static_cast<size_t>(E)))) return rc;
     HRMGPU_CUDA(c, cudaMemsetAsync(c->q_flag.p, 0, sizeof(unsigned int) * E, c->stream));
     if (So > 0) {
-        QueryParams p;
+        QueryParams p{};
         p.a = d_v1;
         p.b = d_v2;
         p.flag = c->q_flag.p;
@@ -612,13 +643,27 @@ int launch_edges(Ctx* c, int k, int E, const double* d_v1, const double* d_v2, u
             else
                 k_mesh_bbox<double><<<nset * So, 128, 0, c->stream>>>(reinterpret_cast<const double*>(mesh), 3, c->M, c->bbox.p, So, p.set_stride);
             HRMGPU_CUDA(c, cudaGetLastError());
+            p.face_n = nullptr;
+            const size_t fn_count = static_cast<size_t>(nset) * So * 6 * (c->n - 1) * (c->n - 1);
+            if (fn_count * sizeof(double) <= (size_t(256) << 20) && !c->no_face_normals) {  // (beyond that the table would not stay in L2 anyway)
+                if ((rc = ensure(c, c->face_n, fn_count))) return rc;
+                if (c->prec == HRMGPU_F64_STRICT)
+                    k_face_normals<Strict, double><<<nset * So, 128, 0, c->stream>>>(reinterpret_cast<const double*>(mesh), c->n, c->M, c->face_n.p, So, p.set_stride);
+                else if (c->prec == HRMGPU_F64)
+                    k_face_normals<Fast, double><<<nset * So, 128, 0, c->stream>>>(reinterpret_cast<const double*>(mesh), c->n, c->M, c->face_n.p, So, p.set_stride);
+                else
+                    k_face_normals<Fast, float><<<nset * So, 128, 0, c->stream>>>(reinterpret_cast<const float*>(mesh), c->n, c->M, c->face_n.p, So, p.set_stride);
+                HRMGPU_CUDA(c, cudaGetLastError());
+                c->launches += 1;
+                p.face_n = c->face_n.p;
+            }
             const unsigned grid = static_cast<unsigned>((work + 127) / 128);  // 32 items per warp, 4 warps per block
             if (c->prec == HRMGPU_F64_STRICT)
-                k_edges3d<Strict, double><<<grid, 128, 0, c->stream>>>(p);
+                p.face_n ? k_edges3d<Strict, double, true><<<grid, 128, 0, c->stream>>>(p) : k_edges3d<Strict, double, false><<<grid, 128, 0, c->stream>>>(p);
             else if (c->prec == HRMGPU_F64)
-                k_edges3d<Fast, double><<<grid, 128, 0, c->stream>>>(p);
+                p.face_n ? k_edges3d<Fast, double, true><<<grid, 128, 0, c->stream>>>(p) : k_edges3d<Fast, double, false><<<grid, 128, 0, c->stream>>>(p);
             else
-                k_edges3d<Fast, float><<<grid, 128, 0, c->stream>>>(p);
+                p.face_n ? k_edges3d<Fast, float, true><<<grid, 128, 0, c->stream>>>(p) : k_edges3d<Fast, float, false><<<grid, 128, 0, c->stream>>>(p);
             c->launches += 2;
         } else {
             p.bbox = nullptr;
@@ -642,7 +687,7 @@ int launch_bridge_test(Ctx* c, int pidx, int Q, const double* d_centres, unsigne
     if ((rc = ensure(c, c->q_flag, static_cast<size_t>(Q)))) return rc;
     HRMGPU_CUDA(c, cudaMemsetAsync(c->q_flag.p, 0, sizeof(unsigned int) * Q, c->stream));
     if (c->n_obs > 0) {
-        QueryParams p;
+        QueryParams p{};
         p.a = d_centres;
         p.b = nullptr;
         p.bbox = nullptr;
@@ -766,7 +811,9 @@ static void touch_kernel(K k) {
 void preload_queries() {
     touch_kernel(k_flags_to_free), touch_kernel(k_mesh_bbox<float>), touch_kernel(k_mesh_bbox<double>);
     touch_kernel(k_mesh_bands<float>), touch_kernel(k_mesh_bands<double>);
-    touch_kernel(k_edges3d<Strict, double>), touch_kernel(k_edges3d<Fast, double>), touch_kernel(k_edges3d<Fast, float>);
+    touch_kernel(k_face_normals<Strict, double>), touch_kernel(k_face_normals<Fast, double>), touch_kernel(k_face_normals<Fast, float>);
+    touch_kernel(k_edges3d<Strict, double, true>), touch_kernel(k_edges3d<Fast, double, true>), touch_kernel(k_edges3d<Fast, float, true>);
+    touch_kernel(k_edges3d<Strict, double, false>), touch_kernel(k_edges3d<Fast, double, false>), touch_kernel(k_edges3d<Fast, float, false>);
     touch_kernel(k_edges2d<Strict>), touch_kernel(k_edges2d<Fast>);
     touch_kernel(k_bridge3d<Strict, double>), touch_kernel(k_bridge3d<Fast, double>), touch_kernel(k_bridge3d<Fast, float>);
     touch_kernel(k_bridge2d<Strict>), touch_kernel(k_bridge2d<Fast>);

@@ -398,3 +398,53 @@ def test_connect_slices3d_equals_host_enumeration(gpu_ctx):
     with pytest.raises(capi.HrmGpuError) as e:  # answer buffer too small
         gpu_ctx.connect_slices3d(first[-1] - 1)
     assert e.value.code == capi.E_CAP
+
+
+@pytest.mark.parametrize("precision", [capi.F64_STRICT, capi.F64, capi.F32])
+def test_tabulated_boxes_and_normals_change_no_answer(monkeypatch, precision):
+    """The planner-side kernels with their per-mesh tables -- band / face xy boxes and the queued line-triangle tests of
+    k_transitions3d, unit face normals of k_edges3d -- against the same kernels without them (HRMGPU_NO_BANDS /
+    HRMGPU_NO_FACE_NORMALS: every face walked, every normal recomputed), on crowded inputs: 20 000 candidate pairs and 30 000
+    segments concentrated around the obstacles, so that warps hold many surviving items and the queue drains mid-item."""
+    sc = util.scenes()["3D_superquadrics_cluttered_rabbit"]
+    rows = sc["arena"] + sc["obstacle"]
+    n_arena, n_obs = len(sc["arena"]), len(sc["obstacle"])
+    n = 10
+    K = 4
+    semi, R, off, quat = util.body_poses3d(sc["robot"], sc["quats"][:K])
+    B = semi.shape[0]
+    rng = np.random.default_rng(11)
+    obs = np.array(sc["obstacle"])
+    centre = obs[rng.integers(0, n_obs, 30000), 5:8]  # (rows: semi-axes 0-2, eps 3-4, position 5-7, quaternion 8-11)
+    a = centre + rng.normal(scale=6.0, size=centre.shape)
+    b = a + rng.normal(scale=5.0, size=centre.shape)
+    axis = rng.integers(0, 4, len(a))  # a share of exactly axis-parallel segments, like the detours of bridgeVertex
+    for d in range(3):
+        keep = (axis != 3) & (axis != d)
+        b[keep, d] = a[keep, d]
+    layer = rng.integers(0, K, len(a))
+    P, T, C = 3, 6, 20000
+    tfe_semi = rng.uniform(3.0, 9.0, size=(P, B, 3))
+    tfe_R = np.array([[hm.flat9(hm.quat_to_rot((q / np.linalg.norm(q)).tolist())) for q in rng.normal(size=(B, 4))] for _ in range(P)])
+    w1 = np.arange(T) * (1.0 / 5.0)
+    w0 = 1.0 - w1
+    link_off = rng.uniform(-6, 6, size=(P, T, B, 3))
+    pair = rng.integers(0, P, C)
+    v0 = obs[rng.integers(0, n_obs, C), 5:8] + rng.normal(scale=9.0, size=(C, 3))
+    v1 = v0 + rng.normal(scale=3.0, size=(C, 3))
+    out = {}
+    for plain in ("0", "1"):
+        monkeypatch.setenv("HRMGPU_NO_BANDS", plain)
+        monkeypatch.setenv("HRMGPU_NO_FACE_NORMALS", plain)
+        ctx = capi.Context(0)
+        try:
+            ctx.set_scene3d(n_arena, n_obs, util.sq17(rows, n), n)
+            ctx.set_sweep(sc["lim"], sc["Lx"], sc["Ly"])
+            ctx.build_layers(semi, R, off, precision)
+            ctx.build_bridge(tfe_semi, tfe_R, precision)
+            out[plain] = (ctx.test_edges_multi(layer, a, b), ctx.test_transitions(pair, v0, v1, w0, w1, link_off))
+        finally:
+            ctx.close()
+    for got, want in zip(out["0"], out["1"]):
+        assert np.array_equal(got, want)
+        assert 0.05 < want.mean() < 0.95
