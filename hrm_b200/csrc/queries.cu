@@ -371,8 +371,9 @@ struct TransParams {
 #ifdef HRMGPU_K5_STATS
 __device__ unsigned long long g_k5_stats[8];
 #endif
+// (6 blocks per SM: 80 registers; measured on the maze scene 1.74 ms against 1.97 ms unbounded (106), 1.76 ms at 7 and 1.88 ms at 8 blocks, which spill)
 template <class A, class Real>
-__global__ void __launch_bounds__(128) k_transitions3d(const TransParams p) {
+__global__ void __launch_bounds__(128, 6) k_transitions3d(const TransParams p) {
     const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const long long item = warp_global * 32 + lane;

@@ -11,6 +11,8 @@ timeout 600 python bench.py --precision f32 --no-cpu-baseline --no-freespace > g
 timeout 600 python bench.py --precision f64_strict --no-cpu-baseline --no-freespace --no-parity > gpurun_out/${TAG}_bench_f64_strict.json 2>/dev/null; cut -c1-200 gpurun_out/${TAG}_bench_f64_strict.json
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2>/dev/null; cut -c1-300 gpurun_out/${TAG}_bench_reference.json
 (echo "## cluttered/rabbit, 11x5 lines"; HRM_HOST_TIMING=1 python tools/plan_timing.py 3D_superquadrics_cluttered_rabbit 0 10 2>&1; echo "## maze/rabbit, 44x20 lines"; HRM_HOST_TIMING=1 python tools/plan_timing.py 3D_superquadrics_maze_rabbit 0 10 44 20 2>&1) > gpurun_out/${TAG}_plan_stages.txt; tail -3 gpurun_out/${TAG}_plan_stages.txt
+bash tools/plan_launches.sh ${TAG} > gpurun_out/${TAG}_plan_kernels.txt 2>&1; cat gpurun_out/${TAG}_plan_kernels.txt
+HRM_HOST_TIMING=1 python tools/prob_timing.py 3 > gpurun_out/${TAG}_prob_stages.txt 2>&1; tail -2 gpurun_out/${TAG}_prob_stages.txt
 python tools/k1_only.py f64 125 > gpurun_out/${TAG}_k1_only.txt 2>&1; cat gpurun_out/${TAG}_k1_only.txt
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --layers 16 --no-cpu-baseline --no-parity --no-freespace > gpurun_out/${TAG}_ncu1.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_minksweep3d -s 2 -c 1 -o gpurun_out/${TAG}_minksweep3d_ws_f64 -f python tools/prof_layers.py f64 16 3 > gpurun_out/${TAG}_ncu2.log 2>&1; tail -2 gpurun_out/${TAG}_ncu2.log
