@@ -50,26 +50,49 @@ __global__ void __launch_bounds__(128) k_pair_candidates(const PairParams p) {
 }
 
 // One warp per pair: m0 in order; the lanes look at 32 candidates of m0 at a time (they are ascending in m1), the first one at or
-// above the moving lower bound whose transition is free is the match (HRM3D.cpp:186-222).
+// above the moving lower bound whose transition is free is the match (HRM3D.cpp:186-222).  The loop is serial in m0 (n22 moves), so
+// it runs at load latency: the candidate ranges of 32 vertices are fetched at once, and the first 32 candidates of vertex m0 + 1
+// are in flight while vertex m0 is decided (they do not depend on n22).
 __global__ void __launch_bounds__(32) k_pair_replay(const long long* m0_first, const long long* cand_first, const int* c_m1, const unsigned char* free_flag,
                                                     int* match) {
     const int pr = blockIdx.x, lane = threadIdx.x;
+    const unsigned full = 0xFFFFFFFFu;
     int n22 = 0;  // (vertex ids are non-negative: the first candidate of the pair is at or above it, like n22 = the layer's first id)
-    for (long long g = m0_first[pr]; g < m0_first[pr + 1]; ++g) {
-        int found = -1;
-        for (long long j0 = cand_first[g]; j0 < cand_first[g + 1] && found < 0; j0 += 32) {
-            const long long j = j0 + lane;
-            int m1 = -1;
-            bool ok = false;
-            if (j < cand_first[g + 1]) {
-                m1 = c_m1[j];
-                ok = m1 >= n22 && free_flag[j] != 0;
+    const long long g_begin = m0_first[pr], g_end = m0_first[pr + 1];
+    for (long long g0 = g_begin; g0 < g_end; g0 += 32) {
+        const int nv = static_cast<int>((g_end - g0 < 32) ? g_end - g0 : 32);
+        const long long cf = (lane <= nv - 1) ? cand_first[g0 + lane] : 0;
+        const long long cf_last = cand_first[g0 + nv];
+        // first chunk of vertex 0 of this block
+        long long b0 = __shfl_sync(full, cf, 0), e0 = (nv > 1) ? __shfl_sync(full, cf, 1) : cf_last;
+        int m1 = -1;
+        unsigned char fl = 0;
+        if (b0 + lane < e0) m1 = c_m1[b0 + lane], fl = free_flag[b0 + lane];
+        for (int t = 0; t < nv; ++t) {
+            // next vertex's first chunk, issued before this vertex is decided
+            long long b1 = 0, e1 = 0;
+            int m1n = -1;
+            unsigned char fln = 0;
+            if (t + 1 < nv) {
+                b1 = __shfl_sync(full, cf, t + 1);
+                e1 = (t + 2 < nv) ? __shfl_sync(full, cf, t + 2) : cf_last;
+                if (b1 + lane < e1) m1n = c_m1[b1 + lane], fln = free_flag[b1 + lane];
             }
-            const unsigned b = __ballot_sync(0xFFFFFFFFu, ok);
-            if (b) found = __shfl_sync(0xFFFFFFFFu, m1, __ffs(b) - 1);
+            int found = -1;
+            for (long long j0 = b0; j0 < e0 && found < 0; j0 += 32) {
+                if (j0 != b0) {  // (more than 32 candidates and no match so far)
+                    const long long j = j0 + lane;
+                    m1 = -1, fl = 0;
+                    if (j < e0) m1 = c_m1[j], fl = free_flag[j];
+                }
+                const bool ok = m1 >= 0 && m1 >= n22 && fl != 0;
+                const unsigned bal = __ballot_sync(full, ok);
+                if (bal) found = __shfl_sync(full, m1, __ffs(bal) - 1);
+            }
+            if (lane == 0) match[g0 + t] = found;
+            if (found >= 0) n22 = found;
+            b0 = b1, e0 = e1, m1 = m1n, fl = fln;
         }
-        if (lane == 0) match[g] = found;
-        if (found >= 0) n22 = found;
     }
 }
 

@@ -275,6 +275,7 @@ void hrmgpu_destroy(hrmgpu_ctx* c) {
     release(c, c->bridge_bbox);
     release(c, c->bridge_bands);
     release(c, c->face_n);
+    release(c, c->scan_state_main), release(c, c->scan_state_side);
     release(c, c->bridge_semi);
     release(c, c->bridge_R);
     release(c, c->bridge_off);

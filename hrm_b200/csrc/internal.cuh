@@ -133,6 +133,7 @@ struct Ctx {
     DevBuf<double> bridge_semi, bridge_R, bridge_off;
     DevBuf<double> bridge_bbox;                  // [P][n_obs * B][6] (3D)
     DevBuf<double> bridge_bands;                 // per bridge mesh: band boxes [2][n-1][4] + face boxes [2(n-1)^2][4] (3D, n - 1 <= 32): k_mesh_bands
+    DevBuf<unsigned long long> scan_state_main, scan_state_side;  // k_scan_counts: ticket + per-tile inclusive totals, per stream
     DevBuf<double> face_n;                       // K4 3D: unit face normals of the queried layers' meshes (k_face_normals)
     bool no_face_normals = false;                // env HRMGPU_NO_FACE_NORMALS=1 (A/B switch)
     bool bridge_bands_ok = false, no_bands = false;  // no_bands: env HRMGPU_NO_BANDS=1 (A/B switch of the banded face walk)

@@ -520,48 +520,77 @@ __global__ void __launch_bounds__(kSegWarps * 32) k_enhance(const SegParams p) {
     }
 }
 
-// Exclusive scan of K*L counts into 64-bit CSR offsets; single CTA (K*L is at most a few 10^5..10^6).
-__global__ void __launch_bounds__(1024) k_scan_counts(const int* cnt, long long* off, long long n, unsigned long long* info) {
+// Exclusive scan of n counts into 64-bit CSR offsets, off[n] = info[1] = the total.  Chained tiles: a CTA takes the next tile of
+// 8192 counts from a ticket counter (so the CTA holding the previous tile is already running), scans it locally while the previous
+// tiles are still in flight, then thread 0 waits for the previous tile's inclusive total (state[1 + tile], stored +1 so that the
+// zeroed state means "not there yet") and publishes its own.  A single CTA took 60-100 us for the 10^5 lines / line pairs of the
+// dense maze scene, a visible share of plan().
+constexpr int kScanItems = 8;
+constexpr int kScanTile = 1024 * kScanItems;
+__global__ void __launch_bounds__(1024) k_scan_counts(const int* cnt, long long* off, long long n, unsigned long long* info, unsigned long long* state) {
     __shared__ long long wsum[32];
-    __shared__ long long carry_s;
+    __shared__ long long prev_s;
+    __shared__ unsigned long long tile_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) carry_s = 0;
+    if (tid == 0) tile_s = atomicAdd(state, 1ULL);
     __syncthreads();
-    for (long long base = 0; base < n; base += 1024) {
-        const long long i = base + tid;
-        long long v = (i < n) ? cnt[i] : 0;
-        long long inc = v;
+    const long long tile = static_cast<long long>(tile_s);
+    const long long i0 = tile * kScanTile + static_cast<long long>(tid) * kScanItems;
+    int v[kScanItems];
+    long long sum = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        v[k] = (i0 + k < n) ? cnt[i0 + k] : 0;
+        sum += v[k];
+    }
+    long long inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        long long w = wsum[lane];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const long long t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-            if (lane >= o) inc += t;
+            const long long t = __shfl_up_sync(0xFFFFFFFFu, w, o);
+            if (lane >= o) w += t;
         }
-        if (lane == 31) wsum[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-            long long w = wsum[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const long long t = __shfl_up_sync(0xFFFFFFFFu, w, o);
-                if (lane >= o) w += t;
+        wsum[lane] = w;
+        if (lane == 31) {  // w = the tile's total
+            unsigned long long prev = 1ULL;
+            if (tile > 0) {
+                volatile unsigned long long* ps = state + tile;  // = state[1 + (tile - 1)]
+                while ((prev = *ps) == 0ULL) {
+                }
             }
-            wsum[lane] = w;
+            const long long before = static_cast<long long>(prev - 1ULL);
+            atomicExch(state + 1 + tile, static_cast<unsigned long long>(before + w) + 1ULL);
+            prev_s = before;
+            if ((tile + 1) * kScanTile >= n) {  // the last tile
+                off[n] = before + w;
+                info[1] = static_cast<unsigned long long>(before + w);
+            }
         }
-        __syncthreads();
-        const long long prefix = carry_s + (warp > 0 ? wsum[warp - 1] : 0) + inc - v;
-        if (i < n) off[i] = prefix;
-        __syncthreads();
-        if (tid == 1023) carry_s = prefix + v;
-        __syncthreads();
     }
-    if (tid == 0) {
-        off[n] = carry_s;
-        info[1] = static_cast<unsigned long long>(carry_s);
+    __syncthreads();
+    long long run = prev_s + (warp > 0 ? wsum[warp - 1] : 0) + inc - sum;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        if (i0 + k < n) off[i0 + k] = run;
+        run += v[k];
     }
 }
 
 int launch_scan_counts(Ctx* c, const int* cnt, long long* off, long long n, unsigned long long* info, cudaStream_t st) {
-    k_scan_counts<<<1, 1024, 0, st>>>(cnt, off, n, info);
+    const long long tiles = n > 0 ? (n + kScanTile - 1) / kScanTile : 1;
+    DevBuf<unsigned long long>& state = (st == c->s2) ? c->scan_state_side : c->scan_state_main;  // (the two streams may scan at the same time)
+    int rc;
+    if (state.n < static_cast<size_t>(tiles) + 2 && (rc = ensure_on(c, st, state, static_cast<size_t>(tiles) + 2 + 64))) return rc;  // (stream-ordered)
+    HRMGPU_CUDA(c, cudaMemsetAsync(state.p, 0, (static_cast<size_t>(tiles) + 2) * sizeof(unsigned long long), st));
+    k_scan_counts<<<static_cast<unsigned>(tiles), 1024, 0, st>>>(cnt, off, n, info, state.p);
     HRMGPU_CUDA(c, cudaGetLastError());
     c->launches += 1;
     return HRMGPU_OK;
@@ -638,9 +667,10 @@ static int enqueue_passes(Ctx* c, int from_pass) {
         }
         k_enhance<false><<<static_cast<unsigned>(g2), kSegWarps * 32, 0, st>>>(p);
         HRMGPU_CUDA(c, cudaGetLastError());
-        k_scan_counts<<<1, 1024, 0, st>>>(c->seg_cnt.p, c->seg_off.p, nl, c->seg_info.p);
         HRMGPU_CUDA(c, cudaGetLastError());
-        c->launches += 2;
+        int rc_scan;
+        if ((rc_scan = launch_scan_counts(c, c->seg_cnt.p, c->seg_off.p, nl, c->seg_info.p, st))) return rc_scan;
+        c->launches += 1;
     }
     k_enhance<true><<<static_cast<unsigned>(g2), kSegWarps * 32, 0, st>>>(p);
     HRMGPU_CUDA(c, cudaGetLastError());
