@@ -126,3 +126,27 @@ def test_errors_are_status_codes_not_crashes():
         assert np.array_equal(o, o2) and np.array_equal(xM, xM2)
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("K,Lx,Ly", [(16, 32, 16), (17, 32, 16), (3, 91, 90), (5, 7, 3)])
+def test_segment_offsets_across_scan_tiles(gpu_ctx, K, Lx, Ly):
+    """The CSR offsets of a batch come from a chained multi-CTA scan over K * Lx * Ly line counts (tiles of 8192): exactly one
+    tile (16 x 512), one line more than a tile boundary allows (17 x 512 = 2 tiles), a ragged count (3 x 8190) and a single small
+    tile must all give, layer by layer, the segments of that layer built on its own (a one-tile scan)."""
+    rows = util.synthetic_scene3d(7, 12, semi_rng=(3.0, 9.0))
+    rng = np.random.default_rng(5)
+    robot = [[6, 4, 3, 1, 1, 0, 0, 0, 1, 0, 0, 0]]
+    semi, R, off, quat = util.body_poses3d(robot, util.random_unit_quats(rng, K))
+    lim = [-58.0, 58.0, -28.0, 28.0, -18.0, 18.0]
+    gpu_ctx.set_scene3d(1, 12, util.sq17(rows.tolist(), 20), 20)
+    gpu_ctx.set_sweep(lim, Lx, Ly)
+    gpu_ctx.build_layers(semi, R, off, capi.F64_STRICT)
+    batch = [gpu_ctx.segments(k) for k in range(K)]
+    total = 0
+    for k in sorted({0, 1, K // 2, K - 1}):
+        gpu_ctx.build_layers(semi, R[k:k + 1], off[k:k + 1], capi.F64_STRICT)
+        alone = gpu_ctx.segments(0)
+        for a, b in zip(batch[k], alone):
+            assert np.array_equal(a, b)
+        total += len(alone[1])
+    assert total > 0

@@ -448,3 +448,36 @@ def test_tabulated_boxes_and_normals_change_no_answer(monkeypatch, precision):
     for got, want in zip(out["0"], out["1"]):
         assert np.array_equal(got, want)
         assert 0.05 < want.mean() < 0.95
+
+
+@pytest.mark.parametrize("n", [33, 36])
+def test_transitions_on_fine_meshes_match_oracle(oracle, gpu_ctx, n):
+    """n = 33 is the finest mesh the band / face-box tables cover (32 bands per direction, face indices up to 2047 in the queue
+    entries); n = 36 takes the plain face walk.  Both against the oracle's point-in-C-free test."""
+    sc = util.scenes()["3D_superquadrics_cluttered_rabbit"]
+    rows = sc["arena"] + sc["obstacle"]
+    n_arena, n_obs = len(sc["arena"]), len(sc["obstacle"])
+    rng = np.random.default_rng(17)
+    B, T, C = 2, 4, 160
+    tfe_semi = rng.uniform(3.0, 9.0, size=(1, B, 3))
+    quat = [(q / np.linalg.norm(q)).tolist() for q in rng.normal(size=(B, 4))]
+    tfe_R = np.array([[hm.flat9(hm.quat_to_rot(q)) for q in quat]])
+    gpu_ctx.set_scene3d(n_arena, n_obs, util.sq17(rows, n), n)
+    gpu_ctx.build_bridge(tfe_semi, tfe_R, capi.F64_STRICT)
+    bounds = [[oracle.minksum3d(rows[n_arena + o], tfe_semi[0][b], quat[b], n, +1) for o in range(n_obs)] for b in range(B)]
+    w1 = np.arange(T) * (1.0 / (T - 1))
+    w0 = 1.0 - w1
+    link_off = rng.uniform(-6, 6, size=(1, T, B, 3))
+    obs = np.array(sc["obstacle"])
+    v0 = obs[rng.integers(0, n_obs, C), 5:8] + rng.normal(scale=12.0, size=(C, 3))
+    v1 = v0 + rng.normal(scale=3.0, size=(C, 3))
+    got = gpu_ctx.test_transitions(np.zeros(C, dtype=np.int64), v0, v1, w0, w1, link_off)
+    want = np.ones(C, dtype=bool)
+    for s_ in range(T):
+        t = w0[s_] * v0 + w1[s_] * v1
+        for b in range(B):
+            centres = t if b == 0 else link_off[0, s_, b] + t
+            w, _ = oracle.pt_in_cfree3d(bounds[b], n, centres)
+            want &= w
+    assert np.array_equal(got, want)
+    assert 0.1 < want.mean() < 0.9
