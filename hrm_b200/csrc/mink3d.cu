@@ -32,9 +32,9 @@
 namespace hrmgpu {
 
 template <int MODE, bool SWEEP, bool CODE8>
-// CTAs per SM: 2 (strict: 128 registers), 3 (f64: 80 registers), 4 (f32: 64 registers without spills; measured +11 % over 3.
-// The f64 variant spills in phase A at 64 registers and loses 25 %).
-__global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : (MODE == HRMGPU_F32 ? 4 : 3)) k_minksweep3d(const MinkParams p) {
+// CTAs per SM: 3 (f64 and strict: 80 registers; strict keeps its matrices in shared memory for that, measured 8.6 % faster than 2 CTAs at
+// 128 registers), 4 (f32: 64 registers without spills; measured +11 % over 3.  The f64 variant spills in phase A at 64 registers and loses 25 %).
+__global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F32 ? 4 : 3) k_minksweep3d(const MinkParams p) {
     using Code = typename std::conditional<CODE8, uint16_t, uint32_t>::type;  // packed line codes: 2 x 8 or 2 x 16 bits
     using A = typename std::conditional<MODE == HRMGPU_F64_STRICT, Strict, Fast>::type;
     using Real = typename RealOf<MODE>::type;
@@ -187,6 +187,10 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : (MOD
 
     __syncthreads();
     if (p.dbg && tid == 0) dbg_max[2] = (unsigned long long)(clock64() - t_start);
+    if constexpr (MODE == HRMGPU_F64_STRICT) {  // R1 beside M1, M2 (the scratch of the matrix products is free now)
+        if (tid < 9) mats[18 + tid] = __ldg(&ob.R[tid]);
+        __syncthreads();
+    }
     if constexpr (MODE != HRMGPU_F64_STRICT) {
         // column table and row-base coefficients.  Two threads per column: the even one writes {ce2, UZ, WZ}, the odd one
         // {ce1, C}; the first two threads also write the row base.
@@ -227,9 +231,11 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : (MOD
         const double px = __ldg(&ob.px), py = __ldg(&ob.py), pz = __ldg(&ob.pz);
         if constexpr (MODE == HRMGPU_F64_STRICT) {
             // IEEE replica of the reference's evaluation order; only exact products are hoisted per column.
-            double R1[9], M1[9], M2[9];
-#pragma unroll
-            for (int i = 0; i < 9; ++i) R1[i] = __ldg(&ob.R[i]), M1[i] = mats[i], M2[i] = mats[9 + i];
+            // The 27 matrix entries stay in shared memory (volatile: hoisted back into registers they take 54 of them and the kernel
+            // drops to 2 CTAs per SM; measured 5.46 -> 4.99 ms per 32 layers).
+            const volatile double* M1 = mats;
+            const volatile double* M2 = mats + 9;
+            const volatile double* R1 = mats + 18;
             for (int c = grp; c < n; c += p.groups) {
                 const double ce1 = tab[c], se1 = tab[n + c], ce2 = tab[2 * n + c], se2 = tab[3 * n + c];
                 const double Z = A::mul(oc, se1);   // c * (se1 * 1.0)
@@ -237,7 +243,7 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : (MOD
                 const double rz0 = A::mul(R1[2], Z), rz1 = A::mul(R1[5], Z), rz2 = A::mul(R1[8], Z);
                 const double uz0 = A::mul(M1[2], gz), uz1 = A::mul(M1[5], gz), uz2 = A::mul(M1[8], gz);
                 const double wz0 = A::mul(M2[2], gz), wz1 = A::mul(M2[5], gz), wz2 = A::mul(M2[8], gz);
-                for (int r = ln; r < n; r += p.lpc) {
+                auto point = [&](int r) {
                     const double cw1 = tab[4 * n + r], sw1 = tab[5 * n + r], cw2 = tab[6 * n + r], sw2 = tab[7 * n + r];
                     const int kk = c * n + r;
                     // getOriginShape: canonical point, rotate, translate              SuperQuadrics.cpp:58-78
@@ -267,7 +273,8 @@ __global__ void __launch_bounds__(kThreads, MODE == HRMGPU_F64_STRICT ? 2 : (MOD
                         const uint32_t cy = line_code(oy, tys, p.Ly, p.inv_dy, p.bias_y);
                         vcode[kk] = pack_code(cx, cy);
                     }
-                }
+                };
+                for (int r = ln; r < n; r += p.lpc) point(r);
             }
         } else {
             // Fast variants: x = P*cw1 + Q*sw1 + C,  u = U1*cw2 + U2*sw2 + U3,  w = W1*cw2 + W2*sw2 + W3 with the nine
