@@ -6,7 +6,7 @@
 // A layer's vertices are its free-segment mid points PLUS the bridge vertices connectOneSlice inserted between them
 // (bridgeVertex, HighwayRoadMap-inl.h:263-326), so the host hands over its vertex positions (a few 10^3 x 24 bytes) and the id
 // range of every layer; what the host no longer does is enumerate, upload and replay the ~10^5 candidate pairs:
-//   k_pair_candidates<false>  counts, per (pair, m0), the vertices of `cur` inside the window (ascending m1)
+//   k_pair_candidates<false>  counts, per (pair, m0) -- one warp each --, the vertices of `cur` inside the window (ascending m1)
 //   k_scan_counts             (segments.cu) turns the counts into offsets
 //   k_pair_candidates<true>   writes pair index, both positions and m1 of every candidate
 //   k_transitions3d           (queries.cu, unchanged) tests all candidates of all pairs in one launch
@@ -17,44 +17,58 @@
 
 namespace hrmgpu {
 
+// One warp per (pair, m0): the lanes take 32 vertices of `cur` at a time, a ballot counts / places the ones inside the window, so the
+// candidates of m0 stay ascending in m1.  (One thread per m0 walking all of `cur` left the grid at a few blocks: 0.6 ms per
+// ProbHRM3D::plan() for 12 slice pairs.)
+constexpr int kCandWarps = 4;
 template <bool FILL>
-__global__ void __launch_bounds__(128) k_pair_candidates(const PairParams p) {
-    const int pr = blockIdx.y;
+__global__ void __launch_bounds__(32 * kCandWarps) k_pair_candidates(const PairParams p) {
+    const int pr = blockIdx.y, lane = threadIdx.x & 31;
     const long long n0 = p.m0_first[pr + 1] - p.m0_first[pr];
-    const long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long v = static_cast<long long>(blockIdx.x) * kCandWarps + (threadIdx.x >> 5);
     if (v >= n0) return;
     const long long g = p.m0_first[pr] + v;
     const int m0 = p.range[4 * pr] + static_cast<int>(v);
     const int c0 = p.range[4 * pr + 2], c1 = p.range[4 * pr + 3];
-    const double x0 = p.vtx[3 * static_cast<size_t>(m0)], y0 = p.vtx[3 * static_cast<size_t>(m0) + 1];
-    if (!FILL) {
-        int n = 0;
-        for (int m1 = c0; m1 < c1; ++m1) {
-            const double x1 = __ldg(p.vtx + 3 * static_cast<size_t>(m1)), y1 = __ldg(p.vtx + 3 * static_cast<size_t>(m1) + 1);
-            n += (fabs(x0 - x1) > p.thx || fabs(y0 - y1) > p.thy) ? 0 : 1;  // HRM3D.cpp:195-200
+    const double x0 = p.vtx[3 * static_cast<size_t>(m0)], y0 = p.vtx[3 * static_cast<size_t>(m0) + 1], z0 = p.vtx[3 * static_cast<size_t>(m0) + 2];
+    const unsigned lt = (1u << lane) - 1u;
+    int n = 0;
+    long long c = FILL ? p.cand_first[g] : 0;
+    for (int base = c0; base < c1; base += 32) {
+        const int m1 = base + lane;
+        double x1 = 0.0, y1 = 0.0;
+        bool in = false;
+        if (m1 < c1) {
+            x1 = __ldg(p.vtx + 3 * static_cast<size_t>(m1)), y1 = __ldg(p.vtx + 3 * static_cast<size_t>(m1) + 1);
+            in = !(fabs(x0 - x1) > p.thx || fabs(y0 - y1) > p.thy);  // HRM3D.cpp:195-200
         }
-        p.cnt[g] = n;
-    } else {
-        long long c = p.cand_first[g];
-        const double z0 = p.vtx[3 * static_cast<size_t>(m0) + 2];
-        for (int m1 = c0; m1 < c1; ++m1) {
-            const double x1 = __ldg(p.vtx + 3 * static_cast<size_t>(m1)), y1 = __ldg(p.vtx + 3 * static_cast<size_t>(m1) + 1);
-            if (fabs(x0 - x1) > p.thx || fabs(y0 - y1) > p.thy) continue;
-            p.c_pair[c] = pr;
-            p.c_v0[3 * c] = x0, p.c_v0[3 * c + 1] = y0, p.c_v0[3 * c + 2] = z0;
-            p.c_v1[3 * c] = x1, p.c_v1[3 * c + 1] = y1, p.c_v1[3 * c + 2] = __ldg(p.vtx + 3 * static_cast<size_t>(m1) + 2);
-            p.c_m1[c] = m1;
-            ++c;
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, in);
+        if (FILL) {
+            if (in) {
+                const long long e = c + __popc(bal & lt);
+                p.c_pair[e] = pr;
+                p.c_v0[3 * e] = x0, p.c_v0[3 * e + 1] = y0, p.c_v0[3 * e + 2] = z0;
+                p.c_v1[3 * e] = x1, p.c_v1[3 * e + 1] = y1, p.c_v1[3 * e + 2] = __ldg(p.vtx + 3 * static_cast<size_t>(m1) + 2);
+                p.c_m1[e] = m1;
+            }
+            c += __popc(bal);
+        } else {
+            n += __popc(bal);
         }
     }
+    if (!FILL && lane == 0) p.cnt[g] = n;
 }
 
 // One warp per pair: m0 in order; the lanes look at 32 candidates of m0 at a time (they are ascending in m1), the first one at or
 // above the moving lower bound whose transition is free is the match (HRM3D.cpp:186-222).  The loop is serial in m0 (n22 moves), so
-// it runs at load latency: the candidate ranges of 32 vertices are fetched at once, and the first 32 candidates of vertex m0 + 1
-// are in flight while vertex m0 is decided (they do not depend on n22).
+// it runs at load latency: the candidate ranges of 32 vertices are fetched at once and, when they fit (kReplayCap), all their
+// candidates are staged in shared memory with coalesced loads; else the first 32 candidates of vertex m0 + 1 are in flight while
+// vertex m0 is decided (they do not depend on n22).
+constexpr int kReplayCap = 2048;
 __global__ void __launch_bounds__(32) k_pair_replay(const long long* m0_first, const long long* cand_first, const int* c_m1, const unsigned char* free_flag,
                                                     int* match) {
+    __shared__ int s_m1[kReplayCap];
+    __shared__ unsigned char s_fl[kReplayCap];
     const int pr = blockIdx.x, lane = threadIdx.x;
     const unsigned full = 0xFFFFFFFFu;
     int n22 = 0;  // (vertex ids are non-negative: the first candidate of the pair is at or above it, like n22 = the layer's first id)
@@ -63,25 +77,34 @@ __global__ void __launch_bounds__(32) k_pair_replay(const long long* m0_first, c
         const int nv = static_cast<int>((g_end - g0 < 32) ? g_end - g0 : 32);
         const long long cf = (lane <= nv - 1) ? cand_first[g0 + lane] : 0;
         const long long cf_last = cand_first[g0 + nv];
+        const long long r0 = __shfl_sync(full, cf, 0);
+        const bool staged = cf_last - r0 <= kReplayCap;
+        if (staged) {
+            __syncwarp();
+            for (long long j = r0 + lane; j < cf_last; j += 32) s_m1[j - r0] = c_m1[j], s_fl[j - r0] = free_flag[j];
+            __syncwarp();
+        }
         // first chunk of vertex 0 of this block
-        long long b0 = __shfl_sync(full, cf, 0), e0 = (nv > 1) ? __shfl_sync(full, cf, 1) : cf_last;
+        long long b0 = r0, e0 = (nv > 1) ? __shfl_sync(full, cf, 1) : cf_last;
         int m1 = -1;
         unsigned char fl = 0;
-        if (b0 + lane < e0) m1 = c_m1[b0 + lane], fl = free_flag[b0 + lane];
+        if (!staged && b0 + lane < e0) m1 = c_m1[b0 + lane], fl = free_flag[b0 + lane];
         for (int t = 0; t < nv; ++t) {
-            // next vertex's first chunk, issued before this vertex is decided
             long long b1 = 0, e1 = 0;
             int m1n = -1;
             unsigned char fln = 0;
             if (t + 1 < nv) {
                 b1 = __shfl_sync(full, cf, t + 1);
                 e1 = (t + 2 < nv) ? __shfl_sync(full, cf, t + 2) : cf_last;
-                if (b1 + lane < e1) m1n = c_m1[b1 + lane], fln = free_flag[b1 + lane];
+                if (!staged && b1 + lane < e1) m1n = c_m1[b1 + lane], fln = free_flag[b1 + lane];  // issued before this vertex is decided
             }
             int found = -1;
             for (long long j0 = b0; j0 < e0 && found < 0; j0 += 32) {
-                if (j0 != b0) {  // (more than 32 candidates and no match so far)
-                    const long long j = j0 + lane;
+                const long long j = j0 + lane;
+                if (staged) {
+                    m1 = -1, fl = 0;
+                    if (j < e0) m1 = s_m1[j - r0], fl = s_fl[j - r0];
+                } else if (j0 != b0) {  // (more than 32 candidates and no match so far)
                     m1 = -1, fl = 0;
                     if (j < e0) m1 = c_m1[j], fl = free_flag[j];
                 }
@@ -172,11 +195,11 @@ int launch_pair_codes(Ctx* c, const unsigned char* free5, long long n_pairs, uns
 }
 
 int launch_pair_candidates(Ctx* c, const PairParams& p, long long max_n0, bool fill) {
-    const dim3 grid(static_cast<unsigned>((max_n0 + 127) / 128), static_cast<unsigned>(p.P));
+    const dim3 grid(static_cast<unsigned>((max_n0 + kCandWarps - 1) / kCandWarps), static_cast<unsigned>(p.P));
     if (fill)
-        k_pair_candidates<true><<<grid, 128, 0, c->stream>>>(p);
+        k_pair_candidates<true><<<grid, 32 * kCandWarps, 0, c->stream>>>(p);
     else
-        k_pair_candidates<false><<<grid, 128, 0, c->stream>>>(p);
+        k_pair_candidates<false><<<grid, 32 * kCandWarps, 0, c->stream>>>(p);
     HRMGPU_CUDA(c, cudaGetLastError());
     c->launches += 1;
     return HRMGPU_OK;

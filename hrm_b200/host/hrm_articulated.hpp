@@ -200,7 +200,8 @@ class ProbHRM3D : public HRM3D {
         do {
             const size_t s = param_.numSlice;
             if (s >= batchEnd) {  // draw the next batch of robot shapes and build their C-layers in one call
-                const size_t want = s < 2 ? 2 : batch_;
+                size_t want = s < 2 ? 2 : batch_;
+                if (refinePeriod_ > 0 && want > refinePeriod_ - s % refinePeriod_) want = refinePeriod_ - s % refinePeriod_;  // (a refinement rebuilds every layer)
                 size_t have = 0;
                 std::vector<MultiBodyTree3D> poses;
                 baseQ.clear();
@@ -239,11 +240,27 @@ class ProbHRM3D : public HRM3D {
                     batchCode_ = freeSpace_.connectSlices3D(layerFirst, total, have);
                     if (batchCode_.size() != total) throw std::runtime_error("connectSlices3D: pair count mismatch");
                 }
+                staged_.clear();
+                if (deviceMatching_ && batchBridge_) stageBatch(s, have, baseQ, tx, ty, off, xL, xU, xM);
             }
             // constructOneSlice: vertices + intra-layer edges of slice s
             const size_t k = s - batchStart;
             vertexTail_.assign(v_.at(s).begin() + 7, v_.at(s).end());
             q_.push_back({v_.at(s)[3], v_.at(s)[4], v_.at(s)[5], v_.at(s)[6]});
+            if (!staged_.empty()) {
+                // the slice was built with its batch (stageBatch): its vertices, intra-slice edges and bridge edges enter the roadmap
+                // now, in the reference's order, so that search() sees exactly the roadmap the reference has after this slice
+                StageScope ss(stage_, "append staged slice");
+                StagedSlice& st = staged_.at(k);
+                auto& g = res_.graphStructure;
+                g.vertex.insert(g.vertex.end(), std::make_move_iterator(st.vertex.begin()), std::make_move_iterator(st.vertex.end()));
+                g.edge.insert(g.edge.end(), st.edge.begin(), st.edge.end());
+                g.weight.insert(g.weight.end(), st.weight.begin(), st.weight.end());
+                vertexIdx_.push_back(st.vertexIdx);
+                numEdgeTests_ += st.edgeTests;
+                param_.numSlice++;
+                for (const auto& e : st.bridge) addEdge(e.first, e.second);
+            } else {
             {
                 StageScope ss(stage_, "connectOneSlice");
                 if (deviceMatching_) {
@@ -259,6 +276,7 @@ class ProbHRM3D : public HRM3D {
             if (param_.numSlice >= 2) {
                 StageScope ss(stage_, "connectNearestSlice");
                 connectNearestSlice();
+            }
             }
             res_.planningTime.buildTime += seconds(t0);
             t0 = std::chrono::high_resolution_clock::now();
@@ -412,6 +430,134 @@ class ProbHRM3D : public HRM3D {
         return mvce;
     }
 
+    /** One slice of a look-ahead batch, built ahead of its turn (stageBatch) */
+    struct StagedSlice {
+        std::vector<std::vector<Coordinate>> vertex;
+        std::vector<std::pair<Index, Index>> edge;  // intra-slice edges (connectOneSlice)
+        std::vector<double> weight;
+        std::pair<Index, Index> vertexIdx;
+        std::vector<std::pair<Index, Index>> bridge;  // edges to the nearest earlier slice (connectMultiSlice), in m0 order
+        long edgeTests = 0;
+    };
+
+    /** Interpolation weights and the chain / link offsets of the interpolated poses between two slices (the part of
+     * isMultiSliceTransitionFree that does not depend on the candidate, see connectNearestSlice) appended for one slice pair */
+    void appendPairOffsets(const std::vector<Coordinate>& vNear, const std::vector<Coordinate>& vNew, std::vector<double>& linkOff,
+                           std::vector<double>& chainOff) {
+        const size_t steps = param_.numPoint, T = steps + 1;
+        const size_t B = robot_.getNumLinks() + 1;
+        const size_t base = linkOff.size();
+        linkOff.resize(base + T * B * 3, 0.0), chainOff.resize(base + T * B * 3, 0.0);
+        const auto vi = interpolateCompoundSE3Rn(vNear, vNew, steps);
+        const auto& tf = robot_.getTF();
+        const size_t nj = kdl_.getNrOfJoints();
+        for (size_t s = 0; s < T; ++s) {
+            const Mat3 R = toRotationMatrix({vi[s][3], vi[s][4], vi[s][5], vi[s][6]});
+            const std::vector<double> joints(vi[s].begin() + 7, vi[s].begin() + 7 + static_cast<long>(nj));
+            for (size_t l = 0; l + 1 < B; ++l) {
+                const SE3Transform fk = kdl_.getTransform(joints, "body" + std::to_string(l + 1));
+                const Vec3 c = matVec(R, fk.t);
+                const Vec3 v = matVec(matMul(R, fk.R), tf[l].t);
+                for (int d = 0; d < 3; ++d) chainOff[base + (s * B + (l + 1)) * 3 + d] = c[d], linkOff[base + (s * B + (l + 1)) * 3 + d] = v[d];
+            }
+        }
+    }
+
+    /** The whole look-ahead batch ahead of its turn (bridge + K5 of a batch in one launch each).  The robot
+     * shapes of the batch are known, and neither the vertices of a slice nor its bridge to the nearest earlier slice depend on
+     * the searches in between: (1) connectOneSlice of every slice is replayed on the batch's pair codes (vertex ids are
+     * consecutive, bridging adds no vertices), (2) the tightly-fitted ellipsoids of ALL slice pairs go into ONE bridge build and
+     * the candidate pairs of all of them into ONE hrmgpu_connect_pairs3d call, (3) everything is taken out of the roadmap again
+     * and kept per slice; plan() appends slice after slice and searches in between, exactly like the reference. */
+    void stageBatch(size_t s0, size_t have, const std::vector<Quaternion>& baseQ, const std::vector<double>& tx, const std::vector<double>& ty,
+                    const std::vector<long long>& off, const std::vector<double>& xL, const std::vector<double>& xU, const std::vector<double>& xM) {
+        auto& g = res_.graphStructure;
+        const size_t V0 = g.vertex.size(), E0 = g.edge.size(), I0 = vertexIdx_.size();
+        const long tests0 = numEdgeTests_;
+        const size_t L = tx.size() * ty.size();
+        std::vector<size_t> vEnd(have), eEnd(have);
+        std::vector<long> tests(have);
+        {
+            StageScope ss(stage_, "connectOneSlice");
+            for (size_t k = 0; k < have; ++k) {
+                vertexTail_.assign(v_.at(s0 + k).begin() + 7, v_.at(s0 + k).end());
+                const SlicePairs& sp = batchSp_.at(k);
+                const std::vector<int> codes(batchCode_.begin() + static_cast<long>(sp.first), batchCode_.begin() + static_cast<long>(sp.first + sp.P));
+                replaySlice3D(baseQ.at(k), tx, ty, off.data() + k * L, xL, xU, xM, sp, codes);
+                vEnd[k] = g.vertex.size(), eEnd[k] = g.edge.size(), tests[k] = static_cast<long>(5 * sp.P);
+            }
+        }
+        // bridges: slice s0 + k against its nearest earlier slice (ProbHRM3D.cpp:105-162)
+        std::vector<std::vector<Ellipsoid>> tfe;
+        std::vector<int> range4;
+        std::vector<size_t> pairSlice;
+        std::vector<double> linkOff, chainOff;
+        {
+            StageScope ss(stage_, "connectNearestSlice");
+            auto tT = std::chrono::high_resolution_clock::now();
+            for (size_t k = 0; k < have; ++k) {
+                const size_t cur = s0 + k;
+                if (cur == 0) continue;
+                double minDist = INFINITY;
+                size_t minIdx = 0;
+                for (size_t i = 0; i < cur; ++i) {
+                    const double dist = vectorEuclidean(v_.at(cur), v_.at(i));
+                    if (dist < minDist) minDist = dist, minIdx = i;
+                }
+                const Index new0 = vertexIdx_.at(cur).first, new1 = vertexIdx_.at(cur).second;
+                const Index start = vertexIdx_.at(minIdx).first, n1 = vertexIdx_.at(minIdx).second;
+                if (n1 <= start || new1 <= new0) continue;
+                tfe.push_back(computeTFE(v_.at(cur), v_.at(minIdx)));
+                appendPairOffsets(g.vertex[start], g.vertex[new0], linkOff, chainOff);
+                range4.insert(range4.end(), {static_cast<int>(start), static_cast<int>(n1), static_cast<int>(new0), static_cast<int>(new1)});
+                pairSlice.push_back(k);
+            }
+            stage_.add("  TFE + FK of the interpolated poses (host)", seconds(tT));
+        }
+        std::vector<StagedSlice> out(have);
+        if (!pairSlice.empty()) {
+            StageScope ss(stage_, "connectNearestSlice");
+            const auto& lim = param_.boundaryLimits;
+            const double thx = 2.0 * (lim[1] - lim[0]) / static_cast<double>(param_.numLineX);
+            const double thy = 2.0 * (lim[3] - lim[2]) / static_cast<double>(param_.numLineY);
+            const size_t steps = param_.numPoint, T = steps + 1;
+            std::vector<double> w0(T), w1(T);
+            const double dt = 1.0 / static_cast<double>(steps);
+            for (size_t t = 0; t < T; ++t) w1[t] = static_cast<double>(t) * dt, w0[t] = 1.0 - static_cast<double>(t) * dt;  // InterpolateSE3.cpp:5-29
+            {
+                StageScope s2(stage_, "  K5a buildBridge (batch)");
+                freeSpace_.buildBridge(tfe, precision_);
+            }
+            std::vector<double> xyz(3 * g.vertex.size());
+            for (size_t m = 0; m < g.vertex.size(); ++m)
+                for (int d = 0; d < 3; ++d) xyz[3 * m + d] = g.vertex[m][d];
+            std::vector<int> match;
+            {
+                StageScope s2(stage_, "  K5b connectPairs (device, batch)");
+                match = freeSpace_.connectPairs3D(xyz, range4, thx, thy, w0, w1, linkOff, &numBridgeCandidates_, &chainOff);
+            }
+            size_t first = 0;
+            for (size_t pi = 0; pi < pairSlice.size(); ++pi) {
+                const Index start = static_cast<Index>(range4[4 * pi]), n1 = static_cast<Index>(range4[4 * pi + 1]);
+                for (Index m0 = start; m0 < n1; ++m0)
+                    if (match.at(first + (m0 - start)) >= 0) out[pairSlice[pi]].bridge.push_back({m0, static_cast<Index>(match[first + (m0 - start)])});
+                first += n1 - start;
+            }
+        }
+        // take the batch out of the roadmap again
+        for (size_t k = 0; k < have; ++k) {
+            const size_t vb = k ? vEnd[k - 1] : V0, eb = k ? eEnd[k - 1] : E0;
+            out[k].vertex.assign(std::make_move_iterator(g.vertex.begin() + static_cast<long>(vb)), std::make_move_iterator(g.vertex.begin() + static_cast<long>(vEnd[k])));
+            out[k].edge.assign(g.edge.begin() + static_cast<long>(eb), g.edge.begin() + static_cast<long>(eEnd[k]));
+            out[k].weight.assign(g.weight.begin() + static_cast<long>(eb), g.weight.begin() + static_cast<long>(eEnd[k]));
+            out[k].vertexIdx = vertexIdx_.at(I0 + k);
+            out[k].edgeTests = tests[k];
+        }
+        g.vertex.resize(V0), g.edge.resize(E0), g.weight.resize(E0), vertexIdx_.resize(I0);
+        numEdgeTests_ = tests0;
+        staged_ = std::move(out);
+    }
+
     /** connectMultiSlice (:105-162): the newest slice against its nearest earlier one; K5 batch + host replay */
     void connectNearestSlice() {
         if (param_.numSlice == 1) return;
@@ -507,6 +653,8 @@ class ProbHRM3D : public HRM3D {
     }
 
     std::vector<unsigned char> batchCode_;  // connectOneSlice pair codes of the look-ahead batch (device matching)
+    std::vector<StagedSlice> staged_;       // the look-ahead batch built ahead of its turn (empty: slice by slice)
+    bool batchBridge_ = std::getenv("HRM_PROB_PER_SLICE") == nullptr;  // (A/B switch: one bridge build + one matching call per slice)
     std::vector<SlicePairs> batchSp_;
     std::string urdfFile_;
     ParseURDF kdl_;
