@@ -179,6 +179,21 @@ def test_prob_hrm3d_roadmap_identical(oracle, name, per_orientation, batch):
         assert ref["slices"] > 2  # several random slices and nearest-slice bridges were needed
 
 
+def test_prob_hrm3d_slice_by_slice_path_identical(oracle, monkeypatch):
+    """HRM_PROB_PER_SLICE=1: one bridge build and one matching call per slice instead of the batch staged ahead of its turn
+    (stageBatch) -- the same roadmap as the oracle, hence as the staged path the other tests run."""
+    monkeypatch.setenv("HRM_PROB_PER_SLICE", "1")
+    ref, got = _prob_case(oracle, "3D_superquadrics_home_snake", True, 30, 8)
+    assert np.array_equal(got["vertex"], ref["vertex"]) and np.array_equal(got["edge"], ref["edge"])
+    assert got["solved"] == ref["solved"] and np.array_equal(got["path"], ref["path"])
+    per_slice_launches = got["gpu_launches"]
+    monkeypatch.delenv("HRM_PROB_PER_SLICE")
+    _, got2 = _prob_case(oracle, "3D_superquadrics_home_snake", True, 30, 8)
+    staged_launches = got2["gpu_launches"]
+    assert np.array_equal(got2["vertex"], got["vertex"]) and np.array_equal(got2["edge"], got["edge"])
+    assert staged_launches < per_slice_launches  # fewer, larger launches
+
+
 def test_prob_hrm3d_stops_when_draws_run_out(oracle):
     """Too few draws to solve the per-orientation home map: both planners stop unsolved after the same number of slices."""
     ref, got = _prob_case(oracle, "3D_superquadrics_home_snake", True, 3, 8)
