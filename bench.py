@@ -566,6 +566,8 @@ def run_gpu(args):
             "cpu_baseline": cpu, "e2e": head["e2e"], "gpu_launches": head["launches"], "clocks": head["clocks"],
             "segments_per_layer": head["segments_per_layer"], "segment_pass_redos_in_timed_region": head["segment_pass_redos_in_timed_region"],
             "allgather_bytes_per_build_per_rank": head["allgather_bytes_per_build_per_rank"],
+            # distinct orientations built inside the timed region, all ranks (defaults: 20 steps x 500 = the 10 000 orientations of configs[4] per GPU)
+            "orientations_in_timed_region": args.steps * bps * layers * world,
             "parity": parity, "freespace": free, "strong_scaling": strong, "plan": plan,
         }
     if world > 1:
