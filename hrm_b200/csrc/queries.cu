@@ -453,8 +453,13 @@ __global__ void __launch_bounds__(128, 6) k_transitions3d(const TransParams p) {
         unsigned char* tab = s_tab[(threadIdx.x >> 5) & 3];
         const unsigned lt = (1u << lane) - 1u;
         const int nm1 = p.n - 1, nc = nm1 * nm1;
-        int qn = 0, cnt = 0;
-        double hz0 = 0.0, hz1 = 0.0;
+        __shared__ int s_cnt_all[4][32];
+        __shared__ double s_hz_all[4][64];
+        int* s_cnt = s_cnt_all[(threadIdx.x >> 5) & 3];  // hits of lane l's item so far (0..2) and the heights of the first two
+        double* s_hz = s_hz_all[(threadIdx.x >> 5) & 3];
+        s_cnt[lane] = 0;
+        __syncwarp();
+        int qn = 0;
         auto drain = [&](int take) {
             int owner = lane, f = 0;
             if (lane < take) {
@@ -477,16 +482,21 @@ __global__ void __launch_bounds__(128, 6) k_transitions3d(const TransParams p) {
                 const D3 dir = {0.0, 0.0, 1.0};
                 hit = line_triangle<A>(org, dir, t0, t1, t2, pt);
             }
-            unsigned bal = __ballot_sync(full, hit);
-            while (bal) {
-                const int src = __ffs(bal) - 1;
-                bal &= bal - 1;
-                const int ow = __shfl_sync(full, owner, src);
-                const double z = __shfl_sync(full, pt.z, src);
-                if (lane == ow && cnt < 2) {  // (the reference stops at the second hit: LineIntersection.cpp:116-120)
-                    if (cnt == 0) hz0 = z; else hz1 = z;
-                    ++cnt;
+            const unsigned bal = __ballot_sync(full, hit);
+            if (bal) {
+                // The hits of one item sit in consecutive lanes (the queue is item-major): a hit lane's rank among the hits of its
+                // owner, added to the owner's count so far, is its place in face order; the first two are kept (the reference stops at
+                // the second hit: LineIntersection.cpp:116-120).  No loop over the hits: they are most of the queued pairs.
+                const unsigned group = __match_any_sync(full, owner);
+                const unsigned mine = bal & group;
+                const int before = hit ? s_cnt[owner] : 0;
+                __syncwarp();
+                if (hit) {
+                    const int at = before + __popc(mine & lt);
+                    if (at < 2) s_hz[2 * owner + at] = pt.z;
+                    if ((mine & lt) == 0u) s_cnt[owner] = min(2, before + __popc(mine));
                 }
+                __syncwarp();
             }
             unsigned short rest = 0;
             if (take + lane < qn) rest = queue[take + lane];
@@ -530,7 +540,10 @@ __global__ void __launch_bounds__(128, 6) k_transitions3d(const TransParams p) {
             __syncwarp();  // (the tables are rewritten for the next item)
         }
         if (qn > 0) drain(qn);
+        __syncwarp();
         if (live) {
+            const int cnt = s_cnt[lane];
+            const double hz0 = s_hz[2 * lane], hz1 = s_hz[2 * lane + 1];
             if (cnt == 2) {
                 if (oz > fmin(hz0, hz1) && oz < fmax(hz0, hz1)) p.flag[c] = 1u;  // HRM3D.cpp:409-413
             } else if (cnt == 1) {
