@@ -723,23 +723,15 @@ struct PlanningResult {  // :53-65
 
 namespace planners {
 
-/** Adjacency of the roadmap in CSR form (neighbours of a vertex in edge order, as pushing both directions of every edge in
- * turn produces them) + connected components: built once per search() and shared by its A* runs. */
+/** Connected components of the roadmap (union-find over the edge list), built once per search(), and -- only when some
+ * (start, goal) candidate pair is connected at all -- its adjacency in CSR form (neighbours of a vertex in edge order, as pushing
+ * both directions of every edge in turn produces them), shared by the A* runs of that search(). */
 struct GraphIndex {
-    std::vector<size_t> off;
-    std::vector<std::pair<Index, double>> nbr;
+    mutable std::vector<size_t> off;  // (filled on demand: needAdjacency)
+    mutable std::vector<std::pair<Index, double>> nbr;
     std::vector<Index> comp;
-    explicit GraphIndex(const Graph& g) {
+    explicit GraphIndex(const Graph& g) : g_(&g) {
         const Index n = g.vertex.size();
-        off.assign(n + 1, 0);
-        for (const auto& e : g.edge) ++off[e.first + 1], ++off[e.second + 1];
-        for (Index i = 0; i < n; ++i) off[i + 1] += off[i];
-        nbr.resize(off[n]);
-        std::vector<size_t> fill(off.begin(), off.end() - 1);
-        for (size_t i = 0; i < g.edge.size(); ++i) {
-            nbr[fill[g.edge[i].first]++] = {g.edge[i].second, g.weight[i]};
-            nbr[fill[g.edge[i].second]++] = {g.edge[i].first, g.weight[i]};
-        }
         comp.resize(n);
         for (Index i = 0; i < n; ++i) comp[i] = i;
         auto find = [&](Index x) {
@@ -753,13 +745,34 @@ struct GraphIndex {
         for (Index i = 0; i < n; ++i) comp[i] = find(i);
     }
     bool connected(Index a, Index b) const { return comp[a] == comp[b]; }
+    void needAdjacency() const {
+        if (!off.empty()) return;
+        const Graph& g = *g_;
+        const Index n = g.vertex.size();
+        auto& o = off;
+        auto& nb = nbr;
+        o.assign(n + 1, 0);
+        for (const auto& e : g.edge) ++o[e.first + 1], ++o[e.second + 1];
+        for (Index i = 0; i < n; ++i) o[i + 1] += o[i];
+        nb.resize(o[n]);
+        std::vector<size_t> fill(o.begin(), o.end() - 1);
+        for (size_t i = 0; i < g.edge.size(); ++i) {
+            nb[fill[g.edge[i].first]++] = {g.edge[i].second, g.weight[i]};
+            nb[fill[g.edge[i].second]++] = {g.edge[i].first, g.weight[i]};
+        }
+    }
+
+  private:
+    const Graph* g_;
 };
 
-/** A* with the Euclidean heuristic of HighwayRoadMap-inl.h:135-147 (Boost.Graph replaced by a binary heap). */
+/** A* with the Euclidean heuristic of HighwayRoadMap-inl.h:135-147 (Boost.Graph replaced by a binary heap).  The heuristic of a
+ * vertex is evaluated once, when the vertex is first reached (the same value every later relaxation would compute). */
 inline bool astar(const Graph& g, const GraphIndex& gi, Index s, Index t, std::vector<Index>& pred) {
     const Index n = g.vertex.size();
     if (!gi.connected(s, t)) return false;  // (the search below would exhaust s's component and fail)
-    std::vector<double> d(n, INFINITY);
+    gi.needAdjacency();
+    std::vector<double> d(n, INFINITY), h(n, -1.0);
     pred.assign(n, n);
     using QE = std::pair<double, Index>;
     std::priority_queue<QE, std::vector<QE>, std::greater<QE>> pq;
@@ -779,7 +792,8 @@ inline bool astar(const Graph& g, const GraphIndex& gi, Index s, Index t, std::v
             if (nd < d[e.first]) {
                 d[e.first] = nd;
                 pred[e.first] = u;
-                pq.push({nd + vectorEuclidean(g.vertex[e.first], g.vertex[t]), e.first});
+                if (h[e.first] < 0.0) h[e.first] = vectorEuclidean(g.vertex[e.first], g.vertex[t]);
+                pq.push({nd + h[e.first], e.first});
             }
         }
     }
@@ -871,9 +885,14 @@ class HighwayRoadMapBase {
     void search() {
         Graph& g = res_.graphStructure;
         if (g.vertex.empty()) return;
+        auto tS = std::chrono::high_resolution_clock::now();
         const auto idxS = getNearestNeighborsOnGraph(start_, param_.numSearchNeighbor, param_.searchRadius);
         const auto idxG = getNearestNeighborsOnGraph(goal_, param_.numSearchNeighbor, param_.searchRadius);
+        stage_.add("  search: nearest vertices", std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - tS).count());
+        tS = std::chrono::high_resolution_clock::now();
         const GraphIndex gi(g);
+        stage_.add("  search: adjacency + components", std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - tS).count());
+        StageScope ssA(stage_, "  search: A*");
         for (Index s : idxS)
             for (Index t : idxG) {
                 std::vector<Index> p;
