@@ -87,3 +87,30 @@ def test_allgather_segments_world2_gloo(oracle):
     for k in range(6):
         xm += oracle.layer3d(1, 7, rows, 10, semi, quat[k], off[k], sc["lim"], sc["Lx"], sc["Ly"], want_bound=False)["xM"].tolist()
     assert res[0][2] == xm
+
+
+def test_bridge_pair_sharding_helpers():
+    """Pure host logic of the pair-sharded bridge stage: every pair has exactly one owner, the pairing is the
+    planner's nearest EARLIER layer, vertex ids follow (layer, line, segment) order."""
+    from hrm_b200 import dist as hd
+    from hrm_b200 import tfe
+    from tests import util
+
+    for n in (0, 1, 7, 59):
+        for w in (1, 2, 3, 8):
+            assert sorted(sum([hd.pair_shard(n, r, w) for r in range(w)], [])) == list(range(n))
+    quats = util.scenes()["3D_superquadrics_cluttered_rabbit"]["quats"][:12]
+    pairs = hd.nearest_earlier_layers(quats)
+    assert [c for _, c in pairs] == list(range(1, 12))
+    for near, cur in pairs:
+        assert near < cur
+        d = [tfe.angular_distance(quats[cur], quats[j]) for j in range(cur)]
+        assert near == int(np.argmin(d))  # (first minimum: the reference keeps the earlier layer on ties)
+    # two layers, 2 x 3 lines
+    off = np.array([0, 1, 1, 3, 3, 3, 4, 4, 6, 6, 6, 6, 7])
+    xM = np.arange(7, dtype=np.float64)
+    xyz, first = hd.layer_vertices((off, xM, xM, xM), [0.0, 1.0, 0.0, 2.0, -1.0, 1.0], 2, 3, 2)
+    assert first.tolist() == [0, 4, 7]
+    assert xyz[:, 2].tolist() == xM.tolist()
+    assert xyz[:4, :2].tolist() == [[0.0, 0.0], [0.0, 2.0], [0.0, 2.0], [1.0, 2.0]]  # lines 0, 2, 2, 5 of layer 0
+    assert xyz[4:, :2].tolist() == [[0.0, 1.0], [0.0, 1.0], [1.0, 2.0]]              # lines 1, 1, 5 of layer 1

@@ -81,3 +81,71 @@ def test_allgather_layers_equals_single_gpu_build(K):
     world = min(torch.cuda.device_count(), 4)
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     mp.spawn(_worker, args=(world, _free_port(), K), nprocs=world, join=True)
+
+
+def _bridge_worker(rank, world, port, K, n_gpus):
+    """Layers sharded by orientation, segments exchanged, bridge pairs re-sharded by pair index: the matches of
+    all pairs assembled from the ranks must equal the matches one context computes for all pairs."""
+    import torch
+    import torch.distributed as dist
+
+    from hrm_b200 import capi
+    from hrm_b200 import dist as hdist
+    from tests import util
+
+    dev = rank if n_gpus >= world else 0  # (a 1-GPU box: both ranks share the device, the segments go through the host)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    sc = util.scenes()["3D_superquadrics_cluttered_rabbit"]
+    rows = sc["arena"] + sc["obstacle"]
+    quats = sc["quats"][:K]
+    semi, R, off, _ = util.body_poses3d(sc["robot"], quats)
+    rb = util.robot3d(sc["robot"])
+    body_semi = [rb.base.semiAxis] + [l.semiAxis for l in rb.link]
+    Lx, Ly, num_point = 10, 6, 5
+    ctx = capi.Context(dev)
+    try:
+        ctx.set_scene3d(1, len(sc["obstacle"]), util.sq17(rows, 10), 10)
+        ctx.set_sweep(sc["lim"], Lx, Ly)
+        k0, k1 = hdist.shard_range(K, rank, world)
+        ctx.build_layers(semi, R[k0:k1], off[k0:k1], capi.F64_STRICT)
+        if n_gpus >= world:
+            hdist.init_exchange(ctx, dist)
+            ctx.allgather_layers(((K + world - 1) // world) * Lx * Ly, 1 << 16)
+            csr = hdist.gathered_csr(ctx)
+        else:
+            shards = [None] * world
+            dist.all_gather_object(shards, tuple(ctx.segments_all()))
+            csr = hdist.merge_shards(shards)
+        pairs, got = hdist.bridge_matches_sharded(ctx, dist, csr, K, body_semi, rb.tf, quats, sc["lim"], Lx, Ly, num_point, capi.F64_STRICT)
+        assert len(pairs) == K - 1 and all(m is not None for m in got)
+        # one context, all layers, all pairs
+        ctx.build_layers(semi, R, off, capi.F64_STRICT)
+        single = ctx.segments_all()
+        for a, b in zip(csr, single):
+            assert np.array_equal(a, b)
+        xyz, first = hdist.layer_vertices(single, sc["lim"], Lx, Ly, K)
+        want = hdist.bridge_matches(ctx, xyz, first, pairs, body_semi, rb.tf, quats, sc["lim"], Lx, Ly, num_point, capi.F64_STRICT)
+        for p in range(len(pairs)):
+            assert np.array_equal(got[p], want[p]), pairs[p]
+        linked = sum(int((m >= 0).sum()) for m in want)
+        assert linked > 20 and any((m < 0).any() for m in want)
+        for (near, cur), m in zip(pairs, want):  # matches point into the `cur` layer of their pair
+            assert ((m < 0) | ((m >= first[cur]) & (m < first[cur + 1]))).all()
+    finally:
+        ctx.close()
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("K", [9])
+def test_bridge_pairs_sharded_by_pair_index(K):
+    """Runs on any box: with >= 2 GPUs one rank per GPU and hrmgpu_allgather_layers over NCCL, with one GPU two ranks on the same
+    device and the segments exchanged through the host."""
+    import torch
+    import torch.multiprocessing as mp
+
+    n_gpus = torch.cuda.device_count()
+    world = 2
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    mp.spawn(_bridge_worker, args=(world, _free_port(), K, n_gpus), nprocs=world, join=True)
