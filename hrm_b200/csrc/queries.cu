@@ -178,8 +178,9 @@ struct QueryParams {
 // directions -- which is the common case, the candidate segments of connectOneSlice run between neighbouring sweep lines);
 // the surviving items are then walked by the whole warp one after the other (faces in order, first two hits).
 template <class A, class Real, bool HASN>
-// (6 blocks per SM: 80 registers instead of 107; measured 7-13 % faster on the bundled maps, the same bound slows k_transitions3d down)
-__global__ void __launch_bounds__(128, 6) k_edges3d(const QueryParams p) {
+// (8 blocks per SM, 64 registers with 56 bytes of spills: 440 / 1407 us on the cluttered / maze map against 541 / 1754 at 4 blocks (124
+// registers, no spills), 483 / 1548 at 6, 453 / 1441 at 10 and 656 / 2041 at 12 -- the kernel wants warps more than registers)
+__global__ void __launch_bounds__(128, 8) k_edges3d(const QueryParams p) {
     const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const long long item = warp_global * 32 + lane;
